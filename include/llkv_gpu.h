@@ -1,0 +1,336 @@
+/*
+ * llkv_gpu.h — C ABI of the B200-native scan -> filter -> MVCC -> aggregate path for LLKV.
+ *
+ * This header is the drop-in boundary.  Every entry point is
+ * `extern "C"`, takes plain pointers and sizes, and replaces one reference
+ * interface, cited as `crate/path.rs:line` relative to jzombie/rust-llkv
+ * v0.8.5-alpha.  A Rust `-sys` crate binds these 1:1 (see INTEGRATION.md and
+ * ffi/llkv-gpu-sys/src/lib.rs); the same symbols are driven from C++
+ * (`rust-llkv_b200/host/llkv_gpu.hpp`) and from Python ctypes in the tests.
+ *
+ * Conventions
+ *   - Every call returns an `int32_t` status.  0 is success; non-zero values
+ *     follow the variant order of `llkv_result::Error`
+ *     (llkv-result/src/error.rs:31-176).  The message for the last failing
+ *     call on the calling thread is read with `llkv_gpu_last_error`.
+ *   - The caller owns every host buffer; the library owns all device memory
+ *     behind opaque handles.  Handles may move between threads, but calls on
+ *     one handle must be serialised by the caller (mirrors `&mut self`).
+ *   - There is no CPU fallback.  Without a usable CUDA device
+ *     `llkv_gpu_ctx_create` fails with LLKV_ERR_IO and nothing else works.
+ */
+#ifndef LLKV_GPU_H
+#define LLKV_GPU_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LLKV_GPU_ABI_VERSION 1
+
+/* ---- status codes: llkv_result::Error variant order (llkv-result/src/error.rs:31-176) ---- */
+enum {
+  LLKV_OK = 0,
+  LLKV_ERR_IO = 1,               /* Error::Io — also "no CUDA device / CUDA runtime failure" */
+  LLKV_ERR_ARROW = 2,            /* Error::Arrow — arithmetic overflow raised by arrow-arith kernels */
+  LLKV_ERR_INVALID_ARGUMENT = 3, /* Error::InvalidArgumentError — e.g. "integer overflow" from SumInt64 */
+  LLKV_ERR_NOT_FOUND = 4,        /* Error::NotFound */
+  LLKV_ERR_CATALOG = 5,
+  LLKV_ERR_CONSTRAINT = 6,
+  LLKV_ERR_TRANSACTION = 7,
+  LLKV_ERR_INTERNAL = 8,         /* Error::Internal */
+  LLKV_ERR_EXPR_CAST = 9,        /* Error::ExprCast */
+  LLKV_ERR_PREDICATE_BUILD = 10, /* Error::PredicateBuild — literal cast / unsupported operator */
+  LLKV_ERR_RESERVED_TABLE_ID = 11
+};
+
+/* ---- column element types: on-disk PrimType codes (llkv-column-map/src/serialization.rs:146-166) ---- */
+enum {
+  LLKV_PT_NULL = 0, /* DataType::Null (only as an expression type) */
+  LLKV_PT_UINT64 = 1,
+  LLKV_PT_INT32 = 2,
+  LLKV_PT_UINT32 = 3,
+  LLKV_PT_FLOAT32 = 4,
+  LLKV_PT_INT64 = 6,
+  LLKV_PT_INT16 = 7,
+  LLKV_PT_INT8 = 8,
+  LLKV_PT_UINT16 = 9,
+  LLKV_PT_UINT8 = 10,
+  LLKV_PT_FLOAT64 = 11,
+  LLKV_PT_UTF8 = 12,     /* short strings only (<= 7 bytes), used as GROUP BY keys / equality predicates */
+  LLKV_PT_BOOLEAN = 15,  /* one byte per value at this boundary (0/1) */
+  LLKV_PT_DATE32 = 16,
+  LLKV_PT_DATE64 = 17,
+  LLKV_PT_DECIMAL128 = 18
+};
+
+/* ---- llkv_types::Literal (llkv-types/src/literal.rs:26-41), variant order ---- */
+enum {
+  LLKV_LIT_NULL = 0,
+  LLKV_LIT_INT128 = 1,     /* lo/hi = two's complement i128 */
+  LLKV_LIT_FLOAT64 = 2,    /* lo = IEEE-754 bits */
+  LLKV_LIT_DECIMAL128 = 3, /* lo/hi = raw i128, scale = DecimalValue::scale */
+  LLKV_LIT_STRING = 4,     /* precision = byte length (<= 15), bytes little-endian in lo/hi */
+  LLKV_LIT_BOOLEAN = 5,    /* lo = 0/1 */
+  LLKV_LIT_DATE32 = 6      /* lo = sign-extended days since epoch */
+};
+
+typedef struct llkv_literal {
+  int32_t kind;
+  uint8_t precision; /* Decimal128: informational; String: length */
+  int8_t scale;
+  uint8_t _pad[2];
+  uint64_t lo;
+  uint64_t hi;
+} llkv_literal;
+
+/* ---- llkv_expr::ScalarExpr (llkv-expr/src/expr.rs:127-182), flattened, children before parents ---- */
+enum {
+  LLKV_SE_COLUMN = 0,
+  LLKV_SE_LITERAL = 1,
+  LLKV_SE_BINARY = 2,
+  LLKV_SE_NOT = 3,
+  LLKV_SE_IS_NULL = 4,
+  LLKV_SE_CAST = 7,
+  LLKV_SE_COMPARE = 8,
+  LLKV_SE_COALESCE = 9
+};
+/* llkv_expr::BinaryOp (expr.rs:311-321) */
+enum { LLKV_BIN_ADD = 0, LLKV_BIN_SUB = 1, LLKV_BIN_MUL = 2, LLKV_BIN_DIV = 3, LLKV_BIN_MOD = 4,
+       LLKV_BIN_AND = 5, LLKV_BIN_OR = 6, LLKV_BIN_SHL = 7, LLKV_BIN_SHR = 8 };
+/* llkv_expr::CompareOp (expr.rs:342-349) */
+enum { LLKV_CMP_EQ = 0, LLKV_CMP_NE = 1, LLKV_CMP_LT = 2, LLKV_CMP_LE = 3, LLKV_CMP_GT = 4, LLKV_CMP_GE = 5 };
+
+typedef struct llkv_scalar_node {
+  int32_t tag;       /* LLKV_SE_* */
+  int32_t op;        /* BINARY: LLKV_BIN_*; COMPARE: LLKV_CMP_*; IS_NULL: negated flag */
+  int32_t left;      /* child node index or -1 */
+  int32_t right;     /* child node index or -1 */
+  uint64_t field_id; /* COLUMN: LogicalFieldId as u64 (llkv-types/src/ids.rs:133-152) */
+  llkv_literal literal;
+  int32_t cast_type; /* CAST: LLKV_PT_* */
+  uint8_t cast_precision;
+  int8_t cast_scale;
+  uint8_t _pad[2];
+} llkv_scalar_node;
+
+/* ---- llkv_compute::program::EvalOp (llkv-compute/src/program.rs:48-78), postfix ---- */
+enum {
+  LLKV_EV_PUSH_PREDICATE = 0,
+  LLKV_EV_PUSH_COMPARE = 1,
+  LLKV_EV_PUSH_IN_LIST = 2,
+  LLKV_EV_PUSH_IS_NULL = 3,
+  LLKV_EV_PUSH_LITERAL = 4,
+  LLKV_EV_FUSED_AND = 5, /* followed by child_count LLKV_EV_FILTER_ITEM entries */
+  LLKV_EV_AND = 6,
+  LLKV_EV_OR = 7,
+  LLKV_EV_NOT = 8,
+  LLKV_EV_FILTER_ITEM = 100
+};
+/* OwnedOperator (program.rs:87-112) */
+enum {
+  LLKV_OP_EQUALS = 0,
+  LLKV_OP_RANGE = 1,
+  LLKV_OP_GT = 2,
+  LLKV_OP_GTE = 3,
+  LLKV_OP_LT = 4,
+  LLKV_OP_LTE = 5,
+  LLKV_OP_IN = 6,
+  LLKV_OP_STARTS_WITH = 7, /* not supported on this path: LLKV_ERR_PREDICATE_BUILD */
+  LLKV_OP_ENDS_WITH = 8,
+  LLKV_OP_CONTAINS = 9,
+  LLKV_OP_IS_NULL = 10,
+  LLKV_OP_IS_NOT_NULL = 11
+};
+/* std::ops::Bound */
+enum { LLKV_BOUND_INCLUDED = 0, LLKV_BOUND_EXCLUDED = 1, LLKV_BOUND_UNBOUNDED = 2 };
+
+typedef struct llkv_eval_op {
+  int32_t tag;          /* LLKV_EV_* */
+  int32_t operator_tag; /* PUSH_PREDICATE / FILTER_ITEM: LLKV_OP_* */
+  uint64_t field_id;    /* PUSH_PREDICATE / FUSED_AND / FILTER_ITEM */
+  int32_t lower_kind;   /* RANGE: LLKV_BOUND_* */
+  int32_t upper_kind;
+  int32_t lit_begin;    /* first literal in literals[]; RANGE: lower (if bounded) then upper (if bounded); IN: the list */
+  int32_t lit_count;
+  int32_t expr_left;    /* PUSH_COMPARE: lhs root; PUSH_IN_LIST / PUSH_IS_NULL: operand root (index into nodes[]) */
+  int32_t expr_right;   /* PUSH_COMPARE: rhs root; PUSH_IN_LIST: first entry in list_roots[] */
+  int32_t cmp_op;       /* PUSH_COMPARE: LLKV_CMP_* */
+  int32_t negated;      /* PUSH_IN_LIST / PUSH_IS_NULL */
+  int32_t child_count;  /* AND / OR / FUSED_AND; PUSH_IN_LIST: list length */
+  int32_t literal_bool; /* PUSH_LITERAL */
+} llkv_eval_op;
+
+/* ---- llkv_aggregate::AggregateKind (llkv-aggregate/src/lib.rs:32-69) ---- */
+enum {
+  LLKV_AGG_COUNT = 0,       /* expr_root < 0 => COUNT(*) (CountStar), else CountColumn */
+  LLKV_AGG_SUM = 1,
+  LLKV_AGG_TOTAL = 2,
+  LLKV_AGG_AVG = 3,
+  LLKV_AGG_MIN = 4,
+  LLKV_AGG_MAX = 5,
+  LLKV_AGG_COUNT_NULLS = 6
+};
+
+typedef struct llkv_agg_spec {
+  int32_t kind;      /* LLKV_AGG_* */
+  int32_t expr_root; /* argument expression root in nodes[], -1 for COUNT(*) */
+  int32_t data_type; /* AggregateKind::*.data_type as LLKV_PT_* — selects the accumulator (lib.rs:463-748) */
+  uint8_t precision;
+  int8_t scale;
+  uint8_t distinct;  /* must be 0 on this path */
+  uint8_t _pad;
+} llkv_agg_spec;
+
+/* How scalar expressions that feed aggregates are typed and rounded (SURVEY.md §8a notes D1/D2). */
+enum {
+  LLKV_EXPR_ARROW = 0, /* ungrouped path: arrow-arith kernels + cast to the inferred type
+                          (llkv-compute/src/eval.rs:565-614, kernels.rs:99-177) */
+  LLKV_EXPR_EXACT = 1  /* GROUP BY path: exact DecimalValue ops per row
+                          (llkv-executor/src/lib.rs:7229-7332, llkv-compute/src/scalar/decimal.rs:128-170) */
+};
+
+/* One finalized aggregate cell: what AggregateAccumulator::finalize puts in its 1-row array (lib.rs:1488-1939). */
+typedef struct llkv_agg_value {
+  uint64_t lo;       /* Int64 / f64 bits / low half of i128 */
+  uint64_t hi;       /* high half of i128 (Decimal128) */
+  int32_t type;      /* LLKV_PT_INT64 / LLKV_PT_FLOAT64 / LLKV_PT_DECIMAL128 / ... */
+  uint8_t precision;
+  int8_t scale;
+  uint8_t valid;     /* 0 => NULL */
+  uint8_t _pad;
+} llkv_agg_value;
+
+/* One GROUP BY key cell (llkv-executor/src/lib.rs:99-106 GroupKeyValue). */
+typedef struct llkv_group_key {
+  uint64_t bits;  /* Int: i64; Bool: 0/1; String: bytes big-endian from the top byte, length in the low byte */
+  int32_t type;   /* LLKV_PT_* of the key column */
+  uint8_t valid;  /* 0 => NULL key (its own group) */
+  uint8_t _pad[3];
+} llkv_group_key;
+
+/* Facts about the most recent llkv_gpu_agg_run / llkv_gpu_filter_bitmap on a handle (for bench.py and ncu notes). */
+typedef struct llkv_run_info {
+  uint64_t rows;                /* rows scanned */
+  uint32_t kernel_launches;     /* CUDA kernels launched by the call */
+  uint32_t used_wide_path;      /* 1 when the 128-bit interpreter ran (narrow path overflowed or not applicable) */
+  uint32_t algorithmic_bytes_per_row; /* sum of Arrow value widths of the columns read */
+  uint32_t physical_bytes_per_row;    /* bytes per row the kernels read from HBM */
+  uint32_t grid, block, rows_per_tile, stages, smem_bytes;
+  uint32_t fast_groups;         /* CTA-local group slots with per-thread accumulators */
+  float last_kernel_ms;         /* device time of the scan kernel (CUDA events) when timing is enabled, else 0 */
+} llkv_run_info;
+
+typedef struct llkv_gpu_ctx llkv_gpu_ctx;
+typedef struct llkv_gpu_column llkv_gpu_column;
+typedef struct llkv_gpu_program llkv_gpu_program;
+typedef struct llkv_gpu_agg llkv_gpu_agg;
+
+/* ---- library / context ---- */
+int32_t llkv_gpu_abi_version(void);
+/* Copies the calling thread's last error message (NUL terminated) and returns its full length. */
+size_t llkv_gpu_last_error(char* buf, size_t cap);
+/* Number of CUDA devices, or 0.  Never fails. */
+int32_t llkv_gpu_device_count(void);
+
+/* One context per GPU.  `n_streams` copy streams feed the pinned staging ring of `pinned_bytes`
+ * bytes that stands where `Pager::batch_get` hands out blobs (llkv-storage/src/pager/mod.rs:89-104). */
+int32_t llkv_gpu_ctx_create(int32_t device_ordinal, int32_t n_streams, uint64_t pinned_bytes, llkv_gpu_ctx** out);
+void llkv_gpu_ctx_destroy(llkv_gpu_ctx* ctx);
+int32_t llkv_gpu_ctx_synchronize(llkv_gpu_ctx* ctx);
+/* The cudaStream_t the scan kernels are launched on (for CUDA-event timing by the caller). */
+int32_t llkv_gpu_ctx_stream(llkv_gpu_ctx* ctx, void** out_stream);
+/* Turns per-run CUDA-event timing of the scan kernel on/off (llkv_run_info.last_kernel_ms). */
+int32_t llkv_gpu_ctx_set_timing(llkv_gpu_ctx* ctx, int32_t enabled);
+/* Tuning knobs: 0 keeps the default.  rows_per_thread in {1,2,4}. */
+int32_t llkv_gpu_ctx_set_tuning(llkv_gpu_ctx* ctx, int32_t ctas_per_sm, int32_t block_threads, int32_t stages,
+                                int32_t rows_per_thread, int32_t force_wide);
+
+/* Page-locked host memory so chunk uploads DMA straight from the caller's buffer. */
+int32_t llkv_gpu_host_alloc(uint64_t bytes, void** out);
+int32_t llkv_gpu_host_free(void* p);
+
+/* ---- columns: ColumnStore::append / scan source (llkv-column-map/src/store/core.rs:787, scan/mod.rs:191) ---- */
+int32_t llkv_gpu_column_register(llkv_gpu_ctx* ctx, uint64_t logical_field_id, int32_t prim_type, uint8_t precision,
+                                 int8_t scale, llkv_gpu_column** out);
+/* Optional capacity hint (rows). */
+int32_t llkv_gpu_column_reserve(llkv_gpu_column* col, uint64_t n_rows);
+/* Appends one chunk.  `values` is the Arrow values buffer (pager blob + 24, serialization.rs:41-53).
+ * `validity` is an optional Arrow validity bitmap (LSB first) for the chunk; NULL = all valid (the
+ * reference's chunk format stores no nulls, serialization.rs:265-269).  `row_ids` is the chunk's
+ * row-id shadow column or NULL for the dense run starting at `row_id_base`.  Row ids must continue the
+ * column densely (SURVEY.md §7 hard part (a)); anything else is LLKV_ERR_INVALID_ARGUMENT for now.
+ * For LLKV_PT_UTF8 `values` is the i32 offsets buffer (n_rows+1) and `aux` the data bytes. */
+int32_t llkv_gpu_column_append_chunk(llkv_gpu_column* col, uint64_t chunk_pk, const void* values, uint64_t n_rows,
+                                     const uint8_t* validity, const uint64_t* row_ids, uint64_t row_id_base,
+                                     const void* aux);
+/* Appends a serialized chunk blob exactly as the pager stores it ("ARR0" header, serialization.rs:41-53,264-307). */
+int32_t llkv_gpu_column_append_blob(llkv_gpu_column* col, uint64_t chunk_pk, const void* blob, uint64_t blob_len,
+                                    const uint64_t* row_ids, uint64_t row_id_base);
+/* Waits for outstanding uploads of this column; after this the column is scannable. */
+int32_t llkv_gpu_column_seal(llkv_gpu_column* col);
+int32_t llkv_gpu_column_rows(const llkv_gpu_column* col, uint64_t* out_rows);
+/* Drops the rows but keeps the device allocation (re-upload the next batch into the same buffer). */
+int32_t llkv_gpu_column_clear(llkv_gpu_column* col);
+int32_t llkv_gpu_column_destroy(llkv_gpu_column* col);
+
+/* ---- predicates: ProgramCompiler::compile (llkv-compute/src/program.rs:271-298) ---- */
+int32_t llkv_gpu_program_compile(llkv_gpu_ctx* ctx, const llkv_eval_op* ops, int32_t n_ops,
+                                 const llkv_literal* literals, int32_t n_literals, const llkv_scalar_node* nodes,
+                                 int32_t n_nodes, const int32_t* list_roots, int32_t n_list_roots,
+                                 llkv_gpu_program** out);
+void llkv_gpu_program_destroy(llkv_gpu_program* prog);
+
+/* ---- MVCC: MvccRowIdFilter (llkv-transaction/src/helpers.rs:259-312), RowVersion::is_visible_for
+ *      (llkv-transaction/src/mvcc.rs:282-334).  `noncommitted` lists every txn id whose
+ *      TxnIdManager::status is Active or Aborted (mvcc.rs:157-171); unknown ids are Committed. ---- */
+int32_t llkv_gpu_mvcc_set(llkv_gpu_ctx* ctx, uint64_t table_id, llkv_gpu_column* created_by,
+                          llkv_gpu_column* deleted_by, uint64_t txn_id, uint64_t snapshot_id,
+                          const uint64_t* noncommitted, int32_t n_noncommitted);
+int32_t llkv_gpu_mvcc_clear(llkv_gpu_ctx* ctx, uint64_t table_id);
+
+/* ---- selection bitmap over row positions (B2: ScanStorage::filter_leaf / RowIdFilter::filter,
+ *      llkv-scan/src/lib.rs:163-229).  Bit i of out_words is row (row_begin + i).  `prog` NULL = all rows. ---- */
+int32_t llkv_gpu_filter_bitmap(llkv_gpu_ctx* ctx, uint64_t table_id, const llkv_gpu_program* prog, int32_t apply_mvcc,
+                               uint64_t row_begin, uint64_t row_end, uint64_t* out_words, uint64_t n_words,
+                               uint64_t* out_count);
+
+/* ---- aggregates: AggregateAccumulator::{new_with_projection_index,update,finalize}
+ *      (llkv-aggregate/src/lib.rs:463,759,1488) fused with the scan that feeds them
+ *      (llkv-executor/src/lib.rs:5357-5682 ungrouped, 4405-4542 + 5028-5355 GROUP BY). ---- */
+int32_t llkv_gpu_agg_create(llkv_gpu_ctx* ctx, uint64_t table_id, const llkv_agg_spec* specs, int32_t n_aggs,
+                            const llkv_scalar_node* nodes, int32_t n_nodes, const uint64_t* group_key_fields,
+                            int32_t n_keys, int32_t expr_mode, uint64_t cardinality_hint, llkv_gpu_agg** out);
+/* Resets all accumulators / group tables (a fresh set of AggregateStates). */
+int32_t llkv_gpu_agg_reset(llkv_gpu_agg* agg);
+/* update(): scans rows [row_begin,row_end) of the table's columns, applies `prog` (NULL = no filter) and,
+ * if apply_mvcc, the snapshot set by llkv_gpu_mvcc_set, and folds the survivors into the accumulators.
+ * Asynchronous on the context stream. */
+int32_t llkv_gpu_agg_run(llkv_gpu_agg* agg, const llkv_gpu_program* prog, int32_t apply_mvcc, uint64_t row_begin,
+                         uint64_t row_end);
+/* Merges the partial states of all ranks of the communicator bound to the context. */
+int32_t llkv_gpu_agg_merge(llkv_gpu_agg* agg);
+/* Number of groups currently held (1 for ungrouped). Synchronises. */
+int32_t llkv_gpu_agg_group_count(llkv_gpu_agg* agg, uint64_t* out_groups);
+/* finalize(): writes n_groups*n_aggs values (group-major) and n_groups*n_keys keys, groups in first-appearance
+ * order when the aggregate tracks it (low cardinality), otherwise ascending key order.  Errors the reference
+ * raises during update (integer overflow, Decimal128 sum overflow, arrow arithmetic overflow) surface here. */
+int32_t llkv_gpu_agg_finalize(llkv_gpu_agg* agg, llkv_agg_value* out_values, llkv_group_key* out_keys,
+                              uint64_t group_capacity, uint64_t* out_groups);
+int32_t llkv_gpu_agg_run_info(const llkv_gpu_agg* agg, llkv_run_info* out);
+void llkv_gpu_agg_destroy(llkv_gpu_agg* agg);
+
+/* ---- multi-GPU: one context per rank, NCCL over NVLink ---- */
+#define LLKV_GPU_UNIQUE_ID_BYTES 128
+int32_t llkv_gpu_comm_unique_id(uint8_t out_id[LLKV_GPU_UNIQUE_ID_BYTES]);
+int32_t llkv_gpu_comm_init(llkv_gpu_ctx* ctx, const uint8_t id[LLKV_GPU_UNIQUE_ID_BYTES], int32_t n_ranks,
+                           int32_t rank);
+int32_t llkv_gpu_comm_destroy(llkv_gpu_ctx* ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LLKV_GPU_H */
