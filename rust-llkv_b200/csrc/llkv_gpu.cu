@@ -1,0 +1,1719 @@
+// llkv_gpu.cu — the C ABI of include/llkv_gpu.h: contexts, device-resident columns (pinned staging ring ->
+// cudaMemcpyAsync on copy streams), predicate programs, MVCC snapshots, the fused aggregate runs, finalize, and the
+// NCCL merge of partial aggregate states.  There is no CPU fallback anywhere in this file: without a CUDA device
+// llkv_gpu_ctx_create fails and every other entry point needs a context.
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <algorithm>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/llkv_gpu.h"
+#include "compiler.h"
+#include "plan.h"
+
+namespace llkv {
+typedef long long i64;
+typedef unsigned long long u64;
+typedef __int128 i128;
+typedef unsigned __int128 u128;
+cudaError_t launch_scan(const Plan* dplan, bool wide, int rows_per_thread, uint32_t grid, uint32_t block, uint32_t smem,
+                        cudaStream_t stream);
+cudaError_t launch_init_table(u64* keys, u64* words, u64 rows, uint32_t n_gwords, const uint8_t* word_class_dev, cudaStream_t stream);
+cudaError_t launch_merge_table(const Plan* dplan, const u64* src_keys, const u64* src_words, u64 src_cap, cudaStream_t stream);
+}  // namespace llkv
+
+using namespace llkv;
+
+// ------------------------------------------------------------------------------------------------ errors
+static thread_local std::string g_last_error;
+
+static int32_t set_error(int32_t code, const char* fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  g_last_error = buf;
+  return code;
+}
+#define CUDA_TRY(expr)                                                                                          \
+  do {                                                                                                          \
+    cudaError_t _e = (expr);                                                                                    \
+    if (_e != cudaSuccess) return set_error(LLKV_ERR_IO, "CUDA error %s at %s:%d (%s)", cudaGetErrorString(_e), \
+                                            __FILE__, __LINE__, #expr);                                         \
+  } while (0)
+
+// ------------------------------------------------------------------------------------------------ column kernels
+struct DevStats {
+  u64 min_enc, max_enc;  // order-preserving u64 image of the column's values (sign bit flipped for signed types)
+  unsigned int not_i64;  // Decimal128: some value is not a sign-extended i64
+  unsigned int max_strlen, min_strlen, bad_string;
+  u64 data_bytes;        // Utf8: total data bytes
+};
+
+template <typename T, bool SIGNED>
+__global__ void stats_kernel(const T* __restrict__ v, u64 n, DevStats* st) {
+  u64 mn = ~0ull, mx = 0ull;
+  for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (u64)gridDim.x * blockDim.x) {
+    u64 e = SIGNED ? ((u64)(i64)v[i] ^ 0x8000000000000000ull) : (u64)v[i];
+    mn = e < mn ? e : mn;
+    mx = e > mx ? e : mx;
+  }
+  for (int o = 16; o; o >>= 1) {
+    const u64 a = __shfl_xor_sync(0xffffffffu, mn, o), b = __shfl_xor_sync(0xffffffffu, mx, o);
+    mn = a < mn ? a : mn;
+    mx = b > mx ? b : mx;
+  }
+  if ((threadIdx.x & 31) == 0 && mn <= mx) {
+    atomicMin(&st->min_enc, mn);
+    atomicMax(&st->max_enc, mx);
+  }
+}
+__global__ void stats_dec_kernel(const ulonglong2* __restrict__ v, u64 n, DevStats* st) {
+  u64 mn = ~0ull, mx = 0ull;
+  unsigned int bad = 0;
+  for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (u64)gridDim.x * blockDim.x) {
+    const ulonglong2 w = v[i];
+    if ((i64)w.y != ((i64)w.x >> 63)) bad = 1;
+    const u64 e = w.x ^ 0x8000000000000000ull;
+    mn = e < mn ? e : mn;
+    mx = e > mx ? e : mx;
+  }
+  for (int o = 16; o; o >>= 1) {
+    const u64 a = __shfl_xor_sync(0xffffffffu, mn, o), b = __shfl_xor_sync(0xffffffffu, mx, o);
+    mn = a < mn ? a : mn;
+    mx = b > mx ? b : mx;
+    bad |= __shfl_xor_sync(0xffffffffu, bad, o);
+  }
+  if ((threadIdx.x & 31) == 0) {
+    if (mn <= mx) {
+      atomicMin(&st->min_enc, mn);
+      atomicMax(&st->max_enc, mx);
+    }
+    if (bad) atomicOr(&st->not_i64, 1u);
+  }
+}
+// Utf8 (offsets + data) -> packed short-string keys: bytes big-endian from the top byte, length in the low byte
+__global__ void pack_utf8_kernel(const int* __restrict__ off, const unsigned char* __restrict__ data, u64 n, u64* __restrict__ out,
+                                 DevStats* st) {
+  unsigned int mx = 0, mn = 0xffffffffu, bad = 0;
+  for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (u64)gridDim.x * blockDim.x) {
+    const int b = off[i], e = off[i + 1];
+    const unsigned int len = (unsigned int)(e - b);
+    u64 k = 0;
+    if (len > 7) bad = 1;
+    else {
+      for (unsigned int j = 0; j < len; ++j) k |= (u64)data[b + j] << (56 - 8 * j);
+      k |= len;
+    }
+    out[i] = k;
+    mx = len > mx ? len : mx;
+    mn = len < mn ? len : mn;
+  }
+  if (mx || mn != 0xffffffffu) {
+    atomicMax(&st->max_strlen, mx);
+    atomicMin(&st->min_strlen, mn);
+  }
+  if (bad) atomicOr(&st->bad_string, 1u);
+}
+__global__ void narrow_str_kernel(const u64* __restrict__ in, unsigned char* __restrict__ out, u64 n) {
+  for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (u64)gridDim.x * blockDim.x) out[i] = (unsigned char)(in[i] >> 56);
+}
+__global__ void widen_str_kernel(const unsigned char* __restrict__ in, u64* __restrict__ out, u64 n) {
+  for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (u64)gridDim.x * blockDim.x) out[i] = ((u64)in[i] << 56) | 1ull;
+}
+// validity bitmaps: OR `n` source bits into dst starting at bit `dst_off`
+__global__ void or_bits_kernel(unsigned int* __restrict__ dst, u64 dst_off, const unsigned char* __restrict__ src, u64 n) {
+  const u64 nw = (n + 31) / 32;
+  for (u64 w = (u64)blockIdx.x * blockDim.x + threadIdx.x; w < nw; w += (u64)gridDim.x * blockDim.x) {
+    unsigned int bits = 0;
+    for (int b = 0; b < 4; ++b) {
+      const u64 byte = w * 4 + b;
+      if (byte * 8 < n) bits |= (unsigned int)src[byte] << (8 * b);
+    }
+    const u64 rem = n - w * 32;
+    if (rem < 32) bits &= (1u << rem) - 1u;
+    if (!bits) continue;
+    const u64 pos = dst_off + w * 32;
+    const unsigned int sh = (unsigned int)(pos & 31);
+    atomicOr(&dst[pos >> 5], bits << sh);
+    if (sh && (bits >> (32 - sh))) atomicOr(&dst[(pos >> 5) + 1], bits >> (32 - sh));
+  }
+}
+__global__ void fill_bits_kernel(unsigned int* __restrict__ dst, u64 bit_begin, u64 bit_end) {
+  if (bit_end <= bit_begin) return;
+  const u64 w0 = bit_begin >> 5, w1 = (bit_end - 1) >> 5;
+  for (u64 w = w0 + (u64)blockIdx.x * blockDim.x + threadIdx.x; w <= w1; w += (u64)gridDim.x * blockDim.x) {
+    unsigned int m = 0xffffffffu;
+    if (w == w0) m &= 0xffffffffu << (bit_begin & 31);
+    if (w == w1 && (bit_end & 31)) m &= (1u << (bit_end & 31)) - 1u;
+    atomicOr(&dst[w], m);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ handles
+struct MvccState {
+  llkv_gpu_column* created_by = nullptr;
+  llkv_gpu_column* deleted_by = nullptr;
+  uint64_t txn_id = 0, snapshot_id = 0;
+  std::vector<uint64_t> noncommitted;
+};
+
+struct NcclIdByValue {  // ncclUniqueId
+  char internal[128];
+};
+typedef int (*nccl_get_unique_id_fn)(void*);
+typedef int (*nccl_comm_init_rank_fn)(void**, int, NcclIdByValue, int);
+typedef int (*nccl_all_gather_fn)(const void*, void*, size_t, int, void*, cudaStream_t);
+typedef int (*nccl_all_reduce_fn)(const void*, void*, size_t, int, int, void*, cudaStream_t);
+typedef int (*nccl_comm_destroy_fn)(void*);
+typedef const char* (*nccl_get_error_string_fn)(int);
+
+struct NcclApi {
+  void* lib = nullptr;
+  nccl_get_unique_id_fn get_unique_id = nullptr;
+  nccl_comm_init_rank_fn comm_init_rank = nullptr;
+  nccl_all_gather_fn all_gather = nullptr;
+  nccl_all_reduce_fn all_reduce = nullptr;
+  nccl_comm_destroy_fn comm_destroy = nullptr;
+  nccl_get_error_string_fn get_error_string = nullptr;
+};
+static NcclApi g_nccl;
+
+static int32_t load_nccl() {
+  if (g_nccl.lib) return LLKV_OK;
+  // prefer a libnccl already mapped into the process (torch's bundled copy), then the system one
+  void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD | RTLD_GLOBAL);
+  if (!h) h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+  if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+  if (!h) return set_error(LLKV_ERR_IO, "NCCL is not available: %s", dlerror());
+  g_nccl.get_unique_id = (nccl_get_unique_id_fn)dlsym(h, "ncclGetUniqueId");
+  g_nccl.comm_init_rank = (nccl_comm_init_rank_fn)dlsym(h, "ncclCommInitRank");
+  g_nccl.all_gather = (nccl_all_gather_fn)dlsym(h, "ncclAllGather");
+  g_nccl.all_reduce = (nccl_all_reduce_fn)dlsym(h, "ncclAllReduce");
+  g_nccl.comm_destroy = (nccl_comm_destroy_fn)dlsym(h, "ncclCommDestroy");
+  g_nccl.get_error_string = (nccl_get_error_string_fn)dlsym(h, "ncclGetErrorString");
+  if (!g_nccl.get_unique_id || !g_nccl.comm_init_rank || !g_nccl.all_gather || !g_nccl.all_reduce || !g_nccl.comm_destroy)
+    return set_error(LLKV_ERR_IO, "libnccl lacks the expected symbols");
+  g_nccl.lib = h;
+  return LLKV_OK;
+}
+#define NCCL_TRY(expr)                                                                                                   \
+  do {                                                                                                                   \
+    int _r = (expr);                                                                                                     \
+    if (_r != 0) return set_error(LLKV_ERR_IO, "NCCL error %d (%s) at %s:%d", _r,                                         \
+                                  g_nccl.get_error_string ? g_nccl.get_error_string(_r) : "?", __FILE__, __LINE__);        \
+  } while (0)
+
+struct llkv_gpu_ctx {
+  int device = 0;
+  int sm_count = 148;
+  int max_smem = 227 * 1024;
+  cudaStream_t stream = nullptr;
+  std::vector<cudaStream_t> copy_streams;
+  std::vector<cudaEvent_t> slot_events;
+  unsigned char* pinned = nullptr;
+  uint64_t slot_bytes = 0;
+  int next_slot = 0;
+  std::map<uint64_t, llkv_gpu_column*> columns;  // LogicalFieldId -> column
+  std::map<uint64_t, MvccState> mvcc;            // table id -> snapshot
+  bool timing = false;
+  int tune_ctas = 0, tune_block = 0, tune_stages = 0, tune_rpt = 0, tune_force_wide = 0;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  void* nccl_comm = nullptr;
+  int n_ranks = 1, rank = 0;
+};
+
+struct llkv_gpu_column {
+  llkv_gpu_ctx* ctx = nullptr;
+  uint64_t lfid = 0;
+  int32_t type = 0;
+  uint8_t precision = 0;
+  int8_t scale = 0;
+  void* values = nullptr;
+  unsigned int* validity = nullptr;
+  uint64_t cap_rows = 0;
+  uint64_t n_rows = 0;
+  uint32_t elem_bytes = 0;
+  uint8_t load_kind = 0;
+  DevStats* dstats = nullptr;
+  DevStats hstats;
+  bool sealed = false;
+  bool has_origin = false;
+  uint64_t row_id_origin = 0;
+  int stream_index = 0;
+  std::vector<void*> deferred_free;  // temp device buffers released at seal
+};
+
+struct llkv_gpu_program {
+  std::vector<llkv_eval_op> ops;
+  std::vector<llkv_literal> literals;
+  std::vector<llkv_scalar_node> nodes;
+  std::vector<int32_t> list_roots;
+  ProgramView view;
+  void bind() {
+    view.ops = ops.data();
+    view.n_ops = (int32_t)ops.size();
+    view.literals = literals.data();
+    view.n_literals = (int32_t)literals.size();
+    view.nodes = nodes.data();
+    view.n_nodes = (int32_t)nodes.size();
+    view.list_roots = list_roots.data();
+    view.n_list_roots = (int32_t)list_roots.size();
+  }
+};
+
+struct PendingRun {
+  bool active = false;
+  bool has_prog = false;
+  llkv_gpu_program prog;
+  int apply_mvcc = 0;
+  uint64_t row_begin = 0, row_end = 0;
+  bool wide = false;
+  bool has_backup = false;
+  bool timed = false;
+};
+
+struct llkv_gpu_agg {
+  llkv_gpu_ctx* ctx = nullptr;
+  uint64_t table_id = 0;
+  std::vector<llkv_agg_spec> specs;
+  std::vector<llkv_scalar_node> nodes;
+  std::vector<uint64_t> keys;
+  int32_t expr_mode = LLKV_EXPR_ARROW;
+  uint64_t hint = 0;
+  // accumulator state
+  bool frozen = false;
+  uint32_t n_gwords = 0;
+  std::vector<uint8_t> gclass;
+  uint8_t* d_gclass = nullptr;
+  u64 gcap = 0;
+  u64* gkeys = nullptr;
+  u64* gwords = nullptr;
+  u64* bk_keys = nullptr;
+  u64* bk_words = nullptr;
+  u64 bk_cap = 0;
+  uint32_t* d_flags = nullptr;
+  uint32_t* h_flags = nullptr;  // pinned
+  Plan* d_plan = nullptr;
+  Plan* h_plan = nullptr;  // pinned
+  CompileResult cr;
+  PendingRun pending;
+  int32_t err_code = 0;
+  std::string err_msg;
+  llkv_run_info info;
+};
+
+// ------------------------------------------------------------------------------------------------ library / context
+extern "C" int32_t llkv_gpu_abi_version(void) { return LLKV_GPU_ABI_VERSION; }
+
+extern "C" size_t llkv_gpu_last_error(char* buf, size_t cap) {
+  if (buf && cap) {
+    const size_t n = g_last_error.size() < cap - 1 ? g_last_error.size() : cap - 1;
+    memcpy(buf, g_last_error.data(), n);
+    buf[n] = 0;
+  }
+  return g_last_error.size();
+}
+
+extern "C" int32_t llkv_gpu_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  return n;
+}
+
+extern "C" int32_t llkv_gpu_ctx_create(int32_t device_ordinal, int32_t n_streams, uint64_t pinned_bytes, llkv_gpu_ctx** out) {
+  if (!out) return set_error(LLKV_ERR_INVALID_ARGUMENT, "out is NULL");
+  *out = nullptr;
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n <= 0) {
+    cudaGetLastError();
+    return set_error(LLKV_ERR_IO, "no CUDA device available (%s): this library has no CPU fallback",
+                     e != cudaSuccess ? cudaGetErrorString(e) : "device count 0");
+  }
+  if (device_ordinal < 0 || device_ordinal >= n) return set_error(LLKV_ERR_INVALID_ARGUMENT, "device ordinal %d out of range (%d devices)", device_ordinal, n);
+  CUDA_TRY(cudaSetDevice(device_ordinal));
+  cudaDeviceProp prop;
+  CUDA_TRY(cudaGetDeviceProperties(&prop, device_ordinal));
+  if (prop.major < 10) return set_error(LLKV_ERR_IO, "device %d is sm_%d%d; this library is built for sm_100a only", device_ordinal, prop.major, prop.minor);
+  llkv_gpu_ctx* c = new llkv_gpu_ctx();
+  c->device = device_ordinal;
+  c->sm_count = prop.multiProcessorCount;
+  c->max_smem = (int)prop.sharedMemPerBlockOptin;
+  if (n_streams < 1) n_streams = 2;
+  if (n_streams > 16) n_streams = 16;
+  if (pinned_bytes < ((uint64_t)n_streams << 20)) pinned_bytes = (uint64_t)n_streams << 22;
+  CUDA_TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+  c->copy_streams.resize((size_t)n_streams);
+  c->slot_events.resize((size_t)n_streams);
+  for (int i = 0; i < n_streams; ++i) {
+    CUDA_TRY(cudaStreamCreateWithFlags(&c->copy_streams[(size_t)i], cudaStreamNonBlocking));
+    CUDA_TRY(cudaEventCreateWithFlags(&c->slot_events[(size_t)i], cudaEventDisableTiming));
+  }
+  c->slot_bytes = (pinned_bytes / (uint64_t)n_streams) & ~(uint64_t)255;
+  CUDA_TRY(cudaHostAlloc((void**)&c->pinned, c->slot_bytes * (uint64_t)n_streams, cudaHostAllocDefault));
+  CUDA_TRY(cudaEventCreate(&c->ev0));
+  CUDA_TRY(cudaEventCreate(&c->ev1));
+  *out = c;
+  return LLKV_OK;
+}
+
+extern "C" void llkv_gpu_ctx_destroy(llkv_gpu_ctx* c) {
+  if (!c) return;
+  cudaSetDevice(c->device);
+  cudaDeviceSynchronize();
+  std::vector<llkv_gpu_column*> cols;
+  for (auto& kv : c->columns) cols.push_back(kv.second);
+  for (llkv_gpu_column* col : cols) llkv_gpu_column_destroy(col);
+  if (c->nccl_comm && g_nccl.comm_destroy) g_nccl.comm_destroy(c->nccl_comm);
+  for (cudaStream_t s : c->copy_streams) cudaStreamDestroy(s);
+  for (cudaEvent_t e : c->slot_events) cudaEventDestroy(e);
+  if (c->stream) cudaStreamDestroy(c->stream);
+  if (c->pinned) cudaFreeHost(c->pinned);
+  if (c->ev0) cudaEventDestroy(c->ev0);
+  if (c->ev1) cudaEventDestroy(c->ev1);
+  delete c;
+}
+
+extern "C" int32_t llkv_gpu_ctx_synchronize(llkv_gpu_ctx* c) {
+  if (!c) return set_error(LLKV_ERR_INVALID_ARGUMENT, "ctx is NULL");
+  CUDA_TRY(cudaSetDevice(c->device));
+  for (cudaStream_t s : c->copy_streams) CUDA_TRY(cudaStreamSynchronize(s));
+  CUDA_TRY(cudaStreamSynchronize(c->stream));
+  return LLKV_OK;
+}
+
+extern "C" int32_t llkv_gpu_ctx_stream(llkv_gpu_ctx* c, void** out_stream) {
+  if (!c || !out_stream) return set_error(LLKV_ERR_INVALID_ARGUMENT, "NULL argument");
+  *out_stream = (void*)c->stream;
+  return LLKV_OK;
+}
+
+extern "C" int32_t llkv_gpu_ctx_set_timing(llkv_gpu_ctx* c, int32_t enabled) {
+  if (!c) return set_error(LLKV_ERR_INVALID_ARGUMENT, "ctx is NULL");
+  c->timing = enabled != 0;
+  return LLKV_OK;
+}
+
+extern "C" int32_t llkv_gpu_ctx_set_tuning(llkv_gpu_ctx* c, int32_t ctas_per_sm, int32_t block_threads, int32_t stages,
+                                            int32_t rows_per_thread, int32_t force_wide) {
+  if (!c) return set_error(LLKV_ERR_INVALID_ARGUMENT, "ctx is NULL");
+  if (block_threads && (block_threads < 64 || block_threads > 512 || (block_threads & 63)))
+    return set_error(LLKV_ERR_INVALID_ARGUMENT, "block_threads must be a multiple of 64 in [64, 512]");
+  if (rows_per_thread && rows_per_thread != 1 && rows_per_thread != 2 && rows_per_thread != 4)
+    return set_error(LLKV_ERR_INVALID_ARGUMENT, "rows_per_thread must be 1, 2 or 4");
+  if (stages < 0 || stages > 8 || ctas_per_sm < 0 || ctas_per_sm > 8) return set_error(LLKV_ERR_INVALID_ARGUMENT, "tuning value out of range");
+  c->tune_ctas = ctas_per_sm;
+  c->tune_block = block_threads;
+  c->tune_stages = stages;
+  c->tune_rpt = rows_per_thread;
+  c->tune_force_wide = force_wide;
+  return LLKV_OK;
+}
+
+extern "C" int32_t llkv_gpu_host_alloc(uint64_t bytes, void** out) {
+  if (!out) return set_error(LLKV_ERR_INVALID_ARGUMENT, "out is NULL");
+  CUDA_TRY(cudaHostAlloc(out, bytes ? bytes : 1, cudaHostAllocDefault));
+  return LLKV_OK;
+}
+extern "C" int32_t llkv_gpu_host_free(void* p) {
+  if (p) CUDA_TRY(cudaFreeHost(p));
+  return LLKV_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ columns
+static uint32_t device_elem_bytes(int32_t type) {
+  if (type == LLKV_PT_UTF8) return 8;
+  return (uint32_t)prim_type_width(type);
+}
+static uint8_t device_load_kind(int32_t type) {
+  switch (type) {
+    case LLKV_PT_INT8: return LK_I8;
+    case LLKV_PT_INT16: return LK_I16;
+    case LLKV_PT_INT32: case LLKV_PT_DATE32: return LK_I32;
+    case LLKV_PT_INT64: case LLKV_PT_DATE64: return LK_I64;
+    case LLKV_PT_UINT8: case LLKV_PT_BOOLEAN: return LK_U8;
+    case LLKV_PT_UINT16: return LK_U16;
+    case LLKV_PT_UINT32: return LK_U32;
+    case LLKV_PT_UINT64: case LLKV_PT_UTF8: return LK_U64;
+    case LLKV_PT_FLOAT32: return LK_F32;
+    case LLKV_PT_FLOAT64: return LK_F64;
+    default: return LK_D128;
+  }
+}
+
+extern "C" int32_t llkv_gpu_column_register(llkv_gpu_ctx* c, uint64_t lfid, int32_t prim_type, uint8_t precision, int8_t scale,
+                                             llkv_gpu_column** out) {
+  if (!c || !out) return set_error(LLKV_ERR_INVALID_ARGUMENT, "NULL argument");
+  *out = nullptr;
+  if (device_elem_bytes(prim_type) == 0) return set_error(LLKV_ERR_INVALID_ARGUMENT, "column type %d does not cross this boundary", prim_type);
+  if (prim_type == LLKV_PT_DECIMAL128 && (precision < 1 || precision > 38)) return set_error(LLKV_ERR_INVALID_ARGUMENT, "Decimal128 precision %d out of range", precision);
+  if (c->columns.count(lfid)) return set_error(LLKV_ERR_INVALID_ARGUMENT, "column %llu is already registered", (unsigned long long)lfid);
+  CUDA_TRY(cudaSetDevice(c->device));
+  llkv_gpu_column* col = new llkv_gpu_column();
+  col->ctx = c;
+  col->lfid = lfid;
+  col->type = prim_type;
+  col->precision = precision;
+  col->scale = scale;
+  col->elem_bytes = device_elem_bytes(prim_type);
+  col->load_kind = device_load_kind(prim_type);
+  col->stream_index = (int)(c->columns.size() % c->copy_streams.size());
+  DevStats init;
+  memset(&init, 0, sizeof(init));
+  init.min_enc = ~0ull;
+  init.min_strlen = 0xffffffffu;
+  col->hstats = init;
+  cudaError_t e = cudaMalloc((void**)&col->dstats, sizeof(DevStats));
+  if (e == cudaSuccess) e = cudaMemcpy(col->dstats, &init, sizeof(init), cudaMemcpyHostToDevice);
+  if (e != cudaSuccess) {
+    delete col;
+    return set_error(LLKV_ERR_IO, "CUDA error %s allocating column state", cudaGetErrorString(e));
+  }
+  c->columns[lfid] = col;
+  *out = col;
+  return LLKV_OK;
+}
+
+static int32_t column_grow(llkv_gpu_column* col, uint64_t need_rows) {
+  if (need_rows + kPadRows <= col->cap_rows) return LLKV_OK;
+  llkv_gpu_ctx* c = col->ctx;
+  cudaStream_t s = c->copy_streams[(size_t)col->stream_index];
+  uint64_t cap = col->cap_rows * 2;
+  if (cap < need_rows + kPadRows) cap = need_rows + kPadRows;
+  cap = (cap + kPadRows - 1) / kPadRows * kPadRows;
+  void* nv = nullptr;
+  CUDA_TRY(cudaMalloc(&nv, cap * col->elem_bytes));
+  if (col->n_rows) CUDA_TRY(cudaMemcpyAsync(nv, col->values, col->n_rows * col->elem_bytes, cudaMemcpyDeviceToDevice, s));
+  // the padding is read by bulk copies of the last tile: keep it defined
+  CUDA_TRY(cudaMemsetAsync((char*)nv + col->n_rows * col->elem_bytes, 0, (cap - col->n_rows) * col->elem_bytes, s));
+  unsigned int* nb = nullptr;
+  if (col->validity) {
+    const uint64_t words = cap / 32 + 4;
+    CUDA_TRY(cudaMalloc((void**)&nb, words * 4));
+    CUDA_TRY(cudaMemsetAsync(nb, 0, words * 4, s));
+    CUDA_TRY(cudaMemcpyAsync(nb, col->validity, (col->n_rows + 31) / 32 * 4, cudaMemcpyDeviceToDevice, s));
+  }
+  CUDA_TRY(cudaStreamSynchronize(s));
+  if (col->values) CUDA_TRY(cudaFree(col->values));
+  if (col->validity) CUDA_TRY(cudaFree(col->validity));
+  col->values = nv;
+  col->validity = nb;
+  col->cap_rows = cap;
+  return LLKV_OK;
+}
+
+extern "C" int32_t llkv_gpu_column_reserve(llkv_gpu_column* col, uint64_t n_rows) {
+  if (!col) return set_error(LLKV_ERR_INVALID_ARGUMENT, "column is NULL");
+  CUDA_TRY(cudaSetDevice(col->ctx->device));
+  return column_grow(col, n_rows);
+}
+
+// host -> device through the pinned staging ring (or directly when the source is already page-locked)
+static int32_t upload(llkv_gpu_column* col, void* dst, const void* src, uint64_t bytes) {
+  llkv_gpu_ctx* c = col->ctx;
+  cudaStream_t cs = c->copy_streams[(size_t)col->stream_index];
+  if (bytes == 0) return LLKV_OK;
+  cudaPointerAttributes attr;
+  bool pinned_src = false;
+  if (cudaPointerGetAttributes(&attr, src) == cudaSuccess) pinned_src = attr.type == cudaMemoryTypeHost;
+  else cudaGetLastError();
+  if (pinned_src) {
+    CUDA_TRY(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, cs));
+    return LLKV_OK;
+  }
+  uint64_t done = 0;
+  while (done < bytes) {
+    const int slot = c->next_slot;
+    c->next_slot = (c->next_slot + 1) % (int)c->copy_streams.size();
+    const uint64_t n = bytes - done < c->slot_bytes ? bytes - done : c->slot_bytes;
+    CUDA_TRY(cudaEventSynchronize(c->slot_events[(size_t)slot]));  // the slot's previous copy has drained
+    unsigned char* stage = c->pinned + (uint64_t)slot * c->slot_bytes;
+    memcpy(stage, (const char*)src + done, n);
+    cudaStream_t s = c->copy_streams[(size_t)slot];
+    CUDA_TRY(cudaMemcpyAsync((char*)dst + done, stage, n, cudaMemcpyHostToDevice, s));
+    CUDA_TRY(cudaEventRecord(c->slot_events[(size_t)slot], s));
+    if (s != cs) CUDA_TRY(cudaStreamWaitEvent(cs, c->slot_events[(size_t)slot], 0));  // the column's stream runs the follow-up kernels
+    done += n;
+  }
+  return LLKV_OK;
+}
+
+static int32_t ensure_validity(llkv_gpu_column* col) {
+  if (col->validity) return LLKV_OK;
+  cudaStream_t s = col->ctx->copy_streams[(size_t)col->stream_index];
+  const uint64_t words = col->cap_rows / 32 + 4;
+  CUDA_TRY(cudaMalloc((void**)&col->validity, words * 4));
+  CUDA_TRY(cudaMemsetAsync(col->validity, 0, words * 4, s));
+  if (col->n_rows) {
+    fill_bits_kernel<<<256, 256, 0, s>>>(col->validity, 0, col->n_rows);
+    CUDA_TRY(cudaGetLastError());
+  }
+  return LLKV_OK;
+}
+
+static int32_t launch_stats(llkv_gpu_column* col, uint64_t first_row, uint64_t n) {
+  if (n == 0) return LLKV_OK;
+  cudaStream_t s = col->ctx->copy_streams[(size_t)col->stream_index];
+  unsigned int blocks = (unsigned int)std::min<uint64_t>((n + 1023) / 1024, 1184);
+  const char* base = (const char*)col->values + first_row * col->elem_bytes;
+  switch (col->type) {
+    case LLKV_PT_INT8: stats_kernel<signed char, true><<<blocks, 256, 0, s>>>((const signed char*)base, n, col->dstats); break;
+    case LLKV_PT_INT16: stats_kernel<short, true><<<blocks, 256, 0, s>>>((const short*)base, n, col->dstats); break;
+    case LLKV_PT_INT32: case LLKV_PT_DATE32: stats_kernel<int, true><<<blocks, 256, 0, s>>>((const int*)base, n, col->dstats); break;
+    case LLKV_PT_INT64: case LLKV_PT_DATE64: stats_kernel<i64, true><<<blocks, 256, 0, s>>>((const i64*)base, n, col->dstats); break;
+    case LLKV_PT_UINT8: case LLKV_PT_BOOLEAN: stats_kernel<unsigned char, false><<<blocks, 256, 0, s>>>((const unsigned char*)base, n, col->dstats); break;
+    case LLKV_PT_UINT16: stats_kernel<unsigned short, false><<<blocks, 256, 0, s>>>((const unsigned short*)base, n, col->dstats); break;
+    case LLKV_PT_UINT32: stats_kernel<unsigned int, false><<<blocks, 256, 0, s>>>((const unsigned int*)base, n, col->dstats); break;
+    case LLKV_PT_UINT64: stats_kernel<u64, false><<<blocks, 256, 0, s>>>((const u64*)base, n, col->dstats); break;
+    case LLKV_PT_DECIMAL128: stats_dec_kernel<<<blocks, 256, 0, s>>>((const ulonglong2*)base, n, col->dstats); break;
+    default: return LLKV_OK;  // floats: no statistics needed; Utf8: gathered by the pack kernel
+  }
+  CUDA_TRY(cudaGetLastError());
+  return LLKV_OK;
+}
+
+extern "C" int32_t llkv_gpu_column_append_chunk(llkv_gpu_column* col, uint64_t chunk_pk, const void* values, uint64_t n_rows,
+                                                 const uint8_t* validity, const uint64_t* row_ids, uint64_t row_id_base,
+                                                 const void* aux) {
+  (void)chunk_pk;
+  if (!col) return set_error(LLKV_ERR_INVALID_ARGUMENT, "column is NULL");
+  if (n_rows && !values) return set_error(LLKV_ERR_INVALID_ARGUMENT, "values is NULL");
+  llkv_gpu_ctx* c = col->ctx;
+  CUDA_TRY(cudaSetDevice(c->device));
+  // row ids must continue the column densely (SURVEY.md §7 hard part (a))
+  const uint64_t first_id = row_ids && n_rows ? row_ids[0] : row_id_base;
+  if (!col->has_origin) {
+    col->row_id_origin = first_id;
+    col->has_origin = true;
+  }
+  if (first_id != col->row_id_origin + col->n_rows)
+    return set_error(LLKV_ERR_INVALID_ARGUMENT, "chunk row ids start at %llu but the column continues at %llu: only dense row-id runs are supported",
+                     (unsigned long long)first_id, (unsigned long long)(col->row_id_origin + col->n_rows));
+  if (row_ids)
+    for (uint64_t i = 1; i < n_rows; ++i)
+      if (row_ids[i] != first_id + i) return set_error(LLKV_ERR_INVALID_ARGUMENT, "chunk row ids are not a dense run at offset %llu", (unsigned long long)i);
+  if (n_rows == 0) return LLKV_OK;
+  col->sealed = false;
+  if (col->load_kind == LK_STR8) {  // sealed as one byte per string: back to packed keys before more chunks arrive
+    u64* wide = nullptr;
+    CUDA_TRY(cudaDeviceSynchronize());
+    CUDA_TRY(cudaMalloc((void**)&wide, col->cap_rows * 8));
+    CUDA_TRY(cudaMemset(wide, 0, col->cap_rows * 8));
+    widen_str_kernel<<<1184, 256>>>((const unsigned char*)col->values, wide, col->n_rows);
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaDeviceSynchronize());
+    CUDA_TRY(cudaFree(col->values));
+    col->values = wide;
+    col->elem_bytes = 8;
+    col->load_kind = LK_U64;
+  }
+  int32_t rc = column_grow(col, col->n_rows + n_rows);
+  if (rc) return rc;
+  cudaStream_t s = c->copy_streams[(size_t)col->stream_index];
+  if (col->type == LLKV_PT_UTF8) {
+    const int32_t* off = (const int32_t*)values;
+    const int64_t data_bytes = (int64_t)off[n_rows] - (int64_t)off[0];
+    if (data_bytes < 0) return set_error(LLKV_ERR_INVALID_ARGUMENT, "Utf8 offsets are not monotonic");
+    if (data_bytes && !aux) return set_error(LLKV_ERR_INVALID_ARGUMENT, "Utf8 data buffer is NULL");
+    int* d_off = nullptr;
+    unsigned char* d_data = nullptr;
+    CUDA_TRY(cudaMalloc((void**)&d_off, (n_rows + 1) * 4));
+    CUDA_TRY(cudaMalloc((void**)&d_data, (size_t)(off[n_rows] > 0 ? off[n_rows] : 1)));
+    col->deferred_free.push_back(d_off);
+    col->deferred_free.push_back(d_data);
+    if ((rc = upload(col, d_off, off, (n_rows + 1) * 4))) return rc;
+    if (off[n_rows] > 0 && (rc = upload(col, d_data, aux, (uint64_t)off[n_rows]))) return rc;
+    const unsigned int blocks = (unsigned int)std::min<uint64_t>((n_rows + 255) / 256, 1184);
+    pack_utf8_kernel<<<blocks, 256, 0, s>>>(d_off, d_data, n_rows, (u64*)col->values + col->n_rows, col->dstats);
+    CUDA_TRY(cudaGetLastError());
+    col->hstats.data_bytes += (u64)data_bytes;
+  } else {
+    if ((rc = upload(col, (char*)col->values + col->n_rows * col->elem_bytes, values, n_rows * col->elem_bytes))) return rc;
+    if ((rc = launch_stats(col, col->n_rows, n_rows))) return rc;
+  }
+  if (validity) {
+    if ((rc = ensure_validity(col))) return rc;
+    unsigned char* d_bits = nullptr;
+    const uint64_t nb = (n_rows + 7) / 8;
+    CUDA_TRY(cudaMalloc((void**)&d_bits, nb));
+    col->deferred_free.push_back(d_bits);
+    if ((rc = upload(col, d_bits, validity, nb))) return rc;
+    const unsigned int blocks = (unsigned int)std::min<uint64_t>((n_rows / 32 + 256) / 256, 1184);
+    or_bits_kernel<<<blocks, 256, 0, s>>>(col->validity, col->n_rows, d_bits, n_rows);
+    CUDA_TRY(cudaGetLastError());
+  } else if (col->validity) {
+    fill_bits_kernel<<<256, 256, 0, s>>>(col->validity, col->n_rows, col->n_rows + n_rows);
+    CUDA_TRY(cudaGetLastError());
+  }
+  col->n_rows += n_rows;
+  return LLKV_OK;
+}
+
+extern "C" int32_t llkv_gpu_column_append_blob(llkv_gpu_column* col, uint64_t chunk_pk, const void* blob, uint64_t blob_len,
+                                                const uint64_t* row_ids, uint64_t row_id_base) {
+  if (!col || !blob) return set_error(LLKV_ERR_INVALID_ARGUMENT, "NULL argument");
+  // "ARR0" | layout u8 | PrimType u8 | precision u8 | scale u8 | len u64 | extra_a u32 | extra_b u32 | payload
+  // (llkv-column-map/src/serialization.rs:41-53,264-307)
+  const unsigned char* b = (const unsigned char*)blob;
+  if (blob_len < 24) return set_error(LLKV_ERR_IO, "chunk blob too short for its header");
+  if (memcmp(b, "ARR0", 4) != 0) return set_error(LLKV_ERR_IO, "chunk blob has a bad magic");
+  if (b[4] != 0) return set_error(LLKV_ERR_INVALID_ARGUMENT, "only the Primitive chunk layout crosses this boundary (layout %d)", b[4]);
+  if ((int32_t)b[5] != col->type) return set_error(LLKV_ERR_INVALID_ARGUMENT, "chunk PrimType %d does not match the column type %d", b[5], col->type);
+  if (col->type == LLKV_PT_DECIMAL128 && (b[6] != col->precision || (int8_t)b[7] != col->scale))
+    return set_error(LLKV_ERR_INVALID_ARGUMENT, "chunk Decimal128(%d,%d) does not match the column", b[6], (int8_t)b[7]);
+  uint64_t len;
+  uint32_t values_len;
+  memcpy(&len, b + 8, 8);
+  memcpy(&values_len, b + 16, 4);
+  const uint64_t w = (uint64_t)prim_type_width(col->type);
+  if (values_len != len * w || 24 + (uint64_t)values_len > blob_len) return set_error(LLKV_ERR_IO, "chunk blob payload length mismatch");
+  return llkv_gpu_column_append_chunk(col, chunk_pk, b + 24, len, nullptr, row_ids, row_id_base, nullptr);
+}
+
+extern "C" int32_t llkv_gpu_column_seal(llkv_gpu_column* col) {
+  if (!col) return set_error(LLKV_ERR_INVALID_ARGUMENT, "column is NULL");
+  llkv_gpu_ctx* c = col->ctx;
+  CUDA_TRY(cudaSetDevice(c->device));
+  for (cudaStream_t s : c->copy_streams) CUDA_TRY(cudaStreamSynchronize(s));
+  for (void* p : col->deferred_free) cudaFree(p);
+  col->deferred_free.clear();
+  const u64 data_bytes = col->hstats.data_bytes;
+  CUDA_TRY(cudaMemcpy(&col->hstats, col->dstats, sizeof(DevStats), cudaMemcpyDeviceToHost));
+  col->hstats.data_bytes = data_bytes;
+  if (col->type == LLKV_PT_UTF8) {
+    if (col->hstats.bad_string) return set_error(LLKV_ERR_INVALID_ARGUMENT, "string longer than 7 bytes in short-string column");
+    // every string exactly one byte long: keep one byte per row
+    if (col->load_kind == LK_U64 && col->n_rows && col->hstats.max_strlen == 1 && col->hstats.min_strlen == 1) {
+      unsigned char* nv = nullptr;
+      CUDA_TRY(cudaMalloc((void**)&nv, col->cap_rows));
+      CUDA_TRY(cudaMemset(nv, 0, col->cap_rows));
+      narrow_str_kernel<<<1184, 256>>>((const u64*)col->values, nv, col->n_rows);
+      CUDA_TRY(cudaGetLastError());
+      CUDA_TRY(cudaDeviceSynchronize());
+      CUDA_TRY(cudaFree(col->values));
+      col->values = nv;
+      col->elem_bytes = 1;
+      col->load_kind = LK_STR8;
+    }
+  }
+  col->sealed = true;
+  return LLKV_OK;
+}
+
+extern "C" int32_t llkv_gpu_column_rows(const llkv_gpu_column* col, uint64_t* out_rows) {
+  if (!col || !out_rows) return set_error(LLKV_ERR_INVALID_ARGUMENT, "NULL argument");
+  *out_rows = col->n_rows;
+  return LLKV_OK;
+}
+
+extern "C" int32_t llkv_gpu_column_clear(llkv_gpu_column* col) {
+  if (!col) return set_error(LLKV_ERR_INVALID_ARGUMENT, "column is NULL");
+  llkv_gpu_ctx* c = col->ctx;
+  CUDA_TRY(cudaSetDevice(c->device));
+  cudaStream_t s = c->copy_streams[(size_t)col->stream_index];
+  CUDA_TRY(cudaStreamSynchronize(c->stream));
+  if (col->type == LLKV_PT_UTF8 && col->load_kind == LK_STR8) {  // back to the packed representation for new appends
+    if (col->values) CUDA_TRY(cudaFree(col->values));
+    col->values = nullptr;
+    col->cap_rows = 0;
+    col->elem_bytes = 8;
+    col->load_kind = LK_U64;
+  }
+  if (col->validity) CUDA_TRY(cudaMemsetAsync(col->validity, 0, (col->cap_rows / 32 + 4) * 4, s));
+  DevStats init;
+  memset(&init, 0, sizeof(init));
+  init.min_enc = ~0ull;
+  init.min_strlen = 0xffffffffu;
+  col->hstats = init;
+  CUDA_TRY(cudaMemcpyAsync(col->dstats, &col->hstats, sizeof(DevStats), cudaMemcpyHostToDevice, s));
+  CUDA_TRY(cudaStreamSynchronize(s));
+  col->n_rows = 0;
+  col->has_origin = false;
+  col->sealed = false;
+  return LLKV_OK;
+}
+
+extern "C" int32_t llkv_gpu_column_destroy(llkv_gpu_column* col) {
+  if (!col) return LLKV_OK;
+  llkv_gpu_ctx* c = col->ctx;
+  cudaSetDevice(c->device);
+  cudaDeviceSynchronize();
+  c->columns.erase(col->lfid);
+  for (auto& kv : c->mvcc)
+    if (kv.second.created_by == col || kv.second.deleted_by == col) kv.second.created_by = kv.second.deleted_by = nullptr;
+  for (void* p : col->deferred_free) cudaFree(p);
+  if (col->values) cudaFree(col->values);
+  if (col->validity) cudaFree(col->validity);
+  if (col->dstats) cudaFree(col->dstats);
+  delete col;
+  return LLKV_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ programs / MVCC
+extern "C" int32_t llkv_gpu_program_compile(llkv_gpu_ctx* ctx, const llkv_eval_op* ops, int32_t n_ops, const llkv_literal* literals,
+                                             int32_t n_literals, const llkv_scalar_node* nodes, int32_t n_nodes,
+                                             const int32_t* list_roots, int32_t n_list_roots, llkv_gpu_program** out) {
+  if (!ctx || !out) return set_error(LLKV_ERR_INVALID_ARGUMENT, "NULL argument");
+  *out = nullptr;
+  if (n_ops < 0 || n_literals < 0 || n_nodes < 0 || n_list_roots < 0) return set_error(LLKV_ERR_INVALID_ARGUMENT, "negative count");
+  if ((n_ops && !ops) || (n_literals && !literals) || (n_nodes && !nodes) || (n_list_roots && !list_roots))
+    return set_error(LLKV_ERR_INVALID_ARGUMENT, "NULL array with a non-zero count");
+  for (int i = 0; i < n_ops; ++i) {
+    const int t = ops[i].tag;
+    if (!((t >= LLKV_EV_PUSH_PREDICATE && t <= LLKV_EV_NOT) || t == LLKV_EV_FILTER_ITEM))
+      return set_error(LLKV_ERR_INTERNAL, "unknown eval op tag %d", t);
+    if ((t == LLKV_EV_PUSH_PREDICATE || t == LLKV_EV_FILTER_ITEM) &&
+        (ops[i].operator_tag == LLKV_OP_STARTS_WITH || ops[i].operator_tag == LLKV_OP_ENDS_WITH || ops[i].operator_tag == LLKV_OP_CONTAINS))
+      return set_error(LLKV_ERR_PREDICATE_BUILD, "string pattern operators are not supported on this path");
+  }
+  llkv_gpu_program* p = new llkv_gpu_program();
+  p->ops.assign(ops, ops + n_ops);
+  p->literals.assign(literals, literals + n_literals);
+  p->nodes.assign(nodes, nodes + n_nodes);
+  p->list_roots.assign(list_roots, list_roots + n_list_roots);
+  p->bind();
+  *out = p;
+  return LLKV_OK;
+}
+
+extern "C" void llkv_gpu_program_destroy(llkv_gpu_program* prog) { delete prog; }
+
+extern "C" int32_t llkv_gpu_mvcc_set(llkv_gpu_ctx* ctx, uint64_t table_id, llkv_gpu_column* created_by, llkv_gpu_column* deleted_by,
+                                      uint64_t txn_id, uint64_t snapshot_id, const uint64_t* noncommitted, int32_t n_noncommitted) {
+  if (!ctx) return set_error(LLKV_ERR_INVALID_ARGUMENT, "ctx is NULL");
+  if (n_noncommitted < 0 || (n_noncommitted && !noncommitted)) return set_error(LLKV_ERR_INVALID_ARGUMENT, "bad non-committed list");
+  if (n_noncommitted > kMaxNoncommitted) return set_error(LLKV_ERR_INVALID_ARGUMENT, "more than %d non-committed transactions in one snapshot", kMaxNoncommitted);
+  if ((created_by && created_by->type != LLKV_PT_UINT64) || (deleted_by && deleted_by->type != LLKV_PT_UINT64))
+    return set_error(LLKV_ERR_INVALID_ARGUMENT, "MVCC columns must be UInt64");
+  MvccState& m = ctx->mvcc[table_id];
+  m.created_by = created_by;
+  m.deleted_by = deleted_by;
+  m.txn_id = txn_id;
+  m.snapshot_id = snapshot_id;
+  m.noncommitted.assign(noncommitted, noncommitted + n_noncommitted);
+  return LLKV_OK;
+}
+
+extern "C" int32_t llkv_gpu_mvcc_clear(llkv_gpu_ctx* ctx, uint64_t table_id) {
+  if (!ctx) return set_error(LLKV_ERR_INVALID_ARGUMENT, "ctx is NULL");
+  ctx->mvcc.erase(table_id);
+  return LLKV_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ plan building
+static uint64_t lfid_table(uint64_t lfid) { return (lfid >> 32) & 0xffffull; }  // llkv-types/src/ids.rs:133-152
+static uint64_t lfid_field(uint64_t lfid) { return lfid & 0xffffffffull; }
+
+static int32_t collect_columns(llkv_gpu_ctx* ctx, uint64_t table_id, std::vector<ColumnMeta>& cols,
+                               std::vector<llkv_gpu_column*>& handles, uint64_t* table_rows) {
+  cols.clear();
+  handles.clear();
+  bool have = false;
+  uint64_t rows = 0;
+  for (auto& kv : ctx->columns) {
+    llkv_gpu_column* col = kv.second;
+    if (lfid_table(col->lfid) != (table_id & 0xffffull)) continue;
+    if (!col->sealed) {
+      int32_t rc = llkv_gpu_column_seal(col);
+      if (rc) return rc;
+    }
+    ColumnMeta m;
+    m.field_id = lfid_field(col->lfid) | ((col->lfid >> 48) << 48);  // namespaced (MVCC) columns keep their namespace bits
+    m.type = col->type;
+    m.precision = col->precision;
+    m.scale = col->scale;
+    m.nullable = col->validity != nullptr;
+    m.load_kind = col->load_kind;
+    m.elem_bytes = col->elem_bytes;
+    if (col->type == LLKV_PT_UTF8) m.arrow_bytes = 4 + (uint32_t)(col->n_rows ? (col->hstats.data_bytes + col->n_rows - 1) / col->n_rows : 0);
+    else m.arrow_bytes = (uint32_t)prim_type_width(col->type);
+    m.dev_values = col->values;
+    m.dev_validity = (const unsigned char*)col->validity;
+    m.n_rows = col->n_rows;
+    m.dec_fits_i64 = col->hstats.not_i64 == 0;
+    const bool is_signed = col->type == LLKV_PT_INT8 || col->type == LLKV_PT_INT16 || col->type == LLKV_PT_INT32 ||
+                           col->type == LLKV_PT_INT64 || col->type == LLKV_PT_DATE32 || col->type == LLKV_PT_DATE64;
+    const bool is_unsigned = col->type == LLKV_PT_UINT8 || col->type == LLKV_PT_UINT16 || col->type == LLKV_PT_UINT32 ||
+                             col->type == LLKV_PT_UINT64 || col->type == LLKV_PT_BOOLEAN;
+    if ((is_signed || is_unsigned) && col->n_rows && col->hstats.min_enc <= col->hstats.max_enc) {
+      m.has_minmax = true;
+      m.min_bits = is_signed ? (col->hstats.min_enc ^ 0x8000000000000000ull) : col->hstats.min_enc;
+      m.max_bits = is_signed ? (col->hstats.max_enc ^ 0x8000000000000000ull) : col->hstats.max_enc;
+    }
+    m.max_strlen = (uint8_t)col->hstats.max_strlen;
+    cols.push_back(m);
+    handles.push_back(col);
+    if (!have) {
+      rows = col->n_rows;
+      have = true;
+    } else if (col->n_rows < rows) {
+      rows = col->n_rows;
+    }
+  }
+  *table_rows = have ? rows : 0;
+  return LLKV_OK;
+}
+
+struct Geometry {
+  uint32_t grid = 0, block = 0, R = 1, smem = 0;
+};
+
+static uint32_t align_up(uint32_t v, uint32_t a) { return (v + a - 1) / a * a; }
+static u64 next_pow2(u64 v) {
+  u64 p = 1;
+  while (p < v) p <<= 1;
+  return p;
+}
+
+// Chooses block size, rows per thread, pipeline depth and CTA-local group slots so that the plan fits in shared memory,
+// and fills the launch-geometry / shared-memory fields of the plan.
+static int32_t plan_geometry(llkv_gpu_ctx* ctx, Plan& p, bool wide, uint64_t row_begin, uint64_t row_end, uint64_t hint,
+                             Geometry& g) {
+  const uint32_t vbytes = wide ? 16u : 8u;
+  uint32_t NT = ctx->tune_block ? (uint32_t)ctx->tune_block : 512u;
+  uint32_t R = ctx->tune_rpt ? (uint32_t)ctx->tune_rpt : (wide ? 1u : 2u);
+  if (wide && R > 2) R = 2;
+  uint32_t stages = ctx->tune_stages ? (uint32_t)ctx->tune_stages : 3u;
+  uint32_t ctas = ctx->tune_ctas ? (uint32_t)ctx->tune_ctas : 2u;
+  uint32_t FG = 0;
+  if (p.n_fast_words) {
+    if (p.n_keys == 0) FG = 1;
+    else if (hint == 0) FG = 16;
+    else if (hint <= 128) FG = (uint32_t)next_pow2(hint + hint / 2 + 1);
+    else FG = 0;
+  }
+  const uint32_t budget_total = (uint32_t)ctx->max_smem;
+  for (int attempt = 0; attempt < 64; ++attempt) {
+    const uint32_t T = NT * R;
+    const bool staged = stages >= 2;
+    uint32_t off = align_up((uint32_t)sizeof(Plan), 128);
+    p.smem_plan_off = 0;
+    p.smem_bar_off = off;
+    off += 128;
+    p.smem_stage_off = off;
+    uint32_t stage_bytes = 0, tx = 0;
+    if (staged) {
+      for (uint32_t c = 0; c < p.n_cols; ++c) {
+        p.cols[c].smem_off = stage_bytes;
+        stage_bytes += align_up(T * p.cols[c].elem_bytes, 128);
+        tx += T * p.cols[c].elem_bytes;
+        if (p.cols[c].validity) {
+          p.cols[c].vsmem_off = stage_bytes;
+          stage_bytes += align_up(T / 8, 128);
+          tx += T / 8;
+        }
+      }
+      off += stage_bytes * stages;
+    }
+    p.smem_acc_off = off;
+    off += align_up(FG * p.n_fast_words * NT * 8, 128);
+    p.smem_spill_off = off;
+    const uint32_t spill_slots = p.max_depth > 2 ? p.max_depth - 2 : 0;
+    off += align_up(spill_slots * R * NT * vbytes, 128);
+    p.smem_tbl_off = off;
+    off += align_up((FG ? FG : 1) * 8, 128);
+    const uint32_t per_cta_budget = budget_total / ctas - 1024;
+    if (off <= per_cta_budget) {
+      p.tile_rows = T;
+      p.stages = staged ? stages : 1;
+      p.staged = staged ? 1 : 0;
+      p.stage_bytes = stage_bytes;
+      p.tx_bytes = tx;
+      p.fast_groups = FG;
+      p.smem_total = off;
+      p.row_begin = row_begin;
+      p.row_end = row_end;
+      p.first_tile = row_begin / T;
+      p.n_tiles = row_end > row_begin ? (row_end + T - 1) / T - p.first_tile : 0;
+      g.block = NT;
+      g.R = R;
+      g.smem = off;
+      u64 grid = (u64)ctx->sm_count * ctas;
+      if (grid > p.n_tiles) grid = p.n_tiles;
+      if (grid == 0) grid = 1;
+      g.grid = (uint32_t)grid;
+      return LLKV_OK;
+    }
+    // shrink: fewer CTAs per SM, shallower pipeline, fewer rows per thread, smaller block, fewer CTA-local groups
+    if (ctas > 1) ctas -= 1;
+    else if (stages > 2) stages -= 1;
+    else if (R > 1) R /= 2;
+    else if (FG > 4 && p.n_keys) FG /= 2;
+    else if (NT > 128) NT /= 2;
+    else if (FG > 0 && p.n_keys) FG = 0;
+    else if (stages >= 2) stages = 1;
+    else break;
+  }
+  return set_error(LLKV_ERR_INVALID_ARGUMENT, "query state does not fit in shared memory on this path");
+}
+
+static int32_t build_request(llkv_gpu_ctx* ctx, uint64_t table_id, const llkv_gpu_program* prog, int apply_mvcc, CompileRequest& req,
+                             std::vector<llkv_gpu_column*>& handles, uint64_t* table_rows) {
+  int32_t rc = collect_columns(ctx, table_id, req.cols, handles, table_rows);
+  if (rc) return rc;
+  req.prog = prog ? &prog->view : nullptr;
+  req.mvcc = MvccView();
+  if (apply_mvcc) {
+    auto it = ctx->mvcc.find(table_id);
+    // missing MVCC columns => every row is visible (llkv-transaction/src/helpers.rs:141-152)
+    if (it != ctx->mvcc.end() && it->second.created_by && it->second.deleted_by) {
+      const MvccState& m = it->second;
+      for (size_t i = 0; i < handles.size(); ++i) {
+        if (handles[i] == m.created_by) req.mvcc.created_by = &req.cols[i];
+        if (handles[i] == m.deleted_by) req.mvcc.deleted_by = &req.cols[i];
+      }
+      if (!req.mvcc.created_by || !req.mvcc.deleted_by)
+        return set_error(LLKV_ERR_INVALID_ARGUMENT, "MVCC columns of table %llu are not registered under that table id", (unsigned long long)table_id);
+      req.mvcc.enabled = true;
+      req.mvcc.txn_id = m.txn_id;
+      req.mvcc.snapshot_id = m.snapshot_id;
+      req.mvcc.noncommitted = m.noncommitted;
+    }
+  }
+  return LLKV_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ selection bitmap
+extern "C" int32_t llkv_gpu_filter_bitmap(llkv_gpu_ctx* ctx, uint64_t table_id, const llkv_gpu_program* prog, int32_t apply_mvcc,
+                                           uint64_t row_begin, uint64_t row_end, uint64_t* out_words, uint64_t n_words,
+                                           uint64_t* out_count) {
+  if (!ctx) return set_error(LLKV_ERR_INVALID_ARGUMENT, "ctx is NULL");
+  if (row_end < row_begin) return set_error(LLKV_ERR_INVALID_ARGUMENT, "row_end < row_begin");
+  CUDA_TRY(cudaSetDevice(ctx->device));
+  CompileRequest req;
+  std::vector<llkv_gpu_column*> handles;
+  uint64_t table_rows = 0;
+  int32_t rc = build_request(ctx, table_id, prog, apply_mvcc, req, handles, &table_rows);
+  if (rc) return rc;
+  if (row_end > table_rows) return set_error(LLKV_ERR_INVALID_ARGUMENT, "row_end %llu beyond the table's %llu rows", (unsigned long long)row_end, (unsigned long long)table_rows);
+  const uint64_t need_words = (row_end - row_begin + 63) / 64;
+  if (out_words && n_words < need_words) return set_error(LLKV_ERR_INVALID_ARGUMENT, "bitmap buffer too small");
+  req.bitmap_mode = true;
+  req.force_wide = ctx->tune_force_wide != 0;
+  u64* d_bits = nullptr;
+  Plan* d_plan = nullptr;
+  uint32_t* d_flags = nullptr;
+  const uint64_t alloc_words = need_words + 2;
+  CUDA_TRY(cudaMalloc((void**)&d_bits, (alloc_words + 1) * 8));
+  CUDA_TRY(cudaMalloc((void**)&d_plan, sizeof(Plan)));
+  CUDA_TRY(cudaMalloc((void**)&d_flags, 4));
+  int32_t result = LLKV_OK;
+  for (int pass = 0; pass < 2; ++pass) {
+    CompileResult cr;
+    if ((rc = compile_plan(req, cr))) { result = set_error(rc, "%s", cr.error.c_str()); break; }
+    Geometry g;
+    if ((rc = plan_geometry(ctx, cr.plan, cr.wide, row_begin, row_end, 0, g))) { result = rc; break; }
+    cr.plan.out_bitmap = d_bits;
+    cr.plan.out_count = d_bits + alloc_words;
+    cr.plan.flags = d_flags;
+    cr.plan.gcap = 1;
+    cudaError_t e = cudaMemsetAsync(d_bits, 0, (alloc_words + 1) * 8, ctx->stream);
+    if (e == cudaSuccess) e = cudaMemsetAsync(d_flags, 0, 4, ctx->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_plan, &cr.plan, sizeof(Plan), cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess && cr.plan.n_tiles) e = launch_scan(d_plan, cr.wide, (int)g.R, g.grid, g.block, g.smem, ctx->stream);
+    uint32_t flags = 0;
+    if (e == cudaSuccess) e = cudaMemcpyAsync(&flags, d_flags, 4, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) { result = set_error(LLKV_ERR_IO, "CUDA error %s in filter_bitmap", cudaGetErrorString(e)); break; }
+    if ((flags & FLAG_NARROW_FAIL) && !cr.wide) {
+      req.force_wide = true;
+      continue;
+    }
+    if (flags & FLAG_BAD_PLAN) { result = set_error(LLKV_ERR_INTERNAL, "device interpreter met an unknown instruction"); break; }
+    if (flags & FLAG_DIV_ZERO) { result = set_error(LLKV_ERR_INTERNAL, "Divide by zero error"); break; }
+    if (flags & FLAG_ARITH_OVERFLOW) { result = set_error(LLKV_ERR_INTERNAL, "Arithmetic overflow: Overflow happened in a predicate expression"); break; }
+    if (flags & FLAG_EXACT_OVERFLOW) { result = set_error(LLKV_ERR_INVALID_ARGUMENT, "Decimal overflow in a predicate expression"); break; }
+    if (out_words && need_words) {
+      e = cudaMemcpy(out_words, d_bits, need_words * 8, cudaMemcpyDeviceToHost);
+      if (e != cudaSuccess) { result = set_error(LLKV_ERR_IO, "CUDA error %s reading the bitmap", cudaGetErrorString(e)); break; }
+    }
+    if (out_count) {
+      e = cudaMemcpy(out_count, d_bits + alloc_words, 8, cudaMemcpyDeviceToHost);
+      if (e != cudaSuccess) { result = set_error(LLKV_ERR_IO, "CUDA error %s reading the count", cudaGetErrorString(e)); break; }
+    }
+    break;
+  }
+  cudaFree(d_bits);
+  cudaFree(d_plan);
+  cudaFree(d_flags);
+  return result;
+}
+
+// ------------------------------------------------------------------------------------------------ aggregates
+extern "C" int32_t llkv_gpu_agg_create(llkv_gpu_ctx* ctx, uint64_t table_id, const llkv_agg_spec* specs, int32_t n_aggs,
+                                        const llkv_scalar_node* nodes, int32_t n_nodes, const uint64_t* group_key_fields,
+                                        int32_t n_keys, int32_t expr_mode, uint64_t cardinality_hint, llkv_gpu_agg** out) {
+  if (!ctx || !out) return set_error(LLKV_ERR_INVALID_ARGUMENT, "NULL argument");
+  *out = nullptr;
+  if (n_aggs < 0 || n_nodes < 0 || n_keys < 0 || (n_aggs && !specs) || (n_nodes && !nodes) || (n_keys && !group_key_fields))
+    return set_error(LLKV_ERR_INVALID_ARGUMENT, "bad aggregate arguments");
+  if (n_keys > kMaxKeys) return set_error(LLKV_ERR_INVALID_ARGUMENT, "too many GROUP BY keys (max %d)", kMaxKeys);
+  if (expr_mode != LLKV_EXPR_ARROW && expr_mode != LLKV_EXPR_EXACT) return set_error(LLKV_ERR_INVALID_ARGUMENT, "bad expr_mode %d", expr_mode);
+  for (int i = 0; i < n_aggs; ++i) {
+    if (specs[i].distinct) return set_error(LLKV_ERR_INVALID_ARGUMENT, "DISTINCT aggregates are outside this path");
+    if (specs[i].expr_root >= n_nodes) return set_error(LLKV_ERR_INVALID_ARGUMENT, "aggregate %d: expression root out of range", i);
+    if (specs[i].expr_root < 0 && specs[i].kind != LLKV_AGG_COUNT) return set_error(LLKV_ERR_INVALID_ARGUMENT, "aggregate %d needs an argument", i);
+  }
+  CUDA_TRY(cudaSetDevice(ctx->device));
+  llkv_gpu_agg* a = new llkv_gpu_agg();
+  a->ctx = ctx;
+  a->table_id = table_id;
+  a->specs.assign(specs, specs + n_aggs);
+  a->nodes.assign(nodes, nodes + n_nodes);
+  a->keys.assign(group_key_fields, group_key_fields + n_keys);
+  a->expr_mode = expr_mode;
+  a->hint = cardinality_hint;
+  memset(&a->info, 0, sizeof(a->info));
+  cudaError_t e = cudaMalloc((void**)&a->d_flags, 4);
+  if (e == cudaSuccess) e = cudaMemset(a->d_flags, 0, 4);
+  if (e == cudaSuccess) e = cudaMalloc((void**)&a->d_plan, sizeof(Plan));
+  if (e == cudaSuccess) e = cudaHostAlloc((void**)&a->h_plan, sizeof(Plan), cudaHostAllocDefault);
+  if (e == cudaSuccess) e = cudaHostAlloc((void**)&a->h_flags, 4, cudaHostAllocDefault);
+  if (e != cudaSuccess) {
+    llkv_gpu_agg_destroy(a);
+    return set_error(LLKV_ERR_IO, "CUDA error %s allocating aggregate state", cudaGetErrorString(e));
+  }
+  *a->h_flags = 0;
+  *out = a;
+  return LLKV_OK;
+}
+
+extern "C" void llkv_gpu_agg_destroy(llkv_gpu_agg* a) {
+  if (!a) return;
+  cudaSetDevice(a->ctx->device);
+  cudaStreamSynchronize(a->ctx->stream);
+  if (a->d_gclass) cudaFree(a->d_gclass);
+  if (a->gkeys) cudaFree(a->gkeys);
+  if (a->gwords) cudaFree(a->gwords);
+  if (a->bk_keys) cudaFree(a->bk_keys);
+  if (a->bk_words) cudaFree(a->bk_words);
+  if (a->d_flags) cudaFree(a->d_flags);
+  if (a->d_plan) cudaFree(a->d_plan);
+  if (a->h_plan) cudaFreeHost(a->h_plan);
+  if (a->h_flags) cudaFreeHost(a->h_flags);
+  delete a;
+}
+
+static int32_t agg_alloc_table(llkv_gpu_agg* a, u64 gcap) {
+  llkv_gpu_ctx* ctx = a->ctx;
+  const u64 rows = gcap + 2;
+  CUDA_TRY(cudaMalloc((void**)&a->gkeys, gcap * 8));
+  CUDA_TRY(cudaMalloc((void**)&a->gwords, rows * a->n_gwords * 8));
+  a->gcap = gcap;
+  CUDA_TRY(launch_init_table(a->gkeys, a->gwords, rows, a->n_gwords, a->d_gclass, ctx->stream));
+  return LLKV_OK;
+}
+
+static int32_t agg_freeze_layout(llkv_gpu_agg* a, const CompileResult& cr) {
+  const Plan& p = cr.plan;
+  if (a->frozen) {
+    if (p.n_gwords != a->n_gwords || memcmp(p.gword_class, a->gclass.data(), a->n_gwords) != 0)
+      return set_error(LLKV_ERR_INTERNAL, "accumulator layout changed between runs (column types changed?)");
+    return LLKV_OK;
+  }
+  a->n_gwords = p.n_gwords;
+  a->gclass.assign(p.gword_class, p.gword_class + p.n_gwords);
+  CUDA_TRY(cudaMalloc((void**)&a->d_gclass, a->n_gwords ? a->n_gwords : 1));
+  CUDA_TRY(cudaMemcpy(a->d_gclass, a->gclass.data(), a->n_gwords, cudaMemcpyHostToDevice));
+  u64 gcap = 1;
+  if (p.n_keys) {
+    gcap = next_pow2(std::max<u64>(1024, a->hint * 2));
+  }
+  int32_t rc = agg_alloc_table(a, gcap);
+  if (rc) return rc;
+  a->frozen = true;
+  return LLKV_OK;
+}
+
+static int32_t agg_backup(llkv_gpu_agg* a) {
+  llkv_gpu_ctx* ctx = a->ctx;
+  if (a->bk_cap != a->gcap) {
+    if (a->bk_keys) CUDA_TRY(cudaFree(a->bk_keys));
+    if (a->bk_words) CUDA_TRY(cudaFree(a->bk_words));
+    a->bk_keys = a->bk_words = nullptr;
+    CUDA_TRY(cudaMalloc((void**)&a->bk_keys, a->gcap * 8));
+    CUDA_TRY(cudaMalloc((void**)&a->bk_words, (a->gcap + 2) * a->n_gwords * 8));
+    a->bk_cap = a->gcap;
+  }
+  CUDA_TRY(cudaMemcpyAsync(a->bk_keys, a->gkeys, a->gcap * 8, cudaMemcpyDeviceToDevice, ctx->stream));
+  CUDA_TRY(cudaMemcpyAsync(a->bk_words, a->gwords, (a->gcap + 2) * a->n_gwords * 8, cudaMemcpyDeviceToDevice, ctx->stream));
+  return LLKV_OK;
+}
+static int32_t agg_restore(llkv_gpu_agg* a) {
+  llkv_gpu_ctx* ctx = a->ctx;
+  CUDA_TRY(cudaMemcpyAsync(a->gkeys, a->bk_keys, a->gcap * 8, cudaMemcpyDeviceToDevice, ctx->stream));
+  CUDA_TRY(cudaMemcpyAsync(a->gwords, a->bk_words, (a->gcap + 2) * a->n_gwords * 8, cudaMemcpyDeviceToDevice, ctx->stream));
+  return LLKV_OK;
+}
+
+// grows the global group table (x4) and rehashes the current contents into it
+static int32_t agg_grow_table(llkv_gpu_agg* a) {
+  llkv_gpu_ctx* ctx = a->ctx;
+  u64* old_keys = a->gkeys;
+  u64* old_words = a->gwords;
+  const u64 old_cap = a->gcap;
+  a->gkeys = nullptr;
+  a->gwords = nullptr;
+  int32_t rc = agg_alloc_table(a, old_cap * 4);
+  if (rc) return rc;
+  Plan mp = a->cr.plan;
+  mp.gkeys = a->gkeys;
+  mp.gwords = a->gwords;
+  mp.gcap = a->gcap;
+  mp.flags = a->d_flags;
+  CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+  memcpy(a->h_plan, &mp, sizeof(Plan));
+  CUDA_TRY(cudaMemcpyAsync(a->d_plan, a->h_plan, sizeof(Plan), cudaMemcpyHostToDevice, ctx->stream));
+  CUDA_TRY(launch_merge_table(a->d_plan, old_keys, old_words, old_cap, ctx->stream));
+  CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+  CUDA_TRY(cudaFree(old_keys));
+  CUDA_TRY(cudaFree(old_words));
+  return LLKV_OK;
+}
+
+static int32_t agg_launch(llkv_gpu_agg* a, const llkv_gpu_program* prog, int apply_mvcc, uint64_t row_begin, uint64_t row_end,
+                          bool force_wide) {
+  llkv_gpu_ctx* ctx = a->ctx;
+  CompileRequest req;
+  std::vector<llkv_gpu_column*> handles;
+  uint64_t table_rows = 0;
+  int32_t rc = build_request(ctx, a->table_id, prog, apply_mvcc, req, handles, &table_rows);
+  if (rc) return rc;
+  if (row_end > table_rows) return set_error(LLKV_ERR_INVALID_ARGUMENT, "row_end %llu beyond the table's %llu rows", (unsigned long long)row_end, (unsigned long long)table_rows);
+  req.specs = a->specs.data();
+  req.n_aggs = (int32_t)a->specs.size();
+  req.agg_nodes = a->nodes.data();
+  req.n_agg_nodes = (int32_t)a->nodes.size();
+  req.key_fields = a->keys;
+  req.expr_mode = a->expr_mode;
+  req.force_wide = force_wide || ctx->tune_force_wide != 0;
+  if ((rc = compile_plan(req, a->cr))) return set_error(rc, "%s", a->cr.error.c_str());
+  if ((rc = agg_freeze_layout(a, a->cr))) return rc;
+  Plan& p = a->cr.plan;
+  Geometry g;
+  if ((rc = plan_geometry(ctx, p, a->cr.wide, row_begin, row_end, a->hint, g))) return rc;
+  p.gkeys = a->gkeys;
+  p.gwords = a->gwords;
+  p.gcap = a->gcap;
+  p.flags = a->d_flags;
+  const bool need_backup = a->cr.can_narrow_fail || p.n_keys != 0;
+  if (need_backup && (rc = agg_backup(a))) return rc;
+  a->pending.has_backup = need_backup;
+  // per-thread i64 partial sums stay exact while a thread folds < 2^15 rows per launch: split very long scans
+  const u64 threads = (u64)g.grid * g.block;
+  const u64 max_rows_per_launch = threads * 32000ull;
+  a->pending.timed = ctx->timing;
+  if (ctx->timing) CUDA_TRY(cudaEventRecord(ctx->ev0, ctx->stream));
+  uint32_t launches = 0;
+  for (u64 rb = row_begin; rb < row_end || (rb == row_begin && launches == 0); rb += max_rows_per_launch) {
+    const u64 re = std::min<u64>(row_end, rb + max_rows_per_launch);
+    Plan lp = p;
+    lp.row_begin = rb;
+    lp.row_end = re;
+    lp.first_tile = rb / p.tile_rows;
+    lp.n_tiles = re > rb ? (re + p.tile_rows - 1) / p.tile_rows - lp.first_tile : 0;
+    if (lp.n_tiles == 0) break;
+    if (launches) CUDA_TRY(cudaStreamSynchronize(ctx->stream));  // h_plan is reused
+    memcpy(a->h_plan, &lp, sizeof(Plan));
+    CUDA_TRY(cudaMemcpyAsync(a->d_plan, a->h_plan, sizeof(Plan), cudaMemcpyHostToDevice, ctx->stream));
+    u64 grid = std::min<u64>(g.grid, lp.n_tiles);
+    CUDA_TRY(launch_scan(a->d_plan, a->cr.wide, (int)g.R, (uint32_t)grid, g.block, g.smem, ctx->stream));
+    ++launches;
+    if (re >= row_end) break;
+  }
+  if (ctx->timing) CUDA_TRY(cudaEventRecord(ctx->ev1, ctx->stream));
+  CUDA_TRY(cudaMemcpyAsync(a->h_flags, a->d_flags, 4, cudaMemcpyDeviceToHost, ctx->stream));
+  a->info.rows = row_end - row_begin;
+  a->info.kernel_launches = launches;
+  a->info.used_wide_path = a->cr.wide ? 1 : 0;
+  a->info.algorithmic_bytes_per_row = a->cr.algorithmic_bytes_per_row;
+  a->info.physical_bytes_per_row = a->cr.physical_bytes_per_row;
+  a->info.grid = g.grid;
+  a->info.block = g.block;
+  a->info.rows_per_tile = p.tile_rows;
+  a->info.stages = p.stages;
+  a->info.smem_bytes = g.smem;
+  a->info.fast_groups = p.fast_groups;
+  return LLKV_OK;
+}
+
+static int32_t agg_fail(llkv_gpu_agg* a, int32_t code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  a->err_code = code;
+  a->err_msg = buf;
+  return set_error(code, "%s", buf);
+}
+
+// waits for the outstanding run and settles it: reruns on the 128-bit interpreter / a larger group table when the
+// device asked for it, and turns device error flags into the reference's errors
+static int32_t agg_resolve(llkv_gpu_agg* a) {
+  llkv_gpu_ctx* ctx = a->ctx;
+  if (!a->pending.active) return LLKV_OK;
+  for (int guard = 0; guard < 24; ++guard) {
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    if (a->pending.timed) {
+      float ms = 0;
+      if (cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1) == cudaSuccess) a->info.last_kernel_ms = ms;
+      else cudaGetLastError();
+    }
+    const uint32_t flags = *a->h_flags;
+    if (flags == 0) break;
+    CUDA_TRY(cudaMemsetAsync(a->d_flags, 0, 4, ctx->stream));
+    *a->h_flags = 0;
+    const bool narrow_fail = (flags & FLAG_NARROW_FAIL) && !a->pending.wide;
+    const bool table_full = (flags & FLAG_TABLE_FULL) != 0;
+    if (narrow_fail || table_full) {
+      if (!a->pending.has_backup) return agg_fail(a, LLKV_ERR_INTERNAL, "device asked for a rerun without a saved state");
+      int32_t rc = agg_restore(a);
+      if (rc) return rc;
+      if (table_full && (rc = agg_grow_table(a))) return rc;
+      if (narrow_fail) a->pending.wide = true;
+      rc = agg_launch(a, a->pending.has_prog ? &a->pending.prog : nullptr, a->pending.apply_mvcc, a->pending.row_begin,
+                      a->pending.row_end, a->pending.wide);
+      if (rc) {
+        a->pending.active = false;
+        return rc;
+      }
+      continue;
+    }
+    a->pending.active = false;
+    if (flags & FLAG_BAD_PLAN) return agg_fail(a, LLKV_ERR_INTERNAL, "device interpreter met an unknown instruction");
+    if (flags & FLAG_TYPE_ERROR) {
+      for (const AggLayout& L : a->cr.aggs)
+        if (L.raise_code) return agg_fail(a, L.raise_code, "%s", L.raise_message.c_str());
+      return agg_fail(a, LLKV_ERR_INTERNAL, "aggregate argument type error");
+    }
+    if (flags & FLAG_DIV_ZERO) return agg_fail(a, LLKV_ERR_INTERNAL, "Divide by zero error");
+    if (flags & FLAG_ARITH_OVERFLOW) return agg_fail(a, LLKV_ERR_INTERNAL, "Arithmetic overflow: Overflow happened in an arrow-arith kernel");
+    if (flags & FLAG_EXACT_OVERFLOW) return agg_fail(a, LLKV_ERR_INVALID_ARGUMENT, "Decimal or integer overflow in an exact aggregate expression");
+    return agg_fail(a, LLKV_ERR_INTERNAL, "unexpected device status %u", flags);
+  }
+  a->pending.active = false;
+  return LLKV_OK;
+}
+
+extern "C" int32_t llkv_gpu_agg_reset(llkv_gpu_agg* a) {
+  if (!a) return set_error(LLKV_ERR_INVALID_ARGUMENT, "agg is NULL");
+  llkv_gpu_ctx* ctx = a->ctx;
+  CUDA_TRY(cudaSetDevice(ctx->device));
+  if (a->pending.active) {
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    a->pending.active = false;
+  }
+  a->err_code = 0;
+  a->err_msg.clear();
+  *a->h_flags = 0;
+  CUDA_TRY(cudaMemsetAsync(a->d_flags, 0, 4, ctx->stream));
+  if (a->frozen) CUDA_TRY(launch_init_table(a->gkeys, a->gwords, a->gcap + 2, a->n_gwords, a->d_gclass, ctx->stream));
+  return LLKV_OK;
+}
+
+extern "C" int32_t llkv_gpu_agg_run(llkv_gpu_agg* a, const llkv_gpu_program* prog, int32_t apply_mvcc, uint64_t row_begin,
+                                     uint64_t row_end) {
+  if (!a) return set_error(LLKV_ERR_INVALID_ARGUMENT, "agg is NULL");
+  if (row_end < row_begin) return set_error(LLKV_ERR_INVALID_ARGUMENT, "row_end < row_begin");
+  CUDA_TRY(cudaSetDevice(a->ctx->device));
+  if (a->err_code) return set_error(a->err_code, "%s", a->err_msg.c_str());
+  int32_t rc = agg_resolve(a);
+  if (rc) return rc;
+  a->pending.has_prog = prog != nullptr;
+  if (prog) {
+    a->pending.prog.ops = prog->ops;
+    a->pending.prog.literals = prog->literals;
+    a->pending.prog.nodes = prog->nodes;
+    a->pending.prog.list_roots = prog->list_roots;
+    a->pending.prog.bind();
+  }
+  a->pending.apply_mvcc = apply_mvcc;
+  a->pending.row_begin = row_begin;
+  a->pending.row_end = row_end;
+  a->pending.wide = false;
+  rc = agg_launch(a, prog, apply_mvcc, row_begin, row_end, false);
+  if (rc) return rc;
+  a->pending.wide = a->cr.wide;
+  a->pending.active = true;
+  return LLKV_OK;
+}
+
+extern "C" int32_t llkv_gpu_agg_run_info(const llkv_gpu_agg* a, llkv_run_info* out) {
+  if (!a || !out) return set_error(LLKV_ERR_INVALID_ARGUMENT, "NULL argument");
+  *out = a->info;
+  return LLKV_OK;
+}
+
+// ---- finalize -----------------------------------------------------------------------------------------------
+static void val_i64(llkv_agg_value* o, i64 v, int valid) {
+  memset(o, 0, sizeof(*o));
+  o->type = LLKV_PT_INT64;
+  o->lo = valid ? (uint64_t)v : 0;
+  o->valid = (uint8_t)valid;
+}
+static void val_f64(llkv_agg_value* o, double v, int valid) {
+  memset(o, 0, sizeof(*o));
+  o->type = LLKV_PT_FLOAT64;
+  if (valid) memcpy(&o->lo, &v, 8);
+  o->valid = (uint8_t)valid;
+}
+static void val_dec(llkv_agg_value* o, i128 v, int p, int s, int valid) {
+  memset(o, 0, sizeof(*o));
+  o->type = LLKV_PT_DECIMAL128;
+  o->precision = (uint8_t)p;
+  o->scale = (int8_t)s;
+  o->valid = (uint8_t)valid;
+  if (valid) {
+    o->lo = (uint64_t)(u128)v;
+    o->hi = (uint64_t)((u128)v >> 64);
+  }
+}
+static double dec_f64_bits(u64 e) {  // inverse of enc_f64
+  const u64 b = (e >> 63) ? (e & 0x7fffffffffffffffull) : ~e;
+  double d;
+  memcpy(&d, &b, 8);
+  return d;
+}
+// exact value of a limb-split integer sum; false when it does not fit in i128
+static bool limbs_value(const u64* w, int n_limbs, i128* out) {
+  if (n_limbs == 2) {
+    *out = (i128)(u128)w[0] + (((i128)(i64)w[1]) << 32);
+    return true;
+  }
+  u128 d0 = w[0];
+  u128 d1 = (u128)w[1] + (d0 >> 32);
+  d0 &= 0xffffffffull;
+  u128 d2 = (u128)w[2] + (d1 >> 32);
+  d1 &= 0xffffffffull;
+  const i128 top = (i128)(i64)w[3] + (i128)(d2 >> 32);
+  d2 &= 0xffffffffull;
+  if (top < -((i128)1 << 31) || top >= ((i128)1 << 31)) return false;
+  *out = (i128)(((u128)top << 96) | (d2 << 64) | (d1 << 32) | d0);
+  return true;
+}
+
+static int32_t finalize_group(llkv_gpu_agg* a, const u64* w, llkv_agg_value* out) {
+  const std::vector<AggLayout>& aggs = a->cr.aggs;
+  const u64 rows = w[0];
+  for (size_t i = 0; i < aggs.size(); ++i) {
+    const AggLayout& L = aggs[i];
+    llkv_agg_value* o = &out[i];
+    const u64 count = L.dead ? 0 : (L.w_count >= 0 ? w[L.w_count] : 0);
+    i128 total = 0;
+    if (L.all_null_group_is_error && rows > 0 && count == 0) return agg_fail(a, LLKV_ERR_INVALID_ARGUMENT, "Expected Decimal128 array");
+    switch (L.acc) {
+      case ACC_COUNT_STAR: val_i64(o, (i64)rows, 1); break;
+      case ACC_COUNT_COL: val_i64(o, (i64)count, 1); break;
+      case ACC_COUNT_NULLS: val_i64(o, (i64)(rows - count), 1); break;
+      case ACC_SUM_I64:
+        if (L.dead || count == 0) { val_i64(o, 0, 0); break; }
+        limbs_value(&w[L.w_val], 2, &total);
+        if (total < (i128)INT64_MIN || total > (i128)INT64_MAX) return agg_fail(a, LLKV_ERR_INVALID_ARGUMENT, "integer overflow");
+        val_i64(o, (i64)total, 1);
+        break;
+      case ACC_AVG_I64:
+        if (L.dead || count == 0) { val_f64(o, 0, 0); break; }
+        limbs_value(&w[L.w_val], 2, &total);
+        if (total < (i128)INT64_MIN || total > (i128)INT64_MAX) return agg_fail(a, LLKV_ERR_INVALID_ARGUMENT, "AVG aggregate sum exceeds i64 range");
+        val_f64(o, (double)(i64)total / (double)(i64)count, 1);
+        break;
+      case ACC_TOTAL_I64: case ACC_TOTAL_F64: {
+        double f = 0.0;
+        if (!L.dead) memcpy(&f, &w[L.w_val], 8);
+        val_f64(o, f, 1);
+        break;
+      }
+      case ACC_SUM_F64: {
+        double f = 0.0;
+        if (!L.dead) memcpy(&f, &w[L.w_val], 8);
+        val_f64(o, f, !L.dead && count > 0);
+        break;
+      }
+      case ACC_AVG_F64: {
+        double f = 0.0;
+        if (!L.dead) memcpy(&f, &w[L.w_val], 8);
+        val_f64(o, count > 0 ? f / (double)(i64)count : 0.0, !L.dead && count > 0);
+        break;
+      }
+      case ACC_MIN_I64: case ACC_MAX_I64:
+        if (L.dead || count == 0) val_i64(o, 0, 0);
+        else val_i64(o, (i64)(w[L.w_val] ^ 0x8000000000000000ull), 1);
+        break;
+      case ACC_MIN_F64: case ACC_MAX_F64: {
+        if (L.dead || w[L.w_first_valid] == ~0ull) { val_f64(o, 0, 0); break; }
+        // a leading NaN sticks: nothing compares Less/Greater than it (llkv-aggregate/src/lib.rs:1309-1331,1377-1399)
+        if (w[L.w_first_nan] == w[L.w_first_valid]) {
+          const u64 qnan = 0x7ff8000000000000ull;
+          double d;
+          memcpy(&d, &qnan, 8);
+          val_f64(o, d, 1);
+        } else {
+          val_f64(o, dec_f64_bits(w[L.w_val]), 1);
+        }
+        break;
+      }
+      case ACC_SUM_DEC: case ACC_TOTAL_DEC:
+        if (!limbs_value(&w[L.w_val], 4, &total))
+          return agg_fail(a, LLKV_ERR_INVALID_ARGUMENT, L.acc == ACC_TOTAL_DEC ? "Decimal128 total overflow" : "Decimal128 sum overflow");
+        val_dec(o, total, L.precision, L.scale, 1);  // always a value: 0 when no rows (lib.rs:1567-1582)
+        break;
+      case ACC_AVG_DEC: {
+        if (count == 0) { val_dec(o, 0, L.precision, L.scale, 0); break; }
+        if (!limbs_value(&w[L.w_val], 4, &total)) return agg_fail(a, LLKV_ERR_INVALID_ARGUMENT, "Decimal128 sum overflow");
+        const i128 c = (i128)count;
+        i128 avg = total / c;
+        const i128 rem = total % c;
+        const i128 ar = rem < 0 ? -rem : rem;
+        if (ar * 2 >= c) {  // round half away from zero (lib.rs:1731-1742)
+          if (total > 0) avg += 1;
+          else avg -= 1;
+        }
+        val_dec(o, avg, L.precision, L.scale, 1);
+        break;
+      }
+      case ACC_MIN_DEC: case ACC_MAX_DEC:
+        if (count == 0) val_dec(o, 0, L.precision, L.scale, 0);
+        else {
+          const u64 hi = w[L.w_val] ^ 0x8000000000000000ull, lo = w[L.w_val + 1];
+          val_dec(o, (i128)(((u128)hi << 64) | lo), L.precision, L.scale, 1);
+        }
+        break;
+      default: return agg_fail(a, LLKV_ERR_INTERNAL, "unknown accumulator %d", L.acc);
+    }
+  }
+  return LLKV_OK;
+}
+
+static void decode_keys(const llkv_gpu_agg* a, u64 K, bool null_slot, llkv_group_key* out) {
+  const std::vector<KeyLayout>& keys = a->cr.keys;
+  const Plan& p = a->cr.plan;
+  int shift = 0;
+  for (size_t k = 0; k < keys.size(); ++k) {
+    const KeyLayout& kl = keys[k];
+    llkv_group_key* o = &out[k];
+    memset(o, 0, sizeof(*o));
+    o->type = kl.type;
+    if (p.single_wide_key) {
+      o->valid = null_slot ? 0 : 1;
+      o->bits = null_slot ? 0 : K;
+      if (kl.type == LLKV_PT_BOOLEAN && o->valid) o->bits = o->bits != 0;
+      continue;
+    }
+    const u64 field = kl.bits == 64 ? (K >> shift) : ((K >> shift) & ((1ull << kl.bits) - 1));
+    shift += kl.bits;
+    bool isnull = false;
+    if (kl.nullable) {
+      isnull = (K >> shift) & 1;
+      shift += 1;
+    }
+    o->valid = isnull ? 0 : 1;
+    if (isnull) continue;
+    if (kl.kind == KK_STR) {
+      const int L = kl.strlen;
+      const u64 len = field & 7, bytes = field >> 3;
+      o->bits = (L ? (bytes << (64 - 8 * L)) : 0ull) | len;
+    } else {
+      u64 v = field + kl.min;
+      // without statistics the field holds the low bits of the sign-extended value
+      if (kl.min == 0 && kl.is_signed && kl.bits < 64 && kl.bits == 8 * prim_type_width(kl.type) && ((v >> (kl.bits - 1)) & 1))
+        v |= ~0ull << kl.bits;
+      o->bits = kl.type == LLKV_PT_BOOLEAN ? (u64)(v != 0) : v;
+    }
+  }
+}
+
+struct GroupRef {
+  u64 slot, first_row;
+};
+
+static int32_t agg_collect(llkv_gpu_agg* a, std::vector<u64>& hk, std::vector<u64>& hw, std::vector<GroupRef>& groups) {
+  llkv_gpu_ctx* ctx = a->ctx;
+  const u64 rows = a->gcap + 2;
+  hk.resize(a->gcap);
+  hw.resize(rows * a->n_gwords);
+  CUDA_TRY(cudaMemcpyAsync(hw.data(), a->gwords, hw.size() * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  if (a->cr.plan.n_keys) CUDA_TRY(cudaMemcpyAsync(hk.data(), a->gkeys, hk.size() * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+  groups.clear();
+  if (a->cr.plan.n_keys == 0) {
+    groups.push_back(GroupRef{0, 0});
+    return LLKV_OK;
+  }
+  for (u64 s = 0; s < rows; ++s) {
+    const bool occupied = s < a->gcap ? hk[s] != kEmptyKey : hw[s * a->n_gwords] != 0;
+    if (!occupied) continue;
+    groups.push_back(GroupRef{s, hw[s * a->n_gwords + 1]});
+  }
+  // first-appearance order of the groups (llkv-executor/src/lib.rs:5064-5089)
+  std::sort(groups.begin(), groups.end(), [](const GroupRef& x, const GroupRef& y) { return x.first_row < y.first_row; });
+  return LLKV_OK;
+}
+
+static int32_t agg_ensure_layout(llkv_gpu_agg* a) {
+  if (a->frozen) return LLKV_OK;
+  // finalize before any run: compile against the table to learn the layout, with an empty scan
+  int32_t rc = agg_launch(a, nullptr, 0, 0, 0, false);
+  if (rc) return rc;
+  CUDA_TRY(cudaStreamSynchronize(a->ctx->stream));
+  return LLKV_OK;
+}
+
+extern "C" int32_t llkv_gpu_agg_group_count(llkv_gpu_agg* a, uint64_t* out_groups) {
+  if (!a || !out_groups) return set_error(LLKV_ERR_INVALID_ARGUMENT, "NULL argument");
+  CUDA_TRY(cudaSetDevice(a->ctx->device));
+  if (a->err_code) return set_error(a->err_code, "%s", a->err_msg.c_str());
+  int32_t rc = agg_resolve(a);
+  if (rc) return rc;
+  if ((rc = agg_ensure_layout(a))) return rc;
+  std::vector<u64> hk, hw;
+  std::vector<GroupRef> groups;
+  if ((rc = agg_collect(a, hk, hw, groups))) return rc;
+  *out_groups = groups.size();
+  return LLKV_OK;
+}
+
+extern "C" int32_t llkv_gpu_agg_finalize(llkv_gpu_agg* a, llkv_agg_value* out_values, llkv_group_key* out_keys, uint64_t group_capacity,
+                                          uint64_t* out_groups) {
+  if (!a) return set_error(LLKV_ERR_INVALID_ARGUMENT, "agg is NULL");
+  CUDA_TRY(cudaSetDevice(a->ctx->device));
+  if (a->err_code) return set_error(a->err_code, "%s", a->err_msg.c_str());
+  int32_t rc = agg_resolve(a);
+  if (rc) return rc;
+  if ((rc = agg_ensure_layout(a))) return rc;
+  std::vector<u64> hk, hw;
+  std::vector<GroupRef> groups;
+  if ((rc = agg_collect(a, hk, hw, groups))) return rc;
+  if (groups.size() > group_capacity)
+    return set_error(LLKV_ERR_INVALID_ARGUMENT, "group capacity %llu < %llu groups", (unsigned long long)group_capacity, (unsigned long long)groups.size());
+  const size_t n_aggs = a->specs.size(), n_keys = a->keys.size();
+  if ((n_aggs && !out_values) || (n_keys && !out_keys)) return set_error(LLKV_ERR_INVALID_ARGUMENT, "output buffer is NULL");
+  for (size_t gi = 0; gi < groups.size(); ++gi) {
+    const u64 s = groups[gi].slot;
+    if ((rc = finalize_group(a, &hw[s * a->n_gwords], out_values + gi * n_aggs))) return rc;
+    if (n_keys) {
+      const bool null_slot = s == a->gcap + 1;
+      const u64 K = s < a->gcap ? hk[s] : kEmptyKey;
+      decode_keys(a, K, null_slot, out_keys + gi * n_keys);
+    }
+  }
+  if (out_groups) *out_groups = groups.size();
+  return LLKV_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ multi-GPU
+extern "C" int32_t llkv_gpu_comm_unique_id(uint8_t out_id[LLKV_GPU_UNIQUE_ID_BYTES]) {
+  if (!out_id) return set_error(LLKV_ERR_INVALID_ARGUMENT, "out_id is NULL");
+  int32_t rc = load_nccl();
+  if (rc) return rc;
+  NCCL_TRY(g_nccl.get_unique_id(out_id));
+  return LLKV_OK;
+}
+
+extern "C" int32_t llkv_gpu_comm_init(llkv_gpu_ctx* ctx, const uint8_t id[LLKV_GPU_UNIQUE_ID_BYTES], int32_t n_ranks, int32_t rank) {
+  if (!ctx || !id) return set_error(LLKV_ERR_INVALID_ARGUMENT, "NULL argument");
+  if (n_ranks < 1 || rank < 0 || rank >= n_ranks) return set_error(LLKV_ERR_INVALID_ARGUMENT, "bad rank %d of %d", rank, n_ranks);
+  int32_t rc = load_nccl();
+  if (rc) return rc;
+  CUDA_TRY(cudaSetDevice(ctx->device));
+  if (ctx->nccl_comm) {
+    g_nccl.comm_destroy(ctx->nccl_comm);
+    ctx->nccl_comm = nullptr;
+  }
+  NcclIdByValue v;
+  memcpy(v.internal, id, 128);
+  NCCL_TRY(g_nccl.comm_init_rank(&ctx->nccl_comm, n_ranks, v, rank));
+  ctx->n_ranks = n_ranks;
+  ctx->rank = rank;
+  return LLKV_OK;
+}
+
+extern "C" int32_t llkv_gpu_comm_destroy(llkv_gpu_ctx* ctx) {
+  if (!ctx) return set_error(LLKV_ERR_INVALID_ARGUMENT, "ctx is NULL");
+  if (ctx->nccl_comm && g_nccl.comm_destroy) {
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    g_nccl.comm_destroy(ctx->nccl_comm);
+  }
+  ctx->nccl_comm = nullptr;
+  ctx->n_ranks = 1;
+  ctx->rank = 0;
+  return LLKV_OK;
+}
+
+// Every rank gathers every rank's partial table (allgather over NVLink) and folds them in rank order into a fresh
+// table, so all ranks end with bit-identical states (f64 sums included).
+extern "C" int32_t llkv_gpu_agg_merge(llkv_gpu_agg* a) {
+  if (!a) return set_error(LLKV_ERR_INVALID_ARGUMENT, "agg is NULL");
+  llkv_gpu_ctx* ctx = a->ctx;
+  CUDA_TRY(cudaSetDevice(ctx->device));
+  if (a->err_code) return set_error(a->err_code, "%s", a->err_msg.c_str());
+  int32_t rc = agg_resolve(a);
+  if (rc) return rc;
+  if ((rc = agg_ensure_layout(a))) return rc;
+  if (!ctx->nccl_comm || ctx->n_ranks == 1) return LLKV_OK;
+  const int N = ctx->n_ranks;
+  const int nccl_u64 = 5 /* ncclUint64 */, nccl_max = 2 /* ncclMax */;
+  // all ranks must use one table size: agree on the largest
+  u64* d_cap = nullptr;
+  CUDA_TRY(cudaMalloc((void**)&d_cap, 8));
+  u64 cap = a->gcap;
+  CUDA_TRY(cudaMemcpyAsync(d_cap, &cap, 8, cudaMemcpyHostToDevice, ctx->stream));
+  NCCL_TRY(g_nccl.all_reduce(d_cap, d_cap, 1, nccl_u64, nccl_max, ctx->nccl_comm, ctx->stream));
+  CUDA_TRY(cudaMemcpyAsync(&cap, d_cap, 8, cudaMemcpyDeviceToHost, ctx->stream));
+  CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+  CUDA_TRY(cudaFree(d_cap));
+  while (a->gcap < cap)
+    if ((rc = agg_grow_table(a))) return rc;
+  const u64 rows = a->gcap + 2;
+  const size_t key_elems = (size_t)a->gcap, word_elems = (size_t)(rows * a->n_gwords);
+  u64 *all_keys = nullptr, *all_words = nullptr;
+  CUDA_TRY(cudaMalloc((void**)&all_keys, key_elems * 8 * (size_t)N));
+  CUDA_TRY(cudaMalloc((void**)&all_words, word_elems * 8 * (size_t)N));
+  NCCL_TRY(g_nccl.all_gather(a->gkeys, all_keys, key_elems, nccl_u64, ctx->nccl_comm, ctx->stream));
+  NCCL_TRY(g_nccl.all_gather(a->gwords, all_words, word_elems, nccl_u64, ctx->nccl_comm, ctx->stream));
+  CUDA_TRY(launch_init_table(a->gkeys, a->gwords, rows, a->n_gwords, a->d_gclass, ctx->stream));
+  Plan mp = a->cr.plan;
+  mp.gkeys = a->gkeys;
+  mp.gwords = a->gwords;
+  mp.gcap = a->gcap;
+  mp.flags = a->d_flags;
+  CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+  memcpy(a->h_plan, &mp, sizeof(Plan));
+  CUDA_TRY(cudaMemcpyAsync(a->d_plan, a->h_plan, sizeof(Plan), cudaMemcpyHostToDevice, ctx->stream));
+  const u64 src_cap = a->gcap;
+  for (int attempt = 0; attempt < 16; ++attempt) {
+    for (int r = 0; r < N; ++r)
+      CUDA_TRY(launch_merge_table(a->d_plan, all_keys + (size_t)r * key_elems, all_words + (size_t)r * word_elems, src_cap, ctx->stream));
+    CUDA_TRY(cudaMemcpyAsync(a->h_flags, a->d_flags, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    if (!(*a->h_flags & FLAG_TABLE_FULL)) break;
+    // the union of the ranks' groups outgrew the table: a larger, empty one, and fold everything again
+    *a->h_flags = 0;
+    CUDA_TRY(cudaMemsetAsync(a->d_flags, 0, 4, ctx->stream));
+    CUDA_TRY(cudaFree(a->gkeys));
+    CUDA_TRY(cudaFree(a->gwords));
+    a->gkeys = a->gwords = nullptr;
+    if ((rc = agg_alloc_table(a, a->gcap * 4))) return rc;
+    mp.gkeys = a->gkeys;
+    mp.gwords = a->gwords;
+    mp.gcap = a->gcap;
+    memcpy(a->h_plan, &mp, sizeof(Plan));
+    CUDA_TRY(cudaMemcpyAsync(a->d_plan, a->h_plan, sizeof(Plan), cudaMemcpyHostToDevice, ctx->stream));
+  }
+  CUDA_TRY(cudaFree(all_keys));
+  CUDA_TRY(cudaFree(all_words));
+  return LLKV_OK;
+}

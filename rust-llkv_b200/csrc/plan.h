@@ -1,0 +1,173 @@
+// plan.h — the compiled scan plan shared by the host compiler (compiler.cpp) and the device interpreter
+// (scan_kernel.cu).  One Plan = one fused pass: stage column tiles -> predicate program -> MVCC rule ->
+// projection arithmetic -> aggregate update, all in registers/shared memory, every column read once.
+#pragma once
+#include <stdint.h>
+
+namespace llkv {
+
+constexpr int kMaxCols = 24;
+constexpr int kMaxInstr = 320;
+constexpr int kMaxLits = 96;
+constexpr int kMaxNoncommitted = 32;
+constexpr int kMaxKeys = 8;
+constexpr int kMaxWords = 96;          // accumulator words per group row
+constexpr int kMaxStackDepth = 12;     // value stack (2 cached in registers + spill slots in shared memory)
+constexpr uint32_t kPadRows = 4096;    // column allocations are padded to this many rows (bulk copies never run off the end)
+constexpr unsigned long long kEmptyKey = ~0ull;
+
+// ---- opcodes of the per-row stack machine -------------------------------------------------------------
+// Value classes: I = signed integer <= 64 bit (sign-extended), U = unsigned 64, F = f64 bits, D = Decimal128
+// (i128; i64 in the narrow interpreter), B = predicate result (bit0 = rows bit T, NULL flag = not in domain).
+enum Op : uint16_t {
+  OP_END = 0,
+  OP_PUSH_COL,   // a = column index, b = LoadKind
+  OP_PUSH_LIT,   // c = literal index, b = 1 -> NULL literal
+  OP_PICK,       // a = depth below top (0 = dup)
+  OP_POP,
+  OP_NIP,        // drop the entry below the top
+  // arrow-arith checked integer ops (llkv-compute/src/kernels.rs:112-137)
+  OP_ADD_I, OP_SUB_I, OP_MUL_I, OP_DIV_I, OP_MOD_I,
+  OP_ADD_F, OP_SUB_F, OP_MUL_F, OP_DIV_F, OP_MOD_F,
+  // Decimal128: b = 1 -> exact mode (DecimalValue::new precision <= 38 check, scalar/decimal.rs:128-170)
+  OP_ADD_D, OP_SUB_D, OP_MUL_D,
+  // casts (arrow-cast, safe mode: failure -> NULL)
+  OP_CAST_I_F, OP_CAST_U_F,
+  OP_CAST_D_F,     // c = literal index holding 10^scale as f64
+  OP_CAST_I_D,     // a = scale (multiply by 10^a), b = precision, c = 1: the integer is unsigned
+  OP_CAST_D_UP,    // a = k, b = precision: x * 10^k
+  OP_CAST_D_DOWN,  // a = k, b = precision: x / 10^k rounded half away from zero
+  OP_CAST_F_I,
+  OP_CAST_I_I,     // a = bits
+  OP_CAST_U_I, OP_CAST_I_U, OP_CAST_I_B,
+  OP_RESCALE_DX,   // a = k: exact-mode rescale up, overflow -> error (scalar/decimal.rs:30-48)
+  // compare -> B (arrow-ord: floats by total order).  a = CompareOp
+  OP_CMP_I, OP_CMP_U, OP_CMP_F, OP_CMP_D,
+  // typed predicates against literals (llkv-expr/src/typed_predicate.rs:75-142). a = lower_kind | upper_kind<<2 | eq<<4,
+  // c = literal index (lower, then upper)
+  OP_PRED_I, OP_PRED_U, OP_PRED_F, OP_PRED_D,
+  OP_IN_BITS,    // b = count, c = first literal (I/U/short-string/bool: bit equality)
+  OP_IN_F, OP_IN_D,
+  OP_PRED_ISNULL, OP_PRED_NOTNULL, OP_PRED_ALL,  // leaf IsNull / IsNotNull / Range(Unbounded,Unbounded): domain = field present
+  OP_ISNULL,     // Expr::IsNull{expr,negated}: a = negated; domain = all rows
+  OP_INLIST_FOLD, // pops item-compare result into the (matched, saw_null) accumulator below it: internal to PushInList
+  OP_INLIST_END,  // a = negated; also folds the NULL flag of the IN target below the accumulator and drops the target
+  OP_AND, OP_OR, OP_NOT,
+  OP_BOOL_LIT,   // a = value
+  OP_FILTER,     // pop B: active &= T.  a bit0 = the warp may stop when no row is active (nothing later can raise an error)
+  OP_SELECT_DONE, // end of the selection phase: from here on errors count for selected rows only
+  OP_RAISE,      // a = FLAG_* bit index: raised when any row is still active (errors the reference raises at update time)
+  OP_MVCC,       // a = created_by column, b = deleted_by column
+  OP_GROUP,      // a = number of keys on the stack (packed per Plan::key_*)
+  // aggregates. a bit0 = keep the value on the stack; b = fast (per-thread) word; c = global word offset
+  OP_AGG_COUNT_STAR, OP_AGG_COUNT,
+  OP_AGG_SUM_I, OP_AGG_SUM_D, OP_AGG_FSUM,
+  OP_AGG_MIN_I, OP_AGG_MAX_I, OP_AGG_MIN_U, OP_AGG_MAX_U, OP_AGG_MIN_F, OP_AGG_MAX_F, OP_AGG_MIN_D, OP_AGG_MAX_D,
+  OP_AGG_FIRSTROW, // MIN over the row index (first-appearance order of groups)
+  OP_AGG_FIRSTVALID, // MIN over the row index of non-NULL values (keeps the value)
+  OP_AGG_FIRSTNAN,   // MIN over the row index of NaN values (keeps the value): MinFloat64/MaxFloat64 leading-NaN rule
+  OP_EMIT_BITMAP,
+  OP_COUNT_
+};
+
+enum KeyKind : uint8_t { KK_INT = 0, KK_STR = 1 };
+enum LoadKind : uint8_t { LK_I8, LK_I16, LK_I32, LK_I64, LK_U8, LK_U16, LK_U32, LK_U64, LK_F32, LK_F64, LK_D128, LK_STR8 };
+
+// classes of accumulator words: how a word is initialised, merged across CTAs / launches / ranks
+enum WordClass : uint8_t {
+  WC_SUM = 0, WC_MIN = 1, WC_MAX = 2, WC_FSUM = 3,
+  WC_MIN128 = 4, WC_MAX128 = 5,          // high word (order-preserving) of a 128-bit min/max pair; the next word is the low half
+  WC_PAIR_LO_MIN = 6, WC_PAIR_LO_MAX = 7
+};
+
+// how a per-thread fast word is folded into the global words at the end of the kernel
+enum FastKind : uint8_t {
+  FK_COUNT = 0,   // u64 count            -> 1 WC_SUM word
+  FK_SUM_I64,     // i64 narrow sum       -> L0, L1, NEG64       (value = L0 + L1*2^32 - NEG64*2^64)
+  FK_SUM_I128,    // i64 narrow sum       -> L0..L3, NEG128      (value = sum L_k 2^(32k) - NEG128*2^128)
+  FK_FSUM,        // f64 sum              -> 1 WC_FSUM word
+  FK_MIN, FK_MAX, // order-preserving u64 -> 1 WC_MIN / WC_MAX word
+  FK_MIN128_HI, FK_MAX128_HI, // two fast words (hi, lo) -> two global words, merged with a 128-bit CAS
+  FK_SKIP         // second word of a 128-bit pair
+};
+
+struct Instr {
+  uint16_t op;
+  uint8_t a, b;
+  uint32_t c;
+};
+
+struct Lit {
+  unsigned long long lo, hi;
+};
+
+struct ColDesc {
+  const void* base;              // device values buffer (Arrow layout, little endian)
+  const unsigned char* validity; // device validity bitmap (LSB first) or null
+  uint32_t elem_bytes;           // 1,2,4,8,16
+  uint32_t smem_off;             // byte offset of this column's tile inside a stage
+  uint32_t vsmem_off;            // byte offset of the validity tile inside a stage
+  uint32_t _pad;
+};
+
+struct FastWord {
+  uint8_t kind;       // FastKind
+  uint8_t _pad[3];
+  uint32_t gword;     // first global word it folds into
+};
+
+struct Plan {
+  // ---- program
+  uint32_t n_instr, n_cols, n_lits, max_depth;
+  Instr code[kMaxInstr];
+  Lit lits[kMaxLits];
+  ColDesc cols[kMaxCols];
+  // ---- MVCC snapshot (llkv-transaction/src/mvcc.rs:282-334,414-419)
+  unsigned long long txn_id, snapshot_id;
+  uint32_t n_noncommitted, _pad0;
+  unsigned long long noncommitted[kMaxNoncommitted];
+  // ---- group keys: each key value is reduced to key_bits[k] bits (+1 null bit when key_nullable) and packed
+  uint32_t n_keys;
+  uint32_t single_wide_key;       // 1: one 64-bit key, K = value, NULL key -> dedicated slot
+  uint8_t key_bits[kMaxKeys];
+  uint8_t key_nullable[kMaxKeys];
+  uint8_t key_kind[kMaxKeys];     // KeyKind
+  uint8_t key_strlen[kMaxKeys];   // KK_STR: longest string in the column (<= 7)
+  unsigned long long key_min[kMaxKeys];  // KK_INT: subtracted before packing (column minimum)
+  // ---- accumulators
+  uint32_t n_fast_words;          // per-thread words per CTA-local group
+  uint32_t n_gwords;              // words per global group row
+  FastWord fast[kMaxWords];
+  uint8_t gword_class[kMaxWords]; // WordClass per global word
+  // ---- launch geometry
+  unsigned long long row_begin, row_end;
+  unsigned long long first_tile, n_tiles;  // tiles are tile_rows-aligned from row 0
+  uint32_t tile_rows;             // blockDim.x * R
+  uint32_t stages;                // >= 2 when staged
+  uint32_t staged;                // 1: cp.async.bulk tiles into shared memory; 0: direct global loads
+  uint32_t stage_bytes;           // stride between stages in shared memory
+  uint32_t tx_bytes;              // bytes one tile's bulk copies deliver (mbarrier expect_tx)
+  uint32_t fast_groups;           // CTA-local group slots with per-thread accumulators (power of two, 0 = none)
+  uint32_t bitmap_mode;           // 1: OP_EMIT_BITMAP present -> never skip inactive warps
+  // shared-memory layout (byte offsets from the dynamic smem base; all 128-byte aligned)
+  uint32_t smem_plan_off, smem_bar_off, smem_stage_off, smem_acc_off, smem_spill_off, smem_tbl_off, smem_total;
+  // ---- global state
+  unsigned long long* gkeys;      // [gcap] open addressing, kEmptyKey = free; group rows gcap (key == kEmptyKey) and gcap+1 (NULL key)
+  unsigned long long* gwords;     // [(gcap+2) * n_gwords]
+  unsigned long long gcap;        // power of two (1 for ungrouped: row 0)
+  uint32_t* flags;                // device status word (FLAG_*)
+  unsigned long long* out_bitmap; // bitmap_mode: bit i = row_begin + i  (32-bit words written)
+  unsigned long long* out_count;  // bitmap_mode: number of selected rows
+};
+
+enum : uint32_t {
+  FLAG_NARROW_FAIL = 1u << 0,      // the 64-bit interpreter met a value that needs 128 bits: rerun wide
+  FLAG_ARITH_OVERFLOW = 1u << 1,   // arrow-arith checked op overflowed on a selected row
+  FLAG_DIV_ZERO = 1u << 2,
+  FLAG_EXACT_OVERFLOW = 1u << 3,   // exact-mode decimal op overflowed / exceeded 38 digits
+  FLAG_TABLE_FULL = 1u << 4,       // global group table is full
+  FLAG_BAD_PLAN = 1u << 5,
+  FLAG_TYPE_ERROR = 1u << 6        // OP_RAISE: aggregate argument of a type the accumulator rejects, met on a selected row
+};
+
+}  // namespace llkv

@@ -1,0 +1,418 @@
+"""ctypes binding of libllkv_gpu.so (include/llkv_gpu.h) + the host-side mirror of the reference's call shape.
+
+`DeviceTable` stands where a `Table` backed by a `ColumnStore` stands in the reference (llkv-table/src/table.rs:231-490):
+chunks are appended column by column (`ColumnStore::append`, llkv-column-map/src/store/core.rs:787), then
+`filter_row_ids` / aggregate scans run against it (llkv-executor/src/lib.rs:5357-5682, 4405-4542).
+
+There is NO CPU fallback: importing works anywhere, but `Context()` raises `LlkvError(Io)` without a CUDA device and
+`load()` raises if the CUDA library has not been built.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import numpy as np
+
+from . import ffi
+from .expr import (AggregateSpec, AggregateValue, Expr, ProgramCompiler, decode_group_key, flatten_aggregates)
+from .table import HostColumn, HostTable, LlkvError, Snapshot
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(os.path.dirname(_HERE), "csrc", "libllkv_gpu.so")
+
+# LogicalStorageNamespace (llkv-types/src/ids.rs:20-62)
+NS_USER, NS_ROW_ID_SHADOW, NS_TXN_CREATED_BY, NS_TXN_DELETED_BY = 0, 1, 2, 3
+# chunk sizes the reference's append path produces (llkv-column-map/src/store/constants.rs:14-28, slicing.rs:33-43,155-166)
+TARGET_CHUNK_BYTES = 1 << 20
+VARWIDTH_FALLBACK_ROWS = 4096
+
+_lib = None
+
+
+def load():
+    """dlopens libllkv_gpu.so; raises if it is missing (the product path has no other implementation)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(f"{LIB_PATH} is missing: build it with rust-llkv_b200/csrc/build.sh (there is no CPU fallback)")
+    lib = C.CDLL(LIB_PATH)
+    P = C.POINTER
+    vp, u64, i32, u8, i8 = C.c_void_p, C.c_uint64, C.c_int32, C.c_uint8, C.c_int8
+    sig = {
+        "llkv_gpu_abi_version": (i32, []),
+        "llkv_gpu_last_error": (C.c_size_t, [C.c_char_p, C.c_size_t]),
+        "llkv_gpu_device_count": (i32, []),
+        "llkv_gpu_ctx_create": (i32, [i32, i32, u64, P(vp)]),
+        "llkv_gpu_ctx_destroy": (None, [vp]),
+        "llkv_gpu_ctx_synchronize": (i32, [vp]),
+        "llkv_gpu_ctx_stream": (i32, [vp, P(vp)]),
+        "llkv_gpu_ctx_set_timing": (i32, [vp, i32]),
+        "llkv_gpu_ctx_set_tuning": (i32, [vp, i32, i32, i32, i32, i32]),
+        "llkv_gpu_host_alloc": (i32, [u64, P(vp)]),
+        "llkv_gpu_host_free": (i32, [vp]),
+        "llkv_gpu_column_register": (i32, [vp, u64, i32, u8, i8, P(vp)]),
+        "llkv_gpu_column_reserve": (i32, [vp, u64]),
+        "llkv_gpu_column_append_chunk": (i32, [vp, u64, vp, u64, vp, vp, u64, vp]),
+        "llkv_gpu_column_append_blob": (i32, [vp, u64, vp, u64, vp, u64]),
+        "llkv_gpu_column_seal": (i32, [vp]),
+        "llkv_gpu_column_rows": (i32, [vp, P(u64)]),
+        "llkv_gpu_column_clear": (i32, [vp]),
+        "llkv_gpu_column_destroy": (i32, [vp]),
+        "llkv_gpu_program_compile": (i32, [vp, vp, i32, vp, i32, vp, i32, vp, i32, P(vp)]),
+        "llkv_gpu_program_destroy": (None, [vp]),
+        "llkv_gpu_mvcc_set": (i32, [vp, u64, vp, vp, u64, u64, vp, i32]),
+        "llkv_gpu_mvcc_clear": (i32, [vp, u64]),
+        "llkv_gpu_filter_bitmap": (i32, [vp, u64, vp, i32, u64, u64, vp, u64, P(u64)]),
+        "llkv_gpu_agg_create": (i32, [vp, u64, vp, i32, vp, i32, vp, i32, i32, u64, P(vp)]),
+        "llkv_gpu_agg_reset": (i32, [vp]),
+        "llkv_gpu_agg_run": (i32, [vp, vp, i32, u64, u64]),
+        "llkv_gpu_agg_merge": (i32, [vp]),
+        "llkv_gpu_agg_group_count": (i32, [vp, P(u64)]),
+        "llkv_gpu_agg_finalize": (i32, [vp, vp, vp, u64, P(u64)]),
+        "llkv_gpu_agg_run_info": (i32, [vp, P(ffi.RunInfo)]),
+        "llkv_gpu_agg_destroy": (None, [vp]),
+        "llkv_gpu_comm_unique_id": (i32, [vp]),
+        "llkv_gpu_comm_init": (i32, [vp, vp, i32, i32]),
+        "llkv_gpu_comm_destroy": (i32, [vp]),
+    }
+    for name, (res, args) in sig.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    if lib.llkv_gpu_abi_version() != 1:
+        raise RuntimeError("libllkv_gpu.so ABI version mismatch")
+    _lib = lib
+    return lib
+
+
+def last_error() -> str:
+    buf = C.create_string_buffer(2048)
+    load().llkv_gpu_last_error(buf, 2048)
+    return buf.value.decode(errors="replace")
+
+
+def _check(rc: int):
+    if rc:
+        raise LlkvError(rc, last_error())
+
+
+def logical_field_id(table_id: int, field_id: int, namespace: int = NS_USER) -> int:
+    """LogicalFieldId::from_parts (llkv-types/src/ids.rs:133-175): field 32 | table 16 | namespace 16."""
+    return (field_id & 0xFFFFFFFF) | ((table_id & 0xFFFF) << 32) | ((namespace & 0xFFFF) << 48)
+
+
+def device_count() -> int:
+    return int(load().llkv_gpu_device_count())
+
+
+class Context:
+    """One per GPU (llkv_gpu_ctx)."""
+
+    def __init__(self, device: int = 0, n_streams: int = 4, pinned_bytes: int = 64 << 20):
+        self.lib = load()
+        h = C.c_void_p()
+        _check(self.lib.llkv_gpu_ctx_create(device, n_streams, pinned_bytes, C.byref(h)))
+        self.handle = h
+        self.device = device
+
+    def close(self):
+        if self.handle:
+            self.lib.llkv_gpu_ctx_destroy(self.handle)
+            self.handle = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def synchronize(self):
+        _check(self.lib.llkv_gpu_ctx_synchronize(self.handle))
+
+    def stream(self) -> int:
+        s = C.c_void_p()
+        _check(self.lib.llkv_gpu_ctx_stream(self.handle, C.byref(s)))
+        return int(s.value or 0)
+
+    def set_timing(self, enabled: bool):
+        _check(self.lib.llkv_gpu_ctx_set_timing(self.handle, int(enabled)))
+
+    def set_tuning(self, ctas_per_sm=0, block_threads=0, stages=0, rows_per_thread=0, force_wide=0):
+        _check(self.lib.llkv_gpu_ctx_set_tuning(self.handle, ctas_per_sm, block_threads, stages, rows_per_thread, force_wide))
+
+    # ---- multi-GPU (NCCL over NVLink): the unique id travels through whatever the host uses for rendezvous
+    def comm_unique_id(self) -> bytes:
+        buf = (C.c_uint8 * ffi.UNIQUE_ID_BYTES)()
+        _check(self.lib.llkv_gpu_comm_unique_id(buf))
+        return bytes(buf)
+
+    def comm_init(self, unique_id: bytes, n_ranks: int, rank: int):
+        buf = (C.c_uint8 * ffi.UNIQUE_ID_BYTES)(*unique_id)
+        _check(self.lib.llkv_gpu_comm_init(self.handle, buf, n_ranks, rank))
+
+    def comm_destroy(self):
+        _check(self.lib.llkv_gpu_comm_destroy(self.handle))
+
+
+def pinned_empty(nbytes: int) -> Tuple[np.ndarray, int]:
+    """Page-locked host buffer as a uint8 numpy view (llkv_gpu_host_alloc); free with pinned_free(ptr)."""
+    p = C.c_void_p()
+    _check(load().llkv_gpu_host_alloc(nbytes, C.byref(p)))
+    arr = np.ctypeslib.as_array((C.c_uint8 * max(1, nbytes)).from_address(p.value))
+    return arr[:nbytes], int(p.value)
+
+
+def pinned_free(ptr: int):
+    _check(load().llkv_gpu_host_free(C.c_void_p(ptr)))
+
+
+def chunk_rows_for(dtype_type: int) -> int:
+    """Rows per chunk the reference's append path produces for a column of this type (slicing.rs:33-43,155-166)."""
+    w = {ffi.PT_UINT64: 8, ffi.PT_INT64: 8, ffi.PT_FLOAT64: 8, ffi.PT_INT32: 4, ffi.PT_UINT32: 4, ffi.PT_FLOAT32: 4,
+         ffi.PT_INT16: 2, ffi.PT_UINT16: 2, ffi.PT_INT8: 1, ffi.PT_UINT8: 1}.get(dtype_type)
+    return TARGET_CHUNK_BYTES // w if w else VARWIDTH_FALLBACK_ROWS
+
+
+class DeviceColumn:
+    def __init__(self, ctx: Context, lfid: int, col: HostColumn):
+        self.ctx = ctx
+        self.lib = ctx.lib
+        self.dtype = col.dtype
+        self.lfid = lfid
+        h = C.c_void_p()
+        _check(self.lib.llkv_gpu_column_register(ctx.handle, lfid, col.dtype.type, col.dtype.precision, col.dtype.scale, C.byref(h)))
+        self.handle = h
+        self.next_pk = 1
+
+    def reserve(self, n_rows: int):
+        _check(self.lib.llkv_gpu_column_reserve(self.handle, n_rows))
+
+    def append(self, col: HostColumn, chunk_rows: Optional[int] = None, row_id_base: Optional[int] = None, as_blob: bool = False):
+        """Appends `col` in chunks of `chunk_rows` rows (default: the reference's chunking for the type)."""
+        n = col.n_rows
+        if chunk_rows is None:
+            chunk_rows = chunk_rows_for(col.dtype.type)
+        base = self.rows() if row_id_base is None else row_id_base
+        t = col.dtype.type
+        for lo in range(0, max(n, 0), chunk_rows):
+            hi = min(n, lo + chunk_rows)
+            m = hi - lo
+            validity = None
+            if col.validity is not None:
+                bits = np.unpackbits(col.validity, bitorder="little")[lo:hi]
+                validity = np.packbits(bits, bitorder="little")
+            vptr = C.c_void_p(validity.ctypes.data) if validity is not None else None
+            if t == ffi.PT_UTF8:
+                offs = col.values[lo:hi + 1]
+                _check(self.lib.llkv_gpu_column_append_chunk(self.handle, self.next_pk, C.c_void_p(offs.ctypes.data), m, vptr, None,
+                                                              base + lo, C.c_void_p(col.aux.ctypes.data) if col.aux.size else None))
+            elif as_blob and validity is None:
+                blob = HostColumn(col.field_id, col.dtype, col.values[lo:hi]).serialize()
+                _check(self.lib.llkv_gpu_column_append_blob(self.handle, self.next_pk, blob, len(blob), None, base + lo))
+            else:
+                vals = col.values[lo:hi]
+                _check(self.lib.llkv_gpu_column_append_chunk(self.handle, self.next_pk, C.c_void_p(vals.ctypes.data), m, vptr, None,
+                                                              base + lo, None))
+            self.next_pk += 1
+
+    def append_raw(self, ptr: int, n_rows: int, row_id_base: int):
+        """One chunk from a raw host pointer (e.g. a slice of a pinned buffer)."""
+        _check(self.lib.llkv_gpu_column_append_chunk(self.handle, self.next_pk, C.c_void_p(ptr), n_rows, None, None, row_id_base, None))
+        self.next_pk += 1
+
+    def seal(self):
+        _check(self.lib.llkv_gpu_column_seal(self.handle))
+
+    def clear(self):
+        _check(self.lib.llkv_gpu_column_clear(self.handle))
+
+    def rows(self) -> int:
+        n = C.c_uint64()
+        _check(self.lib.llkv_gpu_column_rows(self.handle, C.byref(n)))
+        return int(n.value)
+
+    def destroy(self):
+        if self.handle:
+            self.lib.llkv_gpu_column_destroy(self.handle)
+            self.handle = None
+
+
+class Program:
+    """A compiled predicate (llkv_gpu_program): ProgramCompiler::compile output crossing the boundary."""
+
+    def __init__(self, ctx: Context, expr: Expr):
+        self.lib = ctx.lib
+        cp = ProgramCompiler(expr).compile()
+        ops, n_ops, lits, n_lits, nodes, n_nodes, roots, n_roots = cp.c_arrays()
+        h = C.c_void_p()
+        _check(self.lib.llkv_gpu_program_compile(ctx.handle, ops, n_ops, lits, n_lits, nodes, n_nodes, roots, n_roots, C.byref(h)))
+        self.handle = h
+
+    def destroy(self):
+        if self.handle:
+            self.lib.llkv_gpu_program_destroy(self.handle)
+            self.handle = None
+
+
+class Aggregation:
+    """A set of AggregateStates fused with the scan that feeds them (llkv_gpu_agg)."""
+
+    def __init__(self, table: "DeviceTable", specs: Sequence[AggregateSpec], group_by: Sequence[int] = (),
+                 expr_mode: Optional[int] = None, cardinality_hint: int = 0):
+        self.table = table
+        self.lib = table.ctx.lib
+        self.n_aggs = len(specs)
+        self.n_keys = len(group_by)
+        if expr_mode is None:
+            expr_mode = ffi.EXPR_EXACT if group_by else ffi.EXPR_ARROW
+        aggs, n_aggs, nodes, n_nodes = flatten_aggregates(specs)
+        keys = (C.c_uint64 * max(1, len(group_by)))(*group_by)
+        h = C.c_void_p()
+        _check(self.lib.llkv_gpu_agg_create(table.ctx.handle, table.table_id, aggs, n_aggs, nodes, n_nodes, keys, len(group_by),
+                                            expr_mode, cardinality_hint, C.byref(h)))
+        self.handle = h
+
+    def reset(self):
+        _check(self.lib.llkv_gpu_agg_reset(self.handle))
+
+    def run(self, program: Optional[Program] = None, apply_mvcc: bool = False, row_begin: int = 0, row_end: Optional[int] = None):
+        row_end = self.table.n_rows if row_end is None else row_end
+        _check(self.lib.llkv_gpu_agg_run(self.handle, program.handle if program else None, int(apply_mvcc), row_begin, row_end))
+
+    def merge(self):
+        _check(self.lib.llkv_gpu_agg_merge(self.handle))
+
+    def group_count(self) -> int:
+        n = C.c_uint64()
+        _check(self.lib.llkv_gpu_agg_group_count(self.handle, C.byref(n)))
+        return int(n.value)
+
+    def finalize_raw(self, group_capacity: int):
+        vals = (ffi.AggValue * (group_capacity * max(1, self.n_aggs)))()
+        keys = (ffi.GroupKey * (group_capacity * max(1, self.n_keys)))()
+        n = C.c_uint64()
+        _check(self.lib.llkv_gpu_agg_finalize(self.handle, vals, keys, group_capacity, C.byref(n)))
+        return vals, keys, int(n.value)
+
+    def finalize(self, group_capacity: Optional[int] = None):
+        """[(key_tuple, [AggregateValue, ...]), ...] in first-appearance order of the groups."""
+        if group_capacity is None:
+            group_capacity = self.group_count() if self.n_keys else 1
+            group_capacity = max(1, group_capacity)
+        vals, keys, n = self.finalize_raw(group_capacity)
+        rows = []
+        for g in range(n):
+            key = tuple(decode_group_key(keys[g * self.n_keys + k]) for k in range(self.n_keys))
+            rows.append((key, [AggregateValue.from_c(vals[g * self.n_aggs + a]) for a in range(self.n_aggs)]))
+        return rows
+
+    def run_info(self) -> ffi.RunInfo:
+        info = ffi.RunInfo()
+        _check(self.lib.llkv_gpu_agg_run_info(self.handle, C.byref(info)))
+        return info
+
+    def destroy(self):
+        if self.handle:
+            self.lib.llkv_gpu_agg_destroy(self.handle)
+            self.handle = None
+
+
+class DeviceTable:
+    """The HBM-resident image of one table: every column concatenated chunk by chunk, dense row ids."""
+
+    def __init__(self, ctx: Context, table_id: int = 1):
+        self.ctx = ctx
+        self.table_id = table_id
+        self.columns: Dict[int, DeviceColumn] = {}
+        self.created_by: Optional[DeviceColumn] = None
+        self.deleted_by: Optional[DeviceColumn] = None
+        self.n_rows = 0
+
+    @staticmethod
+    def from_host(ctx: Context, table: HostTable, chunk_rows: Optional[int] = None, as_blob: bool = False) -> "DeviceTable":
+        dt = DeviceTable(ctx, table.table_id)
+        for col in table.columns.values():
+            dt.add_column(col, chunk_rows, as_blob)
+        if table.created_by is not None:
+            dt.add_mvcc(table.created_by, table.deleted_by, chunk_rows)
+        dt.seal()
+        return dt
+
+    def add_column(self, col: HostColumn, chunk_rows: Optional[int] = None, as_blob: bool = False) -> DeviceColumn:
+        dc = DeviceColumn(self.ctx, logical_field_id(self.table_id, col.field_id), col)
+        dc.reserve(col.n_rows)
+        dc.append(col, chunk_rows, as_blob=as_blob)
+        self.columns[col.field_id] = dc
+        self.n_rows = col.n_rows
+        return dc
+
+    def add_mvcc(self, created_by: HostColumn, deleted_by: HostColumn, chunk_rows: Optional[int] = None):
+        self.created_by = DeviceColumn(self.ctx, logical_field_id(self.table_id, 0xFFFFFFFF, NS_TXN_CREATED_BY), created_by)
+        self.created_by.reserve(created_by.n_rows)
+        self.created_by.append(created_by, chunk_rows)
+        self.deleted_by = DeviceColumn(self.ctx, logical_field_id(self.table_id, 0xFFFFFFFE, NS_TXN_DELETED_BY), deleted_by)
+        self.deleted_by.reserve(deleted_by.n_rows)
+        self.deleted_by.append(deleted_by, chunk_rows)
+
+    def seal(self):
+        for c in self._all():
+            c.seal()
+
+    def _all(self) -> List[DeviceColumn]:
+        cols = list(self.columns.values())
+        if self.created_by is not None:
+            cols += [self.created_by, self.deleted_by]
+        return cols
+
+    def set_snapshot(self, snapshot: Optional[Snapshot]):
+        """MvccRowIdFilter::new(txn_manager, snapshot) (llkv-transaction/src/helpers.rs:259-312)."""
+        lib = self.ctx.lib
+        if snapshot is None or self.created_by is None:
+            _check(lib.llkv_gpu_mvcc_clear(self.ctx.handle, self.table_id))
+            return
+        nc = list(snapshot.noncommitted)
+        arr = (C.c_uint64 * max(1, len(nc)))(*nc)
+        _check(lib.llkv_gpu_mvcc_set(self.ctx.handle, self.table_id, self.created_by.handle, self.deleted_by.handle,
+                                     snapshot.txn_id, snapshot.snapshot_id, arr, len(nc)))
+
+    def filter_bitmap(self, expr: Optional[Expr], snapshot: Optional[Snapshot] = None, row_begin: int = 0,
+                      row_end: Optional[int] = None) -> Tuple[np.ndarray, int]:
+        """Selection bitmap over row positions + its popcount (ScanStorage::filter_leaf / RowIdFilter::filter)."""
+        row_end = self.n_rows if row_end is None else row_end
+        prog = Program(self.ctx, expr) if expr is not None else None
+        self.set_snapshot(snapshot)
+        n_words = (row_end - row_begin + 63) // 64
+        words = np.zeros(max(1, n_words), dtype=np.uint64)
+        count = C.c_uint64()
+        try:
+            _check(self.ctx.lib.llkv_gpu_filter_bitmap(self.ctx.handle, self.table_id, prog.handle if prog else None,
+                                                       int(snapshot is not None), row_begin, row_end,
+                                                       C.c_void_p(words.ctypes.data), n_words, C.byref(count)))
+        finally:
+            if prog:
+                prog.destroy()
+        return words[:n_words], int(count.value)
+
+    def aggregate(self, expr: Optional[Expr], specs: Sequence[AggregateSpec], snapshot: Optional[Snapshot] = None,
+                  group_by: Sequence[int] = (), expr_mode: Optional[int] = None, row_begin: int = 0,
+                  row_end: Optional[int] = None, cardinality_hint: int = 0, group_capacity: Optional[int] = None):
+        """One-shot: new accumulators, one fused scan, finalize.  Same result shape as oracle.aggregate."""
+        prog = Program(self.ctx, expr) if expr is not None else None
+        self.set_snapshot(snapshot)
+        agg = Aggregation(self, specs, group_by, expr_mode, cardinality_hint)
+        try:
+            agg.run(prog, snapshot is not None, row_begin, row_end)
+            return agg.finalize(group_capacity)
+        finally:
+            agg.destroy()
+            if prog:
+                prog.destroy()
+
+    def destroy(self):
+        for c in self._all():
+            c.destroy()
+        self.columns.clear()
+        self.created_by = self.deleted_by = None
