@@ -249,6 +249,7 @@ struct llkv_gpu_column {
   bool has_origin = false;
   uint64_t row_id_origin = 0;
   int stream_index = 0;
+  uint64_t stats_rows = 0;  // rows already covered by the statistics pass (run at seal, not per chunk)
   std::vector<void*> deferred_free;  // temp device buffers released at seal
 };
 
@@ -641,7 +642,6 @@ extern "C" int32_t llkv_gpu_column_append_chunk(llkv_gpu_column* col, uint64_t c
     col->hstats.data_bytes += (u64)data_bytes;
   } else {
     if ((rc = upload(col, (char*)col->values + col->n_rows * col->elem_bytes, values, n_rows * col->elem_bytes))) return rc;
-    if ((rc = launch_stats(col, col->n_rows, n_rows))) return rc;
   }
   if (validity) {
     if ((rc = ensure_validity(col))) return rc;
@@ -689,6 +689,12 @@ extern "C" int32_t llkv_gpu_column_seal(llkv_gpu_column* col) {
   for (cudaStream_t s : c->copy_streams) CUDA_TRY(cudaStreamSynchronize(s));
   for (void* p : col->deferred_free) cudaFree(p);
   col->deferred_free.clear();
+  if (col->stats_rows < col->n_rows && col->load_kind != LK_STR8) {  // min / max / fits-i64 over the rows appended since the last seal
+    int32_t rc = launch_stats(col, col->stats_rows, col->n_rows - col->stats_rows);
+    if (rc) return rc;
+    CUDA_TRY(cudaStreamSynchronize(c->copy_streams[(size_t)col->stream_index]));
+    col->stats_rows = col->n_rows;
+  }
   const u64 data_bytes = col->hstats.data_bytes;
   CUDA_TRY(cudaMemcpy(&col->hstats, col->dstats, sizeof(DevStats), cudaMemcpyDeviceToHost));
   col->hstats.data_bytes = data_bytes;
@@ -740,6 +746,7 @@ extern "C" int32_t llkv_gpu_column_clear(llkv_gpu_column* col) {
   CUDA_TRY(cudaMemcpyAsync(col->dstats, &col->hstats, sizeof(DevStats), cudaMemcpyHostToDevice, s));
   CUDA_TRY(cudaStreamSynchronize(s));
   col->n_rows = 0;
+  col->stats_rows = 0;
   col->has_origin = false;
   col->sealed = false;
   return LLKV_OK;
@@ -1466,12 +1473,13 @@ static int32_t finalize_group(llkv_gpu_agg* a, const u64* w, llkv_agg_value* out
         break;
       }
       case ACC_SUM_DEC: case ACC_TOTAL_DEC:
+        if (L.dead) { val_dec(o, 0, L.precision, L.scale, 1); break; }
         if (!limbs_value(&w[L.w_val], 4, &total))
           return agg_fail(a, LLKV_ERR_INVALID_ARGUMENT, L.acc == ACC_TOTAL_DEC ? "Decimal128 total overflow" : "Decimal128 sum overflow");
         val_dec(o, total, L.precision, L.scale, 1);  // always a value: 0 when no rows (lib.rs:1567-1582)
         break;
       case ACC_AVG_DEC: {
-        if (count == 0) { val_dec(o, 0, L.precision, L.scale, 0); break; }
+        if (L.dead || count == 0) { val_dec(o, 0, L.precision, L.scale, 0); break; }
         if (!limbs_value(&w[L.w_val], 4, &total)) return agg_fail(a, LLKV_ERR_INVALID_ARGUMENT, "Decimal128 sum overflow");
         const i128 c = (i128)count;
         i128 avg = total / c;
@@ -1485,7 +1493,7 @@ static int32_t finalize_group(llkv_gpu_agg* a, const u64* w, llkv_agg_value* out
         break;
       }
       case ACC_MIN_DEC: case ACC_MAX_DEC:
-        if (count == 0) val_dec(o, 0, L.precision, L.scale, 0);
+        if (L.dead || count == 0) val_dec(o, 0, L.precision, L.scale, 0);
         else {
           const u64 hi = w[L.w_val] ^ 0x8000000000000000ull, lo = w[L.w_val + 1];
           val_dec(o, (i128)(((u128)hi << 64) | lo), L.precision, L.scale, 1);
