@@ -222,6 +222,7 @@ typedef struct llkv_run_info {
   uint32_t grid, block, rows_per_tile, stages, smem_bytes;
   uint32_t fast_groups;         /* CTA-local group slots with per-thread accumulators */
   float last_kernel_ms;         /* device time of the scan kernel (CUDA events) when timing is enabled, else 0 */
+  uint32_t used_fast_kernel;    /* 1 when the lean kernel (fast_scan_kernel) ran, 0 for the general interpreter */
 } llkv_run_info;
 
 typedef struct llkv_gpu_ctx llkv_gpu_ctx;
@@ -245,7 +246,8 @@ int32_t llkv_gpu_ctx_synchronize(llkv_gpu_ctx* ctx);
 int32_t llkv_gpu_ctx_stream(llkv_gpu_ctx* ctx, void** out_stream);
 /* Turns per-run CUDA-event timing of the scan kernel on/off (llkv_run_info.last_kernel_ms). */
 int32_t llkv_gpu_ctx_set_timing(llkv_gpu_ctx* ctx, int32_t enabled);
-/* Tuning knobs: 0 keeps the default.  rows_per_thread in {1,2,4}. */
+/* Tuning knobs: 0 keeps the default.  rows_per_thread in {1,2,4,8} (8: lean kernel only).  force_wide: 1 = always the 128-bit general
+ * interpreter, 2 = always the 64-bit general interpreter (never the lean kernel). */
 int32_t llkv_gpu_ctx_set_tuning(llkv_gpu_ctx* ctx, int32_t ctas_per_sm, int32_t block_threads, int32_t stages,
                                 int32_t rows_per_thread, int32_t force_wide);
 

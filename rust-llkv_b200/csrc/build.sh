@@ -7,7 +7,8 @@ FLAGS="-gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompil
 mkdir -p build
 $NVCC $FLAGS -c scan_kernel.cu -o build/scan_kernel.o &
 $NVCC $FLAGS -c llkv_gpu.cu -o build/llkv_gpu.o &
+$NVCC $FLAGS -c fast_kernel.cu -o build/fast_kernel.o &
 g++ -O2 -std=c++17 -fPIC -Wall -Wno-nonnull -c compiler.cpp -o build/compiler.o &
 wait
-$NVCC -gencode arch=compute_100a,code=sm_100a -shared -o libllkv_gpu.so build/scan_kernel.o build/llkv_gpu.o build/compiler.o -cudart static -ldl -lpthread -lrt
+$NVCC -gencode arch=compute_100a,code=sm_100a -shared -o libllkv_gpu.so build/scan_kernel.o build/fast_kernel.o build/llkv_gpu.o build/compiler.o -cudart static -ldl -lpthread -lrt
 echo built $(pwd)/libllkv_gpu.so

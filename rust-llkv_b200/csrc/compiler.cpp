@@ -1551,6 +1551,386 @@ class Emitter {
     out_.can_narrow_fail = can_narrow_fail_ && !wide_;
     out_.algorithmic_bytes_per_row = alg;
     out_.physical_bytes_per_row = phys;
+    out_.fast = false;
+    p.n_finstr = 0;
+    if (!req_.no_fast) {
+      const size_t lits_mark = lits_.size();
+      if (lower_fast()) {
+        out_.fast = true;
+        p.n_lits = (uint32_t)lits_.size();
+        for (size_t i = 0; i < lits_.size(); ++i) p.lits[i] = lits_[i];
+      } else {
+        lits_.resize(lits_mark);
+        p.n_finstr = 0;
+      }
+    }
+  }
+
+  // ---- lowering to the lean kernel (fast_kernel.cu) -----------------------------------------------------------------
+  // Abstract interpretation of the generic program with value intervals from the columns' min/max statistics: when no
+  // input can be NULL and every arithmetic result provably fits 64 bits (so no check can fire), the plan also gets a
+  // FastOp program.  Anything outside the hot subset keeps only the generic program.
+  struct Iv {
+    bool known = false;  // integer interval [lo, hi] is valid
+    i128 lo = 0, hi = 0;
+    bool is_float = false;
+  };
+  static Iv iv_exact(i128 v) {
+    Iv x;
+    x.known = true;
+    x.lo = x.hi = v;
+    return x;
+  }
+  static bool iv_fits(const Iv& x, i128 lo, i128 hi) { return x.known && x.lo >= lo && x.hi <= hi; }
+  static bool iv_fits_i64(const Iv& x) { return iv_fits(x, (i128)INT64_MIN, (i128)INT64_MAX); }
+  static bool iv_fits_i32(const Iv& x) { return iv_fits(x, (i128)INT32_MIN, (i128)INT32_MAX); }
+  static Iv iv_arith(int op, const Iv& a, const Iv& b) {  // 0 add, 1 sub, 2 mul
+    Iv r;
+    if (!a.known || !b.known) return r;
+    i128 c[4];
+    bool ov = false;
+    if (op == 0) { ov |= __builtin_add_overflow(a.lo, b.lo, &c[0]); ov |= __builtin_add_overflow(a.hi, b.hi, &c[1]); c[2] = c[0]; c[3] = c[1]; }
+    else if (op == 1) { ov |= __builtin_sub_overflow(a.lo, b.hi, &c[0]); ov |= __builtin_sub_overflow(a.hi, b.lo, &c[1]); c[2] = c[0]; c[3] = c[1]; }
+    else {
+      ov |= __builtin_mul_overflow(a.lo, b.lo, &c[0]);
+      ov |= __builtin_mul_overflow(a.lo, b.hi, &c[1]);
+      ov |= __builtin_mul_overflow(a.hi, b.lo, &c[2]);
+      ov |= __builtin_mul_overflow(a.hi, b.hi, &c[3]);
+    }
+    if (ov) return r;
+    r.known = true;
+    r.lo = r.hi = c[0];
+    for (int i = 1; i < 4; ++i) {
+      if (c[i] < r.lo) r.lo = c[i];
+      if (c[i] > r.hi) r.hi = c[i];
+    }
+    return r;
+  }
+  static i128 round_div(i128 x, i128 d) {  // half away from zero
+    i128 q = x / d, rem = x % d, half = d / 2;
+    if (x >= 0) { if (rem >= half) q += 1; } else { if (rem <= -half) q -= 1; }
+    return q;
+  }
+  Iv column_interval(const ColumnMeta& c) const {
+    Iv x;
+    switch (c.load_kind) {
+      case LK_F32: case LK_F64: x.is_float = true; return x;
+      case LK_STR8: case LK_U64: case LK_D128: case LK_I64: break;
+      default: break;
+    }
+    const bool is_signed = type_is_signed_int(c.type) || c.type == LLKV_PT_DECIMAL128;
+    if (c.has_minmax) {
+      x.known = true;
+      x.lo = is_signed ? (i128)(int64_t)c.min_bits : (i128)c.min_bits;
+      x.hi = is_signed ? (i128)(int64_t)c.max_bits : (i128)c.max_bits;
+      return x;
+    }
+    if (c.type == LLKV_PT_UTF8) return x;
+    const int bits = c.type == LLKV_PT_DECIMAL128 ? 64 : (c.type == LLKV_PT_BOOLEAN ? 8 : type_bits(c.type));
+    x.known = true;
+    if (is_signed) { x.lo = -((i128)1 << (bits - 1)); x.hi = ((i128)1 << (bits - 1)) - 1; }
+    else { x.lo = 0; x.hi = ((i128)1 << bits) - 1; }
+    return x;
+  }
+
+  // symbolic value-stack entry of the accumulator machine
+  struct Sym {
+    enum Where : uint8_t { ACC, COL, LIT, TMP } where = LIT;
+    uint8_t col = 0, load = 0, tmp = 0;
+    uint32_t lit = 0;
+    Iv iv;
+  };
+
+  bool lower_fast() {
+    Plan& p = out_.plan;
+    if (wide_ || req_.bitmap_mode) return false;
+    for (const ColumnMeta* c : plan_cols_) {
+      if (c->nullable) return false;
+      if (c->load_kind == LK_D128 && !c->dec_fits_i64) return false;
+    }
+    std::vector<Instr> f;
+    std::vector<Sym> st;
+    bool tmp_used[kFastTmps] = {false, false, false};
+    int max_tmps = 0;
+    bool ok = true;
+    auto femit = [&](uint16_t op, uint8_t a, uint8_t b, uint32_t c) {
+      Instr in;
+      in.op = op;
+      in.a = a;
+      in.b = b;
+      in.c = c;
+      f.push_back(in);
+    };
+    auto free_sym = [&](const Sym& x) {
+      if (x.where == Sym::TMP) tmp_used[x.tmp] = false;
+    };
+    // whoever currently sits in the accumulator (other than `keep`) moves to a tile-sized temporary
+    auto spill_acc = [&](size_t keep) {
+      for (size_t i = 0; i < st.size(); ++i) {
+        if (i == keep || st[i].where != Sym::ACC) continue;
+        int k = -1;
+        for (int t = 0; t < kFastTmps; ++t)
+          if (!tmp_used[t]) { k = t; break; }
+        if (k < 0) { ok = false; return; }
+        tmp_used[k] = true;
+        if (k + 1 > max_tmps) max_tmps = k + 1;
+        femit(FO_ST_TMP, (uint8_t)k, 0, 0);
+        st[i].where = Sym::TMP;
+        st[i].tmp = (uint8_t)k;
+      }
+    };
+    auto load_acc = [&](size_t i) {  // make entry i the accumulator
+      if (st[i].where == Sym::ACC) return;
+      spill_acc(i);
+      if (st[i].where == Sym::COL) femit(FO_LD_COL, st[i].col, st[i].load, 0);
+      else if (st[i].where == Sym::LIT) femit(FO_LD_LIT, 0, 0, st[i].lit);
+      else {
+        femit(FO_LD_TMP, st[i].tmp, 0, 0);
+        tmp_used[st[i].tmp] = false;
+      }
+      st[i].where = Sym::ACC;
+    };
+    auto emit_binary = [&](uint8_t fb) {  // st[n-2] op st[n-1] -> accumulator
+      const size_t n = st.size();
+      Sym& a = st[n - 2];
+      Sym& b = st[n - 1];
+      uint8_t rev = 0;
+      const Sym* other;
+      if (a.where == Sym::ACC) other = &b;
+      else if (b.where == Sym::ACC) { other = &a; rev = FB_REV; }
+      else { load_acc(n - 2); other = &b; }
+      if (!ok) return;
+      if (other->where == Sym::COL) femit(FO_OP_COL, fb | rev, other->load, other->col);
+      else if (other->where == Sym::LIT) femit(FO_OP_LIT, fb | rev, 0, other->lit);
+      else femit(FO_OP_TMP, fb | rev, other->tmp, 0);
+      free_sym(*other);
+    };
+    auto fold_lit = [&](Sym& x, i128 v) {  // constant folding of unary ops on literals
+      x.lit = add_lit((uint64_t)(u128)v, (uint64_t)((u128)v >> 64));
+      x.iv = iv_exact(v);
+    };
+
+    const size_t n = code_.size();
+    for (size_t i = 0; i < n && ok; ++i) {
+      const Instr& in = code_[i];
+      switch (in.op) {
+        case OP_END: femit(FO_END, 0, 0, 0); break;
+        case OP_PUSH_COL: {
+          const ColumnMeta& c = *plan_cols_[in.a];
+          // typed leaf at the top level: PUSH_COL, PRED_*, FILTER
+          if (i + 2 < n && code_[i + 2].op == OP_FILTER && i + 2 < select_end_) {
+            const Instr& pr = code_[i + 1];
+            if (pr.op == OP_PRED_ALL || pr.op == OP_PRED_NOTNULL) { i += 2; break; }  // every row present: always true
+            if (pr.op == OP_PRED_I || pr.op == OP_PRED_U || pr.op == OP_PRED_D || pr.op == OP_PRED_ISNULL) {
+              const bool uns = pr.op == OP_PRED_U;
+              i128 tmin, tmax;
+              if (uns) { tmin = 0; tmax = (i128)UINT64_MAX; } else { tmin = (i128)INT64_MIN; tmax = (i128)INT64_MAX; }
+              // the column's own value range bounds the comparison domain (and lets 32-bit columns compare in 32 bits)
+              const Iv ci = column_interval(c);
+              if (ci.known) { if (ci.lo > tmin) tmin = ci.lo; if (ci.hi < tmax) tmax = ci.hi; }
+              if (c.load_kind == LK_I32) { if (tmin < INT32_MIN) tmin = INT32_MIN; if (tmax > INT32_MAX) tmax = INT32_MAX; }
+              i128 lo = tmin, hi = tmax;
+              bool empty = pr.op == OP_PRED_ISNULL;
+              if (!empty) {
+                const int lk = pr.a & 3, uk = (pr.a >> 2) & 3, eq = (pr.a >> 4) & 1;
+                auto lit_val = [&](uint32_t idx) -> i128 {
+                  const Lit& L = lits_[idx];
+                  if (uns) return (i128)L.lo;
+                  if (pr.op == OP_PRED_D) return (i128)(((u128)L.hi << 64) | (u128)L.lo);
+                  return (i128)(int64_t)L.lo;
+                };
+                if (eq) {
+                  lo = hi = lit_val(pr.c);
+                } else {
+                  uint32_t li = pr.c;
+                  if (lk != LLKV_BOUND_UNBOUNDED) {
+                    const i128 v = lit_val(li++);
+                    if (lk == LLKV_BOUND_EXCLUDED) { if (v >= tmax) empty = true; else lo = v + 1; } else lo = v;
+                  }
+                  if (uk != LLKV_BOUND_UNBOUNDED) {
+                    const i128 v = lit_val(li);
+                    if (uk == LLKV_BOUND_EXCLUDED) { if (v <= tmin) empty = true; else hi = v - 1; } else hi = v;
+                  }
+                }
+                if (lo < tmin) lo = tmin;
+                if (hi > tmax) hi = tmax;
+                if (lo > hi) empty = true;
+              }
+              Lit a, b;
+              if (empty) { a = mk_lit_i(1); b = mk_lit_i(0); }
+              else { a = mk_lit_i(lo); b = mk_lit_i(hi); }
+              std::vector<Lit> run = {a, b};
+              if (lits_.size() + 2 > (size_t)kMaxLits) return false;
+              const uint32_t first = add_lit_run(run);
+              femit(FO_LEAF, in.a, in.b, first);
+              i += 2;
+              break;
+            }
+            return false;  // float / IN leaves stay on the general interpreter
+          }
+          Sym x;
+          x.where = Sym::COL;
+          x.col = in.a;
+          x.load = in.b;
+          x.iv = column_interval(c);
+          st.push_back(x);
+          break;
+        }
+        case OP_PUSH_LIT: {
+          if (in.b) return false;
+          const Lit& L = lits_[in.c];
+          const i128 v = (i128)(((u128)L.hi << 64) | (u128)L.lo);
+          Sym x;
+          x.where = Sym::LIT;
+          x.lit = in.c;
+          if (fits_i64(v)) x.iv = iv_exact(v);
+          else if (L.hi == 0) x.iv = iv_exact((i128)(int64_t)L.lo);  // f64 bits / unsigned stored with hi = 0
+          else return false;
+          st.push_back(x);
+          break;
+        }
+        case OP_POP:
+          if (st.empty()) return false;
+          free_sym(st.back());
+          st.pop_back();
+          break;
+        case OP_ADD_I: case OP_SUB_I: case OP_MUL_I: case OP_ADD_D: case OP_SUB_D: case OP_MUL_D: {
+          if (st.size() < 2) return false;
+          const Iv b = st[st.size() - 1].iv, a = st[st.size() - 2].iv;
+          const bool is_d = in.op == OP_ADD_D || in.op == OP_SUB_D || in.op == OP_MUL_D;
+          const int k = (in.op == OP_ADD_I || in.op == OP_ADD_D) ? 0 : (in.op == OP_SUB_I || in.op == OP_SUB_D) ? 1 : 2;
+          const Iv r = iv_arith(k, a, b);
+          uint8_t fb;
+          if (iv_fits_i64(r)) fb = k == 0 ? FB_ADD : k == 1 ? FB_SUB : (iv_fits_i32(a) && iv_fits_i32(b) ? FB_MUL32 : FB_MUL);
+          else if (is_d) fb = k == 0 ? FB_ADD_CK : k == 1 ? FB_SUB_CK : FB_MUL_CK;  // overflow -> rerun on the 128-bit interpreter
+          else return false;  // a real i64 overflow is an error with its own message: general interpreter
+          emit_binary(fb);
+          st.pop_back();
+          st.back().where = Sym::ACC;
+          st.back().iv = iv_fits_i64(r) ? r : Iv();
+          break;
+        }
+        case OP_ADD_F: case OP_SUB_F: case OP_MUL_F: {
+          if (st.size() < 2) return false;
+          emit_binary(in.op == OP_ADD_F ? FB_ADD_F : in.op == OP_SUB_F ? FB_SUB_F : FB_MUL_F);
+          st.pop_back();
+          st.back().where = Sym::ACC;
+          st.back().iv = Iv();
+          st.back().iv.is_float = true;
+          break;
+        }
+        case OP_CAST_D_DOWN: {
+          if (st.empty() || !st.back().iv.known || in.a > 18) return false;
+          const i128 d = pow10_i128(in.a);
+          const Iv src = st.back().iv;
+          Iv x = src;
+          x.lo = round_div(x.lo, d);
+          x.hi = round_div(x.hi, d);
+          const i128 lim = in.b >= 39 ? ((i128)1 << 126) : pow10_i128(in.b);
+          if (!(x.lo > -lim && x.hi < lim)) return false;  // the precision check could turn a value into NULL
+          if (st.back().where == Sym::LIT) { fold_lit(st.back(), x.lo); break; }
+          load_acc(st.size() - 1);
+          femit(FO_DIVR, in.a, src.lo >= 0 ? (src.hi < ((i128)1 << 32) ? 2 : 1) : 0, 0);
+          st.back().iv = x;
+          break;
+        }
+        case OP_CAST_I_D: case OP_CAST_D_UP: case OP_RESCALE_DX: {
+          if (st.empty() || !st.back().iv.known || in.a > 18) return false;
+          if (in.op == OP_CAST_I_D && in.c) return false;
+          const Iv r = iv_arith(2, st.back().iv, iv_exact(pow10_i128(in.a)));
+          if (!iv_fits_i64(r)) return false;
+          if (in.op != OP_RESCALE_DX) {
+            const i128 lim = in.b >= 39 ? ((i128)1 << 126) : pow10_i128(in.b);
+            if (!(r.lo > -lim && r.hi < lim)) return false;
+          }
+          if (st.back().where == Sym::LIT) { fold_lit(st.back(), r.lo); break; }
+          if (in.a) {
+            load_acc(st.size() - 1);
+            femit(FO_MULP, in.a, 0, 0);
+          }
+          st.back().iv = r;
+          break;
+        }
+        case OP_CAST_I_I: {
+          if (st.empty()) return false;
+          const int bits = in.a;
+          if (bits < 64 && !iv_fits(st.back().iv, -((i128)1 << (bits - 1)), ((i128)1 << (bits - 1)) - 1)) return false;
+          break;
+        }
+        case OP_CAST_I_F: case OP_CAST_D_F: {
+          if (st.empty()) return false;
+          load_acc(st.size() - 1);
+          if (in.op == OP_CAST_I_F) femit(FO_I2F, 0, 0, 0);
+          else femit(FO_D2F, 0, 0, in.c);
+          st.back().iv = Iv();
+          st.back().iv.is_float = true;
+          break;
+        }
+        case OP_MVCC: femit(FO_MVCC, in.a, in.b, 0); break;
+        case OP_SELECT_DONE: femit(FO_SELECT_DONE, 0, 0, 0); break;
+        case OP_GROUP: {
+          const int nk = in.a;
+          if ((int)st.size() < nk) return false;
+          for (int k = nk - 1; k >= 0; --k) {
+            const Sym x = st.back();
+            if (x.where != Sym::COL) return false;
+            st.pop_back();
+            p.key_col[k] = x.col;
+            p.key_load[k] = x.load;
+          }
+          femit(FO_GROUP, (uint8_t)nk, 0, 0);
+          break;
+        }
+        case OP_AGG_COUNT_STAR: femit(FO_COUNT_STAR, 0, in.b, in.c); break;
+        case OP_AGG_FIRSTROW: femit(FO_FIRSTROW, 0, in.b, in.c); break;
+        case OP_AGG_COUNT: case OP_AGG_SUM_I: case OP_AGG_SUM_D: case OP_AGG_FSUM: case OP_AGG_MIN_I: case OP_AGG_MAX_I:
+        case OP_AGG_MIN_F: case OP_AGG_MAX_F: case OP_AGG_FIRSTVALID: case OP_AGG_FIRSTNAN: {
+          if (st.empty()) return false;
+          uint8_t a = 0;
+          uint16_t op;
+          bool keep = (in.a & 1) != 0;
+          switch (in.op) {
+            case OP_AGG_COUNT: op = FO_COUNT; break;
+            case OP_AGG_SUM_I: case OP_AGG_SUM_D: {
+              op = FO_SUM;
+              // 24-bit limbs a lane's partial sum (up to 8 rows) needs: redux.sync adds 32 lanes of each limb in 32 bits
+              const Iv& v = st.back().iv;
+              if (v.known) {
+                i128 m = v.hi > -v.lo ? v.hi : -v.lo;
+                if (m < 0) m = 0;
+                m *= 8;
+                if (v.lo >= 0 && m < ((i128)1 << 24)) a = 1;
+                else if (v.lo < 0 && m < ((i128)1 << 23)) a = 1;
+                else if (m < ((i128)1 << 45)) a = 2;  // |v| < 2^42: a warp's i64 partial stays exact over 2^20 rows per launch
+              }
+              if (in.op == OP_AGG_SUM_D) a |= 0x80;
+              break;
+            }
+            case OP_AGG_FSUM: op = FO_FSUM; break;
+            case OP_AGG_MIN_I: op = FO_MIN_I; break;
+            case OP_AGG_MAX_I: op = FO_MAX_I; break;
+            case OP_AGG_MIN_F: op = FO_MIN_F; break;
+            case OP_AGG_MAX_F: op = FO_MAX_F; break;
+            case OP_AGG_FIRSTVALID: op = FO_FIRSTVALID; keep = true; break;
+            default: op = FO_FIRSTNAN; keep = true; break;
+          }
+          if (op != FO_COUNT && op != FO_FIRSTVALID) load_acc(st.size() - 1);  // counts do not look at the value
+          femit(op, a, in.b, in.c);
+          if (!keep) {
+            free_sym(st.back());
+            st.pop_back();
+          }
+          break;
+        }
+        default: return false;  // anything else (OR/NOT trees, IN lists, float leaves, divisions, 128-bit min/max, ...)
+      }
+      if (f.size() >= (size_t)kMaxFastInstr) return false;
+    }
+    if (!ok) return false;
+    p.n_finstr = (uint32_t)f.size();
+    p.fast_tmps = (uint32_t)max_tmps;
+    for (size_t i = 0; i < f.size(); ++i) p.fcode[i] = f[i];
+    return true;
   }
 };
 

@@ -102,12 +102,14 @@ struct CompileRequest {
   int32_t expr_mode = LLKV_EXPR_ARROW;
   bool bitmap_mode = false;
   bool force_wide = false;
+  bool no_fast = false;  // keep only the general interpreter's program
 };
 
 struct CompileResult {
   Plan plan;  // program, literals, columns, MVCC, keys, accumulator layout.  Geometry / table pointers are the caller's.
   std::vector<AggLayout> aggs;
   std::vector<KeyLayout> keys;
+  bool fast = false;             // plan.fcode holds a lean-kernel program (fast_kernel.cu)
   bool wide = false;             // compiled for the 128-bit interpreter
   bool can_narrow_fail = false;  // 64-bit interpreter may raise FLAG_NARROW_FAIL
   uint32_t algorithmic_bytes_per_row = 0, physical_bytes_per_row = 0;

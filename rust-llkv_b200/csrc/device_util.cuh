@@ -4,6 +4,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "plan.h"
+
 namespace llkv {
 
 typedef long long i64;
@@ -18,6 +20,9 @@ __device__ __forceinline__ void mbar_init(void* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
 }
 __device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_arrive(void* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
 __device__ __forceinline__ void mbar_arrive_expect_tx(void* bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
@@ -133,7 +138,7 @@ __device__ __forceinline__ bool sub_ck(i128 a, i128 b, i128& r) {
   r = (i128)((u128)a - (u128)b);
   return (((a ^ b) & (a ^ r)) >> 127) == 0;
 }
-__device__ __noinline__ bool mul_ck(i128 a, i128 b, i128& out) {
+static __device__ __noinline__ bool mul_ck(i128 a, i128 b, i128& out) {
   const bool neg = (a < 0) != (b < 0);
   const u128 ua = a < 0 ? (u128)0 - (u128)a : (u128)a;
   const u128 ub = b < 0 ? (u128)0 - (u128)b : (u128)b;
@@ -162,7 +167,7 @@ __device__ __forceinline__ bool fits_precision(i64 v, int p) {
 
 // Rust `i128 as f64`: round to nearest even
 __device__ __forceinline__ double to_f64(i64 v) { return __ll2double_rn(v); }
-__device__ __noinline__ double to_f64(i128 v) {
+static __device__ __noinline__ double to_f64(i128 v) {
   const bool neg = v < 0;
   const u128 a = neg ? (u128)0 - (u128)v : (u128)v;
   const u64 hi = (u64)(a >> 64), lo = (u64)a;
@@ -205,7 +210,7 @@ __device__ __forceinline__ i64 div_pow10_round<i64>(i64 x, int k) {
   return d;
 }
 template <>
-__device__ __noinline__ i128 div_pow10_round<i128>(i128 x, int k) {
+__device__ __forceinline__ i128 div_pow10_round<i128>(i128 x, int k) {
   const i128 div = pow10_i128(k);
   i128 d = x / div;
   const i128 rem = x - d * div;
@@ -217,5 +222,61 @@ __device__ __noinline__ i128 div_pow10_round<i128>(i128 x, int k) {
   }
   return d;
 }
+
+// ------------------------------------------------------------------ global group table
+static __device__ __noinline__ u64 global_slot(const Plan& p, u64 K, bool key_is_null, uint32_t& errbits) {
+  if (p.n_keys == 0) return 0;
+  if (key_is_null) return p.gcap + 1;
+  if (K == kEmptyKey) return p.gcap;
+  const u64 mask = p.gcap - 1;
+  u64 h = mix64(K) & mask;
+  for (u64 i = 0; i <= mask; ++i) {
+    u64 cur = p.gkeys[h];
+    if (cur == K) return h;
+    if (cur == kEmptyKey) {
+      const u64 old = atomicCAS(&p.gkeys[h], kEmptyKey, K);
+      if (old == kEmptyKey || old == K) return h;
+    }
+    h = (h + 1) & mask;
+  }
+  errbits |= FLAG_TABLE_FULL;
+  return p.gcap;  // parked on the spare row; the flag makes the run fail
+}
+
+// exact integer value -> limb words (see FastKind)
+__device__ __forceinline__ void gadd_sum_i64(u64* w, i128 t) {
+  atomicAdd(&w[0], (u64)t & 0xffffffffull);
+  atomicAdd(&w[1], (u64)(i64)(t >> 32));
+}
+__device__ __forceinline__ void gadd_sum_i128(u64* w, i128 t) {
+  atomicAdd(&w[0], (u64)t & 0xffffffffull);
+  atomicAdd(&w[1], (u64)(t >> 32) & 0xffffffffull);
+  atomicAdd(&w[2], (u64)(t >> 64) & 0xffffffffull);
+  atomicAdd(&w[3], (u64)(i64)(t >> 96));
+}
+__device__ __forceinline__ void gmin128(u64* w, u64 hi_enc, u64 lo, bool is_max) {
+  // 16-byte CAS loop on (hi_enc, lo): lexicographic order of (hi_enc, lo) == numeric order of the i128
+  ulonglong2* addr = reinterpret_cast<ulonglong2*>(w);
+  u64 cur_hi = w[0], cur_lo = w[1];
+  while (true) {
+    const bool better = is_max ? (hi_enc > cur_hi || (hi_enc == cur_hi && lo > cur_lo))
+                               : (hi_enc < cur_hi || (hi_enc == cur_hi && lo < cur_lo));
+    if (!better) return;
+    u64 old_hi, old_lo;
+    asm volatile(
+        "{\n\t.reg .b128 cmp, swp, old;\n\t"
+        "mov.b128 cmp, {%2, %3};\n\t"
+        "mov.b128 swp, {%4, %5};\n\t"
+        "atom.global.cas.b128 old, [%6], cmp, swp;\n\t"
+        "mov.b128 {%0, %1}, old;\n\t}"
+        : "=l"(old_hi), "=l"(old_lo)
+        : "l"(cur_hi), "l"(cur_lo), "l"(hi_enc), "l"(lo), "l"(addr)
+        : "memory");
+    if (old_hi == cur_hi && old_lo == cur_lo) return;
+    cur_hi = old_hi;
+    cur_lo = old_lo;
+  }
+}
+
 
 }  // namespace llkv

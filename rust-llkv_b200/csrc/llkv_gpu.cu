@@ -25,6 +25,7 @@ typedef __int128 i128;
 typedef unsigned __int128 u128;
 cudaError_t launch_scan(const Plan* dplan, bool wide, int rows_per_thread, uint32_t grid, uint32_t block, uint32_t smem,
                         cudaStream_t stream);
+cudaError_t launch_fast(const Plan* dplan, int rows_per_thread, uint32_t grid, uint32_t consumer_threads, uint32_t smem, cudaStream_t stream);
 cudaError_t launch_init_table(u64* keys, u64* words, u64 rows, uint32_t n_gwords, const uint8_t* word_class_dev, cudaStream_t stream);
 cudaError_t launch_merge_table(const Plan* dplan, const u64* src_keys, const u64* src_words, u64 src_cap, cudaStream_t stream);
 }  // namespace llkv
@@ -412,8 +413,8 @@ extern "C" int32_t llkv_gpu_ctx_set_tuning(llkv_gpu_ctx* c, int32_t ctas_per_sm,
   if (!c) return set_error(LLKV_ERR_INVALID_ARGUMENT, "ctx is NULL");
   if (block_threads && (block_threads < 64 || block_threads > 512 || (block_threads & 63)))
     return set_error(LLKV_ERR_INVALID_ARGUMENT, "block_threads must be a multiple of 64 in [64, 512]");
-  if (rows_per_thread && rows_per_thread != 1 && rows_per_thread != 2 && rows_per_thread != 4)
-    return set_error(LLKV_ERR_INVALID_ARGUMENT, "rows_per_thread must be 1, 2 or 4");
+  if (rows_per_thread && rows_per_thread != 1 && rows_per_thread != 2 && rows_per_thread != 4 && rows_per_thread != 8)
+    return set_error(LLKV_ERR_INVALID_ARGUMENT, "rows_per_thread must be 1, 2, 4 or 8");
   if (stages < 0 || stages > 8 || ctas_per_sm < 0 || ctas_per_sm > 8) return set_error(LLKV_ERR_INVALID_ARGUMENT, "tuning value out of range");
   c->tune_ctas = ctas_per_sm;
   c->tune_block = block_threads;
@@ -854,10 +855,11 @@ static int32_t collect_columns(llkv_gpu_ctx* ctx, uint64_t table_id, std::vector
                            col->type == LLKV_PT_INT64 || col->type == LLKV_PT_DATE32 || col->type == LLKV_PT_DATE64;
     const bool is_unsigned = col->type == LLKV_PT_UINT8 || col->type == LLKV_PT_UINT16 || col->type == LLKV_PT_UINT32 ||
                              col->type == LLKV_PT_UINT64 || col->type == LLKV_PT_BOOLEAN;
-    if ((is_signed || is_unsigned) && col->n_rows && col->hstats.min_enc <= col->hstats.max_enc) {
+    const bool dec_narrow = col->type == LLKV_PT_DECIMAL128 && col->hstats.not_i64 == 0;
+    if ((is_signed || is_unsigned || dec_narrow) && col->n_rows && col->hstats.min_enc <= col->hstats.max_enc) {
       m.has_minmax = true;
-      m.min_bits = is_signed ? (col->hstats.min_enc ^ 0x8000000000000000ull) : col->hstats.min_enc;
-      m.max_bits = is_signed ? (col->hstats.max_enc ^ 0x8000000000000000ull) : col->hstats.max_enc;
+      m.min_bits = (is_signed || dec_narrow) ? (col->hstats.min_enc ^ 0x8000000000000000ull) : col->hstats.min_enc;
+      m.max_bits = (is_signed || dec_narrow) ? (col->hstats.max_enc ^ 0x8000000000000000ull) : col->hstats.max_enc;
     }
     m.max_strlen = (uint8_t)col->hstats.max_strlen;
     cols.push_back(m);
@@ -886,20 +888,22 @@ static u64 next_pow2(u64 v) {
 
 // Chooses block size, rows per thread, pipeline depth and CTA-local group slots so that the plan fits in shared memory,
 // and fills the launch-geometry / shared-memory fields of the plan.
-static int32_t plan_geometry(llkv_gpu_ctx* ctx, Plan& p, bool wide, uint64_t row_begin, uint64_t row_end, uint64_t hint,
+static int32_t plan_geometry(llkv_gpu_ctx* ctx, Plan& p, bool wide, bool fast, uint64_t row_begin, uint64_t row_end, uint64_t hint,
                              Geometry& g) {
   const uint32_t vbytes = wide ? 16u : 8u;
-  uint32_t NT = ctx->tune_block ? (uint32_t)ctx->tune_block : 512u;
-  uint32_t R = ctx->tune_rpt ? (uint32_t)ctx->tune_rpt : (wide ? 1u : 2u);
+  uint32_t NT = ctx->tune_block ? (uint32_t)ctx->tune_block : (fast ? 256u : 512u);
+  uint32_t R = ctx->tune_rpt ? (uint32_t)ctx->tune_rpt : (wide ? 1u : (fast ? 4u : 2u));
   if (wide && R > 2) R = 2;
-  uint32_t stages = ctx->tune_stages ? (uint32_t)ctx->tune_stages : 3u;
+  if (!fast && R > 4) R = 4;
+  uint32_t stages = ctx->tune_stages ? (uint32_t)ctx->tune_stages : (fast ? 2u : 3u);
+  if (fast && stages < 2) stages = 2;  // the lean kernel is always staged
   uint32_t ctas = ctx->tune_ctas ? (uint32_t)ctx->tune_ctas : 2u;
   uint32_t FG = 0;
   if (p.n_fast_words) {
     if (p.n_keys == 0) FG = 1;
     else if (hint == 0) FG = 16;
     else if (hint <= 128) FG = (uint32_t)next_pow2(hint + hint / 2 + 1);
-    else FG = 0;
+    else FG = fast ? 32 : 0;  // high cardinality: the lean kernel still folds the hottest keys per CTA, the rest go global
   }
   const uint32_t budget_total = (uint32_t)ctx->max_smem;
   for (int attempt = 0; attempt < 64; ++attempt) {
@@ -925,10 +929,17 @@ static int32_t plan_geometry(llkv_gpu_ctx* ctx, Plan& p, bool wide, uint64_t row
       off += stage_bytes * stages;
     }
     p.smem_acc_off = off;
-    off += align_up(FG * p.n_fast_words * NT * 8, 128);
-    p.smem_spill_off = off;
-    const uint32_t spill_slots = p.max_depth > 2 ? p.max_depth - 2 : 0;
-    off += align_up(spill_slots * R * NT * vbytes, 128);
+    if (fast) {
+      off += align_up(FG * p.n_fast_words * (NT / 32) * 8, 128);  // one accumulator row per warp and group slot
+      p.smem_spill_off = off;
+      p.smem_tmp_off = off;
+      off += align_up(p.fast_tmps * T * 8, 128);  // tile-sized temporaries of the accumulator machine
+    } else {
+      off += align_up(FG * p.n_fast_words * NT * 8, 128);
+      p.smem_spill_off = off;
+      const uint32_t spill_slots = p.max_depth > 2 ? p.max_depth - 2 : 0;
+      off += align_up(spill_slots * R * NT * vbytes, 128);
+    }
     p.smem_tbl_off = off;
     off += align_up((FG ? FG : 1) * 8, 128);
     const uint32_t per_cta_budget = budget_total / ctas - 1024;
@@ -959,8 +970,8 @@ static int32_t plan_geometry(llkv_gpu_ctx* ctx, Plan& p, bool wide, uint64_t row
     else if (R > 1) R /= 2;
     else if (FG > 4 && p.n_keys) FG /= 2;
     else if (NT > 128) NT /= 2;
-    else if (FG > 0 && p.n_keys) FG = 0;
-    else if (stages >= 2) stages = 1;
+    else if (FG > 0 && p.n_keys && !fast) FG = 0;
+    else if (stages >= 2 && !fast) stages = 1;
     else break;
   }
   return set_error(LLKV_ERR_INVALID_ARGUMENT, "query state does not fit in shared memory on this path");
@@ -1008,7 +1019,7 @@ extern "C" int32_t llkv_gpu_filter_bitmap(llkv_gpu_ctx* ctx, uint64_t table_id, 
   const uint64_t need_words = (row_end - row_begin + 63) / 64;
   if (out_words && n_words < need_words) return set_error(LLKV_ERR_INVALID_ARGUMENT, "bitmap buffer too small");
   req.bitmap_mode = true;
-  req.force_wide = ctx->tune_force_wide != 0;
+  req.force_wide = ctx->tune_force_wide == 1;
   u64* d_bits = nullptr;
   Plan* d_plan = nullptr;
   uint32_t* d_flags = nullptr;
@@ -1021,7 +1032,7 @@ extern "C" int32_t llkv_gpu_filter_bitmap(llkv_gpu_ctx* ctx, uint64_t table_id, 
     CompileResult cr;
     if ((rc = compile_plan(req, cr))) { result = set_error(rc, "%s", cr.error.c_str()); break; }
     Geometry g;
-    if ((rc = plan_geometry(ctx, cr.plan, cr.wide, row_begin, row_end, 0, g))) { result = rc; break; }
+    if ((rc = plan_geometry(ctx, cr.plan, cr.wide, false, row_begin, row_end, 0, g))) { result = rc; break; }
     cr.plan.out_bitmap = d_bits;
     cr.plan.out_count = d_bits + alloc_words;
     cr.plan.flags = d_flags;
@@ -1205,12 +1216,13 @@ static int32_t agg_launch(llkv_gpu_agg* a, const llkv_gpu_program* prog, int app
   req.n_agg_nodes = (int32_t)a->nodes.size();
   req.key_fields = a->keys;
   req.expr_mode = a->expr_mode;
-  req.force_wide = force_wide || ctx->tune_force_wide != 0;
+  req.force_wide = force_wide || ctx->tune_force_wide == 1;
+  req.no_fast = ctx->tune_force_wide != 0;
   if ((rc = compile_plan(req, a->cr))) return set_error(rc, "%s", a->cr.error.c_str());
   if ((rc = agg_freeze_layout(a, a->cr))) return rc;
   Plan& p = a->cr.plan;
   Geometry g;
-  if ((rc = plan_geometry(ctx, p, a->cr.wide, row_begin, row_end, a->hint, g))) return rc;
+  if ((rc = plan_geometry(ctx, p, a->cr.wide, a->cr.fast, row_begin, row_end, a->hint, g))) return rc;
   p.gkeys = a->gkeys;
   p.gwords = a->gwords;
   p.gcap = a->gcap;
@@ -1219,6 +1231,7 @@ static int32_t agg_launch(llkv_gpu_agg* a, const llkv_gpu_program* prog, int app
   if (need_backup && (rc = agg_backup(a))) return rc;
   a->pending.has_backup = need_backup;
   // per-thread i64 partial sums stay exact while a thread folds < 2^15 rows per launch: split very long scans
+  // (the lean kernel keeps one i64 partial per warp: < 2^20 rows per warp per launch keeps 2^40-bounded values exact)
   const u64 threads = (u64)g.grid * g.block;
   const u64 max_rows_per_launch = threads * 32000ull;
   a->pending.timed = ctx->timing;
@@ -1236,7 +1249,8 @@ static int32_t agg_launch(llkv_gpu_agg* a, const llkv_gpu_program* prog, int app
     memcpy(a->h_plan, &lp, sizeof(Plan));
     CUDA_TRY(cudaMemcpyAsync(a->d_plan, a->h_plan, sizeof(Plan), cudaMemcpyHostToDevice, ctx->stream));
     u64 grid = std::min<u64>(g.grid, lp.n_tiles);
-    CUDA_TRY(launch_scan(a->d_plan, a->cr.wide, (int)g.R, (uint32_t)grid, g.block, g.smem, ctx->stream));
+    if (a->cr.fast) CUDA_TRY(launch_fast(a->d_plan, (int)g.R, (uint32_t)grid, g.block, g.smem, ctx->stream));
+    else CUDA_TRY(launch_scan(a->d_plan, a->cr.wide, (int)g.R, (uint32_t)grid, g.block, g.smem, ctx->stream));
     ++launches;
     if (re >= row_end) break;
   }
@@ -1245,6 +1259,7 @@ static int32_t agg_launch(llkv_gpu_agg* a, const llkv_gpu_program* prog, int app
   a->info.rows = row_end - row_begin;
   a->info.kernel_launches = launches;
   a->info.used_wide_path = a->cr.wide ? 1 : 0;
+  a->info.used_fast_kernel = a->cr.fast ? 1 : 0;
   a->info.algorithmic_bytes_per_row = a->cr.algorithmic_bytes_per_row;
   a->info.physical_bytes_per_row = a->cr.physical_bytes_per_row;
   a->info.grid = g.grid;

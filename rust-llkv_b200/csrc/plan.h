@@ -8,6 +8,7 @@ namespace llkv {
 
 constexpr int kMaxCols = 24;
 constexpr int kMaxInstr = 320;
+constexpr int kMaxFastInstr = 96;      // lean-kernel program (fast_kernel.cu)
 constexpr int kMaxLits = 96;
 constexpr int kMaxNoncommitted = 32;
 constexpr int kMaxKeys = 8;
@@ -69,6 +70,42 @@ enum Op : uint16_t {
   OP_EMIT_BITMAP,
   OP_COUNT_
 };
+
+// ---- opcodes of the lean kernel (fast_kernel.cu): the hot subset of the machine above as an accumulator machine,
+// lowered by the compiler's range analysis for plans without NULLs whose values provably fit 64 bits.  One i64 (or f64
+// bits) accumulator per row lives in registers; other operands come straight from column tiles, literals or tile-sized
+// temporaries in shared memory.  No NULL flags, no overflow checks that the analysis proved dead.
+enum FastOp : uint16_t {
+  FO_END = 0,
+  FO_LEAF,        // a = column, b = LoadKind, c = literal index of (lo, hi): active &= lo <= v <= hi (signed unless LK_U*/LK_STR8)
+  FO_MVCC,        // a = created_by column, b = deleted_by column
+  FO_SELECT_DONE, // warp leaves the tile when no row is active
+  FO_GROUP,       // keys come from Plan::key_col[] (packed as Plan::key_*): CTA-local slot per row
+  FO_LD_COL,      // acc = column.            a = column, b = LoadKind
+  FO_LD_LIT,      // acc = literal.           c = literal index
+  FO_LD_TMP,      // acc = tmp[a]
+  FO_ST_TMP,      // tmp[a] = acc
+  FO_OP_COL,      // acc = acc op column.     a = FastBin | FB_REV (column op acc), b = LoadKind, c = column
+  FO_OP_LIT,      // acc = acc op literal.    a = FastBin | FB_REV, c = literal index
+  FO_OP_TMP,      // acc = acc op tmp[b].     a = FastBin | FB_REV
+  FO_DIVR,        // a = k, b = 0 signed / 1 non-negative / 2 non-negative and < 2^32: acc / 10^k rounded half away from zero
+  FO_MULP,        // a = k: acc * 10^k (proven not to overflow)
+  FO_I2F,         // i64 -> f64
+  FO_D2F,         // c = literal holding 10^scale as f64: (f64)acc / 10^scale
+  // aggregates over acc: b = per-warp word, c = global word
+  FO_COUNT_STAR, FO_COUNT, FO_FIRSTROW,
+  FO_SUM,         // a = 24-bit limbs needed for a lane's partial sum (1..3), 0 = not proven small (checked per value); a bit7 = 4-limb global layout
+  FO_FSUM, FO_MIN_I, FO_MAX_I, FO_MIN_F, FO_MAX_F, FO_FIRSTVALID, FO_FIRSTNAN,
+  FO_COUNT_
+};
+enum FastBin : uint8_t {
+  FB_ADD = 0, FB_SUB, FB_MUL,   // 64-bit, proven not to overflow
+  FB_MUL32,                      // both operands proven to fit i32
+  FB_ADD_CK, FB_SUB_CK, FB_MUL_CK,  // checked: overflow raises FLAG_NARROW_FAIL (the 128-bit interpreter decides what it means)
+  FB_ADD_F, FB_SUB_F, FB_MUL_F,
+  FB_REV = 0x80                  // operands swapped: (other) op acc
+};
+constexpr int kFastTmps = 3;     // tile-sized temporaries of the lean kernel
 
 enum KeyKind : uint8_t { KK_INT = 0, KK_STR = 1 };
 enum LoadKind : uint8_t { LK_I8, LK_I16, LK_I32, LK_I64, LK_U8, LK_U16, LK_U32, LK_U64, LK_F32, LK_F64, LK_D128, LK_STR8 };
@@ -149,6 +186,13 @@ struct Plan {
   uint32_t tx_bytes;              // bytes one tile's bulk copies deliver (mbarrier expect_tx)
   uint32_t fast_groups;           // CTA-local group slots with per-thread accumulators (power of two, 0 = none)
   uint32_t bitmap_mode;           // 1: OP_EMIT_BITMAP present -> never skip inactive warps
+  // ---- lean-kernel program (valid when n_finstr != 0)
+  uint32_t n_finstr;
+  uint32_t fast_tmps;             // tile-sized temporaries the lean program uses (<= kFastTmps)
+  uint32_t smem_tmp_off;          // their shared-memory offset (fast kernel)
+  Instr fcode[kMaxFastInstr];
+  uint8_t key_col[kMaxKeys];      // plan column index of each GROUP BY key
+  uint8_t key_load[kMaxKeys];     // its LoadKind
   // shared-memory layout (byte offsets from the dynamic smem base; all 128-byte aligned)
   uint32_t smem_plan_off, smem_bar_off, smem_stage_off, smem_acc_off, smem_spill_off, smem_tbl_off, smem_total;
   // ---- global state

@@ -33,61 +33,6 @@ __device__ __forceinline__ double as_f64(i64 v) { return __longlong_as_double(v)
 __device__ __forceinline__ double as_f64(i128 v) { return __longlong_as_double((i64)v); }
 __device__ __forceinline__ i64 f64_bits(double d) { return __double_as_longlong(d); }
 
-// ------------------------------------------------------------------ global group table
-__device__ __noinline__ u64 global_slot(const Plan& p, u64 K, bool key_is_null, uint32_t& errbits) {
-  if (p.n_keys == 0) return 0;
-  if (key_is_null) return p.gcap + 1;
-  if (K == kEmptyKey) return p.gcap;
-  const u64 mask = p.gcap - 1;
-  u64 h = mix64(K) & mask;
-  for (u64 i = 0; i <= mask; ++i) {
-    u64 cur = p.gkeys[h];
-    if (cur == K) return h;
-    if (cur == kEmptyKey) {
-      const u64 old = atomicCAS(&p.gkeys[h], kEmptyKey, K);
-      if (old == kEmptyKey || old == K) return h;
-    }
-    h = (h + 1) & mask;
-  }
-  errbits |= FLAG_TABLE_FULL;
-  return p.gcap;  // parked on the spare row; the flag makes the run fail
-}
-
-// exact integer value -> limb words (see FastKind)
-__device__ __forceinline__ void gadd_sum_i64(u64* w, i128 t) {
-  atomicAdd(&w[0], (u64)t & 0xffffffffull);
-  atomicAdd(&w[1], (u64)(i64)(t >> 32));
-}
-__device__ __forceinline__ void gadd_sum_i128(u64* w, i128 t) {
-  atomicAdd(&w[0], (u64)t & 0xffffffffull);
-  atomicAdd(&w[1], (u64)(t >> 32) & 0xffffffffull);
-  atomicAdd(&w[2], (u64)(t >> 64) & 0xffffffffull);
-  atomicAdd(&w[3], (u64)(i64)(t >> 96));
-}
-__device__ __forceinline__ void gmin128(u64* w, u64 hi_enc, u64 lo, bool is_max) {
-  // 16-byte CAS loop on (hi_enc, lo): lexicographic order of (hi_enc, lo) == numeric order of the i128
-  ulonglong2* addr = reinterpret_cast<ulonglong2*>(w);
-  u64 cur_hi = w[0], cur_lo = w[1];
-  while (true) {
-    const bool better = is_max ? (hi_enc > cur_hi || (hi_enc == cur_hi && lo > cur_lo))
-                               : (hi_enc < cur_hi || (hi_enc == cur_hi && lo < cur_lo));
-    if (!better) return;
-    u64 old_hi, old_lo;
-    asm volatile(
-        "{\n\t.reg .b128 cmp, swp, old;\n\t"
-        "mov.b128 cmp, {%2, %3};\n\t"
-        "mov.b128 swp, {%4, %5};\n\t"
-        "atom.global.cas.b128 old, [%6], cmp, swp;\n\t"
-        "mov.b128 {%0, %1}, old;\n\t}"
-        : "=l"(old_hi), "=l"(old_lo)
-        : "l"(cur_hi), "l"(cur_lo), "l"(hi_enc), "l"(lo), "l"(addr)
-        : "memory");
-    if (old_hi == cur_hi && old_lo == cur_lo) return;
-    cur_hi = old_hi;
-    cur_lo = old_lo;
-  }
-}
-
 // ------------------------------------------------------------------ the interpreter
 template <bool WIDE, int R>
 __global__ void __launch_bounds__(512) scan_kernel(const Plan* __restrict__ gplan) {

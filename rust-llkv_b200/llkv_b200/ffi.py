@@ -74,7 +74,8 @@ class RunInfo(C.Structure):
     _fields_ = [("rows", C.c_uint64), ("kernel_launches", C.c_uint32), ("used_wide_path", C.c_uint32),
                 ("algorithmic_bytes_per_row", C.c_uint32), ("physical_bytes_per_row", C.c_uint32),
                 ("grid", C.c_uint32), ("block", C.c_uint32), ("rows_per_tile", C.c_uint32), ("stages", C.c_uint32),
-                ("smem_bytes", C.c_uint32), ("fast_groups", C.c_uint32), ("last_kernel_ms", C.c_float)]
+                ("smem_bytes", C.c_uint32), ("fast_groups", C.c_uint32), ("last_kernel_ms", C.c_float),
+                ("used_fast_kernel", C.c_uint32)]
 
 
 def i128_to_words(v: int):

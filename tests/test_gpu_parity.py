@@ -407,8 +407,10 @@ def test_accumulators_fold_across_runs(gpu_ctx):
 
 
 @pytest.mark.parametrize("tuning", [dict(block_threads=128, rows_per_thread=1, stages=1), dict(block_threads=256, rows_per_thread=4, stages=2),
-                                    dict(block_threads=512, rows_per_thread=2, stages=4, ctas_per_sm=1), dict(force_wide=1)],
-                         ids=["direct-128x1", "staged-256x4", "staged-512x2x4", "wide"])
+                                    dict(block_threads=512, rows_per_thread=2, stages=4, ctas_per_sm=1), dict(force_wide=1),
+                                    dict(force_wide=2), dict(force_wide=2, block_threads=128, rows_per_thread=1, stages=1),
+                                    dict(block_threads=64, rows_per_thread=1, stages=2), dict(block_threads=128, rows_per_thread=8, ctas_per_sm=3)],
+                         ids=["lean-128x1", "lean-256x4", "lean-512x2x4", "wide", "general64", "general64-direct", "lean-64x1", "lean-128x8"])
 def test_every_kernel_geometry_agrees(gpu_ctx, tuning):
     t, snap = tpch.lineitem_table(60_000, seed=3, with_q1=True, with_mvcc=True)
     gpu_ctx.set_tuning(**tuning)
@@ -423,6 +425,45 @@ def test_every_kernel_geometry_agrees(gpu_ctx, tuning):
             dt.destroy()
     finally:
         gpu_ctx.set_tuning()
+
+
+def test_lean_kernel_runs_the_benchmark_plans(gpu_ctx):
+    """Q6, Q1 and the filtered SUM lower to the lean kernel; plans with NULLs / OR trees stay on the general interpreter."""
+    from llkv_b200 import gpu
+    t, snap = tpch.lineitem_table(50_000, seed=3, with_q1=True, with_mvcc=True)
+    dt = device_table(gpu_ctx, t)
+    try:
+        dt.set_snapshot(snap)
+        for expr, specs, keys, mvcc, want_fast in [
+            (tpch.q6_filter(), tpch.q6_aggregates(), (), False, 1),
+            (tpch.q1_filter(), tpch.q1_aggregates(), tpch.Q1_GROUP_BY, True, 1),
+            (Expr.Or([tpch.q1_filter(), tpch.q6_filter()]), tpch.q6_aggregates(), (), False, 0),
+        ]:
+            prog = gpu.Program(gpu_ctx, expr)
+            agg = gpu.Aggregation(dt, specs, keys, cardinality_hint=6 if keys else 0)
+            try:
+                agg.run(prog, mvcc)
+                agg.finalize(16)
+                assert agg.run_info().used_fast_kernel == want_fast
+            finally:
+                agg.destroy()
+                prog.destroy()
+    finally:
+        dt.destroy()
+    t2, snap2 = tpch.int64_table(10_000, seed=1)
+    dt = device_table(gpu_ctx, t2)
+    try:
+        dt.set_snapshot(snap2)
+        prog = gpu.Program(gpu_ctx, tpch.between_filter(tpch.X_FIELD, -5, 10**8))
+        agg = gpu.Aggregation(dt, tpch.sum_int64(tpch.X_FIELD))
+        agg.run(prog, True)
+        got = agg.finalize(1)
+        assert agg.run_info().used_fast_kernel == 1
+        util.assert_same_result(got, oracle.aggregate(t2, tpch.between_filter(tpch.X_FIELD, -5, 10**8), tpch.sum_int64(tpch.X_FIELD), snap2))
+        agg.destroy()
+        prog.destroy()
+    finally:
+        dt.destroy()
 
 
 def test_full_size_properties_q6(gpu_ctx):
