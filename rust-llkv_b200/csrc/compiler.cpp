@@ -1648,17 +1648,46 @@ class Emitter {
       if (c->nullable) return false;
       if (c->load_kind == LK_D128 && !c->dec_fits_i64) return false;
     }
-    std::vector<Instr> f;
+    std::vector<FInstr> f;
     std::vector<Sym> st;
     bool tmp_used[kFastTmps] = {false, false, false};
     int max_tmps = 0;
     bool ok = true;
-    auto femit = [&](uint16_t op, uint8_t a, uint8_t b, uint32_t c) {
-      Instr in;
+    auto map_load = [&](uint8_t lk) -> uint32_t {  // physical layouts the lean kernel reads
+      switch (lk) {
+        case LK_I32: return LKF_4;
+        case LK_I64: case LK_U64: case LK_F64: case LK_D64: return LKF_8;
+        case LK_D128: return LKF_16;
+        case LK_U8: return LKF_1;
+        case LK_STR8: return LKF_S1;
+        default: ok = false; return LKF_8;
+      }
+    };
+    auto femit = [&](uint16_t op, uint32_t a, uint32_t b, uint32_t c) {
+      FInstr in;
+      memset(&in, 0, sizeof(in));
       in.op = op;
       in.a = a;
       in.b = b;
       in.c = c;
+      // a pending "acc = ..." load folds into the instruction that consumes it
+      if (!f.empty() && (f.back().op == FO_LD_COL || f.back().op == FO_LD_LIT || f.back().op == FO_LD_TMP) && op != FO_LEAF &&
+          op != FO_MVCC && op != FO_SELECT_DONE && op != FO_GROUP && op != FO_END && op != FO_LD_COL && op != FO_LD_LIT &&
+          op != FO_LD_TMP && op != FO_COUNT_STAR && op != FO_FIRSTROW) {
+        in.d = f.back().d;
+        in.e = f.back().e;
+        in.f = f.back().f;
+        f.pop_back();
+      }
+      f.push_back(in);
+    };
+    auto femit_load = [&](uint16_t op, uint32_t d, uint32_t e, uint32_t ff) {
+      FInstr in;
+      memset(&in, 0, sizeof(in));
+      in.op = op;
+      in.d = d;
+      in.e = e;
+      in.f = ff;
       f.push_back(in);
     };
     auto free_sym = [&](const Sym& x) {
@@ -1682,10 +1711,10 @@ class Emitter {
     auto load_acc = [&](size_t i) {  // make entry i the accumulator
       if (st[i].where == Sym::ACC) return;
       spill_acc(i);
-      if (st[i].where == Sym::COL) femit(FO_LD_COL, st[i].col, st[i].load, 0);
-      else if (st[i].where == Sym::LIT) femit(FO_LD_LIT, 0, 0, st[i].lit);
+      if (st[i].where == Sym::COL) femit_load(FO_LD_COL, 2, st[i].col, map_load(st[i].load));
+      else if (st[i].where == Sym::LIT) femit_load(FO_LD_LIT, 1, st[i].lit, 0);
       else {
-        femit(FO_LD_TMP, st[i].tmp, 0, 0);
+        femit_load(FO_LD_TMP, 3, st[i].tmp, 0);
         tmp_used[st[i].tmp] = false;
       }
       st[i].where = Sym::ACC;
@@ -1700,7 +1729,7 @@ class Emitter {
       else if (b.where == Sym::ACC) { other = &a; rev = FB_REV; }
       else { load_acc(n - 2); other = &b; }
       if (!ok) return;
-      if (other->where == Sym::COL) femit(FO_OP_COL, fb | rev, other->load, other->col);
+      if (other->where == Sym::COL) femit(FO_OP_COL, fb | rev, map_load(other->load), other->col);
       else if (other->where == Sym::LIT) femit(FO_OP_LIT, fb | rev, 0, other->lit);
       else femit(FO_OP_TMP, fb | rev, other->tmp, 0);
       free_sym(*other);
@@ -1762,7 +1791,9 @@ class Emitter {
               std::vector<Lit> run = {a, b};
               if (lits_.size() + 2 > (size_t)kMaxLits) return false;
               const uint32_t first = add_lit_run(run);
-              femit(FO_LEAF, in.a, in.b, first);
+              femit(FO_LEAF, in.a, map_load(in.b), first);
+              f.back().g = uns ? 1u : 0u;
+              if (c.load_kind == LK_STR8 || c.load_kind == LK_U8 || c.load_kind == LK_U64) f.back().g = 1u;
               i += 2;
               break;
             }
@@ -1876,7 +1907,7 @@ class Emitter {
             if (x.where != Sym::COL) return false;
             st.pop_back();
             p.key_col[k] = x.col;
-            p.key_load[k] = x.load;
+            p.key_load[k] = (uint8_t)map_load(x.load);
           }
           femit(FO_GROUP, (uint8_t)nk, 0, 0);
           break;

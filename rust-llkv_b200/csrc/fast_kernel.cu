@@ -27,8 +27,33 @@ namespace llkv {
 __device__ __forceinline__ double f_as_f64(i64 v) { return __longlong_as_double(v); }
 __device__ __forceinline__ i64 f_bits(double d) { return __double_as_longlong(d); }
 
+// rows without a CTA-local group slot (more groups than slots) and values too large for the per-warp i64 partials go
+// straight to the global table, one atomic per row: rare, kept out of line
+static __device__ __noinline__ void slow_accumulate(const Plan& p, uint32_t op, uint32_t flags, u64 K, i64 v, u64 row, uint32_t gword,
+                                                    uint32_t& errbits) {
+  u64* w = &p.gwords[global_slot(p, K, false, errbits) * p.n_gwords + gword];
+  switch (op) {
+    case FO_COUNT_STAR: case FO_COUNT: atomicAdd(w, 1ull); break;
+    case FO_FIRSTROW: case FO_FIRSTVALID: case FO_FIRSTNAN: atomicMin(w, row); break;
+    case FO_SUM:
+      if (flags & 0x80) gadd_sum_i128(w, (i128)v);
+      else gadd_sum_i64(w, (i128)v);
+      break;
+    case FO_FSUM: atomicAdd(reinterpret_cast<double*>(w), f_as_f64(v)); break;
+    case FO_MIN_I: atomicMin(w, enc_i64(v)); break;
+    case FO_MAX_I: atomicMax(w, enc_i64(v)); break;
+    case FO_MIN_F: atomicMin(w, enc_f64(f_as_f64(v))); break;
+    default: atomicMax(w, enc_f64(f_as_f64(v))); break;
+  }
+}
+
+__device__ __forceinline__ void mbar_wait_backoff(void* bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  while (!mbar_try_wait(bar, parity)) __nanosleep(40);
+}
+
 template <int R>
-__global__ void __launch_bounds__(544, 1) fast_scan_kernel(const Plan* __restrict__ gplan) {
+__global__ void __launch_bounds__(R >= 8 ? 160 : 288, R >= 8 ? 3 : 2) fast_scan_kernel(const Plan* __restrict__ gplan) {
   extern __shared__ __align__(128) unsigned char smem[];
   const int tid = threadIdx.x;
   const int NC = blockDim.x - 32;  // consumer threads
@@ -82,7 +107,7 @@ __global__ void __launch_bounds__(544, 1) fast_scan_kernel(const Plan* __restric
     if (lane == 0) {
       for (u64 li = 0; li < my_tiles; ++li) {
         const uint32_t s = (uint32_t)(li % S);
-        if (li >= S) mbar_wait(&empty_bar[s], (uint32_t)(((li / S) - 1) & 1));
+        if (li >= S) mbar_wait_backoff(&empty_bar[s], (uint32_t)(((li / S) - 1) & 1));
         const u64 tile = p.first_tile + blockIdx.x + li * gridDim.x;
         unsigned char* sb = stage0 + (size_t)s * p.stage_bytes;
         mbar_arrive_expect_tx(&full_bar[s], p.tx_bytes);
@@ -101,14 +126,16 @@ __global__ void __launch_bounds__(544, 1) fast_scan_kernel(const Plan* __restric
       const uint32_t s = (uint32_t)(li % S);
       const u64 tile = p.first_tile + blockIdx.x + li * gridDim.x;
       const u64 row0 = tile * (u64)T;
-      mbar_wait(&full_bar[s], (uint32_t)((li / S) & 1));
+      mbar_wait_backoff(&full_bar[s], (uint32_t)((li / S) & 1));
       const unsigned char* sb = stage0 + (size_t)s * p.stage_bytes;
 
       // per-row state kept in registers across ops: the accumulator, the active bit and the CTA-local group slot
       i64 acc[R];
       int slot[R];
       unsigned actm = 0;       // bit r: row r of this thread is selected
+      unsigned negm = 0;       // bit r: selected row without a CTA-local group slot (goes to the global table directly)
       unsigned present = 1u;   // CTA-local group slots present among this warp's selected rows (ungrouped: slot 0)
+      bool has_slow = false;   // warp-uniform: some lane has a row in negm
 #pragma unroll
       for (int r = 0; r < R; ++r) {
         const u64 row = row0 + (u64)r * NC + tid;
@@ -117,50 +144,24 @@ __global__ void __launch_bounds__(544, 1) fast_scan_kernel(const Plan* __restric
         slot[r] = 0;
       }
 
-      // one column's R values as sign/zero-extended i64 (f32 widened to f64 bits)
+      // one column's R values as sign/zero-extended i64.  The lean kernel knows four physical layouts.
       auto load_col = [&](uint32_t col, uint32_t kind, i64 (&out)[R]) {
         const unsigned char* base = sb + p.cols[col].smem_off;
-        switch (kind) {
-          case LK_I32:
+        if (kind == LKF_8) {
 #pragma unroll
-            for (int r = 0; r < R; ++r) out[r] = reinterpret_cast<const int*>(base)[r * NC + tid];
-            break;
-          case LK_I64: case LK_U64: case LK_F64:
+          for (int r = 0; r < R; ++r) out[r] = reinterpret_cast<const i64*>(base)[r * NC + tid];
+        } else if (kind == LKF_4) {
 #pragma unroll
-            for (int r = 0; r < R; ++r) out[r] = reinterpret_cast<const i64*>(base)[r * NC + tid];
-            break;
-          case LK_D128:  // values proven to be sign-extended i64: the low half is the value
+          for (int r = 0; r < R; ++r) out[r] = reinterpret_cast<const int*>(base)[r * NC + tid];
+        } else if (kind == LKF_16) {  // Decimal128 proven to hold sign-extended i64 values: the low half is the value
 #pragma unroll
-            for (int r = 0; r < R; ++r) out[r] = reinterpret_cast<const i64*>(base)[2 * (r * NC + tid)];
-            break;
-          case LK_U32:
+          for (int r = 0; r < R; ++r) out[r] = reinterpret_cast<const i64*>(base)[2 * (r * NC + tid)];
+        } else if (kind == LKF_1) {
 #pragma unroll
-            for (int r = 0; r < R; ++r) out[r] = reinterpret_cast<const unsigned int*>(base)[r * NC + tid];
-            break;
-          case LK_I16:
+          for (int r = 0; r < R; ++r) out[r] = base[r * NC + tid];
+        } else {  // LKF_S1: one-byte strings as packed keys
 #pragma unroll
-            for (int r = 0; r < R; ++r) out[r] = reinterpret_cast<const short*>(base)[r * NC + tid];
-            break;
-          case LK_U16:
-#pragma unroll
-            for (int r = 0; r < R; ++r) out[r] = reinterpret_cast<const unsigned short*>(base)[r * NC + tid];
-            break;
-          case LK_I8:
-#pragma unroll
-            for (int r = 0; r < R; ++r) out[r] = reinterpret_cast<const signed char*>(base)[r * NC + tid];
-            break;
-          case LK_U8:
-#pragma unroll
-            for (int r = 0; r < R; ++r) out[r] = base[r * NC + tid];
-            break;
-          case LK_STR8:
-#pragma unroll
-            for (int r = 0; r < R; ++r) out[r] = (i64)(((u64)base[r * NC + tid] << 56) | 1ull);
-            break;
-          default:  // LK_F32
-#pragma unroll
-            for (int r = 0; r < R; ++r) out[r] = f_bits((double)reinterpret_cast<const float*>(base)[r * NC + tid]);
-            break;
+          for (int r = 0; r < R; ++r) out[r] = (i64)(((u64)base[r * NC + tid] << 56) | 1ull);
         }
       };
       // acc = acc op other  (rev: other op acc)
@@ -208,24 +209,19 @@ __global__ void __launch_bounds__(544, 1) fast_scan_kernel(const Plan* __restric
             break;
         }
       };
-      // packed GROUP BY key of row r (recomputed on the slow path only)
+      // packed GROUP BY key of row r
       auto row_key = [&](int r) -> u64 {
         u64 K = 0;
         int shift = 0;
         for (uint32_t k = 0; k < p.n_keys; ++k) {
           const unsigned char* base = sb + p.cols[p.key_col[k]].smem_off;
           const uint32_t i = (uint32_t)(r * NC + tid);
+          const uint32_t kind = p.key_load[k];
           i64 v;
-          switch (p.key_load[k]) {
-            case LK_I8: v = reinterpret_cast<const signed char*>(base)[i]; break;
-            case LK_I16: v = reinterpret_cast<const short*>(base)[i]; break;
-            case LK_I32: v = reinterpret_cast<const int*>(base)[i]; break;
-            case LK_U8: v = base[i]; break;
-            case LK_U16: v = reinterpret_cast<const unsigned short*>(base)[i]; break;
-            case LK_U32: v = reinterpret_cast<const unsigned int*>(base)[i]; break;
-            case LK_STR8: v = (i64)(((u64)base[i] << 56) | 1ull); break;
-            default: v = reinterpret_cast<const i64*>(base)[i]; break;
-          }
+          if (kind == LKF_S1) v = (i64)(((u64)base[i] << 56) | 1ull);
+          else if (kind == LKF_1) v = base[i];
+          else if (kind == LKF_4) v = reinterpret_cast<const int*>(base)[i];
+          else v = reinterpret_cast<const i64*>(base)[i];
           const int bits = p.key_bits[k];
           u64 f;
           if (p.key_kind[k] == KK_STR) {
@@ -240,53 +236,61 @@ __global__ void __launch_bounds__(544, 1) fast_scan_kernel(const Plan* __restric
         }
         return K;
       };
-      auto global_row = [&](int r) -> u64* {  // the group row of a row that has no CTA-local slot
-        return &p.gwords[global_slot(p, row_key(r), false, errbits) * p.n_gwords];
+      auto slow_rows = [&](uint32_t op, uint32_t flags, unsigned rows, uint32_t gword) {  // warp-uniform guard at the call site
+#pragma unroll
+        for (int r = 0; r < R; ++r)
+          if ((rows >> r) & 1u) slow_accumulate(p, op, flags, row_key(r), acc[r], row0 + (u64)r * NC + tid, gword, errbits);
       };
 
-      for (uint32_t pc = 0; pc < p.n_finstr; ++pc) {
-        const Instr in = p.fcode[pc];
+      uint32_t pc = 0;
+      FInstr in = p.fcode[0];
+      while (true) {
+        // optional operand pre-load fused into the instruction: acc = literal / column / temporary
+        if (in.d) {
+          if (in.d == 2) load_col(in.e, in.f, acc);
+          else if (in.d == 1) {
+            const i64 v = (i64)p.lits[in.e].lo;
+#pragma unroll
+            for (int r = 0; r < R; ++r) acc[r] = v;
+          } else {
+            const i64* t = tmp_base + (size_t)in.e * T;
+#pragma unroll
+            for (int r = 0; r < R; ++r) acc[r] = t[r * NC + tid];
+          }
+        }
+        bool done = false;
         switch (in.op) {
-          case FO_END: pc = p.n_finstr; break;
-
           case FO_LEAF: {
-            const Lit lo = p.lits[in.c], hi = p.lits[in.c + 1];
-            const unsigned char* base = sb + p.cols[in.a].smem_off;
-            unsigned m = 0;
-            switch (in.b) {
-              case LK_I32: {
+            // consecutive leaves run back to back without going through the dispatcher again
+            do {
+              const Lit lo = p.lits[in.c], hi = p.lits[in.c + 1];
+              const unsigned char* base = sb + p.cols[in.a].smem_off;
+              unsigned m = 0;
+              if (in.b == LKF_4) {
                 const int l = (int)(i64)lo.lo, h = (int)(i64)hi.lo;
 #pragma unroll
                 for (int r = 0; r < R; ++r) {
                   const int v = reinterpret_cast<const int*>(base)[r * NC + tid];
                   m |= (unsigned)(v >= l && v <= h) << r;
                 }
-                break;
-              }
-              case LK_D128: case LK_I64: {
+              } else if ((in.b == LKF_8 || in.b == LKF_16) && !in.g) {
                 const i64 l = (i64)lo.lo, h = (i64)hi.lo;
-                const int stride = in.b == LK_D128 ? 2 : 1;
+                const int stride = in.b == LKF_16 ? 2 : 1;
 #pragma unroll
                 for (int r = 0; r < R; ++r) {
                   const i64 v = reinterpret_cast<const i64*>(base)[stride * (r * NC + tid)];
                   m |= (unsigned)(v >= l && v <= h) << r;
                 }
-                break;
-              }
-              default: {
+              } else {  // unsigned 8-byte / 1-byte kinds
                 i64 v[R];
                 load_col(in.a, in.b, v);
-                const bool uns = in.b == LK_U8 || in.b == LK_U16 || in.b == LK_U32 || in.b == LK_U64 || in.b == LK_STR8;
 #pragma unroll
-                for (int r = 0; r < R; ++r) {
-                  const bool ok = uns ? ((u64)v[r] >= lo.lo && (u64)v[r] <= hi.lo) : (v[r] >= (i64)lo.lo && v[r] <= (i64)hi.lo);
-                  m |= (unsigned)ok << r;
-                }
-                break;
+                for (int r = 0; r < R; ++r) m |= (unsigned)((u64)v[r] >= lo.lo && (u64)v[r] <= hi.lo) << r;
               }
-            }
-            actm &= m;
-            break;
+              actm &= m;
+              in = p.fcode[++pc];
+            } while (in.op == FO_LEAF);
+            continue;
           }
           case FO_MVCC: {
             // RowVersion::is_visible_for (llkv-transaction/src/mvcc.rs:282-334)
@@ -319,7 +323,7 @@ __global__ void __launch_bounds__(544, 1) fast_scan_kernel(const Plan* __restric
             break;
           }
           case FO_SELECT_DONE:
-            if (!__any_sync(FULL, actm != 0)) pc = p.n_finstr;
+            if (!__any_sync(FULL, actm != 0)) done = true;
             break;
           case FO_GROUP: {
             unsigned mine = 0;
@@ -345,24 +349,14 @@ __global__ void __launch_bounds__(544, 1) fast_scan_kernel(const Plan* __restric
               sl = __shfl_sync(FULL, sl, __ffs(peers) - 1);
               slot[r] = usable ? sl : -1;
               if (usable && sl >= 0) mine |= 1u << sl;
+              if (a && !(usable && sl >= 0)) negm |= 1u << r;
             }
             present = __reduce_or_sync(FULL, mine);
+            has_slow = __any_sync(FULL, negm != 0);
             break;
           }
 
-          case FO_LD_COL: load_col(in.a, in.b, acc); break;
-          case FO_LD_LIT: {
-            const i64 v = (i64)p.lits[in.c].lo;
-#pragma unroll
-            for (int r = 0; r < R; ++r) acc[r] = v;
-            break;
-          }
-          case FO_LD_TMP: {
-            const i64* t = tmp_base + (size_t)in.a * T;
-#pragma unroll
-            for (int r = 0; r < R; ++r) acc[r] = t[r * NC + tid];
-            break;
-          }
+          case FO_LD_COL: case FO_LD_LIT: case FO_LD_TMP: break;  // the pre-load above is the whole instruction
           case FO_ST_TMP: {
             i64* t = tmp_base + (size_t)in.a * T;
 #pragma unroll
@@ -434,14 +428,13 @@ __global__ void __launch_bounds__(544, 1) fast_scan_kernel(const Plan* __restric
           // ------------------------------------------------------------ aggregates: group-major over the slots present
           // in this warp; a lane first folds its own R rows, then the warp reduces once per group
           case FO_COUNT_STAR: case FO_COUNT: {
-#pragma unroll
-            for (int r = 0; r < R; ++r)
-              if (((actm >> r) & 1u) && slot[r] < 0) atomicAdd(&global_row(r)[in.c], 1ull);
+            if (has_slow) slow_rows(in.op, in.a, negm, in.c);
+            const unsigned okm = actm & ~negm;
             for (unsigned gm = present; gm; gm &= gm - 1) {
               const int g = __ffs(gm) - 1;
               unsigned c = 0;
 #pragma unroll
-              for (int r = 0; r < R; ++r) c += ((actm >> r) & 1u) && slot[r] == g;
+              for (int r = 0; r < R; ++r) c += ((okm >> r) & 1u) && slot[r] == g;
               c = __reduce_add_sync(FULL, c);
               if (lane == 0) my_acc[(uint32_t)g * NFW + in.b] += c;
             }
@@ -456,9 +449,8 @@ __global__ void __launch_bounds__(544, 1) fast_scan_kernel(const Plan* __restric
                 if (d == d) setm &= ~(1u << r);
               }
             }
-#pragma unroll
-            for (int r = 0; r < R; ++r)
-              if (((setm >> r) & 1u) && slot[r] < 0) atomicMin(&global_row(r)[in.c], row0 + (u64)r * NC + tid);
+            if (has_slow) slow_rows(in.op, in.a, setm & negm, in.c);
+            setm &= ~negm;
             for (unsigned gm = present; gm; gm &= gm - 1) {
               const int g = __ffs(gm) - 1;
               unsigned off = 0xffffffffu;
@@ -476,20 +468,17 @@ __global__ void __launch_bounds__(544, 1) fast_scan_kernel(const Plan* __restric
           }
           case FO_SUM: {
             const int limbs = in.a & 3;  // 0: check each value
-            const bool wide_sum = (in.a & 0x80) != 0;
-            unsigned fastm = actm;
+            unsigned fastm = actm & ~negm;
             if (limbs == 0) {
+              unsigned bigm = 0;
 #pragma unroll
               for (int r = 0; r < R; ++r)
-                if (!(acc[r] < ((i64)1 << 40) && acc[r] > -((i64)1 << 40))) fastm &= ~(1u << r);
-            }
-#pragma unroll
-            for (int r = 0; r < R; ++r) {
-              if (((actm >> r) & 1u) && (slot[r] < 0 || !((fastm >> r) & 1u))) {
-                u64* w = &global_row(r)[in.c];
-                if (wide_sum) gadd_sum_i128(w, (i128)acc[r]);
-                else gadd_sum_i64(w, (i128)acc[r]);
-              }
+                if (!(acc[r] < ((i64)1 << 40) && acc[r] > -((i64)1 << 40))) bigm |= 1u << r;
+              bigm &= actm;
+              if (__any_sync(FULL, (bigm | negm) != 0)) slow_rows(FO_SUM, in.a, bigm | negm, in.c);
+              fastm &= ~bigm;
+            } else if (has_slow) {
+              slow_rows(FO_SUM, in.a, negm, in.c);
             }
             for (unsigned gm = present; gm; gm &= gm - 1) {
               const int g = __ffs(gm) - 1;
@@ -499,7 +488,7 @@ __global__ void __launch_bounds__(544, 1) fast_scan_kernel(const Plan* __restric
                 if (((fastm >> r) & 1u) && slot[r] == g) x += acc[r];
               i64 tot;
               if (limbs == 1) {
-                tot = (i64)__reduce_add_sync(FULL, (int)x);  // |x| < 2^23 per lane
+                tot = (i64)__reduce_add_sync(FULL, (int)x);  // |x| < 2^24 per lane
               } else if (limbs == 2) {
                 const unsigned lo24 = __reduce_add_sync(FULL, (unsigned)((u64)x & 0xffffffull));
                 const int hi = __reduce_add_sync(FULL, (int)(x >> 24));
@@ -518,15 +507,14 @@ __global__ void __launch_bounds__(544, 1) fast_scan_kernel(const Plan* __restric
             break;
           }
           case FO_FSUM: {
-#pragma unroll
-            for (int r = 0; r < R; ++r)
-              if (((actm >> r) & 1u) && slot[r] < 0) atomicAdd(reinterpret_cast<double*>(&global_row(r)[in.c]), f_as_f64(acc[r]));
+            if (has_slow) slow_rows(FO_FSUM, in.a, negm, in.c);
+            const unsigned okm = actm & ~negm;
             for (unsigned gm = present; gm; gm &= gm - 1) {
               const int g = __ffs(gm) - 1;
               double x = 0.0;
 #pragma unroll
               for (int r = 0; r < R; ++r)
-                if (((actm >> r) & 1u) && slot[r] == g) x += f_as_f64(acc[r]);
+                if (((okm >> r) & 1u) && slot[r] == g) x += f_as_f64(acc[r]);
               for (int o = 16; o; o >>= 1) x += __shfl_xor_sync(FULL, x, o);
               if (lane == 0) {
                 u64* a = &my_acc[(uint32_t)g * NFW + in.b];
@@ -547,12 +535,9 @@ __global__ void __launch_bounds__(544, 1) fast_scan_kernel(const Plan* __restric
                 if (d != d) setm &= ~(1u << r);  // NaN never replaces a number (llkv-aggregate/src/lib.rs:1309-1331)
                 e[r] = enc_f64(d);
               } else e[r] = enc_i64(acc[r]);
-              if (((setm >> r) & 1u) && slot[r] < 0) {
-                u64* w = &global_row(r)[in.c];
-                if (is_min) atomicMin(w, e[r]);
-                else atomicMax(w, e[r]);
-              }
             }
+            if (has_slow) slow_rows(in.op, in.a, setm & negm, in.c);
+            setm &= ~negm;
             for (unsigned gm = present; gm; gm &= gm - 1) {
               const int g = __ffs(gm) - 1;
               u64 x = is_min ? ~0ull : 0ull;
@@ -570,8 +555,11 @@ __global__ void __launch_bounds__(544, 1) fast_scan_kernel(const Plan* __restric
             }
             break;
           }
-          default: errbits |= FLAG_BAD_PLAN; pc = p.n_finstr; break;
+          case FO_END: done = true; break;
+          default: errbits |= FLAG_BAD_PLAN; done = true; break;
         }
+        if (done) break;
+        in = p.fcode[++pc];
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(&empty_bar[s]);  // this warp is done with the stage

@@ -127,6 +127,15 @@ __global__ void pack_utf8_kernel(const int* __restrict__ off, const unsigned cha
 __global__ void narrow_str_kernel(const u64* __restrict__ in, unsigned char* __restrict__ out, u64 n) {
   for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (u64)gridDim.x * blockDim.x) out[i] = (unsigned char)(in[i] >> 56);
 }
+__global__ void narrow_dec_kernel(const ulonglong2* __restrict__ in, u64* __restrict__ out, u64 n) {
+  for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (u64)gridDim.x * blockDim.x) out[i] = in[i].x;
+}
+__global__ void widen_dec_kernel(const u64* __restrict__ in, ulonglong2* __restrict__ out, u64 n) {
+  for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (u64)gridDim.x * blockDim.x) {
+    const u64 v = in[i];
+    out[i] = make_ulonglong2(v, (u64)((i64)v >> 63));
+  }
+}
 __global__ void widen_str_kernel(const unsigned char* __restrict__ in, u64* __restrict__ out, u64 n) {
   for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (u64)gridDim.x * blockDim.x) out[i] = ((u64)in[i] << 56) | 1ull;
 }
@@ -227,6 +236,7 @@ struct llkv_gpu_ctx {
   std::map<uint64_t, MvccState> mvcc;            // table id -> snapshot
   bool timing = false;
   int tune_ctas = 0, tune_block = 0, tune_stages = 0, tune_rpt = 0, tune_force_wide = 0;
+  bool keep_wide_decimals = false;  // LLKV_GPU_KEEP_WIDE_DECIMALS=1: never narrow Decimal128 columns at seal
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   void* nccl_comm = nullptr;
   int n_ranks = 1, rank = 0;
@@ -353,6 +363,10 @@ extern "C" int32_t llkv_gpu_ctx_create(int32_t device_ordinal, int32_t n_streams
   c->device = device_ordinal;
   c->sm_count = prop.multiProcessorCount;
   c->max_smem = (int)prop.sharedMemPerBlockOptin;
+  {
+    const char* e = getenv("LLKV_GPU_KEEP_WIDE_DECIMALS");
+    c->keep_wide_decimals = e && e[0] == '1';
+  }
   if (n_streams < 1) n_streams = 2;
   if (n_streams > 16) n_streams = 16;
   if (pinned_bytes < ((uint64_t)n_streams << 20)) pinned_bytes = (uint64_t)n_streams << 22;
@@ -621,6 +635,19 @@ extern "C" int32_t llkv_gpu_column_append_chunk(llkv_gpu_column* col, uint64_t c
     col->elem_bytes = 8;
     col->load_kind = LK_U64;
   }
+  if (col->load_kind == LK_D64) {  // sealed as i64: back to the Arrow layout before more chunks arrive
+    ulonglong2* wide = nullptr;
+    CUDA_TRY(cudaDeviceSynchronize());
+    CUDA_TRY(cudaMalloc((void**)&wide, col->cap_rows * 16));
+    CUDA_TRY(cudaMemset(wide, 0, col->cap_rows * 16));
+    widen_dec_kernel<<<1184, 256>>>((const u64*)col->values, wide, col->n_rows);
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaDeviceSynchronize());
+    CUDA_TRY(cudaFree(col->values));
+    col->values = wide;
+    col->elem_bytes = 16;
+    col->load_kind = LK_D128;
+  }
   int32_t rc = column_grow(col, col->n_rows + n_rows);
   if (rc) return rc;
   cudaStream_t s = c->copy_streams[(size_t)col->stream_index];
@@ -690,7 +717,7 @@ extern "C" int32_t llkv_gpu_column_seal(llkv_gpu_column* col) {
   for (cudaStream_t s : c->copy_streams) CUDA_TRY(cudaStreamSynchronize(s));
   for (void* p : col->deferred_free) cudaFree(p);
   col->deferred_free.clear();
-  if (col->stats_rows < col->n_rows && col->load_kind != LK_STR8) {  // min / max / fits-i64 over the rows appended since the last seal
+  if (col->stats_rows < col->n_rows && col->load_kind != LK_STR8 && col->load_kind != LK_D64) {  // min / max / fits-i64 over the rows appended since the last seal
     int32_t rc = launch_stats(col, col->stats_rows, col->n_rows - col->stats_rows);
     if (rc) return rc;
     CUDA_TRY(cudaStreamSynchronize(c->copy_streams[(size_t)col->stream_index]));
@@ -715,6 +742,20 @@ extern "C" int32_t llkv_gpu_column_seal(llkv_gpu_column* col) {
       col->load_kind = LK_STR8;
     }
   }
+  // Decimal128 whose every value is a sign-extended i64: keep 8 bytes per row resident (half the HBM traffic and half
+  // the shared-memory tile of every scan); the Arrow layout is restored if more chunks are appended
+  if (col->type == LLKV_PT_DECIMAL128 && col->load_kind == LK_D128 && col->n_rows && col->hstats.not_i64 == 0 && !c->keep_wide_decimals) {
+    u64* nv = nullptr;
+    CUDA_TRY(cudaMalloc((void**)&nv, col->cap_rows * 8));
+    CUDA_TRY(cudaMemset(nv, 0, col->cap_rows * 8));
+    narrow_dec_kernel<<<1184, 256>>>((const ulonglong2*)col->values, nv, col->n_rows);
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaDeviceSynchronize());
+    CUDA_TRY(cudaFree(col->values));
+    col->values = nv;
+    col->elem_bytes = 8;
+    col->load_kind = LK_D64;
+  }
   col->sealed = true;
   return LLKV_OK;
 }
@@ -737,6 +778,13 @@ extern "C" int32_t llkv_gpu_column_clear(llkv_gpu_column* col) {
     col->cap_rows = 0;
     col->elem_bytes = 8;
     col->load_kind = LK_U64;
+  }
+  if (col->load_kind == LK_D64) {  // back to the Arrow layout for new appends
+    if (col->values) CUDA_TRY(cudaFree(col->values));
+    col->values = nullptr;
+    col->cap_rows = 0;
+    col->elem_bytes = 16;
+    col->load_kind = LK_D128;
   }
   if (col->validity) CUDA_TRY(cudaMemsetAsync(col->validity, 0, (col->cap_rows / 32 + 4) * 4, s));
   DevStats init;
@@ -891,13 +939,17 @@ static u64 next_pow2(u64 v) {
 static int32_t plan_geometry(llkv_gpu_ctx* ctx, Plan& p, bool wide, bool fast, uint64_t row_begin, uint64_t row_end, uint64_t hint,
                              Geometry& g) {
   const uint32_t vbytes = wide ? 16u : 8u;
-  uint32_t NT = ctx->tune_block ? (uint32_t)ctx->tune_block : (fast ? 256u : 512u);
+  uint32_t NT = ctx->tune_block ? (uint32_t)ctx->tune_block : (fast ? 128u : 512u);
   uint32_t R = ctx->tune_rpt ? (uint32_t)ctx->tune_rpt : (wide ? 1u : (fast ? 4u : 2u));
   if (wide && R > 2) R = 2;
   if (!fast && R > 4) R = 4;
+  if (fast) {  // launch bounds of fast_scan_kernel<R>
+    const uint32_t cap = R >= 8 ? 128u : 256u;
+    if (NT > cap) NT = cap;
+  }
   uint32_t stages = ctx->tune_stages ? (uint32_t)ctx->tune_stages : (fast ? 2u : 3u);
   if (fast && stages < 2) stages = 2;  // the lean kernel is always staged
-  uint32_t ctas = ctx->tune_ctas ? (uint32_t)ctx->tune_ctas : 2u;
+  uint32_t ctas = ctx->tune_ctas ? (uint32_t)ctx->tune_ctas : (fast ? 4u : 2u);
   uint32_t FG = 0;
   if (p.n_fast_words) {
     if (p.n_keys == 0) FG = 1;

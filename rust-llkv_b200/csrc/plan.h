@@ -108,7 +108,8 @@ enum FastBin : uint8_t {
 constexpr int kFastTmps = 3;     // tile-sized temporaries of the lean kernel
 
 enum KeyKind : uint8_t { KK_INT = 0, KK_STR = 1 };
-enum LoadKind : uint8_t { LK_I8, LK_I16, LK_I32, LK_I64, LK_U8, LK_U16, LK_U32, LK_U64, LK_F32, LK_F64, LK_D128, LK_STR8 };
+enum LoadKind : uint8_t { LK_I8, LK_I16, LK_I32, LK_I64, LK_U8, LK_U16, LK_U32, LK_U64, LK_F32, LK_F64, LK_D128, LK_STR8,
+                          LK_D64 };  // Decimal128 column kept as i64 in HBM: every value is a sign-extended i64 (narrowed at seal)
 
 // classes of accumulator words: how a word is initialised, merged across CTAs / launches / ranks
 enum WordClass : uint8_t {
@@ -133,6 +134,14 @@ struct Instr {
   uint8_t a, b;
   uint32_t c;
 };
+
+struct FInstr {  // lean-kernel instruction, pre-decoded (two 16-byte shared-memory loads, no field unpacking)
+  uint32_t op, a, b, c;
+  uint32_t d, e, f;  // fused operand pre-load: d = 0 none / 1 acc = literal e / 2 acc = column e of FastLoad f / 3 acc = tmp e
+  uint32_t g;        // FO_LEAF: 1 = unsigned comparison
+};
+// physical layouts the lean kernel reads (everything else stays on the general interpreter)
+enum FastLoad : uint32_t { LKF_4 = 0, LKF_8 = 1, LKF_16 = 2, LKF_1 = 3, LKF_S1 = 4 };
 
 struct Lit {
   unsigned long long lo, hi;
@@ -190,7 +199,7 @@ struct Plan {
   uint32_t n_finstr;
   uint32_t fast_tmps;             // tile-sized temporaries the lean program uses (<= kFastTmps)
   uint32_t smem_tmp_off;          // their shared-memory offset (fast kernel)
-  Instr fcode[kMaxFastInstr];
+  FInstr fcode[kMaxFastInstr];
   uint8_t key_col[kMaxKeys];      // plan column index of each GROUP BY key
   uint8_t key_load[kMaxKeys];     // its LoadKind
   // shared-memory layout (byte offsets from the dynamic smem base; all 128-byte aligned)
