@@ -1040,8 +1040,13 @@ class Emitter {
     int kind = 0;  // 0 Null, 1 Integer, 2 Float, 3 Decimal
     int scale = 0;
   };
+  int reuse_node_ = -1;  // exact mode: this node's value is already on top of the stack (kept by the previous aggregate)
   ExactKind emit_exact(int idx) {
     check_node(idx);
+    if (idx == reuse_node_) {
+      reuse_node_ = -1;
+      return exact_kind(idx);
+    }
     const llkv_scalar_node& nd = nodes_[idx];
     ExactKind out;
     switch (nd.tag) {
@@ -1346,9 +1351,30 @@ class Emitter {
       const std::vector<bool> stack_mark = nullable_;
       const std::map<std::string, int> facts_mark = facts_;
       const bool wide_mark = wide_, cnf_mark = can_narrow_fail_;
+      // common prefix: when the next aggregate's argument is `this argument <op> something`, the value stays on the stack
+      // (TPC-H Q1: sum(price*(1-disc)) then sum(price*(1-disc)*(1+tax)))
+      bool keep_for_next = false;
+      int next_left = -1;
+      if (req_.expr_mode == LLKV_EXPR_EXACT && a + 1 < req_.n_aggs && sp.expr_root >= 0 && req_.specs[a + 1].expr_root >= 0 &&
+          nodes_[sp.expr_root].tag == LLKV_SE_BINARY && nodes_[req_.specs[a + 1].expr_root].tag == LLKV_SE_BINARY) {
+        next_left = nodes_[req_.specs[a + 1].expr_root].left;
+        if (next_left >= 0 && next_left < n_nodes_ && signature(next_left) == signature(sp.expr_root) && reuse_node_ < 0) keep_for_next = true;
+      }
+      const bool had_reuse = reuse_node_ >= 0;
       try {
-        emit_one_aggregate(sp, L, rows.g);
+        emit_one_aggregate(sp, L, rows.g, keep_for_next);
+        if (had_reuse && reuse_node_ >= 0) {  // the kept value was not needed after all
+          reuse_node_ = -1;
+          emit(OP_POP, 0, 0, 0);
+          popped();
+        }
+        if (keep_for_next) {
+          if (kept_on_stack_) reuse_node_ = next_left;
+          kept_on_stack_ = false;
+        }
       } catch (const CompileError& e) {
+        reuse_node_ = -1;
+        kept_on_stack_ = false;
         code_.resize(code_mark);
         lits_.resize(lits_mark);
         gclass_.resize(g_mark);
@@ -1374,7 +1400,8 @@ class Emitter {
     bool after_numeric_cast;  // operates on the array_value_to_numeric (f64) image of the argument
   };
 
-  void emit_one_aggregate(const llkv_agg_spec& sp, AggLayout& L, int rows_word) {
+  bool kept_on_stack_ = false;
+  void emit_one_aggregate(const llkv_agg_spec& sp, AggLayout& L, int rows_word, bool keep_for_next = false) {
     check_node(sp.expr_root);
     const DT at = arg_type(sp);
     const Kind ak = kind_of_type(at.type);
@@ -1478,11 +1505,15 @@ class Emitter {
           new_fast(FK_SKIP, w.g + 1);
         }
         facts_[sig + "|" + f.name] = w.g;
-        const bool keep = i + 1 < todo.size();
+        const bool keep = i + 1 < todo.size() || keep_for_next;
         emit(f.op, keep ? 1 : 0, (uint8_t)w.f, (uint32_t)w.g);
       }
-      if (todo.empty()) emit(OP_POP, 0, 0, 0);
-      popped();
+      if (keep_for_next && !casted) {
+        kept_on_stack_ = true;  // raw value stays for the next aggregate
+      } else {
+        if (todo.empty() || (keep_for_next && casted)) emit(OP_POP, 0, 0, 0);
+        popped();
+      }
     }
     auto fact = [&](const char* name) -> int {
       auto it = facts_.find(sig + "|" + name);

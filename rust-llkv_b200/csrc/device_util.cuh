@@ -37,6 +37,18 @@ __device__ __forceinline__ bool mbar_try_wait(void* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
+// try_wait with a suspend-time hint: the hardware parks the thread until the phase completes or ~ns elapse
+__device__ __forceinline__ bool mbar_try_wait_hint(void* bar, uint32_t parity, uint32_t ns) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity), "r"(ns)
+      : "memory");
+  return ok != 0;
+}
 __device__ __forceinline__ void mbar_wait(void* bar, uint32_t parity) {
   while (!mbar_try_wait(bar, parity)) {
   }

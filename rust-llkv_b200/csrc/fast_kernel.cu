@@ -49,7 +49,8 @@ static __device__ __noinline__ void slow_accumulate(const Plan& p, uint32_t op, 
 
 __device__ __forceinline__ void mbar_wait_backoff(void* bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;
-  while (!mbar_try_wait(bar, parity)) __nanosleep(40);
+  while (!mbar_try_wait_hint(bar, parity, 20000u)) {
+  }
 }
 
 template <int R>
@@ -327,10 +328,32 @@ __global__ void __launch_bounds__(R >= 8 ? 160 : 288, R >= 8 ? 3 : 2) fast_scan_
             break;
           case FO_GROUP: {
             unsigned mine = 0;
+            u64 keys[R];
+#pragma unroll
+            for (int r = 0; r < R; ++r) keys[r] = 0;
+            {
+              int shift = 0;
+              for (uint32_t k = 0; k < p.n_keys; ++k) {  // key-major: each key column's constants are read once
+                i64 v[R];
+                load_col(p.key_col[k], p.key_load[k], v);
+                const int bits = p.key_bits[k];
+                const u64 kmin = p.key_min[k];
+                const bool is_str = p.key_kind[k] == KK_STR;
+                const int L = p.key_strlen[k];
+                const u64 mask = bits == 64 ? ~0ull : ((1ull << bits) - 1);
+#pragma unroll
+                for (int r = 0; r < R; ++r) {
+                  const u64 f = is_str ? ((L ? (((u64)v[r] >> (64 - 8 * L)) << 3) : 0ull) | ((u64)v[r] & 7ull)) : (u64)v[r] - kmin;
+                  if (p.single_wide_key) keys[r] = (u64)v[r];
+                  else keys[r] |= (f & mask) << shift;
+                }
+                shift += bits;
+              }
+            }
 #pragma unroll
             for (int r = 0; r < R; ++r) {
               const bool a = (actm >> r) & 1u;
-              const u64 K = a ? row_key(r) : kEmptyKey;
+              const u64 K = a ? keys[r] : kEmptyKey;
               const bool usable = a && K != kEmptyKey;
               const unsigned peers = __match_any_sync(FULL, usable ? K : kEmptyKey);
               int sl = -1;

@@ -261,6 +261,13 @@ struct llkv_gpu_column {
   uint64_t row_id_origin = 0;
   int stream_index = 0;
   uint64_t stats_rows = 0;  // rows already covered by the statistics pass (run at seal, not per chunk)
+  // Decimal128 narrowing: `values` is what scans read.  While narrow (LK_D64) the Arrow-layout landing buffer can stay
+  // allocated (`landing`, after a clear(): the caller re-uploads the column every batch) so no allocation happens per batch.
+  void* landing = nullptr;     // parked Arrow-layout buffer (16 B per row), capacity landing_cap rows
+  uint64_t landing_cap = 0;
+  void* narrow = nullptr;      // parked i64 buffer, capacity narrow_cap rows
+  uint64_t narrow_cap = 0;
+  bool reupload_hint = false;  // set by clear(): keep both buffers across batches
   std::vector<void*> deferred_free;  // temp device buffers released at seal
 };
 
@@ -312,6 +319,11 @@ struct llkv_gpu_agg {
   u64* bk_keys = nullptr;
   u64* bk_words = nullptr;
   u64 bk_cap = 0;
+  // gather buffers of the multi-GPU merge, kept across calls
+  u64* mg_keys = nullptr;
+  u64* mg_words = nullptr;
+  size_t mg_key_elems = 0, mg_word_elems = 0;
+  u64* mg_cap = nullptr;
   uint32_t* d_flags = nullptr;
   uint32_t* h_flags = nullptr;  // pinned
   Plan* d_plan = nullptr;
@@ -636,14 +648,24 @@ extern "C" int32_t llkv_gpu_column_append_chunk(llkv_gpu_column* col, uint64_t c
     col->load_kind = LK_U64;
   }
   if (col->load_kind == LK_D64) {  // sealed as i64: back to the Arrow layout before more chunks arrive
-    ulonglong2* wide = nullptr;
     CUDA_TRY(cudaDeviceSynchronize());
-    CUDA_TRY(cudaMalloc((void**)&wide, col->cap_rows * 16));
-    CUDA_TRY(cudaMemset(wide, 0, col->cap_rows * 16));
-    widen_dec_kernel<<<1184, 256>>>((const u64*)col->values, wide, col->n_rows);
-    CUDA_TRY(cudaGetLastError());
-    CUDA_TRY(cudaDeviceSynchronize());
-    CUDA_TRY(cudaFree(col->values));
+    ulonglong2* wide = (ulonglong2*)col->landing;
+    if (!wide || col->landing_cap < col->cap_rows) {
+      if (wide) CUDA_TRY(cudaFree(wide));
+      CUDA_TRY(cudaMalloc((void**)&wide, col->cap_rows * 16));
+      CUDA_TRY(cudaMemset(wide, 0, col->cap_rows * 16));
+      col->landing_cap = col->cap_rows;
+    }
+    if (col->n_rows) {
+      widen_dec_kernel<<<1184, 256>>>((const u64*)col->values, wide, col->n_rows);
+      CUDA_TRY(cudaGetLastError());
+      CUDA_TRY(cudaDeviceSynchronize());
+    }
+    // park the i64 buffer for the next seal
+    col->narrow = col->values;
+    col->narrow_cap = col->cap_rows;
+    col->landing = nullptr;
+    col->landing_cap = 0;
     col->values = wide;
     col->elem_bytes = 16;
     col->load_kind = LK_D128;
@@ -745,13 +767,27 @@ extern "C" int32_t llkv_gpu_column_seal(llkv_gpu_column* col) {
   // Decimal128 whose every value is a sign-extended i64: keep 8 bytes per row resident (half the HBM traffic and half
   // the shared-memory tile of every scan); the Arrow layout is restored if more chunks are appended
   if (col->type == LLKV_PT_DECIMAL128 && col->load_kind == LK_D128 && col->n_rows && col->hstats.not_i64 == 0 && !c->keep_wide_decimals) {
-    u64* nv = nullptr;
-    CUDA_TRY(cudaMalloc((void**)&nv, col->cap_rows * 8));
-    CUDA_TRY(cudaMemset(nv, 0, col->cap_rows * 8));
-    narrow_dec_kernel<<<1184, 256>>>((const ulonglong2*)col->values, nv, col->n_rows);
+    u64* nv = (u64*)col->narrow;
+    if (!nv || col->narrow_cap < col->cap_rows) {
+      if (nv) CUDA_TRY(cudaFree(nv));
+      CUDA_TRY(cudaMalloc((void**)&nv, col->cap_rows * 8));
+      CUDA_TRY(cudaMemset(nv, 0, col->cap_rows * 8));
+      col->narrow_cap = col->cap_rows;
+    }
+    cudaStream_t ns = c->copy_streams[(size_t)col->stream_index];
+    narrow_dec_kernel<<<1184, 256, 0, ns>>>((const ulonglong2*)col->values, nv, col->n_rows);
     CUDA_TRY(cudaGetLastError());
-    CUDA_TRY(cudaDeviceSynchronize());
-    CUDA_TRY(cudaFree(col->values));
+    CUDA_TRY(cudaStreamSynchronize(ns));
+    if (col->reupload_hint) {  // the Arrow-layout buffer stays for the next batch
+      col->landing = col->values;
+      col->landing_cap = col->cap_rows;
+    } else {
+      CUDA_TRY(cudaFree(col->values));
+      col->landing = nullptr;
+      col->landing_cap = 0;
+    }
+    col->narrow = nullptr;
+    col->narrow_cap = 0;
     col->values = nv;
     col->elem_bytes = 8;
     col->load_kind = LK_D64;
@@ -779,10 +815,14 @@ extern "C" int32_t llkv_gpu_column_clear(llkv_gpu_column* col) {
     col->elem_bytes = 8;
     col->load_kind = LK_U64;
   }
-  if (col->load_kind == LK_D64) {  // back to the Arrow layout for new appends
-    if (col->values) CUDA_TRY(cudaFree(col->values));
-    col->values = nullptr;
-    col->cap_rows = 0;
+  col->reupload_hint = true;
+  if (col->load_kind == LK_D64) {  // back to the Arrow layout for new appends; the i64 buffer is parked for the next seal
+    col->narrow = col->values;
+    col->narrow_cap = col->cap_rows;
+    col->values = col->landing;
+    if (!col->landing) col->cap_rows = 0;
+    col->landing = nullptr;
+    col->landing_cap = 0;
     col->elem_bytes = 16;
     col->load_kind = LK_D128;
   }
@@ -810,6 +850,8 @@ extern "C" int32_t llkv_gpu_column_destroy(llkv_gpu_column* col) {
   for (auto& kv : c->mvcc)
     if (kv.second.created_by == col || kv.second.deleted_by == col) kv.second.created_by = kv.second.deleted_by = nullptr;
   for (void* p : col->deferred_free) cudaFree(p);
+  if (col->landing) cudaFree(col->landing);
+  if (col->narrow) cudaFree(col->narrow);
   if (col->values) cudaFree(col->values);
   if (col->validity) cudaFree(col->validity);
   if (col->dstats) cudaFree(col->dstats);
@@ -1169,6 +1211,9 @@ extern "C" void llkv_gpu_agg_destroy(llkv_gpu_agg* a) {
   if (a->gwords) cudaFree(a->gwords);
   if (a->bk_keys) cudaFree(a->bk_keys);
   if (a->bk_words) cudaFree(a->bk_words);
+  if (a->mg_keys) cudaFree(a->mg_keys);
+  if (a->mg_words) cudaFree(a->mg_words);
+  if (a->mg_cap) cudaFree(a->mg_cap);
   if (a->d_flags) cudaFree(a->d_flags);
   if (a->d_plan) cudaFree(a->d_plan);
   if (a->h_plan) cudaFreeHost(a->h_plan);
@@ -1741,23 +1786,33 @@ extern "C" int32_t llkv_gpu_agg_merge(llkv_gpu_agg* a) {
   if (!ctx->nccl_comm || ctx->n_ranks == 1) return LLKV_OK;
   const int N = ctx->n_ranks;
   const int nccl_u64 = 5 /* ncclUint64 */, nccl_max = 2 /* ncclMax */;
-  // all ranks must use one table size: agree on the largest
-  u64* d_cap = nullptr;
-  CUDA_TRY(cudaMalloc((void**)&d_cap, 8));
-  u64 cap = a->gcap;
-  CUDA_TRY(cudaMemcpyAsync(d_cap, &cap, 8, cudaMemcpyHostToDevice, ctx->stream));
-  NCCL_TRY(g_nccl.all_reduce(d_cap, d_cap, 1, nccl_u64, nccl_max, ctx->nccl_comm, ctx->stream));
-  CUDA_TRY(cudaMemcpyAsync(&cap, d_cap, 8, cudaMemcpyDeviceToHost, ctx->stream));
-  CUDA_TRY(cudaStreamSynchronize(ctx->stream));
-  CUDA_TRY(cudaFree(d_cap));
-  while (a->gcap < cap)
-    if ((rc = agg_grow_table(a))) return rc;
+  const bool grouped = a->cr.plan.n_keys != 0;
+  if (grouped) {
+    // all ranks must use one table size: agree on the largest
+    if (!a->mg_cap) CUDA_TRY(cudaMalloc((void**)&a->mg_cap, 8));
+    u64 cap = a->gcap;
+    CUDA_TRY(cudaMemcpyAsync(a->mg_cap, &cap, 8, cudaMemcpyHostToDevice, ctx->stream));
+    NCCL_TRY(g_nccl.all_reduce(a->mg_cap, a->mg_cap, 1, nccl_u64, nccl_max, ctx->nccl_comm, ctx->stream));
+    CUDA_TRY(cudaMemcpyAsync(&cap, a->mg_cap, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    while (a->gcap < cap)
+      if ((rc = agg_grow_table(a))) return rc;
+  }
   const u64 rows = a->gcap + 2;
   const size_t key_elems = (size_t)a->gcap, word_elems = (size_t)(rows * a->n_gwords);
-  u64 *all_keys = nullptr, *all_words = nullptr;
-  CUDA_TRY(cudaMalloc((void**)&all_keys, key_elems * 8 * (size_t)N));
-  CUDA_TRY(cudaMalloc((void**)&all_words, word_elems * 8 * (size_t)N));
-  NCCL_TRY(g_nccl.all_gather(a->gkeys, all_keys, key_elems, nccl_u64, ctx->nccl_comm, ctx->stream));
+  if (a->mg_key_elems < key_elems * (size_t)N) {
+    if (a->mg_keys) CUDA_TRY(cudaFree(a->mg_keys));
+    CUDA_TRY(cudaMalloc((void**)&a->mg_keys, key_elems * 8 * (size_t)N));
+    a->mg_key_elems = key_elems * (size_t)N;
+  }
+  if (a->mg_word_elems < word_elems * (size_t)N) {
+    if (a->mg_words) CUDA_TRY(cudaFree(a->mg_words));
+    CUDA_TRY(cudaMalloc((void**)&a->mg_words, word_elems * 8 * (size_t)N));
+    a->mg_word_elems = word_elems * (size_t)N;
+  }
+  u64* all_keys = a->mg_keys;
+  u64* all_words = a->mg_words;
+  if (grouped) NCCL_TRY(g_nccl.all_gather(a->gkeys, all_keys, key_elems, nccl_u64, ctx->nccl_comm, ctx->stream));
   NCCL_TRY(g_nccl.all_gather(a->gwords, all_words, word_elems, nccl_u64, ctx->nccl_comm, ctx->stream));
   CUDA_TRY(launch_init_table(a->gkeys, a->gwords, rows, a->n_gwords, a->d_gclass, ctx->stream));
   Plan mp = a->cr.plan;
@@ -1765,8 +1820,7 @@ extern "C" int32_t llkv_gpu_agg_merge(llkv_gpu_agg* a) {
   mp.gwords = a->gwords;
   mp.gcap = a->gcap;
   mp.flags = a->d_flags;
-  CUDA_TRY(cudaStreamSynchronize(ctx->stream));
-  memcpy(a->h_plan, &mp, sizeof(Plan));
+  memcpy(a->h_plan, &mp, sizeof(Plan));  // the stream is idle here: agg_resolve synchronised it and nothing reads h_plan since
   CUDA_TRY(cudaMemcpyAsync(a->d_plan, a->h_plan, sizeof(Plan), cudaMemcpyHostToDevice, ctx->stream));
   const u64 src_cap = a->gcap;
   for (int attempt = 0; attempt < 16; ++attempt) {
@@ -1788,7 +1842,5 @@ extern "C" int32_t llkv_gpu_agg_merge(llkv_gpu_agg* a) {
     memcpy(a->h_plan, &mp, sizeof(Plan));
     CUDA_TRY(cudaMemcpyAsync(a->d_plan, a->h_plan, sizeof(Plan), cudaMemcpyHostToDevice, ctx->stream));
   }
-  CUDA_TRY(cudaFree(all_keys));
-  CUDA_TRY(cudaFree(all_words));
   return LLKV_OK;
 }

@@ -18,7 +18,7 @@ def run(filter_expr,specs,keys=(),snapshot=None,hint=0,reps=5):
         if i>=2: ms.append(agg.run_info().last_kernel_ms)
     info=agg.run_info(); agg.destroy(); prog.destroy()
     return min(ms), info
-for nt,r,st,ct in [(256,4,2,2),(256,4,2,3),(256,4,3,2),(128,4,2,4),(128,4,2,6),(128,4,3,4),(256,2,2,3),(128,8,2,3),(128,8,2,2),(128,8,3,2),(64,8,2,6),(256,4,4,2),(128,4,4,4)]:
+for nt,r,st,ct in [(128,4,2,4),(128,4,2,3),(256,4,2,2),(128,8,2,3),(64,4,2,8),(64,8,2,6),(128,2,2,6),(128,4,3,3)]:
     ctx.set_tuning(ctas_per_sm=ct, block_threads=nt, stages=st, rows_per_thread=r)
     try:
         m6,i6=run(tpch.q6_filter(),tpch.q6_aggregates())
