@@ -222,7 +222,8 @@ typedef struct llkv_run_info {
   uint32_t grid, block, rows_per_tile, stages, smem_bytes;
   uint32_t fast_groups;         /* CTA-local group slots with per-thread accumulators */
   float last_kernel_ms;         /* device time of the scan kernel (CUDA events) when timing is enabled, else 0 */
-  uint32_t used_fast_kernel;    /* 1 when the lean kernel (fast_scan_kernel) ran, 0 for the general interpreter */
+  uint32_t used_fast_kernel;    /* 1 when the lean kernel (lean_kernel.cuh) ran, 0 for the general interpreter */
+  uint32_t used_jit_kernel;     /* 1 when the lean kernel ran as a build specialised on this plan shape (jit.cpp) */
 } llkv_run_info;
 
 typedef struct llkv_gpu_ctx llkv_gpu_ctx;
@@ -250,6 +251,12 @@ int32_t llkv_gpu_ctx_set_timing(llkv_gpu_ctx* ctx, int32_t enabled);
  * interpreter, 2 = always the 64-bit general interpreter (never the lean kernel). */
 int32_t llkv_gpu_ctx_set_tuning(llkv_gpu_ctx* ctx, int32_t ctas_per_sm, int32_t block_threads, int32_t stages,
                                 int32_t rows_per_thread, int32_t force_wide);
+
+/* Run-time specialisation of the lean kernel on a plan shape (program + layout), compiled with NVRTC and cached per
+ * device: 0 = never (always interpret the lowered program), 1 = from the second run of a shape on (default), 2 = from
+ * the first run.  Literals, row ranges and snapshots are run-time parameters of the specialised kernel.  Without NVRTC
+ * on the machine the lean kernel keeps interpreting on the GPU. */
+int32_t llkv_gpu_ctx_set_jit(llkv_gpu_ctx* ctx, int32_t mode);
 
 /* Page-locked host memory so chunk uploads DMA straight from the caller's buffer. */
 int32_t llkv_gpu_host_alloc(uint64_t bytes, void** out);
@@ -324,6 +331,30 @@ int32_t llkv_gpu_agg_finalize(llkv_gpu_agg* agg, llkv_agg_value* out_values, llk
                               uint64_t group_capacity, uint64_t* out_groups);
 int32_t llkv_gpu_agg_run_info(const llkv_gpu_agg* agg, llkv_run_info* out);
 void llkv_gpu_agg_destroy(llkv_gpu_agg* agg);
+
+/* ---- diagnostics (no GPU needed) ----
+ * Compiles a plan against column *descriptions* exactly as llkv_gpu_agg_run would against registered columns and writes a
+ * listing (lean program, geometry, accumulator layout) to `out_text`.  With `jit` != 0 the lean kernel is also
+ * specialised on the plan shape with NVRTC (cubin written to `cubin_path` when not NULL).  Used by the CPU test-suite
+ * and for reading SASS / register counts without a GPU.  Decimal128 columns whose values fit i64 are described as
+ * resident i64 (as llkv_gpu_column_seal stores them), one-byte Utf8 columns as one byte per row. */
+typedef struct llkv_debug_column {
+  uint64_t logical_field_id;
+  int32_t prim_type;
+  uint8_t precision;
+  int8_t scale;
+  uint8_t has_minmax;    /* min_value / max_value are valid (integers, dates, decimals that fit i64) */
+  uint8_t dec_fits_i64;  /* Decimal128: every value is a sign-extended i64 */
+  int64_t min_value, max_value;
+  uint64_t n_rows;
+  uint8_t max_strlen;    /* Utf8 */
+  uint8_t _pad[7];
+} llkv_debug_column;
+int32_t llkv_gpu_debug_plan(const llkv_debug_column* cols, int32_t n_cols, const llkv_gpu_program* prog, int32_t created_by_col,
+                            int32_t deleted_by_col, uint64_t txn_id, uint64_t snapshot_id, const llkv_agg_spec* specs, int32_t n_aggs,
+                            const llkv_scalar_node* nodes, int32_t n_nodes, const uint64_t* group_key_fields, int32_t n_keys,
+                            int32_t expr_mode, uint64_t cardinality_hint, int32_t block_threads, int32_t rows_per_thread, int32_t stages,
+                            int32_t ctas_per_sm, int32_t jit, const char* cubin_path, char* out_text, uint64_t out_cap);
 
 /* ---- multi-GPU: one context per rank, NCCL over NVLink ---- */
 #define LLKV_GPU_UNIQUE_ID_BYTES 128

@@ -1770,6 +1770,16 @@ class Emitter {
       x.iv = iv_exact(v);
     };
 
+    // per-thread accumulator width of fast word w in the lean kernel (the widest any of its ops needs)
+    if (p.n_fast_words > (uint32_t)kLeanMaxWords) return false;
+    for (uint32_t w = 0; w < p.n_fast_words; ++w) p.fast[w].lean_width = p.fast[w].lean_rowrel = 0;
+    auto lean_word = [&](uint32_t w, uint8_t width, bool rowrel) {
+      if (w >= p.n_fast_words) { ok = false; return; }
+      if (p.fast[w].lean_width && (p.fast[w].lean_rowrel != 0) != rowrel) width = 8, rowrel = false;
+      if (width > p.fast[w].lean_width) p.fast[w].lean_width = width;
+      p.fast[w].lean_rowrel = rowrel && p.fast[w].lean_width == 4 ? 1 : 0;
+    };
+
     const size_t n = code_.size();
     for (size_t i = 0; i < n && ok; ++i) {
       const Instr& in = code_[i];
@@ -1943,27 +1953,28 @@ class Emitter {
           femit(FO_GROUP, (uint8_t)nk, 0, 0);
           break;
         }
-        case OP_AGG_COUNT_STAR: femit(FO_COUNT_STAR, 0, in.b, in.c); break;
-        case OP_AGG_FIRSTROW: femit(FO_FIRSTROW, 0, in.b, in.c); break;
+        case OP_AGG_COUNT_STAR: femit(FO_COUNT_STAR, 0, in.b, in.c); lean_word(in.b, 4, false); break;
+        case OP_AGG_FIRSTROW: femit(FO_FIRSTROW, 0, in.b, in.c); lean_word(in.b, 4, true); break;
         case OP_AGG_COUNT: case OP_AGG_SUM_I: case OP_AGG_SUM_D: case OP_AGG_FSUM: case OP_AGG_MIN_I: case OP_AGG_MAX_I:
         case OP_AGG_MIN_F: case OP_AGG_MAX_F: case OP_AGG_FIRSTVALID: case OP_AGG_FIRSTNAN: {
           if (st.empty()) return false;
           uint8_t a = 0;
           uint16_t op;
           bool keep = (in.a & 1) != 0;
+          uint8_t width = 8;
+          bool rowrel = false;
           switch (in.op) {
-            case OP_AGG_COUNT: op = FO_COUNT; break;
+            case OP_AGG_COUNT: op = FO_COUNT; width = 4; break;
             case OP_AGG_SUM_I: case OP_AGG_SUM_D: {
               op = FO_SUM;
-              // 24-bit limbs a lane's partial sum (up to 8 rows) needs: redux.sync adds 32 lanes of each limb in 32 bits
+              // value class: every consumer thread keeps a private accumulator and folds at most 2^15 rows per launch
+              // (kLeanRowsPerThreadLog2): values in [0, 2^16) sum exactly in 32 bits, |v| < 2^47 in 64 bits
               const Iv& v = st.back().iv;
               if (v.known) {
                 i128 m = v.hi > -v.lo ? v.hi : -v.lo;
                 if (m < 0) m = 0;
-                m *= 8;
-                if (v.lo >= 0 && m < ((i128)1 << 24)) a = 1;
-                else if (v.lo < 0 && m < ((i128)1 << 23)) a = 1;
-                else if (m < ((i128)1 << 45)) a = 2;  // |v| < 2^42: a warp's i64 partial stays exact over 2^20 rows per launch
+                if (v.lo >= 0 && m < ((i128)1 << 16)) { a = 1; width = 4; }
+                else if (m < ((i128)1 << 47)) a = 2;
               }
               if (in.op == OP_AGG_SUM_D) a |= 0x80;
               break;
@@ -1973,9 +1984,10 @@ class Emitter {
             case OP_AGG_MAX_I: op = FO_MAX_I; break;
             case OP_AGG_MIN_F: op = FO_MIN_F; break;
             case OP_AGG_MAX_F: op = FO_MAX_F; break;
-            case OP_AGG_FIRSTVALID: op = FO_FIRSTVALID; keep = true; break;
-            default: op = FO_FIRSTNAN; keep = true; break;
+            case OP_AGG_FIRSTVALID: op = FO_FIRSTVALID; keep = true; width = 4; rowrel = true; break;
+            default: op = FO_FIRSTNAN; keep = true; width = 4; rowrel = true; break;
           }
+          lean_word(in.b, width, rowrel);
           if (op != FO_COUNT && op != FO_FIRSTVALID) load_acc(st.size() - 1);  // counts do not look at the value
           femit(op, a, in.b, in.c);
           if (!keep) {

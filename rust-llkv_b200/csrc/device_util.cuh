@@ -1,8 +1,10 @@
 // device_util.cuh — sm_100a device helpers: bulk-copy (TMA) + mbarrier PTX, 128-bit integer arithmetic with the
 // overflow rules of the reference's arithmetic, order-preserving encodings, hashing.
 #pragma once
+#ifndef __CUDACC_RTC__
 #include <cuda_runtime.h>
 #include <stdint.h>
+#endif
 
 #include "plan.h"
 

@@ -1,0 +1,788 @@
+// lean_kernel.cuh — body of the lean scan -> filter -> MVCC -> project -> aggregate kernel for sm_100a.
+//
+// Runs the FastOp program the compiler lowers (compiler.cpp: lower_fast) when a plan has no NULLs and range analysis over
+// the columns' min/max statistics proves that every value fits 64 bits.  Everything else runs on the general
+// interpreter (scan_kernel.cu); both produce identical accumulator states.
+//
+// The same source is compiled twice:
+//   * ahead of time (lean_kernel.cu, nvcc): Cfg = LeanDynCfg, the program and layout are read from the __grid_constant__
+//     kernel parameter and interpreted (one dispatch per instruction and tile);
+//   * at run time (jit.cpp, NVRTC) for plans that run repeatedly: Cfg = LeanJitCfg, the program and layout (LeanShape) are
+//     a compile-time constant, `step()` is instantiated once per program position with a constexpr instruction, so the
+//     dispatch, the operand decoding and every layout offset fold away and the compiler sees straight-line code.
+//
+// Shape of one CTA: NC consumer threads + one producer warp.
+//   * The producer's elected lane keeps `stages` row tiles in flight with cp.async.bulk (TMA 1-D bulk copies, one per
+//     column per tile) and full/empty mbarriers per stage; consumers never wait on HBM and there is no __syncthreads
+//     in the tile loop.
+//   * Each consumer thread owns R rows of the tile (row = r * NC + thread, so a warp's shared-memory reads of 4/8 B
+//     elements are conflict free).  Typed predicate leaves compare straight out of the tile into a bit mask; the
+//     projection arithmetic is an accumulator machine: one i64 per row in registers, the other operand read from a
+//     column tile, a literal or a tile-sized temporary in shared memory.
+//   * Aggregates are thread-private: every consumer thread owns one accumulator per (CTA-local group slot, word) in
+//     shared memory, laid out [slot][word][thread] so a warp's read-modify-write is conflict free and needs no atomics
+//     (64-bit shared-memory atomics are CAS loops on this architecture).  Words whose per-thread total provably fits
+//     32 bits (counts, row indices, small sums) are 4 bytes wide.
+//   * At the end the threads' accumulators are reduced per (slot, word) with warp shuffles and folded into the global
+//     group table with one atomic per word.
+#pragma once
+#include "device_util.cuh"
+#include "plan.h"
+
+namespace llkv {
+
+#define LLKV_FULL 0xffffffffu
+
+__device__ __forceinline__ double lean_f64(i64 v) { return __longlong_as_double(v); }
+__device__ __forceinline__ i64 lean_bits(double d) { return __double_as_longlong(d); }
+
+static __device__ __noinline__ u64 lean_global_slot(u64* gkeys, u64 gcap, uint32_t n_keys, u64 K, uint32_t* errbits) {
+  if (n_keys == 0) return 0;
+  if (K == kEmptyKey) return gcap;
+  const u64 mask = gcap - 1;
+  u64 h = mix64(K) & mask;
+  for (u64 i = 0; i <= mask; ++i) {
+    u64 cur = gkeys[h];
+    if (cur == K) return h;
+    if (cur == kEmptyKey) {
+      const u64 old = atomicCAS(&gkeys[h], kEmptyKey, K);
+      if (old == kEmptyKey || old == K) return h;
+    }
+    h = (h + 1) & mask;
+  }
+  *errbits |= FLAG_TABLE_FULL;
+  return gcap;  // parked on the spare row; the flag makes the run fail
+}
+
+// rows without a CTA-local group slot (more groups than slots) and values too large for the per-thread i64 partials go
+// straight to the global table, one atomic per row: rare, kept out of line
+// (returns error flags: no state of the caller has its address taken, so the per-row registers stay registers)
+static __device__ __noinline__ uint32_t lean_slow_accumulate(u64* gkeys, u64* gwords, u64 gcap, uint32_t n_keys, uint32_t n_gwords, uint32_t op,
+                                                             uint32_t flags, u64 K, i64 v, u64 row, uint32_t gword) {
+  uint32_t err = 0;
+  u64* w = &gwords[lean_global_slot(gkeys, gcap, n_keys, K, &err) * n_gwords + gword];
+  switch (op) {
+    case FO_COUNT_STAR: case FO_COUNT: atomicAdd(w, 1ull); break;
+    case FO_FIRSTROW: case FO_FIRSTVALID: case FO_FIRSTNAN: atomicMin(w, row); break;
+    case FO_SUM:
+      if (flags & 0x80) gadd_sum_i128(w, (i128)v);
+      else gadd_sum_i64(w, (i128)v);
+      break;
+    case FO_FSUM: atomicAdd(reinterpret_cast<double*>(w), lean_f64(v)); break;
+    case FO_MIN_I: atomicMin(w, enc_i64(v)); break;
+    case FO_MAX_I: atomicMax(w, enc_i64(v)); break;
+    case FO_MIN_F: atomicMin(w, enc_f64(lean_f64(v))); break;
+    default: atomicMax(w, enc_f64(lean_f64(v))); break;
+  }
+  return err;
+}
+
+// packed GROUP BY key of row `idx` of the staged tile (slow path; the hot path computes keys in LeanTile::row_keys)
+static __device__ __noinline__ u64 lean_row_key(const LeanPlan& p, const LeanShape& S, const unsigned char* sb, uint32_t idx) {
+  u64 K = 0;
+  int shift = 0;
+  for (uint32_t k = 0; k < S.n_keys; ++k) {
+    const unsigned char* base = sb + S.cols[S.key_col[k]].smem_off;
+    const uint32_t kind = S.key_load[k];
+    i64 v;
+    if (kind == LKF_S1) v = (i64)(((u64)base[idx] << 56) | 1ull);
+    else if (kind == LKF_1) v = base[idx];
+    else if (kind == LKF_4) v = reinterpret_cast<const int*>(base)[idx];
+    else if (kind == LKF_16) v = reinterpret_cast<const i64*>(base)[2 * idx];
+    else v = reinterpret_cast<const i64*>(base)[idx];
+    const int bits = (int)S.key_bits[k];
+    u64 f;
+    if (S.key_kind[k] == KK_STR) {
+      const int L = (int)S.key_strlen[k];
+      f = (L ? (((u64)v >> (64 - 8 * L)) << 3) : 0ull) | ((u64)v & 7ull);
+    } else {
+      f = (u64)v - p.key_min[k];
+    }
+    if (S.single_wide_key) K = (u64)v;
+    else K |= (bits == 64 ? f : (f & ((1ull << bits) - 1))) << shift;
+    shift += bits;
+  }
+  return K;
+}
+
+__device__ __forceinline__ void mbar_wait_parked(void* bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  while (!mbar_try_wait_hint(bar, parity, 20000u)) {
+  }
+}
+
+__device__ __forceinline__ uint32_t hash_key32(u64 K) {
+  const uint32_t x = (uint32_t)K ^ (uint32_t)(K >> 32) * 0x9e3779b1u;
+  return (x * 0x85ebca6bu) >> 8;
+}
+
+// interpreted: the shape comes with the kernel parameter
+struct LeanDynCfg {
+  static constexpr bool kStatic = false;
+  static __device__ __forceinline__ const LeanShape& shape(const LeanPlan& p) { return p.s; }
+};
+
+// Per-tile execution state of one consumer thread.  Everything lives in registers: step() is force-inlined into the
+// dispatch loop (interpreted) or into the unrolled program (specialised).
+template <int R, class Cfg>
+struct LeanTile {
+  const LeanPlan& p;
+  const LeanShape& S;
+  const int tid, NC;
+  const uint32_t T;
+  unsigned char* const my4;  // this thread's 4-byte accumulators: my4 + word.off + soff[r]
+  unsigned char* const my8;
+  i64* const tmp_base;
+  u64* const tbl;
+  const bool grouped;
+  // per tile
+  const unsigned char* sb = nullptr;
+  u64 row0 = 0;
+  uint32_t rel0 = 0;
+  i64 acc[R];
+  uint32_t soff[R];  // byte offset of the row's slot inside the accumulator area
+  unsigned actm = 0;  // bit r: row r of this thread is selected
+  unsigned negm = 0;  // bit r: selected row without a CTA-local group slot (goes to the global table directly)
+  bool has_slow = false;  // warp-uniform: some lane has a row in negm
+  uint32_t errbits = 0;
+
+  __device__ __forceinline__ LeanTile(const LeanPlan& plan, const LeanShape& shape, unsigned char* smem, int tid_, int nc)
+      : p(plan), S(shape), tid(tid_), NC(nc), T(shape.tile_rows), my4(smem + shape.smem_acc_off + tid_ * 4),
+        my8(smem + shape.smem_acc_off + tid_ * 8), tmp_base(reinterpret_cast<i64*>(smem + shape.smem_tmp_off)),
+        tbl(reinterpret_cast<u64*>(smem + shape.smem_tbl_off)), grouped(shape.n_keys != 0) {}
+
+  // one column's R values as sign/zero-extended i64.  The lean kernel knows four physical layouts.
+  __device__ __forceinline__ void load_col(uint32_t col, uint32_t kind, i64 (&out)[R]) const {
+    const unsigned char* base = sb + S.cols[col].smem_off;
+    if (kind == LKF_8) {
+#pragma unroll
+      for (int r = 0; r < R; ++r) out[r] = reinterpret_cast<const i64*>(base)[r * NC + tid];
+    } else if (kind == LKF_4) {
+#pragma unroll
+      for (int r = 0; r < R; ++r) out[r] = reinterpret_cast<const int*>(base)[r * NC + tid];
+    } else if (kind == LKF_16) {  // Decimal128 proven to hold sign-extended i64 values: the low half is the value
+#pragma unroll
+      for (int r = 0; r < R; ++r) out[r] = reinterpret_cast<const i64*>(base)[2 * (r * NC + tid)];
+    } else if (kind == LKF_1) {
+#pragma unroll
+      for (int r = 0; r < R; ++r) out[r] = base[r * NC + tid];
+    } else {  // LKF_S1: one-byte strings as packed keys
+#pragma unroll
+      for (int r = 0; r < R; ++r) out[r] = (i64)(((u64)base[r * NC + tid] << 56) | 1ull);
+    }
+  }
+
+  // acc = acc op other  (rev: other op acc)
+  __device__ __forceinline__ void binop(uint32_t opr, const i64 (&o)[R]) {
+    const bool rev = (opr & FB_REV) != 0;
+    switch (opr & 0x7f) {
+      case FB_ADD:
+#pragma unroll
+        for (int r = 0; r < R; ++r) acc[r] += o[r];
+        break;
+      case FB_SUB:
+#pragma unroll
+        for (int r = 0; r < R; ++r) acc[r] = rev ? o[r] - acc[r] : acc[r] - o[r];
+        break;
+      case FB_MUL:
+#pragma unroll
+        for (int r = 0; r < R; ++r) acc[r] *= o[r];
+        break;
+      case FB_MUL32:
+#pragma unroll
+        for (int r = 0; r < R; ++r) acc[r] = (i64)(int)acc[r] * (i64)(int)o[r];
+        break;
+      case FB_ADD_CK: case FB_SUB_CK: case FB_MUL_CK:
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+          const i64 a = rev ? o[r] : acc[r], b = rev ? acc[r] : o[r];
+          i64 c;
+          const uint32_t k = opr & 0x7f;
+          const bool ok = k == FB_ADD_CK ? add_ck(a, b, c) : k == FB_SUB_CK ? sub_ck(a, b, c) : mul_ck(a, b, c);
+          if (!ok && ((actm >> r) & 1u)) errbits |= FLAG_NARROW_FAIL;
+          acc[r] = c;
+        }
+        break;
+      case FB_ADD_F:
+#pragma unroll
+        for (int r = 0; r < R; ++r) acc[r] = lean_bits(lean_f64(acc[r]) + lean_f64(o[r]));
+        break;
+      case FB_SUB_F:
+#pragma unroll
+        for (int r = 0; r < R; ++r) acc[r] = lean_bits(rev ? lean_f64(o[r]) - lean_f64(acc[r]) : lean_f64(acc[r]) - lean_f64(o[r]));
+        break;
+      default:
+#pragma unroll
+        for (int r = 0; r < R; ++r) acc[r] = lean_bits(lean_f64(acc[r]) * lean_f64(o[r]));
+        break;
+    }
+  }
+
+  // packed GROUP BY keys of this thread's R rows (key-major: each key column's constants are read once)
+  __device__ __forceinline__ void row_keys(u64 (&keys)[R]) const {
+#pragma unroll
+    for (int r = 0; r < R; ++r) keys[r] = 0;
+    int shift = 0;
+#pragma unroll
+    for (uint32_t k = 0; k < (uint32_t)kMaxKeys; ++k) {
+      if (k < S.n_keys) {
+        i64 v[R];
+        load_col(S.key_col[k], S.key_load[k], v);
+        const int bits = (int)S.key_bits[k];
+        const u64 kmin = p.key_min[k];
+        const bool is_str = S.key_kind[k] == KK_STR;
+        const int L = (int)S.key_strlen[k];
+        const u64 mask = bits == 64 ? ~0ull : ((1ull << bits) - 1);
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+          const u64 f = is_str ? ((L ? (((u64)v[r] >> (64 - 8 * L)) << 3) : 0ull) | ((u64)v[r] & 7ull)) : (u64)v[r] - kmin;
+          if (S.single_wide_key) keys[r] = (u64)v[r];
+          else keys[r] |= (f & mask) << shift;
+        }
+        shift += bits;
+      }
+    }
+  }
+
+  // rare: rows that go to the global table one atomic at a time.  Kept small (the key is recomputed out of line per
+  // row) because a specialised build carries one copy per aggregate instruction.
+  __device__ __forceinline__ void slow_rows(uint32_t op, uint32_t flags, unsigned rows, uint32_t gword) {
+    if (__any_sync(LLKV_FULL, rows != 0)) {
+#pragma unroll
+      for (int r = 0; r < R; ++r)  // unrolled: acc[] must never be indexed dynamically
+        if ((rows >> r) & 1u) {
+          const u64 K = lean_row_key(p, S, sb, (uint32_t)(r * NC + tid));
+          errbits |= lean_slow_accumulate(p.gkeys, p.gwords, p.gcap, S.n_keys, S.n_gwords, op, flags, K, acc[r], row0 + (u64)r * NC + tid, gword);
+        }
+    }
+  }
+
+  __device__ __forceinline__ void begin_tile(const unsigned char* stage, u64 tile_row0, u64 base_row) {
+    sb = stage;
+    row0 = tile_row0;
+    rel0 = (uint32_t)(row0 - base_row) + (uint32_t)tid;  // launch-relative index of this thread's row r = 0
+    negm = 0;
+    has_slow = false;
+    if (row0 >= p.row_begin && row0 + T <= p.row_end) {
+      actm = (1u << R) - 1u;
+    } else {
+      actm = 0;
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        const u64 row = row0 + (u64)r * NC + tid;
+        if (row >= p.row_begin && row < p.row_end) actm |= 1u << r;
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      acc[r] = 0;
+      soff[r] = 0;
+    }
+  }
+
+  // executes one instruction for this thread's R rows; false = the warp is done with the tile
+  __device__ __forceinline__ bool step(const FInstr& in) {
+    // optional operand pre-load fused into the instruction: acc = literal / column / temporary
+    if (in.d == 2) load_col(in.e, in.f, acc);
+    else if (in.d == 1) {
+      const i64 v = p.lits[in.e];
+#pragma unroll
+      for (int r = 0; r < R; ++r) acc[r] = v;
+    } else if (in.d == 3) {
+      const i64* t = tmp_base + (size_t)in.e * T;
+#pragma unroll
+      for (int r = 0; r < R; ++r) acc[r] = t[r * NC + tid];
+    }
+    switch (in.op) {
+      case FO_LEAF: {
+        const i64 lo = p.lits[in.c], hi = p.lits[in.c + 1];
+        const unsigned char* base = sb + S.cols[in.a].smem_off;
+        unsigned m = 0;
+        if (in.g ? (u64)hi < (u64)lo : hi < lo) {
+          // empty range: nothing matches
+        } else if (in.b == LKF_4) {
+          // lo <= v <= hi as one unsigned compare of (v - lo)
+          const uint32_t l = (uint32_t)(int)lo, span = (uint32_t)(int)hi - l;
+#pragma unroll
+          for (int r = 0; r < R; ++r) {
+            const uint32_t v = reinterpret_cast<const uint32_t*>(base)[r * NC + tid];
+            m |= (unsigned)((v - l) <= span) << r;
+          }
+        } else if ((in.b == LKF_8 || in.b == LKF_16) && !in.g) {
+          const u64 span = (u64)hi - (u64)lo;
+          const int stride = in.b == LKF_16 ? 2 : 1;
+#pragma unroll
+          for (int r = 0; r < R; ++r) {
+            const u64 v = reinterpret_cast<const u64*>(base)[stride * (r * NC + tid)];
+            m |= (unsigned)((v - (u64)lo) <= span) << r;
+          }
+        } else {  // unsigned 8-byte / 1-byte kinds
+          i64 v[R];
+          load_col(in.a, in.b, v);
+          const u64 span = (u64)hi - (u64)lo;
+#pragma unroll
+          for (int r = 0; r < R; ++r) m |= (unsigned)(((u64)v[r] - (u64)lo) <= span) << r;
+        }
+        actm &= m;
+        return true;
+      }
+      case FO_MVCC: {
+        // RowVersion::is_visible_for (llkv-transaction/src/mvcc.rs:282-334), branch free
+        const u64* cbase = reinterpret_cast<const u64*>(sb + S.cols[in.a].smem_off);
+        const u64* dbase = reinterpret_cast<const u64*>(sb + S.cols[in.b].smem_off);
+        const u64 txn = p.txn_id, snap = p.snapshot_id;
+        const bool own_enabled = txn != 1ull;
+        unsigned m = 0;
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+          const u64 cb = cbase[r * NC + tid], db = dbase[r * NC + tid];
+          bool c_comm = cb != ~0ull, d_comm = true;  // TxnIdManager::status: MAX -> None, 1 -> Committed, unknown -> Committed
+          for (uint32_t k = 0; k < p.n_noncommitted; ++k) {
+            const u64 id = p.noncommitted[k];
+            c_comm = c_comm && !(id == cb && cb != 1ull);
+            d_comm = d_comm && !(id == db && db != 1ull);
+          }
+          const bool own_c = own_enabled && cb == txn;
+          const bool own_d = own_enabled && db == txn;
+          const bool others = c_comm && cb <= snap && (db == ~0ull || (!own_d && (!d_comm || db > snap)));
+          const bool vis = own_c ? !own_d : others;
+          m |= (unsigned)vis << r;
+        }
+        actm &= m;
+        return true;
+      }
+      case FO_SELECT_DONE: return __any_sync(LLKV_FULL, actm != 0);
+      case FO_GROUP: {
+        u64 keys[R];
+        row_keys(keys);
+        const uint32_t FG = S.fg;
+        negm = 0;
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+          const bool a = (actm >> r) & 1u;
+          const u64 K = keys[r];
+          int sl = -1;
+          if (a && K != kEmptyKey) {  // every lane probes the CTA's table itself: after the first tiles this is one hit
+            uint32_t h = hash_key32(K) & (FG - 1);
+#pragma unroll 1
+            for (uint32_t i = 0; i < FG; ++i) {
+              const u64 cur = tbl[h];
+              if (cur == K) { sl = (int)h; break; }
+              if (cur == kEmptyKey) {
+                const u64 old = atomicCAS(&tbl[h], kEmptyKey, K);
+                if (old == kEmptyKey || old == K) { sl = (int)h; break; }
+              }
+              h = (h + 1) & (FG - 1);
+            }
+          }
+          soff[r] = sl >= 0 ? (uint32_t)sl * S.slot_stride : 0u;
+          if (a && sl < 0) negm |= 1u << r;
+        }
+        has_slow = __any_sync(LLKV_FULL, negm != 0);
+        return true;
+      }
+
+      case FO_LD_COL: case FO_LD_LIT: case FO_LD_TMP: return true;  // the pre-load above is the whole instruction
+      case FO_ST_TMP: {
+        i64* t = tmp_base + (size_t)in.a * T;
+#pragma unroll
+        for (int r = 0; r < R; ++r) t[r * NC + tid] = acc[r];
+        return true;
+      }
+      case FO_OP_COL: {
+        i64 v[R];
+        load_col(in.c, in.b, v);
+        binop(in.a, v);
+        return true;
+      }
+      case FO_OP_LIT: {
+        i64 v[R];
+        const i64 l = p.lits[in.c];
+#pragma unroll
+        for (int r = 0; r < R; ++r) v[r] = l;
+        binop(in.a, v);
+        return true;
+      }
+      case FO_OP_TMP: {
+        i64 v[R];
+        const i64* t = tmp_base + (size_t)in.b * T;
+#pragma unroll
+        for (int r = 0; r < R; ++r) v[r] = t[r * NC + tid];
+        binop(in.a, v);
+        return true;
+      }
+      case FO_DIVR: {
+        if (in.b == 2) {  // 0 <= x < 2^32
+          const unsigned d = (unsigned)kPow10U64[in.a], half = d / 2;
+#pragma unroll
+          for (int r = 0; r < R; ++r) {
+            const unsigned x = (unsigned)acc[r];
+            const unsigned q = x / d;
+            acc[r] = (i64)(q + ((x - q * d) >= half ? 1u : 0u));
+          }
+        } else if (in.b == 1) {  // x >= 0
+          const u64 d = kPow10U64[in.a], half = d / 2;
+#pragma unroll
+          for (int r = 0; r < R; ++r) {
+            const u64 x = (u64)acc[r];
+            const u64 q = x / d;
+            acc[r] = (i64)(q + ((x - q * d) >= half ? 1ull : 0ull));
+          }
+        } else {
+#pragma unroll
+          for (int r = 0; r < R; ++r) acc[r] = div_pow10_round<i64>(acc[r], (int)in.a);
+        }
+        return true;
+      }
+      case FO_MULP: {
+        const i64 m = pow10_i64((int)in.a);
+#pragma unroll
+        for (int r = 0; r < R; ++r) acc[r] *= m;
+        return true;
+      }
+      case FO_I2F:
+#pragma unroll
+        for (int r = 0; r < R; ++r) acc[r] = lean_bits(__ll2double_rn(acc[r]));
+        return true;
+      case FO_D2F: {
+        const double den = __longlong_as_double(p.lits[in.c]);
+#pragma unroll
+        for (int r = 0; r < R; ++r) acc[r] = lean_bits(__ll2double_rn(acc[r]) / den);
+        return true;
+      }
+
+      // ------------------------------------------------------------ aggregates: one private accumulator per thread,
+      // CTA-local slot and word.  Ungrouped plans fold the thread's R rows in registers first.
+      case FO_COUNT_STAR: case FO_COUNT: {
+        if (has_slow) slow_rows(in.op, in.a, negm, in.c);
+        const unsigned okm = actm & ~negm;
+        const LeanWord lw = S.words[in.b];
+        if (!grouped) {
+          const unsigned c = __popc(okm);
+          if (lw.width == 4) *reinterpret_cast<uint32_t*>(my4 + lw.off) += c;
+          else *reinterpret_cast<u64*>(my8 + lw.off) += c;
+        } else if (lw.width == 4) {
+#pragma unroll
+          for (int r = 0; r < R; ++r)
+            if ((okm >> r) & 1u) *reinterpret_cast<uint32_t*>(my4 + lw.off + soff[r]) += 1u;
+        } else {
+#pragma unroll
+          for (int r = 0; r < R; ++r)
+            if ((okm >> r) & 1u) *reinterpret_cast<u64*>(my8 + lw.off + soff[r]) += 1ull;
+        }
+        return true;
+      }
+      case FO_FIRSTROW: case FO_FIRSTVALID: case FO_FIRSTNAN: {
+        unsigned setm = actm;
+        if (in.op == FO_FIRSTNAN) {
+#pragma unroll
+          for (int r = 0; r < R; ++r) {
+            const double d = lean_f64(acc[r]);
+            if (d == d) setm &= ~(1u << r);
+          }
+        }
+        if (has_slow) slow_rows(in.op, in.a, setm & negm, in.c);
+        setm &= ~negm;
+        const LeanWord lw = S.words[in.b];
+        if (lw.width == 4) {  // launch-relative row index
+#pragma unroll
+          for (int r = 0; r < R; ++r)
+            if ((setm >> r) & 1u) {
+              uint32_t* a = reinterpret_cast<uint32_t*>(my4 + lw.off + soff[r]);
+              const uint32_t cand = rel0 + (uint32_t)(r * NC);
+              if (cand < *a) *a = cand;
+            }
+        } else {
+#pragma unroll
+          for (int r = 0; r < R; ++r)
+            if ((setm >> r) & 1u) {
+              u64* a = reinterpret_cast<u64*>(my8 + lw.off + soff[r]);
+              const u64 cand = row0 + (u64)(r * NC + tid);
+              if (cand < *a) *a = cand;
+            }
+        }
+        return true;
+      }
+      case FO_SUM: {
+        const uint32_t cls = in.a & 3;  // 0: check each value
+        unsigned fastm = actm & ~negm;
+        if (cls == 0) {
+          unsigned bigm = 0;
+#pragma unroll
+          for (int r = 0; r < R; ++r)
+            if (!(acc[r] < ((i64)1 << 47) && acc[r] > -((i64)1 << 47))) bigm |= 1u << r;
+          bigm &= actm;
+          slow_rows(FO_SUM, in.a, bigm | negm, in.c);
+          fastm &= ~bigm;
+        } else if (has_slow) {
+          slow_rows(FO_SUM, in.a, negm, in.c);
+        }
+        const LeanWord lw = S.words[in.b];
+        if (!grouped) {
+          i64 x = 0;
+#pragma unroll
+          for (int r = 0; r < R; ++r)
+            if ((fastm >> r) & 1u) x += acc[r];
+          if (lw.width == 4) *reinterpret_cast<uint32_t*>(my4 + lw.off) += (uint32_t)x;
+          else *reinterpret_cast<u64*>(my8 + lw.off) += (u64)x;
+        } else if (lw.width == 4) {
+#pragma unroll
+          for (int r = 0; r < R; ++r)
+            if ((fastm >> r) & 1u) *reinterpret_cast<uint32_t*>(my4 + lw.off + soff[r]) += (uint32_t)acc[r];
+        } else {
+#pragma unroll
+          for (int r = 0; r < R; ++r)
+            if ((fastm >> r) & 1u) *reinterpret_cast<u64*>(my8 + lw.off + soff[r]) += (u64)acc[r];
+        }
+        return true;
+      }
+      case FO_FSUM: {
+        if (has_slow) slow_rows(FO_FSUM, in.a, negm, in.c);
+        const unsigned okm = actm & ~negm;
+        const LeanWord lw = S.words[in.b];
+        if (!grouped) {
+          double x = 0.0;
+#pragma unroll
+          for (int r = 0; r < R; ++r)
+            if ((okm >> r) & 1u) x += lean_f64(acc[r]);
+          double* a = reinterpret_cast<double*>(my8 + lw.off);
+          *a += x;
+        } else {
+#pragma unroll
+          for (int r = 0; r < R; ++r)
+            if ((okm >> r) & 1u) {
+              double* a = reinterpret_cast<double*>(my8 + lw.off + soff[r]);
+              *a += lean_f64(acc[r]);
+            }
+        }
+        return true;
+      }
+      case FO_MIN_I: case FO_MAX_I: case FO_MIN_F: case FO_MAX_F: {
+        const bool is_min = in.op == FO_MIN_I || in.op == FO_MIN_F;
+        const bool is_f = in.op == FO_MIN_F || in.op == FO_MAX_F;
+        unsigned setm = actm;
+        u64 e[R];
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+          if (is_f) {
+            const double d = lean_f64(acc[r]);
+            if (d != d) setm &= ~(1u << r);  // NaN never replaces a number (llkv-aggregate/src/lib.rs:1309-1331)
+            e[r] = enc_f64(d);
+          } else e[r] = enc_i64(acc[r]);
+        }
+        if (has_slow) slow_rows(in.op, in.a, setm & negm, in.c);
+        setm &= ~negm;
+        const LeanWord lw = S.words[in.b];
+#pragma unroll
+        for (int r = 0; r < R; ++r)
+          if ((setm >> r) & 1u) {
+            u64* a = reinterpret_cast<u64*>(my8 + lw.off + soff[r]);
+            const u64 cur = *a;
+            if (is_min ? e[r] < cur : e[r] > cur) *a = e[r];
+          }
+        return true;
+      }
+      case FO_END: return false;
+      default: errbits |= FLAG_BAD_PLAN; return false;
+    }
+  }
+
+  // specialised: one instantiation of step() per program position, the instruction is a compile-time constant
+  template <int PC>
+  __device__ __forceinline__ void run_static() {
+    if constexpr (Cfg::kStatic) {
+      constexpr FInstr in = Cfg::code(PC);
+      if (!step(in)) return;
+      if constexpr (in.op != FO_END && PC + 1 < kMaxFastInstr) run_static<PC + 1>();
+    }
+  }
+  // interpreted: the next instruction is fetched early so the constant-cache latency overlaps this instruction's work
+  __device__ __forceinline__ void run_dynamic() {
+    uint32_t pc = 0;
+    FInstr in = S.code[0];
+    while (true) {
+      const FInstr nxt = S.code[pc + 1];
+      if (!step(in)) break;
+      in = nxt;
+      ++pc;
+    }
+  }
+};
+
+template <int R, class Cfg>
+__device__ __forceinline__ void lean_body(const LeanPlan& p) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  const LeanShape& S = Cfg::shape(p);
+  const int tid = threadIdx.x;
+  const int NC = (int)S.nc;  // consumer threads (blockDim.x - 32)
+  const int lane = tid & 31;
+  const int warp = tid >> 5;
+  const int n_cwarps = NC >> 5;
+  const bool is_producer = warp == n_cwarps;
+
+  u64* const full_bar = reinterpret_cast<u64*>(smem + S.smem_bar_off);
+  u64* const empty_bar = full_bar + S.stages;
+  unsigned char* const stage0 = smem + S.smem_stage_off;
+  unsigned char* const accb = smem + S.smem_acc_off;               // [slot][word][consumer thread]
+  u64* const tbl = reinterpret_cast<u64*>(smem + S.smem_tbl_off);  // CTA-local group keys, then the slots' global rows
+  u64* const gslot_s = tbl + S.fg;
+
+  const uint32_t FG = S.fg;
+  const uint32_t NW = S.n_words;
+  const uint32_t ST = S.stages;
+  const bool grouped = S.n_keys != 0;
+
+  // accumulator init: MIN-class words start at all ones
+  if (tid < NC) {
+    for (uint32_t g = 0; g < FG; ++g)
+      for (uint32_t w = 0; w < NW; ++w) {
+        const LeanWord lw = S.words[w];
+        unsigned char* blk = accb + g * S.slot_stride + lw.off;
+        if (lw.width == 4) reinterpret_cast<uint32_t*>(blk)[tid] = lw.kind == FK_MIN ? 0xffffffffu : 0u;
+        else reinterpret_cast<u64*>(blk)[tid] = lw.kind == FK_MIN ? ~0ull : 0ull;
+      }
+  }
+  for (uint32_t g = tid; g < FG; g += blockDim.x) tbl[g] = grouped ? kEmptyKey : 0ull;
+  if (tid == 0) {
+    for (uint32_t s = 0; s < ST; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], (uint32_t)n_cwarps);
+    }
+    mbar_fence_init();
+  }
+  __syncthreads();
+
+  const u64 n_tiles = p.n_tiles;
+  const uint32_t T = S.tile_rows;
+  const u64 my_tiles = (n_tiles > blockIdx.x) ? (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+  const u64 base_row = p.first_tile * (u64)T;
+  uint32_t errbits = 0;
+
+  if (is_producer) {
+    // ---------------------------------------------------------------- producer: TMA bulk copies, `stages` tiles in flight
+    if (lane == 0) {
+      uint32_t s = 0, round = 0;
+      for (u64 li = 0; li < my_tiles; ++li) {
+        if (round) mbar_wait_parked(&empty_bar[s], (round - 1) & 1);
+        const u64 tile = p.first_tile + blockIdx.x + li * gridDim.x;
+        unsigned char* sbuf = stage0 + (size_t)s * S.stage_bytes;
+        mbar_arrive_expect_tx(&full_bar[s], S.tx_bytes);
+#pragma unroll
+        for (uint32_t c = 0; c < (uint32_t)kMaxCols; ++c) {
+          if (c < S.n_cols) {
+            const uint32_t bytes = T * S.cols[c].elem_bytes;
+            bulk_g2s(sbuf + S.cols[c].smem_off, reinterpret_cast<const unsigned char*>(p.col_base[c]) + tile * (u64)bytes, bytes, &full_bar[s]);
+          }
+        }
+        if (++s == ST) {
+          s = 0;
+          ++round;
+        }
+      }
+    }
+  } else {
+    // ---------------------------------------------------------------- consumers
+    LeanTile<R, Cfg> t(p, S, smem, tid, NC);
+    uint32_t s = 0, round = 0;
+    for (u64 li = 0; li < my_tiles; ++li) {
+      const u64 tile = p.first_tile + blockIdx.x + li * gridDim.x;
+      mbar_wait_parked(&full_bar[s], round & 1);
+      t.begin_tile(stage0 + (size_t)s * S.stage_bytes, tile * (u64)T, base_row);
+      if constexpr (Cfg::kStatic) t.template run_static<0>();
+      else t.run_dynamic();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&empty_bar[s]);  // this warp is done with the stage
+      if (++s == ST) {
+        s = 0;
+        ++round;
+      }
+    }
+    errbits = t.errbits;
+  }
+
+  // ---------------------------------------------------------------- fold the threads' accumulators into the global group table
+  __syncthreads();
+  const int n_warps = (NC >> 5) + 1;
+  for (uint32_t g = tid; g < FG; g += blockDim.x) {
+    const u64 K = tbl[g];
+    u64 gs = ~0ull;
+    if (!grouped) gs = 0;
+    else if (K != kEmptyKey) gs = lean_global_slot(p.gkeys, p.gcap, S.n_keys, K, &errbits);
+    gslot_s[g] = gs;
+  }
+  __syncthreads();
+  for (uint32_t i = (uint32_t)warp; i < FG * NW; i += (uint32_t)n_warps) {
+    const uint32_t g = i / NW, w = i % NW;
+    const u64 gs = gslot_s[g];
+    if (gs == ~0ull) continue;
+    const LeanWord lw = S.words[w];
+    if (lw.kind == FK_SKIP) continue;
+    const unsigned char* blk = accb + g * S.slot_stride + lw.off;
+    u64* grow = &p.gwords[gs * S.n_gwords];
+    switch (lw.kind) {
+      case FK_COUNT: {
+        u64 s = 0;
+        for (int t = lane; t < NC; t += 32) s += lw.width == 4 ? (u64)reinterpret_cast<const uint32_t*>(blk)[t] : reinterpret_cast<const u64*>(blk)[t];
+        for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(LLKV_FULL, s, o);
+        if (lane == 0 && s) atomicAdd(&grow[lw.gword], s);
+        break;
+      }
+      case FK_SUM_I64: case FK_SUM_I128: {
+        i128 t128 = 0;
+        for (int t = lane; t < NC; t += 32)
+          t128 += lw.width == 4 ? (i128)reinterpret_cast<const uint32_t*>(blk)[t] : (i128)reinterpret_cast<const i64*>(blk)[t];
+        for (int o = 16; o; o >>= 1) {
+          const u64 olo = __shfl_xor_sync(LLKV_FULL, (u64)t128, o);
+          const u64 ohi = __shfl_xor_sync(LLKV_FULL, (u64)((u128)t128 >> 64), o);
+          t128 += (i128)(((u128)ohi << 64) | (u128)olo);
+        }
+        if (lane == 0 && t128 != 0) {
+          if (lw.kind == FK_SUM_I64) gadd_sum_i64(&grow[lw.gword], t128);
+          else gadd_sum_i128(&grow[lw.gword], t128);
+        }
+        break;
+      }
+      case FK_FSUM: {
+        double s = 0.0;
+        for (int t = lane; t < NC; t += 32) s += reinterpret_cast<const double*>(blk)[t];
+        for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(LLKV_FULL, s, o);
+        if (lane == 0) atomicAdd(reinterpret_cast<double*>(&grow[lw.gword]), s);
+        break;
+      }
+      case FK_MIN: {
+        u64 s = ~0ull;
+        for (int t = lane; t < NC; t += 32) {
+          u64 v;
+          if (lw.width == 4) {
+            const uint32_t x = reinterpret_cast<const uint32_t*>(blk)[t];
+            v = x == 0xffffffffu ? ~0ull : (lw.rowrel ? base_row + x : (u64)x);
+          } else v = reinterpret_cast<const u64*>(blk)[t];
+          s = v < s ? v : s;
+        }
+        for (int o = 16; o; o >>= 1) {
+          const u64 y = __shfl_xor_sync(LLKV_FULL, s, o);
+          s = y < s ? y : s;
+        }
+        if (lane == 0 && s != ~0ull) atomicMin(&grow[lw.gword], s);
+        break;
+      }
+      case FK_MAX: {
+        u64 s = 0ull;
+        for (int t = lane; t < NC; t += 32) {
+          const u64 v = reinterpret_cast<const u64*>(blk)[t];
+          s = v > s ? v : s;
+        }
+        for (int o = 16; o; o >>= 1) {
+          const u64 y = __shfl_xor_sync(LLKV_FULL, s, o);
+          s = y > s ? y : s;
+        }
+        if (lane == 0) atomicMax(&grow[lw.gword], s);
+        break;
+      }
+      default: errbits |= FLAG_BAD_PLAN; break;
+    }
+  }
+  if (errbits) atomicOr(p.flags, errbits);
+}
+
+}  // namespace llkv

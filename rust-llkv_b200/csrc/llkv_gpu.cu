@@ -16,6 +16,7 @@
 
 #include "../../include/llkv_gpu.h"
 #include "compiler.h"
+#include "jit.h"
 #include "plan.h"
 
 namespace llkv {
@@ -25,7 +26,7 @@ typedef __int128 i128;
 typedef unsigned __int128 u128;
 cudaError_t launch_scan(const Plan* dplan, bool wide, int rows_per_thread, uint32_t grid, uint32_t block, uint32_t smem,
                         cudaStream_t stream);
-cudaError_t launch_fast(const Plan* dplan, int rows_per_thread, uint32_t grid, uint32_t consumer_threads, uint32_t smem, cudaStream_t stream);
+cudaError_t launch_lean(const LeanPlan& plan, uint32_t grid, cudaStream_t stream);
 cudaError_t launch_init_table(u64* keys, u64* words, u64 rows, uint32_t n_gwords, const uint8_t* word_class_dev, cudaStream_t stream);
 cudaError_t launch_merge_table(const Plan* dplan, const u64* src_keys, const u64* src_words, u64 src_cap, cudaStream_t stream);
 }  // namespace llkv
@@ -236,6 +237,8 @@ struct llkv_gpu_ctx {
   std::map<uint64_t, MvccState> mvcc;            // table id -> snapshot
   bool timing = false;
   int tune_ctas = 0, tune_block = 0, tune_stages = 0, tune_rpt = 0, tune_force_wide = 0;
+  int jit_mode = 1;  // 0 never, 1 specialise a plan shape from its second run on, 2 always
+  std::map<std::string, uint32_t> shape_runs;
   bool keep_wide_decimals = false;  // LLKV_GPU_KEEP_WIDE_DECIMALS=1: never narrow Decimal128 columns at seal
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   void* nccl_comm = nullptr;
@@ -434,11 +437,18 @@ extern "C" int32_t llkv_gpu_ctx_set_timing(llkv_gpu_ctx* c, int32_t enabled) {
   return LLKV_OK;
 }
 
+extern "C" int32_t llkv_gpu_ctx_set_jit(llkv_gpu_ctx* c, int32_t mode) {
+  if (!c) return set_error(LLKV_ERR_INVALID_ARGUMENT, "ctx is NULL");
+  if (mode < 0 || mode > 2) return set_error(LLKV_ERR_INVALID_ARGUMENT, "jit mode must be 0, 1 or 2");
+  c->jit_mode = mode;
+  return LLKV_OK;
+}
+
 extern "C" int32_t llkv_gpu_ctx_set_tuning(llkv_gpu_ctx* c, int32_t ctas_per_sm, int32_t block_threads, int32_t stages,
                                             int32_t rows_per_thread, int32_t force_wide) {
   if (!c) return set_error(LLKV_ERR_INVALID_ARGUMENT, "ctx is NULL");
   if (block_threads && (block_threads < 64 || block_threads > 512 || (block_threads & 63)))
-    return set_error(LLKV_ERR_INVALID_ARGUMENT, "block_threads must be a multiple of 64 in [64, 512]");
+    return set_error(LLKV_ERR_INVALID_ARGUMENT, "block_threads must be a multiple of 32 in [32, 512]");
   if (rows_per_thread && rows_per_thread != 1 && rows_per_thread != 2 && rows_per_thread != 4 && rows_per_thread != 8)
     return set_error(LLKV_ERR_INVALID_ARGUMENT, "rows_per_thread must be 1, 2, 4 or 8");
   if (stages < 0 || stages > 8 || ctas_per_sm < 0 || ctas_per_sm > 8) return set_error(LLKV_ERR_INVALID_ARGUMENT, "tuning value out of range");
@@ -863,7 +873,8 @@ extern "C" int32_t llkv_gpu_column_destroy(llkv_gpu_column* col) {
 extern "C" int32_t llkv_gpu_program_compile(llkv_gpu_ctx* ctx, const llkv_eval_op* ops, int32_t n_ops, const llkv_literal* literals,
                                              int32_t n_literals, const llkv_scalar_node* nodes, int32_t n_nodes,
                                              const int32_t* list_roots, int32_t n_list_roots, llkv_gpu_program** out) {
-  if (!ctx || !out) return set_error(LLKV_ERR_INVALID_ARGUMENT, "NULL argument");
+  (void)ctx;  // programs are host objects: a NULL context is accepted (llkv_gpu_debug_plan)
+  if (!out) return set_error(LLKV_ERR_INVALID_ARGUMENT, "NULL argument");
   *out = nullptr;
   if (n_ops < 0 || n_literals < 0 || n_nodes < 0 || n_list_roots < 0) return set_error(LLKV_ERR_INVALID_ARGUMENT, "negative count");
   if ((n_ops && !ops) || (n_literals && !literals) || (n_nodes && !nodes) || (n_list_roots && !list_roots))
@@ -1071,6 +1082,167 @@ static int32_t plan_geometry(llkv_gpu_ctx* ctx, Plan& p, bool wide, bool fast, u
   return set_error(LLKV_ERR_INVALID_ARGUMENT, "query state does not fit in shared memory on this path");
 }
 
+// Lean kernel (lean_kernel.cuh): picks consumer threads, rows per thread, pipeline depth, CTAs per SM and CTA-local group
+// slots so that stages + thread-private accumulators fit in shared memory, and builds the kernel's by-value plan.
+struct LeanTune {
+  int block = 0, rpt = 0, stages = 0, ctas = 0;
+  int max_smem = 227 * 1024, sm_count = 148;
+};
+static int32_t lean_geometry(const LeanTune& tn, const Plan& p, uint64_t row_begin, uint64_t row_end, uint64_t hint, LeanPlan& lp, Geometry& g,
+                             uint32_t* ctas_out) {
+  memset(&lp, 0, sizeof(lp));
+  LeanShape& s = lp.s;
+  if (p.n_finstr > (uint32_t)kMaxFastInstr || p.n_lits > (uint32_t)kMaxLits || p.n_fast_words > (uint32_t)kLeanMaxWords)
+    return set_error(LLKV_ERR_INTERNAL, "lean plan exceeds its limits");
+  s.n_code = p.n_finstr;
+  for (uint32_t i = 0; i < p.n_finstr; ++i) s.code[i] = p.fcode[i];
+  for (uint32_t i = 0; i < p.n_lits; ++i) lp.lits[i] = (long long)p.lits[i].lo;
+  s.n_cols = p.n_cols;
+  for (uint32_t c = 0; c < p.n_cols; ++c) {
+    lp.col_base[c] = p.cols[c].base;
+    s.cols[c].elem_bytes = p.cols[c].elem_bytes;
+  }
+  lp.txn_id = p.txn_id;
+  lp.snapshot_id = p.snapshot_id;
+  lp.n_noncommitted = p.n_noncommitted;
+  memcpy(lp.noncommitted, p.noncommitted, sizeof(lp.noncommitted));
+  s.n_keys = p.n_keys;
+  s.single_wide_key = p.single_wide_key;
+  for (int k = 0; k < kMaxKeys; ++k) {
+    s.key_bits[k] = p.key_bits[k];
+    s.key_kind[k] = p.key_kind[k];
+    s.key_strlen[k] = p.key_strlen[k];
+    s.key_col[k] = p.key_col[k];
+    s.key_load[k] = p.key_load[k];
+    lp.key_min[k] = p.key_min[k];
+  }
+  s.n_words = p.n_fast_words;
+  s.n_gwords = p.n_gwords;
+  uint32_t thread_bytes = 0;  // accumulator bytes per consumer thread and slot
+  for (uint32_t w = 0; w < p.n_fast_words; ++w) {
+    s.words[w].kind = p.fast[w].kind;
+    s.words[w].width = p.fast[w].lean_width == 4 ? 4 : 8;
+    s.words[w].rowrel = s.words[w].width == 4 ? p.fast[w].lean_rowrel : 0;
+    s.words[w].gword = p.fast[w].gword;
+    thread_bytes += s.words[w].width;
+  }
+  uint32_t NC = tn.block ? (uint32_t)tn.block : 128u;
+  if (NC > 256) NC = 256;
+  if (NC < 32) NC = 32;
+  NC = NC / 32 * 32;
+  // CTA-local group slots: every slot costs thread_bytes per consumer thread
+  uint32_t FG = 1;
+  if (p.n_keys) {
+    if (hint == 0) FG = 8;
+    else if (hint <= 16) FG = (uint32_t)std::max<u64>(4, next_pow2(hint));
+    else if (hint <= 128) FG = 16;
+    else FG = 4;  // high cardinality: nearly every row goes to the global table anyway
+    while (FG > 4 && (u64)FG * thread_bytes * NC > 64u * 1024u) FG /= 2;
+  }
+  const uint32_t budget_total = (uint32_t)tn.max_smem;
+  uint32_t want_stages = tn.stages ? (uint32_t)tn.stages : 0u;
+  if (want_stages == 1) want_stages = 2;
+  const uint32_t want_ctas = tn.ctas ? (uint32_t)tn.ctas : 0u;
+  uint32_t want_R = tn.rpt ? (uint32_t)tn.rpt : 0u;
+  if (want_R == 2) want_R = 1;  // the lean kernel is built for 8, 4 and 1 rows per thread
+
+  // layout for one candidate geometry; returns the stages that fit (0 = does not fit)
+  auto layout = [&](uint32_t R, uint32_t ctas, uint32_t fg, uint32_t nc) -> uint32_t {
+    const uint32_t T = nc * R;
+    uint32_t stage_bytes = 0, tx = 0;
+    for (uint32_t c = 0; c < p.n_cols; ++c) {
+      s.cols[c].smem_off = stage_bytes;
+      stage_bytes += align_up(T * s.cols[c].elem_bytes, 128);
+      tx += T * s.cols[c].elem_bytes;
+    }
+    uint32_t woff = 0;
+    for (uint32_t w = 0; w < s.n_words; ++w) {
+      s.words[w].off = woff;
+      woff += s.words[w].width * nc;
+    }
+    const uint32_t slot_stride = align_up(woff, 128);
+    const uint32_t acc_bytes = align_up(fg * slot_stride, 128), tmp_bytes = align_up(p.fast_tmps * T * 8, 128), tbl_bytes = align_up(fg * 16, 128);
+    const uint32_t fixed = 128 /* barriers */ + acc_bytes + tmp_bytes + tbl_bytes;
+    const uint32_t per_cta = budget_total / ctas - 1024;
+    if (!stage_bytes || per_cta < fixed + 2 * stage_bytes) return 0;
+    uint32_t st = (per_cta - fixed) / stage_bytes;
+    if (want_stages) {
+      if (st < want_stages) return 0;
+      st = want_stages;
+    } else if (st > 4) st = 4;
+    uint32_t off = 0;
+    s.smem_bar_off = off;
+    off += 128;
+    s.smem_stage_off = off;
+    off += stage_bytes * st;
+    s.smem_acc_off = off;
+    off += acc_bytes;
+    s.smem_tmp_off = off;
+    off += tmp_bytes;
+    s.smem_tbl_off = off;
+    off += tbl_bytes;
+    s.smem_total = off;
+    s.nc = nc;
+    s.rows_per_thread = R;
+    s.fg = fg;
+    s.slot_stride = slot_stride;
+    s.tile_rows = T;
+    s.stages = st;
+    s.stage_bytes = stage_bytes;
+    s.tx_bytes = tx;
+    return st;
+  };
+  // candidates in order of preference: several CTAs per SM (the producer of one covers the consumers of another) with
+  // the most rows per thread that leaves a pipeline of >= 3 (else 2) stages; then a single CTA per SM; then fewer
+  // CTA-local groups and consumer threads.  Explicit tuning pins the corresponding dimension.
+  const uint32_t Rs[3] = {8, 4, 1};
+  uint32_t got_ctas = 0;
+  for (uint32_t fg = FG, nc = NC; !got_ctas;) {
+    for (int single = 0; single < 2 && !got_ctas; ++single)
+      for (int ri = 0; ri < 3 && !got_ctas; ++ri) {
+        if (want_R && Rs[ri] != want_R) continue;
+        for (int min_stages = 3; min_stages >= 2 && !got_ctas; --min_stages)
+          for (uint32_t ctas = single ? 1 : 4; ctas >= (single ? 1u : 2u) && !got_ctas; --ctas) {
+            const uint32_t c = want_ctas ? want_ctas : ctas;
+            if (layout(Rs[ri], c, fg, nc) >= (uint32_t)min_stages) got_ctas = c;
+            if (want_ctas) break;
+          }
+      }
+    if (got_ctas) break;
+    if (p.n_keys && fg > 2) fg /= 2;
+    else if (nc > 32) nc /= 2;
+    else break;
+  }
+  if (got_ctas) {
+    const uint32_t T = s.tile_rows;
+    lp.row_begin = row_begin;
+    lp.row_end = row_end;
+    lp.first_tile = row_begin / T;
+    lp.n_tiles = row_end > row_begin ? (row_end + T - 1) / T - lp.first_tile : 0;
+    g.block = s.nc;
+    g.R = s.rows_per_thread;
+    g.smem = s.smem_total;
+    u64 grid = (u64)tn.sm_count * got_ctas;
+    if (grid > lp.n_tiles) grid = lp.n_tiles;
+    if (grid == 0) grid = 1;
+    g.grid = (uint32_t)grid;
+    *ctas_out = got_ctas;
+    return LLKV_OK;
+  }
+  return set_error(LLKV_ERR_INVALID_ARGUMENT, "query state does not fit in shared memory on the lean path");
+}
+
+static LeanTune lean_tune(const llkv_gpu_ctx* ctx) {
+  LeanTune t;
+  t.block = ctx->tune_block;
+  t.rpt = ctx->tune_rpt;
+  t.stages = ctx->tune_stages;
+  t.ctas = ctx->tune_ctas;
+  t.max_smem = ctx->max_smem;
+  t.sm_count = ctx->sm_count;
+  return t;
+}
+
 static int32_t build_request(llkv_gpu_ctx* ctx, uint64_t table_id, const llkv_gpu_program* prog, int apply_mvcc, CompileRequest& req,
                              std::vector<llkv_gpu_column*>& handles, uint64_t* table_rows) {
   int32_t rc = collect_columns(ctx, table_id, req.cols, handles, table_rows);
@@ -1093,6 +1265,147 @@ static int32_t build_request(llkv_gpu_ctx* ctx, uint64_t table_id, const llkv_gp
       req.mvcc.snapshot_id = m.snapshot_id;
       req.mvcc.noncommitted = m.noncommitted;
     }
+  }
+  return LLKV_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ diagnostics
+static const char* fast_op_name(uint32_t op) {
+  static const char* names[] = {"END", "LEAF", "MVCC", "SELECT_DONE", "GROUP", "LD_COL", "LD_LIT", "LD_TMP", "ST_TMP", "OP_COL", "OP_LIT",
+                                "OP_TMP", "DIVR", "MULP", "I2F", "D2F", "COUNT_STAR", "COUNT", "FIRSTROW", "SUM", "FSUM", "MIN_I", "MAX_I",
+                                "MIN_F", "MAX_F", "FIRSTVALID", "FIRSTNAN"};
+  return op < sizeof(names) / sizeof(names[0]) ? names[op] : "?";
+}
+static std::string lean_listing(const LeanPlan& lp, const Geometry& g, uint32_t ctas) {
+  const LeanShape& s = lp.s;
+  char b[256];
+  std::string o;
+  snprintf(b, sizeof(b), "lean plan: %u instr, %u cols, %u words, %u keys | NC=%u R=%u tile=%u stages=%u stage_bytes=%u fg=%u slot_stride=%u smem=%u ctas/SM=%u grid=%u\n",
+           s.n_code, s.n_cols, s.n_words, s.n_keys, s.nc, s.rows_per_thread, s.tile_rows, s.stages, s.stage_bytes, s.fg, s.slot_stride, s.smem_total, ctas, g.grid);
+  o += b;
+  for (uint32_t c = 0; c < s.n_cols; ++c) {
+    snprintf(b, sizeof(b), "  col %u: %u B/row at stage+%u\n", c, s.cols[c].elem_bytes, s.cols[c].smem_off);
+    o += b;
+  }
+  for (uint32_t w = 0; w < s.n_words; ++w) {
+    snprintf(b, sizeof(b), "  word %u: kind %u width %u rowrel %u off %u -> gword %u\n", w, s.words[w].kind, s.words[w].width, s.words[w].rowrel, s.words[w].off,
+             s.words[w].gword);
+    o += b;
+  }
+  for (uint32_t i = 0; i < s.n_code; ++i) {
+    const FInstr& in = s.code[i];
+    snprintf(b, sizeof(b), "  %2u %-11s a=%u b=%u c=%u", i, fast_op_name(in.op), in.a, in.b, in.c);
+    o += b;
+    if (in.d) {
+      snprintf(b, sizeof(b), "  [pre: %s %u kind %u]", in.d == 1 ? "lit" : in.d == 2 ? "col" : "tmp", in.e, in.f);
+      o += b;
+    }
+    if (in.op == FO_LEAF) {
+      snprintf(b, sizeof(b), "  range [%lld, %lld]%s", lp.lits[in.c], lp.lits[in.c + 1], in.g ? " unsigned" : "");
+      o += b;
+    }
+    if (in.op == FO_OP_LIT || in.op == FO_LD_LIT) {
+      snprintf(b, sizeof(b), "  lit %lld", lp.lits[in.op == FO_OP_LIT ? in.c : in.e]);
+      o += b;
+    }
+    o += "\n";
+  }
+  return o;
+}
+
+extern "C" int32_t llkv_gpu_debug_plan(const llkv_debug_column* cols, int32_t n_cols, const llkv_gpu_program* prog, int32_t created_by_col,
+                                        int32_t deleted_by_col, uint64_t txn_id, uint64_t snapshot_id, const llkv_agg_spec* specs,
+                                        int32_t n_aggs, const llkv_scalar_node* nodes, int32_t n_nodes, const uint64_t* group_key_fields,
+                                        int32_t n_keys, int32_t expr_mode, uint64_t cardinality_hint, int32_t block_threads,
+                                        int32_t rows_per_thread, int32_t stages, int32_t ctas_per_sm, int32_t jit, const char* cubin_path,
+                                        char* out_text, uint64_t out_cap) {
+  if (!cols || n_cols <= 0 || n_aggs < 0 || n_keys < 0 || n_keys > kMaxKeys) return set_error(LLKV_ERR_INVALID_ARGUMENT, "bad arguments");
+  CompileRequest req;
+  uint64_t rows = ~0ull;
+  for (int i = 0; i < n_cols; ++i) {
+    const llkv_debug_column& d = cols[i];
+    ColumnMeta m;
+    m.field_id = lfid_field(d.logical_field_id) | ((d.logical_field_id >> 48) << 48);
+    m.type = d.prim_type;
+    m.precision = d.precision;
+    m.scale = d.scale;
+    m.nullable = false;
+    m.load_kind = device_load_kind(d.prim_type);
+    m.elem_bytes = device_elem_bytes(d.prim_type);
+    if (m.elem_bytes == 0) return set_error(LLKV_ERR_INVALID_ARGUMENT, "column type %d does not cross this boundary", d.prim_type);
+    m.arrow_bytes = d.prim_type == LLKV_PT_UTF8 ? 4u + d.max_strlen : (uint32_t)prim_type_width(d.prim_type);
+    if (d.prim_type == LLKV_PT_DECIMAL128 && d.dec_fits_i64) {  // as sealed: resident i64
+      m.load_kind = LK_D64;
+      m.elem_bytes = 8;
+    }
+    if (d.prim_type == LLKV_PT_UTF8 && d.max_strlen == 1) {  // as sealed: one byte per row
+      m.load_kind = LK_STR8;
+      m.elem_bytes = 1;
+    }
+    m.dev_values = reinterpret_cast<const void*>((uintptr_t)0x1000);  // never dereferenced here
+    m.n_rows = d.n_rows;
+    m.dec_fits_i64 = d.dec_fits_i64 != 0;
+    if (d.has_minmax) {
+      m.has_minmax = true;
+      m.min_bits = (uint64_t)d.min_value;
+      m.max_bits = (uint64_t)d.max_value;
+    }
+    m.max_strlen = d.max_strlen;
+    req.cols.push_back(m);
+    rows = std::min<uint64_t>(rows, d.n_rows);
+  }
+  req.prog = prog ? &prog->view : nullptr;
+  if (created_by_col >= 0 && deleted_by_col >= 0) {
+    if (created_by_col >= n_cols || deleted_by_col >= n_cols) return set_error(LLKV_ERR_INVALID_ARGUMENT, "MVCC column index out of range");
+    req.mvcc.enabled = true;
+    req.mvcc.created_by = &req.cols[(size_t)created_by_col];
+    req.mvcc.deleted_by = &req.cols[(size_t)deleted_by_col];
+    req.mvcc.txn_id = txn_id;
+    req.mvcc.snapshot_id = snapshot_id;
+  }
+  req.specs = specs;
+  req.n_aggs = n_aggs;
+  req.agg_nodes = nodes;
+  req.n_agg_nodes = n_nodes;
+  req.key_fields.assign(group_key_fields, group_key_fields + n_keys);
+  req.expr_mode = expr_mode;
+  CompileResult cr;
+  int32_t rc = compile_plan(req, cr);
+  if (rc) return set_error(rc, "%s", cr.error.c_str());
+  std::string text;
+  if (!cr.fast) {
+    text = "general interpreter (no lean program)\n";
+  } else {
+    LeanTune tn;
+    tn.block = block_threads;
+    tn.rpt = rows_per_thread;
+    tn.stages = stages;
+    tn.ctas = ctas_per_sm;
+    LeanPlan lp;
+    Geometry g;
+    uint32_t ctas = 1;
+    if ((rc = lean_geometry(tn, cr.plan, 0, rows, cardinality_hint, lp, g, &ctas))) return rc;
+    text = lean_listing(lp, g, ctas);
+    if (jit) {
+      std::vector<char> cubin;
+      std::string log;
+      if (jit_compile_cubin(lp.s, (int)ctas, cubin, log) != 0) return set_error(LLKV_ERR_INTERNAL, "specialisation failed: %s", log.c_str());
+      char b[128];
+      snprintf(b, sizeof(b), "specialised cubin: %zu bytes\n", cubin.size());
+      text += b;
+      if (!log.empty()) text += "nvrtc log: " + log + "\n";
+      if (cubin_path) {
+        FILE* f = fopen(cubin_path, "wb");
+        if (!f) return set_error(LLKV_ERR_IO, "cannot write %s", cubin_path);
+        fwrite(cubin.data(), 1, cubin.size(), f);
+        fclose(f);
+      }
+    }
+  }
+  if (out_text && out_cap) {
+    const size_t n = std::min<size_t>(text.size(), (size_t)out_cap - 1);
+    memcpy(out_text, text.data(), n);
+    out_text[n] = 0;
   }
   return LLKV_OK;
 }
@@ -1319,35 +1632,67 @@ static int32_t agg_launch(llkv_gpu_agg* a, const llkv_gpu_program* prog, int app
   if ((rc = agg_freeze_layout(a, a->cr))) return rc;
   Plan& p = a->cr.plan;
   Geometry g;
-  if ((rc = plan_geometry(ctx, p, a->cr.wide, a->cr.fast, row_begin, row_end, a->hint, g))) return rc;
+  LeanPlan lean;
+  uint32_t lean_ctas = 1;
+  bool use_jit = false;
+  if (a->cr.fast) {
+    if ((rc = lean_geometry(lean_tune(ctx), p, row_begin, row_end, a->hint, lean, g, &lean_ctas))) return rc;
+    p.tile_rows = lean.s.tile_rows;
+    p.stages = lean.s.stages;
+    p.fast_groups = lean.s.fg;
+    // specialise a plan shape once it repeats (jit_mode 1), always (2) or never (0)
+    if (ctx->jit_mode == 2) use_jit = true;
+    else if (ctx->jit_mode == 1) {
+      const std::string key(reinterpret_cast<const char*>(&lean.s), sizeof(LeanShape));
+      use_jit = ++ctx->shape_runs[key] >= 2;
+    }
+  } else if ((rc = plan_geometry(ctx, p, a->cr.wide, false, row_begin, row_end, a->hint, g))) return rc;
   p.gkeys = a->gkeys;
   p.gwords = a->gwords;
   p.gcap = a->gcap;
   p.flags = a->d_flags;
+  lean.gkeys = a->gkeys;
+  lean.gwords = a->gwords;
+  lean.gcap = a->gcap;
+  lean.flags = a->d_flags;
   const bool need_backup = a->cr.can_narrow_fail || p.n_keys != 0;
   if (need_backup && (rc = agg_backup(a))) return rc;
   a->pending.has_backup = need_backup;
-  // per-thread i64 partial sums stay exact while a thread folds < 2^15 rows per launch: split very long scans
-  // (the lean kernel keeps one i64 partial per warp: < 2^20 rows per warp per launch keeps 2^40-bounded values exact)
+  // thread-private partial sums stay exact while a thread folds a bounded number of rows per launch: split very long scans
+  // (general interpreter: < 2^15 rows per thread; lean kernel: 2^kLeanRowsPerThreadLog2 rows per consumer thread, and
+  // launch-relative row indices must fit 32 bits)
   const u64 threads = (u64)g.grid * g.block;
-  const u64 max_rows_per_launch = threads * 32000ull;
+  u64 max_rows_per_launch = threads * 32000ull;
+  if (a->cr.fast) max_rows_per_launch = std::min<u64>(max_rows_per_launch, 0xf0000000ull) / p.tile_rows * p.tile_rows;
   a->pending.timed = ctx->timing;
   if (ctx->timing) CUDA_TRY(cudaEventRecord(ctx->ev0, ctx->stream));
   uint32_t launches = 0;
   for (u64 rb = row_begin; rb < row_end || (rb == row_begin && launches == 0); rb += max_rows_per_launch) {
     const u64 re = std::min<u64>(row_end, rb + max_rows_per_launch);
-    Plan lp = p;
-    lp.row_begin = rb;
-    lp.row_end = re;
-    lp.first_tile = rb / p.tile_rows;
-    lp.n_tiles = re > rb ? (re + p.tile_rows - 1) / p.tile_rows - lp.first_tile : 0;
-    if (lp.n_tiles == 0) break;
-    if (launches) CUDA_TRY(cudaStreamSynchronize(ctx->stream));  // h_plan is reused
-    memcpy(a->h_plan, &lp, sizeof(Plan));
-    CUDA_TRY(cudaMemcpyAsync(a->d_plan, a->h_plan, sizeof(Plan), cudaMemcpyHostToDevice, ctx->stream));
-    u64 grid = std::min<u64>(g.grid, lp.n_tiles);
-    if (a->cr.fast) CUDA_TRY(launch_fast(a->d_plan, (int)g.R, (uint32_t)grid, g.block, g.smem, ctx->stream));
-    else CUDA_TRY(launch_scan(a->d_plan, a->cr.wide, (int)g.R, (uint32_t)grid, g.block, g.smem, ctx->stream));
+    const u64 first_tile = rb / p.tile_rows;
+    const u64 n_tiles = re > rb ? (re + p.tile_rows - 1) / p.tile_rows - first_tile : 0;
+    if (n_tiles == 0) break;
+    const u64 grid = std::min<u64>(g.grid, n_tiles);
+    if (a->cr.fast) {
+      lean.row_begin = rb;
+      lean.row_end = re;
+      lean.first_tile = first_tile;
+      lean.n_tiles = n_tiles;
+      bool jitted = false;
+      if (use_jit) CUDA_TRY(jit_launch(ctx->device, lean, (int)lean_ctas, (uint32_t)grid, ctx->stream, &jitted, nullptr));
+      if (!jitted) CUDA_TRY(launch_lean(lean, (uint32_t)grid, ctx->stream));
+      a->info.used_jit_kernel = jitted ? 1 : 0;
+    } else {
+      Plan lp = p;
+      lp.row_begin = rb;
+      lp.row_end = re;
+      lp.first_tile = first_tile;
+      lp.n_tiles = n_tiles;
+      if (launches) CUDA_TRY(cudaStreamSynchronize(ctx->stream));  // h_plan is reused
+      memcpy(a->h_plan, &lp, sizeof(Plan));
+      CUDA_TRY(cudaMemcpyAsync(a->d_plan, a->h_plan, sizeof(Plan), cudaMemcpyHostToDevice, ctx->stream));
+      CUDA_TRY(launch_scan(a->d_plan, a->cr.wide, (int)g.R, (uint32_t)grid, g.block, g.smem, ctx->stream));
+    }
     ++launches;
     if (re >= row_end) break;
   }

@@ -2,7 +2,17 @@
 // (scan_kernel.cu).  One Plan = one fused pass: stage column tiles -> predicate program -> MVCC rule ->
 // projection arithmetic -> aggregate update, all in registers/shared memory, every column read once.
 #pragma once
+#ifdef __CUDACC_RTC__  // runtime compilation (jit.cpp): no host headers
+typedef unsigned char uint8_t;
+typedef unsigned short uint16_t;
+typedef unsigned int uint32_t;
+typedef unsigned long long uint64_t;
+typedef int int32_t;
+typedef long long int64_t;
+typedef unsigned long size_t;
+#else
 #include <stdint.h>
+#endif
 
 namespace llkv {
 
@@ -94,7 +104,9 @@ enum FastOp : uint16_t {
   FO_D2F,         // c = literal holding 10^scale as f64: (f64)acc / 10^scale
   // aggregates over acc: b = per-warp word, c = global word
   FO_COUNT_STAR, FO_COUNT, FO_FIRSTROW,
-  FO_SUM,         // a = 24-bit limbs needed for a lane's partial sum (1..3), 0 = not proven small (checked per value); a bit7 = 4-limb global layout
+  FO_SUM,         // a & 3 = value class: 1 -> 0 <= v < 2^16 (u32 per-thread accumulator), 2 -> |v| < 2^47 (i64 per-thread
+                  // accumulator stays exact over 2^15 rows per thread and launch), 0 -> not proven (checked per value);
+                  // a bit7 = 4-limb global layout
   FO_FSUM, FO_MIN_I, FO_MAX_I, FO_MIN_F, FO_MAX_F, FO_FIRSTVALID, FO_FIRSTNAN,
   FO_COUNT_
 };
@@ -158,7 +170,9 @@ struct ColDesc {
 
 struct FastWord {
   uint8_t kind;       // FastKind
-  uint8_t _pad[3];
+  uint8_t lean_width; // lean kernel: bytes of the per-thread accumulator (4 or 8; 0 = 8), set by the lean lowering
+  uint8_t lean_rowrel;// lean kernel: the word holds a row index, kept relative to the launch's first tile
+  uint8_t _pad;
   uint32_t gword;     // first global word it folds into
 };
 
@@ -211,6 +225,51 @@ struct Plan {
   uint32_t* flags;                // device status word (FLAG_*)
   unsigned long long* out_bitmap; // bitmap_mode: bit i = row_begin + i  (32-bit words written)
   unsigned long long* out_count;  // bitmap_mode: number of selected rows
+};
+
+// ---- the lean kernel's view of a plan (lean_kernel.cuh): passed by value as a __grid_constant__ kernel parameter, so the
+// program, literals and layout are read through the constant cache / uniform registers and cost no shared memory.
+// LeanShape is everything structural (program, layout, geometry): the runtime compiler (jit.cpp) specialises the kernel on
+// it, so a specialised kernel reads only the dynamic half (pointers, literals, row range, snapshot) from the parameter.
+constexpr int kLeanMaxWords = 48;
+constexpr uint32_t kLeanRowsPerThreadLog2 = 15;  // a thread folds at most 2^15 rows per launch (keeps narrow accumulators exact)
+struct LeanCol {
+  uint32_t elem_bytes;
+  uint32_t smem_off;  // byte offset of this column's tile inside a stage
+};
+struct LeanWord {
+  uint32_t kind;    // FastKind
+  uint32_t width;   // 4 or 8 bytes per thread
+  uint32_t rowrel;  // row index relative to first_tile * tile_rows
+  uint32_t off;     // byte offset of this word's [consumer thread] block inside a slot
+  uint32_t gword;   // first global word it folds into
+};
+struct LeanShape {
+  FInstr code[kMaxFastInstr];
+  LeanCol cols[kMaxCols];
+  LeanWord words[kLeanMaxWords];
+  uint32_t key_bits[kMaxKeys], key_kind[kMaxKeys], key_strlen[kMaxKeys], key_col[kMaxKeys], key_load[kMaxKeys];
+  uint32_t n_code, n_cols, n_words, n_gwords, n_keys, single_wide_key;
+  uint32_t nc;           // consumer threads per CTA
+  uint32_t rows_per_thread;
+  uint32_t fg;           // CTA-local group slots (power of two; 1 when ungrouped)
+  uint32_t slot_stride;  // bytes of one slot's accumulators (all consumer threads)
+  uint32_t tile_rows, stages, stage_bytes, tx_bytes;
+  uint32_t smem_bar_off, smem_stage_off, smem_acc_off, smem_tmp_off, smem_tbl_off, smem_total;
+};
+struct LeanPlan {
+  LeanShape s;
+  long long lits[kMaxLits];
+  const void* col_base[kMaxCols];
+  unsigned long long noncommitted[kMaxNoncommitted];
+  unsigned long long key_min[kMaxKeys];
+  unsigned long long txn_id, snapshot_id;
+  unsigned long long row_begin, row_end, first_tile, n_tiles;
+  unsigned long long* gkeys;
+  unsigned long long* gwords;
+  unsigned long long gcap;
+  uint32_t* flags;
+  uint32_t n_noncommitted, _pad;
 };
 
 enum : uint32_t {

@@ -75,7 +75,13 @@ class RunInfo(C.Structure):
                 ("algorithmic_bytes_per_row", C.c_uint32), ("physical_bytes_per_row", C.c_uint32),
                 ("grid", C.c_uint32), ("block", C.c_uint32), ("rows_per_tile", C.c_uint32), ("stages", C.c_uint32),
                 ("smem_bytes", C.c_uint32), ("fast_groups", C.c_uint32), ("last_kernel_ms", C.c_float),
-                ("used_fast_kernel", C.c_uint32)]
+                ("used_fast_kernel", C.c_uint32), ("used_jit_kernel", C.c_uint32)]
+
+
+class DebugColumn(C.Structure):
+    _fields_ = [("logical_field_id", C.c_uint64), ("prim_type", C.c_int32), ("precision", C.c_uint8), ("scale", C.c_int8),
+                ("has_minmax", C.c_uint8), ("dec_fits_i64", C.c_uint8), ("min_value", C.c_int64), ("max_value", C.c_int64),
+                ("n_rows", C.c_uint64), ("max_strlen", C.c_uint8), ("_pad", C.c_uint8 * 7)]
 
 
 def i128_to_words(v: int):

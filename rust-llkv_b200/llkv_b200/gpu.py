@@ -51,6 +51,9 @@ def load():
         "llkv_gpu_ctx_stream": (i32, [vp, P(vp)]),
         "llkv_gpu_ctx_set_timing": (i32, [vp, i32]),
         "llkv_gpu_ctx_set_tuning": (i32, [vp, i32, i32, i32, i32, i32]),
+        "llkv_gpu_ctx_set_jit": (i32, [vp, i32]),
+        "llkv_gpu_debug_plan": (i32, [vp, i32, vp, i32, i32, u64, u64, vp, i32, vp, i32, vp, i32, i32, u64, i32, i32, i32, i32, i32,
+                                       C.c_char_p, C.c_char_p, u64]),
         "llkv_gpu_host_alloc": (i32, [u64, P(vp)]),
         "llkv_gpu_host_free": (i32, [vp]),
         "llkv_gpu_column_register": (i32, [vp, u64, i32, u8, i8, P(vp)]),
@@ -142,6 +145,10 @@ class Context:
 
     def set_tuning(self, ctas_per_sm=0, block_threads=0, stages=0, rows_per_thread=0, force_wide=0):
         _check(self.lib.llkv_gpu_ctx_set_tuning(self.handle, ctas_per_sm, block_threads, stages, rows_per_thread, force_wide))
+
+    def set_jit(self, mode: int):
+        """0 = interpret the lean program, 1 = specialise a plan shape from its second run on (default), 2 = always."""
+        _check(self.lib.llkv_gpu_ctx_set_jit(self.handle, mode))
 
     # ---- multi-GPU (NCCL over NVLink): the unique id travels through whatever the host uses for rendezvous
     def comm_unique_id(self) -> bytes:
@@ -318,6 +325,71 @@ class Aggregation:
         if self.handle:
             self.lib.llkv_gpu_agg_destroy(self.handle)
             self.handle = None
+
+
+def debug_plan(table: HostTable, expr: Optional[Expr], specs: Sequence[AggregateSpec], snapshot: Optional[Snapshot] = None,
+               group_by: Sequence[int] = (), expr_mode: Optional[int] = None, cardinality_hint: int = 0, block_threads: int = 0,
+               rows_per_thread: int = 0, stages: int = 0, ctas_per_sm: int = 0, jit: bool = False, cubin_path: Optional[str] = None) -> str:
+    """llkv_gpu_debug_plan: compiles the plan against the host table's column statistics (no GPU needed) and returns the
+    listing of the lean program; with jit=True the lean kernel is also specialised with NVRTC."""
+    lib = load()
+    cols = []
+    host_cols = list(table.columns.values())
+    lfids = [logical_field_id(table.table_id, c.field_id) for c in host_cols]
+    created = deleted = -1
+    if table.created_by is not None and snapshot is not None:
+        created, deleted = len(host_cols), len(host_cols) + 1
+        host_cols += [table.created_by, table.deleted_by]
+        lfids += [logical_field_id(table.table_id, 0xFFFFFFFF, NS_TXN_CREATED_BY), logical_field_id(table.table_id, 0xFFFFFFFE, NS_TXN_DELETED_BY)]
+    arr = (ffi.DebugColumn * len(host_cols))()
+    for i, (c, lfid) in enumerate(zip(host_cols, lfids)):
+        if c.validity is not None:
+            raise ValueError("debug_plan describes non-nullable columns only")
+        d = arr[i]
+        d.logical_field_id = lfid
+        d.prim_type = c.dtype.type
+        d.precision = c.dtype.precision
+        d.scale = c.dtype.scale
+        d.n_rows = c.n_rows
+        t = c.dtype.type
+        if t == ffi.PT_UTF8:
+            lens = np.diff(c.values.astype(np.int64))
+            d.max_strlen = int(lens.max()) if lens.size else 0
+        elif t == ffi.PT_DECIMAL128:
+            v = c.values.reshape(-1, 2) if c.values.ndim == 1 else c.values
+            lo = v[:, 0].view(np.int64)
+            hi = v[:, 1].view(np.int64)
+            fits = bool(np.all(hi == (lo >> 63)))
+            d.dec_fits_i64 = int(fits)
+            if fits and lo.size:
+                d.has_minmax, d.min_value, d.max_value = 1, int(lo.min()), int(lo.max())
+        elif t in (ffi.PT_FLOAT32, ffi.PT_FLOAT64):
+            pass
+        elif c.n_rows:
+            if t == ffi.PT_UINT64:
+                d.has_minmax, d.min_value, d.max_value = 1, int(np.int64(np.uint64(c.values.min()))), int(np.int64(np.uint64(c.values.max())))
+            else:
+                d.has_minmax, d.min_value, d.max_value = 1, int(c.values.min()), int(c.values.max())
+    prog = None
+    if expr is not None:
+        cp = ProgramCompiler(expr).compile()
+        ops, n_ops, lits, n_lits, nodes, n_nodes, roots, n_roots = cp.c_arrays()
+        prog = C.c_void_p()
+        _check(lib.llkv_gpu_program_compile(None, ops, n_ops, lits, n_lits, nodes, n_nodes, roots, n_roots, C.byref(prog)))
+    try:
+        if expr_mode is None:
+            expr_mode = ffi.EXPR_EXACT if group_by else ffi.EXPR_ARROW
+        aggs, n_aggs, anodes, n_anodes = flatten_aggregates(specs)
+        keys = (C.c_uint64 * max(1, len(group_by)))(*group_by)
+        out = C.create_string_buffer(1 << 16)
+        _check(lib.llkv_gpu_debug_plan(arr, len(host_cols), prog, created, deleted, snapshot.txn_id if snapshot else 0,
+                                       snapshot.snapshot_id if snapshot else 0, aggs, n_aggs, anodes, n_anodes, keys, len(group_by), expr_mode,
+                                       cardinality_hint, block_threads, rows_per_thread, stages, ctas_per_sm, int(jit),
+                                       cubin_path.encode() if cubin_path else None, out, len(out)))
+        return out.value.decode()
+    finally:
+        if prog is not None:
+            lib.llkv_gpu_program_destroy(prog)
 
 
 class DeviceTable:
