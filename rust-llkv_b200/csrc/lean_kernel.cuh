@@ -188,9 +188,13 @@ struct LeanTile {
 #pragma unroll
         for (int r = 0; r < R; ++r) acc[r] *= o[r];
         break;
-      case FB_MUL32:
+      case FB_MUL32:  // both operands proven to fit i32: one mul.wide.s32 (the optimiser otherwise widens to a 64 x 64 product)
 #pragma unroll
-        for (int r = 0; r < R; ++r) acc[r] = (i64)(int)acc[r] * (i64)(int)o[r];
+        for (int r = 0; r < R; ++r) {
+          i64 prod;
+          asm("mul.wide.s32 %0, %1, %2;" : "=l"(prod) : "r"((int)acc[r]), "r"((int)o[r]));
+          acc[r] = prod;
+        }
         break;
       case FB_ADD_CK: case FB_SUB_CK: case FB_MUL_CK:
 #pragma unroll
@@ -327,26 +331,57 @@ struct LeanTile {
         return true;
       }
       case FO_MVCC: {
-        // RowVersion::is_visible_for (llkv-transaction/src/mvcc.rs:282-334), branch free
+        // RowVersion::is_visible_for (llkv-transaction/src/mvcc.rs:282-334), branch free.  TxnIdManager::status: MAX -> None
+        // (not committed), 1 -> Committed, listed ids -> Active/Aborted, anything else -> Committed.  The host keeps 1 out
+        // of the non-committed list.
         const u64* cbase = reinterpret_cast<const u64*>(sb + S.cols[in.a].smem_off);
         const u64* dbase = reinterpret_cast<const u64*>(sb + S.cols[in.b].smem_off);
         const u64 txn = p.txn_id, snap = p.snapshot_id;
         const bool own_enabled = txn != 1ull;
-        unsigned m = 0;
+        u64 cb[R], db[R];
 #pragma unroll
         for (int r = 0; r < R; ++r) {
-          const u64 cb = cbase[r * NC + tid], db = dbase[r * NC + tid];
-          bool c_comm = cb != ~0ull, d_comm = true;  // TxnIdManager::status: MAX -> None, 1 -> Committed, unknown -> Committed
+          cb[r] = cbase[r * NC + tid];
+          db[r] = dbase[r * NC + tid];
+        }
+        unsigned m = 0;
+        if (snap != ~0ull && txn != ~0ull) {
+          // creator passes iff cb <= snap (which excludes MAX) and cb is not listed; the deletion does not hide the row
+          // iff db > snap (which includes MAX = never deleted) or db is listed.  Rows this transaction created / deleted
+          // follow rules (1) and (5).
+          unsigned cin = 0, din = 0;  // bit r: created_by / deleted_by is a non-committed transaction
           for (uint32_t k = 0; k < p.n_noncommitted; ++k) {
             const u64 id = p.noncommitted[k];
-            c_comm = c_comm && !(id == cb && cb != 1ull);
-            d_comm = d_comm && !(id == db && db != 1ull);
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+              cin |= (unsigned)(cb[r] == id) << r;
+              din |= (unsigned)(db[r] == id) << r;
+            }
           }
-          const bool own_c = own_enabled && cb == txn;
-          const bool own_d = own_enabled && db == txn;
-          const bool others = c_comm && cb <= snap && (db == ~0ull || (!own_d && (!d_comm || db > snap)));
-          const bool vis = own_c ? !own_d : others;
-          m |= (unsigned)vis << r;
+#pragma unroll
+          for (int r = 0; r < R; ++r) {
+            const bool own_c = own_enabled && cb[r] == txn;
+            const bool own_d = own_enabled && db[r] == txn;
+            const bool c_ok = cb[r] <= snap && !((cin >> r) & 1u);
+            const bool d_ok = db[r] > snap || ((din >> r) & 1u);
+            const bool vis = !own_d && (own_c || (c_ok && d_ok));
+            m |= (unsigned)vis << r;
+          }
+        } else {  // degenerate snapshot ids: the rule as written
+#pragma unroll
+          for (int r = 0; r < R; ++r) {
+            bool c_comm = cb[r] != ~0ull, d_comm = true;
+            for (uint32_t k = 0; k < p.n_noncommitted; ++k) {
+              const u64 id = p.noncommitted[k];
+              c_comm = c_comm && id != cb[r];
+              d_comm = d_comm && id != db[r];
+            }
+            const bool own_c = own_enabled && cb[r] == txn;
+            const bool own_d = own_enabled && db[r] == txn;
+            const bool others = c_comm && cb[r] <= snap && (db[r] == ~0ull || (!own_d && (!d_comm || db[r] > snap)));
+            const bool vis = own_c ? !own_d : others;
+            m |= (unsigned)vis << r;
+          }
         }
         actm &= m;
         return true;
@@ -357,26 +392,38 @@ struct LeanTile {
         row_keys(keys);
         const uint32_t FG = S.fg;
         negm = 0;
+        // first probe without branches: after the first tiles every key of a low-cardinality GROUP BY sits at its home slot
+        unsigned miss = 0;
 #pragma unroll
         for (int r = 0; r < R; ++r) {
-          const bool a = (actm >> r) & 1u;
-          const u64 K = keys[r];
-          int sl = -1;
-          if (a && K != kEmptyKey) {  // every lane probes the CTA's table itself: after the first tiles this is one hit
-            uint32_t h = hash_key32(K) & (FG - 1);
+          const uint32_t h = hash_key32(keys[r]) & (FG - 1);
+          const bool hit = tbl[h] == keys[r] && keys[r] != kEmptyKey;
+          soff[r] = h * S.slot_stride;
+          if (!hit && ((actm >> r) & 1u)) miss |= 1u << r;
+        }
+        if (__any_sync(LLKV_FULL, miss != 0)) {  // new key, collision chain, table full or the reserved key value
+#pragma unroll
+          for (int r = 0; r < R; ++r) {
+            if ((miss >> r) & 1u) {
+              const u64 K = keys[r];
+              int sl = -1;
+              if (K != kEmptyKey) {
+                uint32_t h = hash_key32(K) & (FG - 1);
 #pragma unroll 1
-            for (uint32_t i = 0; i < FG; ++i) {
-              const u64 cur = tbl[h];
-              if (cur == K) { sl = (int)h; break; }
-              if (cur == kEmptyKey) {
-                const u64 old = atomicCAS(&tbl[h], kEmptyKey, K);
-                if (old == kEmptyKey || old == K) { sl = (int)h; break; }
+                for (uint32_t i = 0; i < FG; ++i) {
+                  const u64 cur = tbl[h];
+                  if (cur == K) { sl = (int)h; break; }
+                  if (cur == kEmptyKey) {
+                    const u64 old = atomicCAS(&tbl[h], kEmptyKey, K);
+                    if (old == kEmptyKey || old == K) { sl = (int)h; break; }
+                  }
+                  h = (h + 1) & (FG - 1);
+                }
               }
-              h = (h + 1) & (FG - 1);
+              soff[r] = sl >= 0 ? (uint32_t)sl * S.slot_stride : 0u;
+              if (sl < 0) negm |= 1u << r;
             }
           }
-          soff[r] = sl >= 0 ? (uint32_t)sl * S.slot_stride : 0u;
-          if (a && sl < 0) negm |= 1u << r;
         }
         has_slow = __any_sync(LLKV_FULL, negm != 0);
         return true;
@@ -489,16 +536,16 @@ struct LeanTile {
           for (int r = 0; r < R; ++r)
             if ((setm >> r) & 1u) {
               uint32_t* a = reinterpret_cast<uint32_t*>(my4 + lw.off + soff[r]);
-              const uint32_t cand = rel0 + (uint32_t)(r * NC);
-              if (cand < *a) *a = cand;
+              const uint32_t cand = rel0 + (uint32_t)(r * NC), cur = *a;
+              *a = cand < cur ? cand : cur;
             }
         } else {
 #pragma unroll
           for (int r = 0; r < R; ++r)
             if ((setm >> r) & 1u) {
               u64* a = reinterpret_cast<u64*>(my8 + lw.off + soff[r]);
-              const u64 cand = row0 + (u64)(r * NC + tid);
-              if (cand < *a) *a = cand;
+              const u64 cand = row0 + (u64)(r * NC + tid), cur = *a;
+              *a = cand < cur ? cand : cur;
             }
         }
         return true;
@@ -578,7 +625,7 @@ struct LeanTile {
           if ((setm >> r) & 1u) {
             u64* a = reinterpret_cast<u64*>(my8 + lw.off + soff[r]);
             const u64 cur = *a;
-            if (is_min ? e[r] < cur : e[r] > cur) *a = e[r];
+            *a = (is_min ? e[r] < cur : e[r] > cur) ? e[r] : cur;
           }
         return true;
       }

@@ -447,7 +447,7 @@ extern "C" int32_t llkv_gpu_ctx_set_jit(llkv_gpu_ctx* c, int32_t mode) {
 extern "C" int32_t llkv_gpu_ctx_set_tuning(llkv_gpu_ctx* c, int32_t ctas_per_sm, int32_t block_threads, int32_t stages,
                                             int32_t rows_per_thread, int32_t force_wide) {
   if (!c) return set_error(LLKV_ERR_INVALID_ARGUMENT, "ctx is NULL");
-  if (block_threads && (block_threads < 64 || block_threads > 512 || (block_threads & 63)))
+  if (block_threads && (block_threads < 32 || block_threads > 512 || (block_threads & 31)))
     return set_error(LLKV_ERR_INVALID_ARGUMENT, "block_threads must be a multiple of 32 in [32, 512]");
   if (rows_per_thread && rows_per_thread != 1 && rows_per_thread != 2 && rows_per_thread != 4 && rows_per_thread != 8)
     return set_error(LLKV_ERR_INVALID_ARGUMENT, "rows_per_thread must be 1, 2, 4 or 8");
@@ -1104,8 +1104,10 @@ static int32_t lean_geometry(const LeanTune& tn, const Plan& p, uint64_t row_beg
   }
   lp.txn_id = p.txn_id;
   lp.snapshot_id = p.snapshot_id;
-  lp.n_noncommitted = p.n_noncommitted;
-  memcpy(lp.noncommitted, p.noncommitted, sizeof(lp.noncommitted));
+  // TXN_ID_AUTO_COMMIT (1) is always committed (llkv-transaction/src/mvcc.rs:157-171): never listed for the kernel
+  lp.n_noncommitted = 0;
+  for (uint32_t i = 0; i < p.n_noncommitted; ++i)
+    if (p.noncommitted[i] != 1ull) lp.noncommitted[lp.n_noncommitted++] = p.noncommitted[i];
   s.n_keys = p.n_keys;
   s.single_wide_key = p.single_wide_key;
   for (int k = 0; k < kMaxKeys; ++k) {
