@@ -91,6 +91,14 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
+def kernel_name(info) -> str:
+    if info.used_jit_kernel:
+        return "llkv_lean_jit (lean_kernel.cuh specialised on the plan shape by jit.cpp)"
+    if info.used_fast_kernel:
+        return "llkv::lean_scan_kernel<R> (lean_kernel.cuh, interpreted)"
+    return "llkv::scan_kernel<WIDE,R> (general interpreter)"
+
+
 def pinned_column(gpu, field_id, dtype, values: np.ndarray):
     """Copies `values` into page-locked host memory and returns (HostColumn view, raw ptr, nbytes)."""
     raw = np.ascontiguousarray(values)
@@ -230,7 +238,6 @@ def run_ours(args):
     if rank == 0:
         sampler.start()
     q6 = bench_query(tpch.q6_filter(), tpch.q6_aggregates())
-    clocks = sampler.stop() if rank == 0 else None
     q1 = None
     if with_q1:
         q1 = bench_query(tpch.q1_filter(), tpch.q1_aggregates(), tpch.Q1_GROUP_BY, snap, hint=6)
@@ -266,6 +273,7 @@ def run_ours(args):
     d2h = 4 + 3 * 6 * 8  # status word + the ungrouped state row (6 words) and its two spare rows, read back by finalize
     agg.destroy()
     prog.destroy()
+    clocks = sampler.stop() if rank == 0 else None  # sampled across the three timed regions (Q6, Q1, end to end)
 
     if rank == 0:
         peak, peak_src = measured_peak()
@@ -278,11 +286,12 @@ def run_ours(args):
         alg_bpr = q6["info"].physical_bytes_per_row
         achieved = alg_bpr * n / (kms * 1e-3) / 1e9 if kms == kms and kms > 0 else None
         achieved_arrow = arrow_bpr * n / (kms * 1e-3) / 1e9 if kms == kms and kms > 0 else None
-        traffic = None
+        traffic = None  # dram__bytes_read + dram__bytes_write of the Q6 kernel from the committed ncu capture, scaled per row
         prof = os.path.join(ROOT, "profiles", "r01_q6_traffic.json")
         if os.path.exists(prof):
             try:
-                traffic = json.load(open(prof)).get("dram_bytes_per_launch")
+                t = json.load(open(prof))
+                traffic = (t["dram_bytes_read"] + t["dram_bytes_write"]) / t["rows"] * n
             except Exception:
                 pass
         line = {
@@ -293,9 +302,10 @@ def run_ours(args):
                                    f"{n} rows per GPU, resident in HBM", "rows_per_gpu": n, "sharding": "row-range per rank" if world > 1 else "none",
                        "l2_policy": "inputs larger than L2 (%.2f GB resident per pass vs 126 MB)" % (alg_bpr * n / 1e9), "chunk_bytes": chunk_bytes,
                        "kernel": {"grid": q6["info"].grid, "block": q6["info"].block, "rows_per_tile": q6["info"].rows_per_tile,
-                                  "stages": q6["info"].stages, "smem_bytes": q6["info"].smem_bytes, "wide": q6["info"].used_wide_path}},
+                                  "stages": q6["info"].stages, "smem_bytes": q6["info"].smem_bytes, "wide": q6["info"].used_wide_path,
+                                  "specialised": q6["info"].used_jit_kernel}},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak if achieved else None,
-                         "traffic": traffic, "peak_source": peak_src, "kernel": "llkv::fast_scan_kernel<R>" if q6["info"].used_fast_kernel else "llkv::scan_kernel<WIDE,R>", "kernel_ms": kms,
+                         "traffic": traffic, "peak_source": peak_src, "kernel": kernel_name(q6["info"]), "kernel_ms": kms,
                          "algorithmic_bytes_per_row": alg_bpr, "arrow_layout_bytes_per_row": arrow_bpr,
                          "arrow_layout_equivalent_gbs": achieved_arrow},
             "e2e": {"value": total_rows * e2e_steps / e2e_dt, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
@@ -313,7 +323,7 @@ def run_ours(args):
                           "roofline": {"bound": "hbm", "achieved": a1, "peak": peak, "unit": "GB/s", "frac": a1 / peak, "kernel_ms": k1,
                                        "algorithmic_bytes_per_row": b1, "arrow_layout_bytes_per_row": q1["info"].algorithmic_bytes_per_row,
                                        "arrow_layout_equivalent_gbs": q1["info"].algorithmic_bytes_per_row * n / (k1 * 1e-3) / 1e9},
-                          "groups": len(q1["result"]), "kernel": {"grid": q1["info"].grid, "block": q1["info"].block,
+                          "groups": len(q1["result"]), "kernel_name": kernel_name(q1["info"]), "kernel": {"grid": q1["info"].grid, "block": q1["info"].block,
                                                                   "rows_per_tile": q1["info"].rows_per_tile, "stages": q1["info"].stages,
                                                                   "smem_bytes": q1["info"].smem_bytes, "fast_groups": q1["info"].fast_groups,
                                                                   "wide": q1["info"].used_wide_path}}

@@ -1,0 +1,178 @@
+//! `extern "C"` bindings to `include/llkv_gpu.h`, 1:1.  Authored, not compiled here (no Rust toolchain in the image):
+//! the same symbols are exercised through Python ctypes (`rust-llkv_b200/llkv_b200/gpu.py`) by the test-suite, and
+//! `tests/test_host_logic.py` checks that the shared library exports every symbol declared below.
+//!
+//! Field layouts mirror the C structs exactly (`#[repr(C)]`); enum values are the `LLKV_*` constants of the header.
+#![allow(non_camel_case_types)]
+
+use core::ffi::{c_char, c_void};
+
+#[repr(C)]
+#[derive(Clone, Copy)]
+pub struct llkv_literal {
+    pub kind: i32,
+    pub precision: u8,
+    pub scale: i8,
+    pub _pad: [u8; 2],
+    pub lo: u64,
+    pub hi: u64,
+}
+
+#[repr(C)]
+#[derive(Clone, Copy)]
+pub struct llkv_scalar_node {
+    pub tag: i32,
+    pub op: i32,
+    pub left: i32,
+    pub right: i32,
+    pub field_id: u64,
+    pub literal: llkv_literal,
+    pub cast_type: i32,
+    pub cast_precision: u8,
+    pub cast_scale: i8,
+    pub _pad: [u8; 2],
+}
+
+#[repr(C)]
+#[derive(Clone, Copy)]
+pub struct llkv_eval_op {
+    pub tag: i32,
+    pub operator_tag: i32,
+    pub field_id: u64,
+    pub lower_kind: i32,
+    pub upper_kind: i32,
+    pub lit_begin: i32,
+    pub lit_count: i32,
+    pub expr_left: i32,
+    pub expr_right: i32,
+    pub cmp_op: i32,
+    pub negated: i32,
+    pub child_count: i32,
+    pub literal_bool: i32,
+}
+
+#[repr(C)]
+#[derive(Clone, Copy)]
+pub struct llkv_agg_spec {
+    pub kind: i32,
+    pub expr_root: i32,
+    pub data_type: i32,
+    pub precision: u8,
+    pub scale: i8,
+    pub distinct: u8,
+    pub _pad: u8,
+}
+
+#[repr(C)]
+#[derive(Clone, Copy)]
+pub struct llkv_agg_value {
+    pub lo: u64,
+    pub hi: u64,
+    pub type_: i32,
+    pub precision: u8,
+    pub scale: i8,
+    pub valid: u8,
+    pub _pad: u8,
+}
+
+#[repr(C)]
+#[derive(Clone, Copy)]
+pub struct llkv_group_key {
+    pub bits: u64,
+    pub type_: i32,
+    pub valid: u8,
+    pub _pad: [u8; 3],
+}
+
+#[repr(C)]
+#[derive(Clone, Copy, Default)]
+pub struct llkv_run_info {
+    pub rows: u64,
+    pub kernel_launches: u32,
+    pub used_wide_path: u32,
+    pub algorithmic_bytes_per_row: u32,
+    pub physical_bytes_per_row: u32,
+    pub grid: u32,
+    pub block: u32,
+    pub rows_per_tile: u32,
+    pub stages: u32,
+    pub smem_bytes: u32,
+    pub fast_groups: u32,
+    pub last_kernel_ms: f32,
+    pub used_fast_kernel: u32,
+    pub used_jit_kernel: u32,
+}
+
+#[repr(C)]
+pub struct llkv_gpu_ctx {
+    _private: [u8; 0],
+}
+#[repr(C)]
+pub struct llkv_gpu_column {
+    _private: [u8; 0],
+}
+#[repr(C)]
+pub struct llkv_gpu_program {
+    _private: [u8; 0],
+}
+#[repr(C)]
+pub struct llkv_gpu_agg {
+    _private: [u8; 0],
+}
+
+pub const LLKV_GPU_ABI_VERSION: i32 = 1;
+pub const LLKV_GPU_UNIQUE_ID_BYTES: usize = 128;
+
+extern "C" {
+    pub fn llkv_gpu_abi_version() -> i32;
+    pub fn llkv_gpu_last_error(buf: *mut c_char, cap: usize) -> usize;
+    pub fn llkv_gpu_device_count() -> i32;
+
+    pub fn llkv_gpu_ctx_create(device_ordinal: i32, n_streams: i32, pinned_bytes: u64, out: *mut *mut llkv_gpu_ctx) -> i32;
+    pub fn llkv_gpu_ctx_destroy(ctx: *mut llkv_gpu_ctx);
+    pub fn llkv_gpu_ctx_synchronize(ctx: *mut llkv_gpu_ctx) -> i32;
+    pub fn llkv_gpu_ctx_stream(ctx: *mut llkv_gpu_ctx, out_stream: *mut *mut c_void) -> i32;
+    pub fn llkv_gpu_ctx_set_timing(ctx: *mut llkv_gpu_ctx, enabled: i32) -> i32;
+    pub fn llkv_gpu_ctx_set_tuning(ctx: *mut llkv_gpu_ctx, ctas_per_sm: i32, block_threads: i32, stages: i32, rows_per_thread: i32, force_wide: i32) -> i32;
+    pub fn llkv_gpu_ctx_set_jit(ctx: *mut llkv_gpu_ctx, mode: i32) -> i32;
+    pub fn llkv_gpu_host_alloc(bytes: u64, out: *mut *mut c_void) -> i32;
+    pub fn llkv_gpu_host_free(p: *mut c_void) -> i32;
+
+    pub fn llkv_gpu_column_register(ctx: *mut llkv_gpu_ctx, logical_field_id: u64, prim_type: i32, precision: u8, scale: i8, out: *mut *mut llkv_gpu_column) -> i32;
+    pub fn llkv_gpu_column_reserve(col: *mut llkv_gpu_column, n_rows: u64) -> i32;
+    pub fn llkv_gpu_column_append_chunk(col: *mut llkv_gpu_column, chunk_pk: u64, values: *const c_void, n_rows: u64, validity: *const u8, row_ids: *const u64, row_id_base: u64, aux: *const c_void) -> i32;
+    pub fn llkv_gpu_column_append_blob(col: *mut llkv_gpu_column, chunk_pk: u64, blob: *const c_void, blob_len: u64, row_ids: *const u64, row_id_base: u64) -> i32;
+    pub fn llkv_gpu_column_seal(col: *mut llkv_gpu_column) -> i32;
+    pub fn llkv_gpu_column_rows(col: *const llkv_gpu_column, out_rows: *mut u64) -> i32;
+    pub fn llkv_gpu_column_clear(col: *mut llkv_gpu_column) -> i32;
+    pub fn llkv_gpu_column_destroy(col: *mut llkv_gpu_column) -> i32;
+
+    pub fn llkv_gpu_program_compile(ctx: *mut llkv_gpu_ctx, ops: *const llkv_eval_op, n_ops: i32, literals: *const llkv_literal, n_literals: i32, nodes: *const llkv_scalar_node, n_nodes: i32, list_roots: *const i32, n_list_roots: i32, out: *mut *mut llkv_gpu_program) -> i32;
+    pub fn llkv_gpu_program_destroy(prog: *mut llkv_gpu_program);
+
+    pub fn llkv_gpu_mvcc_set(ctx: *mut llkv_gpu_ctx, table_id: u64, created_by: *mut llkv_gpu_column, deleted_by: *mut llkv_gpu_column, txn_id: u64, snapshot_id: u64, noncommitted: *const u64, n_noncommitted: i32) -> i32;
+    pub fn llkv_gpu_mvcc_clear(ctx: *mut llkv_gpu_ctx, table_id: u64) -> i32;
+
+    pub fn llkv_gpu_filter_bitmap(ctx: *mut llkv_gpu_ctx, table_id: u64, prog: *const llkv_gpu_program, apply_mvcc: i32, row_begin: u64, row_end: u64, out_words: *mut u64, n_words: u64, out_count: *mut u64) -> i32;
+
+    pub fn llkv_gpu_agg_create(ctx: *mut llkv_gpu_ctx, table_id: u64, specs: *const llkv_agg_spec, n_aggs: i32, nodes: *const llkv_scalar_node, n_nodes: i32, group_key_fields: *const u64, n_keys: i32, expr_mode: i32, cardinality_hint: u64, out: *mut *mut llkv_gpu_agg) -> i32;
+    pub fn llkv_gpu_agg_reset(agg: *mut llkv_gpu_agg) -> i32;
+    pub fn llkv_gpu_agg_run(agg: *mut llkv_gpu_agg, prog: *const llkv_gpu_program, apply_mvcc: i32, row_begin: u64, row_end: u64) -> i32;
+    pub fn llkv_gpu_agg_merge(agg: *mut llkv_gpu_agg) -> i32;
+    pub fn llkv_gpu_agg_group_count(agg: *mut llkv_gpu_agg, out_groups: *mut u64) -> i32;
+    pub fn llkv_gpu_agg_finalize(agg: *mut llkv_gpu_agg, out_values: *mut llkv_agg_value, out_keys: *mut llkv_group_key, group_capacity: u64, out_groups: *mut u64) -> i32;
+    pub fn llkv_gpu_agg_run_info(agg: *const llkv_gpu_agg, out: *mut llkv_run_info) -> i32;
+    pub fn llkv_gpu_agg_destroy(agg: *mut llkv_gpu_agg);
+
+    pub fn llkv_gpu_comm_unique_id(out_id: *mut u8) -> i32;
+    pub fn llkv_gpu_comm_init(ctx: *mut llkv_gpu_ctx, id: *const u8, n_ranks: i32, rank: i32) -> i32;
+    pub fn llkv_gpu_comm_destroy(ctx: *mut llkv_gpu_ctx) -> i32;
+}
+
+/// `llkv_result::Error` from a status code + the thread's last message (llkv-result/src/error.rs:31-176).
+pub fn last_error_message() -> String {
+    let mut buf = vec![0u8; 1024];
+    let n = unsafe { llkv_gpu_last_error(buf.as_mut_ptr() as *mut c_char, buf.len()) };
+    buf.truncate(n.min(buf.len().saturating_sub(1)));
+    String::from_utf8_lossy(&buf).into_owned()
+}

@@ -5,8 +5,9 @@
  * `extern "C"`, takes plain pointers and sizes, and replaces one reference
  * interface, cited as `crate/path.rs:line` relative to jzombie/rust-llkv
  * v0.8.5-alpha.  A Rust `-sys` crate binds these 1:1 (see INTEGRATION.md and
- * ffi/llkv-gpu-sys/src/lib.rs); the same symbols are driven from C++
- * (`rust-llkv_b200/host/llkv_gpu.hpp`) and from Python ctypes in the tests.
+ * ffi/llkv-gpu-sys/src/lib.rs; authored, the image has no Rust toolchain); the
+ * same symbols are driven from Python ctypes (`rust-llkv_b200/llkv_b200/gpu.py`),
+ * the host-side mirror of the reference's types that the tests use.
  *
  * Conventions
  *   - Every call returns an `int32_t` status.  0 is success; non-zero values

@@ -327,6 +327,48 @@ class Aggregation:
             self.handle = None
 
 
+def shard_rows(n_rows: int, world: int, rank: int, align: int = 131072) -> Tuple[int, int]:
+    """Row range [begin, end) of `rank` among `world` GPUs: contiguous, aligned to `align` rows (a chunk boundary:
+    131 072 = one 1 MiB Int64 chunk, llkv-column-map/src/store/slicing.rs:33-43) so every column of a shard covers the
+    same chunks; the last rank takes the remainder."""
+    if world <= 0 or not (0 <= rank < world):
+        raise ValueError("bad rank/world")
+    units = (n_rows + align - 1) // align
+    lo = units * rank // world * align
+    hi = units * (rank + 1) // world * align
+    return min(lo, n_rows), (n_rows if rank == world - 1 else min(hi, n_rows))
+
+
+def merge_partial_results(parts, rules):
+    """Host-side statement of what llkv_gpu_agg_merge does on the device for SUM/COUNT/MIN/MAX states: folds per-rank
+    finalized rows [(key, [AggregateValue...])] in rank order; `rules[i]` is "sum", "min" or "max" for aggregate i
+    (COUNT merges as "sum"; AVG is merged as its (sum, count) pair and divided afterwards, as the device keeps it).
+    NULL (no rows seen on that rank) is the identity.  Used by the multi-rank CPU tests."""
+    import dataclasses
+    merged, order = {}, []
+    for rows in parts:
+        for key, vals in rows:
+            if key not in merged:
+                merged[key] = list(vals)
+                order.append(key)
+                continue
+            cur = merged[key]
+            for i, v in enumerate(vals):
+                if v.value is None:
+                    continue
+                if cur[i].value is None:
+                    cur[i] = v
+                elif rules[i] == "sum":
+                    cur[i] = dataclasses.replace(cur[i], value=cur[i].value + v.value)
+                elif rules[i] == "min":
+                    cur[i] = cur[i] if cur[i].value <= v.value else v
+                elif rules[i] == "max":
+                    cur[i] = cur[i] if cur[i].value >= v.value else v
+                else:
+                    raise ValueError("unknown merge rule %r" % (rules[i],))
+    return [(k, merged[k]) for k in order]
+
+
 def debug_plan(table: HostTable, expr: Optional[Expr], specs: Sequence[AggregateSpec], snapshot: Optional[Snapshot] = None,
                group_by: Sequence[int] = (), expr_mode: Optional[int] = None, cardinality_hint: int = 0, block_threads: int = 0,
                rows_per_thread: int = 0, stages: int = 0, ctas_per_sm: int = 0, jit: bool = False, cubin_path: Optional[str] = None) -> str:

@@ -1,0 +1,85 @@
+"""CPU: the plan compiler's lean lowering and the run-time specialisation of the lean kernel, through the diagnostics
+entry of the C ABI (llkv_gpu_debug_plan).  NVRTC compiles for sm_100a without a GPU, so the specialised build of the
+benchmark plans is checked here: it must compile, keep its registers in bounds and contain the Blackwell path
+(cp.async.bulk = UBLKCP, mbarrier = SYNCS) and no shared-memory CAS loop in the ungrouped kernel."""
+import os
+import shutil
+import subprocess
+
+import pytest
+
+from llkv_b200 import gpu, tpch
+from llkv_b200.expr import Expr
+
+
+@pytest.fixture(scope="module")
+def lineitem():
+    return tpch.lineitem_table(20_000, seed=6, with_q1=True, with_mvcc=True)
+
+
+def test_q6_lowers_to_the_lean_program(lineitem):
+    t, _ = lineitem
+    text = gpu.debug_plan(t, tpch.q6_filter(), tpch.q6_aggregates())
+    assert text.startswith("lean plan:")
+    ops = [ln.split()[1] for ln in text.splitlines() if ln.startswith("  ") and ln.split()[0].isdigit()]
+    # three typed range leaves, early exit, revenue = round(price * discount / 100) summed exactly
+    assert ops[:4] == ["LEAF", "LEAF", "LEAF", "SELECT_DONE"] and ops[-1] == "END"
+    assert "OP_COL" in ops and "DIVR" in ops and "SUM" in ops
+    # the date range and the decimal bounds were folded against the columns' own min/max statistics
+    assert "range [8766, 9130]" in text and "range [5, 7]" in text
+
+
+def test_q1_lowers_to_the_lean_program_with_narrow_accumulators(lineitem):
+    t, snap = lineitem
+    text = gpu.debug_plan(t, tpch.q1_filter(), tpch.q1_aggregates(), snap, group_by=tpch.Q1_GROUP_BY, cardinality_hint=6)
+    assert text.startswith("lean plan:")
+    ops = [ln.split()[1] for ln in text.splitlines() if ln.startswith("  ") and ln.split()[0].isdigit()]
+    assert ops[:4] == ["LEAF", "MVCC", "SELECT_DONE", "GROUP"]
+    assert ops.count("SUM") == 5  # qty, price, disc_price, charge, disc: the AVGs share the SUM words, COUNT(*) the count
+    words = [ln for ln in text.splitlines() if ln.startswith("  word")]
+    assert sum("width 4" in w for w in words) == 4 and sum("width 8" in w for w in words) == 3
+    assert "fg=8" in text  # six expected groups -> eight CTA-local slots
+
+
+def test_or_trees_stay_on_the_general_interpreter(lineitem):
+    t, _ = lineitem
+    text = gpu.debug_plan(t, Expr.Or([tpch.q1_filter(), tpch.q6_filter()]), tpch.q6_aggregates())
+    assert text.startswith("general interpreter")
+
+
+def test_geometry_respects_tuning_and_shared_memory(lineitem):
+    t, snap = lineitem
+    text = gpu.debug_plan(t, tpch.q1_filter(), tpch.q1_aggregates(), snap, group_by=tpch.Q1_GROUP_BY, cardinality_hint=6,
+                          block_threads=64, rows_per_thread=4, stages=2, ctas_per_sm=4)
+    head = text.splitlines()[0]
+    assert "NC=64 R=4 tile=256 stages=2" in head and "ctas/SM=4" in head
+    smem = int(head.split("smem=")[1].split()[0])
+    assert 4 * (smem + 1024) <= 227 * 1024
+
+
+def _nvrtc_available():
+    return any(os.path.exists(p) for p in ("/usr/local/cuda/lib64/libnvrtc.so.12", "/usr/local/cuda/lib64/libnvrtc.so"))
+
+
+@pytest.mark.skipif(not _nvrtc_available(), reason="NVRTC is not installed")
+@pytest.mark.parametrize("query", ["q6", "q1"])
+def test_specialised_kernel_compiles_for_sm_100a(lineitem, tmp_path, query):
+    t, snap = lineitem
+    cubin = str(tmp_path / f"{query}.cubin")
+    if query == "q6":
+        text = gpu.debug_plan(t, tpch.q6_filter(), tpch.q6_aggregates(), jit=True, cubin_path=cubin)
+    else:
+        text = gpu.debug_plan(t, tpch.q1_filter(), tpch.q1_aggregates(), snap, group_by=tpch.Q1_GROUP_BY, cardinality_hint=6, jit=True,
+                              cubin_path=cubin)
+    assert "specialised cubin:" in text and os.path.getsize(cubin) > 10_000
+    cuobjdump = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(cuobjdump):
+        return
+    sass = subprocess.run([cuobjdump, "-sass", cubin], capture_output=True, text=True, check=True).stdout
+    assert "sm_100a" in sass and "llkv_lean_jit" in sass
+    assert "UBLKCP" in sass and "SYNCS.ARRIVE" in sass and "SYNCS.PHASECHK" in sass
+    usage = subprocess.run([cuobjdump, "-res-usage", cubin], capture_output=True, text=True, check=True).stdout
+    regs = int(usage.split("REG:")[1].split()[0])
+    assert regs <= (80 if query == "q6" else 128)
+    if query == "q6":
+        assert "ATOMS" not in sass  # ungrouped: thread-private accumulators, no shared-memory atomics at all
