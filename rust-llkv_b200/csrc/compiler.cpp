@@ -1956,7 +1956,7 @@ class Emitter {
         case OP_AGG_COUNT_STAR: femit(FO_COUNT_STAR, 0, in.b, in.c); lean_word(in.b, 4, false); break;
         case OP_AGG_FIRSTROW: femit(FO_FIRSTROW, 0, in.b, in.c); lean_word(in.b, 4, true); break;
         case OP_AGG_COUNT: case OP_AGG_SUM_I: case OP_AGG_SUM_D: case OP_AGG_FSUM: case OP_AGG_MIN_I: case OP_AGG_MAX_I:
-        case OP_AGG_MIN_F: case OP_AGG_MAX_F: case OP_AGG_FIRSTVALID: case OP_AGG_FIRSTNAN: {
+        case OP_AGG_MIN_F: case OP_AGG_MAX_F: case OP_AGG_FIRSTVALID: case OP_AGG_FIRSTNAN: case OP_AGG_MIN_D: case OP_AGG_MAX_D: {
           if (st.empty()) return false;
           uint8_t a = 0;
           uint16_t op;
@@ -1964,6 +1964,15 @@ class Emitter {
           uint8_t width = 8;
           bool rowrel = false;
           switch (in.op) {
+            case OP_AGG_MIN_D: case OP_AGG_MAX_D: {
+              // Decimal128 MIN/MAX over values proven to sit strictly inside i64: the thread-private state is one
+              // order-preserving u64 (its identity is then never a real value); the global state stays the 128-bit pair
+              const Iv& v = st.back().iv;
+              if (!v.known || !(v.lo > (i128)INT64_MIN && v.hi < (i128)INT64_MAX)) return false;
+              op = in.op == OP_AGG_MIN_D ? FO_MIN_I : FO_MAX_I;
+              a = 0x80;
+              break;
+            }
             case OP_AGG_COUNT: op = FO_COUNT; width = 4; break;
             case OP_AGG_SUM_I: case OP_AGG_SUM_D: {
               op = FO_SUM;

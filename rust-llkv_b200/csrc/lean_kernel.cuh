@@ -69,8 +69,14 @@ static __device__ __noinline__ uint32_t lean_slow_accumulate(u64* gkeys, u64* gw
       else gadd_sum_i64(w, (i128)v);
       break;
     case FO_FSUM: atomicAdd(reinterpret_cast<double*>(w), lean_f64(v)); break;
-    case FO_MIN_I: atomicMin(w, enc_i64(v)); break;
-    case FO_MAX_I: atomicMax(w, enc_i64(v)); break;
+    case FO_MIN_I:
+      if (flags & 0x80) gmin128(w, enc_i64(v >> 63), (u64)v, false);  // Decimal128 state: (hi encoded, lo) pair
+      else atomicMin(w, enc_i64(v));
+      break;
+    case FO_MAX_I:
+      if (flags & 0x80) gmin128(w, enc_i64(v >> 63), (u64)v, true);
+      else atomicMax(w, enc_i64(v));
+      break;
     case FO_MIN_F: atomicMin(w, enc_f64(lean_f64(v))); break;
     default: atomicMax(w, enc_f64(lean_f64(v))); break;
   }
@@ -685,8 +691,9 @@ __device__ __forceinline__ void lean_body(const LeanPlan& p) {
       for (uint32_t w = 0; w < NW; ++w) {
         const LeanWord lw = S.words[w];
         unsigned char* blk = accb + g * S.slot_stride + lw.off;
-        if (lw.width == 4) reinterpret_cast<uint32_t*>(blk)[tid] = lw.kind == FK_MIN ? 0xffffffffu : 0u;
-        else reinterpret_cast<u64*>(blk)[tid] = lw.kind == FK_MIN ? ~0ull : 0ull;
+        const bool min_class = lw.kind == FK_MIN || lw.kind == FK_MIN128_HI;
+        if (lw.width == 4) reinterpret_cast<uint32_t*>(blk)[tid] = min_class ? 0xffffffffu : 0u;
+        else if (lw.width == 8) reinterpret_cast<u64*>(blk)[tid] = min_class ? ~0ull : 0ull;
       }
   }
   for (uint32_t g = tid; g < FG; g += blockDim.x) tbl[g] = grouped ? kEmptyKey : 0ull;
@@ -824,6 +831,23 @@ __device__ __forceinline__ void lean_body(const LeanPlan& p) {
           s = y > s ? y : s;
         }
         if (lane == 0) atomicMax(&grow[lw.gword], s);
+        break;
+      }
+      case FK_MIN128_HI: case FK_MAX128_HI: {  // thread state: one order-preserving u64 of an i64-ranged Decimal128
+        const bool is_max = lw.kind == FK_MAX128_HI;
+        u64 s = is_max ? 0ull : ~0ull;
+        for (int t = lane; t < NC; t += 32) {
+          const u64 v = reinterpret_cast<const u64*>(blk)[t];
+          s = is_max ? (v > s ? v : s) : (v < s ? v : s);
+        }
+        for (int o = 16; o; o >>= 1) {
+          const u64 y = __shfl_xor_sync(LLKV_FULL, s, o);
+          s = is_max ? (y > s ? y : s) : (y < s ? y : s);
+        }
+        if (lane == 0 && s != (is_max ? 0ull : ~0ull)) {
+          const i64 v = (i64)(s ^ 0x8000000000000000ull);
+          gmin128(&grow[lw.gword], enc_i64(v >> 63), (u64)v, is_max);
+        }
         break;
       }
       default: errbits |= FLAG_BAD_PLAN; break;

@@ -1123,7 +1123,7 @@ static int32_t lean_geometry(const LeanTune& tn, const Plan& p, uint64_t row_beg
   uint32_t thread_bytes = 0;  // accumulator bytes per consumer thread and slot
   for (uint32_t w = 0; w < p.n_fast_words; ++w) {
     s.words[w].kind = p.fast[w].kind;
-    s.words[w].width = p.fast[w].lean_width == 4 ? 4 : 8;
+    s.words[w].width = p.fast[w].kind == FK_SKIP ? 0 : (p.fast[w].lean_width == 4 ? 4 : 8);  // the low half of a 128-bit pair has no thread state
     s.words[w].rowrel = s.words[w].width == 4 ? p.fast[w].lean_rowrel : 0;
     s.words[w].gword = p.fast[w].gword;
     thread_bytes += s.words[w].width;
@@ -1669,6 +1669,7 @@ static int32_t agg_launch(llkv_gpu_agg* a, const llkv_gpu_program* prog, int app
   a->pending.timed = ctx->timing;
   if (ctx->timing) CUDA_TRY(cudaEventRecord(ctx->ev0, ctx->stream));
   uint32_t launches = 0;
+  a->info.used_jit_kernel = 0;
   for (u64 rb = row_begin; rb < row_end || (rb == row_begin && launches == 0); rb += max_rows_per_launch) {
     const u64 re = std::min<u64>(row_end, rb + max_rows_per_launch);
     const u64 first_tile = rb / p.tile_rows;

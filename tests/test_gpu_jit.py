@@ -1,0 +1,160 @@
+"""GPU: the lean kernel as a build specialised on the plan shape (jit.cpp) against the oracle and against its own
+interpreted build.  Same bar as test_gpu_parity: bit-exact for integer / decimal / count / min / max, 1e-12 for f64."""
+import numpy as np
+import pytest
+
+import util
+from llkv_b200 import tpch
+from llkv_b200.expr import AggregateKind, AggregateSpec, DataType, Expr, ScalarExpr
+from llkv_b200.table import HostColumn, HostTable, Snapshot
+from oracle import oracle
+from test_gpu_parity import PREDICATES, REL, all_aggs, device_table, mixed_table
+
+pytestmark = pytest.mark.gpu
+G = util.golden()
+
+
+@pytest.fixture()
+def jit_always(gpu_ctx):
+    gpu_ctx.set_jit(2)
+    yield gpu_ctx
+    gpu_ctx.set_jit(1)
+    gpu_ctx.set_tuning()
+
+
+def run(ctx, dt, expr, specs, snapshot=None, group_by=(), hint=0, row_begin=0, row_end=None, cap=None):
+    from llkv_b200 import gpu
+    prog = gpu.Program(ctx, expr) if expr is not None else None
+    dt.set_snapshot(snapshot)
+    agg = gpu.Aggregation(dt, specs, group_by, cardinality_hint=hint)
+    try:
+        agg.run(prog, snapshot is not None, row_begin, row_end)
+        got = agg.finalize(cap)
+        return got, agg.run_info()
+    finally:
+        agg.destroy()
+        if prog:
+            prog.destroy()
+
+
+def test_specialised_kernel_runs_q6_and_q1(jit_always):
+    ctx = jit_always
+    t, snap = tpch.lineitem_table(150_000, seed=6, with_q1=True, with_mvcc=True)
+    dt = device_table(ctx, t)
+    try:
+        got, info = run(ctx, dt, tpch.q6_filter(), tpch.q6_aggregates())
+        assert info.used_fast_kernel == 1 and info.used_jit_kernel == 1
+        util.assert_same_result(got, oracle.aggregate(t, tpch.q6_filter(), tpch.q6_aggregates()), REL)
+        got, info = run(ctx, dt, tpch.q1_filter(), tpch.q1_aggregates(), snap, tpch.Q1_GROUP_BY, hint=6, cap=16)
+        assert info.used_jit_kernel == 1
+        util.assert_same_result(got, oracle.aggregate(t, tpch.q1_filter(), tpch.q1_aggregates(), snap, group_by=tpch.Q1_GROUP_BY, group_capacity=16), REL)
+        # ragged row ranges reuse the same specialised kernel: row range, literals and snapshot are run-time parameters
+        for lo, hi in [(0, 1), (1, 1), (1023, 1025), (77_777, 150_000), (149_999, 150_000)]:
+            got, info = run(ctx, dt, tpch.q6_filter(), tpch.q6_aggregates(), row_begin=lo, row_end=hi)
+            assert info.used_jit_kernel == (1 if hi > lo else 0)  # an empty range launches nothing
+            util.assert_same_result(got, oracle.aggregate(t, tpch.q6_filter(), tpch.q6_aggregates(), row_begin=lo, row_end=hi), REL)
+    finally:
+        dt.destroy()
+
+
+def test_auto_mode_specialises_from_the_second_run(gpu_ctx):
+    from llkv_b200 import gpu
+    gpu_ctx.set_jit(1)
+    t, _ = tpch.lineitem_table(40_000, seed=9, with_q1=False)
+    dt = device_table(gpu_ctx, t)
+    prog = gpu.Program(gpu_ctx, tpch.q6_filter())
+    agg = gpu.Aggregation(dt, tpch.q6_aggregates() + [AggregateSpec("mx", AggregateKind.Max(tpch.L_QUANTITY, tpch.DEC_15_2))])
+    try:
+        want = oracle.aggregate(t, tpch.q6_filter(), tpch.q6_aggregates() + [AggregateSpec("mx", AggregateKind.Max(tpch.L_QUANTITY, tpch.DEC_15_2))])
+        seen = []
+        for _ in range(3):
+            agg.reset()
+            agg.run(prog, False)
+            util.assert_same_result(agg.finalize(1), want, REL)
+            seen.append(agg.run_info().used_jit_kernel)
+        assert seen == [0, 1, 1]
+    finally:
+        agg.destroy()
+        prog.destroy()
+        dt.destroy()
+
+
+@pytest.mark.parametrize("n", [1, 777, 20011])
+def test_specialised_ungrouped_aggregates_match_oracle(jit_always, n):
+    ctx = jit_always
+    t = mixed_table(n, seed=5 + n)
+    dt = device_table(ctx, t)
+    try:
+        for e in (None, PREDICATES[0], PREDICATES[5], Expr.Literal(False)):
+            got, info = run(ctx, dt, e, all_aggs())
+            util.assert_same_result(got, oracle.aggregate(t, e, all_aggs()), REL)
+    finally:
+        dt.destroy()
+
+
+def test_specialised_group_by_matches_oracle(jit_always):
+    ctx = jit_always
+    t = mixed_table(9000, seed=21, long_strings=False)
+    d = DataType.Decimal128(15, 2)
+    specs = [
+        AggregateSpec("n", AggregateKind.CountStar()),
+        AggregateSpec("s1", AggregateKind.Sum(1, DataType.Int64)),
+        AggregateSpec("s5", AggregateKind.Sum(5, d)),
+        AggregateSpec("a5", AggregateKind.Avg(5, d)),
+        AggregateSpec("sx", AggregateKind.Sum(ScalarExpr.Column(5) * (1 - ScalarExpr.Column(5)), DataType.Decimal128(38, 4))),
+        AggregateSpec("mn3", AggregateKind.Min(3, DataType.Float64)),
+        AggregateSpec("s3", AggregateKind.Sum(3, DataType.Float64)),
+        AggregateSpec("mx1", AggregateKind.Max(1, DataType.Int64)),
+    ]
+    dt = device_table(ctx, t)
+    try:
+        jitted = 0
+        for keys, hint in [((10,), 6), ((2,), 100), ((9, 10), 0), ((8,), 600), ((1,), 2000)]:
+            for e in (None, PREDICATES[0]):
+                got, info = run(ctx, dt, e, specs, group_by=keys, hint=hint, cap=1 << 14)
+                jitted += info.used_jit_kernel
+                want = oracle.aggregate(t, e, specs, group_by=keys, group_capacity=1 << 14)
+                util.assert_same_result(got, want, REL)
+        assert jitted >= 8
+    finally:
+        dt.destroy()
+
+
+@pytest.mark.parametrize("mode", [0, 2], ids=["interpreted", "specialised"])
+def test_mvcc_truth_table_through_the_lean_kernel(gpu_ctx, mode):
+    """RowVersion::is_visible_for vectors (llkv-transaction/src/mvcc.rs:528-555 + one vector per rule) as COUNT(*) under
+    a snapshot: all vectors in one table would share a snapshot, so each runs alone; every run has the same plan shape."""
+    gpu_ctx.set_jit(mode)
+    try:
+        for v in G["mvcc"]["vectors"] + G["mvcc"]["rule_vectors"]:
+            t = HostTable(1).add(HostColumn(1, DataType.Int64, np.array([5], dtype=np.int64)))
+            t.add_mvcc(np.array([v["created_by"]], np.uint64), np.array([v["deleted_by"]], np.uint64))
+            snap = Snapshot(v["txn_id"], v["snapshot_id"], tuple(v["noncommitted"]))
+            dt = device_table(gpu_ctx, t)
+            try:
+                got, info = run(gpu_ctx, dt, None, [AggregateSpec("n", AggregateKind.CountStar())], snap)
+                assert info.used_fast_kernel == 1 and info.used_jit_kernel == (1 if mode else 0)
+            finally:
+                dt.destroy()
+            assert got[0][1][0].value == (1 if v["visible"] else 0), v["note"]
+    finally:
+        gpu_ctx.set_jit(1)
+
+
+@pytest.mark.parametrize("tuning", [dict(block_threads=32, rows_per_thread=8, stages=4), dict(block_threads=256, rows_per_thread=1, stages=2, ctas_per_sm=2),
+                                    dict(block_threads=64, rows_per_thread=4, ctas_per_sm=4), dict(block_threads=96, rows_per_thread=8)],
+                         ids=["32x8", "256x1", "64x4", "96x8"])
+def test_specialised_geometries_agree(jit_always, tuning):
+    ctx = jit_always
+    t, snap = tpch.lineitem_table(60_000, seed=3, with_q1=True, with_mvcc=True)
+    ctx.set_tuning(**tuning)
+    dt = device_table(ctx, t)
+    try:
+        got, info = run(ctx, dt, tpch.q6_filter(), tpch.q6_aggregates())
+        assert info.used_jit_kernel == 1
+        util.assert_same_result(got, oracle.aggregate(t, tpch.q6_filter(), tpch.q6_aggregates()), REL)
+        got, info = run(ctx, dt, tpch.q1_filter(), tpch.q1_aggregates(), snap, tpch.Q1_GROUP_BY, hint=6, cap=16)
+        assert info.used_jit_kernel == 1
+        util.assert_same_result(got, oracle.aggregate(t, tpch.q1_filter(), tpch.q1_aggregates(), snap, group_by=tpch.Q1_GROUP_BY, group_capacity=16), REL)
+    finally:
+        dt.destroy()
