@@ -36,7 +36,11 @@ namespace llkv {
 __device__ __forceinline__ double lean_f64(i64 v) { return __longlong_as_double(v); }
 __device__ __forceinline__ i64 lean_bits(double d) { return __double_as_longlong(d); }
 
-static __device__ __noinline__ u64 lean_global_slot(u64* gkeys, u64 gcap, uint32_t n_keys, u64 K, uint32_t* errbits) {
+// Row of the global group table for key K (inserting it if new).  Bit 63 of the result reports a full table (the row is
+// then the spare one and the run is repeated with a larger table): no pointer to caller state, so callers' per-row
+// registers never get their address taken.
+constexpr u64 kSlotTableFull = 1ull << 63;
+static __device__ __noinline__ u64 lean_global_slot_raw(u64* gkeys, u64 gcap, uint32_t n_keys, u64 K) {
   if (n_keys == 0) return 0;
   if (K == kEmptyKey) return gcap;
   const u64 mask = gcap - 1;
@@ -50,17 +54,17 @@ static __device__ __noinline__ u64 lean_global_slot(u64* gkeys, u64 gcap, uint32
     }
     h = (h + 1) & mask;
   }
-  *errbits |= FLAG_TABLE_FULL;
-  return gcap;  // parked on the spare row; the flag makes the run fail
+  return gcap | kSlotTableFull;  // parked on the spare row; the flag makes the run fail
+}
+__device__ __forceinline__ u64 lean_global_slot(u64* gkeys, u64 gcap, uint32_t n_keys, u64 K, uint32_t& errbits) {
+  const u64 gs = lean_global_slot_raw(gkeys, gcap, n_keys, K);
+  if (gs & kSlotTableFull) errbits |= FLAG_TABLE_FULL;
+  return gs & ~kSlotTableFull;
 }
 
 // rows without a CTA-local group slot (more groups than slots) and values too large for the per-thread i64 partials go
-// straight to the global table, one atomic per row: rare, kept out of line
-// (returns error flags: no state of the caller has its address taken, so the per-row registers stay registers)
-static __device__ __noinline__ uint32_t lean_slow_accumulate(u64* gkeys, u64* gwords, u64 gcap, uint32_t n_keys, uint32_t n_gwords, uint32_t op,
-                                                             uint32_t flags, u64 K, i64 v, u64 row, uint32_t gword) {
-  uint32_t err = 0;
-  u64* w = &gwords[lean_global_slot(gkeys, gcap, n_keys, K, &err) * n_gwords + gword];
+// straight to the global table, one atomic per word: kept out of line
+static __device__ __noinline__ void lean_slow_accumulate(u64* w, uint32_t op, uint32_t flags, i64 v, u64 row) {
   switch (op) {
     case FO_COUNT_STAR: case FO_COUNT: atomicAdd(w, 1ull); break;
     case FO_FIRSTROW: case FO_FIRSTVALID: case FO_FIRSTNAN: atomicMin(w, row); break;
@@ -80,7 +84,6 @@ static __device__ __noinline__ uint32_t lean_slow_accumulate(u64* gkeys, u64* gw
     case FO_MIN_F: atomicMin(w, enc_f64(lean_f64(v))); break;
     default: atomicMax(w, enc_f64(lean_f64(v))); break;
   }
-  return err;
 }
 
 // packed GROUP BY key of row `idx` of the staged tile (slow path; the hot path computes keys in LeanTile::row_keys)
@@ -147,6 +150,7 @@ struct LeanTile {
   uint32_t rel0 = 0;
   i64 acc[R];
   uint32_t soff[R];  // byte offset of the row's slot inside the accumulator area
+  uint32_t gsl[R];   // rows in negm: their row of the global table (capacity < 2^32)
   unsigned actm = 0;  // bit r: row r of this thread is selected
   unsigned negm = 0;  // bit r: selected row without a CTA-local group slot (goes to the global table directly)
   bool has_slow = false;  // warp-uniform: some lane has a row in negm
@@ -254,15 +258,17 @@ struct LeanTile {
     }
   }
 
-  // rare: rows that go to the global table one atomic at a time.  Kept small (the key is recomputed out of line per
-  // row) because a specialised build carries one copy per aggregate instruction.
+  // Rows that go to the global table one atomic at a time: rows without a CTA-local slot (their global row was looked up
+  // once, at GROUP: high-cardinality plans send nearly every row this way) and values outside the proven range (rare:
+  // the global row is looked up here).
   __device__ __forceinline__ void slow_rows(uint32_t op, uint32_t flags, unsigned rows, uint32_t gword) {
     if (__any_sync(LLKV_FULL, rows != 0)) {
 #pragma unroll
       for (int r = 0; r < R; ++r)  // unrolled: acc[] must never be indexed dynamically
         if ((rows >> r) & 1u) {
-          const u64 K = lean_row_key(p, S, sb, (uint32_t)(r * NC + tid));
-          errbits |= lean_slow_accumulate(p.gkeys, p.gwords, p.gcap, S.n_keys, S.n_gwords, op, flags, K, acc[r], row0 + (u64)r * NC + tid, gword);
+          u64 gs = gsl[r];
+          if (!((negm >> r) & 1u)) gs = lean_global_slot(p.gkeys, p.gcap, S.n_keys, lean_row_key(p, S, sb, (uint32_t)(r * NC + tid)), errbits);
+          lean_slow_accumulate(&p.gwords[gs * S.n_gwords + gword], op, flags, acc[r], row0 + (u64)r * NC + tid);
         }
     }
   }
@@ -287,6 +293,7 @@ struct LeanTile {
     for (int r = 0; r < R; ++r) {
       acc[r] = 0;
       soff[r] = 0;
+      gsl[r] = 0;
     }
   }
 
@@ -398,6 +405,16 @@ struct LeanTile {
         row_keys(keys);
         const uint32_t FG = S.fg;
         negm = 0;
+        if (S.direct_global) {  // high cardinality: a CTA-local table would hold a vanishing share of the keys
+          negm = actm;
+          has_slow = __any_sync(LLKV_FULL, negm != 0);
+          if (has_slow) {
+#pragma unroll
+            for (int r = 0; r < R; ++r)
+              if ((negm >> r) & 1u) gsl[r] = (uint32_t)lean_global_slot(p.gkeys, p.gcap, S.n_keys, keys[r], errbits);
+          }
+          return true;
+        }
         // first probe without branches: after the first tiles every key of a low-cardinality GROUP BY sits at its home slot
         unsigned miss = 0;
 #pragma unroll
@@ -432,6 +449,11 @@ struct LeanTile {
           }
         }
         has_slow = __any_sync(LLKV_FULL, negm != 0);
+        if (has_slow) {  // one global-table lookup per row, shared by every aggregate of the plan
+#pragma unroll
+          for (int r = 0; r < R; ++r)
+            if ((negm >> r) & 1u) gsl[r] = (uint32_t)lean_global_slot(p.gkeys, p.gcap, S.n_keys, keys[r], errbits);
+        }
         return true;
       }
 
@@ -761,7 +783,7 @@ __device__ __forceinline__ void lean_body(const LeanPlan& p) {
     const u64 K = tbl[g];
     u64 gs = ~0ull;
     if (!grouped) gs = 0;
-    else if (K != kEmptyKey) gs = lean_global_slot(p.gkeys, p.gcap, S.n_keys, K, &errbits);
+    else if (K != kEmptyKey) gs = lean_global_slot(p.gkeys, p.gcap, S.n_keys, K, errbits);
     gslot_s[g] = gs;
   }
   __syncthreads();

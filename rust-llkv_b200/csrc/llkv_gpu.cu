@@ -1138,7 +1138,10 @@ static int32_t lean_geometry(const LeanTune& tn, const Plan& p, uint64_t row_beg
     if (hint == 0) FG = 8;
     else if (hint <= 16) FG = (uint32_t)std::max<u64>(4, next_pow2(hint));
     else if (hint <= 128) FG = 16;
-    else FG = 4;  // high cardinality: nearly every row goes to the global table anyway
+    else {  // high cardinality: nearly every row goes to the global table anyway
+      FG = 1;
+      s.direct_global = 1;
+    }
     while (FG > 4 && (u64)FG * thread_bytes * NC > 64u * 1024u) FG /= 2;
   }
   const uint32_t budget_total = (uint32_t)tn.max_smem;

@@ -250,6 +250,7 @@ struct LeanShape {
   LeanWord words[kLeanMaxWords];
   uint32_t key_bits[kMaxKeys], key_kind[kMaxKeys], key_strlen[kMaxKeys], key_col[kMaxKeys], key_load[kMaxKeys];
   uint32_t n_code, n_cols, n_words, n_gwords, n_keys, single_wide_key;
+  uint32_t direct_global;  // high-cardinality GROUP BY: no CTA-local slots, every selected row updates the global table
   uint32_t nc;           // consumer threads per CTA
   uint32_t rows_per_thread;
   uint32_t fg;           // CTA-local group slots (power of two; 1 when ungrouped)

@@ -81,5 +81,8 @@ def test_specialised_kernel_compiles_for_sm_100a(lineitem, tmp_path, query):
     usage = subprocess.run([cuobjdump, "-res-usage", cubin], capture_output=True, text=True, check=True).stdout
     regs = int(usage.split("REG:")[1].split()[0])
     assert regs <= (80 if query == "q6" else 128)
+    # the per-row state (accumulator, slot offsets, masks) must stay in registers: any stack frame means some helper took
+    # the address of the tile state or indexed a register array dynamically
+    assert int(usage.split("STACK:")[1].split()[0]) == 0
     if query == "q6":
         assert "ATOMS" not in sass  # ungrouped: thread-private accumulators, no shared-memory atomics at all
