@@ -327,8 +327,14 @@ struct llkv_gpu_agg {
   u64* mg_words = nullptr;
   size_t mg_key_elems = 0, mg_word_elems = 0;
   u64* mg_cap = nullptr;
+  // the lean plan of the previous run, reusable while request_signature() does not change
+  LeanPlan lean;
+  uint64_t lean_sig = 0;
+  uint32_t lean_grid = 0, lean_block = 0, lean_R = 0, lean_smem = 0, lean_ctas = 1, lean_jit_runs = 0;
   uint32_t* d_flags = nullptr;
   uint32_t* h_flags = nullptr;  // pinned
+  unsigned char* h_stage = nullptr;  // pinned landing buffer of finalize (small tables)
+  size_t h_stage_bytes = 0;
   Plan* d_plan = nullptr;
   Plan* h_plan = nullptr;  // pinned
   CompileResult cr;
@@ -1227,10 +1233,7 @@ static int32_t lean_geometry(const LeanTune& tn, const Plan& p, uint64_t row_beg
     g.block = s.nc;
     g.R = s.rows_per_thread;
     g.smem = s.smem_total;
-    u64 grid = (u64)tn.sm_count * got_ctas;
-    if (grid > lp.n_tiles) grid = lp.n_tiles;
-    if (grid == 0) grid = 1;
-    g.grid = (uint32_t)grid;
+    g.grid = (uint32_t)((u64)tn.sm_count * got_ctas);  // persistent CTAs; a launch uses min(grid, tiles of its row range)
     *ctas_out = got_ctas;
     return LLKV_OK;
   }
@@ -1536,6 +1539,7 @@ extern "C" void llkv_gpu_agg_destroy(llkv_gpu_agg* a) {
   if (a->d_plan) cudaFree(a->d_plan);
   if (a->h_plan) cudaFreeHost(a->h_plan);
   if (a->h_flags) cudaFreeHost(a->h_flags);
+  if (a->h_stage) cudaFreeHost(a->h_stage);
   delete a;
 }
 
@@ -1562,7 +1566,9 @@ static int32_t agg_freeze_layout(llkv_gpu_agg* a, const CompileResult& cr) {
   CUDA_TRY(cudaMemcpy(a->d_gclass, a->gclass.data(), a->n_gwords, cudaMemcpyHostToDevice));
   u64 gcap = 1;
   if (p.n_keys) {
-    gcap = next_pow2(std::max<u64>(1024, a->hint * 2));
+    // a small table when the caller knows the cardinality (Q1: 6 groups -> 32 rows): finalize and the multi-GPU merge
+    // move the whole table; it grows x4 on FLAG_TABLE_FULL if the hint was wrong
+    gcap = a->hint ? next_pow2(std::max<u64>(32, a->hint * 2)) : 1024;
   }
   int32_t rc = agg_alloc_table(a, gcap);
   if (rc) return rc;
@@ -1616,6 +1622,57 @@ static int32_t agg_grow_table(llkv_gpu_agg* a) {
   return LLKV_OK;
 }
 
+// Everything the compiled plan of a run depends on, folded into one word: the columns as the compiler sees them (device
+// pointers, row counts, statistics), the predicate program, the snapshot, tuning.  A prepared aggregate that runs again
+// over unchanged inputs reuses its lean plan instead of recompiling (the compile is ~20 us, a Q6 scan of SF10 240 us).
+static uint64_t fnv1a(uint64_t h, const void* data, size_t n) {
+  const unsigned char* b = static_cast<const unsigned char*>(data);
+  for (size_t i = 0; i < n; ++i) h = (h ^ b[i]) * 0x100000001b3ull;
+  return h;
+}
+template <typename T>
+static uint64_t fnv_pod(uint64_t h, const T& v) {
+  return fnv1a(h, &v, sizeof(T));
+}
+static uint64_t request_signature(const llkv_gpu_ctx* ctx, const CompileRequest& req, const llkv_gpu_program* prog, bool force_wide) {
+  uint64_t h = 0xcbf29ce484222325ull;
+  for (const ColumnMeta& c : req.cols) {
+    h = fnv_pod(h, c.field_id);
+    h = fnv_pod(h, c.type);
+    h = fnv_pod(h, c.precision);
+    h = fnv_pod(h, c.scale);
+    h = fnv_pod(h, c.nullable);
+    h = fnv_pod(h, c.load_kind);
+    h = fnv_pod(h, c.elem_bytes);
+    h = fnv_pod(h, c.dev_values);
+    h = fnv_pod(h, c.dev_validity);
+    h = fnv_pod(h, c.n_rows);
+    h = fnv_pod(h, c.dec_fits_i64);
+    h = fnv_pod(h, c.has_minmax);
+    h = fnv_pod(h, c.min_bits);
+    h = fnv_pod(h, c.max_bits);
+    h = fnv_pod(h, c.max_strlen);
+  }
+  if (prog) {
+    h = fnv1a(h, prog->ops.data(), prog->ops.size() * sizeof(llkv_eval_op));
+    h = fnv1a(h, prog->literals.data(), prog->literals.size() * sizeof(llkv_literal));
+    h = fnv1a(h, prog->nodes.data(), prog->nodes.size() * sizeof(llkv_scalar_node));
+    h = fnv1a(h, prog->list_roots.data(), prog->list_roots.size() * sizeof(int32_t));
+  }
+  h = fnv_pod(h, (int)(prog != nullptr));
+  h = fnv_pod(h, req.mvcc.enabled);
+  if (req.mvcc.enabled) {
+    h = fnv_pod(h, (size_t)(req.mvcc.created_by - req.cols.data()));
+    h = fnv_pod(h, (size_t)(req.mvcc.deleted_by - req.cols.data()));
+    h = fnv_pod(h, req.mvcc.txn_id);
+    h = fnv_pod(h, req.mvcc.snapshot_id);
+    h = fnv1a(h, req.mvcc.noncommitted.data(), req.mvcc.noncommitted.size() * 8);
+  }
+  const int tune[6] = {ctx->tune_ctas, ctx->tune_block, ctx->tune_stages, ctx->tune_rpt, ctx->tune_force_wide, (int)force_wide};
+  h = fnv1a(h, tune, sizeof(tune));
+  return h ? h : 1;
+}
+
 static int32_t agg_launch(llkv_gpu_agg* a, const llkv_gpu_program* prog, int apply_mvcc, uint64_t row_begin, uint64_t row_end,
                           bool force_wide) {
   llkv_gpu_ctx* ctx = a->ctx;
@@ -1625,33 +1682,61 @@ static int32_t agg_launch(llkv_gpu_agg* a, const llkv_gpu_program* prog, int app
   int32_t rc = build_request(ctx, a->table_id, prog, apply_mvcc, req, handles, &table_rows);
   if (rc) return rc;
   if (row_end > table_rows) return set_error(LLKV_ERR_INVALID_ARGUMENT, "row_end %llu beyond the table's %llu rows", (unsigned long long)row_end, (unsigned long long)table_rows);
-  req.specs = a->specs.data();
-  req.n_aggs = (int32_t)a->specs.size();
-  req.agg_nodes = a->nodes.data();
-  req.n_agg_nodes = (int32_t)a->nodes.size();
-  req.key_fields = a->keys;
-  req.expr_mode = a->expr_mode;
-  req.force_wide = force_wide || ctx->tune_force_wide == 1;
-  req.no_fast = ctx->tune_force_wide != 0;
-  if ((rc = compile_plan(req, a->cr))) return set_error(rc, "%s", a->cr.error.c_str());
-  if ((rc = agg_freeze_layout(a, a->cr))) return rc;
   Plan& p = a->cr.plan;
   Geometry g;
-  LeanPlan lean;
+  LeanPlan& lean = a->lean;
   uint32_t lean_ctas = 1;
   bool use_jit = false;
+  const uint64_t sig = request_signature(ctx, req, prog, force_wide);
+  if (a->lean_sig == sig && a->cr.fast && a->frozen) {
+    // same inputs as the previous run of this aggregate: the lean plan is still right, only the row range changes
+    g.grid = a->lean_grid;
+    g.block = a->lean_block;
+    g.R = a->lean_R;
+    g.smem = a->lean_smem;
+    lean_ctas = a->lean_ctas;
+    const uint32_t T = lean.s.tile_rows;
+    lean.row_begin = row_begin;
+    lean.row_end = row_end;
+    lean.first_tile = row_begin / T;
+    lean.n_tiles = row_end > row_begin ? (row_end + T - 1) / T - lean.first_tile : 0;
+  } else {
+    a->lean_sig = 0;
+    a->lean_jit_runs = 0;
+    req.specs = a->specs.data();
+    req.n_aggs = (int32_t)a->specs.size();
+    req.agg_nodes = a->nodes.data();
+    req.n_agg_nodes = (int32_t)a->nodes.size();
+    req.key_fields = a->keys;
+    req.expr_mode = a->expr_mode;
+    req.force_wide = force_wide || ctx->tune_force_wide == 1;
+    req.no_fast = ctx->tune_force_wide != 0;
+    if ((rc = compile_plan(req, a->cr))) return set_error(rc, "%s", a->cr.error.c_str());
+    if ((rc = agg_freeze_layout(a, a->cr))) return rc;
+    if (a->cr.fast) {
+      if ((rc = lean_geometry(lean_tune(ctx), p, row_begin, row_end, a->hint, lean, g, &lean_ctas))) return rc;
+      p.tile_rows = lean.s.tile_rows;
+      p.stages = lean.s.stages;
+      p.fast_groups = lean.s.fg;
+      a->lean_grid = g.grid;
+      a->lean_block = g.block;
+      a->lean_R = g.R;
+      a->lean_smem = g.smem;
+      a->lean_ctas = lean_ctas;
+      a->lean_sig = sig;
+    } else if ((rc = plan_geometry(ctx, p, a->cr.wide, false, row_begin, row_end, a->hint, g))) return rc;
+  }
   if (a->cr.fast) {
-    if ((rc = lean_geometry(lean_tune(ctx), p, row_begin, row_end, a->hint, lean, g, &lean_ctas))) return rc;
-    p.tile_rows = lean.s.tile_rows;
-    p.stages = lean.s.stages;
-    p.fast_groups = lean.s.fg;
     // specialise a plan shape once it repeats (jit_mode 1), always (2) or never (0)
     if (ctx->jit_mode == 2) use_jit = true;
     else if (ctx->jit_mode == 1) {
-      const std::string key(reinterpret_cast<const char*>(&lean.s), sizeof(LeanShape));
-      use_jit = ++ctx->shape_runs[key] >= 2;
+      if (a->lean_jit_runs < 2) {
+        const std::string key(reinterpret_cast<const char*>(&lean.s), sizeof(LeanShape));
+        a->lean_jit_runs = ++ctx->shape_runs[key];
+      }
+      use_jit = a->lean_jit_runs >= 2;
     }
-  } else if ((rc = plan_geometry(ctx, p, a->cr.wide, false, row_begin, row_end, a->hint, g))) return rc;
+  }
   p.gkeys = a->gkeys;
   p.gwords = a->gwords;
   p.gcap = a->gcap;
@@ -1679,6 +1764,7 @@ static int32_t agg_launch(llkv_gpu_agg* a, const llkv_gpu_program* prog, int app
     const u64 n_tiles = re > rb ? (re + p.tile_rows - 1) / p.tile_rows - first_tile : 0;
     if (n_tiles == 0) break;
     const u64 grid = std::min<u64>(g.grid, n_tiles);
+    if (!launches) a->info.grid = (uint32_t)grid;
     if (a->cr.fast) {
       lean.row_begin = rb;
       lean.row_end = re;
@@ -1710,7 +1796,6 @@ static int32_t agg_launch(llkv_gpu_agg* a, const llkv_gpu_program* prog, int app
   a->info.used_fast_kernel = a->cr.fast ? 1 : 0;
   a->info.algorithmic_bytes_per_row = a->cr.algorithmic_bytes_per_row;
   a->info.physical_bytes_per_row = a->cr.physical_bytes_per_row;
-  a->info.grid = g.grid;
   a->info.block = g.block;
   a->info.rows_per_tile = p.tile_rows;
   a->info.stages = p.stages;
@@ -2015,9 +2100,24 @@ static int32_t agg_collect(llkv_gpu_agg* a, std::vector<u64>& hk, std::vector<u6
   const u64 rows = a->gcap + 2;
   hk.resize(a->gcap);
   hw.resize(rows * a->n_gwords);
-  CUDA_TRY(cudaMemcpyAsync(hw.data(), a->gwords, hw.size() * 8, cudaMemcpyDeviceToHost, ctx->stream));
-  if (a->cr.plan.n_keys) CUDA_TRY(cudaMemcpyAsync(hk.data(), a->gkeys, hk.size() * 8, cudaMemcpyDeviceToHost, ctx->stream));
-  CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+  const size_t wbytes = hw.size() * 8, kbytes = a->cr.plan.n_keys ? hk.size() * 8 : 0;
+  if (wbytes + kbytes <= (4u << 20)) {  // small tables land in a page-locked buffer (one DMA each, no pageable staging)
+    if (a->h_stage_bytes < wbytes + kbytes) {
+      if (a->h_stage) CUDA_TRY(cudaFreeHost(a->h_stage));
+      a->h_stage = nullptr;
+      CUDA_TRY(cudaHostAlloc((void**)&a->h_stage, wbytes + kbytes, cudaHostAllocDefault));
+      a->h_stage_bytes = wbytes + kbytes;
+    }
+    CUDA_TRY(cudaMemcpyAsync(a->h_stage, a->gwords, wbytes, cudaMemcpyDeviceToHost, ctx->stream));
+    if (kbytes) CUDA_TRY(cudaMemcpyAsync(a->h_stage + wbytes, a->gkeys, kbytes, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    memcpy(hw.data(), a->h_stage, wbytes);
+    if (kbytes) memcpy(hk.data(), a->h_stage + wbytes, kbytes);
+  } else {
+    CUDA_TRY(cudaMemcpyAsync(hw.data(), a->gwords, wbytes, cudaMemcpyDeviceToHost, ctx->stream));
+    if (kbytes) CUDA_TRY(cudaMemcpyAsync(hk.data(), a->gkeys, kbytes, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+  }
   groups.clear();
   if (a->cr.plan.n_keys == 0) {
     groups.push_back(GroupRef{0, 0});
