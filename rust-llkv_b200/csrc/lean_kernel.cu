@@ -22,7 +22,7 @@ cudaError_t launch_lean(const LeanPlan& plan, uint32_t grid, cudaStream_t stream
   } while (0)
   if (plan.s.rows_per_thread == 8) LLKV_LAUNCH_LEAN(8);
   if (plan.s.rows_per_thread == 4) LLKV_LAUNCH_LEAN(4);
-  // rows_per_thread is 8, 4 or 1 (lean_geometry): nvcc 12.9's cicc crashes on the R = 2 instantiation with -lineinfo
+  if (plan.s.rows_per_thread == 2) LLKV_LAUNCH_LEAN(2);
   LLKV_LAUNCH_LEAN(1);
 #undef LLKV_LAUNCH_LEAN
 }

@@ -273,20 +273,22 @@ struct LeanTile {
     }
   }
 
-  __device__ __forceinline__ void begin_tile(const unsigned char* stage, u64 tile_row0, u64 base_row) {
+  // `rel_row0`: first row of the tile relative to the launch's first tile (a launch covers < 2^32 rows, so the per-tile
+  // bookkeeping is 32-bit; the absolute row is only formed where an aggregate needs it)
+  __device__ __forceinline__ void begin_tile(const unsigned char* stage, uint32_t rel_row0, u64 base_row, uint32_t begin_rel, uint32_t end_rel) {
     sb = stage;
-    row0 = tile_row0;
-    rel0 = (uint32_t)(row0 - base_row) + (uint32_t)tid;  // launch-relative index of this thread's row r = 0
+    row0 = base_row + rel_row0;
+    rel0 = rel_row0 + (uint32_t)tid;  // launch-relative index of this thread's row r = 0
     negm = 0;
     has_slow = false;
-    if (row0 >= p.row_begin && row0 + T <= p.row_end) {
+    if (rel_row0 >= begin_rel && rel_row0 + T <= end_rel) {
       actm = (1u << R) - 1u;
     } else {
       actm = 0;
 #pragma unroll
       for (int r = 0; r < R; ++r) {
-        const u64 row = row0 + (u64)r * NC + tid;
-        if (row >= p.row_begin && row < p.row_end) actm |= 1u << r;
+        const uint32_t row = rel0 + (uint32_t)(r * NC);
+        if (row >= begin_rel && row < end_rel) actm |= 1u << r;
       }
     }
 #pragma unroll
@@ -415,32 +417,37 @@ struct LeanTile {
           }
           return true;
         }
-        // first probe without branches: after the first tiles every key of a low-cardinality GROUP BY sits at its home slot
+        // Probe without branches: the key's home pair of slots (two adjacent entries, one 16-byte read).  Probe order is
+        // home slot, its pair neighbour, then the following pairs, so after the first tiles a key of a low-cardinality
+        // GROUP BY is found here even when two keys share a home slot.
         unsigned miss = 0;
 #pragma unroll
         for (int r = 0; r < R; ++r) {
           const uint32_t h = hash_key32(keys[r]) & (FG - 1);
-          const bool hit = tbl[h] == keys[r] && keys[r] != kEmptyKey;
-          soff[r] = h * S.slot_stride;
-          if (!hit && ((actm >> r) & 1u)) miss |= 1u << r;
+          const ulonglong2 pair = *reinterpret_cast<const ulonglong2*>(&tbl[h & ~1u]);
+          const u64 k_home = (h & 1u) ? pair.y : pair.x, k_other = (h & 1u) ? pair.x : pair.y;
+          const bool hit_home = k_home == keys[r], hit_other = k_other == keys[r];
+          const uint32_t sl = hit_home ? h : (h ^ 1u);
+          soff[r] = sl * S.slot_stride;
+          if (!((hit_home || hit_other) && keys[r] != kEmptyKey) && ((actm >> r) & 1u)) miss |= 1u << r;
         }
-        if (__any_sync(LLKV_FULL, miss != 0)) {  // new key, collision chain, table full or the reserved key value
+        if (__any_sync(LLKV_FULL, miss != 0)) {  // new key, longer collision chain, table full or the reserved key value
 #pragma unroll
           for (int r = 0; r < R; ++r) {
             if ((miss >> r) & 1u) {
               const u64 K = keys[r];
               int sl = -1;
               if (K != kEmptyKey) {
-                uint32_t h = hash_key32(K) & (FG - 1);
+                const uint32_t h0 = hash_key32(K) & (FG - 1);
 #pragma unroll 1
                 for (uint32_t i = 0; i < FG; ++i) {
+                  const uint32_t h = ((((h0 >> 1) + (i >> 1)) << 1) | ((h0 ^ i) & 1u)) & (FG - 1);
                   const u64 cur = tbl[h];
                   if (cur == K) { sl = (int)h; break; }
                   if (cur == kEmptyKey) {
                     const u64 old = atomicCAS(&tbl[h], kEmptyKey, K);
                     if (old == kEmptyKey || old == K) { sl = (int)h; break; }
                   }
-                  h = (h + 1) & (FG - 1);
                 }
               }
               soff[r] = sl >= 0 ? (uint32_t)sl * S.slot_stride : 0u;
@@ -728,9 +735,9 @@ __device__ __forceinline__ void lean_body(const LeanPlan& p) {
   }
   __syncthreads();
 
-  const u64 n_tiles = p.n_tiles;
   const uint32_t T = S.tile_rows;
-  const u64 my_tiles = (n_tiles > blockIdx.x) ? (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+  const uint32_t n_tiles = (uint32_t)p.n_tiles;  // < 2^32 / T per launch (the host splits longer scans)
+  const uint32_t my_tiles = (n_tiles > blockIdx.x) ? (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
   const u64 base_row = p.first_tile * (u64)T;
   uint32_t errbits = 0;
 
@@ -738,9 +745,9 @@ __device__ __forceinline__ void lean_body(const LeanPlan& p) {
     // ---------------------------------------------------------------- producer: TMA bulk copies, `stages` tiles in flight
     if (lane == 0) {
       uint32_t s = 0, round = 0;
-      for (u64 li = 0; li < my_tiles; ++li) {
+      for (uint32_t li = 0, rt = blockIdx.x; li < my_tiles; ++li, rt += gridDim.x) {
         if (round) mbar_wait_parked(&empty_bar[s], (round - 1) & 1);
-        const u64 tile = p.first_tile + blockIdx.x + li * gridDim.x;
+        const u64 tile = p.first_tile + rt;
         unsigned char* sbuf = stage0 + (size_t)s * S.stage_bytes;
         mbar_arrive_expect_tx(&full_bar[s], S.tx_bytes);
 #pragma unroll
@@ -759,11 +766,13 @@ __device__ __forceinline__ void lean_body(const LeanPlan& p) {
   } else {
     // ---------------------------------------------------------------- consumers
     LeanTile<R, Cfg> t(p, S, smem, tid, NC);
+    const uint32_t begin_rel = (uint32_t)(p.row_begin - base_row);
+    const u64 end64 = p.row_end - base_row;
+    const uint32_t end_rel = end64 > 0xffffffffull ? 0xffffffffu : (uint32_t)end64;
     uint32_t s = 0, round = 0;
-    for (u64 li = 0; li < my_tiles; ++li) {
-      const u64 tile = p.first_tile + blockIdx.x + li * gridDim.x;
+    for (uint32_t li = 0, rt = blockIdx.x; li < my_tiles; ++li, rt += gridDim.x) {
       mbar_wait_parked(&full_bar[s], round & 1);
-      t.begin_tile(stage0 + (size_t)s * S.stage_bytes, tile * (u64)T, base_row);
+      t.begin_tile(stage0 + (size_t)s * S.stage_bytes, rt * T, base_row, begin_rel, end_rel);
       if constexpr (Cfg::kStatic) t.template run_static<0>();
       else t.run_dynamic();
       __syncwarp();

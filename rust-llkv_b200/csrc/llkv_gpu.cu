@@ -1155,7 +1155,6 @@ static int32_t lean_geometry(const LeanTune& tn, const Plan& p, uint64_t row_beg
   if (want_stages == 1) want_stages = 2;
   const uint32_t want_ctas = tn.ctas ? (uint32_t)tn.ctas : 0u;
   uint32_t want_R = tn.rpt ? (uint32_t)tn.rpt : 0u;
-  if (want_R == 2) want_R = 1;  // the lean kernel is built for 8, 4 and 1 rows per thread
 
   // layout for one candidate geometry; returns the stages that fit (0 = does not fit)
   auto layout = [&](uint32_t R, uint32_t ctas, uint32_t fg, uint32_t nc) -> uint32_t {
@@ -1203,23 +1202,33 @@ static int32_t lean_geometry(const LeanTune& tn, const Plan& p, uint64_t row_beg
     s.tx_bytes = tx;
     return st;
   };
-  // candidates in order of preference: several CTAs per SM (the producer of one covers the consumers of another) with
-  // the most rows per thread that leaves a pipeline of >= 3 (else 2) stages; then a single CTA per SM; then fewer
-  // CTA-local groups and consumer threads.  Explicit tuning pins the corresponding dimension.
-  const uint32_t Rs[3] = {8, 4, 1};
+  // Candidates: rows per thread x CTAs per SM, each with the deepest pipeline (2..4 stages) that fits.  The kernel is
+  // latency-bound when its per-thread state is fat (Q1) and HBM-bound when it is thin (Q6), so the choice maximises
+  // resident consumer warps (up to 12 per SM: beyond that nothing measured gained), then rows per thread (fewer
+  // per-tile fixed costs), then stages.  One row per thread only when nothing else fits; then fewer CTA-local groups
+  // and consumer threads.  Explicit tuning pins the corresponding dimension.
   uint32_t got_ctas = 0;
   for (uint32_t fg = FG, nc = NC; !got_ctas;) {
-    for (int single = 0; single < 2 && !got_ctas; ++single)
-      for (int ri = 0; ri < 3 && !got_ctas; ++ri) {
-        if (want_R && Rs[ri] != want_R) continue;
-        for (int min_stages = 3; min_stages >= 2 && !got_ctas; --min_stages)
-          for (uint32_t ctas = single ? 1 : 4; ctas >= (single ? 1u : 2u) && !got_ctas; --ctas) {
-            const uint32_t c = want_ctas ? want_ctas : ctas;
-            if (layout(Rs[ri], c, fg, nc) >= (uint32_t)min_stages) got_ctas = c;
-            if (want_ctas) break;
-          }
+    uint32_t best_score = 0, best_R = 0, best_c = 0;
+    const uint32_t Rs[4] = {8, 4, 2, 1};
+    for (int ri = 0; ri < 4; ++ri) {
+      if (want_R ? Rs[ri] != want_R : (Rs[ri] == 1 && best_score)) continue;
+      for (uint32_t ctas = 4; ctas >= 1; --ctas) {
+        const uint32_t c = want_ctas ? want_ctas : ctas;
+        const uint32_t st = layout(Rs[ri], c, fg, nc);
+        if (st >= 2) {
+          const uint32_t warps = std::min<uint32_t>(c * (nc / 32), 12);
+          const uint32_t score = warps * 1000 + Rs[ri] * 10 + st;
+          if (score > best_score) { best_score = score; best_R = Rs[ri]; best_c = c; }
+        }
+        if (want_ctas) break;
       }
-    if (got_ctas) break;
+    }
+    if (best_score) {
+      layout(best_R, best_c, fg, nc);  // re-establish the winner's layout in `s`
+      got_ctas = best_c;
+      break;
+    }
     if (p.n_keys && fg > 2) fg /= 2;
     else if (nc > 32) nc /= 2;
     else break;
