@@ -29,6 +29,8 @@ cudaError_t launch_scan(const Plan* dplan, bool wide, int rows_per_thread, uint3
 cudaError_t launch_lean(const LeanPlan& plan, uint32_t grid, cudaStream_t stream);
 cudaError_t launch_init_table(u64* keys, u64* words, u64 rows, uint32_t n_gwords, const uint8_t* word_class_dev, cudaStream_t stream);
 cudaError_t launch_merge_table(const Plan* dplan, const u64* src_keys, const u64* src_words, u64 src_cap, cudaStream_t stream);
+cudaError_t launch_merge_ungrouped(u64* dst, const u64* all_words, int n_ranks, uint32_t n_gwords, u64 rank_stride, const uint8_t* word_class_dev,
+                                   cudaStream_t stream);
 }  // namespace llkv
 
 using namespace llkv;
@@ -2282,12 +2284,26 @@ extern "C" int32_t llkv_gpu_agg_merge(llkv_gpu_agg* a) {
   llkv_gpu_ctx* ctx = a->ctx;
   CUDA_TRY(cudaSetDevice(ctx->device));
   if (a->err_code) return set_error(a->err_code, "%s", a->err_msg.c_str());
-  int32_t rc = agg_resolve(a);
+  int32_t rc;
+  const int N = ctx->n_ranks;
+  const int nccl_u64 = 5 /* ncclUint64 */, nccl_max = 2 /* ncclMax */;
+  // Ungrouped state whose run cannot ask for a rerun (no 64-bit narrowing to fail, no table to fill): the merge is
+  // queued behind the scan on the same stream without waiting for it: all-gather of the one state row, one kernel.
+  if (a->frozen && a->cr.plan.n_keys == 0 && !a->cr.can_narrow_fail && ctx->nccl_comm && N > 1) {
+    const size_t word_elems = (size_t)(3 * a->n_gwords);
+    if (a->mg_word_elems < word_elems * (size_t)N) {
+      if (a->mg_words) CUDA_TRY(cudaFree(a->mg_words));
+      CUDA_TRY(cudaMalloc((void**)&a->mg_words, word_elems * 8 * (size_t)N));
+      a->mg_word_elems = word_elems * (size_t)N;
+    }
+    NCCL_TRY(g_nccl.all_gather(a->gwords, a->mg_words, word_elems, nccl_u64, ctx->nccl_comm, ctx->stream));
+    CUDA_TRY(launch_merge_ungrouped(a->gwords, a->mg_words, N, a->n_gwords, word_elems, a->d_gclass, ctx->stream));
+    return LLKV_OK;
+  }
+  rc = agg_resolve(a);
   if (rc) return rc;
   if ((rc = agg_ensure_layout(a))) return rc;
   if (!ctx->nccl_comm || ctx->n_ranks == 1) return LLKV_OK;
-  const int N = ctx->n_ranks;
-  const int nccl_u64 = 5 /* ncclUint64 */, nccl_max = 2 /* ncclMax */;
   const bool grouped = a->cr.plan.n_keys != 0;
   if (grouped) {
     // all ranks must use one table size: agree on the largest

@@ -949,7 +949,49 @@ __global__ void merge_table_kernel(const Plan* __restrict__ gplan, const u64* sr
   if (err) atomicOr(p.flags, err);
 }
 
+// Ungrouped multi-GPU merge: the state is one row of words.  One thread per word folds the N gathered rows in rank
+// order starting from the word's identity, so every rank ends with the bit-identical state (f64 sums included) and the
+// whole merge is one launch after the all-gather: no table re-initialisation, no plan upload.
+__global__ void merge_ungrouped_kernel(u64* dst, const u64* all_words, int n_ranks, uint32_t n_gwords, u64 rank_stride,
+                                       const uint8_t* word_class_dev) {
+  const uint32_t w = blockIdx.x * blockDim.x + threadIdx.x;
+  if (w >= n_gwords) return;
+  const uint8_t c = word_class_dev[w];
+  if (c == WC_PAIR_LO_MIN || c == WC_PAIR_LO_MAX) return;  // written with its high word
+  if (c == WC_MIN128 || c == WC_MAX128) {
+    const bool is_max = c == WC_MAX128;
+    u64 bh = is_max ? 0ull : ~0ull, bl = bh;
+    for (int r = 0; r < n_ranks; ++r) {
+      const u64 h = all_words[(u64)r * rank_stride + w], l = all_words[(u64)r * rank_stride + w + 1];
+      const bool better = is_max ? (h > bh || (h == bh && l > bl)) : (h < bh || (h == bh && l < bl));
+      if (better) { bh = h; bl = l; }
+    }
+    dst[w] = bh;
+    dst[w + 1] = bl;
+    return;
+  }
+  u64 acc = c == WC_MIN ? ~0ull : 0ull;
+  double facc = 0.0;
+  for (int r = 0; r < n_ranks; ++r) {
+    const u64 v = all_words[(u64)r * rank_stride + w];
+    switch (c) {
+      case WC_SUM: acc += v; break;
+      case WC_FSUM: facc += __longlong_as_double((i64)v); break;
+      case WC_MIN: acc = v < acc ? v : acc; break;
+      case WC_MAX: acc = v > acc ? v : acc; break;
+      default: break;
+    }
+  }
+  dst[w] = c == WC_FSUM ? (u64)__double_as_longlong(facc) : acc;
+}
+
 // ------------------------------------------------------------------ host-callable launchers
+cudaError_t launch_merge_ungrouped(u64* dst, const u64* all_words, int n_ranks, uint32_t n_gwords, u64 rank_stride,
+                                   const uint8_t* word_class_dev, cudaStream_t stream) {
+  merge_ungrouped_kernel<<<(n_gwords + 127) / 128, 128, 0, stream>>>(dst, all_words, n_ranks, n_gwords, rank_stride, word_class_dev);
+  return cudaGetLastError();
+}
+
 cudaError_t launch_scan(const Plan* dplan, bool wide, int rows_per_thread, uint32_t grid, uint32_t block, uint32_t smem,
                         cudaStream_t stream) {
 #define LLKV_LAUNCH(W, RR)                                                                              \
