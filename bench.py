@@ -17,6 +17,9 @@ import sys
 import threading
 import time
 
+# stdout carries exactly one JSON line: NCCL's own banner ("NCCL version ...") goes to stderr
+os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+
 ROOT = os.path.dirname(os.path.abspath(__file__))
 for p in (os.path.join(ROOT, "rust-llkv_b200"), ROOT):
     if p not in sys.path:
