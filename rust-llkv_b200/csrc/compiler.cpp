@@ -1675,6 +1675,7 @@ class Emitter {
   bool lower_fast() {
     Plan& p = out_.plan;
     if (wide_ || req_.bitmap_mode) return false;
+    if (plan_cols_.empty()) return false;  // nothing to stream (COUNT(*) without a filter): no tiles for the lean pipeline
     for (const ColumnMeta* c : plan_cols_) {
       if (c->nullable) return false;
       if (c->load_kind == LK_D128 && !c->dec_fits_i64) return false;

@@ -268,24 +268,31 @@ __device__ __forceinline__ void gadd_sum_i128(u64* w, i128 t) {
   atomicAdd(&w[2], (u64)(t >> 64) & 0xffffffffull);
   atomicAdd(&w[3], (u64)(i64)(t >> 96));
 }
+__device__ __forceinline__ void cas128(ulonglong2* addr, u64 cmp_hi, u64 cmp_lo, u64 swp_hi, u64 swp_lo, u64& old_hi, u64& old_lo) {
+  asm volatile(
+      "{\n\t.reg .b128 cmp, swp, old;\n\t"
+      "mov.b128 cmp, {%2, %3};\n\t"
+      "mov.b128 swp, {%4, %5};\n\t"
+      "atom.global.cas.b128 old, [%6], cmp, swp;\n\t"
+      "mov.b128 {%0, %1}, old;\n\t}"
+      : "=l"(old_hi), "=l"(old_lo)
+      : "l"(cmp_hi), "l"(cmp_lo), "l"(swp_hi), "l"(swp_lo), "l"(addr)
+      : "memory");
+}
 __device__ __forceinline__ void gmin128(u64* w, u64 hi_enc, u64 lo, bool is_max) {
-  // 16-byte CAS loop on (hi_enc, lo): lexicographic order of (hi_enc, lo) == numeric order of the i128
+  // 16-byte CAS loop on (hi_enc, lo): lexicographic order of (hi_enc, lo) == numeric order of the i128.
+  // The current pair is read with a CAS too (cmp == swp leaves memory unchanged): two plain 8-byte loads could pair the
+  // high word of one update with the low word of another, and a candidate compared against such a torn pair can be
+  // dropped although it beats both real states (values of mixed sign).
   ulonglong2* addr = reinterpret_cast<ulonglong2*>(w);
-  u64 cur_hi = w[0], cur_lo = w[1];
+  u64 cur_hi, cur_lo;
+  cas128(addr, 0ull, 0ull, 0ull, 0ull, cur_hi, cur_lo);
   while (true) {
     const bool better = is_max ? (hi_enc > cur_hi || (hi_enc == cur_hi && lo > cur_lo))
                                : (hi_enc < cur_hi || (hi_enc == cur_hi && lo < cur_lo));
     if (!better) return;
     u64 old_hi, old_lo;
-    asm volatile(
-        "{\n\t.reg .b128 cmp, swp, old;\n\t"
-        "mov.b128 cmp, {%2, %3};\n\t"
-        "mov.b128 swp, {%4, %5};\n\t"
-        "atom.global.cas.b128 old, [%6], cmp, swp;\n\t"
-        "mov.b128 {%0, %1}, old;\n\t}"
-        : "=l"(old_hi), "=l"(old_lo)
-        : "l"(cur_hi), "l"(cur_lo), "l"(hi_enc), "l"(lo), "l"(addr)
-        : "memory");
+    cas128(addr, cur_hi, cur_lo, hi_enc, lo, old_hi, old_lo);
     if (old_hi == cur_hi && old_lo == cur_lo) return;
     cur_hi = old_hi;
     cur_lo = old_lo;

@@ -158,3 +158,19 @@ def test_specialised_geometries_agree(jit_always, tuning):
         util.assert_same_result(got, oracle.aggregate(t, tpch.q1_filter(), tpch.q1_aggregates(), snap, group_by=tpch.Q1_GROUP_BY, group_capacity=16), REL)
     finally:
         dt.destroy()
+
+
+def test_count_star_without_any_column(gpu_ctx):
+    """COUNT(*) with no filter and no snapshot reads no column at all: the plan must not take the tile pipeline."""
+    t, _ = tpch.lineitem_table(10_000, seed=2, with_q1=False)
+    dt = device_table(gpu_ctx, t)
+    try:
+        for mode in (0, 2):
+            gpu_ctx.set_jit(mode)
+            got, info = run(gpu_ctx, dt, None, [AggregateSpec("n", AggregateKind.CountStar())])
+            assert got[0][1][0].value == 10_000
+            got, info = run(gpu_ctx, dt, None, [AggregateSpec("n", AggregateKind.CountStar())], row_begin=17, row_end=4242)
+            assert got[0][1][0].value == 4242 - 17
+    finally:
+        gpu_ctx.set_jit(1)
+        dt.destroy()

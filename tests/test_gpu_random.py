@@ -1,0 +1,111 @@
+"""GPU: randomised differential test.  Random (seeded) predicates, aggregate lists, GROUP BY keys, cardinality hints and
+row ranges over a mixed-type table without NULLs, so most plans take the lean kernel; each plan runs interpreted and
+specialised and both must equal the oracle (bit-exact integers / decimals / counts / min / max, 1e-12 for f64)."""
+import numpy as np
+import pytest
+
+import util
+from llkv_b200.expr import AggregateKind, AggregateSpec, Bound, DataType, Expr, Literal, Operator, ScalarExpr, pred
+from llkv_b200 import tpch
+from llkv_b200.table import LlkvError, Snapshot
+from oracle import oracle
+from test_gpu_parity import REL, device_table, mixed_table
+
+pytestmark = pytest.mark.gpu
+D = DataType.Decimal128(15, 2)
+
+
+def random_filter(rng):
+    leaves = [
+        lambda: pred(1, Operator.Range(Bound.Included(int(rng.integers(-900, 0))), Bound.Excluded(int(rng.integers(0, 900))))),
+        lambda: pred(2, Operator.LessThan(int(rng.integers(-40, 50)))),
+        lambda: pred(4, Operator.GreaterThanOrEquals(int(rng.integers(0, 400)))),
+        lambda: pred(5, Operator.Range(Bound.Included(Literal.Decimal128(int(rng.integers(-10**7, 0)), 2)), Bound.Included(Literal.Decimal128(int(rng.integers(0, 10**7)), 2)))),
+        lambda: pred(6, Operator.LessThanOrEquals(Literal.Date32(int(rng.integers(8000, 11000))))),
+        lambda: pred(2, Operator.GreaterThan(int(rng.integers(-50, 30)))),
+        lambda: pred(9, Operator.Equals(bool(rng.integers(0, 2)))),
+    ]
+    k = int(rng.integers(0, 4))
+    if k == 0:
+        return None
+    picks = [leaves[i]() for i in rng.choice(len(leaves), size=k, replace=False)]
+    return picks[0] if k == 1 else Expr.And(picks)
+
+
+def random_aggs(rng):
+    c = ScalarExpr.Column
+    pool = [
+        AggregateSpec("n", AggregateKind.CountStar()),
+        AggregateSpec("c2", AggregateKind.Count(2)),
+        AggregateSpec("s1", AggregateKind.Sum(1, DataType.Int64)),
+        AggregateSpec("a1", AggregateKind.Avg(1, DataType.Int64)),
+        AggregateSpec("mn1", AggregateKind.Min(1, DataType.Int64)),
+        AggregateSpec("mx8", AggregateKind.Max(c(8) * c(2), DataType.Int64)),
+        AggregateSpec("s3", AggregateKind.Sum(3, DataType.Float64)),
+        AggregateSpec("mn3", AggregateKind.Min(3, DataType.Float64)),
+        AggregateSpec("mx3", AggregateKind.Max(c(3) * c(1), DataType.Float64)),
+        AggregateSpec("s5", AggregateKind.Sum(5, D)),
+        AggregateSpec("a5", AggregateKind.Avg(5, D)),
+        AggregateSpec("mn5", AggregateKind.Min(5, D)),
+        AggregateSpec("mx5", AggregateKind.Max(5, D)),
+        AggregateSpec("sx", AggregateKind.Sum(c(1) * c(2) + c(8) - 7, DataType.Int64)),
+        AggregateSpec("sdd", AggregateKind.Sum(c(5) * c(5), DataType.Decimal128(38, 4))),
+        AggregateSpec("sdi", AggregateKind.Sum(c(5) * (1 - c(5)), DataType.Decimal128(38, 4))),
+        AggregateSpec("sf", AggregateKind.Sum(c(3) * c(2), DataType.Float64)),
+        AggregateSpec("t4", AggregateKind.Total(4, DataType.UInt64)),
+    ]
+    k = int(rng.integers(1, 7))
+    return [pool[i] for i in sorted(rng.choice(len(pool), size=k, replace=False))]
+
+
+@pytest.mark.parametrize("seed", range(10))
+def test_random_plans_match_oracle(gpu_ctx, seed):
+    from llkv_b200 import gpu
+    rng = np.random.default_rng(1000 + seed)
+    n = int(rng.integers(3000, 40000))
+    t = mixed_table(n, seed=seed + 77, long_strings=False)
+    c_by, d_by, snap_all = tpch.mvcc_arrays(n, seed=seed)
+    t.add_mvcc(c_by, d_by)
+    dt = device_table(gpu_ctx, t)
+    lean_runs = 0
+    try:
+        for trial in range(5):
+            f = random_filter(rng)
+            specs = random_aggs(rng)
+            keys = [(), (), (10,), (9,), (2,), (9, 10), (8,), (6,)][int(rng.integers(0, 8))]
+            hint = int(rng.choice([0, 2, 6, 100, 5000])) if keys else 0
+            lo = int(rng.integers(0, n // 3)) if rng.random() < 0.5 else 0
+            hi = int(rng.integers(2 * n // 3, n + 1)) if rng.random() < 0.5 else n
+            snap = [None, snap_all, Snapshot(77, 100, (77, 101))][int(rng.integers(0, 3))]
+            ctx_note = f"seed {seed} trial {trial} keys {keys} hint {hint} rows [{lo},{hi}) snapshot {snap} aggs {[s.alias for s in specs]}"
+            try:
+                want = oracle.aggregate(t, f, specs, snap, keys, row_begin=lo, row_end=hi, group_capacity=1 << 15)
+            except LlkvError as e:
+                want = e
+            for mode in (0, 2):
+                gpu_ctx.set_jit(mode)
+                prog = gpu.Program(gpu_ctx, f) if f is not None else None
+                dt.set_snapshot(snap)
+                agg = gpu.Aggregation(dt, specs, keys, cardinality_hint=hint)
+                try:
+                    if isinstance(want, LlkvError):
+                        with pytest.raises(LlkvError) as got:
+                            agg.run(prog, snap is not None, lo, hi)
+                            agg.finalize(1 << 15)
+                        assert got.value.code == want.code, ctx_note
+                    else:
+                        agg.run(prog, snap is not None, lo, hi)
+                        got = agg.finalize(1 << 15)
+                        lean_runs += agg.run_info().used_fast_kernel
+                        try:
+                            util.assert_same_result(got, want, REL)
+                        except AssertionError as e:
+                            raise AssertionError(f"{ctx_note} jit={mode}: {e}") from e
+                finally:
+                    agg.destroy()
+                    if prog:
+                        prog.destroy()
+        assert lean_runs >= 2  # the point of this test is the lean kernel (Int16 arguments stay on the general interpreter)
+    finally:
+        gpu_ctx.set_jit(1)
+        dt.destroy()
