@@ -493,3 +493,72 @@ def test_full_size_properties_q6(gpu_ctx):
         assert whole[0].value == int(((prod + 50) // 100).sum())
     finally:
         dt.destroy()
+
+
+def test_full_size_properties_sf10_q6_q1(gpu_ctx):
+    """BASELINE.json configs 2 and 3 at their full size (SF10, 59 986 052 rows), where the oracle does not finish in
+    seconds: size-independent properties.  Exact integer identities against numpy restatements of the two queries over
+    the generator's arrays (per group for Q1, with the snapshot rule evaluated for the generator's transaction ids),
+    additivity over disjoint row ranges, and COUNT(*) against the popcount of the selection bitmap, which a different
+    kernel (the general interpreter) produces.  Runs on the specialised lean kernel from the second run on."""
+    from llkv_b200 import gpu
+    n = tpch.lineitem_rows(10.0)
+    assert n == 59_986_052
+    a = tpch.lineitem_arrays(n, seed=6, with_q1=True)
+    t, _ = tpch.lineitem_table(n, seed=6, with_q1=True)
+    created, deleted, snap = tpch.mvcc_arrays(n, seed=6)
+    t.add_mvcc(created, deleted)
+    dt = gpu.DeviceTable.from_host(gpu_ctx, t, chunk_rows=1 << 20)
+    del t
+    try:
+        # ---- Q6
+        specs6 = tpch.q6_aggregates() + [AggregateSpec("n", AggregateKind.CountStar()),
+                                         AggregateSpec("sp", AggregateKind.Sum(tpch.L_EXTENDEDPRICE, tpch.DEC_15_2))]
+        cuts = [0, 7_000_001, 33_333_333, n]
+        whole = dt.aggregate(tpch.q6_filter(), specs6)[0][1]
+        parts = [dt.aggregate(tpch.q6_filter(), specs6, row_begin=lo, row_end=hi)[0][1] for lo, hi in zip(cuts, cuts[1:])]
+        for i in range(3):
+            assert whole[i].value == sum(p[i].value for p in parts)
+        m = ((a["shipdate"] >= tpch.date32(1994, 1, 1)) & (a["shipdate"] < tpch.date32(1995, 1, 1)) & (a["discount"] >= 5)
+             & (a["discount"] <= 7) & (a["quantity"] < 2400))
+        _, count = dt.filter_bitmap(tpch.q6_filter())
+        assert count == whole[1].value == int(m.sum())
+        assert whole[2].value == int(a["extendedprice"][m].sum())
+        prod = a["extendedprice"][m] * a["discount"][m]  # scale 4 -> scale 2, half away from zero (values are >= 0)
+        assert whole[0].value == int(((prod + 50) // 100).sum())
+        # ---- Q1 under the snapshot
+        vis = (created == 1) & ((deleted == np.uint64(tpch.TXN_ID_NONE)) | (deleted == np.uint64(77)))
+        sel = vis & (a["shipdate"] <= tpch.date32(1998, 9, 2))
+        _, count1 = dt.filter_bitmap(tpch.q1_filter(), snap)
+        assert count1 == int(sel.sum())
+        got = dt.aggregate(tpch.q1_filter(), tpch.q1_aggregates(), snap, group_by=tpch.Q1_GROUP_BY, cardinality_hint=6, group_capacity=16)
+        lo_half = dt.aggregate(tpch.q1_filter(), tpch.q1_aggregates(), snap, group_by=tpch.Q1_GROUP_BY, cardinality_hint=6, group_capacity=16,
+                               row_end=29_000_003)
+        hi_half = dt.aggregate(tpch.q1_filter(), tpch.q1_aggregates(), snap, group_by=tpch.Q1_GROUP_BY, cardinality_hint=6, group_capacity=16,
+                               row_begin=29_000_003)
+        assert len(got) == 4 and sum(v[7].value for _, v in got) == count1
+        halves = {}
+        for rows in (lo_half, hi_half):
+            for k, v in rows:
+                acc = halves.setdefault(k, [0, 0, 0, 0, 0])
+                for i, j in enumerate((0, 1, 2, 3, 7)):
+                    acc[i] += v[j].value
+        disc_price = a["extendedprice"] * (100 - a["discount"])      # scale 4, exact
+        for key, v in got:
+            g = sel & (a["returnflag"] == ord(key[0])) & (a["linestatus"] == ord(key[1]))
+            cnt = int(g.sum())
+            assert v[7].value == cnt and cnt > 0, key
+            assert v[0].value == int(a["quantity"][g].sum()), key
+            assert v[1].value == int(a["extendedprice"][g].sum()), key
+            assert v[2].value == int(disc_price[g].sum()), key
+            charge = disc_price[g].astype(object) * (100 + a["tax"][g]).astype(object) if cnt < 200_000 else None
+            if charge is not None:
+                assert v[3].value == int(charge.sum()), key
+            else:  # exact in int64: disc_price < 2^31, (100 + tax) < 2^7, 3e7 rows
+                assert v[3].value == int((disc_price[g] * (100 + a["tax"][g])).sum()), key
+            # AVG = sum / count at the input scale, rounded half away from zero (llkv-aggregate/src/lib.rs:1720-1761)
+            q, r = divmod(int(a["quantity"][g].sum()), cnt)
+            assert v[4].value == q + (1 if 2 * r >= cnt else 0), key
+            assert [v[j].value for j in (0, 1, 2, 3, 7)] == halves[key], key
+    finally:
+        dt.destroy()
