@@ -91,6 +91,10 @@ std::string shape_source(const LeanShape& s, int ctas_per_sm) {
   const uint32_t* w = reinterpret_cast<const uint32_t*>(&s);
   size_t n = sizeof(LeanShape) / 4;
   while (n > 1 && w[n - 1] == 0) --n;  // trailing zeros are value-initialised
+  int n_stash = 0;
+  for (uint32_t i = 0; i < s.n_code && i < (uint32_t)kMaxFastInstr; ++i)
+    if (s.code[i].op >= FO_COUNT_STAR && s.code[i].op <= FO_FIRSTNAN) ++n_stash;
+  if (n_stash == 0) n_stash = 1;
   std::ostringstream o;
   o << "#include \"lean_kernel.cuh\"\n"
        "namespace llkv {\n"
@@ -104,7 +108,9 @@ std::string shape_source(const LeanShape& s, int ctas_per_sm) {
        "struct LeanJitCfg {\n"
        "  static constexpr bool kStatic = true;\n"
        "  static __device__ __forceinline__ const LeanShape& shape(const LeanPlan&) { return kJitShape; }\n"
-       "  static __device__ constexpr FInstr code(int pc) { return kJitShape.code[pc]; }\n"
+       "  static __host__ __device__ constexpr FInstr code(int pc) { return kJitShape.code[pc]; }\n"
+       "  static constexpr bool kDefer = kJitShape.n_keys != 0 && kJitShape.direct_global == 0;\n"
+       "  static constexpr int kStash = " << n_stash << ";\n"
        "};\n"
        "}  // namespace llkv\n"
        "extern \"C\" __global__ void __launch_bounds__("

@@ -125,9 +125,22 @@ __device__ __forceinline__ uint32_t hash_key32(u64 K) {
   return (x * 0x85ebca6bu) >> 8;
 }
 
+__host__ __device__ constexpr bool lean_is_aggregate(uint32_t op) { return op >= FO_COUNT_STAR && op <= FO_FIRSTNAN; }
+// index of the aggregate instruction at `pc` among the program's aggregate instructions (specialised builds)
+template <class Cfg>
+__host__ __device__ constexpr int lean_stash_index(int pc) {
+  int k = 0;
+  for (int i = 0; i < pc; ++i)
+    if (lean_is_aggregate(Cfg::code(i).op)) ++k;
+  return k;
+}
+
 // interpreted: the shape comes with the kernel parameter
 struct LeanDynCfg {
   static constexpr bool kStatic = false;
+  static constexpr bool kDefer = false;
+  static constexpr int kStash = 1;
+  static __host__ __device__ constexpr FInstr code(int) { return FInstr{}; }
   static __device__ __forceinline__ const LeanShape& shape(const LeanPlan& p) { return p.s; }
 };
 
@@ -155,6 +168,9 @@ struct LeanTile {
   unsigned negm = 0;  // bit r: selected row without a CTA-local group slot (goes to the global table directly)
   bool has_slow = false;  // warp-uniform: some lane has a row in negm
   uint32_t errbits = 0;
+  // specialised + grouped: operands / row masks of the tile's aggregate instructions, applied by flush()
+  u64 stash_v[Cfg::kStash][R];
+  unsigned stash_m[Cfg::kStash];
 
   __device__ __forceinline__ LeanTile(const LeanPlan& plan, const LeanShape& shape, unsigned char* smem, int tid_, int nc)
       : p(plan), S(shape), tid(tid_), NC(nc), T(shape.tile_rows), my4(smem + shape.smem_acc_off + tid_ * 4),
@@ -300,6 +316,7 @@ struct LeanTile {
   }
 
   // executes one instruction for this thread's R rows; false = the warp is done with the tile
+  template <int PC>
   __device__ __forceinline__ bool step(const FInstr& in) {
     // optional operand pre-load fused into the instruction: acc = literal / column / temporary
     if (in.d == 2) load_col(in.e, in.f, acc);
@@ -364,21 +381,26 @@ struct LeanTile {
           // creator passes iff cb <= snap (which excludes MAX) and cb is not listed; the deletion does not hide the row
           // iff db > snap (which includes MAX = never deleted) or db is listed.  Rows this transaction created / deleted
           // follow rules (1) and (5).
-          unsigned cin = 0, din = 0;  // bit r: created_by / deleted_by is a non-committed transaction
-          for (uint32_t k = 0; k < p.n_noncommitted; ++k) {
-            const u64 id = p.noncommitted[k];
-#pragma unroll
-            for (int r = 0; r < R; ++r) {
-              cin |= (unsigned)(cb[r] == id) << r;
-              din |= (unsigned)(db[r] == id) << r;
-            }
-          }
+          // Fast path per row slot of the warp: rows written by auto-commit and never deleted (created_by = 1,
+          // deleted_by = MAX: all of a bulk-loaded table) are visible to every snapshot >= 1; when all 32 lanes hold
+          // such a row the rule is skipped.
 #pragma unroll
           for (int r = 0; r < R; ++r) {
+            const bool trivial = cb[r] == 1ull && db[r] == ~0ull;
+            if (__all_sync(LLKV_FULL, trivial)) {
+              m |= (unsigned)(snap >= 1ull) << r;
+              continue;
+            }
+            bool c_listed = false, d_listed = false;  // created_by / deleted_by is a non-committed transaction
+            for (uint32_t k = 0; k < p.n_noncommitted; ++k) {
+              const u64 id = p.noncommitted[k];
+              c_listed = c_listed || cb[r] == id;
+              d_listed = d_listed || db[r] == id;
+            }
             const bool own_c = own_enabled && cb[r] == txn;
             const bool own_d = own_enabled && db[r] == txn;
-            const bool c_ok = cb[r] <= snap && !((cin >> r) & 1u);
-            const bool d_ok = db[r] > snap || ((din >> r) & 1u);
+            const bool c_ok = cb[r] <= snap && !c_listed;
+            const bool d_ok = db[r] > snap || d_listed;
             const bool vis = !own_d && (own_c || (c_ok && d_ok));
             m |= (unsigned)vis << r;
           }
@@ -534,7 +556,8 @@ struct LeanTile {
       }
 
       // ------------------------------------------------------------ aggregates: one private accumulator per thread,
-      // CTA-local slot and word.  Ungrouped plans fold the thread's R rows in registers first.
+      // CTA-local slot and word.  Ungrouped plans fold the thread's R rows in registers first.  Grouped plans update
+      // per row (emit): at once when interpreted, deferred to the end of the tile when specialised (see flush()).
       case FO_COUNT_STAR: case FO_COUNT: {
         if (has_slow) slow_rows(in.op, in.a, negm, in.c);
         const unsigned okm = actm & ~negm;
@@ -543,14 +566,11 @@ struct LeanTile {
           const unsigned c = __popc(okm);
           if (lw.width == 4) *reinterpret_cast<uint32_t*>(my4 + lw.off) += c;
           else *reinterpret_cast<u64*>(my8 + lw.off) += c;
-        } else if (lw.width == 4) {
-#pragma unroll
-          for (int r = 0; r < R; ++r)
-            if ((okm >> r) & 1u) *reinterpret_cast<uint32_t*>(my4 + lw.off + soff[r]) += 1u;
         } else {
+          u64 none[R];
 #pragma unroll
-          for (int r = 0; r < R; ++r)
-            if ((okm >> r) & 1u) *reinterpret_cast<u64*>(my8 + lw.off + soff[r]) += 1ull;
+          for (int r = 0; r < R; ++r) none[r] = 0;
+          emit<PC>(in, okm, none);
         }
         return true;
       }
@@ -565,24 +585,10 @@ struct LeanTile {
         }
         if (has_slow) slow_rows(in.op, in.a, setm & negm, in.c);
         setm &= ~negm;
-        const LeanWord lw = S.words[in.b];
-        if (lw.width == 4) {  // launch-relative row index
+        u64 none[R];
 #pragma unroll
-          for (int r = 0; r < R; ++r)
-            if ((setm >> r) & 1u) {
-              uint32_t* a = reinterpret_cast<uint32_t*>(my4 + lw.off + soff[r]);
-              const uint32_t cand = rel0 + (uint32_t)(r * NC), cur = *a;
-              *a = cand < cur ? cand : cur;
-            }
-        } else {
-#pragma unroll
-          for (int r = 0; r < R; ++r)
-            if ((setm >> r) & 1u) {
-              u64* a = reinterpret_cast<u64*>(my8 + lw.off + soff[r]);
-              const u64 cand = row0 + (u64)(r * NC + tid), cur = *a;
-              *a = cand < cur ? cand : cur;
-            }
-        }
+        for (int r = 0; r < R; ++r) none[r] = 0;
+        emit<PC>(in, setm, none);  // also the ungrouped case: soff[] is zero
         return true;
       }
       case FO_SUM: {
@@ -607,14 +613,11 @@ struct LeanTile {
             if ((fastm >> r) & 1u) x += acc[r];
           if (lw.width == 4) *reinterpret_cast<uint32_t*>(my4 + lw.off) += (uint32_t)x;
           else *reinterpret_cast<u64*>(my8 + lw.off) += (u64)x;
-        } else if (lw.width == 4) {
-#pragma unroll
-          for (int r = 0; r < R; ++r)
-            if ((fastm >> r) & 1u) *reinterpret_cast<uint32_t*>(my4 + lw.off + soff[r]) += (uint32_t)acc[r];
         } else {
+          u64 v[R];
 #pragma unroll
-          for (int r = 0; r < R; ++r)
-            if ((fastm >> r) & 1u) *reinterpret_cast<u64*>(my8 + lw.off + soff[r]) += (u64)acc[r];
+          for (int r = 0; r < R; ++r) v[r] = (u64)acc[r];
+          emit<PC>(in, fastm, v);
         }
         return true;
       }
@@ -630,17 +633,14 @@ struct LeanTile {
           double* a = reinterpret_cast<double*>(my8 + lw.off);
           *a += x;
         } else {
+          u64 v[R];
 #pragma unroll
-          for (int r = 0; r < R; ++r)
-            if ((okm >> r) & 1u) {
-              double* a = reinterpret_cast<double*>(my8 + lw.off + soff[r]);
-              *a += lean_f64(acc[r]);
-            }
+          for (int r = 0; r < R; ++r) v[r] = (u64)acc[r];
+          emit<PC>(in, okm, v);
         }
         return true;
       }
       case FO_MIN_I: case FO_MAX_I: case FO_MIN_F: case FO_MAX_F: {
-        const bool is_min = in.op == FO_MIN_I || in.op == FO_MIN_F;
         const bool is_f = in.op == FO_MIN_F || in.op == FO_MAX_F;
         unsigned setm = actm;
         u64 e[R];
@@ -654,18 +654,91 @@ struct LeanTile {
         }
         if (has_slow) slow_rows(in.op, in.a, setm & negm, in.c);
         setm &= ~negm;
-        const LeanWord lw = S.words[in.b];
-#pragma unroll
-        for (int r = 0; r < R; ++r)
-          if ((setm >> r) & 1u) {
-            u64* a = reinterpret_cast<u64*>(my8 + lw.off + soff[r]);
-            const u64 cur = *a;
-            *a = (is_min ? e[r] < cur : e[r] > cur) ? e[r] : cur;
-          }
+        emit<PC>(in, setm, e);  // also the ungrouped case: soff[] is zero
         return true;
       }
-      case FO_END: return false;
+      case FO_END:
+        if constexpr (Cfg::kStatic && PC >= 0) flush();
+        return false;
       default: errbits |= FLAG_BAD_PLAN; return false;
+    }
+  }
+
+  // One row's update of one accumulator word (`in` is the aggregate instruction, `v` its operand for this row).
+  __device__ __forceinline__ void apply_row(const FInstr& in, bool on, u64 v, int r) {
+    if (!on) return;
+    const LeanWord lw = S.words[in.b];
+    switch (in.op) {
+      case FO_COUNT_STAR: case FO_COUNT:
+        if (lw.width == 4) *reinterpret_cast<uint32_t*>(my4 + lw.off + soff[r]) += 1u;
+        else *reinterpret_cast<u64*>(my8 + lw.off + soff[r]) += 1ull;
+        break;
+      case FO_FIRSTROW: case FO_FIRSTVALID: case FO_FIRSTNAN:
+        if (lw.width == 4) {  // launch-relative row index
+          uint32_t* a = reinterpret_cast<uint32_t*>(my4 + lw.off + soff[r]);
+          const uint32_t cand = rel0 + (uint32_t)(r * NC), cur = *a;
+          *a = cand < cur ? cand : cur;
+        } else {
+          u64* a = reinterpret_cast<u64*>(my8 + lw.off + soff[r]);
+          const u64 cand = row0 + (u64)(r * NC + tid), cur = *a;
+          *a = cand < cur ? cand : cur;
+        }
+        break;
+      case FO_SUM:
+        if (lw.width == 4) *reinterpret_cast<uint32_t*>(my4 + lw.off + soff[r]) += (uint32_t)v;
+        else *reinterpret_cast<u64*>(my8 + lw.off + soff[r]) += v;
+        break;
+      case FO_FSUM: {
+        double* a = reinterpret_cast<double*>(my8 + lw.off + soff[r]);
+        *a += lean_f64((i64)v);
+        break;
+      }
+      default: {  // FO_MIN_* / FO_MAX_* on order-preserving encodings
+        const bool is_min = in.op == FO_MIN_I || in.op == FO_MIN_F;
+        u64* a = reinterpret_cast<u64*>(my8 + lw.off + soff[r]);
+        const u64 cur = *a;
+        *a = (is_min ? v < cur : v > cur) ? v : cur;
+        break;
+      }
+    }
+  }
+
+  // Interpreted: the update happens at once, aggregate by aggregate.  Specialised + grouped: operands and row masks are
+  // parked in registers (one entry per aggregate instruction, indexed at compile time) and applied by flush() row by
+  // row: the words of one row are provably distinct addresses, so their loads and stores overlap instead of forming one
+  // read-modify-write chain per aggregate (two rows of a thread may share a slot, which serialises them).
+  template <int PC>
+  __device__ __forceinline__ void emit(const FInstr& in, unsigned mask, const u64 (&v)[R]) {
+    if constexpr (Cfg::kStatic && PC >= 0) {
+      if constexpr (Cfg::kDefer) {
+        constexpr int k = lean_stash_index<Cfg>(PC);
+        stash_m[k] = mask;
+#pragma unroll
+        for (int r = 0; r < R; ++r) stash_v[k][r] = v[r];
+        return;
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < R; ++r) apply_row(in, (mask >> r) & 1u, v[r], r);
+  }
+
+  template <int PC>
+  __device__ __forceinline__ void flush_row(int r) {
+    if constexpr (Cfg::kStatic) {
+      constexpr FInstr in = Cfg::code(PC);
+      if constexpr (lean_is_aggregate(in.op)) {
+        constexpr int k = lean_stash_index<Cfg>(PC);
+        apply_row(in, (stash_m[k] >> r) & 1u, stash_v[k][r], r);
+      }
+      if constexpr (in.op != FO_END && PC + 1 < kMaxFastInstr) flush_row<PC + 1>(r);
+    }
+  }
+  __device__ __forceinline__ void flush() {
+    if constexpr (Cfg::kStatic) {
+      if constexpr (Cfg::kDefer) {
+#pragma unroll
+        for (int r = 0; r < R; ++r) flush_row<0>(r);
+      }
     }
   }
 
@@ -674,7 +747,7 @@ struct LeanTile {
   __device__ __forceinline__ void run_static() {
     if constexpr (Cfg::kStatic) {
       constexpr FInstr in = Cfg::code(PC);
-      if (!step(in)) return;
+      if (!step<PC>(in)) return;
       if constexpr (in.op != FO_END && PC + 1 < kMaxFastInstr) run_static<PC + 1>();
     }
   }
@@ -684,7 +757,7 @@ struct LeanTile {
     FInstr in = S.code[0];
     while (true) {
       const FInstr nxt = S.code[pc + 1];
-      if (!step(in)) break;
+      if (!step<-1>(in)) break;
       in = nxt;
       ++pc;
     }

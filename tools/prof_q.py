@@ -4,7 +4,8 @@ sys.path[:0] = ['rust-llkv_b200', '.']
 from llkv_b200 import gpu, tpch
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 20_000_000
 reps = int(sys.argv[2]) if len(sys.argv) > 2 else 2
-tune = [int(x) for x in sys.argv[3].split(',')] if len(sys.argv) > 3 else None  # block,R,stages,ctas
+tune = [int(x) for x in sys.argv[3].split(',')] if len(sys.argv) > 3 and sys.argv[3] != '-' else None  # block,R,stages,ctas
+hint1 = int(sys.argv[4]) if len(sys.argv) > 4 else 6
 ctx = gpu.Context(0)
 ctx.set_timing(True)
 import os
@@ -14,7 +15,7 @@ if tune:
 t, snap = tpch.lineitem_table(n, seed=6, with_q1=True, with_mvcc=True)
 dt = gpu.DeviceTable.from_host(ctx, t, chunk_rows=1 << 20)
 for name, f, specs, keys, sn, hint in [("q6", tpch.q6_filter(), tpch.q6_aggregates(), (), None, 0),
-                                       ("q1", tpch.q1_filter(), tpch.q1_aggregates(), tpch.Q1_GROUP_BY, snap, 6)]:
+                                       ("q1", tpch.q1_filter(), tpch.q1_aggregates(), tpch.Q1_GROUP_BY, snap, hint1)]:
     prog = gpu.Program(ctx, f)
     dt.set_snapshot(sn)
     agg = gpu.Aggregation(dt, specs, keys, cardinality_hint=hint)
