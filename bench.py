@@ -214,7 +214,7 @@ def run_ours(args):
             nonlocal launches, result
             agg.reset()
             agg.run(prog, snapshot is not None, 0, n)
-            if world > 1:
+            if world > 1 and not os.environ.get("LLKV_BENCH_NO_MERGE"):  # (diagnostic switch: cost of the merge alone)
                 agg.merge()
             result = agg.finalize(64 if group_by else 1)
             if record:

@@ -29,6 +29,8 @@ cudaError_t launch_scan(const Plan* dplan, bool wide, int rows_per_thread, uint3
 cudaError_t launch_lean(const LeanPlan& plan, uint32_t grid, cudaStream_t stream);
 cudaError_t launch_init_table(u64* keys, u64* words, u64 rows, uint32_t n_gwords, const uint8_t* word_class_dev, cudaStream_t stream);
 cudaError_t launch_merge_table(const Plan* dplan, const u64* src_keys, const u64* src_words, u64 src_cap, cudaStream_t stream);
+cudaError_t launch_merge_ungrouped_p2p(u64* state, u64* const* peer_boxes, int n_ranks, int rank, uint32_t n_gwords, u64 epoch,
+                                       const uint8_t* word_class_dev, uint32_t* flags, cudaStream_t stream);
 cudaError_t launch_merge_ungrouped(u64* dst, const u64* all_words, int n_ranks, uint32_t n_gwords, u64 rank_stride, const uint8_t* word_class_dev,
                                    cudaStream_t stream);
 }  // namespace llkv
@@ -245,6 +247,12 @@ struct llkv_gpu_ctx {
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   void* nccl_comm = nullptr;
   int n_ranks = 1, rank = 0;
+  // peer-memory mailboxes for the ungrouped merge (scan_kernel.cu: merge_ungrouped_p2p_kernel): every rank maps every
+  // other rank's mailbox through CUDA IPC at llkv_gpu_comm_init; all ranks use this path or none does
+  u64* mbox = nullptr;            // this rank's mailbox: [n_ranks][2][128] words
+  u64* peer_mbox[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  bool p2p_merge = false;
+  u64 merge_epoch = 0;
 };
 
 struct llkv_gpu_column {
@@ -412,6 +420,7 @@ extern "C" int32_t llkv_gpu_ctx_create(int32_t device_ordinal, int32_t n_streams
   return LLKV_OK;
 }
 
+static void comm_teardown_p2p(llkv_gpu_ctx* ctx);
 extern "C" void llkv_gpu_ctx_destroy(llkv_gpu_ctx* c) {
   if (!c) return;
   cudaSetDevice(c->device);
@@ -419,7 +428,10 @@ extern "C" void llkv_gpu_ctx_destroy(llkv_gpu_ctx* c) {
   std::vector<llkv_gpu_column*> cols;
   for (auto& kv : c->columns) cols.push_back(kv.second);
   for (llkv_gpu_column* col : cols) llkv_gpu_column_destroy(col);
-  if (c->nccl_comm && g_nccl.comm_destroy) g_nccl.comm_destroy(c->nccl_comm);
+  if (c->nccl_comm && g_nccl.comm_destroy) {
+    comm_teardown_p2p(c);
+    g_nccl.comm_destroy(c->nccl_comm);
+  }
   for (cudaStream_t s : c->copy_streams) cudaStreamDestroy(s);
   for (cudaEvent_t e : c->slot_events) cudaEventDestroy(e);
   if (c->stream) cudaStreamDestroy(c->stream);
@@ -1902,6 +1914,7 @@ static int32_t agg_resolve(llkv_gpu_agg* a) {
     }
     a->pending.active = false;
     if (flags & FLAG_BAD_PLAN) return agg_fail(a, LLKV_ERR_INTERNAL, "device interpreter met an unknown instruction");
+    if (flags & FLAG_MERGE_TIMEOUT) return agg_fail(a, LLKV_ERR_IO, "multi-GPU merge: a peer's partial state did not arrive within 10 s");
     if (flags & FLAG_TYPE_ERROR) {
       for (const AggLayout& L : a->cr.aggs)
         if (L.raise_code) return agg_fail(a, L.raise_code, "%s", L.raise_message.c_str());
@@ -2246,6 +2259,69 @@ extern "C" int32_t llkv_gpu_comm_unique_id(uint8_t out_id[LLKV_GPU_UNIQUE_ID_BYT
   return LLKV_OK;
 }
 
+static void comm_teardown_p2p(llkv_gpu_ctx* ctx);
+// Maps every rank's mailbox into every other rank (CUDA IPC over NVLink peer access).  The handles travel through the
+// NCCL communicator that was just created; the peer-memory path is used only when every rank managed to map every peer
+// (agreed with an all-reduce), otherwise the merge stays on NCCL.  LLKV_GPU_NO_P2P_MERGE=1 forces the NCCL path.
+static void comm_setup_p2p(llkv_gpu_ctx* ctx) {
+  const int N = ctx->n_ranks;
+  ctx->p2p_merge = false;
+  const char* off = getenv("LLKV_GPU_NO_P2P_MERGE");
+  if (N < 2 || N > 8 || (off && off[0] && off[0] != '0')) return;
+  const int nccl_u8 = 1 /* ncclUint8 */, nccl_u64 = 5 /* ncclUint64 */, nccl_min = 3 /* ncclMin */;
+  const size_t box_bytes = (size_t)N * 2 * 128 * 8;
+  u64 ok = 1;
+  cudaIpcMemHandle_t mine;
+  memset(&mine, 0, sizeof(mine));
+  if (cudaMalloc((void**)&ctx->mbox, box_bytes) != cudaSuccess || cudaMemset(ctx->mbox, 0, box_bytes) != cudaSuccess ||
+      cudaIpcGetMemHandle(&mine, ctx->mbox) != cudaSuccess)
+    ok = 0;
+  cudaGetLastError();
+  unsigned char* d_handles = nullptr;
+  u64* d_ok = nullptr;
+  std::vector<cudaIpcMemHandle_t> all((size_t)N);
+  if (cudaMalloc((void**)&d_handles, sizeof(mine) * (size_t)(N + 1)) != cudaSuccess || cudaMalloc((void**)&d_ok, 8) != cudaSuccess) {
+    // without scratch memory the collectives below cannot run: every rank would need to know; give up on the whole setup
+    if (d_handles) cudaFree(d_handles);
+    comm_teardown_p2p(ctx);
+    cudaGetLastError();
+    return;
+  }
+  // all-gather the handles (the collective runs on every rank whatever `ok` says, so the ranks stay in step)
+  cudaMemcpyAsync(d_handles + sizeof(mine) * (size_t)N, &mine, sizeof(mine), cudaMemcpyHostToDevice, ctx->stream);
+  int nrc = g_nccl.all_gather(d_handles + sizeof(mine) * (size_t)N, d_handles, sizeof(mine), nccl_u8, ctx->nccl_comm, ctx->stream);
+  cudaMemcpyAsync(all.data(), d_handles, sizeof(mine) * (size_t)N, cudaMemcpyDeviceToHost, ctx->stream);
+  if (cudaStreamSynchronize(ctx->stream) != cudaSuccess || nrc != 0) ok = 0;
+  if (ok) {
+    for (int r = 0; r < N; ++r) {
+      if (r == ctx->rank) {
+        ctx->peer_mbox[r] = ctx->mbox;
+        continue;
+      }
+      void* p = nullptr;
+      if (cudaIpcOpenMemHandle(&p, all[(size_t)r], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+        ok = 0;
+        cudaGetLastError();
+        break;
+      }
+      ctx->peer_mbox[r] = (u64*)p;
+    }
+  }
+  // every rank or none
+  cudaMemcpyAsync(d_ok, &ok, 8, cudaMemcpyHostToDevice, ctx->stream);
+  nrc = g_nccl.all_reduce(d_ok, d_ok, 1, nccl_u64, nccl_min, ctx->nccl_comm, ctx->stream);
+  u64 all_ok = 0;
+  cudaMemcpyAsync(&all_ok, d_ok, 8, cudaMemcpyDeviceToHost, ctx->stream);
+  if (cudaStreamSynchronize(ctx->stream) != cudaSuccess || nrc != 0) all_ok = 0;
+  cudaFree(d_handles);
+  cudaFree(d_ok);
+  cudaGetLastError();
+  if (all_ok) ctx->p2p_merge = true;
+  else comm_teardown_p2p(ctx);
+  if (getenv("LLKV_GPU_VERBOSE"))
+    fprintf(stderr, "[llkv] rank %d/%d: ungrouped merge over %s\n", ctx->rank, N, ctx->p2p_merge ? "NVLink peer mailboxes (CUDA IPC)" : "NCCL all-gather");
+}
+
 extern "C" int32_t llkv_gpu_comm_init(llkv_gpu_ctx* ctx, const uint8_t id[LLKV_GPU_UNIQUE_ID_BYTES], int32_t n_ranks, int32_t rank) {
   if (!ctx || !id) return set_error(LLKV_ERR_INVALID_ARGUMENT, "NULL argument");
   if (n_ranks < 1 || rank < 0 || rank >= n_ranks) return set_error(LLKV_ERR_INVALID_ARGUMENT, "bad rank %d of %d", rank, n_ranks);
@@ -2261,7 +2337,20 @@ extern "C" int32_t llkv_gpu_comm_init(llkv_gpu_ctx* ctx, const uint8_t id[LLKV_G
   NCCL_TRY(g_nccl.comm_init_rank(&ctx->nccl_comm, n_ranks, v, rank));
   ctx->n_ranks = n_ranks;
   ctx->rank = rank;
+  comm_setup_p2p(ctx);
   return LLKV_OK;
+}
+
+static void comm_teardown_p2p(llkv_gpu_ctx* ctx) {
+  for (int r = 0; r < 8; ++r) {
+    if (ctx->peer_mbox[r] && r != ctx->rank) cudaIpcCloseMemHandle(ctx->peer_mbox[r]);
+    ctx->peer_mbox[r] = nullptr;
+  }
+  if (ctx->mbox) cudaFree(ctx->mbox);
+  ctx->mbox = nullptr;
+  ctx->p2p_merge = false;
+  ctx->merge_epoch = 0;
+  cudaGetLastError();
 }
 
 extern "C" int32_t llkv_gpu_comm_destroy(llkv_gpu_ctx* ctx) {
@@ -2269,6 +2358,7 @@ extern "C" int32_t llkv_gpu_comm_destroy(llkv_gpu_ctx* ctx) {
   if (ctx->nccl_comm && g_nccl.comm_destroy) {
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
+    comm_teardown_p2p(ctx);
     g_nccl.comm_destroy(ctx->nccl_comm);
   }
   ctx->nccl_comm = nullptr;
@@ -2287,9 +2377,18 @@ extern "C" int32_t llkv_gpu_agg_merge(llkv_gpu_agg* a) {
   int32_t rc;
   const int N = ctx->n_ranks;
   const int nccl_u64 = 5 /* ncclUint64 */, nccl_max = 2 /* ncclMax */;
-  // Ungrouped state whose run cannot ask for a rerun (no 64-bit narrowing to fail, no table to fill): the merge is
-  // queued behind the scan on the same stream without waiting for it: all-gather of the one state row, one kernel.
-  if (a->frozen && a->cr.plan.n_keys == 0 && !a->cr.can_narrow_fail && ctx->nccl_comm && N > 1) {
+  // Ungrouped state: the merge is queued behind the scan on the same stream without waiting for it (there is no table
+  // to fill): peer-memory mailboxes over NVLink, or an all-gather of the one state row and one kernel.
+  // (Every rank must take the same branch here: the condition only uses properties of the plan that do not depend on
+  // the rank's data.  Whether the 64-bit run of THIS rank may still ask for a rerun does depend on its statistics, so
+  // that is settled locally first.)
+  if (a->frozen && a->cr.plan.n_keys == 0 && ctx->nccl_comm && N > 1) {
+    if (a->cr.can_narrow_fail && (rc = agg_resolve(a))) return rc;
+    if (ctx->p2p_merge && a->n_gwords < 127) {  // NVLink peer stores + flags, no collective library on the path
+      CUDA_TRY(launch_merge_ungrouped_p2p(a->gwords, ctx->peer_mbox, N, ctx->rank, a->n_gwords, ++ctx->merge_epoch, a->d_gclass, a->d_flags,
+                                          ctx->stream));
+      return LLKV_OK;
+    }
     const size_t word_elems = (size_t)(3 * a->n_gwords);
     if (a->mg_word_elems < word_elems * (size_t)N) {
       if (a->mg_words) CUDA_TRY(cudaFree(a->mg_words));

@@ -280,7 +280,8 @@ enum : uint32_t {
   FLAG_EXACT_OVERFLOW = 1u << 3,   // exact-mode decimal op overflowed / exceeded 38 digits
   FLAG_TABLE_FULL = 1u << 4,       // global group table is full
   FLAG_BAD_PLAN = 1u << 5,
-  FLAG_TYPE_ERROR = 1u << 6        // OP_RAISE: aggregate argument of a type the accumulator rejects, met on a selected row
+  FLAG_TYPE_ERROR = 1u << 6,       // OP_RAISE: aggregate argument of a type the accumulator rejects, met on a selected row
+  FLAG_MERGE_TIMEOUT = 1u << 7     // multi-GPU merge: a peer's partial state never arrived
 };
 
 }  // namespace llkv

@@ -985,7 +985,100 @@ __global__ void merge_ungrouped_kernel(u64* dst, const u64* all_words, int n_ran
   dst[w] = c == WC_FSUM ? (u64)__double_as_longlong(facc) : acc;
 }
 
+// Ungrouped multi-GPU merge over NVLink peer memory, no collective library on the path: every rank stores its state row
+// into a mailbox slot on every peer (plain stores into peer-mapped memory, cudaIpc), publishes it with a release flag, waits
+// for the flags of all ranks in its own mailbox and folds the rows in rank order (bit-identical states on all ranks, f64
+// sums included).  One small kernel per rank and merge; latency = one NVLink store + flag round.
+//   mailbox layout per rank: [source rank][epoch parity][kMergeMboxWords]; word kMergeMboxWords-1 is the flag (= epoch).
+// Two parities: a rank can be one merge ahead of a peer, never two (merge e+1 needs the peer's flag of e+1, which the
+// peer's stream writes after its merge e).  A peer that never arrives ends the wait after ~10 s with FLAG_MERGE_TIMEOUT.
+constexpr uint32_t kMergeMboxWords = 128;
+struct PeerMailboxes {
+  u64* box[8];
+};
+__device__ __forceinline__ u64 ld_acquire_sys(const u64* p) {
+  u64 v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_sys(u64* p, u64 v) { asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory"); }
+__device__ __forceinline__ u64 global_timer_ns() {
+  u64 t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+__global__ void merge_ungrouped_p2p_kernel(u64* state, PeerMailboxes peers, int n_ranks, int rank, uint32_t n_gwords, u64 epoch,
+                                           const uint8_t* word_class_dev, uint32_t* flags) {
+  const uint32_t w = threadIdx.x;
+  const uint32_t slot = (uint32_t)(rank * 2 + (int)(epoch & 1)) * kMergeMboxWords;
+  if (w < n_gwords) {
+    const u64 v = state[w];
+    for (int r = 0; r < n_ranks; ++r) peers.box[r][slot + w] = v;
+  }
+  __threadfence_system();
+  __syncthreads();
+  if (w < (uint32_t)n_ranks) st_release_sys(&peers.box[w][slot + kMergeMboxWords - 1], epoch);
+  __shared__ int timed_out;
+  if (w == 0) timed_out = 0;
+  __syncthreads();
+  if (w < (uint32_t)n_ranks) {
+    const u64* flag = &peers.box[rank][(w * 2 + (uint32_t)(epoch & 1)) * kMergeMboxWords + kMergeMboxWords - 1];
+    const u64 t0 = global_timer_ns();
+    while (ld_acquire_sys(flag) != epoch) {
+      if (global_timer_ns() - t0 > 10000000000ull) {
+        timed_out = 1;
+        break;
+      }
+      __nanosleep(200);
+    }
+  }
+  __syncthreads();
+  if (timed_out) {
+    if (w == 0) atomicOr(flags, FLAG_MERGE_TIMEOUT);
+    return;
+  }
+  __threadfence_system();
+  if (w >= n_gwords) return;
+  const uint8_t c = word_class_dev[w];
+  if (c == WC_PAIR_LO_MIN || c == WC_PAIR_LO_MAX) return;  // written with its high word
+  const u64* mine = peers.box[rank];
+  const uint32_t par = (uint32_t)(epoch & 1);
+  if (c == WC_MIN128 || c == WC_MAX128) {
+    const bool is_max = c == WC_MAX128;
+    u64 bh = is_max ? 0ull : ~0ull, bl = bh;
+    for (int r = 0; r < n_ranks; ++r) {
+      const u64* row = mine + ((uint32_t)r * 2 + par) * kMergeMboxWords;
+      const u64 h = row[w], l = row[w + 1];
+      const bool better = is_max ? (h > bh || (h == bh && l > bl)) : (h < bh || (h == bh && l < bl));
+      if (better) { bh = h; bl = l; }
+    }
+    state[w] = bh;
+    state[w + 1] = bl;
+    return;
+  }
+  u64 acc = c == WC_MIN ? ~0ull : 0ull;
+  double facc = 0.0;
+  for (int r = 0; r < n_ranks; ++r) {
+    const u64 v = mine[((uint32_t)r * 2 + par) * kMergeMboxWords + w];
+    switch (c) {
+      case WC_SUM: acc += v; break;
+      case WC_FSUM: facc += __longlong_as_double((i64)v); break;
+      case WC_MIN: acc = v < acc ? v : acc; break;
+      case WC_MAX: acc = v > acc ? v : acc; break;
+      default: break;
+    }
+  }
+  state[w] = c == WC_FSUM ? (u64)__double_as_longlong(facc) : acc;
+}
+
 // ------------------------------------------------------------------ host-callable launchers
+cudaError_t launch_merge_ungrouped_p2p(u64* state, u64* const* peer_boxes, int n_ranks, int rank, uint32_t n_gwords, u64 epoch,
+                                       const uint8_t* word_class_dev, uint32_t* flags, cudaStream_t stream) {
+  PeerMailboxes pm;
+  for (int r = 0; r < 8; ++r) pm.box[r] = r < n_ranks ? peer_boxes[r] : nullptr;
+  merge_ungrouped_p2p_kernel<<<1, kMergeMboxWords, 0, stream>>>(state, pm, n_ranks, rank, n_gwords, epoch, word_class_dev, flags);
+  return cudaGetLastError();
+}
 cudaError_t launch_merge_ungrouped(u64* dst, const u64* all_words, int n_ranks, uint32_t n_gwords, u64 rank_stride,
                                    const uint8_t* word_class_dev, cudaStream_t stream) {
   merge_ungrouped_kernel<<<(n_gwords + 127) / 128, 128, 0, stream>>>(dst, all_words, n_ranks, n_gwords, rank_stride, word_class_dev);
