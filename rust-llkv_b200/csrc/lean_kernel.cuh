@@ -293,7 +293,7 @@ struct LeanTile {
   // bookkeeping is 32-bit; the absolute row is only formed where an aggregate needs it)
   __device__ __forceinline__ void begin_tile(const unsigned char* stage, uint32_t rel_row0, u64 base_row, uint32_t begin_rel, uint32_t end_rel) {
     sb = stage;
-    row0 = base_row + rel_row0;
+    row0 = p.row_origin + base_row + rel_row0;  // a row id: only first-row words and the per-row global path use it
     rel0 = rel_row0 + (uint32_t)tid;  // launch-relative index of this thread's row r = 0
     negm = 0;
     has_slow = false;
@@ -913,7 +913,7 @@ __device__ __forceinline__ void lean_body(const LeanPlan& p) {
           u64 v;
           if (lw.width == 4) {
             const uint32_t x = reinterpret_cast<const uint32_t*>(blk)[t];
-            v = x == 0xffffffffu ? ~0ull : (lw.rowrel ? base_row + x : (u64)x);
+            v = x == 0xffffffffu ? ~0ull : (lw.rowrel ? p.row_origin + base_row + x : (u64)x);
           } else v = reinterpret_cast<const u64*>(blk)[t];
           s = v < s ? v : s;
         }

@@ -1802,6 +1802,18 @@ static int32_t agg_launch(llkv_gpu_agg* a, const llkv_gpu_program* prog, int app
       use_jit = a->lean_jit_runs >= 2;
     }
   }
+  // first-row words hold row ids (position + the row id of position 0), so shards of one table uploaded with their own
+  // row_id_base merge into the table's first-appearance order
+  uint64_t row_origin = 0;
+  for (size_t i = 0; i < handles.size(); ++i) {
+    if (!handles[i]->has_origin) continue;
+    if (i && handles[0]->has_origin && handles[i]->row_id_origin != handles[0]->row_id_origin)
+      return set_error(LLKV_ERR_INVALID_ARGUMENT, "columns of table %llu start at different row ids (%llu vs %llu)", (unsigned long long)a->table_id,
+                       (unsigned long long)handles[i]->row_id_origin, (unsigned long long)handles[0]->row_id_origin);
+    row_origin = handles[i]->row_id_origin;
+  }
+  p.row_origin = row_origin;
+  lean.row_origin = row_origin;
   p.gkeys = a->gkeys;
   p.gwords = a->gwords;
   p.gcap = a->gcap;

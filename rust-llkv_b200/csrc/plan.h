@@ -225,6 +225,8 @@ struct Plan {
   uint32_t* flags;                // device status word (FLAG_*)
   unsigned long long* out_bitmap; // bitmap_mode: bit i = row_begin + i  (32-bit words written)
   unsigned long long* out_count;  // bitmap_mode: number of selected rows
+  unsigned long long row_origin;  // row id of the columns' position 0: first-row words hold row ids, so shards of one table merge into
+                                  // the table's first-appearance order
 };
 
 // ---- the lean kernel's view of a plan (lean_kernel.cuh): passed by value as a __grid_constant__ kernel parameter, so the
@@ -270,6 +272,7 @@ struct LeanPlan {
   unsigned long long* gwords;
   unsigned long long gcap;
   uint32_t* flags;
+  unsigned long long row_origin;  // row id of position 0 (see Plan::row_origin)
   uint32_t n_noncommitted, _pad;
 };
 

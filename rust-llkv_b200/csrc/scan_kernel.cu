@@ -711,7 +711,7 @@ __global__ void __launch_bounds__(512) scan_kernel(const Plan* __restrict__ gpla
 #pragma unroll
           for (int r = 0; r < R; ++r) {
             if (!act[r]) continue;
-            const u64 row = row0 + (u64)r * NT + tid;
+            const u64 row = p.row_origin + row0 + (u64)r * NT + tid;
             if (slot[r] >= 0) {
               u64* a = &acc[((uint32_t)slot[r] * NFW + in.b) * NT + tid];
               if (row < *a) *a = row;
@@ -727,7 +727,7 @@ __global__ void __launch_bounds__(512) scan_kernel(const Plan* __restrict__ gpla
               const double d = as_f64(t0[r]);
               if (d == d) continue;
             }
-            const u64 row = row0 + (u64)r * NT + tid;
+            const u64 row = p.row_origin + row0 + (u64)r * NT + tid;
             if (slot[r] >= 0) {
               u64* a = &acc[((uint32_t)slot[r] * NFW + in.b) * NT + tid];
               if (row < *a) *a = row;

@@ -39,11 +39,11 @@ def main():
     n = 400_000
     full, snap = tpch.lineitem_table(n, seed=6, with_q1=True, with_mvcc=True)
     lo, hi = tpch.shard_range(n, world, rank, align=4096)
-    dt = gpu.DeviceTable.from_host(ctx, shard_table(full, lo, hi))
+    dt = from_host_at(ctx, shard_table(full, lo, hi), lo)  # the shard keeps its rows' ids: first-appearance order is global
     dt.set_snapshot(snap)
     hc = tpch.highcard_table(300_000, 40_000, seed=4)
     hlo, hhi = tpch.shard_range(300_000, world, rank, align=4096)
-    hdt = gpu.DeviceTable.from_host(ctx, shard_table(hc, hlo, hhi).__class__(2) if False else _retable(shard_table(hc, hlo, hhi), 2))
+    hdt = from_host_at(ctx, _retable(shard_table(hc, hlo, hhi), 2), hlo)
     cases = [
         (dt, full, tpch.q6_filter(), tpch.q6_aggregates(), (), snap, 0, True),
         (dt, full, tpch.q1_filter(), tpch.q1_aggregates(), tpch.Q1_GROUP_BY, snap, 6, True),
@@ -65,6 +65,24 @@ def main():
         print(f"multi-GPU merge ok on {world} ranks: Q6, Q1 and a 40k-group hash aggregate match the oracle", flush=True)
     ctx.comm_destroy()
     dist.destroy_process_group()
+
+
+def from_host_at(ctx, t: HostTable, row_id_base: int):
+    """DeviceTable.from_host with the shard's row ids starting at row_id_base."""
+    dt = gpu.DeviceTable(ctx, t.table_id)
+    for col in t.columns.values():
+        dc = gpu.DeviceColumn(ctx, gpu.logical_field_id(t.table_id, col.field_id), col)
+        dc.reserve(col.n_rows)
+        dc.append(col, row_id_base=row_id_base)
+        dt.columns[col.field_id] = dc
+        dt.n_rows = col.n_rows
+    if t.created_by is not None:
+        dt.created_by = gpu.DeviceColumn(ctx, gpu.logical_field_id(t.table_id, 0xFFFFFFFF, gpu.NS_TXN_CREATED_BY), t.created_by)
+        dt.created_by.append(t.created_by, row_id_base=row_id_base)
+        dt.deleted_by = gpu.DeviceColumn(ctx, gpu.logical_field_id(t.table_id, 0xFFFFFFFE, gpu.NS_TXN_DELETED_BY), t.deleted_by)
+        dt.deleted_by.append(t.deleted_by, row_id_base=row_id_base)
+    dt.seal()
+    return dt
 
 
 def _retable(t: HostTable, table_id: int) -> HostTable:
