@@ -25,7 +25,7 @@ __device__ constexpr LeanShape kJitShape = {
 0u,0u,0u,0u,0u,0u,0u,0u,0u,0u,0u,0u,0u,0u,0u,0u,0u,0u,0u,0u,0u,0u,0u,0u,0u,0u,0u,0u,0u,0u,0u,0u,
 0u,0u,0u,0u,0u,0u,0u,0u,0u,0u,0u,0u,0u,0u,0u,0u,0u,0u,0u,0u,0u,0u,0u,0u,0u,0u,0u,0u,0u,0u,0u,0u,
 0u,0u,0u,0u,0u,0u,0u,0u,0u,0u,0u,0u,0u,0u,0u,0u,0u,0u,0u,0u,0u,0u,0u,0u,0u,0u,0u,0u,0u,0u,0u,0u,
-4u,0u,8u,2048u,8u,6144u,1u,10240u,1u,10752u,8u,11264u,8u,15360u,8u,19456u,8u,23552u,0u,0u,0u,0u,0u,0u,0u,0u,0u,0u,0u,0u,0u,0u,
+4u,0u,8u,1024u,8u,3072u,1u,5120u,1u,5376u,8u,5632u,8u,7680u,8u,9728u,8u,11776u,0u,0u,0u,0u,0u,0u,0u,0u,0u,0u,0u,0u,0u,0u,
 0u,0u,0u,0u,0u,0u,0u,0u,0u,0u,0u,0u,0u,0u,0u,0u,0u,4u,0u,0u,0u,4u,4u,1u,512u,1u,2u,4u,0u,1024u,2u,2u,
 8u,0u,1536u,6u,2u,8u,0u,2560u,10u,2u,8u,0u,3584u,14u,2u,4u,0u,4608u,18u,0u,0u,0u,0u,0u,0u,0u,0u,0u,0u,0u,0u,0u,
 0u,0u,0u,0u,0u,0u,0u,0u,0u,0u,0u,0u,0u,0u,0u,0u,0u,0u,0u,0u,0u,0u,0u,0u,0u,0u,0u,0u,0u,0u,0u,0u,
@@ -35,13 +35,15 @@ __device__ constexpr LeanShape kJitShape = {
 0u,0u,0u,0u,0u,0u,0u,0u,0u,0u,0u,0u,0u,0u,0u,0u,0u,0u,0u,0u,0u,0u,0u,0u,0u,0u,0u,0u,0u,0u,0u,0u,
 0u,0u,0u,0u,0u,0u,0u,0u,0u,0u,0u,0u,0u,0u,0u,0u,0u,0u,0u,0u,0u,0u,0u,0u,0u,0u,0u,0u,0u,0u,0u,0u,
 11u,11u,0u,0u,0u,0u,0u,0u,1u,1u,0u,0u,0u,0u,0u,0u,1u,1u,0u,0u,0u,0u,0u,0u,3u,4u,0u,0u,0u,0u,0u,0u,
-4u,4u,0u,0u,0u,0u,0u,0u,17u,9u,7u,22u,2u,0u,128u,4u,8u,5120u,512u,2u,27648u,27648u,0u,128u,55424u,96384u,100480u,100608u};
+4u,4u,0u,0u,0u,0u,0u,0u,17u,9u,7u,22u,2u,0u,0u,128u,2u,8u,5120u,256u,2u,13824u,13824u,0u,128u,27776u,68736u,70784u,70912u};
 struct LeanJitCfg {
   static constexpr bool kStatic = true;
   static __device__ __forceinline__ const LeanShape& shape(const LeanPlan&) { return kJitShape; }
-  static __device__ constexpr FInstr code(int pc) { return kJitShape.code[pc]; }
+  static __host__ __device__ constexpr FInstr code(int pc) { return kJitShape.code[pc]; }
+  static constexpr bool kDefer = kJitShape.n_keys != 0 && kJitShape.direct_global == 0;
+  static constexpr int kStash = 7;
 };
 }  // namespace llkv
-extern "C" __global__ void __launch_bounds__(160, 2) llkv_lean_jit(const __grid_constant__ llkv::LeanPlan p) {
-  llkv::lean_body<4, llkv::LeanJitCfg>(p);
+extern "C" __global__ void __launch_bounds__(160, 3) llkv_lean_jit(const __grid_constant__ llkv::LeanPlan p) {
+  llkv::lean_body<2, llkv::LeanJitCfg>(p);
 }

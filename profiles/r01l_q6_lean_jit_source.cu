@@ -35,13 +35,15 @@ __device__ constexpr LeanShape kJitShape = {
 0u,0u,0u,0u,0u,0u,0u,0u,0u,0u,0u,0u,0u,0u,0u,0u,0u,0u,0u,0u,0u,0u,0u,0u,0u,0u,0u,0u,0u,0u,0u,0u,
 0u,0u,0u,0u,0u,0u,0u,0u,0u,0u,0u,0u,0u,0u,0u,0u,0u,0u,0u,0u,0u,0u,0u,0u,0u,0u,0u,0u,0u,0u,0u,0u,
 0u,0u,0u,0u,0u,0u,0u,0u,0u,0u,0u,0u,0u,0u,0u,0u,0u,0u,0u,0u,0u,0u,0u,0u,0u,0u,0u,0u,0u,0u,0u,0u,
-0u,0u,0u,0u,0u,0u,0u,0u,10u,4u,3u,6u,0u,0u,128u,8u,1u,2048u,1024u,3u,28672u,28672u,0u,128u,86144u,88192u,88192u,88320u};
+0u,0u,0u,0u,0u,0u,0u,0u,10u,4u,3u,6u,0u,0u,0u,128u,8u,1u,2048u,1024u,2u,28672u,28672u,0u,128u,57472u,59520u,59520u,59648u};
 struct LeanJitCfg {
   static constexpr bool kStatic = true;
   static __device__ __forceinline__ const LeanShape& shape(const LeanPlan&) { return kJitShape; }
-  static __device__ constexpr FInstr code(int pc) { return kJitShape.code[pc]; }
+  static __host__ __device__ constexpr FInstr code(int pc) { return kJitShape.code[pc]; }
+  static constexpr bool kDefer = kJitShape.n_keys != 0 && kJitShape.direct_global == 0;
+  static constexpr int kStash = 3;
 };
 }  // namespace llkv
-extern "C" __global__ void __launch_bounds__(160, 2) llkv_lean_jit(const __grid_constant__ llkv::LeanPlan p) {
+extern "C" __global__ void __launch_bounds__(160, 3) llkv_lean_jit(const __grid_constant__ llkv::LeanPlan p) {
   llkv::lean_body<8, llkv::LeanJitCfg>(p);
 }
