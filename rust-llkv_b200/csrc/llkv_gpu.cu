@@ -341,6 +341,10 @@ struct llkv_gpu_agg {
   u64* mg_words = nullptr;
   size_t mg_key_elems = 0, mg_word_elems = 0;
   u64* mg_cap = nullptr;
+  u64* mg_stats = nullptr;  // scratch of agree_key_stats
+  size_t mg_stats_elems = 0;
+  std::vector<u64> agreed_stats;  // what the ranks agreed on in the current run (reused by this rank's reruns)
+  bool in_rerun = false;
   // the lean plan of the previous run, reusable while request_signature() does not change
   LeanPlan lean;
   uint64_t lean_sig = 0;
@@ -1600,6 +1604,7 @@ extern "C" void llkv_gpu_agg_destroy(llkv_gpu_agg* a) {
   if (a->mg_keys) cudaFree(a->mg_keys);
   if (a->mg_words) cudaFree(a->mg_words);
   if (a->mg_cap) cudaFree(a->mg_cap);
+  if (a->mg_stats) cudaFree(a->mg_stats);
   if (a->d_flags) cudaFree(a->d_flags);
   if (a->d_plan) cudaFree(a->d_plan);
   if (a->h_plan) cudaFreeHost(a->h_plan);
@@ -1738,6 +1743,58 @@ static uint64_t request_signature(const llkv_gpu_ctx* ctx, const CompileRequest&
   return h ? h : 1;
 }
 
+static int32_t agree_key_stats(llkv_gpu_ctx* ctx, llkv_gpu_agg* a, CompileRequest& req) {
+  const size_t nk = a->keys.size();
+  std::vector<u64> v(nk * 4);
+  std::vector<int> col_of(nk, -1);
+  const u64 sign = 0x8000000000000000ull;
+  for (size_t k = 0; k < nk; ++k) {
+    for (size_t i = 0; i < req.cols.size(); ++i)
+      if (req.cols[i].field_id == a->keys[k]) col_of[k] = (int)i;
+    if (col_of[k] < 0) return set_error(LLKV_ERR_NOT_FOUND, "unknown GROUP BY field %llu", (unsigned long long)a->keys[k]);
+    const ColumnMeta& c = req.cols[(size_t)col_of[k]];
+    const bool is_signed = c.type == LLKV_PT_INT8 || c.type == LLKV_PT_INT16 || c.type == LLKV_PT_INT32 || c.type == LLKV_PT_INT64 ||
+                           c.type == LLKV_PT_DATE32 || c.type == LLKV_PT_DATE64;
+    const u64 flip = is_signed ? sign : 0;
+    // all four lanes reduce with MIN: maxima and lengths travel complemented
+    v[4 * k + 0] = c.has_minmax ? (c.min_bits ^ flip) : ~0ull;
+    v[4 * k + 1] = c.has_minmax ? ~(c.max_bits ^ flip) : ~0ull;
+    v[4 * k + 2] = ~(u64)c.max_strlen;
+    v[4 * k + 3] = (c.has_minmax || c.n_rows == 0) ? 1 : 0;  // an empty shard does not veto the statistics of the others
+  }
+  if (a->in_rerun && a->agreed_stats.size() == v.size()) {
+    // a rerun (wider interpreter, larger table) is this rank's own business: no collective, the agreed values again
+    v = a->agreed_stats;
+  } else {
+  if (a->mg_stats_elems < v.size()) {
+    if (a->mg_stats) CUDA_TRY(cudaFree(a->mg_stats));
+    CUDA_TRY(cudaMalloc((void**)&a->mg_stats, v.size() * 8));
+    a->mg_stats_elems = v.size();
+  }
+  CUDA_TRY(cudaMemcpyAsync(a->mg_stats, v.data(), v.size() * 8, cudaMemcpyHostToDevice, ctx->stream));
+  NCCL_TRY(g_nccl.all_reduce(a->mg_stats, a->mg_stats, v.size(), 5 /* ncclUint64 */, 3 /* ncclMin */, ctx->nccl_comm, ctx->stream));
+  CUDA_TRY(cudaMemcpyAsync(v.data(), a->mg_stats, v.size() * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+  a->agreed_stats = v;
+  }
+  for (size_t k = 0; k < nk; ++k) {
+    ColumnMeta& c = req.cols[(size_t)col_of[k]];
+    const bool is_signed = c.type == LLKV_PT_INT8 || c.type == LLKV_PT_INT16 || c.type == LLKV_PT_INT32 || c.type == LLKV_PT_INT64 ||
+                           c.type == LLKV_PT_DATE32 || c.type == LLKV_PT_DATE64;
+    const u64 flip = is_signed ? sign : 0;
+    const bool all_have = v[4 * k + 3] != 0 && v[4 * k + 0] != ~0ull;
+    if (all_have) {
+      c.has_minmax = true;
+      c.min_bits = v[4 * k + 0] ^ flip;
+      c.max_bits = (~v[4 * k + 1]) ^ flip;
+    } else {
+      c.has_minmax = false;
+    }
+    c.max_strlen = (uint8_t)(~v[4 * k + 2]);
+  }
+  return LLKV_OK;
+}
+
 static int32_t agg_launch(llkv_gpu_agg* a, const llkv_gpu_program* prog, int apply_mvcc, uint64_t row_begin, uint64_t row_end,
                           bool force_wide) {
   llkv_gpu_ctx* ctx = a->ctx;
@@ -1747,6 +1804,10 @@ static int32_t agg_launch(llkv_gpu_agg* a, const llkv_gpu_program* prog, int app
   int32_t rc = build_request(ctx, a->table_id, prog, apply_mvcc, req, handles, &table_rows);
   if (rc) return rc;
   if (row_end > table_rows) return set_error(LLKV_ERR_INVALID_ARGUMENT, "row_end %llu beyond the table's %llu rows", (unsigned long long)row_end, (unsigned long long)table_rows);
+  // Multi-GPU GROUP BY: the packed key layout (bits, minimum, string length per key) comes from column statistics, and
+  // partial tables can only be merged key by key if every rank packs alike.  The ranks agree on the statistics of the
+  // key columns (min of minima, max of maxima / string lengths) with one small all-reduce before compiling.
+  if (ctx->nccl_comm && ctx->n_ranks > 1 && !a->keys.empty() && (rc = agree_key_stats(ctx, a, req))) return rc;
   Plan& p = a->cr.plan;
   Geometry g;
   LeanPlan& lean = a->lean;
@@ -1916,8 +1977,10 @@ static int32_t agg_resolve(llkv_gpu_agg* a) {
       if (rc) return rc;
       if (table_full && (rc = agg_grow_table(a))) return rc;
       if (narrow_fail) a->pending.wide = true;
+      a->in_rerun = true;
       rc = agg_launch(a, a->pending.has_prog ? &a->pending.prog : nullptr, a->pending.apply_mvcc, a->pending.row_begin,
                       a->pending.row_end, a->pending.wide);
+      a->in_rerun = false;
       if (rc) {
         a->pending.active = false;
         return rc;
