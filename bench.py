@@ -243,7 +243,7 @@ def run_ours(args):
     q6 = bench_query(tpch.q6_filter(), tpch.q6_aggregates())
     q1 = None
     if with_q1:
-        q1 = bench_query(tpch.q1_filter(), tpch.q1_aggregates(), tpch.Q1_GROUP_BY, snap, hint=6)
+        q1 = bench_query(tpch.q1_filter(), tpch.q1_aggregates(), tpch.Q1_GROUP_BY, snap, hint=4)  # BASELINE.json: "4-group GROUP BY"
 
     # ---- end to end: host (pinned) buffers -> chunk appends -> fused scan -> result on the host, every step
     e2e_cols = [tpch.L_QUANTITY, tpch.L_EXTENDEDPRICE, tpch.L_DISCOUNT, tpch.L_SHIPDATE]

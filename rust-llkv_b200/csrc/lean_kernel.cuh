@@ -439,19 +439,35 @@ struct LeanTile {
           }
           return true;
         }
-        // Probe without branches: the key's home pair of slots (two adjacent entries, one 16-byte read).  Probe order is
-        // home slot, its pair neighbour, then the following pairs, so after the first tiles a key of a low-cardinality
-        // GROUP BY is found here even when two keys share a home slot.
         unsigned miss = 0;
+        if (FG == 4) {
+          // Four slots (GROUP BY of at most four expected groups, TPC-H Q1): fully associative, no hashing.  The four
+          // keys are two broadcast 16-byte reads; the slot is the index of the matching key.  Half the accumulator
+          // footprint of an eight-slot table, which is what bounds the resident warps of a grouped plan.
+          const ulonglong2 k01 = *reinterpret_cast<const ulonglong2*>(&tbl[0]);
+          const ulonglong2 k23 = *reinterpret_cast<const ulonglong2*>(&tbl[2]);
 #pragma unroll
-        for (int r = 0; r < R; ++r) {
-          const uint32_t h = hash_key32(keys[r]) & (FG - 1);
-          const ulonglong2 pair = *reinterpret_cast<const ulonglong2*>(&tbl[h & ~1u]);
-          const u64 k_home = (h & 1u) ? pair.y : pair.x, k_other = (h & 1u) ? pair.x : pair.y;
-          const bool hit_home = k_home == keys[r], hit_other = k_other == keys[r];
-          const uint32_t sl = hit_home ? h : (h ^ 1u);
-          soff[r] = sl * S.slot_stride;
-          if (!((hit_home || hit_other) && keys[r] != kEmptyKey) && ((actm >> r) & 1u)) miss |= 1u << r;
+          for (int r = 0; r < R; ++r) {
+            const u64 K = keys[r];
+            const bool h0 = K == k01.x, h1 = K == k01.y, h2 = K == k23.x, h3 = K == k23.y;
+            const uint32_t sl = h0 ? 0u : h1 ? 1u : h2 ? 2u : 3u;
+            soff[r] = sl * S.slot_stride;
+            if (!((h0 || h1 || h2 || h3) && K != kEmptyKey) && ((actm >> r) & 1u)) miss |= 1u << r;
+          }
+        } else {
+          // Probe without branches: the key's home pair of slots (two adjacent entries, one 16-byte read).  Probe order
+          // is home slot, its pair neighbour, then the following pairs, so after the first tiles a key of a
+          // low-cardinality GROUP BY is found here even when two keys share a home slot.
+#pragma unroll
+          for (int r = 0; r < R; ++r) {
+            const uint32_t h = hash_key32(keys[r]) & (FG - 1);
+            const ulonglong2 pair = *reinterpret_cast<const ulonglong2*>(&tbl[h & ~1u]);
+            const u64 k_home = (h & 1u) ? pair.y : pair.x, k_other = (h & 1u) ? pair.x : pair.y;
+            const bool hit_home = k_home == keys[r], hit_other = k_other == keys[r];
+            const uint32_t sl = hit_home ? h : (h ^ 1u);
+            soff[r] = sl * S.slot_stride;
+            if (!((hit_home || hit_other) && keys[r] != kEmptyKey) && ((actm >> r) & 1u)) miss |= 1u << r;
+          }
         }
         if (__any_sync(LLKV_FULL, miss != 0)) {  // new key, longer collision chain, table full or the reserved key value
 #pragma unroll
@@ -460,7 +476,7 @@ struct LeanTile {
               const u64 K = keys[r];
               int sl = -1;
               if (K != kEmptyKey) {
-                const uint32_t h0 = hash_key32(K) & (FG - 1);
+                const uint32_t h0 = FG == 4 ? 0u : (hash_key32(K) & (FG - 1));  // four slots: filled in index order
 #pragma unroll 1
                 for (uint32_t i = 0; i < FG; ++i) {
                   const uint32_t h = ((((h0 >> 1) + (i >> 1)) << 1) | ((h0 ^ i) & 1u)) & (FG - 1);

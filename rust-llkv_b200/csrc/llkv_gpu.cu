@@ -1264,7 +1264,7 @@ static int32_t lean_geometry(const LeanTune& tn, const Plan& p, uint64_t row_beg
   };
   // Candidates: rows per thread x CTAs per SM, each with the deepest pipeline (2..4 stages) that fits.  The kernel is
   // latency-bound when its per-thread state is fat (Q1) and HBM-bound when it is thin (Q6), so the choice maximises
-  // resident consumer warps (up to 12 per SM: beyond that nothing measured gained), then rows per thread (fewer
+  // resident consumer warps (up to 16 per SM: Q1 still gains from 12 -> 16), then rows per thread (fewer
   // per-tile fixed costs), then stages.  One row per thread only when nothing else fits; then fewer CTA-local groups
   // and consumer threads.  Explicit tuning pins the corresponding dimension.
   uint32_t got_ctas = 0;
@@ -1277,7 +1277,7 @@ static int32_t lean_geometry(const LeanTune& tn, const Plan& p, uint64_t row_beg
         const uint32_t c = want_ctas ? want_ctas : ctas;
         const uint32_t st = layout(Rs[ri], c, fg, nc);
         if (st >= 2) {
-          const uint32_t warps = std::min<uint32_t>(c * (nc / 32), 12);
+          const uint32_t warps = std::min<uint32_t>(c * (nc / 32), 16);
           const uint32_t score = warps * 1000 + Rs[ri] * 10 + st;
           if (score > best_score) { best_score = score; best_R = Rs[ri]; best_c = c; }
         }

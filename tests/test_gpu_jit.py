@@ -174,3 +174,32 @@ def test_count_star_without_any_column(gpu_ctx):
     finally:
         gpu_ctx.set_jit(1)
         dt.destroy()
+
+
+@pytest.mark.parametrize("mode", [0, 2], ids=["interpreted", "specialised"])
+@pytest.mark.parametrize("hint", [1, 3, 4])
+def test_four_slot_associative_group_table(gpu_ctx, mode, hint):
+    """Cardinality hints <= 4 take the four-slot fully associative CTA table (Q1 has four groups); a hint below the real
+    cardinality and a fifth, sixth ... group (column 10 has six distinct strings) overflow to the global table."""
+    gpu_ctx.set_jit(mode)
+    try:
+        t, snap = tpch.lineitem_table(90_000, seed=11, with_q1=True, with_mvcc=True)
+        dt = device_table(gpu_ctx, t)
+        try:
+            got, info = run(gpu_ctx, dt, tpch.q1_filter(), tpch.q1_aggregates(), snap, tpch.Q1_GROUP_BY, hint=hint, cap=16)
+            assert info.used_fast_kernel == 1 and info.fast_groups == 4
+            util.assert_same_result(got, oracle.aggregate(t, tpch.q1_filter(), tpch.q1_aggregates(), snap, group_by=tpch.Q1_GROUP_BY, group_capacity=16), REL)
+        finally:
+            dt.destroy()
+        m = mixed_table(7000, seed=4, long_strings=False)
+        dm = device_table(gpu_ctx, m)
+        try:
+            specs = [AggregateSpec("n", AggregateKind.CountStar()), AggregateSpec("s1", AggregateKind.Sum(1, DataType.Int64)),
+                     AggregateSpec("mx5", AggregateKind.Max(5, DataType.Decimal128(15, 2)))]
+            for keys in [(10,), (9,), (9, 10)]:
+                got, info = run(gpu_ctx, dm, PREDICATES[0], specs, group_by=keys, hint=hint, cap=64)
+                util.assert_same_result(got, oracle.aggregate(m, PREDICATES[0], specs, group_by=keys, group_capacity=64), REL)
+        finally:
+            dm.destroy()
+    finally:
+        gpu_ctx.set_jit(1)
