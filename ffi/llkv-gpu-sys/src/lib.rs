@@ -144,6 +144,7 @@ extern "C" {
     pub fn llkv_gpu_column_append_blob(col: *mut llkv_gpu_column, chunk_pk: u64, blob: *const c_void, blob_len: u64, row_ids: *const u64, row_id_base: u64) -> i32;
     pub fn llkv_gpu_column_seal(col: *mut llkv_gpu_column) -> i32;
     pub fn llkv_gpu_column_rows(col: *const llkv_gpu_column, out_rows: *mut u64) -> i32;
+    pub fn llkv_gpu_column_read(col: *mut llkv_gpu_column, row_begin: u64, n_rows: u64, out: *mut c_void, out_bytes: u64) -> i32;
     pub fn llkv_gpu_column_clear(col: *mut llkv_gpu_column) -> i32;
     pub fn llkv_gpu_column_destroy(col: *mut llkv_gpu_column) -> i32;
 

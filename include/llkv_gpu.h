@@ -283,6 +283,12 @@ int32_t llkv_gpu_column_append_blob(llkv_gpu_column* col, uint64_t chunk_pk, con
 /* Waits for outstanding uploads of this column; after this the column is scannable. */
 int32_t llkv_gpu_column_seal(llkv_gpu_column* col);
 int32_t llkv_gpu_column_rows(const llkv_gpu_column* col, uint64_t* out_rows);
+/* Reads rows [row_begin, row_begin + n_rows) of a sealed fixed-width column back into `out` in the Arrow values layout
+ * the chunks were appended in (Decimal128 columns kept as i64 on the device are widened again): what a
+ * PrimitiveVisitor::*_chunk callback would be handed for that row range (llkv-column-map/src/store/scan/visitors.rs:89-148,
+ * scan/unsorted.rs:202-345).  For tests and diagnostics of the resident image; aggregates never copy rows back.
+ * LLKV_PT_UTF8 is not supported here. */
+int32_t llkv_gpu_column_read(llkv_gpu_column* col, uint64_t row_begin, uint64_t n_rows, void* out, uint64_t out_bytes);
 /* Drops the rows but keeps the device allocation (re-upload the next batch into the same buffer). */
 int32_t llkv_gpu_column_clear(llkv_gpu_column* col);
 int32_t llkv_gpu_column_destroy(llkv_gpu_column* col);

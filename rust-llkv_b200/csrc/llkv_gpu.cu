@@ -877,6 +877,37 @@ extern "C" int32_t llkv_gpu_column_rows(const llkv_gpu_column* col, uint64_t* ou
   return LLKV_OK;
 }
 
+extern "C" int32_t llkv_gpu_column_read(llkv_gpu_column* col, uint64_t row_begin, uint64_t n_rows, void* out, uint64_t out_bytes) {
+  if (!col || (n_rows && !out)) return set_error(LLKV_ERR_INVALID_ARGUMENT, "NULL argument");
+  if (col->type == LLKV_PT_UTF8) return set_error(LLKV_ERR_INVALID_ARGUMENT, "llkv_gpu_column_read does not support Utf8 columns");
+  llkv_gpu_ctx* c = col->ctx;
+  CUDA_TRY(cudaSetDevice(c->device));
+  if (!col->sealed) {
+    int32_t rc = llkv_gpu_column_seal(col);
+    if (rc) return rc;
+  }
+  if (row_begin > col->n_rows || n_rows > col->n_rows - row_begin)
+    return set_error(LLKV_ERR_INVALID_ARGUMENT, "rows [%llu, +%llu) beyond the column's %llu rows", (unsigned long long)row_begin, (unsigned long long)n_rows,
+                     (unsigned long long)col->n_rows);
+  const uint64_t width = (uint64_t)prim_type_width(col->type);
+  if (out_bytes < n_rows * width) return set_error(LLKV_ERR_INVALID_ARGUMENT, "output buffer too small");
+  if (n_rows == 0) return LLKV_OK;
+  if (col->load_kind == LK_D64) {  // resident i64 image of a Decimal128 column: widen the range on the device first
+    ulonglong2* wide = nullptr;
+    CUDA_TRY(cudaMalloc((void**)&wide, n_rows * 16));
+    widen_dec_kernel<<<(unsigned)std::min<uint64_t>((n_rows + 255) / 256, 1184), 256, 0, c->stream>>>((const u64*)col->values + row_begin, wide, n_rows);
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaMemcpyAsync(out, wide, n_rows * 16, cudaMemcpyDeviceToHost, c->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+    cudaFree(wide);
+    if (e != cudaSuccess) return set_error(LLKV_ERR_IO, "CUDA error %s reading the column", cudaGetErrorString(e));
+    return LLKV_OK;
+  }
+  CUDA_TRY(cudaMemcpyAsync(out, (const char*)col->values + row_begin * col->elem_bytes, n_rows * col->elem_bytes, cudaMemcpyDeviceToHost, c->stream));
+  CUDA_TRY(cudaStreamSynchronize(c->stream));
+  return LLKV_OK;
+}
+
 extern "C" int32_t llkv_gpu_column_clear(llkv_gpu_column* col) {
   if (!col) return set_error(LLKV_ERR_INVALID_ARGUMENT, "column is NULL");
   llkv_gpu_ctx* c = col->ctx;

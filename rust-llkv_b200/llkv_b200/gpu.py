@@ -62,6 +62,7 @@ def load():
         "llkv_gpu_column_append_blob": (i32, [vp, u64, vp, u64, vp, u64]),
         "llkv_gpu_column_seal": (i32, [vp]),
         "llkv_gpu_column_rows": (i32, [vp, P(u64)]),
+        "llkv_gpu_column_read": (i32, [vp, u64, u64, vp, u64]),
         "llkv_gpu_column_clear": (i32, [vp]),
         "llkv_gpu_column_destroy": (i32, [vp]),
         "llkv_gpu_program_compile": (i32, [vp, vp, i32, vp, i32, vp, i32, vp, i32, P(vp)]),
@@ -232,6 +233,20 @@ class DeviceColumn:
 
     def seal(self):
         _check(self.lib.llkv_gpu_column_seal(self.handle))
+
+    def read(self, row_begin: int = 0, n_rows: Optional[int] = None) -> np.ndarray:
+        """Rows of the resident image back in the Arrow values layout (what a PrimitiveVisitor chunk callback would see)."""
+        n_rows = self.rows() - row_begin if n_rows is None else n_rows
+        t = self.dtype.type
+        if t == ffi.PT_DECIMAL128:
+            out = np.empty((n_rows, 2), dtype=np.uint64)
+        else:
+            np_t = {ffi.PT_UINT64: np.uint64, ffi.PT_INT64: np.int64, ffi.PT_FLOAT64: np.float64, ffi.PT_INT32: np.int32, ffi.PT_UINT32: np.uint32,
+                    ffi.PT_FLOAT32: np.float32, ffi.PT_DATE32: np.int32, ffi.PT_INT16: np.int16, ffi.PT_UINT16: np.uint16, ffi.PT_INT8: np.int8,
+                    ffi.PT_UINT8: np.uint8, ffi.PT_BOOLEAN: np.uint8, ffi.PT_DATE64: np.int64}[t]
+            out = np.empty(n_rows, dtype=np_t)
+        _check(self.lib.llkv_gpu_column_read(self.handle, row_begin, n_rows, C.c_void_p(out.ctypes.data), out.nbytes))
+        return out
 
     def clear(self):
         _check(self.lib.llkv_gpu_column_clear(self.handle))

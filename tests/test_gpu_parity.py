@@ -562,3 +562,26 @@ def test_full_size_properties_sf10_q6_q1(gpu_ctx):
             assert [v[j].value for j in (0, 1, 2, 3, 7)] == halves[key], key
     finally:
         dt.destroy()
+
+
+@pytest.mark.parametrize("as_blob", [False, True], ids=["values", "blobs"])
+def test_resident_image_round_trips_chunks(gpu_ctx, as_blob):
+    """Chunks appended as Arrow value buffers or as the pager's serialized blobs ("ARR0" header,
+    llkv-column-map/src/serialization.rs:41-53) land as one dense resident image; reading row ranges back gives the Arrow
+    values again, including Decimal128 columns the device keeps as i64 and ranges that straddle chunk boundaries."""
+    t = mixed_table(10_007, seed=2)
+    dt = device_table(gpu_ctx, t, chunk_rows=1000, as_blob=as_blob)
+    try:
+        for fid, col in t.columns.items():
+            if col.dtype.type == ffi.PT_UTF8:
+                continue
+            dc = dt.columns[fid]
+            assert dc.rows() == 10_007
+            want = col.values.reshape(-1, 2) if col.dtype.type == ffi.PT_DECIMAL128 else col.values
+            for lo, n in [(0, 10_007), (999, 2), (1000, 1000), (5555, 4452), (10_006, 1), (17, 0)]:
+                got = dc.read(lo, n)
+                assert np.array_equal(got.view(np.uint8), np.ascontiguousarray(want[lo:lo + n]).view(np.uint8)), (fid, lo, n)
+        with pytest.raises(LlkvError):
+            dt.columns[1].read(10_000, 8)
+    finally:
+        dt.destroy()
