@@ -309,8 +309,10 @@ def run_ours(args):
                                   "specialised": q6["info"].used_jit_kernel}},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak if achieved else None,
                          "traffic": traffic, "peak_source": peak_src, "kernel": kernel_name(q6["info"]), "kernel_ms": kms,
-                         "algorithmic_bytes_per_row": alg_bpr, "arrow_layout_bytes_per_row": arrow_bpr,
-                         "arrow_layout_equivalent_gbs": achieved_arrow},
+                         "basis": "resident bytes: what the kernel reads from HBM (Decimal128(15,2) columns are kept as i64 after seal, "
+                                  "DESIGN.md section 2); SURVEY.md section 8(d) counts Arrow-layout bytes, given beside it",
+                         "resident_bytes_per_row": alg_bpr, "algorithmic_bytes_per_row": arrow_bpr,
+                         "algorithmic_gbs": achieved_arrow},
             "e2e": {"value": total_rows * e2e_steps / e2e_dt, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": e2e_dt / e2e_steps * 1e3, "steps": e2e_steps},
             "gpu_launches": q6["launches"],
@@ -324,8 +326,8 @@ def run_ours(args):
             line["q1"] = {"workload": f"TPC-H Q1 (4-group GROUP BY, Decimal SUM/AVG/COUNT) with MVCC on the same lineitem, {n} rows per GPU",
                           "value": total_rows * args.steps / q1["seconds"], "unit": UNIT, "ms_per_step": q1["seconds"] / args.steps * 1e3,
                           "roofline": {"bound": "hbm", "achieved": a1, "peak": peak, "unit": "GB/s", "frac": a1 / peak, "kernel_ms": k1,
-                                       "algorithmic_bytes_per_row": b1, "arrow_layout_bytes_per_row": q1["info"].algorithmic_bytes_per_row,
-                                       "arrow_layout_equivalent_gbs": q1["info"].algorithmic_bytes_per_row * n / (k1 * 1e-3) / 1e9},
+                                       "resident_bytes_per_row": b1, "algorithmic_bytes_per_row": q1["info"].algorithmic_bytes_per_row,
+                                       "algorithmic_gbs": q1["info"].algorithmic_bytes_per_row * n / (k1 * 1e-3) / 1e9},
                           "groups": len(q1["result"]), "kernel_name": kernel_name(q1["info"]), "kernel": {"grid": q1["info"].grid, "block": q1["info"].block,
                                                                   "rows_per_tile": q1["info"].rows_per_tile, "stages": q1["info"].stages,
                                                                   "smem_bytes": q1["info"].smem_bytes, "fast_groups": q1["info"].fast_groups,

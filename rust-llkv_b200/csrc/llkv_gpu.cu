@@ -347,8 +347,11 @@ struct llkv_gpu_agg {
   bool in_rerun = false;
   // the lean plan of the previous run, reusable while request_signature() does not change
   LeanPlan lean;
+  LeanPlan lean2[2];  // [0] interpreted geometry, [1] geometry of the specialised build
+  bool lean_have[2] = {false, false};
+  uint32_t lean_grid2[2] = {0, 0}, lean_ctas2[2] = {1, 1};
   uint64_t lean_sig = 0;
-  uint32_t lean_grid = 0, lean_block = 0, lean_R = 0, lean_smem = 0, lean_ctas = 1, lean_jit_runs = 0;
+  uint32_t lean_jit_runs = 0;
   uint32_t* d_flags = nullptr;
   uint32_t* h_flags = nullptr;  // pinned
   unsigned char* h_stage = nullptr;  // pinned landing buffer of finalize (small tables)
@@ -1184,6 +1187,8 @@ static int32_t plan_geometry(llkv_gpu_ctx* ctx, Plan& p, bool wide, bool fast, u
 struct LeanTune {
   int block = 0, rpt = 0, stages = 0, ctas = 0;
   int max_smem = 227 * 1024, sm_count = 148;
+  bool interpreted = false;  // geometry for the ahead-of-time (interpreting) build: dispatch cost per instruction and tile
+                             // is amortised over the rows per thread, so rows per thread weigh more than resident warps
 };
 static int32_t lean_geometry(const LeanTune& tn, const Plan& p, uint64_t row_begin, uint64_t row_end, uint64_t hint, LeanPlan& lp, Geometry& g,
                              uint32_t* ctas_out) {
@@ -1308,8 +1313,8 @@ static int32_t lean_geometry(const LeanTune& tn, const Plan& p, uint64_t row_beg
         const uint32_t c = want_ctas ? want_ctas : ctas;
         const uint32_t st = layout(Rs[ri], c, fg, nc);
         if (st >= 2) {
-          const uint32_t warps = std::min<uint32_t>(c * (nc / 32), 16);
-          const uint32_t score = warps * 1000 + Rs[ri] * 10 + st;
+          const uint32_t warps = std::min<uint32_t>(c * (nc / 32), tn.interpreted ? 8 : 16);
+          const uint32_t score = tn.interpreted ? (Rs[ri] >= 4 ? 100000u : 0u) + warps * 1000 + Rs[ri] * 10 + st : warps * 1000 + Rs[ri] * 10 + st;
           if (score > best_score) { best_score = score; best_R = Rs[ri]; best_c = c; }
         }
         if (want_ctas) break;
@@ -1845,21 +1850,10 @@ static int32_t agg_launch(llkv_gpu_agg* a, const llkv_gpu_program* prog, int app
   uint32_t lean_ctas = 1;
   bool use_jit = false;
   const uint64_t sig = request_signature(ctx, req, prog, force_wide);
-  if (a->lean_sig == sig && a->cr.fast && a->frozen) {
-    // same inputs as the previous run of this aggregate: the lean plan is still right, only the row range changes
-    g.grid = a->lean_grid;
-    g.block = a->lean_block;
-    g.R = a->lean_R;
-    g.smem = a->lean_smem;
-    lean_ctas = a->lean_ctas;
-    const uint32_t T = lean.s.tile_rows;
-    lean.row_begin = row_begin;
-    lean.row_end = row_end;
-    lean.first_tile = row_begin / T;
-    lean.n_tiles = row_end > row_begin ? (row_end + T - 1) / T - lean.first_tile : 0;
-  } else {
+  if (!(a->lean_sig == sig && a->cr.fast && a->frozen)) {
     a->lean_sig = 0;
     a->lean_jit_runs = 0;
+    a->lean_have[0] = a->lean_have[1] = false;
     req.specs = a->specs.data();
     req.n_aggs = (int32_t)a->specs.size();
     req.agg_nodes = a->nodes.data();
@@ -1870,29 +1864,51 @@ static int32_t agg_launch(llkv_gpu_agg* a, const llkv_gpu_program* prog, int app
     req.no_fast = ctx->tune_force_wide != 0;
     if ((rc = compile_plan(req, a->cr))) return set_error(rc, "%s", a->cr.error.c_str());
     if ((rc = agg_freeze_layout(a, a->cr))) return rc;
-    if (a->cr.fast) {
-      if ((rc = lean_geometry(lean_tune(ctx), p, row_begin, row_end, a->hint, lean, g, &lean_ctas))) return rc;
-      p.tile_rows = lean.s.tile_rows;
-      p.stages = lean.s.stages;
-      p.fast_groups = lean.s.fg;
-      a->lean_grid = g.grid;
-      a->lean_block = g.block;
-      a->lean_R = g.R;
-      a->lean_smem = g.smem;
-      a->lean_ctas = lean_ctas;
-      a->lean_sig = sig;
-    } else if ((rc = plan_geometry(ctx, p, a->cr.wide, false, row_begin, row_end, a->hint, g))) return rc;
+    if (a->cr.fast) a->lean_sig = sig;
+    else if ((rc = plan_geometry(ctx, p, a->cr.wide, false, row_begin, row_end, a->hint, g))) return rc;
   }
   if (a->cr.fast) {
-    // specialise a plan shape once it repeats (jit_mode 1), always (2) or never (0)
+    // Two geometries per plan (kept while request_signature() does not change): [0] for the interpreting build (rows per
+    // thread first), [1] for a build specialised on the plan shape (resident warps first).  A shape is specialised once
+    // it repeats (jit_mode 1), always (2) or never (0); runs are counted on the interpreted shape.
+    auto geometry = [&](int which) -> int32_t {
+      if (a->lean_have[which]) return LLKV_OK;
+      LeanTune tn = lean_tune(ctx);
+      tn.interpreted = which == 0;
+      Geometry gg;
+      uint32_t cc = 1;
+      int32_t grc = lean_geometry(tn, p, row_begin, row_end, a->hint, a->lean2[which], gg, &cc);
+      if (grc) return grc;
+      a->lean_grid2[which] = gg.grid;
+      a->lean_ctas2[which] = cc;
+      a->lean_have[which] = true;
+      return LLKV_OK;
+    };
+    if ((rc = geometry(0))) return rc;
     if (ctx->jit_mode == 2) use_jit = true;
     else if (ctx->jit_mode == 1) {
       if (a->lean_jit_runs < 2) {
-        const std::string key(reinterpret_cast<const char*>(&lean.s), sizeof(LeanShape));
+        const std::string key(reinterpret_cast<const char*>(&a->lean2[0].s), sizeof(LeanShape));
         a->lean_jit_runs = ++ctx->shape_runs[key];
       }
       use_jit = a->lean_jit_runs >= 2;
     }
+    const int which = use_jit ? 1 : 0;
+    if ((rc = geometry(which))) return rc;
+    lean = a->lean2[which];
+    lean_ctas = a->lean_ctas2[which];
+    g.grid = a->lean_grid2[which];
+    g.block = lean.s.nc;
+    g.R = lean.s.rows_per_thread;
+    g.smem = lean.s.smem_total;
+    const uint32_t T = lean.s.tile_rows;
+    lean.row_begin = row_begin;
+    lean.row_end = row_end;
+    lean.first_tile = row_begin / T;
+    lean.n_tiles = row_end > row_begin ? (row_end + T - 1) / T - lean.first_tile : 0;
+    p.tile_rows = lean.s.tile_rows;
+    p.stages = lean.s.stages;
+    p.fast_groups = lean.s.fg;
   }
   // first-row words hold row ids (position + the row id of position 0), so shards of one table uploaded with their own
   // row_id_base merge into the table's first-appearance order
