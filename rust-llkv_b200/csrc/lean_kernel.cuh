@@ -316,6 +316,13 @@ struct LeanTile {
   }
 
   // executes one instruction for this thread's R rows; false = the warp is done with the tile
+  // specialised builds instantiate only the case of the instruction at PC (the others are discarded at compile time:
+  // a quarter of the NVRTC time); the interpreting build keeps them all
+  template <int PC>
+  static __host__ __device__ constexpr bool live(uint32_t op) {
+    if constexpr (Cfg::kStatic && PC >= 0) return Cfg::code(PC).op == op;
+    else return true;
+  }
   template <int PC>
   __device__ __forceinline__ bool step(const FInstr& in) {
     // optional operand pre-load fused into the instruction: acc = literal / column / temporary
@@ -330,7 +337,7 @@ struct LeanTile {
       for (int r = 0; r < R; ++r) acc[r] = t[r * NC + tid];
     }
     switch (in.op) {
-      case FO_LEAF: {
+      case FO_LEAF: if constexpr (live<PC>(FO_LEAF)) {
         const i64 lo = p.lits[in.c], hi = p.lits[in.c + 1];
         const unsigned char* base = sb + S.cols[in.a].smem_off;
         unsigned m = 0;
@@ -362,7 +369,7 @@ struct LeanTile {
         actm &= m;
         return true;
       }
-      case FO_MVCC: {
+      case FO_MVCC: if constexpr (live<PC>(FO_MVCC)) {
         // RowVersion::is_visible_for (llkv-transaction/src/mvcc.rs:282-334), branch free.  TxnIdManager::status: MAX -> None
         // (not committed), 1 -> Committed, listed ids -> Active/Aborted, anything else -> Committed.  The host keeps 1 out
         // of the non-committed list.
@@ -424,7 +431,7 @@ struct LeanTile {
         return true;
       }
       case FO_SELECT_DONE: return __any_sync(LLKV_FULL, actm != 0);
-      case FO_GROUP: {
+      case FO_GROUP: if constexpr (live<PC>(FO_GROUP)) {
         u64 keys[R];
         row_keys(keys);
         const uint32_t FG = S.fg;
@@ -503,19 +510,19 @@ struct LeanTile {
       }
 
       case FO_LD_COL: case FO_LD_LIT: case FO_LD_TMP: return true;  // the pre-load above is the whole instruction
-      case FO_ST_TMP: {
+      case FO_ST_TMP: if constexpr (live<PC>(FO_ST_TMP)) {
         i64* t = tmp_base + (size_t)in.a * T;
 #pragma unroll
         for (int r = 0; r < R; ++r) t[r * NC + tid] = acc[r];
         return true;
       }
-      case FO_OP_COL: {
+      case FO_OP_COL: if constexpr (live<PC>(FO_OP_COL)) {
         i64 v[R];
         load_col(in.c, in.b, v);
         binop(in.a, v);
         return true;
       }
-      case FO_OP_LIT: {
+      case FO_OP_LIT: if constexpr (live<PC>(FO_OP_LIT)) {
         i64 v[R];
         const i64 l = p.lits[in.c];
 #pragma unroll
@@ -523,7 +530,7 @@ struct LeanTile {
         binop(in.a, v);
         return true;
       }
-      case FO_OP_TMP: {
+      case FO_OP_TMP: if constexpr (live<PC>(FO_OP_TMP)) {
         i64 v[R];
         const i64* t = tmp_base + (size_t)in.b * T;
 #pragma unroll
@@ -531,7 +538,7 @@ struct LeanTile {
         binop(in.a, v);
         return true;
       }
-      case FO_DIVR: {
+      case FO_DIVR: if constexpr (live<PC>(FO_DIVR)) {
         if (in.b == 2) {  // 0 <= x < 2^32
           const unsigned d = (unsigned)kPow10U64[in.a], half = d / 2;
 #pragma unroll
@@ -554,7 +561,7 @@ struct LeanTile {
         }
         return true;
       }
-      case FO_MULP: {
+      case FO_MULP: if constexpr (live<PC>(FO_MULP)) {
         const i64 m = pow10_i64((int)in.a);
 #pragma unroll
         for (int r = 0; r < R; ++r) acc[r] *= m;
@@ -564,7 +571,7 @@ struct LeanTile {
 #pragma unroll
         for (int r = 0; r < R; ++r) acc[r] = lean_bits(__ll2double_rn(acc[r]));
         return true;
-      case FO_D2F: {
+      case FO_D2F: if constexpr (live<PC>(FO_D2F)) {
         const double den = __longlong_as_double(p.lits[in.c]);
 #pragma unroll
         for (int r = 0; r < R; ++r) acc[r] = lean_bits(__ll2double_rn(acc[r]) / den);
@@ -574,7 +581,7 @@ struct LeanTile {
       // ------------------------------------------------------------ aggregates: one private accumulator per thread,
       // CTA-local slot and word.  Ungrouped plans fold the thread's R rows in registers first.  Grouped plans update
       // per row (emit): at once when interpreted, deferred to the end of the tile when specialised (see flush()).
-      case FO_COUNT_STAR: case FO_COUNT: {
+      case FO_COUNT_STAR: case FO_COUNT: if constexpr (live<PC>(FO_COUNT_STAR) || live<PC>(FO_COUNT)) {
         if (has_slow) slow_rows(in.op, in.a, negm, in.c);
         const unsigned okm = actm & ~negm;
         const LeanWord lw = S.words[in.b];
@@ -590,7 +597,7 @@ struct LeanTile {
         }
         return true;
       }
-      case FO_FIRSTROW: case FO_FIRSTVALID: case FO_FIRSTNAN: {
+      case FO_FIRSTROW: case FO_FIRSTVALID: case FO_FIRSTNAN: if constexpr (live<PC>(FO_FIRSTROW) || live<PC>(FO_FIRSTVALID) || live<PC>(FO_FIRSTNAN)) {
         unsigned setm = actm;
         if (in.op == FO_FIRSTNAN) {
 #pragma unroll
@@ -607,7 +614,7 @@ struct LeanTile {
         emit<PC>(in, setm, none);  // also the ungrouped case: soff[] is zero
         return true;
       }
-      case FO_SUM: {
+      case FO_SUM: if constexpr (live<PC>(FO_SUM)) {
         const uint32_t cls = in.a & 3;  // 0: check each value
         unsigned fastm = actm & ~negm;
         if (cls == 0) {
@@ -637,7 +644,7 @@ struct LeanTile {
         }
         return true;
       }
-      case FO_FSUM: {
+      case FO_FSUM: if constexpr (live<PC>(FO_FSUM)) {
         if (has_slow) slow_rows(FO_FSUM, in.a, negm, in.c);
         const unsigned okm = actm & ~negm;
         const LeanWord lw = S.words[in.b];
@@ -656,7 +663,7 @@ struct LeanTile {
         }
         return true;
       }
-      case FO_MIN_I: case FO_MAX_I: case FO_MIN_F: case FO_MAX_F: {
+      case FO_MIN_I: case FO_MAX_I: case FO_MIN_F: case FO_MAX_F: if constexpr (live<PC>(FO_MIN_I) || live<PC>(FO_MAX_I) || live<PC>(FO_MIN_F) || live<PC>(FO_MAX_F)) {
         const bool is_f = in.op == FO_MIN_F || in.op == FO_MAX_F;
         unsigned setm = actm;
         u64 e[R];
