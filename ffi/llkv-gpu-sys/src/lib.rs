@@ -101,6 +101,8 @@ pub struct llkv_run_info {
     pub last_kernel_ms: f32,
     pub used_fast_kernel: u32,
     pub used_jit_kernel: u32,
+    pub partitions: u32,
+    pub _pad: u32,
 }
 
 #[repr(C)]
@@ -135,6 +137,7 @@ extern "C" {
     pub fn llkv_gpu_ctx_set_timing(ctx: *mut llkv_gpu_ctx, enabled: i32) -> i32;
     pub fn llkv_gpu_ctx_set_tuning(ctx: *mut llkv_gpu_ctx, ctas_per_sm: i32, block_threads: i32, stages: i32, rows_per_thread: i32, force_wide: i32) -> i32;
     pub fn llkv_gpu_ctx_set_jit(ctx: *mut llkv_gpu_ctx, mode: i32) -> i32;
+    pub fn llkv_gpu_ctx_set_partitioning(ctx: *mut llkv_gpu_ctx, mode: i32) -> i32;
     pub fn llkv_gpu_host_alloc(bytes: u64, out: *mut *mut c_void) -> i32;
     pub fn llkv_gpu_host_free(p: *mut c_void) -> i32;
 

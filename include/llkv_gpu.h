@@ -225,6 +225,8 @@ typedef struct llkv_run_info {
   float last_kernel_ms;         /* device time of the scan kernel (CUDA events) when timing is enabled, else 0 */
   uint32_t used_fast_kernel;    /* 1 when the lean kernel (lean_kernel.cuh) ran, 0 for the general interpreter */
   uint32_t used_jit_kernel;     /* 1 when the lean kernel ran as a build specialised on this plan shape (jit.cpp) */
+  uint32_t partitions;          /* hash partitions of a partitioned high-cardinality GROUP BY run, 0 = not partitioned */
+  uint32_t _pad;
 } llkv_run_info;
 
 typedef struct llkv_gpu_ctx llkv_gpu_ctx;
@@ -258,6 +260,14 @@ int32_t llkv_gpu_ctx_set_tuning(llkv_gpu_ctx* ctx, int32_t ctas_per_sm, int32_t 
  * the first run.  Literals, row ranges and snapshots are run-time parameters of the specialised kernel.  Without NVRTC
  * on the machine the lean kernel keeps interpreting on the GPU. */
 int32_t llkv_gpu_ctx_set_jit(llkv_gpu_ctx* ctx, int32_t mode);
+
+/* High-cardinality GROUP BY (cardinality_hint > 128; the reference's hash-map GROUP BY, llkv-executor/src/lib.rs:
+ * 5028-5355) updates the global open-addressing table once per row.  When the table is much larger than L2 that is one
+ * random DRAM sector read-modify-write per row and word; the partitioned form writes (key, row id, operands) tuples into
+ * hash partitions whose table slice fits in L2 and folds them partition by partition (two streaming passes instead of
+ * random access).  mode: 0 = never, 1 = when the table exceeds L2 and the scan is long enough (default), 2 = whenever
+ * the plan allows it (tests).  Results are identical in every mode.  Needs the specialised kernel (jit mode != 0). */
+int32_t llkv_gpu_ctx_set_partitioning(llkv_gpu_ctx* ctx, int32_t mode);
 
 /* Page-locked host memory so chunk uploads DMA straight from the caller's buffer. */
 int32_t llkv_gpu_host_alloc(uint64_t bytes, void** out);
@@ -361,7 +371,7 @@ int32_t llkv_gpu_debug_plan(const llkv_debug_column* cols, int32_t n_cols, const
                             int32_t deleted_by_col, uint64_t txn_id, uint64_t snapshot_id, const llkv_agg_spec* specs, int32_t n_aggs,
                             const llkv_scalar_node* nodes, int32_t n_nodes, const uint64_t* group_key_fields, int32_t n_keys,
                             int32_t expr_mode, uint64_t cardinality_hint, int32_t block_threads, int32_t rows_per_thread, int32_t stages,
-                            int32_t ctas_per_sm, int32_t jit, const char* cubin_path, char* out_text, uint64_t out_cap);
+                            int32_t ctas_per_sm, int32_t jit /* bit 0: specialise with NVRTC, bit 1: as the partitioned GROUP BY scan */, const char* cubin_path, char* out_text, uint64_t out_cap);
 
 /* ---- multi-GPU: one context per rank, NCCL over NVLink ---- */
 #define LLKV_GPU_UNIQUE_ID_BYTES 128

@@ -109,7 +109,8 @@ std::string shape_source(const LeanShape& s, int ctas_per_sm) {
        "  static constexpr bool kStatic = true;\n"
        "  static __device__ __forceinline__ const LeanShape& shape(const LeanPlan&) { return kJitShape; }\n"
        "  static __host__ __device__ constexpr FInstr code(int pc) { return kJitShape.code[pc]; }\n"
-       "  static constexpr bool kDefer = kJitShape.n_keys != 0 && kJitShape.direct_global == 0;\n"
+       "  static constexpr bool kPartition = kJitShape.partition != 0;\n"
+       "  static constexpr bool kDefer = kJitShape.n_keys != 0 && (kJitShape.direct_global == 0 || kPartition);\n"
        "  static constexpr int kStash = " << n_stash << ";\n"
        "};\n"
        "}  // namespace llkv\n"
@@ -184,8 +185,7 @@ int jit_compile_cubin(const LeanShape& shape, int ctas_per_sm, std::vector<char>
   return 0;
 }
 
-cudaError_t jit_launch(int device, const LeanPlan& plan, int ctas_per_sm, uint32_t grid, cudaStream_t stream, bool* used, std::string* why) {
-  *used = false;
+static Entry* jit_entry(int device, const LeanPlan& plan, int ctas_per_sm) {
   std::string key;
   key.reserve(sizeof(LeanShape) + 16);
   key.append(reinterpret_cast<const char*>(&device), sizeof(device));
@@ -216,6 +216,14 @@ cudaError_t jit_launch(int device, const LeanPlan& plan, int ctas_per_sm, uint32
     }
     e = &it->second;
   }
+  return e;
+}
+
+bool jit_ready(int device, const LeanPlan& plan, int ctas_per_sm) { return !jit_entry(device, plan, ctas_per_sm)->failed; }
+
+cudaError_t jit_launch(int device, const LeanPlan& plan, int ctas_per_sm, uint32_t grid, cudaStream_t stream, bool* used, std::string* why) {
+  *used = false;
+  Entry* e = jit_entry(device, plan, ctas_per_sm);
   if (e->failed) {
     if (why) *why = e->log;
     return cudaSuccess;  // the caller interprets instead

@@ -16,6 +16,8 @@ int jit_compile_cubin(const LeanShape& shape, int ctas_per_sm, std::vector<char>
 // Launches the specialised kernel for plan.s (compiled and cached per device on first use).  `*used` is false, with
 // cudaSuccess returned, when specialisation is not possible (NVRTC missing, compile error): the caller then launches the
 // interpreted kernel instead.
+// compiles (or finds) the specialised kernel of the plan's shape; false = NVRTC missing or the compile failed
+bool jit_ready(int device, const LeanPlan& plan, int ctas_per_sm);
 cudaError_t jit_launch(int device, const LeanPlan& plan, int ctas_per_sm, uint32_t grid, cudaStream_t stream, bool* used, std::string* why);
 
 }  // namespace llkv

@@ -86,6 +86,13 @@ static __device__ __noinline__ void lean_slow_accumulate(u64* w, uint32_t op, ui
   }
 }
 
+// one aggregate's update from a tuple field of a partitioned plan: MIN/MAX operands travel in their order-preserving
+// encoding (what emit() parks), everything else as the raw value
+__device__ __forceinline__ void lean_apply_field(u64* w, uint32_t op, uint32_t flags, u64 field, u64 row) {
+  const bool enc = op == FO_MIN_I || op == FO_MAX_I;
+  lean_slow_accumulate(w, op, flags, enc ? (i64)(field ^ 0x8000000000000000ull) : (i64)field, row);
+}
+
 // packed GROUP BY key of row `idx` of the staged tile (slow path; the hot path computes keys in LeanTile::row_keys)
 static __device__ __noinline__ u64 lean_row_key(const LeanPlan& p, const LeanShape& S, const unsigned char* sb, uint32_t idx) {
   u64 K = 0;
@@ -135,10 +142,21 @@ __host__ __device__ constexpr int lean_stash_index(int pc) {
   return k;
 }
 
+// partitioned plans: tuple field of the aggregate at `pc` (0 = key, 1 = row id, then one per operand-taking aggregate)
+template <class Cfg>
+__host__ __device__ constexpr int lean_field_index(int pc) {
+  int k = 2;
+  for (int i = 0; i < pc; ++i)
+    if (lean_takes_operand(Cfg::code(i).op)) ++k;
+  return k;
+}
+__device__ __forceinline__ void lean_consumer_barrier(int nc) { asm volatile("bar.sync 1, %0;" ::"r"(nc) : "memory"); }
+
 // interpreted: the shape comes with the kernel parameter
 struct LeanDynCfg {
   static constexpr bool kStatic = false;
   static constexpr bool kDefer = false;
+  static constexpr bool kPartition = false;
   static constexpr int kStash = 1;
   static __host__ __device__ constexpr FInstr code(int) { return FInstr{}; }
   static __device__ __forceinline__ const LeanShape& shape(const LeanPlan& p) { return p.s; }
@@ -171,11 +189,13 @@ struct LeanTile {
   // specialised + grouped: operands / row masks of the tile's aggregate instructions, applied by flush()
   u64 stash_v[Cfg::kStash][R];
   unsigned stash_m[Cfg::kStash];
+  u64 pk[Cfg::kPartition ? R : 1];  // partitioned plans: the rows' packed keys, kept from GROUP to scatter()
+  unsigned char* const part_smem;
 
   __device__ __forceinline__ LeanTile(const LeanPlan& plan, const LeanShape& shape, unsigned char* smem, int tid_, int nc)
       : p(plan), S(shape), tid(tid_), NC(nc), T(shape.tile_rows), my4(smem + shape.smem_acc_off + tid_ * 4),
         my8(smem + shape.smem_acc_off + tid_ * 8), tmp_base(reinterpret_cast<i64*>(smem + shape.smem_tmp_off)),
-        tbl(reinterpret_cast<u64*>(smem + shape.smem_tbl_off)), grouped(shape.n_keys != 0) {}
+        tbl(reinterpret_cast<u64*>(smem + shape.smem_tbl_off)), grouped(shape.n_keys != 0), part_smem(smem + shape.smem_part_off) {}
 
   // one column's R values as sign/zero-extended i64.  The lean kernel knows four physical layouts.
   __device__ __forceinline__ void load_col(uint32_t col, uint32_t kind, i64 (&out)[R]) const {
@@ -436,6 +456,12 @@ struct LeanTile {
         row_keys(keys);
         const uint32_t FG = S.fg;
         negm = 0;
+        if constexpr (Cfg::kPartition) {  // the rows leave this kernel as tuples: scatter()
+#pragma unroll
+          for (int r = 0; r < R; ++r) pk[r] = keys[r];
+          has_slow = false;
+          return true;
+        }
         if (S.direct_global) {  // high cardinality: a CTA-local table would hold a vanishing share of the keys
           negm = actm;
           has_slow = __any_sync(LLKV_FULL, negm != 0);
@@ -617,7 +643,7 @@ struct LeanTile {
       case FO_SUM: if constexpr (live<PC>(FO_SUM)) {
         const uint32_t cls = in.a & 3;  // 0: check each value
         unsigned fastm = actm & ~negm;
-        if (cls == 0) {
+        if (cls == 0 && !Cfg::kPartition) {  // (tuples carry the full value; the table update is exact for any i64)
           unsigned bigm = 0;
 #pragma unroll
           for (int r = 0; r < R; ++r)
@@ -681,7 +707,7 @@ struct LeanTile {
         return true;
       }
       case FO_END:
-        if constexpr (Cfg::kStatic && PC >= 0) flush();
+        if constexpr (Cfg::kStatic && PC >= 0 && !Cfg::kPartition) flush();
         return false;
       default: errbits |= FLAG_BAD_PLAN; return false;
     }
@@ -732,17 +758,15 @@ struct LeanTile {
   // read-modify-write chain per aggregate (two rows of a thread may share a slot, which serialises them).
   template <int PC>
   __device__ __forceinline__ void emit(const FInstr& in, unsigned mask, const u64 (&v)[R]) {
-    if constexpr (Cfg::kStatic && PC >= 0) {
-      if constexpr (Cfg::kDefer) {
-        constexpr int k = lean_stash_index<Cfg>(PC);
-        stash_m[k] = mask;
+    if constexpr (Cfg::kStatic && PC >= 0 && Cfg::kDefer) {
+      constexpr int k = lean_stash_index<Cfg>(PC);
+      stash_m[k] = mask;
 #pragma unroll
-        for (int r = 0; r < R; ++r) stash_v[k][r] = v[r];
-        return;
-      }
+      for (int r = 0; r < R; ++r) stash_v[k][r] = v[r];
+    } else {
+#pragma unroll
+      for (int r = 0; r < R; ++r) apply_row(in, (mask >> r) & 1u, v[r], r);
     }
-#pragma unroll
-    for (int r = 0; r < R; ++r) apply_row(in, (mask >> r) & 1u, v[r], r);
   }
 
   template <int PC>
@@ -762,6 +786,102 @@ struct LeanTile {
 #pragma unroll
         for (int r = 0; r < R; ++r) flush_row<0>(r);
       }
+    }
+  }
+
+  // ---------------------------------------------------------------------------------- partitioned GROUP BY (pass 1)
+  // Every consumer thread calls scatter() once per tile (also warps that left the program early: their actm is 0).
+  // The tile's selected rows become tuples (key, row id, operands), are counting-sorted by hash partition in shared
+  // memory and leave as one run per partition and field; space in a partition is reserved with one atomic per
+  // partition and tile, so each partition's stream grows sequentially and full lines reach DRAM.
+  __device__ __forceinline__ uint32_t part_of(u64 K) const {
+    return K == kEmptyKey ? 0u : (uint32_t)((mix64(K) & (p.gcap - 1)) >> p.part_shift);
+  }
+  template <int PC>
+  __device__ __forceinline__ void stage_row(u64* stage, uint32_t idx, int r) {
+    if constexpr (Cfg::kStatic) {
+      constexpr FInstr in = Cfg::code(PC);
+      if constexpr (lean_takes_operand(in.op)) stage[(uint32_t)lean_field_index<Cfg>(PC) * T + idx] = stash_v[lean_stash_index<Cfg>(PC)][r];
+      if constexpr (in.op != FO_END && PC + 1 < kMaxFastInstr) stage_row<PC + 1>(stage, idx, r);
+    }
+  }
+  // a tuple that found its partition full: applied to the table here (the per-row path of direct_global plans)
+  template <int PC>
+  __device__ __forceinline__ void apply_tuple(const u64* stage, uint32_t i, u64 gs, u64 row) {
+    if constexpr (Cfg::kStatic) {
+      constexpr FInstr in = Cfg::code(PC);
+      if constexpr (lean_is_aggregate(in.op)) {
+        u64 v = 0;
+        if constexpr (lean_takes_operand(in.op)) v = stage[(uint32_t)lean_field_index<Cfg>(PC) * T + i];
+        lean_apply_field(&p.gwords[gs * S.n_gwords + in.c], in.op, in.a, v, row);
+      }
+      if constexpr (in.op != FO_END && PC + 1 < kMaxFastInstr) apply_tuple<PC + 1>(stage, i, gs, row);
+    }
+  }
+  __device__ __forceinline__ void scatter() {
+    if constexpr (Cfg::kPartition) {
+      uint32_t* const s_cnt = reinterpret_cast<uint32_t*>(part_smem);
+      uint32_t* const s_off = s_cnt + (kMaxPartitions + 1);
+      uint32_t* const s_gb = s_off + (kMaxPartitions + 1);
+      u64* const stage = reinterpret_cast<u64*>(s_gb + (kMaxPartitions + 1) + 1);
+      const uint32_t P = 1u << p.part_bits;
+      uint32_t part[R], pos[R];
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        part[r] = part_of(pk[r]);
+        pos[r] = 0;
+        if ((actm >> r) & 1u) pos[r] = atomicAdd(&s_cnt[part[r]], 1u);
+      }
+      lean_consumer_barrier(NC);
+      for (uint32_t q = (uint32_t)tid; q < P; q += (uint32_t)NC) {
+        const uint32_t c = s_cnt[q];
+        s_gb[q] = c ? atomicAdd(&p.part_cursor[q], c) : 0u;
+      }
+      if (tid < 32) {  // exclusive prefix of the counts: each lane sums a contiguous share, then a warp scan
+        const uint32_t per = (P + 31u) >> 5;
+        const uint32_t lo = (uint32_t)tid * per;
+        uint32_t sum = 0;
+        for (uint32_t q = lo; q < lo + per && q < P; ++q) sum += s_cnt[q];
+        uint32_t inc = sum;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const uint32_t y = __shfl_up_sync(LLKV_FULL, inc, o);
+          if (tid >= o) inc += y;
+        }
+        uint32_t run = inc - sum;
+        for (uint32_t q = lo; q < lo + per && q < P; ++q) {
+          s_off[q] = run;
+          run += s_cnt[q];
+        }
+        if (tid == 31) s_off[P] = inc;  // tuples of the tile
+      }
+      lean_consumer_barrier(NC);
+#pragma unroll
+      for (int r = 0; r < R; ++r)
+        if ((actm >> r) & 1u) {
+          const uint32_t idx = s_off[part[r]] + pos[r];
+          stage[idx] = pk[r];
+          stage[T + idx] = row0 + (u64)(r * NC + tid);
+          stage_row<0>(stage, idx, r);
+        }
+      lean_consumer_barrier(NC);
+      const uint32_t total = s_off[P];
+      const u64 cap = p.part_cap;
+      const uint32_t NF = S.n_fields;
+      for (uint32_t i = (uint32_t)tid; i < total; i += (uint32_t)NC) {
+        const u64 K = stage[i];
+        const uint32_t q = part_of(K);
+        const u64 j = (u64)s_gb[q] + (i - s_off[q]);
+        if (j < cap) {
+          u64* out = p.part_out + (u64)q * NF * cap + j;
+          for (uint32_t f = 0; f < NF; ++f) __stcs(&out[(u64)f * cap], stage[f * T + i]);  // read once, by the next kernel
+        } else {
+          const u64 gs = lean_global_slot(p.gkeys, p.gcap, S.n_keys, K, errbits);
+          apply_tuple<0>(stage, i, gs, stage[T + i]);
+        }
+      }
+      for (uint32_t q = (uint32_t)tid; q < P; q += (uint32_t)NC) s_cnt[q] = 0;
+      lean_consumer_barrier(NC);
     }
   }
 
@@ -822,6 +942,10 @@ __device__ __forceinline__ void lean_body(const LeanPlan& p) {
       }
   }
   for (uint32_t g = tid; g < FG; g += blockDim.x) tbl[g] = grouped ? kEmptyKey : 0ull;
+  if constexpr (Cfg::kPartition) {
+    uint32_t* const s_cnt = reinterpret_cast<uint32_t*>(smem + S.smem_part_off);
+    for (uint32_t q = tid; q < 3u * (kMaxPartitions + 1) + 1u; q += blockDim.x) s_cnt[q] = 0;
+  }
   if (tid == 0) {
     for (uint32_t s = 0; s < ST; ++s) {
       mbar_init(&full_bar[s], 1);
@@ -871,6 +995,7 @@ __device__ __forceinline__ void lean_body(const LeanPlan& p) {
       t.begin_tile(stage0 + (size_t)s * S.stage_bytes, rt * T, base_row, begin_rel, end_rel);
       if constexpr (Cfg::kStatic) t.template run_static<0>();
       else t.run_dynamic();
+      if constexpr (Cfg::kPartition) t.scatter();
       __syncwarp();
       if (lane == 0) mbar_arrive(&empty_bar[s]);  // this warp is done with the stage
       if (++s == ST) {

@@ -27,6 +27,7 @@ typedef unsigned __int128 u128;
 cudaError_t launch_scan(const Plan* dplan, bool wide, int rows_per_thread, uint32_t grid, uint32_t block, uint32_t smem,
                         cudaStream_t stream);
 cudaError_t launch_lean(const LeanPlan& plan, uint32_t grid, cudaStream_t stream);
+cudaError_t launch_partition_apply(const PartPlan& plan, uint32_t grid, cudaStream_t stream);
 cudaError_t launch_init_table(u64* keys, u64* words, u64 rows, uint32_t n_gwords, const uint8_t* word_class_dev, cudaStream_t stream);
 cudaError_t launch_merge_table(const Plan* dplan, const u64* src_keys, const u64* src_words, u64 src_cap, cudaStream_t stream);
 cudaError_t launch_merge_ungrouped_p2p(u64* state, u64* const* peer_boxes, int n_ranks, int rank, uint32_t n_gwords, u64 epoch,
@@ -242,6 +243,7 @@ struct llkv_gpu_ctx {
   bool timing = false;
   int tune_ctas = 0, tune_block = 0, tune_stages = 0, tune_rpt = 0, tune_force_wide = 0;
   int jit_mode = 1;  // 0 never, 1 specialise a plan shape from its second run on, 2 always
+  int partition_mode = 1;  // partitioned high-cardinality GROUP BY: 0 never, 1 when the table exceeds L2, 2 whenever possible
   std::map<std::string, uint32_t> shape_runs;
   bool keep_wide_decimals = false;  // LLKV_GPU_KEEP_WIDE_DECIMALS=1: never narrow Decimal128 columns at seal
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -347,9 +349,13 @@ struct llkv_gpu_agg {
   bool in_rerun = false;
   // the lean plan of the previous run, reusable while request_signature() does not change
   LeanPlan lean;
-  LeanPlan lean2[2];  // [0] interpreted geometry, [1] geometry of the specialised build
-  bool lean_have[2] = {false, false};
-  uint32_t lean_grid2[2] = {0, 0}, lean_ctas2[2] = {1, 1};
+  LeanPlan lean2[3];  // [0] interpreted geometry, [1] geometry of the specialised build, [2] specialised + partitioned
+  bool lean_have[3] = {false, false, false};
+  uint32_t lean_grid2[3] = {0, 0, 0}, lean_ctas2[3] = {1, 1, 1};
+  // partitioned high-cardinality GROUP BY: tuple partitions and their fill counters, kept across runs
+  u64* part_out = nullptr;
+  size_t part_out_elems = 0;
+  uint32_t* part_cursor = nullptr;
   uint64_t lean_sig = 0;
   uint32_t lean_jit_runs = 0;
   uint32_t* d_flags = nullptr;
@@ -472,6 +478,13 @@ extern "C" int32_t llkv_gpu_ctx_set_jit(llkv_gpu_ctx* c, int32_t mode) {
   if (!c) return set_error(LLKV_ERR_INVALID_ARGUMENT, "ctx is NULL");
   if (mode < 0 || mode > 2) return set_error(LLKV_ERR_INVALID_ARGUMENT, "jit mode must be 0, 1 or 2");
   c->jit_mode = mode;
+  return LLKV_OK;
+}
+
+extern "C" int32_t llkv_gpu_ctx_set_partitioning(llkv_gpu_ctx* c, int32_t mode) {
+  if (!c) return set_error(LLKV_ERR_INVALID_ARGUMENT, "ctx is NULL");
+  if (mode < 0 || mode > 2) return set_error(LLKV_ERR_INVALID_ARGUMENT, "partitioning mode must be 0, 1 or 2");
+  c->partition_mode = mode;
   return LLKV_OK;
 }
 
@@ -1189,7 +1202,27 @@ struct LeanTune {
   int max_smem = 227 * 1024, sm_count = 148;
   bool interpreted = false;  // geometry for the ahead-of-time (interpreting) build: dispatch cost per instruction and tile
                              // is amortised over the rows per thread, so rows per thread weigh more than resident warps
+  bool partition = false;    // partitioned high-cardinality GROUP BY: the scan emits tuples (LeanTile::scatter)
 };
+
+// A grouped lean plan can run partitioned when everything after GROUP is arithmetic plus aggregates whose row mask is the
+// selection itself and whose update partition_apply_kernel knows (no NaN-dependent masks).
+static bool partition_eligible(const Plan& p) {
+  if (p.n_keys == 0) return false;
+  bool after_group = false;
+  uint32_t fields = 2;
+  for (uint32_t i = 0; i < p.n_finstr; ++i) {
+    const uint32_t op = p.fcode[i].op;
+    if (op == FO_GROUP) {
+      after_group = true;
+      continue;
+    }
+    if (!after_group) continue;
+    if (op == FO_LEAF || op == FO_MVCC || op == FO_SELECT_DONE || op == FO_MIN_F || op == FO_MAX_F || op == FO_FIRSTNAN) return false;
+    if (lean_takes_operand(op)) ++fields;
+  }
+  return after_group && fields <= 2 + (uint32_t)kMaxPartOperands;
+}
 static int32_t lean_geometry(const LeanTune& tn, const Plan& p, uint64_t row_begin, uint64_t row_end, uint64_t hint, LeanPlan& lp, Geometry& g,
                              uint32_t* ctas_out) {
   memset(&lp, 0, sizeof(lp));
@@ -1244,6 +1277,14 @@ static int32_t lean_geometry(const LeanTune& tn, const Plan& p, uint64_t row_beg
       FG = 1;
       s.direct_global = 1;
     }
+    if (tn.partition) {
+      FG = 1;
+      s.direct_global = 1;
+      s.partition = 1;
+      s.n_fields = 2;
+      for (uint32_t i = 0; i < p.n_finstr; ++i)
+        if (lean_takes_operand(p.fcode[i].op)) ++s.n_fields;
+    }
     while (FG > 4 && (u64)FG * thread_bytes * NC > 64u * 1024u) FG /= 2;
   }
   const uint32_t budget_total = (uint32_t)tn.max_smem;
@@ -1268,7 +1309,8 @@ static int32_t lean_geometry(const LeanTune& tn, const Plan& p, uint64_t row_beg
     }
     const uint32_t slot_stride = align_up(woff, 128);
     const uint32_t acc_bytes = align_up(fg * slot_stride, 128), tmp_bytes = align_up(p.fast_tmps * T * 8, 128), tbl_bytes = align_up(fg * 16, 128);
-    const uint32_t fixed = 128 /* barriers */ + acc_bytes + tmp_bytes + tbl_bytes;
+    const uint32_t part_bytes = s.partition ? align_up(3u * (kMaxPartitions + 1) * 4 + 4 + s.n_fields * T * 8, 128) : 0;
+    const uint32_t fixed = 128 /* barriers */ + acc_bytes + tmp_bytes + tbl_bytes + part_bytes;
     const uint32_t per_cta = budget_total / ctas - 1024;
     if (!stage_bytes || per_cta < fixed + 2 * stage_bytes) return 0;
     uint32_t st = (per_cta - fixed) / stage_bytes;
@@ -1287,6 +1329,8 @@ static int32_t lean_geometry(const LeanTune& tn, const Plan& p, uint64_t row_beg
     off += tmp_bytes;
     s.smem_tbl_off = off;
     off += tbl_bytes;
+    s.smem_part_off = off;
+    off += part_bytes;
     s.smem_total = off;
     s.nc = nc;
     s.rows_per_thread = R;
@@ -1314,7 +1358,9 @@ static int32_t lean_geometry(const LeanTune& tn, const Plan& p, uint64_t row_beg
         const uint32_t st = layout(Rs[ri], c, fg, nc);
         if (st >= 2) {
           const uint32_t warps = std::min<uint32_t>(c * (nc / 32), tn.interpreted ? 8 : 16);
-          const uint32_t score = tn.interpreted ? (Rs[ri] >= 4 ? 100000u : 0u) + warps * 1000 + Rs[ri] * 10 + st : warps * 1000 + Rs[ri] * 10 + st;
+          // (partitioned scans: rows per tile first — longer runs per partition, fewer barriers and reservations per row)
+          const uint32_t score = tn.partition ? Rs[ri] * 100000u + warps * 1000 + st
+                                 : tn.interpreted ? (Rs[ri] >= 4 ? 100000u : 0u) + warps * 1000 + Rs[ri] * 10 + st : warps * 1000 + Rs[ri] * 10 + st;
           if (score > best_score) { best_score = score; best_R = Rs[ri]; best_c = c; }
         }
         if (want_ctas) break;
@@ -1396,6 +1442,10 @@ static std::string lean_listing(const LeanPlan& lp, const Geometry& g, uint32_t 
   snprintf(b, sizeof(b), "lean plan: %u instr, %u cols, %u words, %u keys | NC=%u R=%u tile=%u stages=%u stage_bytes=%u fg=%u slot_stride=%u smem=%u ctas/SM=%u grid=%u\n",
            s.n_code, s.n_cols, s.n_words, s.n_keys, s.nc, s.rows_per_thread, s.tile_rows, s.stages, s.stage_bytes, s.fg, s.slot_stride, s.smem_total, ctas, g.grid);
   o += b;
+  if (s.partition) {
+    snprintf(b, sizeof(b), "  partitioned: %u fields per tuple, staging at smem+%u\n", s.n_fields, s.smem_part_off);
+    o += b;
+  }
   for (uint32_t c = 0; c < s.n_cols; ++c) {
     snprintf(b, sizeof(b), "  col %u: %u B/row at stage+%u\n", c, s.cols[c].elem_bytes, s.cols[c].smem_off);
     o += b;
@@ -1494,6 +1544,7 @@ extern "C" int32_t llkv_gpu_debug_plan(const llkv_debug_column* cols, int32_t n_
     tn.rpt = rows_per_thread;
     tn.stages = stages;
     tn.ctas = ctas_per_sm;
+    tn.partition = (jit & 2) != 0 && partition_eligible(cr.plan);  // jit bit 1: the partitioned form of a GROUP BY
     LeanPlan lp;
     Geometry g;
     uint32_t ctas = 1;
@@ -1641,6 +1692,8 @@ extern "C" void llkv_gpu_agg_destroy(llkv_gpu_agg* a) {
   if (a->mg_words) cudaFree(a->mg_words);
   if (a->mg_cap) cudaFree(a->mg_cap);
   if (a->mg_stats) cudaFree(a->mg_stats);
+  if (a->part_out) cudaFree(a->part_out);
+  if (a->part_cursor) cudaFree(a->part_cursor);
   if (a->d_flags) cudaFree(a->d_flags);
   if (a->d_plan) cudaFree(a->d_plan);
   if (a->h_plan) cudaFreeHost(a->h_plan);
@@ -1853,7 +1906,7 @@ static int32_t agg_launch(llkv_gpu_agg* a, const llkv_gpu_program* prog, int app
   if (!(a->lean_sig == sig && a->cr.fast && a->frozen)) {
     a->lean_sig = 0;
     a->lean_jit_runs = 0;
-    a->lean_have[0] = a->lean_have[1] = false;
+    a->lean_have[0] = a->lean_have[1] = a->lean_have[2] = false;
     req.specs = a->specs.data();
     req.n_aggs = (int32_t)a->specs.size();
     req.agg_nodes = a->nodes.data();
@@ -1875,6 +1928,7 @@ static int32_t agg_launch(llkv_gpu_agg* a, const llkv_gpu_program* prog, int app
       if (a->lean_have[which]) return LLKV_OK;
       LeanTune tn = lean_tune(ctx);
       tn.interpreted = which == 0;
+      tn.partition = which == 2;
       Geometry gg;
       uint32_t cc = 1;
       int32_t grc = lean_geometry(tn, p, row_begin, row_end, a->hint, a->lean2[which], gg, &cc);
@@ -1893,7 +1947,20 @@ static int32_t agg_launch(llkv_gpu_agg* a, const llkv_gpu_program* prog, int app
       }
       use_jit = a->lean_jit_runs >= 2;
     }
-    const int which = use_jit ? 1 : 0;
+    int which = use_jit ? 1 : 0;
+    // Partitioned form of a high-cardinality GROUP BY: worth two extra streaming passes over the tuples once the group
+    // table is far larger than L2 (every row is then a random DRAM read-modify-write).  Needs the specialised kernel.
+    if (ctx->partition_mode && ctx->jit_mode && a->lean2[0].s.direct_global && partition_eligible(p)) {
+      const u64 table_bytes = a->gcap * (8ull + 8ull * a->n_gwords);
+      const bool big = table_bytes > (64ull << 20) && row_end - row_begin >= (4ull << 20);
+      if ((big || ctx->partition_mode == 2) && a->gcap >= 64) {
+        if ((rc = geometry(2))) return rc;
+        if (jit_ready(ctx->device, a->lean2[2], (int)a->lean_ctas2[2])) {
+          which = 2;
+          use_jit = true;
+        }
+      }
+    }
     if ((rc = geometry(which))) return rc;
     lean = a->lean2[which];
     lean_ctas = a->lean_ctas2[which];
@@ -1939,6 +2006,67 @@ static int32_t agg_launch(llkv_gpu_agg* a, const llkv_gpu_program* prog, int app
   const u64 threads = (u64)g.grid * g.block;
   u64 max_rows_per_launch = threads * 32000ull;
   if (a->cr.fast) max_rows_per_launch = std::min<u64>(max_rows_per_launch, 0xf0000000ull) / p.tile_rows * p.tile_rows;
+  // Partitioned GROUP BY: 2^bits partitions, each a contiguous slice of the table of about 24 MB (keys + words) so a
+  // slice and the tuple stream share L2 comfortably; a launch covers at most 2^28 rows so the tuple buffers stay bounded
+  // (capacity = the uniform share + 25 %; a partition that fills up — skewed keys — hands its surplus rows to the per-row
+  // path inside the scan, so no rerun is ever needed).
+  PartPlan pp;
+  uint32_t part_grid = 0;
+  const bool partitioned = a->cr.fast && lean.s.partition != 0;
+  if (partitioned) {
+    const u64 table_bytes = a->gcap * (8ull + 8ull * a->n_gwords);
+    uint32_t cap_log2 = 0;
+    while ((1ull << cap_log2) < a->gcap) ++cap_log2;
+    uint32_t bits = 1;
+    u64 slice_mb = 24;
+    if (const char* e = getenv("LLKV_GPU_PART_SLICE_MB")) slice_mb = std::max<u64>(1, strtoull(e, nullptr, 10));  // experiments
+    while (bits < 8 && (table_bytes >> bits) > (slice_mb << 20)) ++bits;
+    if (bits + 3 > cap_log2) bits = cap_log2 > 3 ? cap_log2 - 3 : 1;
+    const u64 P = 1ull << bits;
+    max_rows_per_launch = std::min<u64>(max_rows_per_launch, 1ull << 28) / p.tile_rows * p.tile_rows;
+    const u64 launch_rows = std::min<u64>(row_end - row_begin + p.tile_rows, max_rows_per_launch);
+    const u64 part_cap = (launch_rows / P + launch_rows / (4 * P) + 1024 + 15) / 16 * 16;
+    const size_t elems = (size_t)(P * lean.s.n_fields * part_cap);
+    if (a->part_out_elems < elems) {
+      if (a->part_out) CUDA_TRY(cudaFree(a->part_out));
+      a->part_out = nullptr;
+      a->part_out_elems = 0;
+      CUDA_TRY(cudaMalloc((void**)&a->part_out, elems * 8));
+      a->part_out_elems = elems;
+    }
+    if (!a->part_cursor) CUDA_TRY(cudaMalloc((void**)&a->part_cursor, kMaxPartitions * 4));
+    lean.part_out = a->part_out;
+    lean.part_cursor = a->part_cursor;
+    lean.part_cap = part_cap;
+    lean.part_bits = bits;
+    lean.part_shift = cap_log2 - bits;
+    memset(&pp, 0, sizeof(pp));
+    pp.tuples = a->part_out;
+    pp.cursor = a->part_cursor;
+    pp.part_cap = part_cap;
+    pp.gkeys = a->gkeys;
+    pp.gwords = a->gwords;
+    pp.gcap = a->gcap;
+    pp.flags = a->d_flags;
+    pp.n_parts = (uint32_t)P;
+    pp.n_fields = lean.s.n_fields;
+    pp.n_keys = lean.s.n_keys;
+    pp.n_gwords = lean.s.n_gwords;
+    pp.chunk = 2048;
+    pp.chunks_per_part = (uint32_t)((part_cap + pp.chunk - 1) / pp.chunk);
+    for (uint32_t i = 0; i < lean.s.n_code; ++i) {  // operand fields follow the order of the aggregates (lean_field_index)
+      const FInstr& in = lean.s.code[i];
+      if (in.op < FO_COUNT_STAR || in.op > FO_FIRSTNAN) continue;
+      PartOp& o = lean_takes_operand(in.op) ? pp.vops[pp.n_vops++] : pp.nops[pp.n_nops++];
+      o.op = in.op;
+      o.flags = in.a;
+      o.gword = in.c;
+    }
+    part_grid = (uint32_t)ctx->sm_count * 4u;
+    a->info.partitions = (uint32_t)P;
+  } else {
+    a->info.partitions = 0;
+  }
   a->pending.timed = ctx->timing;
   if (ctx->timing) CUDA_TRY(cudaEventRecord(ctx->ev0, ctx->stream));
   uint32_t launches = 0;
@@ -1956,7 +2084,13 @@ static int32_t agg_launch(llkv_gpu_agg* a, const llkv_gpu_program* prog, int app
       lean.first_tile = first_tile;
       lean.n_tiles = n_tiles;
       bool jitted = false;
+      if (partitioned) CUDA_TRY(cudaMemsetAsync(a->part_cursor, 0, kMaxPartitions * 4, ctx->stream));
       if (use_jit) CUDA_TRY(jit_launch(ctx->device, lean, (int)lean_ctas, (uint32_t)grid, ctx->stream, &jitted, nullptr));
+      if (partitioned) {
+        if (!jitted) return set_error(LLKV_ERR_INTERNAL, "the partitioned scan needs its specialised kernel");
+        CUDA_TRY(launch_partition_apply(pp, part_grid, ctx->stream));
+        ++launches;
+      }
       if (!jitted) CUDA_TRY(launch_lean(lean, (uint32_t)grid, ctx->stream));
       a->info.used_jit_kernel = jitted ? 1 : 0;
     } else {

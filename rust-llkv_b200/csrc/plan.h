@@ -110,6 +110,15 @@ enum FastOp : uint16_t {
   FO_FSUM, FO_MIN_I, FO_MAX_I, FO_MIN_F, FO_MAX_F, FO_FIRSTVALID, FO_FIRSTNAN,
   FO_COUNT_
 };
+#if defined(__CUDACC__) || defined(__CUDACC_RTC__)
+#define LLKV_HD __host__ __device__
+#else
+#define LLKV_HD
+#endif
+// aggregates whose update needs the row's operand value (the others need the row id or nothing)
+LLKV_HD constexpr bool lean_takes_operand(uint32_t op) {
+  return op == FO_SUM || op == FO_FSUM || op == FO_MIN_I || op == FO_MAX_I || op == FO_MIN_F || op == FO_MAX_F;
+}
 enum FastBin : uint8_t {
   FB_ADD = 0, FB_SUB, FB_MUL,   // 64-bit, proven not to overflow
   FB_MUL32,                      // both operands proven to fit i32
@@ -259,7 +268,14 @@ struct LeanShape {
   uint32_t slot_stride;  // bytes of one slot's accumulators (all consumer threads)
   uint32_t tile_rows, stages, stage_bytes, tx_bytes;
   uint32_t smem_bar_off, smem_stage_off, smem_acc_off, smem_tmp_off, smem_tbl_off, smem_total;
+  // Partitioned high-cardinality GROUP BY (specialised builds only): instead of updating the global table row by row
+  // (random DRAM sectors), the scan writes (key, row id, aggregate operands) tuples into hash partitions whose slice of the
+  // table fits in L2; partition_apply_kernel then folds one partition after the other.
+  uint32_t partition;      // 1: tuples out, no accumulation in this kernel
+  uint32_t n_fields;       // 64-bit fields per tuple: key, row id, one per aggregate that takes an operand
+  uint32_t smem_part_off;  // counters [3][kMaxPartitions + 1] u32, then the tile's tuples [n_fields][tile_rows] u64
 };
+constexpr int kMaxPartitions = 256;
 struct LeanPlan {
   LeanShape s;
   long long lits[kMaxLits];
@@ -274,6 +290,30 @@ struct LeanPlan {
   uint32_t* flags;
   unsigned long long row_origin;  // row id of position 0 (see Plan::row_origin)
   uint32_t n_noncommitted, _pad;
+  // partitioned GROUP BY: partition q's field f of tuple j is part_out[(q * n_fields + f) * part_cap + j]; part_cursor[q]
+  // counts the tuples reserved so far (tuples past part_cap are applied to the table directly by the scan)
+  unsigned long long* part_out;
+  uint32_t* part_cursor;
+  unsigned long long part_cap;
+  uint32_t part_bits, part_shift;  // partition = (mix64(key) & (gcap - 1)) >> part_shift, 2^part_bits partitions
+};
+
+// one aggregate of a partitioned plan as partition_apply_kernel sees it
+struct PartOp {
+  uint32_t op, flags, gword, _pad;
+};
+constexpr int kMaxPartOperands = 8;  // operand fields per tuple (tuple = key, row id, operands)
+struct PartPlan {
+  const unsigned long long* tuples;
+  const uint32_t* cursor;
+  unsigned long long part_cap;
+  unsigned long long* gkeys;
+  unsigned long long* gwords;
+  unsigned long long gcap;
+  uint32_t* flags;
+  uint32_t n_parts, n_fields, n_keys, n_gwords, n_nops, n_vops, chunk, chunks_per_part;
+  PartOp nops[kLeanMaxWords];       // aggregates without an operand (COUNT, first row)
+  PartOp vops[kMaxPartOperands];    // aggregates with one: vops[j] reads tuple field 2 + j
 };
 
 enum : uint32_t {

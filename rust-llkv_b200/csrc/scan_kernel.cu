@@ -913,7 +913,7 @@ __global__ void __launch_bounds__(512) scan_kernel(const Plan* __restrict__ gpla
 __global__ void init_table_kernel(u64* keys, u64* words, u64 rows, uint32_t n_gwords, const uint8_t* word_class_dev) {
   const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
   const u64 total = rows * n_gwords;
-  if (i < rows && keys) keys[i] = kEmptyKey;
+  if (keys && i + 2 < rows) keys[i] = kEmptyKey;  // `rows` counts the two spare rows (reserved key value, NULL key), which have no key slot
   for (u64 j = i; j < total; j += (u64)gridDim.x * blockDim.x) {
     const uint8_t c = word_class_dev[j % n_gwords];
     words[j] = (c == WC_MIN || c == WC_MIN128 || c == WC_PAIR_LO_MIN) ? ~0ull : 0ull;

@@ -52,6 +52,7 @@ def load():
         "llkv_gpu_ctx_set_timing": (i32, [vp, i32]),
         "llkv_gpu_ctx_set_tuning": (i32, [vp, i32, i32, i32, i32, i32]),
         "llkv_gpu_ctx_set_jit": (i32, [vp, i32]),
+        "llkv_gpu_ctx_set_partitioning": (i32, [vp, i32]),
         "llkv_gpu_debug_plan": (i32, [vp, i32, vp, i32, i32, u64, u64, vp, i32, vp, i32, vp, i32, i32, u64, i32, i32, i32, i32, i32,
                                        C.c_char_p, C.c_char_p, u64]),
         "llkv_gpu_host_alloc": (i32, [u64, P(vp)]),
@@ -150,6 +151,11 @@ class Context:
     def set_jit(self, mode: int):
         """0 = interpret the lean program, 1 = specialise a plan shape from its second run on (default), 2 = always."""
         _check(self.lib.llkv_gpu_ctx_set_jit(self.handle, mode))
+
+    def set_partitioning(self, mode: int):
+        """Partitioned high-cardinality GROUP BY: 0 = never, 1 = when the group table exceeds L2 (default), 2 = whenever
+        the plan allows it."""
+        _check(self.lib.llkv_gpu_ctx_set_partitioning(self.handle, mode))
 
     # ---- multi-GPU (NCCL over NVLink): the unique id travels through whatever the host uses for rendezvous
     def comm_unique_id(self) -> bytes:
@@ -386,7 +392,8 @@ def merge_partial_results(parts, rules):
 
 def debug_plan(table: HostTable, expr: Optional[Expr], specs: Sequence[AggregateSpec], snapshot: Optional[Snapshot] = None,
                group_by: Sequence[int] = (), expr_mode: Optional[int] = None, cardinality_hint: int = 0, block_threads: int = 0,
-               rows_per_thread: int = 0, stages: int = 0, ctas_per_sm: int = 0, jit: bool = False, cubin_path: Optional[str] = None) -> str:
+               rows_per_thread: int = 0, stages: int = 0, ctas_per_sm: int = 0, jit: bool = False, cubin_path: Optional[str] = None,
+               partition: bool = False) -> str:
     """llkv_gpu_debug_plan: compiles the plan against the host table's column statistics (no GPU needed) and returns the
     listing of the lean program; with jit=True the lean kernel is also specialised with NVRTC."""
     lib = load()
@@ -441,7 +448,7 @@ def debug_plan(table: HostTable, expr: Optional[Expr], specs: Sequence[Aggregate
         out = C.create_string_buffer(1 << 16)
         _check(lib.llkv_gpu_debug_plan(arr, len(host_cols), prog, created, deleted, snapshot.txn_id if snapshot else 0,
                                        snapshot.snapshot_id if snapshot else 0, aggs, n_aggs, anodes, n_anodes, keys, len(group_by), expr_mode,
-                                       cardinality_hint, block_threads, rows_per_thread, stages, ctas_per_sm, int(jit),
+                                       cardinality_hint, block_threads, rows_per_thread, stages, ctas_per_sm, int(jit) | (2 if partition else 0),
                                        cubin_path.encode() if cubin_path else None, out, len(out)))
         return out.value.decode()
     finally:

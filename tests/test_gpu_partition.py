@@ -1,0 +1,93 @@
+"""GPU: the partitioned high-cardinality GROUP BY (LeanTile::scatter + partition_apply_kernel) against the oracle and
+against the per-row global-table path: results must be identical whatever path runs."""
+import numpy as np
+import pytest
+
+import util
+from llkv_b200 import tpch
+from llkv_b200.expr import AggregateKind, AggregateSpec, BinaryOp, DataType, ScalarExpr
+from llkv_b200.table import HostColumn, HostTable, decimal_from_i64
+from oracle import oracle
+
+pytestmark = pytest.mark.gpu
+REL = 1e-12
+
+
+def run(gpu_ctx, dt, expr, specs, keys, hint, snap=None, lo=0, hi=None, part=2, cap=1 << 17):
+    from llkv_b200 import gpu
+    gpu_ctx.set_partitioning(part)
+    gpu_ctx.set_jit(2)
+    prog = gpu.Program(gpu_ctx, expr) if expr is not None else None
+    dt.set_snapshot(snap)
+    agg = gpu.Aggregation(dt, specs, keys, cardinality_hint=hint)
+    try:
+        agg.run(prog, snap is not None, lo, dt.n_rows if hi is None else hi)
+        got = agg.finalize(cap)
+        return got, agg.run_info()
+    finally:
+        agg.destroy()
+        if prog:
+            prog.destroy()
+        gpu_ctx.set_partitioning(1)
+        gpu_ctx.set_jit(1)
+
+
+def test_partitioned_matches_oracle_and_per_row_path(gpu_ctx):
+    from llkv_b200 import gpu
+    t = tpch.highcard_table(300_000, 50_000, seed=4)
+    dt = gpu.DeviceTable.from_host(gpu_ctx, t)
+    try:
+        want = oracle.aggregate(t, None, tpch.highcard_aggregates(), None, (tpch.K_FIELD,), group_capacity=1 << 17)
+        got, info = run(gpu_ctx, dt, None, tpch.highcard_aggregates(), (tpch.K_FIELD,), 50_000)
+        assert info.partitions >= 2 and info.used_jit_kernel == 1 and info.kernel_launches == 2
+        util.assert_same_result(got, want, REL)
+        direct, info0 = run(gpu_ctx, dt, None, tpch.highcard_aggregates(), (tpch.K_FIELD,), 50_000, part=0)
+        assert info0.partitions == 0
+        util.assert_same_result(direct, want, REL)
+        # ragged row ranges: first / last tiles partly selected
+        for lo, hi in ((1, 299_999), (12_345, 123_457), (0, 1), (77, 77)):
+            want = oracle.aggregate(t, None, tpch.highcard_aggregates(), None, (tpch.K_FIELD,), row_begin=lo, row_end=hi, group_capacity=1 << 17)
+            got, _ = run(gpu_ctx, dt, None, tpch.highcard_aggregates(), (tpch.K_FIELD,), 50_000, lo=lo, hi=hi)
+            util.assert_same_result(got, want, REL)
+    finally:
+        dt.destroy()
+
+
+def test_partition_overflow_goes_to_the_per_row_path(gpu_ctx):
+    """Half of the rows share one key: its partition fills up (capacity = uniform share + 25 %) and the surplus tuples are
+    applied by the scan itself."""
+    from llkv_b200 import gpu
+    rng = np.random.default_rng(11)
+    n = 400_000
+    k = rng.integers(0, 30_000, n, dtype=np.int64)
+    k[rng.random(n) < 0.5] = 4242
+    v = rng.integers(-1000, 1001, n, dtype=np.int64)
+    t = HostTable(1).add(HostColumn(tpch.K_FIELD, DataType.Int64, k)).add(HostColumn(tpch.V_FIELD, DataType.Int64, v))
+    specs = tpch.highcard_aggregates() + [AggregateSpec("lo", AggregateKind.Min(tpch.V_FIELD, DataType.Int64)),
+                                          AggregateSpec("hi", AggregateKind.Max(tpch.V_FIELD, DataType.Int64))]
+    dt = gpu.DeviceTable.from_host(gpu_ctx, t)
+    try:
+        want = oracle.aggregate(t, None, specs, None, (tpch.K_FIELD,), group_capacity=1 << 17)
+        got, info = run(gpu_ctx, dt, None, specs, (tpch.K_FIELD,), 30_000)
+        assert info.partitions >= 2
+        util.assert_same_result(got, want, REL)
+    finally:
+        dt.destroy()
+
+
+def test_partitioned_q1_shape_with_mvcc_and_filter(gpu_ctx):
+    """Q1's aggregates (exact decimal products, AVG, COUNT) grouped by a high-cardinality key, with the Q1 filter and an
+    MVCC snapshot in front: everything before GROUP runs as usual, only the accumulation is partitioned."""
+    from llkv_b200 import gpu
+    n = 120_000
+    t, snap = tpch.lineitem_table(n, seed=3, with_mvcc=True)
+    rng = np.random.default_rng(5)
+    t.add(HostColumn(900, DataType.Int64, rng.integers(-5_000, 5_000, n, dtype=np.int64)))
+    dt = gpu.DeviceTable.from_host(gpu_ctx, t)
+    try:
+        want = oracle.aggregate(t, tpch.q1_filter(), tpch.q1_aggregates(), snap, (900,), group_capacity=1 << 15)
+        got, info = run(gpu_ctx, dt, tpch.q1_filter(), tpch.q1_aggregates(), (900,), 10_000, snap=snap, cap=1 << 15)
+        assert info.partitions >= 2
+        util.assert_same_result(got, want, REL)
+    finally:
+        dt.destroy()

@@ -68,6 +68,7 @@ def test_random_plans_match_oracle(gpu_ctx, seed):
     t.add_mvcc(c_by, d_by)
     dt = device_table(gpu_ctx, t)
     lean_runs = 0
+    part_runs = 0
     try:
         for trial in range(5):
             f = random_filter(rng)
@@ -82,8 +83,11 @@ def test_random_plans_match_oracle(gpu_ctx, seed):
                 want = oracle.aggregate(t, f, specs, snap, keys, row_begin=lo, row_end=hi, group_capacity=1 << 15)
             except LlkvError as e:
                 want = e
-            for mode in (0, 2):
+            for mode, part in ((0, 1), (2, 1), (2, 2)):  # interpreted, specialised, specialised + partitioned GROUP BY
+                if part == 2 and hint <= 128:
+                    continue
                 gpu_ctx.set_jit(mode)
+                gpu_ctx.set_partitioning(part)
                 prog = gpu.Program(gpu_ctx, f) if f is not None else None
                 dt.set_snapshot(snap)
                 agg = gpu.Aggregation(dt, specs, keys, cardinality_hint=hint)
@@ -97,10 +101,11 @@ def test_random_plans_match_oracle(gpu_ctx, seed):
                         agg.run(prog, snap is not None, lo, hi)
                         got = agg.finalize(1 << 15)
                         lean_runs += agg.run_info().used_fast_kernel
+                        part_runs += 1 if agg.run_info().partitions else 0
                         try:
                             util.assert_same_result(got, want, REL)
                         except AssertionError as e:
-                            raise AssertionError(f"{ctx_note} jit={mode}: {e}") from e
+                            raise AssertionError(f"{ctx_note} jit={mode} partitioning={part}: {e}") from e
                 finally:
                     agg.destroy()
                     if prog:
@@ -108,4 +113,5 @@ def test_random_plans_match_oracle(gpu_ctx, seed):
         assert lean_runs >= 2  # the point of this test is the lean kernel (Int16 arguments stay on the general interpreter)
     finally:
         gpu_ctx.set_jit(1)
+        gpu_ctx.set_partitioning(1)
         dt.destroy()

@@ -33,7 +33,8 @@ def timed(dt, expr, specs, snap=None, group_by=(), hint=0, reps=4, cap=None):
 
 
 # ---- config 1: SELECT SUM(x) FROM t WHERE x BETWEEN a AND b, single Int64 column, 10 M rows, MVCC columns present
-for n in (10_000_000, 1_000_000_000 // 4):
+only4 = len(sys.argv) > 3 and sys.argv[3] == 'only4'
+for n in (() if only4 else (10_000_000, 1_000_000_000 // 4)):
     t, snap = tpch.int64_table(n, seed=1)
     x = t.columns[tpch.X_FIELD].values
     a, b = np.percentile(x[:1_000_000], [25, 75]).astype(np.int64)
@@ -56,5 +57,5 @@ t = HostTable(1).add(HostColumn(tpch.K_FIELD, DataType.Int64, k)).add(HostColumn
 dt = gpu.DeviceTable.from_host(ctx, t, chunk_rows=1 << 20)
 ms, info, _, n_groups = timed(dt, None, tpch.highcard_aggregates(), group_by=(tpch.K_FIELD,), hint=keys4, reps=3)
 kk = min(m[0] for m in ms[1:])
-print(f"config4 n={n4} keys={keys4}: groups={n_groups} kernel {kk:.3f} ms  {n4 / kk / 1e6:.2f} Grows/s  stream {16 * n4 / kk / 1e6:.0f} GB/s  fast={info.used_fast_kernel} jit={info.used_jit_kernel} launches={info.kernel_launches}", flush=True)
+print(f"config4 n={n4} keys={keys4}: groups={n_groups} kernel {kk:.3f} ms  {n4 / kk / 1e6:.2f} Grows/s  stream {16 * n4 / kk / 1e6:.0f} GB/s  fast={info.used_fast_kernel} jit={info.used_jit_kernel} launches={info.kernel_launches} partitions={info.partitions} all_ms={[round(m[0], 3) for m in ms]}", flush=True)
 assert n_groups == len(np.unique(k))
