@@ -2062,7 +2062,7 @@ static int32_t agg_launch(llkv_gpu_agg* a, const llkv_gpu_program* prog, int app
       o.flags = in.a;
       o.gword = in.c;
     }
-    part_grid = (uint32_t)ctx->sm_count * 4u;
+    part_grid = (uint32_t)ctx->sm_count;  // launch_partition_apply multiplies by the kernel's resident CTAs per SM
     a->info.partitions = (uint32_t)P;
   } else {
     a->info.partitions = 0;

@@ -12,24 +12,43 @@
 namespace llkv {
 
 constexpr int kPartThreads = 256;
-constexpr int kPartUnroll = 4;
 
-template <int NV>  // operand fields held in registers (>= pp.n_vops)
-__global__ void __launch_bounds__(kPartThreads, NV <= 2 ? 4 : 2) partition_apply_kernel(const __grid_constant__ PartPlan pp) {
+template <int NV, int kPartUnroll, int kMinBlocks>  // NV: operand fields held in registers (>= pp.n_vops)
+__global__ void __launch_bounds__(kPartThreads, kMinBlocks) partition_apply_kernel(const __grid_constant__ PartPlan pp) {
   constexpr int NVR = NV ? NV : 1;
   const u64 mask = pp.gcap - 1;
   const u64 cap = pp.part_cap;
   uint32_t errbits = 0;
-  const uint32_t items = pp.n_parts * pp.chunks_per_part;
+  // Work items = the filled chunks of all partitions, in partition order; CTA b takes items b, b + grid, ...  Every CTA
+  // gets the same number of chunks (+-1) and all of them sit in the same one or two partitions at any time, which is
+  // what keeps the table slice in L2.
+  __shared__ uint32_t s_first[kMaxPartitions + 1];  // first item of each partition
+  if (threadIdx.x == 0) {
+    uint32_t run = 0;
+    for (uint32_t q = 0; q < pp.n_parts; ++q) {
+      s_first[q] = run;
+      const u64 filled = pp.cursor[q];
+      const u64 n = filled < cap ? filled : cap;  // tuples past the capacity were applied by the scan itself
+      run += (uint32_t)((n + pp.chunk - 1) / pp.chunk);
+    }
+    s_first[pp.n_parts] = run;
+  }
+  __syncthreads();
+  const uint32_t items = s_first[pp.n_parts];
+  uint32_t q = 0;
   for (uint32_t item = blockIdx.x; item < items; item += gridDim.x) {
-    const uint32_t q = item / pp.chunks_per_part, c = item % pp.chunks_per_part;
+    while (item >= s_first[q + 1]) ++q;
+    const uint32_t c = item - s_first[q];
     const u64 filled = pp.cursor[q];
-    const u64 n = filled < cap ? filled : cap;  // tuples past the capacity were applied by the scan itself
+    const u64 n = filled < cap ? filled : cap;
     const u64 start = (u64)c * pp.chunk;
-    if (start >= n) continue;
     const u64 end = n < start + pp.chunk ? n : start + pp.chunk;
     const u64* base = pp.tuples + (u64)q * pp.n_fields * cap;
-    for (u64 i0 = start + threadIdx.x; i0 < end; i0 += (u64)kPartThreads * kPartUnroll) {
+    // The loop is warp-uniform and every phase reconverges (__syncwarp / __any_sync): a warp that stays split after the
+    // probe loop issues each coalesced tuple load once per fragment (measured: 3 fragments, 6x the tuple bytes from L2).
+    for (u64 b0 = start; b0 < end; b0 += (u64)kPartThreads * kPartUnroll) {
+      __syncwarp();
+      const u64 i0 = b0 + threadIdx.x;
       u64 K[kPartUnroll], row[kPartUnroll], fv[kPartUnroll][NVR], h[kPartUnroll], cur[kPartUnroll];
       bool on[kPartUnroll];
 #pragma unroll
@@ -41,36 +60,41 @@ __global__ void __launch_bounds__(kPartThreads, NV <= 2 ? 4 : 2) partition_apply
 #pragma unroll
         for (int j = 0; j < NV; ++j) fv[u][j] = (on[u] && j < (int)pp.n_vops) ? __ldcs(base + (u64)(2 + j) * cap + i) : 0ull;
       }
+      unsigned need = 0;  // bit u: tuple u still looks for its slot
 #pragma unroll
       for (int u = 0; u < kPartUnroll; ++u) {
-        h[u] = mix64(K[u]) & mask;
-        cur[u] = (K[u] != kEmptyKey && pp.n_keys) ? __ldcg(&pp.gkeys[h[u]]) : 0ull;
+        const bool probe = on[u] && K[u] != kEmptyKey && pp.n_keys != 0;
+        h[u] = probe ? (mix64(K[u]) & mask) : (pp.n_keys ? pp.gcap : 0ull);  // the reserved key value has its own row
+        cur[u] = probe ? __ldcg(&pp.gkeys[h[u]]) : 0ull;
+        need |= (unsigned)probe << u;
       }
+      // one probe step of every unresolved tuple per round: the next slots of a thread's tuples are requested together
+      u64 rounds = 0;
+      while (__any_sync(LLKV_FULL, need != 0)) {
 #pragma unroll
-      for (int u = 0; u < kPartUnroll; ++u) {
-        if (!on[u]) continue;
-        u64 gs = pp.gcap;  // the reserved key value has its own row
-        if (pp.n_keys == 0) gs = 0;
-        else if (K[u] != kEmptyKey) {
-          u64 hh = h[u], cc = cur[u], probes = 0;
-          while (true) {
-            if (cc == K[u]) break;
-            if (cc == kEmptyKey) {
-              const u64 old = atomicCAS(&pp.gkeys[hh], kEmptyKey, K[u]);
-              if (old == kEmptyKey || old == K[u]) break;
-            }
-            if (++probes > mask) {
-              errbits |= FLAG_TABLE_FULL;
-              hh = pp.gcap;
-              break;
-            }
-            hh = (hh + 1) & mask;
-            cc = __ldcg(&pp.gkeys[hh]);
+        for (int u = 0; u < kPartUnroll; ++u) {
+          if (!((need >> u) & 1u)) continue;
+          const u64 cc = cur[u];
+          bool done = cc == K[u];
+          if (!done && cc == kEmptyKey) {
+            const u64 old = atomicCAS(&pp.gkeys[h[u]], kEmptyKey, K[u]);
+            done = old == kEmptyKey || old == K[u];
           }
-          gs = hh;
+          if (done) need &= ~(1u << u);
+          else {
+            h[u] = (h[u] + 1) & mask;
+            cur[u] = __ldcg(&pp.gkeys[h[u]]);
+          }
         }
-        h[u] = gs;
+        if (++rounds > mask && need) {  // every slot seen: the table is full
+          errbits |= FLAG_TABLE_FULL;
+#pragma unroll
+          for (int u = 0; u < kPartUnroll; ++u)
+            if ((need >> u) & 1u) h[u] = pp.gcap;
+          need = 0;
+        }
       }
+      __syncwarp();
       // aggregate-major: the words of one group row share a sector, and back-to-back atomics on one sector queue up in
       // the L2 atomic unit; other tuples' updates go in between
       for (uint32_t k = 0; k < pp.n_nops; ++k) {
@@ -108,13 +132,24 @@ __global__ void __launch_bounds__(kPartThreads, NV <= 2 ? 4 : 2) partition_apply
 
 cudaError_t launch_partition_apply(const PartPlan& plan, uint32_t grid, cudaStream_t stream) {
   const uint32_t nv = plan.n_vops;
-  if (nv == 0) partition_apply_kernel<0><<<grid, kPartThreads, 0, stream>>>(plan);
-  else if (nv == 1) partition_apply_kernel<1><<<grid, kPartThreads, 0, stream>>>(plan);
-  else if (nv == 2) partition_apply_kernel<2><<<grid, kPartThreads, 0, stream>>>(plan);
-  else if (nv <= 4) partition_apply_kernel<4><<<grid, kPartThreads, 0, stream>>>(plan);
-  else if (nv <= kMaxPartOperands) partition_apply_kernel<kMaxPartOperands><<<grid, kPartThreads, 0, stream>>>(plan);
-  else return cudaErrorInvalidValue;
-  return cudaGetLastError();
+  int variant = 0;
+  if (const char* e = getenv("LLKV_GPU_PART_VARIANT")) variant = atoi(e);  // experiments
+  // grid = `sms` x the kernel's resident CTAs per SM (the caller passes grid = SM count): all CTAs are resident at once
+#define LLKV_PART_LAUNCH(NV, U, B)                                                \
+  do {                                                                            \
+    partition_apply_kernel<NV, U, B><<<grid * B, kPartThreads, 0, stream>>>(plan); \
+    return cudaGetLastError();                                                    \
+  } while (0)
+  if (nv == 0) LLKV_PART_LAUNCH(0, 4, 4);
+  if (nv == 1 && variant == 1) LLKV_PART_LAUNCH(1, 8, 2);
+  if (nv == 1 && variant == 2) LLKV_PART_LAUNCH(1, 2, 6);
+  if (nv == 1 && variant == 3) LLKV_PART_LAUNCH(1, 8, 3);
+  if (nv == 1) LLKV_PART_LAUNCH(1, 4, 4);
+  if (nv == 2) LLKV_PART_LAUNCH(2, 4, 4);
+  if (nv <= 4) LLKV_PART_LAUNCH(4, 4, 2);
+  if (nv <= kMaxPartOperands) LLKV_PART_LAUNCH(kMaxPartOperands, 4, 2);
+#undef LLKV_PART_LAUNCH
+  return cudaErrorInvalidValue;
 }
 
 }  // namespace llkv

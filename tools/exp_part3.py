@@ -10,16 +10,13 @@ rng = np.random.default_rng(4)
 k = rng.integers(0, keys, n, dtype=np.int64); v = rng.integers(0, 1001, n, dtype=np.int64)
 t = HostTable(1).add(HostColumn(tpch.K_FIELD, DataType.Int64, k)).add(HostColumn(tpch.V_FIELD, DataType.Int64, v))
 dt = gpu.DeviceTable.from_host(ctx, t, chunk_rows=1 << 20)
-for dbg in ("0", "1", "2", "3"):
-    os.environ["LLKV_GPU_PART_DEBUG"] = dbg
+for var in sys.argv[3].split(","):
+    os.environ["LLKV_GPU_PART_VARIANT"] = var
     agg = gpu.Aggregation(dt, tpch.highcard_aggregates(), (tpch.K_FIELD,), cardinality_hint=keys)
     ms = []
     for i in range(3):
-        agg.reset(); agg.run(None, False); agg._resolve() if hasattr(agg, "_resolve") else None
-        try:
-            g = agg.group_count()
-        except Exception as e:
-            g = repr(e)[:60]
+        agg.reset(); agg.run(None, False)
+        g = agg.group_count()
         ms.append(round(agg.run_info().last_kernel_ms, 3))
-    print(f"keys={keys} debug={dbg} groups={g} ms={ms}", flush=True)
+    print(f"keys={keys} variant={var} groups={g} ms={ms}", flush=True)
     agg.destroy()
