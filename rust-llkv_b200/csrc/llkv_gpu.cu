@@ -2023,7 +2023,9 @@ static int32_t agg_launch(llkv_gpu_agg* a, const llkv_gpu_program* prog, int app
     while (bits < 8 && (table_bytes >> bits) > (slice_mb << 20)) ++bits;
     if (bits + 3 > cap_log2) bits = cap_log2 > 3 ? cap_log2 - 3 : 1;
     const u64 P = 1ull << bits;
-    max_rows_per_launch = std::min<u64>(max_rows_per_launch, 1ull << 28) / p.tile_rows * p.tile_rows;
+    u64 batch_rows = 1ull << 28;
+    if (const char* e = getenv("LLKV_GPU_PART_BATCH_ROWS")) batch_rows = std::max<u64>(p.tile_rows, strtoull(e, nullptr, 10));  // tests: several launches on small tables
+    max_rows_per_launch = std::max<u64>(p.tile_rows, std::min<u64>(max_rows_per_launch, batch_rows) / p.tile_rows * p.tile_rows);
     const u64 launch_rows = std::min<u64>(row_end - row_begin + p.tile_rows, max_rows_per_launch);
     const u64 part_cap = (launch_rows / P + launch_rows / (4 * P) + 1024 + 15) / 16 * 16;
     const size_t elems = (size_t)(P * lean.s.n_fields * part_cap);

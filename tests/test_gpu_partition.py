@@ -53,6 +53,22 @@ def test_partitioned_matches_oracle_and_per_row_path(gpu_ctx):
         dt.destroy()
 
 
+def test_partitioned_scan_in_several_launches(gpu_ctx, monkeypatch):
+    """Long scans run as a sequence of (scan, apply) launch pairs over bounded tuple buffers (2^28 rows each); here the
+    bound is lowered so a small table takes five of them."""
+    from llkv_b200 import gpu
+    monkeypatch.setenv("LLKV_GPU_PART_BATCH_ROWS", "70000")
+    t = tpch.highcard_table(300_000, 40_000, seed=9)
+    dt = gpu.DeviceTable.from_host(gpu_ctx, t)
+    try:
+        want = oracle.aggregate(t, None, tpch.highcard_aggregates(), None, (tpch.K_FIELD,), group_capacity=1 << 17)
+        got, info = run(gpu_ctx, dt, None, tpch.highcard_aggregates(), (tpch.K_FIELD,), 40_000)
+        assert info.partitions >= 2 and info.kernel_launches >= 8
+        util.assert_same_result(got, want, REL)
+    finally:
+        dt.destroy()
+
+
 def test_partition_overflow_goes_to_the_per_row_path(gpu_ctx):
     """Half of the rows share one key: its partition fills up (capacity = uniform share + 25 %) and the surplus tuples are
     applied by the scan itself."""

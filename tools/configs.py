@@ -50,12 +50,31 @@ for n in (() if only4 else (10_000_000, 1_000_000_000 // 4)):
     del t, x
 
 # ---- config 4: high-cardinality GROUP BY (keys4 distinct Int64 keys, SUM + COUNT) over n4 rows
+# (the table is generated and uploaded in pieces of 2^26 rows: the 1 B-row configuration is 16 GB of input)
 rng = np.random.default_rng(4)
-k = rng.integers(0, keys4, n4, dtype=np.int64)
-v = rng.integers(0, 1001, n4, dtype=np.int64)
-t = HostTable(1).add(HostColumn(tpch.K_FIELD, DataType.Int64, k)).add(HostColumn(tpch.V_FIELD, DataType.Int64, v))
-dt = gpu.DeviceTable.from_host(ctx, t, chunk_rows=1 << 20)
-ms, info, _, n_groups = timed(dt, None, tpch.highcard_aggregates(), group_by=(tpch.K_FIELD,), hint=keys4, reps=3)
-kk = min(m[0] for m in ms[1:])
-print(f"config4 n={n4} keys={keys4}: groups={n_groups} kernel {kk:.3f} ms  {n4 / kk / 1e6:.2f} Grows/s  stream {16 * n4 / kk / 1e6:.0f} GB/s  fast={info.used_fast_kernel} jit={info.used_jit_kernel} launches={info.kernel_launches} partitions={info.partitions} all_ms={[round(m[0], 3) for m in ms]}", flush=True)
-assert n_groups == len(np.unique(k))
+piece = 1 << 26
+dt = gpu.DeviceTable(ctx, 1)
+cols = {}
+seen = np.zeros(keys4, dtype=bool)
+for lo in range(0, n4, piece):
+    m = min(piece, n4 - lo)
+    k = rng.integers(0, keys4, m, dtype=np.int64)
+    v = rng.integers(0, 1001, m, dtype=np.int64)
+    seen[k] = True
+    for fid, arr in ((tpch.K_FIELD, k), (tpch.V_FIELD, v)):
+        hc = HostColumn(fid, DataType.Int64, arr)
+        if fid not in cols:
+            cols[fid] = gpu.DeviceColumn(ctx, gpu.logical_field_id(1, fid), hc)
+            cols[fid].reserve(n4)
+            dt.columns[fid] = cols[fid]
+        cols[fid].append(hc, 1 << 20, row_id_base=lo)
+dt.n_rows = n4
+dt.seal()
+n_unique = int(seen.sum())
+del k, v, seen
+for part_mode in ((0, 1) if len(sys.argv) > 4 and sys.argv[4] == 'both' else (1,)):
+    ctx.set_partitioning(part_mode)
+    ms, info, _, n_groups = timed(dt, None, tpch.highcard_aggregates(), group_by=(tpch.K_FIELD,), hint=keys4, reps=3)
+    kk = min(m[0] for m in ms[1:])
+    print(f"config4 n={n4} keys={keys4} partitioning={part_mode}: groups={n_groups} kernel {kk:.3f} ms  {n4 / kk / 1e6:.2f} Grows/s  stream {16 * n4 / kk / 1e6:.0f} GB/s  fast={info.used_fast_kernel} jit={info.used_jit_kernel} launches={info.kernel_launches} partitions={info.partitions} all_ms={[round(m[0], 3) for m in ms]}", flush=True)
+    assert n_groups == n_unique
