@@ -276,7 +276,38 @@ def run_ours(args):
     d2h = 4 + 3 * 6 * 8  # status word + the ungrouped state row (6 words) and its two spare rows, read back by finalize
     agg.destroy()
     prog.destroy()
-    clocks = sampler.stop() if rank == 0 else None  # sampled across the three timed regions (Q6, Q1, end to end)
+    # ---- BASELINE.json configs[3] at a bounded size (one GPU only): high-cardinality GROUP BY, 10 M distinct Int64 keys,
+    # SUM + COUNT.  Kernel time only (CUDA events around the scan + apply launches): reading 10 M groups back is not part
+    # of the hot path.  Both forms: partitioned (default once the group table exceeds L2) and the per-row global table.
+    highcard = None
+    if world == 1 and not args.no_highcard:
+        hc_rows, hc_keys = (1 << 26, 10_000_000) if n >= 20_000_000 else (1 << 22, 2_000_000)
+        rng = np.random.default_rng(4)
+        hk = rng.integers(0, hc_keys, hc_rows, dtype=np.int64)
+        ht = HostTable(2).add(HostColumn(tpch.K_FIELD, DataType.Int64, hk)).add(
+            HostColumn(tpch.V_FIELD, DataType.Int64, rng.integers(0, 1001, hc_rows, dtype=np.int64)))
+        n_unique = int(np.unique(hk).size)
+        hdt = gpu.DeviceTable.from_host(ctx, ht, chunk_rows=1 << 20)
+        del hk, ht
+        highcard = {"workload": f"GROUP BY over {hc_keys} distinct Int64 keys, SUM + COUNT, {hc_rows} rows (BASELINE.json configs[3] at a bounded size)",
+                    "rows": hc_rows, "keys": hc_keys, "unit": UNIT}
+        for name, mode in (("partitioned", 2), ("per_row", 0)):
+            ctx.set_partitioning(mode)
+            hagg = gpu.Aggregation(hdt, tpch.highcard_aggregates(), (tpch.K_FIELD,), cardinality_hint=hc_keys)
+            ms = []
+            for i in range(4):
+                hagg.reset()
+                hagg.run(None, False, 0, hc_rows)
+                groups = hagg.group_count()
+                if i:
+                    ms.append(hagg.run_info().last_kernel_ms)
+            hinfo = hagg.run_info()
+            hagg.destroy()
+            highcard[name] = {"kernel_ms": statistics.mean(ms), "value": hc_rows / (statistics.mean(ms) * 1e-3), "groups": groups,
+                              "groups_expected": n_unique, "partitions": hinfo.partitions, "launches_per_run": hinfo.kernel_launches}
+        ctx.set_partitioning(1)
+        hdt.destroy()
+    clocks = sampler.stop() if rank == 0 else None  # sampled across the timed regions (Q6, Q1, end to end, high cardinality)
 
     if rank == 0:
         peak, peak_src = measured_peak()
@@ -332,6 +363,8 @@ def run_ours(args):
                                                                   "rows_per_tile": q1["info"].rows_per_tile, "stages": q1["info"].stages,
                                                                   "smem_bytes": q1["info"].smem_bytes, "fast_groups": q1["info"].fast_groups,
                                                                   "wide": q1["info"].used_wide_path}}
+        if highcard is not None:
+            line["highcard"] = highcard
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(seed=6)
         print(json.dumps(line), flush=True)
@@ -406,6 +439,7 @@ def main():
     ap.add_argument("--rows", type=int, default=0, help="override the row count per GPU (smoke runs)")
     ap.add_argument("--no-q1", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-highcard", action="store_true")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3

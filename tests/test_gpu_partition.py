@@ -107,3 +107,19 @@ def test_partitioned_q1_shape_with_mvcc_and_filter(gpu_ctx):
         util.assert_same_result(got, want, REL)
     finally:
         dt.destroy()
+
+
+@pytest.mark.parametrize("hint", [131_072, 250_000, 1_048_576])
+def test_group_table_sizes_that_end_on_an_allocation_boundary(gpu_ctx, hint):
+    """2^k slots x 8 B of keys end exactly on a 2 MiB / 4 MiB / 16 MiB boundary: initialising the table must not touch the
+    key array past its end (the two spare rows have accumulator words but no key slot)."""
+    from llkv_b200 import gpu
+    t = tpch.highcard_table(50_000, 10_000, seed=2)
+    dt = gpu.DeviceTable.from_host(gpu_ctx, t)
+    try:
+        want = oracle.aggregate(t, None, tpch.highcard_aggregates(), None, (tpch.K_FIELD,), group_capacity=1 << 17)
+        for part in (0, 2):
+            got, _ = run(gpu_ctx, dt, None, tpch.highcard_aggregates(), (tpch.K_FIELD,), hint, part=part)
+            util.assert_same_result(got, want, REL)
+    finally:
+        dt.destroy()

@@ -9,7 +9,10 @@ import subprocess
 import pytest
 
 from llkv_b200 import gpu, tpch
-from llkv_b200.expr import Expr
+import numpy as np
+
+from llkv_b200.expr import AggregateKind, AggregateSpec, DataType, Expr
+from llkv_b200.table import HostColumn, HostTable
 
 
 @pytest.fixture(scope="module")
@@ -86,3 +89,29 @@ def test_specialised_kernel_compiles_for_sm_100a(lineitem, tmp_path, query):
     assert int(usage.split("STACK:")[1].split()[0]) == 0
     if query == "q6":
         assert "ATOMS" not in sass  # ungrouped: thread-private accumulators, no shared-memory atomics at all
+
+
+@pytest.mark.skipif(not _nvrtc_available(), reason="NVRTC is not installed")
+def test_partitioned_scan_compiles_for_sm_100a(tmp_path):
+    """The partitioned form of a high-cardinality GROUP BY: the specialised scan stages tuples in shared memory (consumer
+    barrier 1), reserves partition space with one global atomic per partition and tile, and writes streaming stores."""
+    t = tpch.highcard_table(50_000, 20_000, seed=4)
+    cubin = str(tmp_path / "part.cubin")
+    text = gpu.debug_plan(t, None, tpch.highcard_aggregates(), group_by=(tpch.K_FIELD,), cardinality_hint=20_000, jit=True, partition=True,
+                          cubin_path=cubin)
+    assert "partitioned: 3 fields per tuple" in text and "specialised cubin:" in text
+    plain = gpu.debug_plan(t, None, tpch.highcard_aggregates(), group_by=(tpch.K_FIELD,), cardinality_hint=20_000)
+    assert "partitioned" not in plain
+    # a plan whose aggregate masks depend on the values (f64 MIN ignores NaN) keeps the per-row path
+    tf = HostTable(1).add(HostColumn(tpch.K_FIELD, DataType.Int64, np.arange(100, dtype=np.int64))).add(
+        HostColumn(tpch.V_FIELD, DataType.Float64, np.arange(100, dtype=np.float64)))
+    nan_dependent = gpu.debug_plan(tf, None, [AggregateSpec("m", AggregateKind.Min(tpch.V_FIELD, DataType.Float64))], group_by=(tpch.K_FIELD,),
+                                   cardinality_hint=20_000, partition=True)
+    assert "partitioned" not in nan_dependent
+    cuobjdump = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(cuobjdump):
+        return
+    sass = subprocess.run([cuobjdump, "-sass", cubin], capture_output=True, text=True, check=True).stdout
+    assert "UBLKCP" in sass and "BAR.SYNC" in sass and "ATOMS.ADD" in sass and "ATOMG.E.ADD" in sass and "STG.E.EF.64" in sass
+    usage = subprocess.run([cuobjdump, "-res-usage", cubin], capture_output=True, text=True, check=True).stdout
+    assert int(usage.split("STACK:")[1].split()[0]) == 0
