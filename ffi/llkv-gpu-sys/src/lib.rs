@@ -84,6 +84,42 @@ pub struct llkv_group_key {
     pub _pad: [u8; 3],
 }
 
+/// ChunkMetadata (llkv-column-map/src/store/descriptor.rs:23-32).
+#[repr(C)]
+#[derive(Clone, Copy, Default, Debug)]
+pub struct llkv_chunk_metadata {
+    pub chunk_pk: u64,
+    pub value_order_perm_pk: u64,
+    pub row_count: u64,
+    pub serialized_bytes: u64,
+    pub min_val_u64: u64,
+    pub max_val_u64: u64,
+    pub null_count: u64,
+    pub distinct_count: u64,
+}
+
+/// ColumnDescriptor, fixed part (descriptor.rs:87-98).
+#[repr(C)]
+#[derive(Clone, Copy, Default, Debug)]
+pub struct llkv_column_descriptor {
+    pub field_id: u64,
+    pub head_page_pk: u64,
+    pub tail_page_pk: u64,
+    pub total_row_count: u64,
+    pub total_chunk_count: u64,
+    pub data_type_code: u32,
+    pub index_meta_len: u32,
+}
+
+/// std::ops::Bound over raw value bits (kind: LLKV_BOUND_INCLUDED 0, LLKV_BOUND_EXCLUDED 1, LLKV_BOUND_UNBOUNDED 2).
+#[repr(C)]
+#[derive(Clone, Copy, Default)]
+pub struct llkv_range_bound {
+    pub kind: i32,
+    pub _pad: i32,
+    pub value_bits: u64,
+}
+
 #[repr(C)]
 #[derive(Clone, Copy, Default)]
 pub struct llkv_run_info {
@@ -140,6 +176,11 @@ extern "C" {
     pub fn llkv_gpu_ctx_set_partitioning(ctx: *mut llkv_gpu_ctx, mode: i32) -> i32;
     pub fn llkv_gpu_host_alloc(bytes: u64, out: *mut *mut c_void) -> i32;
     pub fn llkv_gpu_host_free(p: *mut c_void) -> i32;
+
+    pub fn llkv_gpu_descriptor_parse(bytes: *const c_void, len: u64, out: *mut llkv_column_descriptor) -> i32;
+    pub fn llkv_gpu_descriptor_page_parse(bytes: *const c_void, len: u64, next_page_pk: *mut u64, out: *mut llkv_chunk_metadata, capacity: u64, n_entries: *mut u64) -> i32;
+    pub fn llkv_gpu_sortable_u64(prim_type: i32, value_bits: u64) -> u64;
+    pub fn llkv_gpu_chunk_overlaps(prim_type: i32, chunk_min_u64: u64, chunk_max_u64: u64, lower: *const llkv_range_bound, upper: *const llkv_range_bound) -> i32;
 
     pub fn llkv_gpu_column_register(ctx: *mut llkv_gpu_ctx, logical_field_id: u64, prim_type: i32, precision: u8, scale: i8, out: *mut *mut llkv_gpu_column) -> i32;
     pub fn llkv_gpu_column_reserve(col: *mut llkv_gpu_column, n_rows: u64) -> i32;

@@ -273,6 +273,62 @@ int32_t llkv_gpu_ctx_set_partitioning(llkv_gpu_ctx* ctx, int32_t mode);
 int32_t llkv_gpu_host_alloc(uint64_t bytes, void** out);
 int32_t llkv_gpu_host_free(void* p);
 
+/* ---- column metadata in front of the scan (host only, no device work): the descriptor walk of
+ * llkv-column-map/src/store/scan/unsorted.rs:202-241.  The caller fetches the blobs (ColumnCatalog -> descriptor pk ->
+ * page chain, one Pager::batch_get per page, llkv-column-map/src/store/descriptor.rs:380-444), these entries read them;
+ * the chunk pks they return are what the caller then fetches in one batched get and hands to
+ * llkv_gpu_column_append_blob. ---- */
+
+/* ChunkMetadata (llkv-column-map/src/store/descriptor.rs:23-32): 64 bytes little endian on disk. */
+typedef struct llkv_chunk_metadata {
+  uint64_t chunk_pk;
+  uint64_t value_order_perm_pk; /* 0 = none */
+  uint64_t row_count;
+  uint64_t serialized_bytes;
+  uint64_t min_val_u64; /* order-preserving u64 image of the chunk's minimum (llkv_gpu_sortable_u64) */
+  uint64_t max_val_u64;
+  uint64_t null_count;
+  uint64_t distinct_count;
+} llkv_chunk_metadata;
+
+/* ColumnDescriptor (descriptor.rs:87-98; from_le_bytes :263-299).  The index metadata bytes follow the fixed part in
+ * the blob at offset 52 (index_meta_len of them). */
+typedef struct llkv_column_descriptor {
+  uint64_t field_id; /* LogicalFieldId as u64 */
+  uint64_t head_page_pk;
+  uint64_t tail_page_pk;
+  uint64_t total_row_count;
+  uint64_t total_chunk_count;
+  uint32_t data_type_code; /* 0 = unknown (older files) */
+  uint32_t index_meta_len;
+} llkv_column_descriptor;
+
+int32_t llkv_gpu_descriptor_parse(const void* bytes, uint64_t len, llkv_column_descriptor* out);
+
+/* One descriptor page: DescriptorPageHeader {next_page_pk u64, entry_count u32, 4 bytes padding} followed by
+ * entry_count packed ChunkMetadata (descriptor.rs:344-378).  *next_page_pk == 0 ends the chain.  LLKV_ERR_IO when the
+ * blob is shorter than its header says (a truncated page), LLKV_ERR_INVALID_ARGUMENT when `capacity` is too small
+ * (*n_entries then holds the count; a page holds at most 256 entries, store/constants.rs:14). */
+int32_t llkv_gpu_descriptor_page_parse(const void* bytes, uint64_t len, uint64_t* next_page_pk, llkv_chunk_metadata* out,
+                                       uint64_t capacity, uint64_t* n_entries);
+
+/* Order-preserving u64 image of a value given as raw bits in the low bytes (llkv-column-map/src/codecs.rs:33-65:
+ * signed integers and dates flip the sign bit of their own width, floats use the sign-flip trick (Float32 through f64),
+ * unsigned integers are themselves). */
+uint64_t llkv_gpu_sortable_u64(int32_t prim_type, uint64_t value_bits);
+
+typedef struct llkv_range_bound {
+  int32_t kind;        /* LLKV_BOUND_* (std::ops::Bound; the same codes as llkv_eval_op ranges) */
+  int32_t _pad;
+  uint64_t value_bits; /* raw bits of the bound in the column's type */
+} llkv_range_bound;
+
+/* IntRanges::matches for the range of one type (llkv-column-map/src/store/pruning.rs:104-258): 1 when a chunk whose
+ * metadata says [chunk_min_u64, chunk_max_u64] may hold rows inside (lower, upper), 0 when it cannot (the scan skips
+ * the chunk).  NULL bounds mean Unbounded. */
+int32_t llkv_gpu_chunk_overlaps(int32_t prim_type, uint64_t chunk_min_u64, uint64_t chunk_max_u64, const llkv_range_bound* lower,
+                                const llkv_range_bound* upper);
+
 /* ---- columns: ColumnStore::append / scan source (llkv-column-map/src/store/core.rs:787, scan/mod.rs:191) ---- */
 int32_t llkv_gpu_column_register(llkv_gpu_ctx* ctx, uint64_t logical_field_id, int32_t prim_type, uint8_t precision,
                                  int8_t scale, llkv_gpu_column** out);

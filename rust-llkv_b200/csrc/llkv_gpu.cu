@@ -50,6 +50,7 @@ static int32_t set_error(int32_t code, const char* fmt, ...) {
   g_last_error = buf;
   return code;
 }
+int32_t llkv_set_error_message(int32_t code, const char* msg) { return set_error(code, "%s", msg); }  // for descriptor.cpp
 #define CUDA_TRY(expr)                                                                                          \
   do {                                                                                                          \
     cudaError_t _e = (expr);                                                                                    \

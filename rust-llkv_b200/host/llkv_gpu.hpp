@@ -448,6 +448,30 @@ inline FlatAggregates flatten_aggregates(const std::vector<AggregateSpec>& specs
 // LogicalFieldId packing (llkv-types/src/ids.rs:133-152): namespace << 48 | table << 32 | field
 inline uint64_t logical_field_id(uint64_t table_id, uint64_t field_id, uint64_t ns = 0) { return (ns << 48) | ((table_id & 0xffff) << 32) | (field_id & 0xffffffffull); }
 
+// ------------------------------------------------------------------------------------------------ column metadata
+// The descriptor walk of unsorted_visit (llkv-column-map/src/store/scan/unsorted.rs:202-241): `batch_get` is the pager
+// (key -> blob); returns the ChunkMetadata of every chunk the scan has to read, in scan order.  `lower` / `upper` prune
+// with IntRanges::matches (store/pruning.rs:104-258).
+template <class BatchGet>  // std::string-like blob = batch_get(uint64_t physical_key)
+inline std::vector<llkv_chunk_metadata> walk_descriptor(BatchGet&& batch_get, uint64_t descriptor_pk, llkv_column_descriptor* descriptor_out = nullptr,
+                                                        int32_t prim_type = 0, const llkv_range_bound* lower = nullptr,
+                                                        const llkv_range_bound* upper = nullptr) {
+  const auto desc_blob = batch_get(descriptor_pk);
+  llkv_column_descriptor desc;
+  check(llkv_gpu_descriptor_parse(desc_blob.data(), desc_blob.size(), &desc));
+  if (descriptor_out) *descriptor_out = desc;
+  std::vector<llkv_chunk_metadata> metas;
+  llkv_chunk_metadata page[256];  // DESCRIPTOR_ENTRIES_PER_PAGE (store/constants.rs:14)
+  for (uint64_t pk = desc.head_page_pk; pk;) {
+    const auto blob = batch_get(pk);
+    uint64_t n = 0;
+    check(llkv_gpu_descriptor_page_parse(blob.data(), blob.size(), &pk, page, 256, &n));
+    for (uint64_t i = 0; i < n; ++i)
+      if (page[i].row_count > 0 && llkv_gpu_chunk_overlaps(prim_type, page[i].min_val_u64, page[i].max_val_u64, lower, upper)) metas.push_back(page[i]);
+  }
+  return metas;
+}
+
 // ------------------------------------------------------------------------------------------------ RAII owners of the ABI handles
 class Context {
  public:

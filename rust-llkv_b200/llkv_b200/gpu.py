@@ -55,6 +55,10 @@ def load():
         "llkv_gpu_ctx_set_partitioning": (i32, [vp, i32]),
         "llkv_gpu_debug_plan": (i32, [vp, i32, vp, i32, i32, u64, u64, vp, i32, vp, i32, vp, i32, i32, u64, i32, i32, i32, i32, i32,
                                        C.c_char_p, C.c_char_p, u64]),
+        "llkv_gpu_descriptor_parse": (i32, [vp, u64, vp]),
+        "llkv_gpu_descriptor_page_parse": (i32, [vp, u64, P(u64), vp, u64, P(u64)]),
+        "llkv_gpu_sortable_u64": (u64, [i32, u64]),
+        "llkv_gpu_chunk_overlaps": (i32, [i32, u64, u64, vp, vp]),
         "llkv_gpu_host_alloc": (i32, [u64, P(vp)]),
         "llkv_gpu_host_free": (i32, [vp]),
         "llkv_gpu_column_register": (i32, [vp, u64, i32, u8, i8, P(vp)]),
