@@ -138,7 +138,7 @@ pub struct llkv_run_info {
     pub used_fast_kernel: u32,
     pub used_jit_kernel: u32,
     pub partitions: u32,
-    pub _pad: u32,
+    pub tiles_pruned: u32,
 }
 
 #[repr(C)]
@@ -174,6 +174,7 @@ extern "C" {
     pub fn llkv_gpu_ctx_set_tuning(ctx: *mut llkv_gpu_ctx, ctas_per_sm: i32, block_threads: i32, stages: i32, rows_per_thread: i32, force_wide: i32) -> i32;
     pub fn llkv_gpu_ctx_set_jit(ctx: *mut llkv_gpu_ctx, mode: i32) -> i32;
     pub fn llkv_gpu_ctx_set_partitioning(ctx: *mut llkv_gpu_ctx, mode: i32) -> i32;
+    pub fn llkv_gpu_ctx_set_pruning(ctx: *mut llkv_gpu_ctx, mode: i32) -> i32;
     pub fn llkv_gpu_host_alloc(bytes: u64, out: *mut *mut c_void) -> i32;
     pub fn llkv_gpu_host_free(p: *mut c_void) -> i32;
 

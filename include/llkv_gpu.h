@@ -226,7 +226,7 @@ typedef struct llkv_run_info {
   uint32_t used_fast_kernel;    /* 1 when the lean kernel (lean_kernel.cuh) ran, 0 for the general interpreter */
   uint32_t used_jit_kernel;     /* 1 when the lean kernel ran as a build specialised on this plan shape (jit.cpp) */
   uint32_t partitions;          /* hash partitions of a partitioned high-cardinality GROUP BY run, 0 = not partitioned */
-  uint32_t _pad;
+  uint32_t tiles_pruned;        /* tiles the scan skipped because no conjunct range predicate can match their zones */
 } llkv_run_info;
 
 typedef struct llkv_gpu_ctx llkv_gpu_ctx;
@@ -268,6 +268,15 @@ int32_t llkv_gpu_ctx_set_jit(llkv_gpu_ctx* ctx, int32_t mode);
  * random access).  mode: 0 = never, 1 = when the table exceeds L2 and the scan is long enough (default), 2 = whenever
  * the plan allows it (tests).  Results are identical in every mode.  Needs the specialised kernel (jit mode != 0). */
 int32_t llkv_gpu_ctx_set_partitioning(llkv_gpu_ctx* ctx, int32_t mode);
+
+/* Zone-map pruning on the device-resident image — the chunk skip of the reference's scans (ChunkMetadata min/max against
+ * the predicate range, llkv-column-map/src/store/pruning.rs:104-258, scan/unsorted.rs:222-227) at a granularity of 4096
+ * rows, with Decimal128 columns included (the reference keeps no statistics for them, store/core.rs:1029-1032).  Minima /
+ * maxima per zone are computed on the device the first time they are wanted; a fused scan whose filter is a conjunction
+ * containing range predicates then visits only the tiles whose zones can match.  mode: 0 = never, 1 = for columns scanned
+ * again without having changed, when at least 1/8 of the tiles drop out (default), 2 = from the first scan, whenever any
+ * tile drops out (tests).  Results are identical in every mode. */
+int32_t llkv_gpu_ctx_set_pruning(llkv_gpu_ctx* ctx, int32_t mode);
 
 /* Page-locked host memory so chunk uploads DMA straight from the caller's buffer. */
 int32_t llkv_gpu_host_alloc(uint64_t bytes, void** out);

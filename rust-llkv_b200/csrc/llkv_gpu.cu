@@ -108,6 +108,32 @@ __global__ void stats_dec_kernel(const ulonglong2* __restrict__ v, u64 n, DevSta
     if (bad) atomicOr(&st->not_i64, 1u);
   }
 }
+// Zone maps: one warp per zone of kZoneRows rows, minimum and maximum as the 64-bit value a lean-kernel leaf compares
+// (sign- or zero-extended; STRIDE = 2 reads the low half of a Decimal128 that holds a sign-extended i64).
+template <typename T, bool SIGNED, int STRIDE>
+__global__ void zone_minmax_kernel(const T* __restrict__ v, u64 n, u64* __restrict__ zones) {
+  const u64 n_zones = (n + kZoneRows - 1) / kZoneRows;
+  const u64 warps = ((u64)gridDim.x * blockDim.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  for (u64 z = ((u64)blockIdx.x * blockDim.x + threadIdx.x) >> 5; z < n_zones; z += warps) {
+    const u64 lo = z * kZoneRows, hi = lo + kZoneRows < n ? lo + kZoneRows : n;
+    u64 mn = ~0ull, mx = 0ull;  // in the order-preserving image
+    for (u64 i = lo + lane; i < hi; i += 32) {
+      const u64 e = SIGNED ? ((u64)(i64)v[i * STRIDE] ^ 0x8000000000000000ull) : (u64)v[i * STRIDE];
+      mn = e < mn ? e : mn;
+      mx = e > mx ? e : mx;
+    }
+    for (int o = 16; o; o >>= 1) {
+      const u64 a = __shfl_xor_sync(0xffffffffu, mn, o), b = __shfl_xor_sync(0xffffffffu, mx, o);
+      mn = a < mn ? a : mn;
+      mx = b > mx ? b : mx;
+    }
+    if (lane == 0) {
+      zones[2 * z] = SIGNED ? (mn ^ 0x8000000000000000ull) : mn;
+      zones[2 * z + 1] = SIGNED ? (mx ^ 0x8000000000000000ull) : mx;
+    }
+  }
+}
 // Utf8 (offsets + data) -> packed short-string keys: bytes big-endian from the top byte, length in the low byte
 __global__ void pack_utf8_kernel(const int* __restrict__ off, const unsigned char* __restrict__ data, u64 n, u64* __restrict__ out,
                                  DevStats* st) {
@@ -245,6 +271,7 @@ struct llkv_gpu_ctx {
   int tune_ctas = 0, tune_block = 0, tune_stages = 0, tune_rpt = 0, tune_force_wide = 0;
   int jit_mode = 1;  // 0 never, 1 specialise a plan shape from its second run on, 2 always
   int partition_mode = 1;  // partitioned high-cardinality GROUP BY: 0 never, 1 when the table exceeds L2, 2 whenever possible
+  int prune_mode = 1;      // zone-map tile skipping: 0 never, 1 columns scanned again unchanged + >= 1/8 of the tiles, 2 always
   std::map<std::string, uint32_t> shape_runs;
   bool keep_wide_decimals = false;  // LLKV_GPU_KEEP_WIDE_DECIMALS=1: never narrow Decimal128 columns at seal
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -289,6 +316,14 @@ struct llkv_gpu_column {
   const void* pend_src = nullptr;
   uint64_t pend_bytes = 0;
   std::vector<void*> deferred_free;  // temp device buffers released at seal
+  // zone maps (minimum / maximum per kZoneRows rows, as the 64-bit values the lean kernel's leaves compare), computed on
+  // the device when a scan first wants them and mirrored on the host, where tile lists are built
+  uint64_t version = 1;          // bumped whenever the content changes (append, clear)
+  uint64_t zones_version = 0;    // content version h_zones describes
+  u64* d_zones = nullptr;
+  size_t d_zones_cap = 0;        // zones
+  std::vector<u64> h_zones;      // [zone][min, max]
+  uint32_t scans_unchanged = 0;  // fused scans with a range leaf on this column since the content last changed
 };
 
 struct llkv_gpu_program {
@@ -357,6 +392,14 @@ struct llkv_gpu_agg {
   u64* part_out = nullptr;
   size_t part_out_elems = 0;
   uint32_t* part_cursor = nullptr;
+  // zone-map pruning: the surviving tiles of the last pruned scan (reused while its key — plan, geometry, row range and
+  // the content versions of the predicate columns — does not change)
+  uint32_t* d_tile_list = nullptr;
+  size_t tile_list_cap = 0;
+  std::vector<uint32_t> h_tile_list;
+  uint64_t tile_list_key = 0;
+  uint64_t tile_list_total = 0;
+  bool tile_list_use = false;
   uint64_t lean_sig = 0;
   uint32_t lean_jit_runs = 0;
   uint32_t* d_flags = nullptr;
@@ -486,6 +529,13 @@ extern "C" int32_t llkv_gpu_ctx_set_partitioning(llkv_gpu_ctx* c, int32_t mode) 
   if (!c) return set_error(LLKV_ERR_INVALID_ARGUMENT, "ctx is NULL");
   if (mode < 0 || mode > 2) return set_error(LLKV_ERR_INVALID_ARGUMENT, "partitioning mode must be 0, 1 or 2");
   c->partition_mode = mode;
+  return LLKV_OK;
+}
+
+extern "C" int32_t llkv_gpu_ctx_set_pruning(llkv_gpu_ctx* c, int32_t mode) {
+  if (!c) return set_error(LLKV_ERR_INVALID_ARGUMENT, "ctx is NULL");
+  if (mode < 0 || mode > 2) return set_error(LLKV_ERR_INVALID_ARGUMENT, "pruning mode must be 0, 1 or 2");
+  c->prune_mode = mode;
   return LLKV_OK;
 }
 
@@ -698,6 +748,55 @@ static int32_t launch_stats(llkv_gpu_column* col, uint64_t first_row, uint64_t n
   return LLKV_OK;
 }
 
+// Zone map of the resident image, on the host (false: this column's layout has none: floats, strings, wide decimals).
+static int32_t ensure_zones(llkv_gpu_column* col, bool* ok) {
+  *ok = false;
+  llkv_gpu_ctx* c = col->ctx;
+  const u64 n = col->n_rows;
+  if (n == 0) return LLKV_OK;
+  const u64 n_zones = (n + kZoneRows - 1) / kZoneRows;
+  if (col->zones_version == col->version && col->h_zones.size() == 2 * n_zones) {
+    *ok = true;
+    return LLKV_OK;
+  }
+  const bool dec64 = col->type == LLKV_PT_DECIMAL128 && col->load_kind == LK_D64;
+  switch (col->type) {
+    case LLKV_PT_INT8: case LLKV_PT_INT16: case LLKV_PT_INT32: case LLKV_PT_INT64: case LLKV_PT_DATE32: case LLKV_PT_DATE64:
+    case LLKV_PT_UINT8: case LLKV_PT_UINT16: case LLKV_PT_UINT32: case LLKV_PT_UINT64: case LLKV_PT_BOOLEAN: break;
+    case LLKV_PT_DECIMAL128: if (dec64) break; return LLKV_OK;
+    default: return LLKV_OK;
+  }
+  if (col->d_zones_cap < n_zones) {
+    if (col->d_zones) CUDA_TRY(cudaFree(col->d_zones));
+    col->d_zones = nullptr;
+    col->d_zones_cap = 0;
+    CUDA_TRY(cudaMalloc((void**)&col->d_zones, n_zones * 16));
+    col->d_zones_cap = n_zones;
+  }
+  cudaStream_t s = c->stream;
+  const unsigned blocks = (unsigned)std::min<u64>((n_zones + 7) / 8, 1184);
+  const void* v = col->values;
+  switch (col->type) {
+    case LLKV_PT_INT8: zone_minmax_kernel<signed char, true, 1><<<blocks, 256, 0, s>>>((const signed char*)v, n, col->d_zones); break;
+    case LLKV_PT_INT16: zone_minmax_kernel<short, true, 1><<<blocks, 256, 0, s>>>((const short*)v, n, col->d_zones); break;
+    case LLKV_PT_INT32: case LLKV_PT_DATE32: zone_minmax_kernel<int, true, 1><<<blocks, 256, 0, s>>>((const int*)v, n, col->d_zones); break;
+    case LLKV_PT_INT64: case LLKV_PT_DATE64: case LLKV_PT_DECIMAL128:
+      zone_minmax_kernel<i64, true, 1><<<blocks, 256, 0, s>>>((const i64*)v, n, col->d_zones);
+      break;
+    case LLKV_PT_UINT8: case LLKV_PT_BOOLEAN: zone_minmax_kernel<unsigned char, false, 1><<<blocks, 256, 0, s>>>((const unsigned char*)v, n, col->d_zones); break;
+    case LLKV_PT_UINT16: zone_minmax_kernel<unsigned short, false, 1><<<blocks, 256, 0, s>>>((const unsigned short*)v, n, col->d_zones); break;
+    case LLKV_PT_UINT32: zone_minmax_kernel<unsigned int, false, 1><<<blocks, 256, 0, s>>>((const unsigned int*)v, n, col->d_zones); break;
+    default: zone_minmax_kernel<u64, false, 1><<<blocks, 256, 0, s>>>((const u64*)v, n, col->d_zones); break;
+  }
+  CUDA_TRY(cudaGetLastError());
+  col->h_zones.resize(2 * n_zones);
+  CUDA_TRY(cudaMemcpyAsync(col->h_zones.data(), col->d_zones, n_zones * 16, cudaMemcpyDeviceToHost, s));
+  CUDA_TRY(cudaStreamSynchronize(s));
+  col->zones_version = col->version;
+  *ok = true;
+  return LLKV_OK;
+}
+
 extern "C" int32_t llkv_gpu_column_append_chunk(llkv_gpu_column* col, uint64_t chunk_pk, const void* values, uint64_t n_rows,
                                                  const uint8_t* validity, const uint64_t* row_ids, uint64_t row_id_base,
                                                  const void* aux) {
@@ -796,6 +895,8 @@ extern "C" int32_t llkv_gpu_column_append_chunk(llkv_gpu_column* col, uint64_t c
     CUDA_TRY(cudaGetLastError());
   }
   col->n_rows += n_rows;
+  ++col->version;
+  col->scans_unchanged = 0;
   return LLKV_OK;
 }
 
@@ -962,6 +1063,8 @@ extern "C" int32_t llkv_gpu_column_clear(llkv_gpu_column* col) {
   col->stats_rows = 0;
   col->has_origin = false;
   col->sealed = false;
+  ++col->version;
+  col->scans_unchanged = 0;
   return LLKV_OK;
 }
 
@@ -979,6 +1082,7 @@ extern "C" int32_t llkv_gpu_column_destroy(llkv_gpu_column* col) {
   if (col->values) cudaFree(col->values);
   if (col->validity) cudaFree(col->validity);
   if (col->dstats) cudaFree(col->dstats);
+  if (col->d_zones) cudaFree(col->d_zones);
   delete col;
   return LLKV_OK;
 }
@@ -1695,6 +1799,7 @@ extern "C" void llkv_gpu_agg_destroy(llkv_gpu_agg* a) {
   if (a->mg_stats) cudaFree(a->mg_stats);
   if (a->part_out) cudaFree(a->part_out);
   if (a->part_cursor) cudaFree(a->part_cursor);
+  if (a->d_tile_list) cudaFree(a->d_tile_list);
   if (a->d_flags) cudaFree(a->d_flags);
   if (a->d_plan) cudaFree(a->d_plan);
   if (a->h_plan) cudaFreeHost(a->h_plan);
@@ -2070,14 +2175,109 @@ static int32_t agg_launch(llkv_gpu_agg* a, const llkv_gpu_program* prog, int app
   } else {
     a->info.partitions = 0;
   }
+  // Zone-map pruning (lean path): every FO_LEAF of the program is a conjunct (`selected &= lo <= v <= hi`), so a tile none
+  // of whose zones can satisfy some leaf holds no selected row.  The surviving tiles are listed on the host from the
+  // columns' zone maps and the launch walks the list instead of the dense tile range.
+  a->info.tiles_pruned = 0;
+  bool use_tile_list = false;
+  if (a->cr.fast && ctx->prune_mode && row_end > row_begin) {
+    struct PruneLeaf { llkv_gpu_column* col; i64 lo, hi; bool uns; };
+    std::vector<PruneLeaf> leaves;
+    uint64_t key = fnv_pod(fnv_pod(fnv_pod(fnv_pod(sig, p.tile_rows), row_begin), row_end), ctx->prune_mode);
+    for (uint32_t i = 0; i < lean.s.n_code; ++i) {
+      const FInstr& in = lean.s.code[i];
+      if (in.op != FO_LEAF) continue;
+      llkv_gpu_column* col = nullptr;
+      for (llkv_gpu_column* h : handles)
+        if (h->values == lean.col_base[in.a]) col = h;
+      if (!col) continue;
+      const bool col_unsigned64 = col->type == LLKV_PT_UINT64;
+      if (col_unsigned64 != (in.g != 0)) continue;  // the zone order must be the leaf's compare order
+      leaves.push_back(PruneLeaf{col, (i64)lean.lits[in.c], (i64)lean.lits[in.c + 1], in.g != 0});
+      key = fnv_pod(fnv_pod(key, col->version), (uint64_t)(uintptr_t)col);
+    }
+    bool wanted = !leaves.empty();
+    if (wanted && ctx->prune_mode == 1) {  // only columns that are scanned again without having changed
+      bool settled = true;
+      for (PruneLeaf& L : leaves) settled = settled && L.col->scans_unchanged >= 1;
+      for (PruneLeaf& L : leaves) ++L.col->scans_unchanged;
+      wanted = settled;
+    }
+    if (wanted && a->tile_list_key == key) {
+      use_tile_list = a->tile_list_use;
+    } else if (wanted) {
+      const u64 T = p.tile_rows;
+      const u64 n_zones = (table_rows + kZoneRows - 1) / kZoneRows;
+      std::vector<uint8_t> zone_ok(n_zones, 1);
+      bool any_map = false;
+      for (PruneLeaf& L : leaves) {
+        bool ok = false;
+        if ((rc = ensure_zones(L.col, &ok))) return rc;
+        if (!ok || L.col->h_zones.size() != 2 * n_zones) continue;
+        any_map = true;
+        const u64* z = L.col->h_zones.data();
+        for (u64 q = 0; q < n_zones; ++q) {
+          const bool disjoint = L.uns ? ((u64)L.hi < z[2 * q] || (u64)L.lo > z[2 * q + 1]) : (L.hi < (i64)z[2 * q] || L.lo > (i64)z[2 * q + 1]);
+          const bool empty = L.uns ? (u64)L.hi < (u64)L.lo : L.hi < L.lo;
+          if (disjoint || empty) zone_ok[q] = 0;
+        }
+      }
+      const u64 t0 = row_begin / T, t1 = (row_end + T - 1) / T;
+      a->h_tile_list.clear();
+      if (any_map) {
+        for (u64 t = t0; t < t1; ++t) {
+          const u64 z0 = t * T / kZoneRows, z1 = std::min<u64>((t + 1) * T - 1, table_rows - 1) / kZoneRows;
+          bool keep = false;
+          for (u64 q = z0; q <= z1 && !keep; ++q) keep = zone_ok[q] != 0;
+          if (keep) a->h_tile_list.push_back((uint32_t)t);
+        }
+      }
+      const u64 total = t1 - t0, kept = any_map ? a->h_tile_list.size() : total;
+      a->tile_list_total = total;
+      a->tile_list_use = any_map && kept < total && (ctx->prune_mode == 2 || (total - kept) * 8 >= total) && t1 <= 0xffffffffull;
+      a->tile_list_key = key;
+      if (a->tile_list_use && kept) {
+        if (a->tile_list_cap < kept) {
+          if (a->d_tile_list) CUDA_TRY(cudaFree(a->d_tile_list));
+          a->d_tile_list = nullptr;
+          a->tile_list_cap = 0;
+          CUDA_TRY(cudaMalloc((void**)&a->d_tile_list, kept * 4));
+          a->tile_list_cap = kept;
+        }
+        CUDA_TRY(cudaMemcpyAsync(a->d_tile_list, a->h_tile_list.data(), kept * 4, cudaMemcpyHostToDevice, ctx->stream));
+        CUDA_TRY(cudaStreamSynchronize(ctx->stream));  // (h_tile_list is pageable; once per list)
+      }
+      use_tile_list = a->tile_list_use;
+    }
+    if (use_tile_list) a->info.tiles_pruned = (uint32_t)(a->tile_list_total - a->h_tile_list.size());
+  }
   a->pending.timed = ctx->timing;
   if (ctx->timing) CUDA_TRY(cudaEventRecord(ctx->ev0, ctx->stream));
   uint32_t launches = 0;
   a->info.used_jit_kernel = 0;
-  for (u64 rb = row_begin; rb < row_end || (rb == row_begin && launches == 0); rb += max_rows_per_launch) {
-    const u64 re = std::min<u64>(row_end, rb + max_rows_per_launch);
-    const u64 first_tile = rb / p.tile_rows;
-    const u64 n_tiles = re > rb ? (re + p.tile_rows - 1) / p.tile_rows - first_tile : 0;
+  lean.tile_list = nullptr;
+  // launches: dense row ranges, or runs of the tile list (bounded in tiles, and in the rows they span: launch-relative
+  // row indices are 32-bit)
+  const u64 list_n = use_tile_list ? a->h_tile_list.size() : 0;
+  const u64 tiles_per_launch = std::max<u64>(1, max_rows_per_launch / p.tile_rows);
+  u64 list_pos = 0;
+  for (u64 rb = row_begin; use_tile_list || rb < row_end || (rb == row_begin && launches == 0); rb += max_rows_per_launch) {
+    u64 re = std::min<u64>(row_end, rb + max_rows_per_launch);
+    u64 first_tile = rb / p.tile_rows;
+    u64 n_tiles = re > rb ? (re + p.tile_rows - 1) / p.tile_rows - first_tile : 0;
+    if (use_tile_list) {
+      if (list_pos >= list_n) break;
+      first_tile = a->h_tile_list[list_pos];
+      n_tiles = 1;
+      while (list_pos + n_tiles < list_n && n_tiles < tiles_per_launch &&
+             ((u64)a->h_tile_list[list_pos + n_tiles] - first_tile + 1) * p.tile_rows < 0xf0000000ull)
+        ++n_tiles;
+      const u64 last_tile = a->h_tile_list[list_pos + n_tiles - 1];
+      rb = std::max<u64>(row_begin, first_tile * p.tile_rows);
+      re = std::min<u64>(row_end, (last_tile + 1) * p.tile_rows);
+      lean.tile_list = a->d_tile_list + list_pos;
+      list_pos += n_tiles;
+    }
     if (n_tiles == 0) break;
     const u64 grid = std::min<u64>(g.grid, n_tiles);
     if (!launches) a->info.grid = (uint32_t)grid;
@@ -2108,7 +2308,7 @@ static int32_t agg_launch(llkv_gpu_agg* a, const llkv_gpu_program* prog, int app
       CUDA_TRY(launch_scan(a->d_plan, a->cr.wide, (int)g.R, (uint32_t)grid, g.block, g.smem, ctx->stream));
     }
     ++launches;
-    if (re >= row_end) break;
+    if (use_tile_list ? list_pos >= list_n : re >= row_end) break;
   }
   if (ctx->timing) CUDA_TRY(cudaEventRecord(ctx->ev1, ctx->stream));
   CUDA_TRY(cudaMemcpyAsync(a->h_flags, a->d_flags, 4, cudaMemcpyDeviceToHost, ctx->stream));

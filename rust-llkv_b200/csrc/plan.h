@@ -296,7 +296,11 @@ struct LeanPlan {
   uint32_t* part_cursor;
   unsigned long long part_cap;
   uint32_t part_bits, part_shift;  // partition = (mix64(key) & (gcap - 1)) >> part_shift, 2^part_bits partitions
+  // zone-map pruning: when set, the launch visits tiles tile_list[0 .. n_tiles) (ascending, >= first_tile) instead of
+  // first_tile .. first_tile + n_tiles: the host dropped the tiles whose zones no conjunct range leaf can match
+  const uint32_t* tile_list;
 };
+constexpr uint32_t kZoneRows = 4096;  // rows per zone-map entry (= the reference's chunk of Decimal128 / Date32 rows, slicing.rs:155-166)
 
 // one aggregate of a partitioned plan as partition_apply_kernel sees it
 struct PartOp {

@@ -484,6 +484,7 @@ class Context {
   void set_timing(bool on) { check(llkv_gpu_ctx_set_timing(h_, on ? 1 : 0)); }
   void set_jit(int mode) { check(llkv_gpu_ctx_set_jit(h_, mode)); }
   void set_partitioning(int mode) { check(llkv_gpu_ctx_set_partitioning(h_, mode)); }
+  void set_pruning(int mode) { check(llkv_gpu_ctx_set_pruning(h_, mode)); }
   // MvccRowIdFilter::new(txn_manager, snapshot) (llkv-transaction/src/helpers.rs:259-312)
   void set_snapshot(uint64_t table_id, llkv_gpu_column* created_by, llkv_gpu_column* deleted_by, uint64_t txn_id, uint64_t snapshot_id,
                     const std::vector<uint64_t>& noncommitted = {}) {

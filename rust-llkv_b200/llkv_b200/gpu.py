@@ -53,6 +53,7 @@ def load():
         "llkv_gpu_ctx_set_tuning": (i32, [vp, i32, i32, i32, i32, i32]),
         "llkv_gpu_ctx_set_jit": (i32, [vp, i32]),
         "llkv_gpu_ctx_set_partitioning": (i32, [vp, i32]),
+        "llkv_gpu_ctx_set_pruning": (i32, [vp, i32]),
         "llkv_gpu_debug_plan": (i32, [vp, i32, vp, i32, i32, u64, u64, vp, i32, vp, i32, vp, i32, i32, u64, i32, i32, i32, i32, i32,
                                        C.c_char_p, C.c_char_p, u64]),
         "llkv_gpu_descriptor_parse": (i32, [vp, u64, vp]),
@@ -160,6 +161,11 @@ class Context:
         """Partitioned high-cardinality GROUP BY: 0 = never, 1 = when the group table exceeds L2 (default), 2 = whenever
         the plan allows it."""
         _check(self.lib.llkv_gpu_ctx_set_partitioning(self.handle, mode))
+
+    def set_pruning(self, mode: int):
+        """Zone-map tile skipping: 0 = never, 1 = for columns scanned again unchanged when >= 1/8 of the tiles drop out
+        (default), 2 = from the first scan, whenever any tile drops out."""
+        _check(self.lib.llkv_gpu_ctx_set_pruning(self.handle, mode))
 
     # ---- multi-GPU (NCCL over NVLink): the unique id travels through whatever the host uses for rendezvous
     def comm_unique_id(self) -> bytes:
