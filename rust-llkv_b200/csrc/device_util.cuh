@@ -260,7 +260,8 @@ static __device__ __noinline__ u64 global_slot(const Plan& p, u64 K, bool key_is
 // exact integer value -> limb words (see FastKind)
 __device__ __forceinline__ void gadd_sum_i64(u64* w, i128 t) {
   atomicAdd(&w[0], (u64)t & 0xffffffffull);
-  atomicAdd(&w[1], (u64)(i64)(t >> 32));
+  const u64 hi = (u64)(i64)(t >> 32);
+  if (hi) atomicAdd(&w[1], hi);  // small non-negative values (most per-row updates) add nothing to the upper limb
 }
 __device__ __forceinline__ void gadd_sum_i128(u64* w, i128 t) {
   atomicAdd(&w[0], (u64)t & 0xffffffffull);

@@ -466,9 +466,42 @@ struct LeanTile {
           negm = actm;
           has_slow = __any_sync(LLKV_FULL, negm != 0);
           if (has_slow) {
+            // The thread's R probes run together, one step of every unresolved row per round (warp-convergent under
+            // __any_sync): R table reads in flight per thread instead of R dependent round trips.
+            const uint32_t mask = (uint32_t)p.gcap - 1u;  // (the table has < 2^32 rows: gsl[] is 32-bit)
+            u64 cur[R];
+            unsigned need = 0;
 #pragma unroll
-            for (int r = 0; r < R; ++r)
-              if ((negm >> r) & 1u) gsl[r] = (uint32_t)lean_global_slot(p.gkeys, p.gcap, S.n_keys, keys[r], errbits);
+            for (int r = 0; r < R; ++r) {
+              const bool probe = ((negm >> r) & 1u) && keys[r] != kEmptyKey;
+              gsl[r] = probe ? ((uint32_t)mix64(keys[r]) & mask) : (uint32_t)p.gcap;  // the reserved key value has its own row
+              cur[r] = probe ? __ldcg(&p.gkeys[gsl[r]]) : 0ull;
+              need |= (unsigned)probe << r;
+            }
+            uint32_t rounds = 0;
+            while (__any_sync(LLKV_FULL, need != 0)) {
+#pragma unroll
+              for (int r = 0; r < R; ++r) {
+                if (!((need >> r) & 1u)) continue;
+                bool done = cur[r] == keys[r];
+                if (!done && cur[r] == kEmptyKey) {
+                  const u64 old = atomicCAS(&p.gkeys[gsl[r]], kEmptyKey, keys[r]);
+                  done = old == kEmptyKey || old == keys[r];
+                }
+                if (done) need &= ~(1u << r);
+                else {
+                  gsl[r] = (gsl[r] + 1u) & mask;
+                  cur[r] = __ldcg(&p.gkeys[gsl[r]]);
+                }
+              }
+              if (++rounds > mask && need) {  // every slot seen: the table is full (the run is repeated with a larger one)
+                errbits |= FLAG_TABLE_FULL;
+#pragma unroll
+                for (int r = 0; r < R; ++r)
+                  if ((need >> r) & 1u) gsl[r] = (uint32_t)p.gcap;
+                need = 0;
+              }
+            }
           }
           return true;
         }
