@@ -49,12 +49,19 @@ def main():
         (dt, full, tpch.q1_filter(), tpch.q1_aggregates(), tpch.Q1_GROUP_BY, snap, 6, True),
         (hdt, hc, None, tpch.highcard_aggregates(), (tpch.K_FIELD,), None, 40_000, False),
     ]
-    for table, host, flt, specs, keys, sn, hint, ordered in cases:
+    cases.append(cases[2] + ("partitioned",))  # the same aggregate through the partitioned (two-pass) form
+    cases.append((dt, full, tpch.q6_filter(), tpch.q6_aggregates(), (), snap, 0, True, "pruned"))  # zone-map tile lists on
+    for table, host, flt, specs, keys, sn, hint, ordered, *mode in cases:
+        ctx.set_partitioning(2 if "partitioned" in mode else 1)
+        ctx.set_pruning(2 if "pruned" in mode else 1)
+        ctx.set_jit(2 if mode else 1)
         prog = gpu.Program(ctx, flt) if flt is not None else None
         agg = gpu.Aggregation(table, specs, keys, cardinality_hint=hint)
         agg.run(prog, sn is not None)
         agg.merge()
         got = agg.finalize(1 << 17)
+        if "partitioned" in mode:
+            assert agg.run_info().partitions >= 2
         want = oracle.aggregate(host, flt, specs, sn, keys, group_capacity=1 << 17)
         util.assert_same_result(got, want, 1e-12, ordered=ordered)
         agg.destroy()
@@ -62,7 +69,7 @@ def main():
             prog.destroy()
     dist.barrier()
     if rank == 0:
-        print(f"multi-GPU merge ok on {world} ranks: Q6, Q1 and a 40k-group hash aggregate match the oracle", flush=True)
+        print(f"multi-GPU merge ok on {world} ranks: Q6 (also with tile lists), Q1 and a 40k-group hash aggregate (per-row and partitioned) match the oracle", flush=True)
     ctx.comm_destroy()
     dist.destroy_process_group()
 
