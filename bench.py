@@ -367,7 +367,7 @@ def run_ours(args):
             line["highcard"] = highcard
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(seed=6)
-        print(json.dumps(line), flush=True)
+        emit(line)
 
     for p in ptrs:
         gpu.pinned_free(p)
@@ -419,17 +419,36 @@ def run_reference(args):
     dt = time.perf_counter() - t0
     v = n * args.steps / dt
     sample = f"each step = TPC-H Q6 over a {n}-row sample of the synthetic lineitem (seed 6)"
-    print(json.dumps({
+    emit({
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": int(os.environ.get("WORLD_SIZE", "1")), "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "i128/i64 (Decimal128, Date32)", "data": "synthetic",
         "config": {"workload": f"TPC-H Q6 on synthetic lineitem SF{args.sf:g} — bounded CPU sample: {sample}"},
         "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-    }), flush=True)
+    })
+
+
+# stdout carries exactly one JSON line.  Native libraries print there too (NCCL's "NCCL version ..." banner is a plain
+# printf when NCCL_DEBUG=VERSION), so file descriptor 1 points at stderr while the benchmark runs and the JSON line goes to
+# the real stdout.
+_REAL_STDOUT = None
+
+
+def emit(obj):
+    data = (json.dumps(obj) + "\n").encode()
+    sys.stdout.flush()
+    if _REAL_STDOUT is None:
+        os.write(1, data)
+    else:
+        os.write(_REAL_STDOUT, data)
 
 
 def main():
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
