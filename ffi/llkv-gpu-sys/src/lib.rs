@@ -177,6 +177,8 @@ extern "C" {
     pub fn llkv_gpu_ctx_set_pruning(ctx: *mut llkv_gpu_ctx, mode: i32) -> i32;
     pub fn llkv_gpu_host_alloc(bytes: u64, out: *mut *mut c_void) -> i32;
     pub fn llkv_gpu_host_free(p: *mut c_void) -> i32;
+    pub fn llkv_gpu_host_register(p: *const c_void, bytes: u64) -> i32;
+    pub fn llkv_gpu_host_unregister(p: *const c_void) -> i32;
 
     pub fn llkv_gpu_descriptor_parse(bytes: *const c_void, len: u64, out: *mut llkv_column_descriptor) -> i32;
     pub fn llkv_gpu_descriptor_page_parse(bytes: *const c_void, len: u64, next_page_pk: *mut u64, out: *mut llkv_chunk_metadata, capacity: u64, n_entries: *mut u64) -> i32;

@@ -281,6 +281,12 @@ int32_t llkv_gpu_ctx_set_pruning(llkv_gpu_ctx* ctx, int32_t mode);
 /* Page-locked host memory so chunk uploads DMA straight from the caller's buffer. */
 int32_t llkv_gpu_host_alloc(uint64_t bytes, void** out);
 int32_t llkv_gpu_host_free(void* p);
+/* Page-locks memory the caller already owns — the pager's mmap-backed blobs (EntryHandle, llkv-storage/src/pager/
+ * simd_r_drive_pager.rs) — so llkv_gpu_column_append_blob / _append_chunk DMA straight out of it
+ * instead of staging through the context's pinned ring.  Read-only mappings are registered read-only.  Unregister before
+ * the mapping goes away. */
+int32_t llkv_gpu_host_register(const void* p, uint64_t bytes);
+int32_t llkv_gpu_host_unregister(const void* p);
 
 /* ---- column metadata in front of the scan (host only, no device work): the descriptor walk of
  * llkv-column-map/src/store/scan/unsorted.rs:202-241.  The caller fetches the blobs (ColumnCatalog -> descriptor pk ->

@@ -999,7 +999,7 @@ __device__ __forceinline__ void lean_body(const LeanPlan& p) {
     if (lane == 0) {
       uint32_t s = 0, round = 0;
       for (uint32_t li = 0, rt = blockIdx.x; li < my_tiles; ++li, rt += gridDim.x) {
-        const u64 tile = p.tile_list ? (u64)p.tile_list[rt] : p.first_tile + rt;  // (read before the wait: off the critical path)
+        const u64 tile = S.use_tile_list ? (u64)p.tile_list[rt] : p.first_tile + rt;  // (read before the wait: off the critical path)
         if (round) mbar_wait_parked(&empty_bar[s], (round - 1) & 1);
         unsigned char* sbuf = stage0 + (size_t)s * S.stage_bytes;
         mbar_arrive_expect_tx(&full_bar[s], S.tx_bytes);
@@ -1024,7 +1024,7 @@ __device__ __forceinline__ void lean_body(const LeanPlan& p) {
     const uint32_t end_rel = end64 > 0xffffffffull ? 0xffffffffu : (uint32_t)end64;
     uint32_t s = 0, round = 0;
     for (uint32_t li = 0, rt = blockIdx.x; li < my_tiles; ++li, rt += gridDim.x) {
-      const uint32_t rel_tile = p.tile_list ? p.tile_list[rt] - (uint32_t)p.first_tile : rt;  // (requested before the wait)
+      const uint32_t rel_tile = S.use_tile_list ? p.tile_list[rt] - (uint32_t)p.first_tile : rt;  // (requested before the wait)
       mbar_wait_parked(&full_bar[s], round & 1);
       t.begin_tile(stage0 + (size_t)s * S.stage_bytes, rel_tile * T, base_row, begin_rel, end_rel);
       if constexpr (Cfg::kStatic) t.template run_static<0>();

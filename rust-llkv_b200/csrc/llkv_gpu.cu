@@ -560,6 +560,25 @@ extern "C" int32_t llkv_gpu_host_alloc(uint64_t bytes, void** out) {
   CUDA_TRY(cudaHostAlloc(out, bytes ? bytes : 1, cudaHostAllocDefault));
   return LLKV_OK;
 }
+extern "C" int32_t llkv_gpu_host_register(const void* p, uint64_t bytes) {
+  if (!p || !bytes) return set_error(LLKV_ERR_INVALID_ARGUMENT, "nothing to register");
+  cudaError_t e = cudaHostRegister(const_cast<void*>(p), bytes, cudaHostRegisterPortable | cudaHostRegisterReadOnly);
+  if (e != cudaSuccess) {  // (read-only registration needs driver support; plain registration needs a writable mapping)
+    cudaGetLastError();
+    e = cudaHostRegister(const_cast<void*>(p), bytes, cudaHostRegisterPortable);
+  }
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    return set_error(LLKV_ERR_IO, "cudaHostRegister: %s", cudaGetErrorString(e));
+  }
+  return LLKV_OK;
+}
+extern "C" int32_t llkv_gpu_host_unregister(const void* p) {
+  if (!p) return LLKV_OK;
+  CUDA_TRY(cudaHostUnregister(const_cast<void*>(p)));
+  return LLKV_OK;
+}
+
 extern "C" int32_t llkv_gpu_host_free(void* p) {
   if (p) CUDA_TRY(cudaFreeHost(p));
   return LLKV_OK;
@@ -2256,6 +2275,7 @@ static int32_t agg_launch(llkv_gpu_agg* a, const llkv_gpu_program* prog, int app
   uint32_t launches = 0;
   a->info.used_jit_kernel = 0;
   lean.tile_list = nullptr;
+  lean.s.use_tile_list = use_tile_list ? 1u : 0u;
   // launches: dense row ranges, or runs of the tile list (bounded in tiles, and in the rows they span: launch-relative
   // row indices are 32-bit)
   const u64 list_n = use_tile_list ? a->h_tile_list.size() : 0;

@@ -274,6 +274,8 @@ struct LeanShape {
   uint32_t partition;      // 1: tuples out, no accumulation in this kernel
   uint32_t n_fields;       // 64-bit fields per tuple: key, row id, one per aggregate that takes an operand
   uint32_t smem_part_off;  // counters [3][kMaxPartitions + 1] u32, then the tile's tuples [n_fields][tile_rows] u64
+  uint32_t use_tile_list;  // 1: the launch walks LeanPlan::tile_list (zone-map pruning); part of the shape so that the
+                           // specialised dense kernel carries no trace of it
 };
 constexpr int kMaxPartitions = 256;
 struct LeanPlan {

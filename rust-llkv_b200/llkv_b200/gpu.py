@@ -62,6 +62,8 @@ def load():
         "llkv_gpu_chunk_overlaps": (i32, [i32, u64, u64, vp, vp]),
         "llkv_gpu_host_alloc": (i32, [u64, P(vp)]),
         "llkv_gpu_host_free": (i32, [vp]),
+        "llkv_gpu_host_register": (i32, [vp, u64]),
+        "llkv_gpu_host_unregister": (i32, [vp]),
         "llkv_gpu_column_register": (i32, [vp, u64, i32, u8, i8, P(vp)]),
         "llkv_gpu_column_reserve": (i32, [vp, u64]),
         "llkv_gpu_column_append_chunk": (i32, [vp, u64, vp, u64, vp, vp, u64, vp]),
@@ -191,6 +193,19 @@ def pinned_empty(nbytes: int) -> Tuple[np.ndarray, int]:
 
 def pinned_free(ptr: int):
     _check(load().llkv_gpu_host_free(C.c_void_p(ptr)))
+
+
+def host_register(buf) -> int:
+    """Page-locks a buffer the caller owns (numpy array or mmap: the pager's blob memory) so appends DMA straight out of
+    it; returns the address to pass to host_unregister."""
+    arr = np.frombuffer(buf, dtype=np.uint8) if not isinstance(buf, np.ndarray) else buf
+    ptr = arr.ctypes.data
+    _check(load().llkv_gpu_host_register(C.c_void_p(ptr), arr.nbytes))
+    return ptr
+
+
+def host_unregister(ptr: int):
+    _check(load().llkv_gpu_host_unregister(C.c_void_p(ptr)))
 
 
 def chunk_rows_for(dtype_type: int) -> int:

@@ -642,3 +642,34 @@ def test_column_loaded_through_its_descriptor_chain(gpu_ctx):
         assert int(kept[(kept >= a) & (kept <= b)].sum()) == got[0][1][0].value  # no matching row lives in a skipped chunk
     finally:
         dt.destroy()
+
+
+def test_chunk_blobs_appended_from_registered_pager_memory(gpu_ctx):
+    """The pager's mmap-backed blobs, page-locked in place (llkv_gpu_host_register): appends DMA out of the mapping and the
+    resident column reads back identical."""
+    import mmap
+    from llkv_b200 import gpu
+    rng = np.random.default_rng(17)
+    x = rng.integers(-10**12, 10**12, 200_000, dtype=np.int64)
+    blobs = [HostColumn(3, DataType.Int64, x[lo:lo + 50_000]).serialize() for lo in range(0, x.size, 50_000)]
+    store = mmap.mmap(-1, sum(len(b) for b in blobs) + 4096)  # an anonymous mapping standing in for the pager's file mapping
+    offs, o = [], 0
+    for b in blobs:
+        store[o:o + len(b)] = b
+        offs.append(o)
+        o += len(b)
+    view = np.frombuffer(store, dtype=np.uint8)
+    ptr = gpu.host_register(view)
+    dc = gpu.DeviceColumn(gpu_ctx, gpu.logical_field_id(1, 3), HostColumn(3, DataType.Int64, x[:1]))
+    try:
+        base = 0
+        for b, off in zip(blobs, offs):
+            gpu._check(gpu_ctx.lib.llkv_gpu_column_append_blob(dc.handle, 1 + base, ptr + off, len(b), None, base))
+            base += 50_000
+        dc.seal()
+        assert np.array_equal(dc.read(), x)
+    finally:
+        dc.destroy()
+        gpu.host_unregister(ptr)
+        del view
+        store.close()
