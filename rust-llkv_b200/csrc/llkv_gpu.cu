@@ -406,6 +406,7 @@ struct llkv_gpu_agg {
   uint32_t* h_flags = nullptr;  // pinned
   unsigned char* h_stage = nullptr;  // pinned landing buffer of finalize (small tables)
   size_t h_stage_bytes = 0;
+  bool prefetched = false;  // h_stage holds the table as the last run left it (copy queued right behind the scan)
   Plan* d_plan = nullptr;
   Plan* h_plan = nullptr;  // pinned
   CompileResult cr;
@@ -2332,6 +2333,24 @@ static int32_t agg_launch(llkv_gpu_agg* a, const llkv_gpu_program* prog, int app
   }
   if (ctx->timing) CUDA_TRY(cudaEventRecord(ctx->ev1, ctx->stream));
   CUDA_TRY(cudaMemcpyAsync(a->h_flags, a->d_flags, 4, cudaMemcpyDeviceToHost, ctx->stream));
+  // Small tables (an ungrouped state row, Q1's 32 rows) travel to the host right behind the scan, so finalize needs the
+  // one synchronisation that settles the run and no copy of its own.
+  a->prefetched = false;
+  {
+    const size_t wbytes = (size_t)(a->gcap + 2) * a->n_gwords * 8, kbytes = p.n_keys ? (size_t)a->gcap * 8 : 0;
+    if (wbytes + kbytes <= (64u << 10)) {
+      if (a->h_stage_bytes < wbytes + kbytes) {
+        if (a->h_stage) CUDA_TRY(cudaFreeHost(a->h_stage));
+        a->h_stage = nullptr;
+        a->h_stage_bytes = 0;
+        CUDA_TRY(cudaHostAlloc((void**)&a->h_stage, 64u << 10, cudaHostAllocDefault));
+        a->h_stage_bytes = 64u << 10;
+      }
+      CUDA_TRY(cudaMemcpyAsync(a->h_stage, a->gwords, wbytes, cudaMemcpyDeviceToHost, ctx->stream));
+      if (kbytes) CUDA_TRY(cudaMemcpyAsync(a->h_stage + wbytes, a->gkeys, kbytes, cudaMemcpyDeviceToHost, ctx->stream));
+      a->prefetched = true;
+    }
+  }
   a->info.rows = row_end - row_begin;
   a->info.kernel_launches = launches;
   a->info.used_wide_path = a->cr.wide ? 1 : 0;
@@ -2371,6 +2390,7 @@ static int32_t agg_resolve(llkv_gpu_agg* a) {
     }
     const uint32_t flags = *a->h_flags;
     if (flags == 0) break;
+    a->prefetched = false;  // the run is repeated or failed: what travelled behind it is not the result
     CUDA_TRY(cudaMemsetAsync(a->d_flags, 0, 4, ctx->stream));
     *a->h_flags = 0;
     const bool narrow_fail = (flags & FLAG_NARROW_FAIL) && !a->pending.wide;
@@ -2418,6 +2438,7 @@ extern "C" int32_t llkv_gpu_agg_reset(llkv_gpu_agg* a) {
   }
   a->err_code = 0;
   a->err_msg.clear();
+  a->prefetched = false;
   *a->h_flags = 0;
   CUDA_TRY(cudaMemsetAsync(a->d_flags, 0, 4, ctx->stream));
   if (a->frozen) CUDA_TRY(launch_init_table(a->gkeys, a->gwords, a->gcap + 2, a->n_gwords, a->d_gclass, ctx->stream));
@@ -2646,7 +2667,10 @@ static int32_t agg_collect(llkv_gpu_agg* a, std::vector<u64>& hk, std::vector<u6
   hk.resize(a->gcap);
   hw.resize(rows * a->n_gwords);
   const size_t wbytes = hw.size() * 8, kbytes = a->cr.plan.n_keys ? hk.size() * 8 : 0;
-  if (wbytes + kbytes <= (4u << 20)) {  // small tables land in a page-locked buffer (one DMA each, no pageable staging)
+  if (a->prefetched && a->h_stage_bytes >= wbytes + kbytes) {  // already here (agg_launch), and agg_resolve has waited for it
+    memcpy(hw.data(), a->h_stage, wbytes);
+    if (kbytes) memcpy(hk.data(), a->h_stage + wbytes, kbytes);
+  } else if (wbytes + kbytes <= (4u << 20)) {  // small tables land in a page-locked buffer (one DMA each, no pageable staging)
     if (a->h_stage_bytes < wbytes + kbytes) {
       if (a->h_stage) CUDA_TRY(cudaFreeHost(a->h_stage));
       a->h_stage = nullptr;
@@ -2854,6 +2878,7 @@ extern "C" int32_t llkv_gpu_agg_merge(llkv_gpu_agg* a) {
   CUDA_TRY(cudaSetDevice(ctx->device));
   if (a->err_code) return set_error(a->err_code, "%s", a->err_msg.c_str());
   int32_t rc;
+  a->prefetched = false;  // the merge rewrites the table
   const int N = ctx->n_ranks;
   const int nccl_u64 = 5 /* ncclUint64 */, nccl_max = 2 /* ncclMax */;
   // Ungrouped state: the merge is queued behind the scan on the same stream without waiting for it (there is no table
