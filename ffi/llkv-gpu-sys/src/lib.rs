@@ -84,6 +84,23 @@ pub struct llkv_group_key {
     pub _pad: [u8; 3],
 }
 
+/// One column as `llkv_gpu_debug_plan` sees it: type and statistics, no data.
+#[repr(C)]
+#[derive(Clone, Copy, Default)]
+pub struct llkv_debug_column {
+    pub logical_field_id: u64,
+    pub prim_type: i32,
+    pub precision: u8,
+    pub scale: i8,
+    pub has_minmax: u8,
+    pub dec_fits_i64: u8,
+    pub min_value: i64,
+    pub max_value: i64,
+    pub n_rows: u64,
+    pub max_strlen: u8,
+    pub _pad: [u8; 7],
+}
+
 /// ChunkMetadata (llkv-column-map/src/store/descriptor.rs:23-32).
 #[repr(C)]
 #[derive(Clone, Copy, Default, Debug)]
@@ -179,6 +196,14 @@ extern "C" {
     pub fn llkv_gpu_host_free(p: *mut c_void) -> i32;
     pub fn llkv_gpu_host_register(p: *const c_void, bytes: u64) -> i32;
     pub fn llkv_gpu_host_unregister(p: *const c_void) -> i32;
+
+    /// Compiles a plan against column statistics only (no device): the lean program's listing, optionally its specialised
+    /// cubin.  For tooling and CPU-side tests.
+    pub fn llkv_gpu_debug_plan(cols: *const llkv_debug_column, n_cols: i32, prog: *const llkv_gpu_program, created_by_col: i32,
+                               deleted_by_col: i32, txn_id: u64, snapshot_id: u64, specs: *const llkv_agg_spec, n_aggs: i32,
+                               nodes: *const llkv_scalar_node, n_nodes: i32, group_key_fields: *const u64, n_keys: i32,
+                               expr_mode: i32, cardinality_hint: u64, block_threads: i32, rows_per_thread: i32, stages: i32,
+                               ctas_per_sm: i32, jit: i32, cubin_path: *const c_char, out_text: *mut c_char, out_cap: u64) -> i32;
 
     pub fn llkv_gpu_descriptor_parse(bytes: *const c_void, len: u64, out: *mut llkv_column_descriptor) -> i32;
     pub fn llkv_gpu_descriptor_page_parse(bytes: *const c_void, len: u64, next_page_pk: *mut u64, out: *mut llkv_chunk_metadata, capacity: u64, n_entries: *mut u64) -> i32;

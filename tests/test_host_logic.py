@@ -117,3 +117,14 @@ def test_serialize_rejects_nulls_and_varlen():
     col = HostColumn.utf8(1, ["a", None])
     with pytest.raises(ValueError):
         col.serialize()
+
+
+def test_rust_sys_crate_declares_every_function_of_the_header():
+    """ffi/llkv-gpu-sys is authored, not compiled here: at least every entry point of include/llkv_gpu.h must be declared."""
+    import os
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    rs = open(os.path.join(root, "ffi", "llkv-gpu-sys", "src", "lib.rs")).read()
+    declared = set(re.findall(r"pub fn (llkv_gpu_[a-z0-9_]+)\s*\(", rs))
+    missing = [s for s in header_symbols() if s not in declared]
+    assert not missing, missing
