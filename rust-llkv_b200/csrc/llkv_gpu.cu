@@ -407,6 +407,7 @@ struct llkv_gpu_agg {
   unsigned char* h_stage = nullptr;  // pinned landing buffer of finalize (small tables)
   size_t h_stage_bytes = 0;
   bool prefetched = false;  // h_stage holds the table as the last run left it (copy queued right behind the scan)
+  cudaEvent_t stage_ev = nullptr;  // recorded behind that copy
   Plan* d_plan = nullptr;
   Plan* h_plan = nullptr;  // pinned
   CompileResult cr;
@@ -1820,6 +1821,7 @@ extern "C" void llkv_gpu_agg_destroy(llkv_gpu_agg* a) {
   if (a->part_out) cudaFree(a->part_out);
   if (a->part_cursor) cudaFree(a->part_cursor);
   if (a->d_tile_list) cudaFree(a->d_tile_list);
+  if (a->stage_ev) cudaEventDestroy(a->stage_ev);
   if (a->d_flags) cudaFree(a->d_flags);
   if (a->d_plan) cudaFree(a->d_plan);
   if (a->h_plan) cudaFreeHost(a->h_plan);
@@ -2007,6 +2009,30 @@ static int32_t agree_key_stats(llkv_gpu_ctx* ctx, llkv_gpu_agg* a, CompileReques
     }
     c.max_strlen = (uint8_t)(~v[4 * k + 2]);
   }
+  return LLKV_OK;
+}
+
+// Queues, behind whatever the stream holds, the copy of the device status word and — for small tables (an ungrouped state
+// row, Q1's 32 rows) — of the table itself into page-locked memory: finalize then needs the one synchronisation that
+// settles the run and no copy of its own.  Called after the scan and again after a merge that was queued behind it.
+static int32_t agg_queue_result_copy(llkv_gpu_agg* a) {
+  llkv_gpu_ctx* ctx = a->ctx;
+  CUDA_TRY(cudaMemcpyAsync(a->h_flags, a->d_flags, 4, cudaMemcpyDeviceToHost, ctx->stream));
+  a->prefetched = false;
+  const size_t wbytes = (size_t)(a->gcap + 2) * a->n_gwords * 8, kbytes = a->cr.plan.n_keys ? (size_t)a->gcap * 8 : 0;
+  if (wbytes + kbytes > (64u << 10)) return LLKV_OK;
+  if (a->h_stage_bytes < wbytes + kbytes) {
+    if (a->h_stage) CUDA_TRY(cudaFreeHost(a->h_stage));
+    a->h_stage = nullptr;
+    a->h_stage_bytes = 0;
+    CUDA_TRY(cudaHostAlloc((void**)&a->h_stage, 64u << 10, cudaHostAllocDefault));
+    a->h_stage_bytes = 64u << 10;
+  }
+  CUDA_TRY(cudaMemcpyAsync(a->h_stage, a->gwords, wbytes, cudaMemcpyDeviceToHost, ctx->stream));
+  if (kbytes) CUDA_TRY(cudaMemcpyAsync(a->h_stage + wbytes, a->gkeys, kbytes, cudaMemcpyDeviceToHost, ctx->stream));
+  if (!a->stage_ev) CUDA_TRY(cudaEventCreateWithFlags(&a->stage_ev, cudaEventDisableTiming));
+  CUDA_TRY(cudaEventRecord(a->stage_ev, ctx->stream));
+  a->prefetched = true;
   return LLKV_OK;
 }
 
@@ -2332,25 +2358,7 @@ static int32_t agg_launch(llkv_gpu_agg* a, const llkv_gpu_program* prog, int app
     if (use_tile_list ? list_pos >= list_n : re >= row_end) break;
   }
   if (ctx->timing) CUDA_TRY(cudaEventRecord(ctx->ev1, ctx->stream));
-  CUDA_TRY(cudaMemcpyAsync(a->h_flags, a->d_flags, 4, cudaMemcpyDeviceToHost, ctx->stream));
-  // Small tables (an ungrouped state row, Q1's 32 rows) travel to the host right behind the scan, so finalize needs the
-  // one synchronisation that settles the run and no copy of its own.
-  a->prefetched = false;
-  {
-    const size_t wbytes = (size_t)(a->gcap + 2) * a->n_gwords * 8, kbytes = p.n_keys ? (size_t)a->gcap * 8 : 0;
-    if (wbytes + kbytes <= (64u << 10)) {
-      if (a->h_stage_bytes < wbytes + kbytes) {
-        if (a->h_stage) CUDA_TRY(cudaFreeHost(a->h_stage));
-        a->h_stage = nullptr;
-        a->h_stage_bytes = 0;
-        CUDA_TRY(cudaHostAlloc((void**)&a->h_stage, 64u << 10, cudaHostAllocDefault));
-        a->h_stage_bytes = 64u << 10;
-      }
-      CUDA_TRY(cudaMemcpyAsync(a->h_stage, a->gwords, wbytes, cudaMemcpyDeviceToHost, ctx->stream));
-      if (kbytes) CUDA_TRY(cudaMemcpyAsync(a->h_stage + wbytes, a->gkeys, kbytes, cudaMemcpyDeviceToHost, ctx->stream));
-      a->prefetched = true;
-    }
-  }
+  if ((rc = agg_queue_result_copy(a))) return rc;
   a->info.rows = row_end - row_begin;
   a->info.kernel_launches = launches;
   a->info.used_wide_path = a->cr.wide ? 1 : 0;
@@ -2667,7 +2675,10 @@ static int32_t agg_collect(llkv_gpu_agg* a, std::vector<u64>& hk, std::vector<u6
   hk.resize(a->gcap);
   hw.resize(rows * a->n_gwords);
   const size_t wbytes = hw.size() * 8, kbytes = a->cr.plan.n_keys ? hk.size() * 8 : 0;
-  if (a->prefetched && a->h_stage_bytes >= wbytes + kbytes) {  // already here (agg_launch), and agg_resolve has waited for it
+  if (a->prefetched && a->h_stage_bytes >= wbytes + kbytes) {  // already on its way (agg_queue_result_copy)
+    // usually complete: agg_resolve waited for the run.  Not when the copy was queued with no run pending (a merge behind
+    // a run that had to be settled first).
+    CUDA_TRY(cudaEventSynchronize(a->stage_ev));
     memcpy(hw.data(), a->h_stage, wbytes);
     if (kbytes) memcpy(hk.data(), a->h_stage + wbytes, kbytes);
   } else if (wbytes + kbytes <= (4u << 20)) {  // small tables land in a page-locked buffer (one DMA each, no pageable staging)
@@ -2888,10 +2899,15 @@ extern "C" int32_t llkv_gpu_agg_merge(llkv_gpu_agg* a) {
   // that is settled locally first.)
   if (a->frozen && a->cr.plan.n_keys == 0 && ctx->nccl_comm && N > 1) {
     if (a->cr.can_narrow_fail && (rc = agg_resolve(a))) return rc;
+    if (!a->pending.active) {  // nothing left to settle from the run: the merge itself still has a status to report
+      a->pending.active = true;
+      a->pending.timed = false;
+      a->pending.has_backup = false;
+    }
     if (ctx->p2p_merge && a->n_gwords < 127) {  // NVLink peer stores + flags, no collective library on the path
       CUDA_TRY(launch_merge_ungrouped_p2p(a->gwords, ctx->peer_mbox, N, ctx->rank, a->n_gwords, ++ctx->merge_epoch, a->d_gclass, a->d_flags,
                                           ctx->stream));
-      return LLKV_OK;
+      return agg_queue_result_copy(a);  // (also the status word again: the merge kernel reports a peer that never arrives)
     }
     const size_t word_elems = (size_t)(3 * a->n_gwords);
     if (a->mg_word_elems < word_elems * (size_t)N) {
@@ -2901,7 +2917,7 @@ extern "C" int32_t llkv_gpu_agg_merge(llkv_gpu_agg* a) {
     }
     NCCL_TRY(g_nccl.all_gather(a->gwords, a->mg_words, word_elems, nccl_u64, ctx->nccl_comm, ctx->stream));
     CUDA_TRY(launch_merge_ungrouped(a->gwords, a->mg_words, N, a->n_gwords, word_elems, a->d_gclass, ctx->stream));
-    return LLKV_OK;
+    return agg_queue_result_copy(a);
   }
   rc = agg_resolve(a);
   if (rc) return rc;
@@ -2963,5 +2979,7 @@ extern "C" int32_t llkv_gpu_agg_merge(llkv_gpu_agg* a) {
     memcpy(a->h_plan, &mp, sizeof(Plan));
     CUDA_TRY(cudaMemcpyAsync(a->d_plan, a->h_plan, sizeof(Plan), cudaMemcpyHostToDevice, ctx->stream));
   }
+  if ((rc = agg_queue_result_copy(a))) return rc;
+  CUDA_TRY(cudaStreamSynchronize(ctx->stream));  // (no run is pending here: nothing else would wait for the copy)
   return LLKV_OK;
 }
