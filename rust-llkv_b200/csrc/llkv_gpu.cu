@@ -2177,16 +2177,25 @@ static int32_t agg_launch(llkv_gpu_agg* a, const llkv_gpu_program* prog, int app
     const u64 P = 1ull << bits;
     u64 batch_rows = 1ull << 28;
     if (const char* e = getenv("LLKV_GPU_PART_BATCH_ROWS")) batch_rows = std::max<u64>(p.tile_rows, strtoull(e, nullptr, 10));  // tests: several launches on small tables
-    max_rows_per_launch = std::max<u64>(p.tile_rows, std::min<u64>(max_rows_per_launch, batch_rows) / p.tile_rows * p.tile_rows);
-    const u64 launch_rows = std::min<u64>(row_end - row_begin + p.tile_rows, max_rows_per_launch);
-    const u64 part_cap = (launch_rows / P + launch_rows / (4 * P) + 1024 + 15) / 16 * 16;
-    const size_t elems = (size_t)(P * lean.s.n_fields * part_cap);
-    if (a->part_out_elems < elems) {
+    const u64 dense_max_rows = max_rows_per_launch;
+    u64 part_cap = 0;
+    for (;;) {  // the tuple buffers of one launch; when HBM is short the launches get smaller instead
+      max_rows_per_launch = std::max<u64>(p.tile_rows, std::min<u64>(dense_max_rows, batch_rows) / p.tile_rows * p.tile_rows);
+      const u64 launch_rows = std::min<u64>(row_end - row_begin + p.tile_rows, max_rows_per_launch);
+      part_cap = (launch_rows / P + launch_rows / (4 * P) + 1024 + 15) / 16 * 16;
+      const size_t elems = (size_t)(P * lean.s.n_fields * part_cap);
+      if (a->part_out_elems >= elems) break;
       if (a->part_out) CUDA_TRY(cudaFree(a->part_out));
       a->part_out = nullptr;
       a->part_out_elems = 0;
-      CUDA_TRY(cudaMalloc((void**)&a->part_out, elems * 8));
-      a->part_out_elems = elems;
+      if (cudaMalloc((void**)&a->part_out, elems * 8) == cudaSuccess) {
+        a->part_out_elems = elems;
+        break;
+      }
+      cudaGetLastError();
+      a->part_out = nullptr;
+      if (batch_rows <= (1ull << 22)) return set_error(LLKV_ERR_IO, "out of device memory for the tuple partitions of a GROUP BY (%zu bytes)", elems * 8);
+      batch_rows >>= 1;
     }
     if (!a->part_cursor) CUDA_TRY(cudaMalloc((void**)&a->part_cursor, kMaxPartitions * 4));
     lean.part_out = a->part_out;

@@ -132,18 +132,15 @@ __global__ void __launch_bounds__(kPartThreads, kMinBlocks) partition_apply_kern
 
 cudaError_t launch_partition_apply(const PartPlan& plan, uint32_t grid, cudaStream_t stream) {
   const uint32_t nv = plan.n_vops;
-  int variant = 0;
-  if (const char* e = getenv("LLKV_GPU_PART_VARIANT")) variant = atoi(e);  // experiments
-  // grid = `sms` x the kernel's resident CTAs per SM (the caller passes grid = SM count): all CTAs are resident at once
+  // grid = `sms` x the kernel's resident CTAs per SM (the caller passes grid = SM count): all CTAs are resident at once.
+  // Four tuples per thread and 1024 threads per SM measured best (tools/exp_part.py history in profiles/r01_summary.md:
+  // two tuples x 1536 threads 7.4 ms, eight x 512 6.8 ms, four x 1024 6.5 ms per 200 M rows).
 #define LLKV_PART_LAUNCH(NV, U, B)                                                \
   do {                                                                            \
     partition_apply_kernel<NV, U, B><<<grid * B, kPartThreads, 0, stream>>>(plan); \
     return cudaGetLastError();                                                    \
   } while (0)
   if (nv == 0) LLKV_PART_LAUNCH(0, 4, 4);
-  if (nv == 1 && variant == 1) LLKV_PART_LAUNCH(1, 8, 2);
-  if (nv == 1 && variant == 2) LLKV_PART_LAUNCH(1, 2, 6);
-  if (nv == 1 && variant == 3) LLKV_PART_LAUNCH(1, 8, 3);
   if (nv == 1) LLKV_PART_LAUNCH(1, 4, 4);
   if (nv == 2) LLKV_PART_LAUNCH(2, 4, 4);
   if (nv <= 4) LLKV_PART_LAUNCH(4, 4, 2);
