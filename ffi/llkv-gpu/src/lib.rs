@@ -1,0 +1,219 @@
+//! Safe handles over `llkv-gpu-sys` in the vocabulary of the reference: what `INTEGRATION.md` section 3 calls `GpuPath`
+//! is built from these.  Authored against jzombie/rust-llkv v0.8.5-alpha, not compiled here (no Rust toolchain in the
+//! image); every call below is exercised through the same C ABI by the Python / C++ host mirrors in the test-suite.
+//!
+//! Ownership and threading follow `include/llkv_gpu.h`: handles are `Send`, calls on one handle are serialised by
+//! `&mut self`, the library never calls back into Rust, and host buffers only have to outlive the call that reads them
+//! (`append_*` until `seal`).
+use std::ffi::c_void;
+use std::ptr;
+use std::sync::Arc;
+
+use llkv_gpu_sys as sys;
+use llkv_result::{Error, Result};
+use llkv_storage::pager::{BatchGet, GetResult, Pager};
+use llkv_storage::types::PhysicalKey;
+
+/// Status codes are `llkv_result::Error` in variant order (`llkv-result/src/error.rs:31-176`).
+fn check(rc: i32) -> Result<()> {
+    if rc == 0 {
+        return Ok(());
+    }
+    let mut buf = vec![0u8; 1024];
+    let n = unsafe { sys::llkv_gpu_last_error(buf.as_mut_ptr().cast(), buf.len()) }.min(buf.len() - 1);
+    let msg = String::from_utf8_lossy(&buf[..n]).into_owned();
+    Err(match rc {
+        1 => Error::Io(std::io::Error::other(msg)),
+        3 => Error::InvalidArgumentError(msg),
+        4 => Error::NotFound,
+        9 => Error::ExprCast(msg),
+        10 => Error::PredicateBuild(msg),
+        _ => Error::Internal(msg),
+    })
+}
+
+/// One GPU: streams, pinned staging ring, the registry of resident columns.  There is no CPU fallback: creating a
+/// context on a machine without a CUDA device is an error.
+pub struct Context {
+    raw: *mut sys::llkv_gpu_ctx,
+}
+unsafe impl Send for Context {}
+unsafe impl Sync for Context {} // the registry is only mutated through handles that borrow the context
+
+impl Context {
+    pub fn new(device_ordinal: i32) -> Result<Arc<Self>> {
+        let mut raw = ptr::null_mut();
+        check(unsafe { sys::llkv_gpu_ctx_create(device_ordinal, 4, 64 << 20, &mut raw) })?;
+        Ok(Arc::new(Self { raw }))
+    }
+}
+impl Drop for Context {
+    fn drop(&mut self) {
+        unsafe { sys::llkv_gpu_ctx_destroy(self.raw) }
+    }
+}
+
+/// A column resident in HBM (`ColumnStore` scan source, `llkv-column-map/src/store/scan/mod.rs:191`).
+pub struct ResidentColumn {
+    ctx: Arc<Context>,
+    raw: *mut sys::llkv_gpu_column,
+}
+unsafe impl Send for ResidentColumn {}
+
+impl ResidentColumn {
+    /// The descriptor walk of `unsorted_visit` (`llkv-column-map/src/store/scan/unsorted.rs:202-241`): descriptor ->
+    /// pages (one get per page) -> one batched get of every chunk -> `llkv_gpu_column_append_blob` per chunk -> seal.
+    /// Tables are dense (row ids `0..n`, `dense_row_runs`, `scan/filter.rs:1510-1582`), so each chunk continues the last.
+    pub fn load<P: Pager>(ctx: &Arc<Context>, pager: &P, descriptor_pk: PhysicalKey, logical_field_id: u64, prim_type: i32,
+                          precision: u8, scale: i8) -> Result<Self> {
+        let mut raw = ptr::null_mut();
+        check(unsafe { sys::llkv_gpu_column_register(ctx.raw, logical_field_id, prim_type, precision, scale, &mut raw) })?;
+        let col = Self { ctx: ctx.clone(), raw };
+        let get_one = |key: PhysicalKey| -> Result<P::Blob> {
+            match pager.batch_get(&[BatchGet::Raw { key }])?.pop() {
+                Some(GetResult::Raw { bytes, .. }) => Ok(bytes),
+                _ => Err(Error::NotFound),
+            }
+        };
+        let desc_blob = get_one(descriptor_pk)?;
+        let mut desc = sys::llkv_column_descriptor::default();
+        let b: &[u8] = desc_blob.as_ref();
+        check(unsafe { sys::llkv_gpu_descriptor_parse(b.as_ptr().cast(), b.len() as u64, &mut desc) })?;
+        check(unsafe { sys::llkv_gpu_column_reserve(col.raw, desc.total_row_count) })?;
+
+        let mut metas: Vec<sys::llkv_chunk_metadata> = Vec::with_capacity(desc.total_chunk_count as usize);
+        let mut page_pk = desc.head_page_pk;
+        let mut page = vec![sys::llkv_chunk_metadata::default(); 256]; // DESCRIPTOR_ENTRIES_PER_PAGE
+        while page_pk != 0 {
+            let blob = get_one(page_pk)?;
+            let b: &[u8] = blob.as_ref();
+            let mut n = 0u64;
+            check(unsafe { sys::llkv_gpu_descriptor_page_parse(b.as_ptr().cast(), b.len() as u64, &mut page_pk, page.as_mut_ptr(), 256, &mut n) })?;
+            metas.extend(page[..n as usize].iter().filter(|m| m.row_count > 0));
+        }
+        let gets: Vec<BatchGet> = metas.iter().map(|m| BatchGet::Raw { key: m.chunk_pk }).collect();
+        let mut row_id_base = 0u64;
+        // the blobs (mmap-backed EntryHandles) stay alive until seal() returns: append_blob may still be reading them
+        let blobs = pager.batch_get(&gets)?;
+        for (meta, got) in metas.iter().zip(blobs.iter()) {
+            let GetResult::Raw { bytes, .. } = got else { return Err(Error::NotFound) };
+            let b: &[u8] = bytes.as_ref();
+            check(unsafe { sys::llkv_gpu_column_append_blob(col.raw, meta.chunk_pk, b.as_ptr().cast(), b.len() as u64, ptr::null(), row_id_base) })?;
+            row_id_base += meta.row_count;
+        }
+        check(unsafe { sys::llkv_gpu_column_seal(col.raw) })?;
+        drop(blobs);
+        Ok(col)
+    }
+
+    pub fn rows(&self) -> Result<u64> {
+        let mut n = 0u64;
+        check(unsafe { sys::llkv_gpu_column_rows(self.raw, &mut n) })?;
+        Ok(n)
+    }
+}
+impl Drop for ResidentColumn {
+    fn drop(&mut self) {
+        unsafe { sys::llkv_gpu_column_destroy(self.raw) };
+        let _ = &self.ctx; // the context outlives its columns
+    }
+}
+
+/// `ProgramCompiler::compile` output (`llkv-compute/src/program.rs:271-298`) on the device side of the boundary.  The
+/// flattening of `EvalOp` / `OwnedFilter` / `ScalarExpr` into the `llkv_*` arrays is mechanical (children before parents;
+/// `rust-llkv_b200/host/llkv_gpu.hpp: ProgramCompiler` is the same code in C++).
+pub struct Program {
+    raw: *mut sys::llkv_gpu_program,
+}
+unsafe impl Send for Program {}
+
+impl Program {
+    pub fn from_flat(ctx: &Context, ops: &[sys::llkv_eval_op], literals: &[sys::llkv_literal], nodes: &[sys::llkv_scalar_node],
+                     list_roots: &[i32]) -> Result<Self> {
+        let mut raw = ptr::null_mut();
+        check(unsafe {
+            sys::llkv_gpu_program_compile(ctx.raw, ops.as_ptr(), ops.len() as i32, literals.as_ptr(), literals.len() as i32, nodes.as_ptr(),
+                                          nodes.len() as i32, list_roots.as_ptr(), list_roots.len() as i32, &mut raw)
+        })?;
+        Ok(Self { raw })
+    }
+}
+impl Drop for Program {
+    fn drop(&mut self) {
+        unsafe { sys::llkv_gpu_program_destroy(self.raw) }
+    }
+}
+
+/// `MvccRowIdFilter::new(txn_manager, snapshot)` (`llkv-transaction/src/helpers.rs:259-312`): the snapshot plus every
+/// transaction id whose `TxnIdManager::status` is Active or Aborted.
+pub fn set_snapshot(ctx: &Context, table_id: u64, created_by: &ResidentColumn, deleted_by: &ResidentColumn, txn_id: u64,
+                    snapshot_id: u64, noncommitted: &[u64]) -> Result<()> {
+    check(unsafe {
+        sys::llkv_gpu_mvcc_set(ctx.raw, table_id, created_by.raw, deleted_by.raw, txn_id, snapshot_id, noncommitted.as_ptr(), noncommitted.len() as i32)
+    })
+}
+
+/// A set of `AggregateState`s fused with the scan that feeds them: one call per query instead of one
+/// `AggregateAccumulator::update` per 65 536-row batch (`llkv-aggregate/src/lib.rs:463,759,1488`;
+/// `llkv-scan/src/execute.rs:47-295`).
+pub struct Aggregation {
+    raw: *mut sys::llkv_gpu_agg,
+    n_aggs: usize,
+    n_keys: usize,
+}
+unsafe impl Send for Aggregation {}
+
+impl Aggregation {
+    pub fn new(ctx: &Context, table_id: u64, specs: &[sys::llkv_agg_spec], nodes: &[sys::llkv_scalar_node], group_key_fields: &[u64],
+               expr_mode: i32, cardinality_hint: u64) -> Result<Self> {
+        let mut raw = ptr::null_mut();
+        check(unsafe {
+            sys::llkv_gpu_agg_create(ctx.raw, table_id, specs.as_ptr(), specs.len() as i32, nodes.as_ptr(), nodes.len() as i32,
+                                     group_key_fields.as_ptr(), group_key_fields.len() as i32, expr_mode, cardinality_hint, &mut raw)
+        })?;
+        Ok(Self { raw, n_aggs: specs.len(), n_keys: group_key_fields.len() })
+    }
+
+    /// Scans rows `[row_begin, row_end)`; asynchronous — `finalize` settles the run (and reruns wider / with a larger group
+    /// table if the device asked for it).
+    pub fn run(&mut self, filter: Option<&Program>, apply_mvcc: bool, row_begin: u64, row_end: u64) -> Result<()> {
+        check(unsafe { sys::llkv_gpu_agg_run(self.raw, filter.map_or(ptr::null(), |p| p.raw.cast_const()), apply_mvcc as i32, row_begin, row_end) })
+    }
+
+    /// `AggregateAccumulator::finalize` for every aggregate of every group, groups in first-appearance order
+    /// (`llkv-executor/src/lib.rs:5064-5089`): (values, keys), `n_aggs` / `n_keys` entries per group.
+    pub fn finalize(&mut self) -> Result<(Vec<sys::llkv_agg_value>, Vec<sys::llkv_group_key>)> {
+        let mut groups = 0u64;
+        check(unsafe { sys::llkv_gpu_agg_group_count(self.raw, &mut groups) })?;
+        let g = groups as usize;
+        let mut values: Vec<sys::llkv_agg_value> = Vec::with_capacity(g * self.n_aggs);
+        let mut keys: Vec<sys::llkv_group_key> = Vec::with_capacity(g * self.n_keys);
+        check(unsafe { sys::llkv_gpu_agg_finalize(self.raw, values.as_mut_ptr(), keys.as_mut_ptr(), groups, &mut groups) })?;
+        unsafe {
+            values.set_len(groups as usize * self.n_aggs);
+            keys.set_len(groups as usize * self.n_keys);
+        }
+        Ok((values, keys))
+    }
+}
+impl Drop for Aggregation {
+    fn drop(&mut self) {
+        unsafe { sys::llkv_gpu_agg_destroy(self.raw) }
+    }
+}
+
+/// Page-locks the pager's mapping for the lifetime of the guard so chunk appends DMA straight out of it.
+pub struct RegisteredMapping(*const c_void);
+impl RegisteredMapping {
+    /// # Safety
+    /// `bytes` must stay mapped until the guard is dropped.
+    pub unsafe fn new(bytes: &[u8]) -> Result<Self> {
+        check(sys::llkv_gpu_host_register(bytes.as_ptr().cast(), bytes.len() as u64))?;
+        Ok(Self(bytes.as_ptr().cast()))
+    }
+}
+impl Drop for RegisteredMapping {
+    fn drop(&mut self) {
+        unsafe { sys::llkv_gpu_host_unregister(self.0) };
+    }
+}
