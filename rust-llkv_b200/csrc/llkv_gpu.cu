@@ -1497,9 +1497,14 @@ static int32_t lean_geometry(const LeanTune& tn, const Plan& p, uint64_t row_beg
       got_ctas = best_c;
       break;
     }
-    if (p.n_keys && fg > 2) fg /= 2;
-    else if (nc > 32) nc /= 2;
-    else break;
+    // Nothing fits: fewer consumer threads first (their accumulators are the fat part), fewer CTA-local group slots last
+    // — a group without a slot sends its rows to the global table one contended atomic at a time (Q1 with two slots for
+    // its four groups: 2 ms instead of 0.035 ms per million rows, tools/tune_check.py).
+    if (nc > 32) nc = nc > 64 ? (nc / 2 + 31) / 32 * 32 : 32;  // whole warps
+    else if (p.n_keys && fg > 2) {
+      fg /= 2;
+      nc = NC;
+    } else break;
   }
   if (got_ctas) {
     const uint32_t T = s.tile_rows;
