@@ -363,6 +363,7 @@ struct llkv_gpu_agg {
   std::vector<uint64_t> keys;
   int32_t expr_mode = LLKV_EXPR_ARROW;
   uint64_t hint = 0;
+  uint64_t observed_groups = 0;  // groups a finalize has seen: the next run sizes its CTA-local slot table for at least that many
   // accumulator state
   bool frozen = false;
   uint32_t n_gwords = 0;
@@ -2088,7 +2089,10 @@ static int32_t agg_launch(llkv_gpu_agg* a, const llkv_gpu_program* prog, int app
       tn.partition = which == 2;
       Geometry gg;
       uint32_t cc = 1;
-      int32_t grc = lean_geometry(tn, p, row_begin, row_end, a->hint, a->lean2[which], gg, &cc);
+      // (a hint below the number of groups already seen would leave groups without a CTA-local slot: every row of such a
+      // group is a contended atomic on the global table)
+      const uint64_t hint_eff = a->hint && a->observed_groups > a->hint ? a->observed_groups : a->hint;
+      int32_t grc = lean_geometry(tn, p, row_begin, row_end, hint_eff, a->lean2[which], gg, &cc);
       if (grc) return grc;
       a->lean_grid2[which] = gg.grid;
       a->lean_ctas2[which] = cc;
@@ -2724,6 +2728,10 @@ static int32_t agg_collect(llkv_gpu_agg* a, std::vector<u64>& hk, std::vector<u6
   }
   // first-appearance order of the groups (llkv-executor/src/lib.rs:5064-5089)
   std::sort(groups.begin(), groups.end(), [](const GroupRef& x, const GroupRef& y) { return x.first_row < y.first_row; });
+  if (a->hint && a->hint <= 128 && groups.size() > a->hint && groups.size() > a->observed_groups) {
+    a->observed_groups = groups.size();  // the caller's hint was low: later runs of this aggregate get more CTA-local slots
+    a->lean_have[0] = a->lean_have[1] = a->lean_have[2] = false;
+  }
   return LLKV_OK;
 }
 

@@ -203,3 +203,27 @@ def test_four_slot_associative_group_table(gpu_ctx, mode, hint):
             dm.destroy()
     finally:
         gpu_ctx.set_jit(1)
+
+
+def test_a_low_cardinality_hint_is_corrected_after_the_first_finalize(gpu_ctx):
+    """Seven groups under a hint of 3: the first run has four CTA-local slots, so three groups send their rows to the global
+    table one atomic at a time.  finalize sees seven groups and the next run of the same aggregate gets eight slots."""
+    from llkv_b200 import gpu
+    rng = np.random.default_rng(5)
+    n = 80_000
+    t = HostTable(1).add(HostColumn(tpch.K_FIELD, DataType.Int64, rng.integers(0, 7, n, dtype=np.int64))).add(
+        HostColumn(tpch.V_FIELD, DataType.Int64, rng.integers(-1000, 1000, n, dtype=np.int64)))
+    dt = gpu.DeviceTable.from_host(gpu_ctx, t)
+    want = oracle.aggregate(t, None, tpch.highcard_aggregates(), None, (tpch.K_FIELD,), group_capacity=16)
+    agg = gpu.Aggregation(dt, tpch.highcard_aggregates(), (tpch.K_FIELD,), cardinality_hint=3)
+    try:
+        slots = []
+        for _ in range(3):
+            agg.reset()
+            agg.run(None, False)
+            util.assert_same_result(agg.finalize(16), want, 1e-12)
+            slots.append(agg.run_info().fast_groups)
+        assert slots == [4, 8, 8]
+    finally:
+        agg.destroy()
+        dt.destroy()
