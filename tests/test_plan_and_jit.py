@@ -115,3 +115,15 @@ def test_partitioned_scan_compiles_for_sm_100a(tmp_path):
     assert "UBLKCP" in sass and "BAR.SYNC" in sass and "ATOMS.ADD" in sass and "ATOMG.E.ADD" in sass and "STG.E.EF.64" in sass
     usage = subprocess.run([cuobjdump, "-res-usage", cubin], capture_output=True, text=True, check=True).stdout
     assert int(usage.split("STACK:")[1].split()[0]) == 0
+
+
+def test_pinned_geometry_that_does_not_fit_keeps_the_group_slots(lineitem):
+    """llkv_gpu_ctx_set_tuning may pin a geometry that does not fit in shared memory.  The fallback gives up consumer
+    threads (whole warps) before CTA-local group slots: Q1's four groups keep their four slots."""
+    t, snap = lineitem
+    for tune in ((96, 2, 2, 6), (128, 1, 4, 5), (128, 2, 2, 4)):
+        text = gpu.debug_plan(t, tpch.q1_filter(), tpch.q1_aggregates(), snap, group_by=tpch.Q1_GROUP_BY, cardinality_hint=4,
+                              block_threads=tune[0], rows_per_thread=tune[1], stages=tune[2], ctas_per_sm=tune[3])
+        head = text.splitlines()[0]
+        nc = int(head.split("NC=")[1].split()[0])
+        assert " fg=4 " in head and nc % 32 == 0 and f"stages={tune[2]}" in head and f"ctas/SM={tune[3]}" in head, head
