@@ -167,8 +167,13 @@ def test_unclustered_columns_and_changed_columns(gpu_ctx):
         dt.destroy()
 
 
-def test_pruned_scan_feeding_the_partitioned_group_by(gpu_ctx):
+@pytest.mark.parametrize("batch_rows", [0, 9_000])
+def test_pruned_scan_feeding_the_partitioned_group_by(gpu_ctx, monkeypatch, batch_rows):
+    """Also in several launches (the tuple buffers bound a launch; here the bound is lowered): each launch walks its own
+    run of the tile list."""
     from llkv_b200 import gpu
+    if batch_rows:
+        monkeypatch.setenv("LLKV_GPU_PART_BATCH_ROWS", str(batch_rows))
     rng = np.random.default_rng(31)
     n = 200_000
     k = np.sort(rng.integers(0, 60_000, n, dtype=np.int64))
@@ -180,6 +185,7 @@ def test_pruned_scan_feeding_the_partitioned_group_by(gpu_ctx):
         want = oracle.aggregate(t, f, tpch.highcard_aggregates(), None, (tpch.K_FIELD,), group_capacity=1 << 16)
         got, info = run(gpu_ctx, dt, f, tpch.highcard_aggregates(), (tpch.K_FIELD,), hint=60_000, part=2)
         assert info.tiles_pruned > 0 and info.partitions >= 2
+        assert info.kernel_launches >= (8 if batch_rows else 2)
         util.assert_same_result(got, want, REL)
     finally:
         dt.destroy()
