@@ -25,6 +25,15 @@
 //     32 bits (counts, row indices, small sums) are 4 bytes wide.
 //   * At the end the threads' accumulators are reduced per (slot, word) with warp shuffles and folded into the global
 //     group table with one atomic per word.
+//
+// Variants selected by the shape (constants in a specialised build):
+//   * direct_global — high-cardinality GROUP BY: no CTA-local slots, every selected row looks up its row of the global
+//     table (the thread's R probes advance together, round by round) and updates it with one RED per word;
+//   * partition (specialised builds only) — the same plans when the table outgrows L2: instead of updating the table the
+//     CTA writes the tile's (key, row id, operands) tuples into hash partitions (LeanTile::scatter); partition_kernel.cu
+//     folds them partition by partition, inside L2;
+//   * use_tile_list — zone-map pruning: the launch walks LeanPlan::tile_list (the tiles whose zones some conjunct range
+//     leaf can match) instead of the dense tile range.
 #pragma once
 #include "device_util.cuh"
 #include "plan.h"
