@@ -76,6 +76,28 @@ mvcc = {
         {"created_by": MAX, "deleted_by": MAX, "txn_id": 5, "snapshot_id": 4, "noncommitted": [], "visible": False,
          "note": "TXN_ID_NONE creator has status None"},
     ]}
+# COUNT(*) while another connection holds uncommitted deletes / appends.  The counts are the reference's expected outputs;
+# the transaction ids are what TxnIdManager hands out (begin_transaction: snapshot_id = last_committed, txn_id = next++;
+# mark_committed advances last_committed; mvcc.rs:128-201), auto-commit statements read as txn 1 (TXN_ID_AUTO_COMMIT).
+# Rows are described as (count, created_by, deleted_by) runs in table order.
+count_star = {
+    "source": "llkv-slt-tester/tests/slt/duckdb/transactions/count_star_transactions.slt (CREATE TABLE tbl (id INT); "
+              "INSERT INTO tbl FROM range(10000); ...)",
+    "steps": [
+        {"note": "after the auto-commit insert", "rows": [[10000, 1, MAX]], "txn_id": 1, "snapshot_id": 1, "noncommitted": [], "count": 10000},
+        {"note": "con1: BEGIN (txn 2); DELETE WHERE id%2=0; its own COUNT(*)", "rows": [[5000, 1, 2], [5000, 1, MAX]], "interleaved": True,
+         "txn_id": 2, "snapshot_id": 1, "noncommitted": [2], "count": 5000},
+        {"note": "default connection while con1 is open: SELECT COUNT(*), COUNT(*) + 1", "rows": [[5000, 1, 2], [5000, 1, MAX]], "interleaved": True,
+         "txn_id": 1, "snapshot_id": 1, "noncommitted": [2], "count": 10000},
+        {"note": "after con1 COMMIT", "rows": [[5000, 1, 2], [5000, 1, MAX]], "interleaved": True, "txn_id": 1, "snapshot_id": 2, "noncommitted": [],
+         "count": 5000},
+        {"note": "con1: BEGIN (txn 3); INSERT range(10000, 15000); its own COUNT(*)", "rows": [[5000, 1, 2], [5000, 1, MAX], [5000, 3, MAX]],
+         "interleaved": True, "txn_id": 3, "snapshot_id": 2, "noncommitted": [3], "count": 10000},
+        {"note": "default connection while con1 is open", "rows": [[5000, 1, 2], [5000, 1, MAX], [5000, 3, MAX]], "interleaved": True,
+         "txn_id": 1, "snapshot_id": 2, "noncommitted": [3], "count": 5000},
+        {"note": "after con1 COMMIT", "rows": [[5000, 1, 2], [5000, 1, MAX], [5000, 3, MAX]], "interleaved": True, "txn_id": 1, "snapshot_id": 3,
+         "noncommitted": [], "count": 10000},
+    ]}
 aggs = [
     {"name": "avg_decimal128_rounding", "source": "llkv-aggregate/tests/avg_decimal_test.rs:7-52",
      "column": {"type": "Decimal128", "precision": 10, "scale": 2, "values": [1051, 1052]}, "agg": "avg", "expect": 1052, "expect_scale": 2},
@@ -85,5 +107,6 @@ aggs = [
 ]
 out = {"_comment": "Known answers transcribed by hand from the reference's own tests (jzombie/rust-llkv v0.8.5-alpha); "
                    "each entry cites file:line. Written by tests/golden/make_golden.py.",
-       "table_t4": t4, "filter_cases": cases, "computed_cases": computed, "mvcc": mvcc, "aggregate_cases": aggs}
+       "table_t4": t4, "filter_cases": cases, "computed_cases": computed, "mvcc": mvcc, "count_star_transactions": count_star,
+       "aggregate_cases": aggs}
 json.dump(out, open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "reference_known_answers.json"), "w"), indent=1)

@@ -673,3 +673,22 @@ def test_chunk_blobs_appended_from_registered_pager_memory(gpu_ctx):
         gpu.host_unregister(ptr)
         del view
         store.close()
+
+
+@pytest.mark.parametrize("step", G["count_star_transactions"]["steps"], ids=lambda s: s["note"][:40])
+def test_count_star_under_transactions(gpu_ctx, step):
+    """The reference's expected COUNT(*) per connection while another one holds uncommitted deletes / appends
+    (llkv-slt-tester/tests/slt/duckdb/transactions/count_star_transactions.slt), interpreted and specialised."""
+    t = util.count_star_scenario_table(step)
+    snap = Snapshot(step["txn_id"], step["snapshot_id"], tuple(step["noncommitted"]))
+    dt = device_table(gpu_ctx, t)
+    try:
+        for mode in (0, 2):
+            gpu_ctx.set_jit(mode)
+            got = dt.aggregate(None, [AggregateSpec("n", AggregateKind.CountStar()), AggregateSpec("s", AggregateKind.Sum(1, DataType.Int64))], snap)
+            assert got[0][1][0].value == step["count"], step["note"]
+        words, count = dt.filter_bitmap(None, snap)
+        assert count == step["count"]
+    finally:
+        gpu_ctx.set_jit(1)
+        dt.destroy()

@@ -6,7 +6,7 @@ import pytest
 import util
 from llkv_b200 import ffi
 from llkv_b200.expr import AggregateKind, AggregateSpec, DataType, Expr, ScalarExpr
-from llkv_b200.table import HostColumn, HostTable
+from llkv_b200.table import HostColumn, HostTable, Snapshot
 from oracle import oracle
 
 G = util.golden()
@@ -76,3 +76,13 @@ def test_sum_decimal_of_no_rows_is_zero_not_null():
     t = HostTable(1).add(util.column_from_json(1, {"type": "Decimal128", "precision": 10, "scale": 2, "values": []}))
     v = oracle.aggregate(t, None, [AggregateSpec("s", AggregateKind.Sum(1, DataType.Decimal128(10, 2)))])[0][1][0]
     assert v.value == 0 and v.scale == 2
+
+
+@pytest.mark.parametrize("step", G["count_star_transactions"]["steps"], ids=lambda s: s["note"][:40])
+def test_count_star_under_transactions(step):
+    """llkv-slt-tester/tests/slt/duckdb/transactions/count_star_transactions.slt: the counts every connection sees while
+    another one holds uncommitted deletes and appends."""
+    t = util.count_star_scenario_table(step)
+    snap = Snapshot(step["txn_id"], step["snapshot_id"], tuple(step["noncommitted"]))
+    got = oracle.aggregate(t, None, [AggregateSpec("n", AggregateKind.CountStar())], snap)
+    assert got[0][1][0].value == step["count"], step["note"]

@@ -115,3 +115,27 @@ def assert_same_result(got, want, rel=1e-12, ordered=True):
         assert len(gv) == len(wv)
         for i, (a, b) in enumerate(zip(gv, wv)):
             assert values_equal(a, b, rel), f"group {gk} aggregate {i}: {a} != {b}"
+
+
+def count_star_scenario_table(step) -> HostTable:
+    """Table state of one step of the COUNT(*)-under-transactions scenario (tests/golden: count_star_transactions): an id
+    column plus created_by / deleted_by built from the step's (count, created_by, deleted_by) runs; the first two runs of
+    an "interleaved" step alternate row by row (DELETE ... WHERE id % 2 = 0)."""
+    runs = step["rows"]
+    created, deleted = [], []
+    if step.get("interleaved"):
+        (n0, c0, d0), (n1, c1, d1) = runs[0], runs[1]
+        assert n0 == n1
+        c = np.empty(2 * n0, dtype=np.uint64)
+        d = np.empty(2 * n0, dtype=np.uint64)
+        c[0::2], c[1::2], d[0::2], d[1::2] = c0, c1, d0, d1
+        created.append(c)
+        deleted.append(d)
+        runs = runs[2:]
+    for n, c, d in runs:
+        created.append(np.full(n, c, dtype=np.uint64))
+        deleted.append(np.full(n, d, dtype=np.uint64))
+    created, deleted = np.concatenate(created), np.concatenate(deleted)
+    t = HostTable(1).add(HostColumn(1, DataType.Int64, np.arange(created.size, dtype=np.int64)))
+    t.add_mvcc(created, deleted)
+    return t
