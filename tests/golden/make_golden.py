@@ -98,6 +98,17 @@ count_star = {
         {"note": "after con1 COMMIT", "rows": [[5000, 1, 2], [5000, 1, MAX], [5000, 3, MAX]], "interleaved": True, "txn_id": 1, "snapshot_id": 3,
          "noncommitted": [], "count": 10000},
     ]}
+# Aggregates over an INTEGER column with NULLs (SQL integers are Int64 in the reference).  `base` repeated `repeat` times;
+# null = NULL.  Expected values are the reference's SLT outputs.
+nullable_aggs = [
+    {"name": "null_values_count_sum_min_max", "source": "llkv-slt-tester/tests/slt/duckdb/insert/null_values.slt:24-35 "
+     "(range(100), then five times range(100) followed by 100 NULLs)",
+     "base": list(range(100)) + (list(range(100)) + [None] * 100) * 5, "repeat": 1,
+     "expect": {"count_col": 600, "sum": 29700, "min": 0, "max": 99, "count_star": 1100}},
+    {"name": "big_append_doubling", "source": "llkv-slt-tester/tests/slt/duckdb/append/test_big_append.slow.slt:17-81 "
+     "((1),(2),(3),(NULL) doubled fifteen times)",
+     "base": [1, 2, 3, None], "repeat": 32768, "expect": {"count_star": 131072, "count_col": 98304, "sum": 196608}},
+]
 aggs = [
     {"name": "avg_decimal128_rounding", "source": "llkv-aggregate/tests/avg_decimal_test.rs:7-52",
      "column": {"type": "Decimal128", "precision": 10, "scale": 2, "values": [1051, 1052]}, "agg": "avg", "expect": 1052, "expect_scale": 2},
@@ -108,5 +119,5 @@ aggs = [
 out = {"_comment": "Known answers transcribed by hand from the reference's own tests (jzombie/rust-llkv v0.8.5-alpha); "
                    "each entry cites file:line. Written by tests/golden/make_golden.py.",
        "table_t4": t4, "filter_cases": cases, "computed_cases": computed, "mvcc": mvcc, "count_star_transactions": count_star,
-       "aggregate_cases": aggs}
+       "aggregate_cases": aggs, "nullable_aggregate_cases": nullable_aggs}
 json.dump(out, open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "reference_known_answers.json"), "w"), indent=1)

@@ -692,3 +692,16 @@ def test_count_star_under_transactions(gpu_ctx, step):
     finally:
         gpu_ctx.set_jit(1)
         dt.destroy()
+
+
+@pytest.mark.parametrize("case", G["nullable_aggregate_cases"], ids=lambda c: c["name"])
+def test_aggregates_over_nullable_integers(gpu_ctx, case):
+    """COUNT(i), SUM(i), MIN(i), MAX(i), COUNT(*) over an INTEGER column with NULLs: the reference's SLT outputs."""
+    t = HostTable(1).add(util.nullable_int_column(1, case))
+    names, specs = util.nullable_aggregate_specs(case)
+    dt = device_table(gpu_ctx, t)
+    try:
+        got = dt.aggregate(None, specs)[0][1]
+        assert {n: v.value for n, v in zip(names, got)} == case["expect"]
+    finally:
+        dt.destroy()

@@ -86,3 +86,11 @@ def test_count_star_under_transactions(step):
     snap = Snapshot(step["txn_id"], step["snapshot_id"], tuple(step["noncommitted"]))
     got = oracle.aggregate(t, None, [AggregateSpec("n", AggregateKind.CountStar())], snap)
     assert got[0][1][0].value == step["count"], step["note"]
+
+
+@pytest.mark.parametrize("case", G["nullable_aggregate_cases"], ids=lambda c: c["name"])
+def test_aggregates_over_nullable_integers(case):
+    t = HostTable(1).add(util.nullable_int_column(1, case))
+    names, specs = util.nullable_aggregate_specs(case)
+    got = oracle.aggregate(t, None, specs)[0][1]
+    assert {n: v.value for n, v in zip(names, got)} == case["expect"]

@@ -139,3 +139,19 @@ def count_star_scenario_table(step) -> HostTable:
     t = HostTable(1).add(HostColumn(1, DataType.Int64, np.arange(created.size, dtype=np.int64)))
     t.add_mvcc(created, deleted)
     return t
+
+
+def nullable_int_column(field, case) -> HostColumn:
+    """Int64 column of a golden "nullable_aggregate_cases" entry: `base` (None = NULL) repeated `repeat` times."""
+    from llkv_b200.table import pack_validity
+    base = case["base"] * case["repeat"]
+    valid = np.array([v is not None for v in base], dtype=bool)
+    values = np.array([0 if v is None else v for v in base], dtype=np.int64)
+    return HostColumn(field, DataType.Int64, values, pack_validity(valid))
+
+
+def nullable_aggregate_specs(case):
+    kinds = {"count_col": AggregateKind.Count(1), "sum": AggregateKind.Sum(1, DataType.Int64), "min": AggregateKind.Min(1, DataType.Int64),
+             "max": AggregateKind.Max(1, DataType.Int64), "count_star": AggregateKind.CountStar()}
+    names = list(case["expect"])
+    return names, [AggregateSpec(n, kinds[n]) for n in names]
