@@ -73,3 +73,30 @@ def test_cpp_host_runs_q6_on_the_gpu(tmp_path):
     r = subprocess.run([exe, "1000003"], capture_output=True, text=True)
     assert r.returncode == 0, r.stdout + r.stderr
     assert r.stdout.startswith("ok ") and "lean=1" in r.stdout and "specialised=1" in r.stdout, r.stdout
+
+
+def test_cpp_descriptor_walk_matches_the_python_mirror(tmp_path):
+    """llkv::walk_descriptor (C++ mirror) over an in-memory pager: same surviving chunks as llkv_b200.metadata and the
+    oracle's rule, with and without a pruning range."""
+    from llkv_b200 import metadata
+    from oracle import metadata as om
+    exe = str(tmp_path / "walk")
+    build("descriptor_walk.cpp", exe, link=True)
+    metas = [(1000 + i, 0, 4096, 65560, om.sortable_u64(om.INT64, i * 10 - 700), om.sortable_u64(om.INT64, i * 10 - 691), 0, 10) for i in range(140)]
+    pages = om.descriptor_pages(metas, [500, 501, 502])
+    pager = {499: om.descriptor_bytes((1 << 32) | 7, 500, 502, 140 * 4096, 140, data_type_code=6), **dict(pages)}
+    lines = [f"{k} {v.hex()}" for k, v in pager.items()]
+    m64 = (1 << 64) - 1
+    queries = [(2, 0, 2, 0), (0, (-95) & m64, 1, 205), (1, 9, 2, 0), (0, 5000, 0, 6000)]  # (lower kind, bits, upper kind, bits)
+    lines += [f"walk 499 {om.INT64} {lk} {lb} {uk} {ub}" for lk, lb, uk, ub in queries]
+    env = dict(os.environ)
+    out = subprocess.run([exe], input="\n".join(lines) + "\n", check=True, capture_output=True, text=True, env=env).stdout.splitlines()
+    assert len(out) == len(queries)
+    for (lk, lb, uk, ub), ln in zip(queries, out):
+        f = ln.split()
+        assert f[:4] == ["desc", str(140 * 4096), "140", "6"], ln
+        lower = None if lk == 2 else (lk, lb)
+        upper = None if uk == 2 else (uk, ub)
+        _, want, _ = metadata.walk_descriptor(lambda pks: [pager[k] for k in pks], 499, om.INT64, lower, upper)
+        assert [int(x) for x in f[4:]] == [c.chunk_pk for c in want], (lk, lb, uk, ub)
+    assert out[0].count(" ") == 3 + 140 and out[3].split()[4:] == []  # no range: every chunk; a range above all values: none

@@ -128,3 +128,15 @@ def test_rust_sys_crate_declares_every_function_of_the_header():
     declared = set(re.findall(r"pub fn (llkv_gpu_[a-z0-9_]+)\s*\(", rs))
     missing = [s for s in header_symbols() if s not in declared]
     assert not missing, missing
+
+
+def test_safe_rust_crate_only_calls_declared_sys_functions():
+    """ffi/llkv-gpu (authored, not compiled here) may only use entry points and types the sys crate declares."""
+    import os
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys_rs = open(os.path.join(root, "ffi", "llkv-gpu-sys", "src", "lib.rs")).read()
+    safe_rs = open(os.path.join(root, "ffi", "llkv-gpu", "src", "lib.rs")).read()
+    declared = set(re.findall(r"pub fn (llkv_gpu_[a-z0-9_]+)\s*\(", sys_rs)) | set(re.findall(r"pub struct (llkv_[a-z0-9_]+)", sys_rs))
+    used = set(re.findall(r"sys::(llkv_[a-z0-9_]+)", safe_rs))
+    assert used and not (used - declared), sorted(used - declared)
