@@ -303,8 +303,14 @@ def run_ours(args):
                     ms.append(hagg.run_info().last_kernel_ms)
             hinfo = hagg.run_info()
             hagg.destroy()
-            highcard[name] = {"kernel_ms": statistics.mean(ms), "value": hc_rows / (statistics.mean(ms) * 1e-3), "groups": groups,
-                              "groups_expected": n_unique, "partitions": hinfo.partitions, "launches_per_run": hinfo.kernel_launches}
+            kms_hc = statistics.mean(ms)
+            # HBM bytes the form has to move per row: the two Int64 columns once; partitioned also writes and re-reads
+            # one (key, row id, operand) tuple.  (The per-row form is bound by random sector traffic on the group table,
+            # the partitioned one by L2 request rate: DESIGN.md 3.1b.)
+            bpr = 16 + (48 if mode else 0)
+            highcard[name] = {"kernel_ms": kms_hc, "value": hc_rows / (kms_hc * 1e-3), "groups": groups,
+                              "groups_expected": n_unique, "partitions": hinfo.partitions, "launches_per_run": hinfo.kernel_launches,
+                              "streamed_bytes_per_row": bpr, "streamed_gbs": bpr * hc_rows / (kms_hc * 1e-3) / 1e9}
         ctx.set_partitioning(1)
         hdt.destroy()
     clocks = sampler.stop() if rank == 0 else None  # sampled across the timed regions (Q6, Q1, end to end, high cardinality)
