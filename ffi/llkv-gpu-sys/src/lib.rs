@@ -208,6 +208,7 @@ extern "C" {
     pub fn llkv_gpu_descriptor_parse(bytes: *const c_void, len: u64, out: *mut llkv_column_descriptor) -> i32;
     pub fn llkv_gpu_descriptor_page_parse(bytes: *const c_void, len: u64, next_page_pk: *mut u64, out: *mut llkv_chunk_metadata, capacity: u64, n_entries: *mut u64) -> i32;
     pub fn llkv_gpu_sortable_u64(prim_type: i32, value_bits: u64) -> u64;
+    pub fn llkv_gpu_chunk_stats(prim_type: i32, values: *const c_void, n_rows: u64, validity: *const u8, out: *mut llkv_chunk_metadata) -> i32;
     pub fn llkv_gpu_chunk_overlaps(prim_type: i32, chunk_min_u64: u64, chunk_max_u64: u64, lower: *const llkv_range_bound, upper: *const llkv_range_bound) -> i32;
 
     pub fn llkv_gpu_column_register(ctx: *mut llkv_gpu_ctx, logical_field_id: u64, prim_type: i32, precision: u8, scale: i8, out: *mut *mut llkv_gpu_column) -> i32;

@@ -344,6 +344,14 @@ typedef struct llkv_range_bound {
 int32_t llkv_gpu_chunk_overlaps(int32_t prim_type, uint64_t chunk_min_u64, uint64_t chunk_max_u64, const llkv_range_bound* lower,
                                 const llkv_range_bound* upper);
 
+/* compute_chunk_stats (llkv-column-map/src/store/pruning.rs:272-470) for one chunk of a primitive column: fills
+ * min_val_u64 / max_val_u64 (sortable images), null_count and distinct_count of `out` (the other fields are left alone).
+ * `validity` is an optional Arrow bitmap (LSB first), NULL = all valid.  An empty chunk is LLKV_ERR_NOT_FOUND (the
+ * reference returns None); a chunk of NULLs only has zero statistics; float chunks skip NaN as a bound (strict < / >
+ * from +-infinity) and count distinct bit patterns.  Host only: the append path's bookkeeping, for wrappers that write
+ * ChunkMetadata themselves. */
+int32_t llkv_gpu_chunk_stats(int32_t prim_type, const void* values, uint64_t n_rows, const uint8_t* validity, llkv_chunk_metadata* out);
+
 /* ---- columns: ColumnStore::append / scan source (llkv-column-map/src/store/core.rs:787, scan/mod.rs:191) ---- */
 int32_t llkv_gpu_column_register(llkv_gpu_ctx* ctx, uint64_t logical_field_id, int32_t prim_type, uint8_t precision,
                                  int8_t scale, llkv_gpu_column** out);

@@ -6,6 +6,8 @@
 #include <stdint.h>
 #include <string.h>
 
+#include <unordered_set>
+
 #include "../../include/llkv_gpu.h"
 
 namespace {
@@ -108,4 +110,89 @@ extern "C" int32_t llkv_gpu_chunk_overlaps(int32_t prim_type, uint64_t chunk_min
     if (lower->kind == LLKV_BOUND_INCLUDED ? l > chunk_max_u64 : l >= chunk_max_u64) return 0;
   }
   return 1;
+}
+
+// compute_chunk_stats (pruning.rs:272-470), primitive arrays
+namespace {
+template <typename T>
+int32_t chunk_stats_int(int32_t prim_type, const T* v, uint64_t n, const uint8_t* validity, llkv_chunk_metadata* out) {
+  bool have = false;
+  T mn = 0, mx = 0;
+  uint64_t nulls = 0;
+  std::unordered_set<T> distinct;
+  distinct.reserve((size_t)n);
+  for (uint64_t i = 0; i < n; ++i) {
+    if (validity && !((validity[i >> 3] >> (i & 7)) & 1)) {
+      ++nulls;
+      continue;
+    }
+    const T x = v[i];
+    distinct.insert(x);
+    if (!have || x < mn) mn = x;
+    if (!have || x > mx) mx = x;
+    have = true;
+  }
+  out->null_count = nulls;
+  if (!have) {
+    out->min_val_u64 = out->max_val_u64 = out->distinct_count = 0;
+    return LLKV_OK;
+  }
+  uint64_t bmn = 0, bmx = 0;  // raw bits in the low bytes (the sign extension beyond the type's width is masked by the codec)
+  memcpy(&bmn, &mn, sizeof(T));
+  memcpy(&bmx, &mx, sizeof(T));
+  out->min_val_u64 = llkv_gpu_sortable_u64(prim_type, bmn);
+  out->max_val_u64 = llkv_gpu_sortable_u64(prim_type, bmx);
+  out->distinct_count = distinct.size();
+  return LLKV_OK;
+}
+template <typename F, typename Bits>
+int32_t chunk_stats_float(int32_t prim_type, const F* v, uint64_t n, const uint8_t* validity, llkv_chunk_metadata* out) {
+  bool have = false;
+  F mn = (F)(1.0 / 0.0), mx = (F)(-1.0 / 0.0);
+  uint64_t nulls = 0;
+  std::unordered_set<Bits> distinct;
+  distinct.reserve((size_t)n);
+  for (uint64_t i = 0; i < n; ++i) {
+    if (validity && !((validity[i >> 3] >> (i & 7)) & 1)) {
+      ++nulls;
+      continue;
+    }
+    have = true;
+    Bits b;
+    memcpy(&b, &v[i], sizeof(F));
+    distinct.insert(b);
+    if (v[i] < mn) mn = v[i];  // NaN never passes a strict comparison
+    if (v[i] > mx) mx = v[i];
+  }
+  out->null_count = nulls;
+  if (!have) {
+    out->min_val_u64 = out->max_val_u64 = out->distinct_count = 0;
+    return LLKV_OK;
+  }
+  Bits bmn, bmx;
+  memcpy(&bmn, &mn, sizeof(F));
+  memcpy(&bmx, &mx, sizeof(F));
+  out->min_val_u64 = llkv_gpu_sortable_u64(prim_type, (uint64_t)bmn);
+  out->max_val_u64 = llkv_gpu_sortable_u64(prim_type, (uint64_t)bmx);
+  out->distinct_count = distinct.size();
+  return LLKV_OK;
+}
+}  // namespace
+
+extern "C" int32_t llkv_gpu_chunk_stats(int32_t prim_type, const void* values, uint64_t n_rows, const uint8_t* validity, llkv_chunk_metadata* out) {
+  if (!out || (n_rows && !values)) return llkv_set_error_message(LLKV_ERR_INVALID_ARGUMENT, "NULL argument");
+  if (n_rows == 0) return llkv_set_error_message(LLKV_ERR_NOT_FOUND, "an empty chunk has no statistics");
+  switch (prim_type) {
+    case LLKV_PT_INT8: return chunk_stats_int(prim_type, static_cast<const int8_t*>(values), n_rows, validity, out);
+    case LLKV_PT_INT16: return chunk_stats_int(prim_type, static_cast<const int16_t*>(values), n_rows, validity, out);
+    case LLKV_PT_INT32: case LLKV_PT_DATE32: return chunk_stats_int(prim_type, static_cast<const int32_t*>(values), n_rows, validity, out);
+    case LLKV_PT_INT64: case LLKV_PT_DATE64: return chunk_stats_int(prim_type, static_cast<const int64_t*>(values), n_rows, validity, out);
+    case LLKV_PT_UINT8: return chunk_stats_int(prim_type, static_cast<const uint8_t*>(values), n_rows, validity, out);
+    case LLKV_PT_UINT16: return chunk_stats_int(prim_type, static_cast<const uint16_t*>(values), n_rows, validity, out);
+    case LLKV_PT_UINT32: return chunk_stats_int(prim_type, static_cast<const uint32_t*>(values), n_rows, validity, out);
+    case LLKV_PT_UINT64: return chunk_stats_int(prim_type, static_cast<const uint64_t*>(values), n_rows, validity, out);
+    case LLKV_PT_FLOAT32: return chunk_stats_float<float, uint32_t>(prim_type, static_cast<const float*>(values), n_rows, validity, out);
+    case LLKV_PT_FLOAT64: return chunk_stats_float<double, uint64_t>(prim_type, static_cast<const double*>(values), n_rows, validity, out);
+    default: return llkv_set_error_message(LLKV_ERR_INVALID_ARGUMENT, "no chunk statistics for this column type (compute_chunk_stats returns None)");
+  }
 }

@@ -59,6 +59,7 @@ def load():
         "llkv_gpu_descriptor_parse": (i32, [vp, u64, vp]),
         "llkv_gpu_descriptor_page_parse": (i32, [vp, u64, P(u64), vp, u64, P(u64)]),
         "llkv_gpu_sortable_u64": (u64, [i32, u64]),
+        "llkv_gpu_chunk_stats": (i32, [i32, vp, u64, vp, vp]),
         "llkv_gpu_chunk_overlaps": (i32, [i32, u64, u64, vp, vp]),
         "llkv_gpu_host_alloc": (i32, [u64, P(vp)]),
         "llkv_gpu_host_free": (i32, [vp]),

@@ -46,6 +46,16 @@ def sortable_u64(prim_type: int, value_bits: int) -> int:
     return int(load().llkv_gpu_sortable_u64(prim_type, value_bits & M64))
 
 
+def chunk_stats(prim_type: int, values, validity=None) -> ChunkMetadata:
+    """compute_chunk_stats for a numpy array (+ optional packed validity bitmap): min/max images, null and distinct counts."""
+    import numpy as np
+    v = np.ascontiguousarray(values)
+    out = ChunkMetadata()
+    vb = np.ascontiguousarray(validity, dtype=np.uint8) if validity is not None else None
+    _check(load().llkv_gpu_chunk_stats(prim_type, v.ctypes.data if v.size else None, v.size, vb.ctypes.data if vb is not None else None, C.byref(out)))
+    return out
+
+
 def chunk_overlaps(prim_type: int, chunk_min: int, chunk_max: int, lower: Optional[Bound], upper: Optional[Bound]) -> bool:
     lo = RangeBound(lower[0], 0, lower[1] & M64) if lower else None
     hi = RangeBound(upper[0], 0, upper[1] & M64) if upper else None

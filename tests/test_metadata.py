@@ -132,3 +132,47 @@ def test_malformed_metadata_is_an_error_not_a_crash():
         metadata.parse_descriptor(b"\x00" * 39)
     empty = struct.pack("<QI4x", 0, 0)
     assert metadata.parse_descriptor_page(empty) == (0, [])
+
+
+# ---- compute_chunk_stats through the C ABI: the reference's known answers (pruning_tests.rs:16-64) and the oracle
+def test_chunk_stats_known_answers_through_the_abi():
+    from llkv_b200.table import pack_validity
+    st = metadata.chunk_stats(om.INT32, np.array([1, 5, 10, 0], dtype=np.int32), pack_validity([1, 1, 1, 0]))
+    assert (st.min_val_u64, st.max_val_u64, st.null_count, st.distinct_count) == ((1 ^ 0x80000000), (10 ^ 0x80000000), 1, 3)
+    st = metadata.chunk_stats(om.FLOAT64, np.array([1.0, -5.0, 10.5, 0.0]), pack_validity([1, 1, 1, 0]))
+    assert st.min_val_u64 < st.max_val_u64 and (st.null_count, st.distinct_count) == (1, 3)
+    st = metadata.chunk_stats(om.INT32, np.array([0, 0], dtype=np.int32), pack_validity([0, 0]))
+    assert (st.min_val_u64, st.max_val_u64, st.null_count, st.distinct_count) == (0, 0, 2, 0)
+    with pytest.raises(LlkvError) as e:
+        metadata.chunk_stats(om.INT32, np.array([], dtype=np.int32))
+    assert e.value.code == 4  # NotFound: the reference returns None for an empty array
+
+
+@pytest.mark.parametrize("prim_type,np_type", [(om.INT8, np.int8), (om.INT16, np.int16), (om.INT32, np.int32), (om.INT64, np.int64), (om.DATE32, np.int32),
+                                               (om.UINT8, np.uint8), (om.UINT16, np.uint16), (om.UINT32, np.uint32), (om.UINT64, np.uint64),
+                                               (om.FLOAT32, np.float32), (om.FLOAT64, np.float64)])
+def test_chunk_stats_match_the_oracle(prim_type, np_type):
+    from llkv_b200.table import pack_validity
+    rng = np.random.default_rng(100 + prim_type)
+    for n in (1, 7, 64, 1000):
+        if np.issubdtype(np_type, np.floating):
+            v = (rng.standard_normal(n) * 1e3).astype(np_type)
+            v[rng.random(n) < 0.1] = np.nan
+            v[rng.random(n) < 0.1] = -0.0
+        else:
+            info = np.iinfo(np_type)
+            v = rng.integers(max(info.min, -50), min(info.max, 50), n, dtype=np_type, endpoint=True)
+            if n > 2:
+                v[0], v[1] = info.min, info.max
+        valid = rng.random(n) < 0.8
+        for vb in (None, valid):
+            st = metadata.chunk_stats(prim_type, v, pack_validity(vb) if vb is not None else None)
+            want = om.chunk_stats(prim_type, v, vb)
+            assert (st.min_val_u64, st.max_val_u64, st.null_count, st.distinct_count) == want, (prim_type, n, vb is not None)
+    # the statistics feed the pruning rule: a range that holds no value of the chunk is reported disjoint or not, never wrongly
+    v = np.array([3, 9, 4], dtype=np_type)
+    st = metadata.chunk_stats(prim_type, v)
+    bits = lambda x: int(np.array([x], dtype=np_type).view({1: np.uint8, 2: np.uint16, 4: np.uint32, 8: np.uint64}[np.dtype(np_type).itemsize])[0])  # noqa: E731
+    assert metadata.chunk_overlaps(prim_type, st.min_val_u64, st.max_val_u64, (0, bits(4)), (0, bits(5)))
+    assert not metadata.chunk_overlaps(prim_type, st.min_val_u64, st.max_val_u64, (0, bits(10)), (2, 0))
+    assert not metadata.chunk_overlaps(prim_type, st.min_val_u64, st.max_val_u64, (2, 0), (1, bits(3)))
