@@ -62,6 +62,32 @@ def chunk_overlaps(prim_type: int, chunk_min: int, chunk_max: int, lower: Option
     return bool(load().llkv_gpu_chunk_overlaps(prim_type, chunk_min, chunk_max, C.byref(lo) if lo else None, C.byref(hi) if hi else None))
 
 
+def shard_chunks(chunks: List[ChunkMetadata], world: int, rank: int) -> Tuple[List[ChunkMetadata], int]:
+    """Multi-GPU loading: rank g of G takes chunks [g C / G, (g + 1) C / G) of every column of the table —
+    contiguous, so each shard is a dense row range — and the row id its first row has in the whole table (the
+    `row_id_base` of its first append; llkv_gpu_agg_merge then orders groups by first appearance across shards).
+    Columns of one table must be cut alike: use the chunk list of one column (rows per chunk differ between types) and
+    cut the others at the same row boundaries with `rows_to_chunks`."""
+    n = len(chunks)
+    lo, hi = n * rank // world, n * (rank + 1) // world
+    base = sum(int(c.row_count) for c in chunks[:lo])
+    return chunks[lo:hi], base
+
+
+def rows_to_chunks(chunks: List[ChunkMetadata], row_begin: int, row_end: int) -> Tuple[List[ChunkMetadata], int, int]:
+    """The chunks of a column that hold rows [row_begin, row_end), the row id of the first of them and how many leading
+    rows of it lie before row_begin (a column whose chunk boundaries differ from the one the shards were cut on)."""
+    out, start, first_base, skip = [], 0, 0, 0
+    for c in chunks:
+        end = start + int(c.row_count)
+        if end > row_begin and start < row_end:
+            if not out:
+                first_base, skip = start, max(0, row_begin - start)
+            out.append(c)
+        start = end
+    return out, first_base, skip
+
+
 def walk_descriptor(batch_get: Callable[[List[int]], List[bytes]], descriptor_pk: int, prim_type: int = 0,
                     lower: Optional[Bound] = None, upper: Optional[Bound] = None) -> Tuple[ColumnDescriptor, List[ChunkMetadata], int]:
     """The descriptor walk of unsorted_visit (llkv-column-map/src/store/scan/unsorted.rs:202-241): descriptor -> pages

@@ -176,3 +176,30 @@ def test_chunk_stats_match_the_oracle(prim_type, np_type):
     assert metadata.chunk_overlaps(prim_type, st.min_val_u64, st.max_val_u64, (0, bits(4)), (0, bits(5)))
     assert not metadata.chunk_overlaps(prim_type, st.min_val_u64, st.max_val_u64, (0, bits(10)), (2, 0))
     assert not metadata.chunk_overlaps(prim_type, st.min_val_u64, st.max_val_u64, (2, 0), (1, bits(3)))
+
+
+def _meta(pk, rows):
+    m = metadata.ChunkMetadata()
+    m.chunk_pk, m.row_count = pk, rows
+    return m
+
+
+def test_chunk_shards_cover_every_row_once():
+    # an Int64 column (131 072 rows per chunk) and a Decimal128 column (4 096 rows per chunk) of one 1 000 000-row table
+    n = 1_000_000
+    wide = [_meta(10 + i, min(131072, n - i * 131072)) for i in range((n + 131071) // 131072)]
+    narrow = [_meta(1000 + i, min(4096, n - i * 4096)) for i in range((n + 4095) // 4096)]
+    for world in (1, 2, 3, 8):
+        covered = 0
+        for rank in range(world):
+            mine, base = metadata.shard_chunks(wide, world, rank)
+            assert base == covered
+            rows = sum(int(c.row_count) for c in mine)
+            # the Decimal128 column is cut at the same rows: whole chunks here, since 131 072 is a multiple of 4 096
+            other, first_base, skip = metadata.rows_to_chunks(narrow, base, base + rows)
+            assert first_base == base and skip == 0 and sum(int(c.row_count) for c in other) == rows
+            covered += rows
+        assert covered == n
+    # boundaries that do not line up: the first chunk starts before the shard
+    other, first_base, skip = metadata.rows_to_chunks(narrow, 5000, 9000)
+    assert [c.chunk_pk for c in other] == [1001, 1002] and first_base == 4096 and skip == 904
