@@ -127,3 +127,17 @@ def test_pinned_geometry_that_does_not_fit_keeps_the_group_slots(lineitem):
         head = text.splitlines()[0]
         nc = int(head.split("NC=")[1].split()[0])
         assert " fg=4 " in head and nc % 32 == 0 and f"stages={tune[2]}" in head and f"ctas/SM={tune[3]}" in head, head
+
+
+@pytest.mark.skipif(not _nvrtc_available(), reason="NVRTC is not installed")
+def test_specialising_a_long_program_stays_fast(tmp_path):
+    """A specialised build instantiates only the switch case of the instruction at each program position
+    (LeanTile::live<PC>): twenty aggregates used to take NVRTC 11 s, and take about 2 s now.  Guard with a wide margin."""
+    import time
+    from test_gpu_parity import PREDICATES, all_aggs, mixed_table
+    t = mixed_table(5000, seed=5)
+    t0 = time.time()
+    text = gpu.debug_plan(t, PREDICATES[0], all_aggs(), jit=True, cubin_path=str(tmp_path / "many.cubin"))
+    took = time.time() - t0
+    assert "specialised cubin:" in text
+    assert took < 8.0, f"NVRTC took {took:.1f} s for {text.splitlines()[0]}"
