@@ -1681,8 +1681,9 @@ extern "C" int32_t llkv_gpu_debug_plan(const llkv_debug_column* cols, int32_t n_
     Geometry g;
     uint32_t ctas = 1;
     if ((rc = lean_geometry(tn, cr.plan, 0, rows, cardinality_hint, lp, g, &ctas))) return rc;
+    lp.s.use_tile_list = (jit & 4) ? 1u : 0u;  // jit bit 2: the variant that walks a zone-map tile list
     text = lean_listing(lp, g, ctas);
-    if (jit) {
+    if (jit & 1) {
       std::vector<char> cubin;
       std::string log;
       if (jit_compile_cubin(lp.s, (int)ctas, cubin, log) != 0) return set_error(LLKV_ERR_INTERNAL, "specialisation failed: %s", log.c_str());

@@ -141,3 +141,27 @@ def test_specialising_a_long_program_stays_fast(tmp_path):
     took = time.time() - t0
     assert "specialised cubin:" in text
     assert took < 8.0, f"NVRTC took {took:.1f} s for {text.splitlines()[0]}"
+
+
+@pytest.mark.skipif(not _nvrtc_available(), reason="NVRTC is not installed")
+def test_every_kernel_variant_specialises_without_a_stack_frame(lineitem, tmp_path):
+    """Dense / tile-list scans of Q6 and Q1, the per-row and the partitioned high-cardinality GROUP BY: each shape compiles
+    for sm_100a and keeps its per-row state in registers."""
+    t, snap = lineitem
+    hc = tpch.highcard_table(50_000, 20_000, seed=4)
+    cuobjdump = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    variants = [
+        ("q6_list", dict(table=t, expr=tpch.q6_filter(), specs=tpch.q6_aggregates(), tile_list=True)),
+        ("q1_list", dict(table=t, expr=tpch.q1_filter(), specs=tpch.q1_aggregates(), snapshot=snap, group_by=tpch.Q1_GROUP_BY, cardinality_hint=4,
+                         tile_list=True)),
+        ("per_row", dict(table=hc, expr=None, specs=tpch.highcard_aggregates(), group_by=(tpch.K_FIELD,), cardinality_hint=20_000)),
+        ("partitioned_list", dict(table=hc, expr=tpch.between_filter(tpch.K_FIELD, 10, 5000), specs=tpch.highcard_aggregates(),
+                                  group_by=(tpch.K_FIELD,), cardinality_hint=20_000, partition=True, tile_list=True)),
+    ]
+    for name, kw in variants:
+        cubin = str(tmp_path / f"{name}.cubin")
+        text = gpu.debug_plan(jit=True, cubin_path=cubin, **kw)
+        assert "specialised cubin:" in text, name
+        if os.path.exists(cuobjdump):
+            usage = subprocess.run([cuobjdump, "-res-usage", cubin], capture_output=True, text=True, check=True).stdout
+            assert int(usage.split("STACK:")[1].split()[0]) == 0, (name, usage)
