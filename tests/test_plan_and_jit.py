@@ -137,10 +137,14 @@ def test_specialising_a_long_program_stays_fast(tmp_path):
     from test_gpu_parity import PREDICATES, all_aggs, mixed_table
     t = mixed_table(5000, seed=5)
     t0 = time.time()
+    gpu.debug_plan(t, PREDICATES[0], all_aggs()[:1], jit=True, cubin_path=str(tmp_path / "one.cubin"))
+    small = time.time() - t0  # the yardstick: the same machine, the same load, one aggregate
+    t0 = time.time()
     text = gpu.debug_plan(t, PREDICATES[0], all_aggs(), jit=True, cubin_path=str(tmp_path / "many.cubin"))
     took = time.time() - t0
     assert "specialised cubin:" in text
-    assert took < 8.0, f"NVRTC took {took:.1f} s for {text.splitlines()[0]}"
+    # measured: 0.6 s / 1.8 s (ratio 3); before the change 0.9 s / 11.3 s (ratio 12)
+    assert took < 6.0 * small + 2.0, f"NVRTC took {took:.1f} s ({small:.1f} s for one aggregate) for {text.splitlines()[0]}"
 
 
 @pytest.mark.skipif(not _nvrtc_available(), reason="NVRTC is not installed")
