@@ -196,6 +196,8 @@ extern "C" {
     pub fn llkv_gpu_host_free(p: *mut c_void) -> i32;
     pub fn llkv_gpu_host_register(p: *const c_void, bytes: u64) -> i32;
     pub fn llkv_gpu_host_unregister(p: *const c_void) -> i32;
+    /// Host workers narrowing Decimal128 chunks from page-locked sources before the DMA: -1 default, 0 off.
+    pub fn llkv_gpu_ctx_set_upload_threads(ctx: *mut llkv_gpu_ctx, n_threads: i32) -> i32;
 
     /// Compiles a plan against column statistics only (no device): the lean program's listing, optionally its specialised
     /// cubin.  For tooling and CPU-side tests.
@@ -215,7 +217,10 @@ extern "C" {
     pub fn llkv_gpu_column_reserve(col: *mut llkv_gpu_column, n_rows: u64) -> i32;
     pub fn llkv_gpu_column_append_chunk(col: *mut llkv_gpu_column, chunk_pk: u64, values: *const c_void, n_rows: u64, validity: *const u8, row_ids: *const u64, row_id_base: u64, aux: *const c_void) -> i32;
     pub fn llkv_gpu_column_append_blob(col: *mut llkv_gpu_column, chunk_pk: u64, blob: *const c_void, blob_len: u64, row_ids: *const u64, row_id_base: u64) -> i32;
+    /// Issues and waits for the copies earlier appends left pending: page-locked sources may be reused afterwards.
+    pub fn llkv_gpu_column_flush(col: *mut llkv_gpu_column) -> i32;
     pub fn llkv_gpu_column_seal(col: *mut llkv_gpu_column) -> i32;
+    pub fn llkv_gpu_column_h2d_bytes(col: *const llkv_gpu_column, out_bytes: *mut u64) -> i32;
     pub fn llkv_gpu_column_rows(col: *const llkv_gpu_column, out_rows: *mut u64) -> i32;
     pub fn llkv_gpu_column_read(col: *mut llkv_gpu_column, row_begin: u64, n_rows: u64, out: *mut c_void, out_bytes: u64) -> i32;
     pub fn llkv_gpu_column_clear(col: *mut llkv_gpu_column) -> i32;

@@ -17,6 +17,11 @@
  *   - The caller owns every host buffer; the library owns all device memory
  *     behind opaque handles.  Handles may move between threads, but calls on
  *     one handle must be serialised by the caller (mirrors `&mut self`).
+ *     Columns, programs and aggregates are children of their context and
+ *     share its state (column registry, staging ring, stream, snapshots):
+ *     the library serialises calls that touch one context with a lock inside
+ *     the context, so different handles of one context may be used from
+ *     different threads.  A child handle must not outlive its context.
  *   - There is no CPU fallback.  Without a usable CUDA device
  *     `llkv_gpu_ctx_create` fails with LLKV_ERR_IO and nothing else works.
  */
@@ -278,9 +283,21 @@ int32_t llkv_gpu_ctx_set_partitioning(llkv_gpu_ctx* ctx, int32_t mode);
  * tile drops out (tests).  Results are identical in every mode. */
 int32_t llkv_gpu_ctx_set_pruning(llkv_gpu_ctx* ctx, int32_t mode);
 
-/* Page-locked host memory so chunk uploads DMA straight from the caller's buffer. */
+/* Page-locked host memory so chunk uploads DMA straight from the caller's buffer.
+ *
+ * LIFETIME OF PAGE-LOCKED SOURCES.  When the `values` / `blob` / `aux` / `validity` buffer of an append is page-locked
+ * (llkv_gpu_host_alloc, llkv_gpu_host_register), the library reads it AFTER the append returns: consecutive chunks are
+ * coalesced into larger DMA transfers and Decimal128 chunks are narrowed by host workers in the background.  Such a
+ * buffer must stay valid and unmodified until llkv_gpu_column_flush or llkv_gpu_column_seal of that column has
+ * returned.  llkv_gpu_host_free and llkv_gpu_host_unregister first issue and wait for every pending copy of every
+ * context, so releasing the memory through them is always safe.  Pageable sources are copied before the append returns. */
 int32_t llkv_gpu_host_alloc(uint64_t bytes, void** out);
 int32_t llkv_gpu_host_free(void* p);
+/* Host worker threads that narrow Decimal128 chunks arriving from page-locked memory to 8 or 4 bytes per value before the
+ * DMA, as long as every value of the column is a sign-extended i64 / i32 (a chunk that does not fit sends the column back
+ * to the Arrow layout, nothing is lost): half or a quarter of the bytes cross PCIe and the device skips its own narrowing
+ * pass at seal.  -1 = default (min(16, hardware threads)), 0 = off (16-byte DMA, narrowed on the device at seal). */
+int32_t llkv_gpu_ctx_set_upload_threads(llkv_gpu_ctx* ctx, int32_t n_threads);
 /* Page-locks memory the caller already owns — the pager's mmap-backed blobs (EntryHandle, llkv-storage/src/pager/
  * simd_r_drive_pager.rs) — so llkv_gpu_column_append_blob / _append_chunk DMA straight out of it
  * instead of staging through the context's pinned ring.  Read-only mappings are registered read-only.  Unregister before
@@ -369,8 +386,13 @@ int32_t llkv_gpu_column_append_chunk(llkv_gpu_column* col, uint64_t chunk_pk, co
 /* Appends a serialized chunk blob exactly as the pager stores it ("ARR0" header, serialization.rs:41-53,264-307). */
 int32_t llkv_gpu_column_append_blob(llkv_gpu_column* col, uint64_t chunk_pk, const void* blob, uint64_t blob_len,
                                     const uint64_t* row_ids, uint64_t row_id_base);
+/* Issues and waits for every copy the column's appends left pending; afterwards page-locked sources may be reused.
+ * (The column stays open for more chunks; llkv_gpu_column_seal implies a flush.) */
+int32_t llkv_gpu_column_flush(llkv_gpu_column* col);
 /* Waits for outstanding uploads of this column; after this the column is scannable. */
 int32_t llkv_gpu_column_seal(llkv_gpu_column* col);
+/* Bytes the column's appends have put on the host-to-device link since it was registered (for end-to-end accounting). */
+int32_t llkv_gpu_column_h2d_bytes(const llkv_gpu_column* col, uint64_t* out_bytes);
 int32_t llkv_gpu_column_rows(const llkv_gpu_column* col, uint64_t* out_rows);
 /* Reads rows [row_begin, row_begin + n_rows) of a sealed fixed-width column back into `out` in the Arrow values layout
  * the chunks were appended in (Decimal128 columns kept as i64 on the device are widened again): what a

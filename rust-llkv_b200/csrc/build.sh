@@ -29,6 +29,7 @@ $NVCC $FLAGS ${LLKV_PTXAS_V:+-Xptxas -v} -c partition_kernel.cu -o build/partiti
 g++ -O2 -std=c++17 -fPIC -Wall -Wno-nonnull -c compiler.cpp -o build/compiler.o & pids+=($!)
 g++ -O2 -std=c++17 -fPIC -Wall -I/usr/local/cuda/include -c jit.cpp -o build/jit.o & pids+=($!)
 g++ -O2 -std=c++17 -fPIC -Wall -c descriptor.cpp -o build/descriptor.o & pids+=($!)
+g++ -O3 -std=c++17 -fPIC -Wall -I/usr/local/cuda/include -c upload.cpp -o build/upload.o & pids+=($!)
 for pid in "${pids[@]}"; do wait "$pid"; done  # any failed compile fails the build (set -e)
-$NVCC -gencode arch=compute_100a,code=sm_100a -shared -o libllkv_gpu.so build/scan_kernel.o build/lean_kernel.o build/partition_kernel.o build/llkv_gpu.o build/compiler.o build/jit.o build/descriptor.o -cudart static -ldl -lpthread -lrt
+$NVCC -gencode arch=compute_100a,code=sm_100a -shared -o libllkv_gpu.so build/scan_kernel.o build/lean_kernel.o build/partition_kernel.o build/llkv_gpu.o build/compiler.o build/jit.o build/descriptor.o build/upload.o -cudart static -ldl -lpthread -lrt
 echo built $(pwd)/libllkv_gpu.so

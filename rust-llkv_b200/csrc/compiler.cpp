@@ -1687,7 +1687,7 @@ class Emitter {
     bool ok = true;
     auto map_load = [&](uint8_t lk) -> uint32_t {  // physical layouts the lean kernel reads
       switch (lk) {
-        case LK_I32: return LKF_4;
+        case LK_I32: case LK_D32: return LKF_4;
         case LK_I64: case LK_U64: case LK_F64: case LK_D64: return LKF_8;
         case LK_D128: return LKF_16;
         case LK_U8: return LKF_1;
@@ -1799,7 +1799,7 @@ class Emitter {
               // the column's own value range bounds the comparison domain (and lets 32-bit columns compare in 32 bits)
               const Iv ci = column_interval(c);
               if (ci.known) { if (ci.lo > tmin) tmin = ci.lo; if (ci.hi < tmax) tmax = ci.hi; }
-              if (c.load_kind == LK_I32) { if (tmin < INT32_MIN) tmin = INT32_MIN; if (tmax > INT32_MAX) tmax = INT32_MAX; }
+              if (c.load_kind == LK_I32 || c.load_kind == LK_D32) { if (tmin < INT32_MIN) tmin = INT32_MIN; if (tmax > INT32_MAX) tmax = INT32_MAX; }
               i128 lo = tmin, hi = tmax;
               bool empty = pr.op == OP_PRED_ISNULL;
               if (!empty) {

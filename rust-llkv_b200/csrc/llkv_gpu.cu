@@ -11,13 +11,17 @@
 
 #include <algorithm>
 #include <map>
+#include <memory>
+#include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/llkv_gpu.h"
 #include "compiler.h"
 #include "jit.h"
 #include "plan.h"
+#include "upload.h"
 
 namespace llkv {
 typedef long long i64;
@@ -135,11 +139,12 @@ __global__ void zone_minmax_kernel(const T* __restrict__ v, u64 n, u64* __restri
   }
 }
 // Utf8 (offsets + data) -> packed short-string keys: bytes big-endian from the top byte, length in the low byte
-__global__ void pack_utf8_kernel(const int* __restrict__ off, const unsigned char* __restrict__ data, u64 n, u64* __restrict__ out,
+// (`data` holds the chunk's slice of the data buffer: offsets are relative to `first`)
+__global__ void pack_utf8_kernel(const int* __restrict__ off, const unsigned char* __restrict__ data, int first, u64 n, u64* __restrict__ out,
                                  DevStats* st) {
   unsigned int mx = 0, mn = 0xffffffffu, bad = 0;
   for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (u64)gridDim.x * blockDim.x) {
-    const int b = off[i], e = off[i + 1];
+    const int b = off[i] - first, e = off[i + 1] - first;
     const unsigned int len = (unsigned int)(e - b);
     u64 k = 0;
     if (len > 7) bad = 1;
@@ -162,6 +167,15 @@ __global__ void narrow_str_kernel(const u64* __restrict__ in, unsigned char* __r
 }
 __global__ void narrow_dec_kernel(const ulonglong2* __restrict__ in, u64* __restrict__ out, u64 n) {
   for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (u64)gridDim.x * blockDim.x) out[i] = in[i].x;
+}
+__global__ void narrow_dec32_kernel(const ulonglong2* __restrict__ in, int* __restrict__ out, u64 n) {
+  for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (u64)gridDim.x * blockDim.x) out[i] = (int)in[i].x;
+}
+__global__ void widen_dec32_kernel(const int* __restrict__ in, ulonglong2* __restrict__ out, u64 n) {
+  for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (u64)gridDim.x * blockDim.x) {
+    const i64 v = in[i];
+    out[i] = make_ulonglong2((u64)v, (u64)(v >> 63));
+  }
 }
 __global__ void widen_dec_kernel(const u64* __restrict__ in, ulonglong2* __restrict__ out, u64 n) {
   for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (u64)gridDim.x * blockDim.x) {
@@ -274,6 +288,7 @@ struct llkv_gpu_ctx {
   int prune_mode = 1;      // zone-map tile skipping: 0 never, 1 columns scanned again unchanged + >= 1/8 of the tiles, 2 always
   std::map<std::string, uint32_t> shape_runs;
   bool keep_wide_decimals = false;  // LLKV_GPU_KEEP_WIDE_DECIMALS=1: never narrow Decimal128 columns at seal
+  bool no_d32 = false;              // LLKV_GPU_NO_D32=1: narrow to i64 only (experiments)
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   void* nccl_comm = nullptr;
   int n_ranks = 1, rank = 0;
@@ -283,6 +298,22 @@ struct llkv_gpu_ctx {
   u64* peer_mbox[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   bool p2p_merge = false;
   u64 merge_epoch = 0;
+  // Calls that share this context's state (column registry, staging ring, stream, snapshots, plan cache) are serialised
+  // here, so handles of one context may be used from several threads (the Rust wrapper's `Sync`).
+  std::recursive_mutex mu;
+  // host workers that narrow Decimal128 chunks from page-locked sources before the DMA (upload.h); created on first use
+  int upload_threads = -1;  // -1 = default (min(16, hardware threads)), 0 = never narrow on the host
+  std::unique_ptr<UploadPool> pool;
+};
+#define CTX_LOCK(c) std::lock_guard<std::recursive_mutex> _ctx_lock((c)->mu)
+
+// live contexts: llkv_gpu_host_free / _host_unregister must not pull memory from under a copy that is still pending
+static std::mutex g_registry_mu;
+static std::vector<llkv_gpu_ctx*> g_contexts;
+
+struct NarrowChunk {  // a chunk appended through the host-narrowing path since the last seal (re-uploaded wide on failure)
+  const void* src;
+  uint64_t first_row, n_rows;
 };
 
 struct llkv_gpu_column {
@@ -308,9 +339,16 @@ struct llkv_gpu_column {
   // allocated (`landing`, after a clear(): the caller re-uploads the column every batch) so no allocation happens per batch.
   void* landing = nullptr;     // parked Arrow-layout buffer (16 B per row), capacity landing_cap rows
   uint64_t landing_cap = 0;
-  void* narrow = nullptr;      // parked i64 buffer, capacity narrow_cap rows
+  void* narrow = nullptr;      // parked narrow buffer (narrow_width bytes per row), capacity narrow_cap rows
   uint64_t narrow_cap = 0;
+  uint32_t narrow_width = 8;
   bool reupload_hint = false;  // set by clear(): keep both buffers across batches
+  // host-side narrowing of page-locked Decimal128 chunks (upload.h): the width tried next (-1 = look at the first chunk,
+  // -2 = a chunk did not fit i64: never again for this column), the jobs in flight, the chunks since the last seal
+  int host_kind = -1;
+  UploadTicket ticket;
+  std::vector<NarrowChunk> narrow_chunks;
+  uint64_t h2d_bytes = 0;      // bytes this column's appends put on the link since it was registered
   // pending coalesced upload from page-locked host memory (upload() / flush_upload())
   void* pend_dst = nullptr;
   const void* pend_src = nullptr;
@@ -461,6 +499,8 @@ extern "C" int32_t llkv_gpu_ctx_create(int32_t device_ordinal, int32_t n_streams
   {
     const char* e = getenv("LLKV_GPU_KEEP_WIDE_DECIMALS");
     c->keep_wide_decimals = e && e[0] == '1';
+    const char* e32 = getenv("LLKV_GPU_NO_D32");
+    c->no_d32 = e32 && e32[0] == '1';
   }
   if (n_streams < 1) n_streams = 2;
   if (n_streams > 16) n_streams = 16;
@@ -476,6 +516,10 @@ extern "C" int32_t llkv_gpu_ctx_create(int32_t device_ordinal, int32_t n_streams
   CUDA_TRY(cudaHostAlloc((void**)&c->pinned, c->slot_bytes * (uint64_t)n_streams, cudaHostAllocDefault));
   CUDA_TRY(cudaEventCreate(&c->ev0));
   CUDA_TRY(cudaEventCreate(&c->ev1));
+  {
+    std::lock_guard<std::mutex> lk(g_registry_mu);
+    g_contexts.push_back(c);
+  }
   *out = c;
   return LLKV_OK;
 }
@@ -483,11 +527,16 @@ extern "C" int32_t llkv_gpu_ctx_create(int32_t device_ordinal, int32_t n_streams
 static void comm_teardown_p2p(llkv_gpu_ctx* ctx);
 extern "C" void llkv_gpu_ctx_destroy(llkv_gpu_ctx* c) {
   if (!c) return;
+  {
+    std::lock_guard<std::mutex> lk(g_registry_mu);
+    g_contexts.erase(std::remove(g_contexts.begin(), g_contexts.end(), c), g_contexts.end());
+  }
   cudaSetDevice(c->device);
   cudaDeviceSynchronize();
   std::vector<llkv_gpu_column*> cols;
   for (auto& kv : c->columns) cols.push_back(kv.second);
   for (llkv_gpu_column* col : cols) llkv_gpu_column_destroy(col);
+  c->pool.reset();
   if (c->nccl_comm && g_nccl.comm_destroy) {
     comm_teardown_p2p(c);
     g_nccl.comm_destroy(c->nccl_comm);
@@ -503,6 +552,7 @@ extern "C" void llkv_gpu_ctx_destroy(llkv_gpu_ctx* c) {
 
 extern "C" int32_t llkv_gpu_ctx_synchronize(llkv_gpu_ctx* c) {
   if (!c) return set_error(LLKV_ERR_INVALID_ARGUMENT, "ctx is NULL");
+  CTX_LOCK(c);
   CUDA_TRY(cudaSetDevice(c->device));
   for (cudaStream_t s : c->copy_streams) CUDA_TRY(cudaStreamSynchronize(s));
   CUDA_TRY(cudaStreamSynchronize(c->stream));
@@ -576,14 +626,59 @@ extern "C" int32_t llkv_gpu_host_register(const void* p, uint64_t bytes) {
   }
   return LLKV_OK;
 }
+// Page-locked memory is about to go away: every copy an append left pending (coalesced DMA, host-narrowing jobs) may
+// still read it, so all of them are issued and waited for first.
+static int32_t column_flush(llkv_gpu_column* col);
+static int32_t flush_all_pending() {
+  std::vector<llkv_gpu_ctx*> ctxs;
+  {
+    std::lock_guard<std::mutex> lk(g_registry_mu);
+    ctxs = g_contexts;
+  }
+  int cur = 0;
+  cudaGetDevice(&cur);
+  int32_t first = LLKV_OK;
+  for (llkv_gpu_ctx* c : ctxs) {
+    CTX_LOCK(c);
+    if (cudaSetDevice(c->device) != cudaSuccess) continue;
+    for (auto& kv : c->columns) {
+      llkv_gpu_column* col = kv.second;
+      if (!col->pend_bytes && col->narrow_chunks.empty() && col->ticket.outstanding.load() == 0) continue;
+      const int32_t rc = column_flush(col);
+      if (rc && !first) first = rc;
+    }
+  }
+  cudaSetDevice(cur);
+  return first;
+}
 extern "C" int32_t llkv_gpu_host_unregister(const void* p) {
   if (!p) return LLKV_OK;
+  int32_t rc = flush_all_pending();
+  if (rc) return rc;
   CUDA_TRY(cudaHostUnregister(const_cast<void*>(p)));
   return LLKV_OK;
 }
 
 extern "C" int32_t llkv_gpu_host_free(void* p) {
-  if (p) CUDA_TRY(cudaFreeHost(p));
+  if (!p) return LLKV_OK;
+  int32_t rc = flush_all_pending();
+  if (rc) return rc;
+  CUDA_TRY(cudaFreeHost(p));
+  return LLKV_OK;
+}
+
+extern "C" int32_t llkv_gpu_ctx_set_upload_threads(llkv_gpu_ctx* c, int32_t n_threads) {
+  if (!c) return set_error(LLKV_ERR_INVALID_ARGUMENT, "ctx is NULL");
+  if (n_threads < -1 || n_threads > 64) return set_error(LLKV_ERR_INVALID_ARGUMENT, "upload threads must be -1 (default), 0 (off) or 1..64");
+  CTX_LOCK(c);
+  if (c->pool && c->pool->threads() != n_threads) {
+    for (auto& kv : c->columns) {
+      const int32_t rc = column_flush(kv.second);
+      if (rc) return rc;
+    }
+    c->pool.reset();
+  }
+  c->upload_threads = n_threads;
   return LLKV_OK;
 }
 
@@ -607,10 +702,12 @@ static uint8_t device_load_kind(int32_t type) {
     default: return LK_D128;
   }
 }
+static bool is_narrow_decimal(const llkv_gpu_column* col) { return col->load_kind == LK_D64 || col->load_kind == LK_D32; }
 
 extern "C" int32_t llkv_gpu_column_register(llkv_gpu_ctx* c, uint64_t lfid, int32_t prim_type, uint8_t precision, int8_t scale,
                                              llkv_gpu_column** out) {
   if (!c || !out) return set_error(LLKV_ERR_INVALID_ARGUMENT, "NULL argument");
+  CTX_LOCK(c);
   *out = nullptr;
   if (device_elem_bytes(prim_type) == 0) return set_error(LLKV_ERR_INVALID_ARGUMENT, "column type %d does not cross this boundary", prim_type);
   if (prim_type == LLKV_PT_DECIMAL128 && (precision < 1 || precision > 38)) return set_error(LLKV_ERR_INVALID_ARGUMENT, "Decimal128 precision %d out of range", precision);
@@ -641,11 +738,31 @@ extern "C" int32_t llkv_gpu_column_register(llkv_gpu_ctx* c, uint64_t lfid, int3
   return LLKV_OK;
 }
 
-static int32_t flush_upload(llkv_gpu_column* col);
+// Issues the column's pending coalesced host->device copy (see upload()).  Must run before anything on the column's
+// stream reads or moves the destination: follow-up kernels, seal, grow, clear, destroy.
+static int32_t flush_upload(llkv_gpu_column* col) {
+  if (!col->pend_bytes) return LLKV_OK;
+  cudaStream_t cs = col->ctx->copy_streams[(size_t)col->stream_index];
+  const uint64_t n = col->pend_bytes;
+  col->pend_bytes = 0;
+  CUDA_TRY(cudaMemcpyAsync(col->pend_dst, col->pend_src, n, cudaMemcpyHostToDevice, cs));
+  return LLKV_OK;
+}
+// ... and waits for the host workers' jobs of this column (their destination is the values buffer too)
+static int32_t drain_jobs(llkv_gpu_column* col) {
+  llkv_gpu_ctx* c = col->ctx;
+  if (!c->pool || (col->ticket.outstanding.load() == 0 && col->narrow_chunks.empty())) return LLKV_OK;
+  const cudaError_t e = c->pool->wait(&col->ticket);
+  col->ticket.cuda_error.store(0);
+  if (e != cudaSuccess) return set_error(LLKV_ERR_IO, "CUDA error %s in a chunk upload worker", cudaGetErrorString(e));
+  return LLKV_OK;
+}
+
 static int32_t column_grow(llkv_gpu_column* col, uint64_t need_rows) {
   if (need_rows + kPadRows <= col->cap_rows) return LLKV_OK;
-  {  // the pending coalesced copy targets the buffer that is about to move
+  {  // pending copies target the buffer that is about to move
     int32_t frc = flush_upload(col);
+    if (!frc) frc = drain_jobs(col);
     if (frc) return frc;
   }
   llkv_gpu_ctx* c = col->ctx;
@@ -676,34 +793,30 @@ static int32_t column_grow(llkv_gpu_column* col, uint64_t need_rows) {
 
 extern "C" int32_t llkv_gpu_column_reserve(llkv_gpu_column* col, uint64_t n_rows) {
   if (!col) return set_error(LLKV_ERR_INVALID_ARGUMENT, "column is NULL");
+  CTX_LOCK(col->ctx);
   CUDA_TRY(cudaSetDevice(col->ctx->device));
   return column_grow(col, n_rows);
 }
 
-// host -> device through the pinned staging ring (or directly when the source is already page-locked)
-// Issues the column's pending coalesced host->device copy (see upload()).  Must run before anything on the column's
-// stream reads or moves the destination: follow-up kernels, seal, grow, clear, destroy.
-static int32_t flush_upload(llkv_gpu_column* col) {
-  if (!col->pend_bytes) return LLKV_OK;
-  cudaStream_t cs = col->ctx->copy_streams[(size_t)col->stream_index];
-  const uint64_t n = col->pend_bytes;
-  col->pend_bytes = 0;
-  CUDA_TRY(cudaMemcpyAsync(col->pend_dst, col->pend_src, n, cudaMemcpyHostToDevice, cs));
-  return LLKV_OK;
+static bool is_page_locked(const void* p) {
+  cudaPointerAttributes attr;
+  if (cudaPointerGetAttributes(&attr, p) == cudaSuccess) return attr.type == cudaMemoryTypeHost;
+  cudaGetLastError();
+  return false;
 }
 
-static int32_t upload(llkv_gpu_column* col, void* dst, const void* src, uint64_t bytes) {
+// host -> device through the pinned staging ring (or directly when the source is already page-locked)
+static int32_t upload(llkv_gpu_column* col, void* dst, const void* src, uint64_t bytes, bool pinned_src) {
   llkv_gpu_ctx* c = col->ctx;
   cudaStream_t cs = c->copy_streams[(size_t)col->stream_index];
   if (bytes == 0) return LLKV_OK;
-  cudaPointerAttributes attr;
-  bool pinned_src = false;
-  if (cudaPointerGetAttributes(&attr, src) == cudaSuccess) pinned_src = attr.type == cudaMemoryTypeHost;
-  else cudaGetLastError();
+  col->h2d_bytes += bytes;
   if (pinned_src) {
     // Page-locked source: DMA straight from the caller's buffer.  Chunks that continue the previous one on both sides
     // (a column appended chunk by chunk from one contiguous buffer) are coalesced into copies of up to 32 MiB: a 1 MiB
-    // copy reaches 46 GB/s on this box's PCIe link, a large one 55 GB/s (tools/pcie.py).
+    // copy reaches 46 GB/s on this box's PCIe link, a large one 55 GB/s (tools/pcie.py).  The copy is issued by the next
+    // append that does not continue it, by llkv_gpu_column_flush or by seal: the source must stay valid and unmodified
+    // until one of the latter two returns (include/llkv_gpu.h).
     constexpr uint64_t kMaxCoalesced = 32ull << 20;
     if (col->pend_bytes && (const char*)col->pend_src + col->pend_bytes == (const char*)src &&
         (char*)col->pend_dst + col->pend_bytes == (char*)dst && col->pend_bytes + bytes <= kMaxCoalesced) {
@@ -754,6 +867,16 @@ static int32_t launch_stats(llkv_gpu_column* col, uint64_t first_row, uint64_t n
   cudaStream_t s = col->ctx->copy_streams[(size_t)col->stream_index];
   unsigned int blocks = (unsigned int)std::min<uint64_t>((n + 1023) / 1024, 1184);
   const char* base = (const char*)col->values + first_row * col->elem_bytes;
+  if (col->load_kind == LK_D64) {  // narrow images of a Decimal128 column: the values are the sign-extended low halves
+    stats_kernel<i64, true><<<blocks, 256, 0, s>>>((const i64*)base, n, col->dstats);
+    CUDA_TRY(cudaGetLastError());
+    return LLKV_OK;
+  }
+  if (col->load_kind == LK_D32) {
+    stats_kernel<int, true><<<blocks, 256, 0, s>>>((const int*)base, n, col->dstats);
+    CUDA_TRY(cudaGetLastError());
+    return LLKV_OK;
+  }
   switch (col->type) {
     case LLKV_PT_INT8: stats_kernel<signed char, true><<<blocks, 256, 0, s>>>((const signed char*)base, n, col->dstats); break;
     case LLKV_PT_INT16: stats_kernel<short, true><<<blocks, 256, 0, s>>>((const short*)base, n, col->dstats); break;
@@ -781,11 +904,10 @@ static int32_t ensure_zones(llkv_gpu_column* col, bool* ok) {
     *ok = true;
     return LLKV_OK;
   }
-  const bool dec64 = col->type == LLKV_PT_DECIMAL128 && col->load_kind == LK_D64;
   switch (col->type) {
     case LLKV_PT_INT8: case LLKV_PT_INT16: case LLKV_PT_INT32: case LLKV_PT_INT64: case LLKV_PT_DATE32: case LLKV_PT_DATE64:
     case LLKV_PT_UINT8: case LLKV_PT_UINT16: case LLKV_PT_UINT32: case LLKV_PT_UINT64: case LLKV_PT_BOOLEAN: break;
-    case LLKV_PT_DECIMAL128: if (dec64) break; return LLKV_OK;
+    case LLKV_PT_DECIMAL128: if (is_narrow_decimal(col)) break; return LLKV_OK;
     default: return LLKV_OK;
   }
   if (col->d_zones_cap < n_zones) {
@@ -798,17 +920,16 @@ static int32_t ensure_zones(llkv_gpu_column* col, bool* ok) {
   cudaStream_t s = c->stream;
   const unsigned blocks = (unsigned)std::min<u64>((n_zones + 7) / 8, 1184);
   const void* v = col->values;
-  switch (col->type) {
-    case LLKV_PT_INT8: zone_minmax_kernel<signed char, true, 1><<<blocks, 256, 0, s>>>((const signed char*)v, n, col->d_zones); break;
-    case LLKV_PT_INT16: zone_minmax_kernel<short, true, 1><<<blocks, 256, 0, s>>>((const short*)v, n, col->d_zones); break;
-    case LLKV_PT_INT32: case LLKV_PT_DATE32: zone_minmax_kernel<int, true, 1><<<blocks, 256, 0, s>>>((const int*)v, n, col->d_zones); break;
-    case LLKV_PT_INT64: case LLKV_PT_DATE64: case LLKV_PT_DECIMAL128:
-      zone_minmax_kernel<i64, true, 1><<<blocks, 256, 0, s>>>((const i64*)v, n, col->d_zones);
-      break;
-    case LLKV_PT_UINT8: case LLKV_PT_BOOLEAN: zone_minmax_kernel<unsigned char, false, 1><<<blocks, 256, 0, s>>>((const unsigned char*)v, n, col->d_zones); break;
-    case LLKV_PT_UINT16: zone_minmax_kernel<unsigned short, false, 1><<<blocks, 256, 0, s>>>((const unsigned short*)v, n, col->d_zones); break;
-    case LLKV_PT_UINT32: zone_minmax_kernel<unsigned int, false, 1><<<blocks, 256, 0, s>>>((const unsigned int*)v, n, col->d_zones); break;
-    default: zone_minmax_kernel<u64, false, 1><<<blocks, 256, 0, s>>>((const u64*)v, n, col->d_zones); break;
+  switch (col->load_kind) {
+    case LK_I8: zone_minmax_kernel<signed char, true, 1><<<blocks, 256, 0, s>>>((const signed char*)v, n, col->d_zones); break;
+    case LK_I16: zone_minmax_kernel<short, true, 1><<<blocks, 256, 0, s>>>((const short*)v, n, col->d_zones); break;
+    case LK_I32: case LK_D32: zone_minmax_kernel<int, true, 1><<<blocks, 256, 0, s>>>((const int*)v, n, col->d_zones); break;
+    case LK_I64: case LK_D64: zone_minmax_kernel<i64, true, 1><<<blocks, 256, 0, s>>>((const i64*)v, n, col->d_zones); break;
+    case LK_U8: zone_minmax_kernel<unsigned char, false, 1><<<blocks, 256, 0, s>>>((const unsigned char*)v, n, col->d_zones); break;
+    case LK_U16: zone_minmax_kernel<unsigned short, false, 1><<<blocks, 256, 0, s>>>((const unsigned short*)v, n, col->d_zones); break;
+    case LK_U32: zone_minmax_kernel<unsigned int, false, 1><<<blocks, 256, 0, s>>>((const unsigned int*)v, n, col->d_zones); break;
+    case LK_U64: zone_minmax_kernel<u64, false, 1><<<blocks, 256, 0, s>>>((const u64*)v, n, col->d_zones); break;
+    default: return LLKV_OK;
   }
   CUDA_TRY(cudaGetLastError());
   col->h_zones.resize(2 * n_zones);
@@ -819,14 +940,78 @@ static int32_t ensure_zones(llkv_gpu_column* col, bool* ok) {
   return LLKV_OK;
 }
 
-extern "C" int32_t llkv_gpu_column_append_chunk(llkv_gpu_column* col, uint64_t chunk_pk, const void* values, uint64_t n_rows,
-                                                 const uint8_t* validity, const uint64_t* row_ids, uint64_t row_id_base,
-                                                 const void* aux) {
-  (void)chunk_pk;
-  if (!col) return set_error(LLKV_ERR_INVALID_ARGUMENT, "column is NULL");
-  if (n_rows && !values) return set_error(LLKV_ERR_INVALID_ARGUMENT, "values is NULL");
+// A Decimal128 column resident as i64 / i32 goes back to the Arrow layout (more chunks arrive that are not narrowed on the
+// host, or a narrowed chunk did not fit).  Rows [0, rows) are widened on the device; the narrow buffer is parked.
+static int32_t widen_decimal(llkv_gpu_column* col, uint64_t rows) {
+  CUDA_TRY(cudaDeviceSynchronize());
+  ulonglong2* wide = (ulonglong2*)col->landing;
+  if (!wide || col->landing_cap < col->cap_rows) {
+    if (wide) CUDA_TRY(cudaFree(wide));
+    col->landing = nullptr;
+    CUDA_TRY(cudaMalloc((void**)&wide, col->cap_rows * 16));
+    CUDA_TRY(cudaMemset(wide, 0, col->cap_rows * 16));
+    col->landing_cap = col->cap_rows;
+  }
+  if (rows) {
+    if (col->load_kind == LK_D32) widen_dec32_kernel<<<1184, 256>>>((const int*)col->values, wide, rows);
+    else widen_dec_kernel<<<1184, 256>>>((const u64*)col->values, wide, rows);
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaDeviceSynchronize());
+  }
+  if (col->narrow && col->narrow != col->values) CUDA_TRY(cudaFree(col->narrow));
+  col->narrow = col->values;  // parked for the next seal
+  col->narrow_cap = col->cap_rows;
+  col->narrow_width = col->elem_bytes;
+  col->landing = nullptr;
+  col->landing_cap = 0;
+  col->values = wide;
+  col->elem_bytes = 16;
+  col->load_kind = LK_D128;
+  return LLKV_OK;
+}
+
+// An empty Decimal128 column starts receiving host-narrowed chunks: `values` becomes a buffer of `width` bytes per row
+// (the parked one when it fits), the Arrow-layout buffer is parked.
+static int32_t begin_narrow_landing(llkv_gpu_column* col, uint32_t width, uint64_t need_rows) {
+  uint64_t cap = std::max<uint64_t>(col->cap_rows, (need_rows + 2 * kPadRows - 1) / kPadRows * kPadRows);
+  void* nv = col->narrow;
+  if (!nv || col->narrow_width != width || col->narrow_cap < cap) {
+    if (nv) CUDA_TRY(cudaFree(nv));
+    col->narrow = nullptr;
+    CUDA_TRY(cudaMalloc(&nv, cap * width));
+    CUDA_TRY(cudaMemset(nv, 0, cap * width));
+  } else {
+    cap = col->narrow_cap;
+  }
+  if (col->landing && col->landing != col->values) CUDA_TRY(cudaFree(col->landing));
+  col->landing = col->values;
+  col->landing_cap = col->values ? col->cap_rows : 0;
+  col->narrow = nullptr;
+  col->narrow_cap = 0;
+  col->values = nv;
+  col->cap_rows = cap;
+  col->elem_bytes = width;
+  col->load_kind = width == 4 ? LK_D32 : LK_D64;
+  if (col->validity) {  // sized by the old capacity
+    CUDA_TRY(cudaFree(col->validity));
+    col->validity = nullptr;
+  }
+  return LLKV_OK;
+}
+
+static UploadPool* upload_pool(llkv_gpu_ctx* c) {
+  if (c->upload_threads == 0) return nullptr;
+  if (!c->pool) {
+    int n = c->upload_threads;
+    if (n < 0) n = (int)std::min<unsigned>(16u, std::max<unsigned>(1u, std::thread::hardware_concurrency()));
+    c->pool.reset(new UploadPool(c->device, n));
+  }
+  return c->pool.get();
+}
+
+static int32_t append_chunk_impl(llkv_gpu_column* col, const void* values, uint64_t n_rows, const uint8_t* validity, const uint64_t* row_ids,
+                                 uint64_t row_id_base, const void* aux) {
   llkv_gpu_ctx* c = col->ctx;
-  CUDA_TRY(cudaSetDevice(c->device));
   // row ids must continue the column densely (SURVEY.md §7 hard part (a))
   const uint64_t first_id = row_ids && n_rows ? row_ids[0] : row_id_base;
   if (!col->has_origin) {
@@ -841,6 +1026,7 @@ extern "C" int32_t llkv_gpu_column_append_chunk(llkv_gpu_column* col, uint64_t c
       if (row_ids[i] != first_id + i) return set_error(LLKV_ERR_INVALID_ARGUMENT, "chunk row ids are not a dense run at offset %llu", (unsigned long long)i);
   if (n_rows == 0) return LLKV_OK;
   col->sealed = false;
+  const bool pinned_src = is_page_locked(values);
   if (col->load_kind == LK_STR8) {  // sealed as one byte per string: back to packed keys before more chunks arrive
     u64* wide = nullptr;
     CUDA_TRY(cudaDeviceSynchronize());
@@ -854,64 +1040,77 @@ extern "C" int32_t llkv_gpu_column_append_chunk(llkv_gpu_column* col, uint64_t c
     col->elem_bytes = 8;
     col->load_kind = LK_U64;
   }
-  if (col->load_kind == LK_D64) {  // sealed as i64: back to the Arrow layout before more chunks arrive
-    CUDA_TRY(cudaDeviceSynchronize());
-    ulonglong2* wide = (ulonglong2*)col->landing;
-    if (!wide || col->landing_cap < col->cap_rows) {
-      if (wide) CUDA_TRY(cudaFree(wide));
-      CUDA_TRY(cudaMalloc((void**)&wide, col->cap_rows * 16));
-      CUDA_TRY(cudaMemset(wide, 0, col->cap_rows * 16));
-      col->landing_cap = col->cap_rows;
+  // Decimal128: chunks from page-locked memory are narrowed by the host workers while the column's values keep fitting
+  // (upload.h); everything else lands in the Arrow layout and is narrowed on the device at seal.
+  int host_kind = -2;
+  int32_t rc;
+  if (col->type == LLKV_PT_DECIMAL128) {
+    UploadPool* pool = (pinned_src && !c->keep_wide_decimals && col->host_kind != -2) ? upload_pool(c) : nullptr;
+    if (pool && is_narrow_decimal(col)) {
+      host_kind = col->load_kind == LK_D32 ? UP_NARROW_D128_I32 : UP_NARROW_D128_I64;
+      if (col->host_kind == UP_NARROW_D128_I64 && host_kind == UP_NARROW_D128_I32) host_kind = -2;  // i32 failed before
+    } else if (pool && col->n_rows == 0) {
+      host_kind = col->host_kind;
+      if (host_kind == -1) {  // look at the first chunk
+        const int64_t* v = static_cast<const int64_t*>(values);
+        bool fits32 = true, fits64 = true;
+        for (uint64_t i = 0; i < n_rows && fits64; ++i) {
+          const int64_t lo = v[2 * i], hi = v[2 * i + 1];
+          fits64 = hi == (lo >> 63);
+          fits32 = fits32 && lo == (int64_t)(int32_t)lo;
+        }
+        host_kind = !fits64 ? -2 : (fits32 && !c->no_d32 ? UP_NARROW_D128_I32 : UP_NARROW_D128_I64);
+        col->host_kind = host_kind;
+      }
+      if (host_kind >= 0 && (rc = begin_narrow_landing(col, host_kind == UP_NARROW_D128_I32 ? 4u : 8u, n_rows))) return rc;
     }
-    if (col->n_rows) {
-      widen_dec_kernel<<<1184, 256>>>((const u64*)col->values, wide, col->n_rows);
-      CUDA_TRY(cudaGetLastError());
-      CUDA_TRY(cudaDeviceSynchronize());
+    if (host_kind < 0 && is_narrow_decimal(col)) {
+      if ((rc = flush_upload(col)) || (rc = drain_jobs(col))) return rc;
+      if ((rc = widen_decimal(col, col->n_rows))) return rc;
     }
-    // park the i64 buffer for the next seal
-    col->narrow = col->values;
-    col->narrow_cap = col->cap_rows;
-    col->landing = nullptr;
-    col->landing_cap = 0;
-    col->values = wide;
-    col->elem_bytes = 16;
-    col->load_kind = LK_D128;
   }
-  int32_t rc = column_grow(col, col->n_rows + n_rows);
-  if (rc) return rc;
+  if ((rc = column_grow(col, col->n_rows + n_rows))) return rc;
   cudaStream_t s = c->copy_streams[(size_t)col->stream_index];
   if (col->type == LLKV_PT_UTF8) {
+    // the chunk's slice of the data buffer is uploaded and the offsets are rebased on the device (a column appended in many
+    // chunks from one data buffer uploads every byte once)
     const int32_t* off = (const int32_t*)values;
-    const int64_t data_bytes = (int64_t)off[n_rows] - (int64_t)off[0];
-    if (data_bytes < 0) return set_error(LLKV_ERR_INVALID_ARGUMENT, "Utf8 offsets are not monotonic");
+    const int64_t first = off[0], data_bytes = (int64_t)off[n_rows] - first;
+    if (first < 0 || data_bytes < 0) return set_error(LLKV_ERR_INVALID_ARGUMENT, "Utf8 offsets are negative or not monotonic");
+    for (uint64_t i = 0; i < n_rows; ++i)
+      if (off[i + 1] < off[i]) return set_error(LLKV_ERR_INVALID_ARGUMENT, "Utf8 offsets are not monotonic at row %llu", (unsigned long long)i);
     if (data_bytes && !aux) return set_error(LLKV_ERR_INVALID_ARGUMENT, "Utf8 data buffer is NULL");
     int* d_off = nullptr;
     unsigned char* d_data = nullptr;
     CUDA_TRY(cudaMalloc((void**)&d_off, (n_rows + 1) * 4));
-    CUDA_TRY(cudaMalloc((void**)&d_data, (size_t)(off[n_rows] > 0 ? off[n_rows] : 1)));
-    col->deferred_free.push_back(d_off);
-    col->deferred_free.push_back(d_data);
-    if ((rc = upload(col, d_off, off, (n_rows + 1) * 4))) return rc;
-    if (off[n_rows] > 0 && (rc = upload(col, d_data, aux, (uint64_t)off[n_rows]))) return rc;
+    CUDA_TRY(cudaMalloc((void**)&d_data, (size_t)(data_bytes > 0 ? data_bytes : 1)));
+    if ((rc = upload(col, d_off, off, (n_rows + 1) * 4, pinned_src))) return rc;
+    if (data_bytes > 0 && (rc = upload(col, d_data, (const char*)aux + first, (uint64_t)data_bytes, is_page_locked(aux)))) return rc;
     const unsigned int blocks = (unsigned int)std::min<uint64_t>((n_rows + 255) / 256, 1184);
     if ((rc = flush_upload(col))) return rc;
-    pack_utf8_kernel<<<blocks, 256, 0, s>>>(d_off, d_data, n_rows, (u64*)col->values + col->n_rows, col->dstats);
+    pack_utf8_kernel<<<blocks, 256, 0, s>>>(d_off, d_data, (int)first, n_rows, (u64*)col->values + col->n_rows, col->dstats);
     CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaFreeAsync(d_off, s));  // stream-ordered: released once the pack kernel has read them
+    CUDA_TRY(cudaFreeAsync(d_data, s));
     col->hstats.data_bytes += (u64)data_bytes;
+  } else if (host_kind >= 0) {
+    col->narrow_chunks.push_back(NarrowChunk{values, col->n_rows, n_rows});
+    col->h2d_bytes += n_rows * col->elem_bytes;
+    c->pool->submit(&col->ticket, values, (char*)col->values + col->n_rows * col->elem_bytes, n_rows, host_kind);
   } else {
-    if ((rc = upload(col, (char*)col->values + col->n_rows * col->elem_bytes, values, n_rows * col->elem_bytes))) return rc;
+    if ((rc = upload(col, (char*)col->values + col->n_rows * col->elem_bytes, values, n_rows * col->elem_bytes, pinned_src))) return rc;
   }
   if (validity) {
     if ((rc = ensure_validity(col))) return rc;
     unsigned char* d_bits = nullptr;
     const uint64_t nb = (n_rows + 7) / 8;
     CUDA_TRY(cudaMalloc((void**)&d_bits, nb));
-    col->deferred_free.push_back(d_bits);
-    if ((rc = upload(col, d_bits, validity, nb))) return rc;
+    if ((rc = upload(col, d_bits, validity, nb, is_page_locked(validity)))) return rc;
     const unsigned int blocks = (unsigned int)std::min<uint64_t>((n_rows / 32 + 256) / 256, 1184);
     if ((rc = flush_upload(col))) return rc;
     or_bits_kernel<<<blocks, 256, 0, s>>>(col->validity, col->n_rows, d_bits, n_rows);
     CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaFreeAsync(d_bits, s));
   } else if (col->validity) {
     fill_bits_kernel<<<256, 256, 0, s>>>(col->validity, col->n_rows, col->n_rows + n_rows);
     CUDA_TRY(cudaGetLastError());
@@ -920,6 +1119,24 @@ extern "C" int32_t llkv_gpu_column_append_chunk(llkv_gpu_column* col, uint64_t c
   ++col->version;
   col->scans_unchanged = 0;
   return LLKV_OK;
+}
+
+extern "C" int32_t llkv_gpu_column_append_chunk(llkv_gpu_column* col, uint64_t chunk_pk, const void* values, uint64_t n_rows,
+                                                 const uint8_t* validity, const uint64_t* row_ids, uint64_t row_id_base,
+                                                 const void* aux) {
+  (void)chunk_pk;
+  if (!col) return set_error(LLKV_ERR_INVALID_ARGUMENT, "column is NULL");
+  if (n_rows && !values) return set_error(LLKV_ERR_INVALID_ARGUMENT, "values is NULL");
+  llkv_gpu_ctx* c = col->ctx;
+  CTX_LOCK(c);
+  CUDA_TRY(cudaSetDevice(c->device));
+  const int32_t rc = append_chunk_impl(col, values, n_rows, validity, row_ids, row_id_base, aux);
+  if (rc) {  // what earlier chunks left pending still belongs to the column; nothing of the failed chunk stays referenced
+    const std::string msg = g_last_error;
+    flush_upload(col);
+    g_last_error = msg;
+  }
+  return rc;
 }
 
 extern "C" int32_t llkv_gpu_column_append_blob(llkv_gpu_column* col, uint64_t chunk_pk, const void* blob, uint64_t blob_len,
@@ -943,18 +1160,55 @@ extern "C" int32_t llkv_gpu_column_append_blob(llkv_gpu_column* col, uint64_t ch
   return llkv_gpu_column_append_chunk(col, chunk_pk, b + 24, len, nullptr, row_ids, row_id_base, nullptr);
 }
 
+// A host-narrowed chunk did not fit: the column goes back to the Arrow layout and the chunks appended since the last seal
+// are copied again, wide, straight from their (page-locked, still valid: llkv_gpu.h) sources.
+static int32_t recover_wide(llkv_gpu_column* col) {
+  llkv_gpu_ctx* c = col->ctx;
+  const uint64_t keep = col->narrow_chunks.empty() ? col->n_rows : col->narrow_chunks.front().first_row;
+  col->host_kind = col->load_kind == LK_D32 ? (int)UP_NARROW_D128_I64 : -2;  // next time: the wider form, or none
+  int32_t rc = widen_decimal(col, keep);
+  if (rc) return rc;
+  cudaStream_t s = c->copy_streams[(size_t)col->stream_index];
+  for (const NarrowChunk& ch : col->narrow_chunks) {
+    CUDA_TRY(cudaMemcpyAsync((char*)col->values + ch.first_row * 16, ch.src, ch.n_rows * 16, cudaMemcpyHostToDevice, s));
+    col->h2d_bytes += ch.n_rows * 16;
+  }
+  CUDA_TRY(cudaStreamSynchronize(s));
+  col->ticket.failed.store(0);
+  return LLKV_OK;
+}
+
+// Issues and waits for everything the column's appends left in flight.  After it returns the sources may be reused.
+static int32_t column_flush(llkv_gpu_column* col) {
+  llkv_gpu_ctx* c = col->ctx;
+  int32_t rc = flush_upload(col);
+  if (rc) return rc;
+  if ((rc = drain_jobs(col))) return rc;
+  if (col->ticket.failed.load() && (rc = recover_wide(col))) return rc;
+  col->narrow_chunks.clear();
+  for (cudaStream_t s : c->copy_streams) CUDA_TRY(cudaStreamSynchronize(s));
+  return LLKV_OK;
+}
+
+extern "C" int32_t llkv_gpu_column_flush(llkv_gpu_column* col) {
+  if (!col) return set_error(LLKV_ERR_INVALID_ARGUMENT, "column is NULL");
+  CTX_LOCK(col->ctx);
+  CUDA_TRY(cudaSetDevice(col->ctx->device));
+  return column_flush(col);
+}
+
 extern "C" int32_t llkv_gpu_column_seal(llkv_gpu_column* col) {
   if (!col) return set_error(LLKV_ERR_INVALID_ARGUMENT, "column is NULL");
   llkv_gpu_ctx* c = col->ctx;
+  CTX_LOCK(c);
   CUDA_TRY(cudaSetDevice(c->device));
   {
-    int32_t frc = flush_upload(col);
+    int32_t frc = column_flush(col);
     if (frc) return frc;
   }
-  for (cudaStream_t s : c->copy_streams) CUDA_TRY(cudaStreamSynchronize(s));
   for (void* p : col->deferred_free) cudaFree(p);
   col->deferred_free.clear();
-  if (col->stats_rows < col->n_rows && col->load_kind != LK_STR8 && col->load_kind != LK_D64) {  // min / max / fits-i64 over the rows appended since the last seal
+  if (col->stats_rows < col->n_rows && col->load_kind != LK_STR8) {  // min / max / fits-i64 over the rows appended since the last seal
     int32_t rc = launch_stats(col, col->stats_rows, col->n_rows - col->stats_rows);
     if (rc) return rc;
     CUDA_TRY(cudaStreamSynchronize(c->copy_streams[(size_t)col->stream_index]));
@@ -979,18 +1233,22 @@ extern "C" int32_t llkv_gpu_column_seal(llkv_gpu_column* col) {
       col->load_kind = LK_STR8;
     }
   }
-  // Decimal128 whose every value is a sign-extended i64: keep 8 bytes per row resident (half the HBM traffic and half
-  // the shared-memory tile of every scan); the Arrow layout is restored if more chunks are appended
+  // Decimal128 whose every value is a sign-extended i64 (i32): keep 8 (4) bytes per row resident — half (a quarter of) the
+  // HBM traffic and shared-memory tile of every scan; the Arrow layout is restored if chunks arrive that do not fit
   if (col->type == LLKV_PT_DECIMAL128 && col->load_kind == LK_D128 && col->n_rows && col->hstats.not_i64 == 0 && !c->keep_wide_decimals) {
-    u64* nv = (u64*)col->narrow;
-    if (!nv || col->narrow_cap < col->cap_rows) {
+    const i64 mn = (i64)(col->hstats.min_enc ^ 0x8000000000000000ull), mx = (i64)(col->hstats.max_enc ^ 0x8000000000000000ull);
+    const bool fits32 = mn >= (i64)INT32_MIN && mx <= (i64)INT32_MAX && !c->no_d32;
+    const uint32_t width = fits32 ? 4u : 8u;
+    void* nv = col->narrow;
+    if (!nv || col->narrow_cap < col->cap_rows || col->narrow_width != width) {
       if (nv) CUDA_TRY(cudaFree(nv));
-      CUDA_TRY(cudaMalloc((void**)&nv, col->cap_rows * 8));
-      CUDA_TRY(cudaMemset(nv, 0, col->cap_rows * 8));
-      col->narrow_cap = col->cap_rows;
+      col->narrow = nullptr;
+      CUDA_TRY(cudaMalloc(&nv, col->cap_rows * width));
+      CUDA_TRY(cudaMemset(nv, 0, col->cap_rows * width));
     }
     cudaStream_t ns = c->copy_streams[(size_t)col->stream_index];
-    narrow_dec_kernel<<<1184, 256, 0, ns>>>((const ulonglong2*)col->values, nv, col->n_rows);
+    if (fits32) narrow_dec32_kernel<<<1184, 256, 0, ns>>>((const ulonglong2*)col->values, (int*)nv, col->n_rows);
+    else narrow_dec_kernel<<<1184, 256, 0, ns>>>((const ulonglong2*)col->values, (u64*)nv, col->n_rows);
     CUDA_TRY(cudaGetLastError());
     CUDA_TRY(cudaStreamSynchronize(ns));
     if (col->reupload_hint) {  // the Arrow-layout buffer stays for the next batch
@@ -1004,8 +1262,8 @@ extern "C" int32_t llkv_gpu_column_seal(llkv_gpu_column* col) {
     col->narrow = nullptr;
     col->narrow_cap = 0;
     col->values = nv;
-    col->elem_bytes = 8;
-    col->load_kind = LK_D64;
+    col->elem_bytes = width;
+    col->load_kind = fits32 ? LK_D32 : LK_D64;
   }
   col->sealed = true;
   return LLKV_OK;
@@ -1017,10 +1275,17 @@ extern "C" int32_t llkv_gpu_column_rows(const llkv_gpu_column* col, uint64_t* ou
   return LLKV_OK;
 }
 
+extern "C" int32_t llkv_gpu_column_h2d_bytes(const llkv_gpu_column* col, uint64_t* out_bytes) {
+  if (!col || !out_bytes) return set_error(LLKV_ERR_INVALID_ARGUMENT, "NULL argument");
+  *out_bytes = col->h2d_bytes;
+  return LLKV_OK;
+}
+
 extern "C" int32_t llkv_gpu_column_read(llkv_gpu_column* col, uint64_t row_begin, uint64_t n_rows, void* out, uint64_t out_bytes) {
   if (!col || (n_rows && !out)) return set_error(LLKV_ERR_INVALID_ARGUMENT, "NULL argument");
   if (col->type == LLKV_PT_UTF8) return set_error(LLKV_ERR_INVALID_ARGUMENT, "llkv_gpu_column_read does not support Utf8 columns");
   llkv_gpu_ctx* c = col->ctx;
+  CTX_LOCK(c);
   CUDA_TRY(cudaSetDevice(c->device));
   if (!col->sealed) {
     int32_t rc = llkv_gpu_column_seal(col);
@@ -1032,10 +1297,12 @@ extern "C" int32_t llkv_gpu_column_read(llkv_gpu_column* col, uint64_t row_begin
   const uint64_t width = (uint64_t)prim_type_width(col->type);
   if (out_bytes < n_rows * width) return set_error(LLKV_ERR_INVALID_ARGUMENT, "output buffer too small");
   if (n_rows == 0) return LLKV_OK;
-  if (col->load_kind == LK_D64) {  // resident i64 image of a Decimal128 column: widen the range on the device first
+  if (is_narrow_decimal(col)) {  // resident i64 / i32 image of a Decimal128 column: widen the range on the device first
     ulonglong2* wide = nullptr;
     CUDA_TRY(cudaMalloc((void**)&wide, n_rows * 16));
-    widen_dec_kernel<<<(unsigned)std::min<uint64_t>((n_rows + 255) / 256, 1184), 256, 0, c->stream>>>((const u64*)col->values + row_begin, wide, n_rows);
+    const unsigned blocks = (unsigned)std::min<uint64_t>((n_rows + 255) / 256, 1184);
+    if (col->load_kind == LK_D32) widen_dec32_kernel<<<blocks, 256, 0, c->stream>>>((const int*)col->values + row_begin, wide, n_rows);
+    else widen_dec_kernel<<<blocks, 256, 0, c->stream>>>((const u64*)col->values + row_begin, wide, n_rows);
     cudaError_t e = cudaGetLastError();
     if (e == cudaSuccess) e = cudaMemcpyAsync(out, wide, n_rows * 16, cudaMemcpyDeviceToHost, c->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
@@ -1051,9 +1318,16 @@ extern "C" int32_t llkv_gpu_column_read(llkv_gpu_column* col, uint64_t row_begin
 extern "C" int32_t llkv_gpu_column_clear(llkv_gpu_column* col) {
   if (!col) return set_error(LLKV_ERR_INVALID_ARGUMENT, "column is NULL");
   llkv_gpu_ctx* c = col->ctx;
+  CTX_LOCK(c);
   CUDA_TRY(cudaSetDevice(c->device));
   cudaStream_t s = c->copy_streams[(size_t)col->stream_index];
   col->pend_bytes = 0;  // rows that were never copied are dropped with the rest
+  {
+    int32_t rc = drain_jobs(col);
+    if (rc) return rc;
+    col->narrow_chunks.clear();
+    col->ticket.failed.store(0);
+  }
   CUDA_TRY(cudaStreamSynchronize(c->stream));
   if (col->type == LLKV_PT_UTF8 && col->load_kind == LK_STR8) {  // back to the packed representation for new appends
     if (col->values) CUDA_TRY(cudaFree(col->values));
@@ -1063,15 +1337,21 @@ extern "C" int32_t llkv_gpu_column_clear(llkv_gpu_column* col) {
     col->load_kind = LK_U64;
   }
   col->reupload_hint = true;
-  if (col->load_kind == LK_D64) {  // back to the Arrow layout for new appends; the i64 buffer is parked for the next seal
+  if (is_narrow_decimal(col)) {  // back to the Arrow layout for new appends; the narrow buffer is parked for the next batch
+    if (col->narrow && col->narrow != col->values) CUDA_TRY(cudaFree(col->narrow));
     col->narrow = col->values;
     col->narrow_cap = col->cap_rows;
+    col->narrow_width = col->elem_bytes;
     col->values = col->landing;
-    if (!col->landing) col->cap_rows = 0;
+    col->cap_rows = col->landing ? col->landing_cap : 0;
     col->landing = nullptr;
     col->landing_cap = 0;
     col->elem_bytes = 16;
     col->load_kind = LK_D128;
+    if (col->validity) {  // sized by the capacity that was just parked
+      CUDA_TRY(cudaFree(col->validity));
+      col->validity = nullptr;
+    }
   }
   if (col->validity) CUDA_TRY(cudaMemsetAsync(col->validity, 0, (col->cap_rows / 32 + 4) * 4, s));
   DevStats init;
@@ -1093,7 +1373,10 @@ extern "C" int32_t llkv_gpu_column_clear(llkv_gpu_column* col) {
 extern "C" int32_t llkv_gpu_column_destroy(llkv_gpu_column* col) {
   if (!col) return LLKV_OK;
   llkv_gpu_ctx* c = col->ctx;
+  CTX_LOCK(c);
   cudaSetDevice(c->device);
+  col->pend_bytes = 0;
+  drain_jobs(col);
   cudaDeviceSynchronize();
   c->columns.erase(col->lfid);
   for (auto& kv : c->mvcc)
@@ -1146,6 +1429,7 @@ extern "C" int32_t llkv_gpu_mvcc_set(llkv_gpu_ctx* ctx, uint64_t table_id, llkv_
   if (n_noncommitted > kMaxNoncommitted) return set_error(LLKV_ERR_INVALID_ARGUMENT, "more than %d non-committed transactions in one snapshot", kMaxNoncommitted);
   if ((created_by && created_by->type != LLKV_PT_UINT64) || (deleted_by && deleted_by->type != LLKV_PT_UINT64))
     return set_error(LLKV_ERR_INVALID_ARGUMENT, "MVCC columns must be UInt64");
+  CTX_LOCK(ctx);
   MvccState& m = ctx->mvcc[table_id];
   m.created_by = created_by;
   m.deleted_by = deleted_by;
@@ -1157,6 +1441,7 @@ extern "C" int32_t llkv_gpu_mvcc_set(llkv_gpu_ctx* ctx, uint64_t table_id, llkv_
 
 extern "C" int32_t llkv_gpu_mvcc_clear(llkv_gpu_ctx* ctx, uint64_t table_id) {
   if (!ctx) return set_error(LLKV_ERR_INVALID_ARGUMENT, "ctx is NULL");
+  CTX_LOCK(ctx);
   ctx->mvcc.erase(table_id);
   return LLKV_OK;
 }
@@ -1629,9 +1914,10 @@ extern "C" int32_t llkv_gpu_debug_plan(const llkv_debug_column* cols, int32_t n_
     m.elem_bytes = device_elem_bytes(d.prim_type);
     if (m.elem_bytes == 0) return set_error(LLKV_ERR_INVALID_ARGUMENT, "column type %d does not cross this boundary", d.prim_type);
     m.arrow_bytes = d.prim_type == LLKV_PT_UTF8 ? 4u + d.max_strlen : (uint32_t)prim_type_width(d.prim_type);
-    if (d.prim_type == LLKV_PT_DECIMAL128 && d.dec_fits_i64) {  // as sealed: resident i64
-      m.load_kind = LK_D64;
-      m.elem_bytes = 8;
+    if (d.prim_type == LLKV_PT_DECIMAL128 && d.dec_fits_i64) {  // as sealed: resident i64, or i32 when the statistics allow
+      const bool fits32 = d.has_minmax && d.min_value >= (int64_t)INT32_MIN && d.max_value <= (int64_t)INT32_MAX;
+      m.load_kind = fits32 ? LK_D32 : LK_D64;
+      m.elem_bytes = fits32 ? 4 : 8;
     }
     if (d.prim_type == LLKV_PT_UTF8 && d.max_strlen == 1) {  // as sealed: one byte per row
       m.load_kind = LK_STR8;
@@ -1713,6 +1999,7 @@ extern "C" int32_t llkv_gpu_filter_bitmap(llkv_gpu_ctx* ctx, uint64_t table_id, 
                                            uint64_t* out_count) {
   if (!ctx) return set_error(LLKV_ERR_INVALID_ARGUMENT, "ctx is NULL");
   if (row_end < row_begin) return set_error(LLKV_ERR_INVALID_ARGUMENT, "row_end < row_begin");
+  CTX_LOCK(ctx);
   CUDA_TRY(cudaSetDevice(ctx->device));
   CompileRequest req;
   std::vector<llkv_gpu_column*> handles;
@@ -1788,6 +2075,7 @@ extern "C" int32_t llkv_gpu_agg_create(llkv_gpu_ctx* ctx, uint64_t table_id, con
     if (specs[i].expr_root >= n_nodes) return set_error(LLKV_ERR_INVALID_ARGUMENT, "aggregate %d: expression root out of range", i);
     if (specs[i].expr_root < 0 && specs[i].kind != LLKV_AGG_COUNT) return set_error(LLKV_ERR_INVALID_ARGUMENT, "aggregate %d needs an argument", i);
   }
+  CTX_LOCK(ctx);
   CUDA_TRY(cudaSetDevice(ctx->device));
   llkv_gpu_agg* a = new llkv_gpu_agg();
   a->ctx = ctx;
@@ -1814,6 +2102,7 @@ extern "C" int32_t llkv_gpu_agg_create(llkv_gpu_ctx* ctx, uint64_t table_id, con
 
 extern "C" void llkv_gpu_agg_destroy(llkv_gpu_agg* a) {
   if (!a) return;
+  CTX_LOCK(a->ctx);
   cudaSetDevice(a->ctx->device);
   cudaStreamSynchronize(a->ctx->stream);
   if (a->d_gclass) cudaFree(a->d_gclass);
@@ -2458,6 +2747,7 @@ static int32_t agg_resolve(llkv_gpu_agg* a) {
 extern "C" int32_t llkv_gpu_agg_reset(llkv_gpu_agg* a) {
   if (!a) return set_error(LLKV_ERR_INVALID_ARGUMENT, "agg is NULL");
   llkv_gpu_ctx* ctx = a->ctx;
+  CTX_LOCK(ctx);
   CUDA_TRY(cudaSetDevice(ctx->device));
   if (a->pending.active) {
     CUDA_TRY(cudaStreamSynchronize(ctx->stream));
@@ -2476,6 +2766,7 @@ extern "C" int32_t llkv_gpu_agg_run(llkv_gpu_agg* a, const llkv_gpu_program* pro
                                      uint64_t row_end) {
   if (!a) return set_error(LLKV_ERR_INVALID_ARGUMENT, "agg is NULL");
   if (row_end < row_begin) return set_error(LLKV_ERR_INVALID_ARGUMENT, "row_end < row_begin");
+  CTX_LOCK(a->ctx);
   CUDA_TRY(cudaSetDevice(a->ctx->device));
   if (a->err_code) return set_error(a->err_code, "%s", a->err_msg.c_str());
   int32_t rc = agg_resolve(a);
@@ -2747,6 +3038,7 @@ static int32_t agg_ensure_layout(llkv_gpu_agg* a) {
 
 extern "C" int32_t llkv_gpu_agg_group_count(llkv_gpu_agg* a, uint64_t* out_groups) {
   if (!a || !out_groups) return set_error(LLKV_ERR_INVALID_ARGUMENT, "NULL argument");
+  CTX_LOCK(a->ctx);
   CUDA_TRY(cudaSetDevice(a->ctx->device));
   if (a->err_code) return set_error(a->err_code, "%s", a->err_msg.c_str());
   int32_t rc = agg_resolve(a);
@@ -2762,6 +3054,7 @@ extern "C" int32_t llkv_gpu_agg_group_count(llkv_gpu_agg* a, uint64_t* out_group
 extern "C" int32_t llkv_gpu_agg_finalize(llkv_gpu_agg* a, llkv_agg_value* out_values, llkv_group_key* out_keys, uint64_t group_capacity,
                                           uint64_t* out_groups) {
   if (!a) return set_error(LLKV_ERR_INVALID_ARGUMENT, "agg is NULL");
+  CTX_LOCK(a->ctx);
   CUDA_TRY(cudaSetDevice(a->ctx->device));
   if (a->err_code) return set_error(a->err_code, "%s", a->err_msg.c_str());
   int32_t rc = agg_resolve(a);
@@ -2864,6 +3157,7 @@ extern "C" int32_t llkv_gpu_comm_init(llkv_gpu_ctx* ctx, const uint8_t id[LLKV_G
   if (n_ranks < 1 || rank < 0 || rank >= n_ranks) return set_error(LLKV_ERR_INVALID_ARGUMENT, "bad rank %d of %d", rank, n_ranks);
   int32_t rc = load_nccl();
   if (rc) return rc;
+  CTX_LOCK(ctx);
   CUDA_TRY(cudaSetDevice(ctx->device));
   if (ctx->nccl_comm) {
     g_nccl.comm_destroy(ctx->nccl_comm);
@@ -2892,6 +3186,7 @@ static void comm_teardown_p2p(llkv_gpu_ctx* ctx) {
 
 extern "C" int32_t llkv_gpu_comm_destroy(llkv_gpu_ctx* ctx) {
   if (!ctx) return set_error(LLKV_ERR_INVALID_ARGUMENT, "ctx is NULL");
+  CTX_LOCK(ctx);
   if (ctx->nccl_comm && g_nccl.comm_destroy) {
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
@@ -2909,6 +3204,7 @@ extern "C" int32_t llkv_gpu_comm_destroy(llkv_gpu_ctx* ctx) {
 extern "C" int32_t llkv_gpu_agg_merge(llkv_gpu_agg* a) {
   if (!a) return set_error(LLKV_ERR_INVALID_ARGUMENT, "agg is NULL");
   llkv_gpu_ctx* ctx = a->ctx;
+  CTX_LOCK(ctx);
   CUDA_TRY(cudaSetDevice(ctx->device));
   if (a->err_code) return set_error(a->err_code, "%s", a->err_msg.c_str());
   int32_t rc;

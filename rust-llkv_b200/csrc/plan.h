@@ -130,7 +130,8 @@ constexpr int kFastTmps = 3;     // tile-sized temporaries of the lean kernel
 
 enum KeyKind : uint8_t { KK_INT = 0, KK_STR = 1 };
 enum LoadKind : uint8_t { LK_I8, LK_I16, LK_I32, LK_I64, LK_U8, LK_U16, LK_U32, LK_U64, LK_F32, LK_F64, LK_D128, LK_STR8,
-                          LK_D64 };  // Decimal128 column kept as i64 in HBM: every value is a sign-extended i64 (narrowed at seal)
+                          LK_D64,    // Decimal128 column kept as i64 in HBM: every value is a sign-extended i64 (narrowed at seal or on the host)
+                          LK_D32 };  // ... kept as i32: every value is a sign-extended i32
 
 // classes of accumulator words: how a word is initialised, merged across CTAs / launches / ranks
 enum WordClass : uint8_t {

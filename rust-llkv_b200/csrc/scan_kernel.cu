@@ -204,6 +204,7 @@ __global__ void __launch_bounds__(512) scan_kernel(const Plan* __restrict__ gpla
               case LK_F32: v = f64_bits((double)*reinterpret_cast<const float*>(src)); break;
               case LK_F64: v = *reinterpret_cast<const i64*>(src); break;
               case LK_D64: v = *reinterpret_cast<const i64*>(src); break;
+              case LK_D32: v = *reinterpret_cast<const int*>(src); break;
               case LK_STR8: v = (V)(((i64)(u64)(*reinterpret_cast<const unsigned char*>(src)) << 56) | 1); break;
               case LK_D128: {
                 ulonglong2 w;

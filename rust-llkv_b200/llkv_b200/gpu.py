@@ -70,6 +70,9 @@ def load():
         "llkv_gpu_column_append_chunk": (i32, [vp, u64, vp, u64, vp, vp, u64, vp]),
         "llkv_gpu_column_append_blob": (i32, [vp, u64, vp, u64, vp, u64]),
         "llkv_gpu_column_seal": (i32, [vp]),
+        "llkv_gpu_column_flush": (i32, [vp]),
+        "llkv_gpu_column_h2d_bytes": (i32, [vp, P(u64)]),
+        "llkv_gpu_ctx_set_upload_threads": (i32, [vp, i32]),
         "llkv_gpu_column_rows": (i32, [vp, P(u64)]),
         "llkv_gpu_column_read": (i32, [vp, u64, u64, vp, u64]),
         "llkv_gpu_column_clear": (i32, [vp]),
@@ -170,6 +173,10 @@ class Context:
         (default), 2 = from the first scan, whenever any tile drops out."""
         _check(self.lib.llkv_gpu_ctx_set_pruning(self.handle, mode))
 
+    def set_upload_threads(self, n_threads: int):
+        """Host workers narrowing Decimal128 chunks from page-locked sources before the DMA: -1 default, 0 off."""
+        _check(self.lib.llkv_gpu_ctx_set_upload_threads(self.handle, n_threads))
+
     # ---- multi-GPU (NCCL over NVLink): the unique id travels through whatever the host uses for rendezvous
     def comm_unique_id(self) -> bytes:
         buf = (C.c_uint8 * ffi.UNIQUE_ID_BYTES)()
@@ -265,6 +272,15 @@ class DeviceColumn:
 
     def seal(self):
         _check(self.lib.llkv_gpu_column_seal(self.handle))
+
+    def flush(self):
+        """Issues and waits for the copies the appends left pending; page-locked sources may be reused afterwards."""
+        _check(self.lib.llkv_gpu_column_flush(self.handle))
+
+    def h2d_bytes(self) -> int:
+        n = C.c_uint64()
+        _check(self.lib.llkv_gpu_column_h2d_bytes(self.handle, C.byref(n)))
+        return int(n.value)
 
     def read(self, row_begin: int = 0, n_rows: Optional[int] = None) -> np.ndarray:
         """Rows of the resident image back in the Arrow values layout (what a PrimitiveVisitor chunk callback would see)."""
