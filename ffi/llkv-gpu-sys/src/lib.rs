@@ -156,6 +156,8 @@ pub struct llkv_run_info {
     pub used_jit_kernel: u32,
     pub partitions: u32,
     pub tiles_pruned: u32,
+    pub graph_replays: u32,
+    pub merged_p2p: u32,
 }
 
 #[repr(C)]
@@ -198,6 +200,8 @@ extern "C" {
     pub fn llkv_gpu_host_unregister(p: *const c_void) -> i32;
     /// Host workers narrowing Decimal128 chunks from page-locked sources before the DMA: -1 default, 0 off.
     pub fn llkv_gpu_ctx_set_upload_threads(ctx: *mut llkv_gpu_ctx, n_threads: i32) -> i32;
+    /// llkv_gpu_agg_execute replays a captured CUDA graph once a step repeats unchanged: 1 (default) / 0.
+    pub fn llkv_gpu_ctx_set_graphs(ctx: *mut llkv_gpu_ctx, mode: i32) -> i32;
 
     /// Compiles a plan against column statistics only (no device): the lean program's listing, optionally its specialised
     /// cubin.  For tooling and CPU-side tests.
@@ -238,6 +242,8 @@ extern "C" {
     pub fn llkv_gpu_agg_reset(agg: *mut llkv_gpu_agg) -> i32;
     pub fn llkv_gpu_agg_run(agg: *mut llkv_gpu_agg, prog: *const llkv_gpu_program, apply_mvcc: i32, row_begin: u64, row_end: u64) -> i32;
     pub fn llkv_gpu_agg_merge(agg: *mut llkv_gpu_agg) -> i32;
+    /// reset + run + (merge) in one call; replayed as one CUDA graph once the step repeats unchanged.
+    pub fn llkv_gpu_agg_execute(agg: *mut llkv_gpu_agg, prog: *const llkv_gpu_program, apply_mvcc: i32, row_begin: u64, row_end: u64, merge: i32) -> i32;
     pub fn llkv_gpu_agg_group_count(agg: *mut llkv_gpu_agg, out_groups: *mut u64) -> i32;
     pub fn llkv_gpu_agg_finalize(agg: *mut llkv_gpu_agg, out_values: *mut llkv_agg_value, out_keys: *mut llkv_group_key, group_capacity: u64, out_groups: *mut u64) -> i32;
     pub fn llkv_gpu_agg_run_info(agg: *const llkv_gpu_agg, out: *mut llkv_run_info) -> i32;

@@ -232,6 +232,8 @@ typedef struct llkv_run_info {
   uint32_t used_jit_kernel;     /* 1 when the lean kernel ran as a build specialised on this plan shape (jit.cpp) */
   uint32_t partitions;          /* hash partitions of a partitioned high-cardinality GROUP BY run, 0 = not partitioned */
   uint32_t tiles_pruned;        /* tiles the scan skipped because no conjunct range predicate can match their zones */
+  uint32_t graph_replays;       /* steps of this aggregate that llkv_gpu_agg_execute replayed from its captured CUDA graph */
+  uint32_t merged_p2p;          /* 1 when the last merge was one kernel over NVLink peer mailboxes (no collective, no host wait) */
 } llkv_run_info;
 
 typedef struct llkv_gpu_ctx llkv_gpu_ctx;
@@ -379,7 +381,9 @@ int32_t llkv_gpu_column_reserve(llkv_gpu_column* col, uint64_t n_rows);
  * reference's chunk format stores no nulls, serialization.rs:265-269).  `row_ids` is the chunk's
  * row-id shadow column or NULL for the dense run starting at `row_id_base`.  Row ids must continue the
  * column densely (SURVEY.md §7 hard part (a)); anything else is LLKV_ERR_INVALID_ARGUMENT for now.
- * For LLKV_PT_UTF8 `values` is the i32 offsets buffer (n_rows+1) and `aux` the data bytes. */
+ * For LLKV_PT_UTF8 `values` is the i32 offsets buffer (n_rows+1) and `aux` the data bytes.
+ * `values` may also point into device memory of the context's GPU (fixed-width types): the chunk is then copied device to
+ * device in stream order, and the page-locked lifetime rule above applies to it. */
 int32_t llkv_gpu_column_append_chunk(llkv_gpu_column* col, uint64_t chunk_pk, const void* values, uint64_t n_rows,
                                      const uint8_t* validity, const uint64_t* row_ids, uint64_t row_id_base,
                                      const void* aux);
@@ -440,6 +444,13 @@ int32_t llkv_gpu_agg_run(llkv_gpu_agg* agg, const llkv_gpu_program* prog, int32_
                          uint64_t row_end);
 /* Merges the partial states of all ranks of the communicator bound to the context. */
 int32_t llkv_gpu_agg_merge(llkv_gpu_agg* agg);
+/* One step of a prepared aggregate in one call: llkv_gpu_agg_reset + llkv_gpu_agg_run + (merge != 0 and the context has
+ * peers) llkv_gpu_agg_merge — what the executor branch of INTEGRATION.md issues per query (llkv-executor/src/lib.rs:
+ * 5357-5682: new states, scan, finalize).  Once a step repeats with nothing changed it is captured as one CUDA graph and
+ * replayed with a single launch (llkv_gpu_ctx_set_graphs: 1 = default, 0 = never).  Results are identical either way. */
+int32_t llkv_gpu_agg_execute(llkv_gpu_agg* agg, const llkv_gpu_program* prog, int32_t apply_mvcc, uint64_t row_begin,
+                             uint64_t row_end, int32_t merge);
+int32_t llkv_gpu_ctx_set_graphs(llkv_gpu_ctx* ctx, int32_t mode);
 /* Number of groups currently held (1 for ungrouped). Synchronises. */
 int32_t llkv_gpu_agg_group_count(llkv_gpu_agg* agg, uint64_t* out_groups);
 /* finalize(): writes n_groups*n_aggs values (group-major) and n_groups*n_keys keys, groups in first-appearance

@@ -10,6 +10,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <atomic>
 #include <map>
 #include <memory>
 #include <mutex>
@@ -34,11 +35,16 @@ cudaError_t launch_lean(const LeanPlan& plan, uint32_t grid, cudaStream_t stream
 cudaError_t launch_partition_apply(const PartPlan& plan, uint32_t grid, cudaStream_t stream);
 cudaError_t launch_init_table(u64* keys, u64* words, u64 rows, uint32_t n_gwords, const uint8_t* word_class_dev, cudaStream_t stream);
 cudaError_t launch_merge_table(const Plan* dplan, const u64* src_keys, const u64* src_words, u64 src_cap, cudaStream_t stream);
-cudaError_t launch_merge_ungrouped_p2p(u64* state, u64* const* peer_boxes, int n_ranks, int rank, uint32_t n_gwords, u64 epoch,
+cudaError_t launch_merge_ungrouped_p2p(u64* state, u64* const* peer_boxes, int n_ranks, int rank, uint32_t n_gwords, u64* epoch_dev,
                                        const uint8_t* word_class_dev, uint32_t* flags, cudaStream_t stream);
 cudaError_t launch_merge_ungrouped(u64* dst, const u64* all_words, int n_ranks, uint32_t n_gwords, u64 rank_stride, const uint8_t* word_class_dev,
                                    cudaStream_t stream);
+cudaError_t launch_merge_grouped_p2p(u64* gkeys, u64* gwords, u64 gcap, uint32_t n_gwords, const uint8_t* word_class_dev, uint32_t* flags,
+                                     u64* const* peer_boxes, uint32_t slot_words, int n_ranks, int rank, u64* epoch_dev, bool exchange, cudaStream_t stream);
 }  // namespace llkv
+// peer mailboxes (llkv_gpu_comm_init): [n_ranks][2][128] words for ungrouped state rows, then [n_ranks][2][kGroupSlotWords]
+// words for small group tables
+static constexpr uint32_t kUngroupedSlotWords = 128, kGroupSlotWords = 16384;
 
 using namespace llkv;
 
@@ -294,13 +300,16 @@ struct llkv_gpu_ctx {
   int n_ranks = 1, rank = 0;
   // peer-memory mailboxes for the ungrouped merge (scan_kernel.cu: merge_ungrouped_p2p_kernel): every rank maps every
   // other rank's mailbox through CUDA IPC at llkv_gpu_comm_init; all ranks use this path or none does
-  u64* mbox = nullptr;            // this rank's mailbox: [n_ranks][2][128] words
+  u64* mbox = nullptr;            // this rank's mailbox: [n_ranks][2][128] words, then [n_ranks][2][kGroupSlotWords]
+  u64* peer_gbox[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};  // the group-table region of every rank's mailbox
   u64* peer_mbox[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   bool p2p_merge = false;
-  u64 merge_epoch = 0;
+  u64* d_epoch = nullptr;  // merges so far, in device memory (the merge kernels advance it: their launches carry no per-merge value)
   // Calls that share this context's state (column registry, staging ring, stream, snapshots, plan cache) are serialised
   // here, so handles of one context may be used from several threads (the Rust wrapper's `Sync`).
   std::recursive_mutex mu;
+  uint64_t state_epoch = 1;  // bumped by every call that can change what a compiled plan depends on (columns, snapshots, knobs)
+  int graph_mode = 1;        // llkv_gpu_agg_execute: 1 = replay a captured CUDA graph once a step repeats unchanged, 0 = never
   // host workers that narrow Decimal128 chunks from page-locked sources before the DMA (upload.h); created on first use
   int upload_threads = -1;  // -1 = default (min(16, hardware threads)), 0 = never narrow on the host
   std::unique_ptr<UploadPool> pool;
@@ -365,6 +374,7 @@ struct llkv_gpu_column {
 };
 
 struct llkv_gpu_program {
+  uint64_t serial = 0;  // identity of the compiled program (handles can be freed and their addresses reused)
   std::vector<llkv_eval_op> ops;
   std::vector<llkv_literal> literals;
   std::vector<llkv_scalar_node> nodes;
@@ -391,6 +401,7 @@ struct PendingRun {
   bool wide = false;
   bool has_backup = false;
   bool timed = false;
+  bool is_merge = false;  // a grouped peer-mailbox merge is queued behind the run (agg_resolve settles both)
 };
 
 struct llkv_gpu_agg {
@@ -421,6 +432,7 @@ struct llkv_gpu_agg {
   u64* mg_stats = nullptr;  // scratch of agree_key_stats
   size_t mg_stats_elems = 0;
   std::vector<u64> agreed_stats;  // what the ranks agreed on in the current run (reused by this rank's reruns)
+  uint64_t agreed_epoch = 0;      // ctx->state_epoch at that time
   bool in_rerun = false;
   // the lean plan of the previous run, reusable while request_signature() does not change
   LeanPlan lean;
@@ -451,6 +463,21 @@ struct llkv_gpu_agg {
   Plan* h_plan = nullptr;  // pinned
   CompileResult cr;
   PendingRun pending;
+  bool reset_pending = false;   // llkv_gpu_agg_reset is applied by whatever touches the state next (in stream order)
+  uint64_t plan_epoch = 1;      // bumped when this aggregate's own launch state changes (table grown, geometry re-chosen)
+  // llkv_gpu_agg_execute: one step = reset -> scan -> [merge] -> result copy.  Once a step repeats with nothing changed
+  // it is captured as a CUDA graph and replayed: one launch call per step.
+  uint64_t exec_key = 0;
+  uint32_t exec_same = 0;       // consecutive clean steps with this key
+  cudaGraphExec_t graph_exec = nullptr;
+  uint64_t graph_key = 0;
+  PendingRun graph_pending;     // the pending-run bookkeeping of the captured step (without the program copy)
+  bool graph_prefetched = false;
+  uint32_t graph_launches = 0;
+  bool in_capture = false;
+  uint32_t capture_failures = 0;
+  bool stage_ev_valid = false;
+  bool p2p_group_disabled = false;  // a rank's group table outgrew a mailbox slot once: this aggregate merges over NCCL from then on
   int32_t err_code = 0;
   std::string err_msg;
   llkv_run_info info;
@@ -568,6 +595,7 @@ extern "C" int32_t llkv_gpu_ctx_stream(llkv_gpu_ctx* c, void** out_stream) {
 extern "C" int32_t llkv_gpu_ctx_set_timing(llkv_gpu_ctx* c, int32_t enabled) {
   if (!c) return set_error(LLKV_ERR_INVALID_ARGUMENT, "ctx is NULL");
   c->timing = enabled != 0;
+  ++c->state_epoch;
   return LLKV_OK;
 }
 
@@ -575,6 +603,7 @@ extern "C" int32_t llkv_gpu_ctx_set_jit(llkv_gpu_ctx* c, int32_t mode) {
   if (!c) return set_error(LLKV_ERR_INVALID_ARGUMENT, "ctx is NULL");
   if (mode < 0 || mode > 2) return set_error(LLKV_ERR_INVALID_ARGUMENT, "jit mode must be 0, 1 or 2");
   c->jit_mode = mode;
+  ++c->state_epoch;
   return LLKV_OK;
 }
 
@@ -582,6 +611,7 @@ extern "C" int32_t llkv_gpu_ctx_set_partitioning(llkv_gpu_ctx* c, int32_t mode) 
   if (!c) return set_error(LLKV_ERR_INVALID_ARGUMENT, "ctx is NULL");
   if (mode < 0 || mode > 2) return set_error(LLKV_ERR_INVALID_ARGUMENT, "partitioning mode must be 0, 1 or 2");
   c->partition_mode = mode;
+  ++c->state_epoch;
   return LLKV_OK;
 }
 
@@ -589,6 +619,7 @@ extern "C" int32_t llkv_gpu_ctx_set_pruning(llkv_gpu_ctx* c, int32_t mode) {
   if (!c) return set_error(LLKV_ERR_INVALID_ARGUMENT, "ctx is NULL");
   if (mode < 0 || mode > 2) return set_error(LLKV_ERR_INVALID_ARGUMENT, "pruning mode must be 0, 1 or 2");
   c->prune_mode = mode;
+  ++c->state_epoch;
   return LLKV_OK;
 }
 
@@ -605,6 +636,7 @@ extern "C" int32_t llkv_gpu_ctx_set_tuning(llkv_gpu_ctx* c, int32_t ctas_per_sm,
   c->tune_stages = stages;
   c->tune_rpt = rows_per_thread;
   c->tune_force_wide = force_wide;
+  ++c->state_epoch;
   return LLKV_OK;
 }
 
@@ -734,6 +766,7 @@ extern "C" int32_t llkv_gpu_column_register(llkv_gpu_ctx* c, uint64_t lfid, int3
     return set_error(LLKV_ERR_IO, "CUDA error %s allocating column state", cudaGetErrorString(e));
   }
   c->columns[lfid] = col;
+  ++c->state_epoch;
   *out = col;
   return LLKV_OK;
 }
@@ -788,6 +821,7 @@ static int32_t column_grow(llkv_gpu_column* col, uint64_t need_rows) {
   col->values = nv;
   col->validity = nb;
   col->cap_rows = cap;
+  ++col->ctx->state_epoch;
   return LLKV_OK;
 }
 
@@ -798,20 +832,31 @@ extern "C" int32_t llkv_gpu_column_reserve(llkv_gpu_column* col, uint64_t n_rows
   return column_grow(col, n_rows);
 }
 
-static bool is_page_locked(const void* p) {
+enum SrcKind { SRC_PAGEABLE = 0, SRC_PINNED = 1, SRC_DEVICE = 2 };
+static SrcKind source_kind(const void* p) {
   cudaPointerAttributes attr;
-  if (cudaPointerGetAttributes(&attr, p) == cudaSuccess) return attr.type == cudaMemoryTypeHost;
+  if (cudaPointerGetAttributes(&attr, p) == cudaSuccess) {
+    if (attr.type == cudaMemoryTypeHost) return SRC_PINNED;
+    if (attr.type == cudaMemoryTypeDevice || attr.type == cudaMemoryTypeManaged) return SRC_DEVICE;
+    return SRC_PAGEABLE;
+  }
   cudaGetLastError();
-  return false;
+  return SRC_PAGEABLE;
 }
 
 // host -> device through the pinned staging ring (or directly when the source is already page-locked)
-static int32_t upload(llkv_gpu_column* col, void* dst, const void* src, uint64_t bytes, bool pinned_src) {
+static int32_t upload(llkv_gpu_column* col, void* dst, const void* src, uint64_t bytes, SrcKind kind) {
   llkv_gpu_ctx* c = col->ctx;
   cudaStream_t cs = c->copy_streams[(size_t)col->stream_index];
   if (bytes == 0) return LLKV_OK;
+  if (kind == SRC_DEVICE) {  // the chunk already sits in device memory (a decoder or generator running on the GPU): one D2D copy
+    int32_t rc = flush_upload(col);
+    if (rc) return rc;
+    CUDA_TRY(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, cs));
+    return LLKV_OK;
+  }
   col->h2d_bytes += bytes;
-  if (pinned_src) {
+  if (kind == SRC_PINNED) {
     // Page-locked source: DMA straight from the caller's buffer.  Chunks that continue the previous one on both sides
     // (a column appended chunk by chunk from one contiguous buffer) are coalesced into copies of up to 32 MiB: a 1 MiB
     // copy reaches 46 GB/s on this box's PCIe link, a large one 55 GB/s (tools/pcie.py).  The copy is issued by the next
@@ -967,6 +1012,7 @@ static int32_t widen_decimal(llkv_gpu_column* col, uint64_t rows) {
   col->values = wide;
   col->elem_bytes = 16;
   col->load_kind = LK_D128;
+  ++col->ctx->state_epoch;
   return LLKV_OK;
 }
 
@@ -992,6 +1038,7 @@ static int32_t begin_narrow_landing(llkv_gpu_column* col, uint32_t width, uint64
   col->cap_rows = cap;
   col->elem_bytes = width;
   col->load_kind = width == 4 ? LK_D32 : LK_D64;
+  ++col->ctx->state_epoch;
   if (col->validity) {  // sized by the old capacity
     CUDA_TRY(cudaFree(col->validity));
     col->validity = nullptr;
@@ -1026,7 +1073,8 @@ static int32_t append_chunk_impl(llkv_gpu_column* col, const void* values, uint6
       if (row_ids[i] != first_id + i) return set_error(LLKV_ERR_INVALID_ARGUMENT, "chunk row ids are not a dense run at offset %llu", (unsigned long long)i);
   if (n_rows == 0) return LLKV_OK;
   col->sealed = false;
-  const bool pinned_src = is_page_locked(values);
+  const SrcKind src_kind = source_kind(values);
+  const bool pinned_src = src_kind == SRC_PINNED;
   if (col->load_kind == LK_STR8) {  // sealed as one byte per string: back to packed keys before more chunks arrive
     u64* wide = nullptr;
     CUDA_TRY(cudaDeviceSynchronize());
@@ -1071,6 +1119,7 @@ static int32_t append_chunk_impl(llkv_gpu_column* col, const void* values, uint6
   }
   if ((rc = column_grow(col, col->n_rows + n_rows))) return rc;
   cudaStream_t s = c->copy_streams[(size_t)col->stream_index];
+  if (col->type == LLKV_PT_UTF8 && src_kind == SRC_DEVICE) return set_error(LLKV_ERR_INVALID_ARGUMENT, "Utf8 chunks must come from host memory (the offsets are validated on the host)");
   if (col->type == LLKV_PT_UTF8) {
     // the chunk's slice of the data buffer is uploaded and the offsets are rebased on the device (a column appended in many
     // chunks from one data buffer uploads every byte once)
@@ -1084,8 +1133,8 @@ static int32_t append_chunk_impl(llkv_gpu_column* col, const void* values, uint6
     unsigned char* d_data = nullptr;
     CUDA_TRY(cudaMalloc((void**)&d_off, (n_rows + 1) * 4));
     CUDA_TRY(cudaMalloc((void**)&d_data, (size_t)(data_bytes > 0 ? data_bytes : 1)));
-    if ((rc = upload(col, d_off, off, (n_rows + 1) * 4, pinned_src))) return rc;
-    if (data_bytes > 0 && (rc = upload(col, d_data, (const char*)aux + first, (uint64_t)data_bytes, is_page_locked(aux)))) return rc;
+    if ((rc = upload(col, d_off, off, (n_rows + 1) * 4, src_kind))) return rc;
+    if (data_bytes > 0 && (rc = upload(col, d_data, (const char*)aux + first, (uint64_t)data_bytes, source_kind(aux)))) return rc;
     const unsigned int blocks = (unsigned int)std::min<uint64_t>((n_rows + 255) / 256, 1184);
     if ((rc = flush_upload(col))) return rc;
     pack_utf8_kernel<<<blocks, 256, 0, s>>>(d_off, d_data, (int)first, n_rows, (u64*)col->values + col->n_rows, col->dstats);
@@ -1098,14 +1147,14 @@ static int32_t append_chunk_impl(llkv_gpu_column* col, const void* values, uint6
     col->h2d_bytes += n_rows * col->elem_bytes;
     c->pool->submit(&col->ticket, values, (char*)col->values + col->n_rows * col->elem_bytes, n_rows, host_kind);
   } else {
-    if ((rc = upload(col, (char*)col->values + col->n_rows * col->elem_bytes, values, n_rows * col->elem_bytes, pinned_src))) return rc;
+    if ((rc = upload(col, (char*)col->values + col->n_rows * col->elem_bytes, values, n_rows * col->elem_bytes, src_kind))) return rc;
   }
   if (validity) {
     if ((rc = ensure_validity(col))) return rc;
     unsigned char* d_bits = nullptr;
     const uint64_t nb = (n_rows + 7) / 8;
     CUDA_TRY(cudaMalloc((void**)&d_bits, nb));
-    if ((rc = upload(col, d_bits, validity, nb, is_page_locked(validity)))) return rc;
+    if ((rc = upload(col, d_bits, validity, nb, source_kind(validity)))) return rc;
     const unsigned int blocks = (unsigned int)std::min<uint64_t>((n_rows / 32 + 256) / 256, 1184);
     if ((rc = flush_upload(col))) return rc;
     or_bits_kernel<<<blocks, 256, 0, s>>>(col->validity, col->n_rows, d_bits, n_rows);
@@ -1117,6 +1166,7 @@ static int32_t append_chunk_impl(llkv_gpu_column* col, const void* values, uint6
   }
   col->n_rows += n_rows;
   ++col->version;
+  ++c->state_epoch;
   col->scans_unchanged = 0;
   return LLKV_OK;
 }
@@ -1266,6 +1316,7 @@ extern "C" int32_t llkv_gpu_column_seal(llkv_gpu_column* col) {
     col->load_kind = fits32 ? LK_D32 : LK_D64;
   }
   col->sealed = true;
+  ++c->state_epoch;
   return LLKV_OK;
 }
 
@@ -1366,6 +1417,7 @@ extern "C" int32_t llkv_gpu_column_clear(llkv_gpu_column* col) {
   col->has_origin = false;
   col->sealed = false;
   ++col->version;
+  ++c->state_epoch;
   col->scans_unchanged = 0;
   return LLKV_OK;
 }
@@ -1379,6 +1431,7 @@ extern "C" int32_t llkv_gpu_column_destroy(llkv_gpu_column* col) {
   drain_jobs(col);
   cudaDeviceSynchronize();
   c->columns.erase(col->lfid);
+  ++c->state_epoch;
   for (auto& kv : c->mvcc)
     if (kv.second.created_by == col || kv.second.deleted_by == col) kv.second.created_by = kv.second.deleted_by = nullptr;
   for (void* p : col->deferred_free) cudaFree(p);
@@ -1411,6 +1464,8 @@ extern "C" int32_t llkv_gpu_program_compile(llkv_gpu_ctx* ctx, const llkv_eval_o
       return set_error(LLKV_ERR_PREDICATE_BUILD, "string pattern operators are not supported on this path");
   }
   llkv_gpu_program* p = new llkv_gpu_program();
+  static std::atomic<uint64_t> next_serial{1};
+  p->serial = next_serial.fetch_add(1);
   p->ops.assign(ops, ops + n_ops);
   p->literals.assign(literals, literals + n_literals);
   p->nodes.assign(nodes, nodes + n_nodes);
@@ -1436,6 +1491,7 @@ extern "C" int32_t llkv_gpu_mvcc_set(llkv_gpu_ctx* ctx, uint64_t table_id, llkv_
   m.txn_id = txn_id;
   m.snapshot_id = snapshot_id;
   m.noncommitted.assign(noncommitted, noncommitted + n_noncommitted);
+  ++ctx->state_epoch;
   return LLKV_OK;
 }
 
@@ -1443,6 +1499,7 @@ extern "C" int32_t llkv_gpu_mvcc_clear(llkv_gpu_ctx* ctx, uint64_t table_id) {
   if (!ctx) return set_error(LLKV_ERR_INVALID_ARGUMENT, "ctx is NULL");
   CTX_LOCK(ctx);
   ctx->mvcc.erase(table_id);
+  ++ctx->state_epoch;
   return LLKV_OK;
 }
 
@@ -2118,6 +2175,7 @@ extern "C" void llkv_gpu_agg_destroy(llkv_gpu_agg* a) {
   if (a->part_cursor) cudaFree(a->part_cursor);
   if (a->d_tile_list) cudaFree(a->d_tile_list);
   if (a->stage_ev) cudaEventDestroy(a->stage_ev);
+  if (a->graph_exec) cudaGraphExecDestroy(a->graph_exec);
   if (a->d_flags) cudaFree(a->d_flags);
   if (a->d_plan) cudaFree(a->d_plan);
   if (a->h_plan) cudaFreeHost(a->h_plan);
@@ -2128,6 +2186,7 @@ extern "C" void llkv_gpu_agg_destroy(llkv_gpu_agg* a) {
 
 static int32_t agg_alloc_table(llkv_gpu_agg* a, u64 gcap) {
   llkv_gpu_ctx* ctx = a->ctx;
+  ++a->plan_epoch;
   const u64 rows = gcap + 2;
   CUDA_TRY(cudaMalloc((void**)&a->gkeys, gcap * 8));
   CUDA_TRY(cudaMalloc((void**)&a->gwords, rows * a->n_gwords * 8));
@@ -2275,8 +2334,10 @@ static int32_t agree_key_stats(llkv_gpu_ctx* ctx, llkv_gpu_agg* a, CompileReques
     v[4 * k + 2] = ~(u64)c.max_strlen;
     v[4 * k + 3] = (c.has_minmax || c.n_rows == 0) ? 1 : 0;  // an empty shard does not veto the statistics of the others
   }
-  if (a->in_rerun && a->agreed_stats.size() == v.size()) {
-    // a rerun (wider interpreter, larger table) is this rank's own business: no collective, the agreed values again
+  if ((a->in_rerun || a->agreed_epoch == ctx->state_epoch) && a->agreed_stats.size() == v.size()) {
+    // a rerun (wider interpreter, larger table) is this rank's own business: no collective, the agreed values again.
+    // Likewise when nothing a plan depends on has changed since the ranks last agreed (ranks issue the same calls on
+    // their handles, so they all skip the collective together).
     v = a->agreed_stats;
   } else {
   if (a->mg_stats_elems < v.size()) {
@@ -2289,6 +2350,7 @@ static int32_t agree_key_stats(llkv_gpu_ctx* ctx, llkv_gpu_agg* a, CompileReques
   CUDA_TRY(cudaMemcpyAsync(v.data(), a->mg_stats, v.size() * 8, cudaMemcpyDeviceToHost, ctx->stream));
   CUDA_TRY(cudaStreamSynchronize(ctx->stream));
   a->agreed_stats = v;
+  a->agreed_epoch = ctx->state_epoch;
   }
   for (size_t k = 0; k < nk; ++k) {
     ColumnMeta& c = req.cols[(size_t)col_of[k]];
@@ -2328,6 +2390,7 @@ static int32_t agg_queue_result_copy(llkv_gpu_agg* a) {
   if (kbytes) CUDA_TRY(cudaMemcpyAsync(a->h_stage + wbytes, a->gkeys, kbytes, cudaMemcpyDeviceToHost, ctx->stream));
   if (!a->stage_ev) CUDA_TRY(cudaEventCreateWithFlags(&a->stage_ev, cudaEventDisableTiming));
   CUDA_TRY(cudaEventRecord(a->stage_ev, ctx->stream));
+  a->stage_ev_valid = true;
   a->prefetched = true;
   return LLKV_OK;
 }
@@ -2692,11 +2755,23 @@ static int32_t agg_fail(llkv_gpu_agg* a, int32_t code, const char* fmt, ...) {
   return set_error(code, "%s", buf);
 }
 
+// llkv_gpu_agg_reset only marks the state; the status word and the table are cleared here, in stream order, right before
+// whatever uses them next (so a reset and the scan that follows it are one run of launches — and one captured graph)
+static int32_t agg_apply_reset(llkv_gpu_agg* a) {
+  if (!a->reset_pending) return LLKV_OK;
+  llkv_gpu_ctx* ctx = a->ctx;
+  a->reset_pending = false;
+  CUDA_TRY(cudaMemsetAsync(a->d_flags, 0, 4, ctx->stream));
+  if (a->frozen) CUDA_TRY(launch_init_table(a->gkeys, a->gwords, a->gcap + 2, a->n_gwords, a->d_gclass, ctx->stream));
+  return LLKV_OK;
+}
+
 // waits for the outstanding run and settles it: reruns on the 128-bit interpreter / a larger group table when the
 // device asked for it, and turns device error flags into the reference's errors
+static int32_t agg_merge_impl(llkv_gpu_agg* a);
 static int32_t agg_resolve(llkv_gpu_agg* a) {
   llkv_gpu_ctx* ctx = a->ctx;
-  if (!a->pending.active) return LLKV_OK;
+  if (!a->pending.active) return agg_apply_reset(a);
   for (int guard = 0; guard < 24; ++guard) {
     CUDA_TRY(cudaStreamSynchronize(ctx->stream));
     if (a->pending.timed) {
@@ -2711,6 +2786,44 @@ static int32_t agg_resolve(llkv_gpu_agg* a) {
     *a->h_flags = 0;
     const bool narrow_fail = (flags & FLAG_NARROW_FAIL) && !a->pending.wide;
     const bool table_full = (flags & FLAG_TABLE_FULL) != 0;
+    const bool merge_retry = a->pending.is_merge && (flags & FLAG_MERGE_RETRY);
+    auto merge_again = [&](bool exchange) -> int32_t {  // (a retry is a new exchange on every rank: they all saw the flag)
+      CUDA_TRY(launch_merge_grouped_p2p(a->gkeys, a->gwords, a->gcap, a->n_gwords, a->d_gclass, a->d_flags, ctx->peer_gbox, kGroupSlotWords, ctx->n_ranks,
+                                        ctx->rank, ctx->d_epoch, exchange, ctx->stream));
+      return agg_queue_result_copy(a);
+    };
+    if (a->pending.is_merge && !merge_retry && table_full && !(flags & ~(uint32_t)FLAG_TABLE_FULL)) {
+      // the union of the ranks' groups outgrew this rank's table while folding: a larger, empty table, and fold again
+      // (the received tables are still in the mailbox)
+      const u64 cap = a->gcap;
+      CUDA_TRY(cudaFree(a->gkeys));
+      CUDA_TRY(cudaFree(a->gwords));
+      a->gkeys = a->gwords = nullptr;
+      int32_t rc = agg_alloc_table(a, cap * 4);
+      if (!rc) rc = merge_again(false);
+      if (rc) {
+        a->pending.active = false;
+        return rc;
+      }
+      continue;
+    }
+    if (a->pending.is_merge && flags == FLAG_MERGE_OVERSIZE) {
+      // some rank's table does not fit a mailbox slot (a cardinality hint far below the truth): every rank saw the marker
+      // and kept its table, and they all merge over NCCL instead, now and from here on
+      a->p2p_group_disabled = true;
+      a->pending.is_merge = false;
+      a->pending.active = false;
+      ++a->plan_epoch;
+      return agg_merge_impl(a);
+    }
+    if (merge_retry && !(narrow_fail || table_full)) {  // another rank repeats its scan: this rank's table is untouched
+      int32_t rc = merge_again(true);
+      if (rc) {
+        a->pending.active = false;
+        return rc;
+      }
+      continue;
+    }
     if (narrow_fail || table_full) {
       if (!a->pending.has_backup) return agg_fail(a, LLKV_ERR_INTERNAL, "device asked for a rerun without a saved state");
       int32_t rc = agg_restore(a);
@@ -2721,6 +2834,7 @@ static int32_t agg_resolve(llkv_gpu_agg* a) {
       rc = agg_launch(a, a->pending.has_prog ? &a->pending.prog : nullptr, a->pending.apply_mvcc, a->pending.row_begin,
                       a->pending.row_end, a->pending.wide);
       a->in_rerun = false;
+      if (!rc && merge_retry) rc = merge_again(true);
       if (rc) {
         a->pending.active = false;
         return rc;
@@ -2738,6 +2852,8 @@ static int32_t agg_resolve(llkv_gpu_agg* a) {
     if (flags & FLAG_DIV_ZERO) return agg_fail(a, LLKV_ERR_INTERNAL, "Divide by zero error");
     if (flags & FLAG_ARITH_OVERFLOW) return agg_fail(a, LLKV_ERR_INTERNAL, "Arithmetic overflow: Overflow happened in an arrow-arith kernel");
     if (flags & FLAG_EXACT_OVERFLOW) return agg_fail(a, LLKV_ERR_INVALID_ARGUMENT, "Decimal or integer overflow in an exact aggregate expression");
+    if (flags & FLAG_MERGE_OVERSIZE) return agg_fail(a, LLKV_ERR_INVALID_ARGUMENT, "multi-GPU merge: a rank's group table outgrew the peer mailbox (the cardinality hint is far too low)");
+    if (flags & FLAG_MERGE_PEER_FAILED) return agg_fail(a, LLKV_ERR_INTERNAL, "multi-GPU merge: the scan of another rank failed");
     return agg_fail(a, LLKV_ERR_INTERNAL, "unexpected device status %u", flags);
   }
   a->pending.active = false;
@@ -2757,8 +2873,32 @@ extern "C" int32_t llkv_gpu_agg_reset(llkv_gpu_agg* a) {
   a->err_msg.clear();
   a->prefetched = false;
   *a->h_flags = 0;
-  CUDA_TRY(cudaMemsetAsync(a->d_flags, 0, 4, ctx->stream));
-  if (a->frozen) CUDA_TRY(launch_init_table(a->gkeys, a->gwords, a->gcap + 2, a->n_gwords, a->d_gclass, ctx->stream));
+  a->reset_pending = true;
+  return LLKV_OK;
+}
+
+static int32_t agg_run_impl(llkv_gpu_agg* a, const llkv_gpu_program* prog, int32_t apply_mvcc, uint64_t row_begin, uint64_t row_end) {
+  if (a->err_code) return set_error(a->err_code, "%s", a->err_msg.c_str());
+  int32_t rc = agg_resolve(a);
+  if (rc) return rc;
+  a->pending.has_prog = prog != nullptr;
+  if (prog && a->pending.prog.serial != prog->serial) {
+    a->pending.prog.ops = prog->ops;
+    a->pending.prog.literals = prog->literals;
+    a->pending.prog.nodes = prog->nodes;
+    a->pending.prog.list_roots = prog->list_roots;
+    a->pending.prog.serial = prog->serial;
+    a->pending.prog.bind();
+  }
+  a->pending.apply_mvcc = apply_mvcc;
+  a->pending.row_begin = row_begin;
+  a->pending.row_end = row_end;
+  a->pending.wide = false;
+  a->pending.is_merge = false;
+  rc = agg_launch(a, prog, apply_mvcc, row_begin, row_end, false);
+  if (rc) return rc;
+  a->pending.wide = a->cr.wide;
+  a->pending.active = true;
   return LLKV_OK;
 }
 
@@ -2768,26 +2908,7 @@ extern "C" int32_t llkv_gpu_agg_run(llkv_gpu_agg* a, const llkv_gpu_program* pro
   if (row_end < row_begin) return set_error(LLKV_ERR_INVALID_ARGUMENT, "row_end < row_begin");
   CTX_LOCK(a->ctx);
   CUDA_TRY(cudaSetDevice(a->ctx->device));
-  if (a->err_code) return set_error(a->err_code, "%s", a->err_msg.c_str());
-  int32_t rc = agg_resolve(a);
-  if (rc) return rc;
-  a->pending.has_prog = prog != nullptr;
-  if (prog) {
-    a->pending.prog.ops = prog->ops;
-    a->pending.prog.literals = prog->literals;
-    a->pending.prog.nodes = prog->nodes;
-    a->pending.prog.list_roots = prog->list_roots;
-    a->pending.prog.bind();
-  }
-  a->pending.apply_mvcc = apply_mvcc;
-  a->pending.row_begin = row_begin;
-  a->pending.row_end = row_end;
-  a->pending.wide = false;
-  rc = agg_launch(a, prog, apply_mvcc, row_begin, row_end, false);
-  if (rc) return rc;
-  a->pending.wide = a->cr.wide;
-  a->pending.active = true;
-  return LLKV_OK;
+  return agg_run_impl(a, prog, apply_mvcc, row_begin, row_end);
 }
 
 extern "C" int32_t llkv_gpu_agg_run_info(const llkv_gpu_agg* a, llkv_run_info* out) {
@@ -2988,7 +3109,8 @@ static int32_t agg_collect(llkv_gpu_agg* a, std::vector<u64>& hk, std::vector<u6
   if (a->prefetched && a->h_stage_bytes >= wbytes + kbytes) {  // already on its way (agg_queue_result_copy)
     // usually complete: agg_resolve waited for the run.  Not when the copy was queued with no run pending (a merge behind
     // a run that had to be settled first).
-    CUDA_TRY(cudaEventSynchronize(a->stage_ev));
+    if (a->stage_ev_valid) CUDA_TRY(cudaEventSynchronize(a->stage_ev));
+    else CUDA_TRY(cudaStreamSynchronize(ctx->stream));  // (replayed from a graph: the event belongs to the capture)
     memcpy(hw.data(), a->h_stage, wbytes);
     if (kbytes) memcpy(hk.data(), a->h_stage + wbytes, kbytes);
   } else if (wbytes + kbytes <= (4u << 20)) {  // small tables land in a page-locked buffer (one DMA each, no pageable staging)
@@ -3023,6 +3145,7 @@ static int32_t agg_collect(llkv_gpu_agg* a, std::vector<u64>& hk, std::vector<u6
   if (a->hint && a->hint <= 128 && groups.size() > a->hint && groups.size() > a->observed_groups) {
     a->observed_groups = groups.size();  // the caller's hint was low: later runs of this aggregate get more CTA-local slots
     a->lean_have[0] = a->lean_have[1] = a->lean_have[2] = false;
+    ++a->plan_epoch;
   }
   return LLKV_OK;
 }
@@ -3099,10 +3222,11 @@ static void comm_setup_p2p(llkv_gpu_ctx* ctx) {
   const char* off = getenv("LLKV_GPU_NO_P2P_MERGE");
   if (N < 2 || N > 8 || (off && off[0] && off[0] != '0')) return;
   const int nccl_u8 = 1 /* ncclUint8 */, nccl_u64 = 5 /* ncclUint64 */, nccl_min = 3 /* ncclMin */;
-  const size_t box_bytes = (size_t)N * 2 * 128 * 8;
+  const size_t box_bytes = (size_t)N * 2 * (kUngroupedSlotWords + kGroupSlotWords) * 8;
   u64 ok = 1;
   cudaIpcMemHandle_t mine;
   memset(&mine, 0, sizeof(mine));
+  if (cudaMalloc((void**)&ctx->d_epoch, 8) != cudaSuccess || cudaMemset(ctx->d_epoch, 0, 8) != cudaSuccess) ok = 0;
   if (cudaMalloc((void**)&ctx->mbox, box_bytes) != cudaSuccess || cudaMemset(ctx->mbox, 0, box_bytes) != cudaSuccess ||
       cudaIpcGetMemHandle(&mine, ctx->mbox) != cudaSuccess)
     ok = 0;
@@ -3146,8 +3270,10 @@ static void comm_setup_p2p(llkv_gpu_ctx* ctx) {
   cudaFree(d_handles);
   cudaFree(d_ok);
   cudaGetLastError();
-  if (all_ok) ctx->p2p_merge = true;
-  else comm_teardown_p2p(ctx);
+  if (all_ok) {
+    ctx->p2p_merge = true;
+    for (int r = 0; r < N; ++r) ctx->peer_gbox[r] = ctx->peer_mbox[r] + (size_t)N * 2 * kUngroupedSlotWords;
+  } else comm_teardown_p2p(ctx);
   if (getenv("LLKV_GPU_VERBOSE"))
     fprintf(stderr, "[llkv] rank %d/%d: ungrouped merge over %s\n", ctx->rank, N, ctx->p2p_merge ? "NVLink peer mailboxes (CUDA IPC)" : "NCCL all-gather");
 }
@@ -3168,6 +3294,7 @@ extern "C" int32_t llkv_gpu_comm_init(llkv_gpu_ctx* ctx, const uint8_t id[LLKV_G
   NCCL_TRY(g_nccl.comm_init_rank(&ctx->nccl_comm, n_ranks, v, rank));
   ctx->n_ranks = n_ranks;
   ctx->rank = rank;
+  ++ctx->state_epoch;
   comm_setup_p2p(ctx);
   return LLKV_OK;
 }
@@ -3176,11 +3303,13 @@ static void comm_teardown_p2p(llkv_gpu_ctx* ctx) {
   for (int r = 0; r < 8; ++r) {
     if (ctx->peer_mbox[r] && r != ctx->rank) cudaIpcCloseMemHandle(ctx->peer_mbox[r]);
     ctx->peer_mbox[r] = nullptr;
+    ctx->peer_gbox[r] = nullptr;
   }
   if (ctx->mbox) cudaFree(ctx->mbox);
   ctx->mbox = nullptr;
   ctx->p2p_merge = false;
-  ctx->merge_epoch = 0;
+  if (ctx->d_epoch) cudaFree(ctx->d_epoch);
+  ctx->d_epoch = nullptr;
   cudaGetLastError();
 }
 
@@ -3196,18 +3325,27 @@ extern "C" int32_t llkv_gpu_comm_destroy(llkv_gpu_ctx* ctx) {
   ctx->nccl_comm = nullptr;
   ctx->n_ranks = 1;
   ctx->rank = 0;
+  ++ctx->state_epoch;
   return LLKV_OK;
 }
 
 // Every rank gathers every rank's partial table (allgather over NVLink) and folds them in rank order into a fresh
 // table, so all ranks end with bit-identical states (f64 sums included).
-extern "C" int32_t llkv_gpu_agg_merge(llkv_gpu_agg* a) {
-  if (!a) return set_error(LLKV_ERR_INVALID_ARGUMENT, "agg is NULL");
+// true when llkv_gpu_agg_merge of this aggregate is one kernel over the peer mailboxes (no collective, no host wait)
+static bool merge_is_p2p(const llkv_gpu_agg* a) {
+  const llkv_gpu_ctx* ctx = a->ctx;
+  if (!a->frozen || !ctx->nccl_comm || ctx->n_ranks < 2 || !ctx->p2p_merge) return false;
+  if (a->cr.plan.n_keys == 0) return !a->cr.can_narrow_fail && a->n_gwords < 127;
+  if (!a->hint || a->p2p_group_disabled) return false;
+  const u64 cap0 = next_pow2(std::max<u64>(32, a->hint * 2)) * 4;
+  return 2 + cap0 + (cap0 + 2) * a->n_gwords <= kGroupSlotWords;
+}
+
+static int32_t agg_merge_impl(llkv_gpu_agg* a) {
   llkv_gpu_ctx* ctx = a->ctx;
-  CTX_LOCK(ctx);
-  CUDA_TRY(cudaSetDevice(ctx->device));
   if (a->err_code) return set_error(a->err_code, "%s", a->err_msg.c_str());
   int32_t rc;
+  if (!a->pending.active && (rc = agg_apply_reset(a))) return rc;
   a->prefetched = false;  // the merge rewrites the table
   const int N = ctx->n_ranks;
   const int nccl_u64 = 5 /* ncclUint64 */, nccl_max = 2 /* ncclMax */;
@@ -3223,8 +3361,9 @@ extern "C" int32_t llkv_gpu_agg_merge(llkv_gpu_agg* a) {
       a->pending.timed = false;
       a->pending.has_backup = false;
     }
+    a->info.merged_p2p = ctx->p2p_merge && a->n_gwords < 127 ? 1 : 0;
     if (ctx->p2p_merge && a->n_gwords < 127) {  // NVLink peer stores + flags, no collective library on the path
-      CUDA_TRY(launch_merge_ungrouped_p2p(a->gwords, ctx->peer_mbox, N, ctx->rank, a->n_gwords, ++ctx->merge_epoch, a->d_gclass, a->d_flags,
+      CUDA_TRY(launch_merge_ungrouped_p2p(a->gwords, ctx->peer_mbox, N, ctx->rank, a->n_gwords, ctx->d_epoch, a->d_gclass, a->d_flags,
                                           ctx->stream));
       return agg_queue_result_copy(a);  // (also the status word again: the merge kernel reports a peer that never arrives)
     }
@@ -3238,10 +3377,29 @@ extern "C" int32_t llkv_gpu_agg_merge(llkv_gpu_agg* a) {
     CUDA_TRY(launch_merge_ungrouped(a->gwords, a->mg_words, N, a->n_gwords, word_elems, a->d_gclass, ctx->stream));
     return agg_queue_result_copy(a);
   }
+  // Small group tables (a cardinality hint that keeps the table within a mailbox slot even after growing x4): the same
+  // peer-mailbox exchange, one kernel queued behind the scan, no collective, no host synchronisation.  The condition only
+  // uses the hint and the accumulator layout, which every rank shares.
+  if (a->frozen && a->cr.plan.n_keys != 0 && ctx->nccl_comm && N > 1 && ctx->p2p_merge && a->hint && !a->p2p_group_disabled) {
+    const u64 cap0 = next_pow2(std::max<u64>(32, a->hint * 2)) * 4;
+    if (2 + cap0 + (cap0 + 2) * a->n_gwords <= kGroupSlotWords) {
+      if (!a->pending.active) {
+        a->pending.active = true;
+        a->pending.timed = false;
+        a->pending.has_backup = false;
+      }
+      a->pending.is_merge = true;
+      a->info.merged_p2p = 1;
+      CUDA_TRY(launch_merge_grouped_p2p(a->gkeys, a->gwords, a->gcap, a->n_gwords, a->d_gclass, a->d_flags, ctx->peer_gbox, kGroupSlotWords, N, ctx->rank,
+                                        ctx->d_epoch, true, ctx->stream));
+      return agg_queue_result_copy(a);
+    }
+  }
   rc = agg_resolve(a);
   if (rc) return rc;
   if ((rc = agg_ensure_layout(a))) return rc;
   if (!ctx->nccl_comm || ctx->n_ranks == 1) return LLKV_OK;
+  a->info.merged_p2p = 0;
   const bool grouped = a->cr.plan.n_keys != 0;
   if (grouped) {
     // all ranks must use one table size: agree on the largest
@@ -3300,5 +3458,125 @@ extern "C" int32_t llkv_gpu_agg_merge(llkv_gpu_agg* a) {
   }
   if ((rc = agg_queue_result_copy(a))) return rc;
   CUDA_TRY(cudaStreamSynchronize(ctx->stream));  // (no run is pending here: nothing else would wait for the copy)
+  return LLKV_OK;
+}
+
+extern "C" int32_t llkv_gpu_agg_merge(llkv_gpu_agg* a) {
+  if (!a) return set_error(LLKV_ERR_INVALID_ARGUMENT, "agg is NULL");
+  CTX_LOCK(a->ctx);
+  CUDA_TRY(cudaSetDevice(a->ctx->device));
+  return agg_merge_impl(a);
+}
+
+// One step of a prepared aggregate: fresh accumulators -> fused scan of rows [row_begin, row_end) -> (merge != 0 and the
+// context has peers) merge of the ranks' partial states -> result on its way to page-locked memory.  The same launches as
+// reset + run + merge; once a step repeats with nothing changed (same columns, program, snapshot, row range, knobs; the
+// previous steps came back clean) it is captured as a CUDA graph and replayed with a single launch call.
+extern "C" int32_t llkv_gpu_agg_execute(llkv_gpu_agg* a, const llkv_gpu_program* prog, int32_t apply_mvcc, uint64_t row_begin, uint64_t row_end,
+                                         int32_t merge) {
+  if (!a) return set_error(LLKV_ERR_INVALID_ARGUMENT, "agg is NULL");
+  if (row_end < row_begin) return set_error(LLKV_ERR_INVALID_ARGUMENT, "row_end < row_begin");
+  llkv_gpu_ctx* ctx = a->ctx;
+  CTX_LOCK(ctx);
+  CUDA_TRY(cudaSetDevice(ctx->device));
+  // reset: an unfinished step is dropped, its errors with it
+  bool prev_clean = a->err_code == 0;
+  if (a->pending.active) {
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    a->pending.active = false;
+    prev_clean = false;  // never settled: whether it came back clean is unknown
+  }
+  a->err_code = 0;
+  a->err_msg.clear();
+  a->prefetched = false;
+  *a->h_flags = 0;
+  a->reset_pending = true;
+  const bool do_merge = merge != 0 && ctx->nccl_comm && ctx->n_ranks > 1;
+  uint64_t key = 0xcbf29ce484222325ull;
+  {
+    const uint64_t parts[8] = {ctx->state_epoch, a->plan_epoch, prog ? prog->serial : 0, (uint64_t)apply_mvcc, row_begin, row_end, (uint64_t)do_merge,
+                               (uint64_t)ctx->timing};
+    key = fnv1a(key, parts, sizeof(parts));
+    if (!key) key = 1;
+  }
+  if (a->graph_exec && a->graph_key == key && prev_clean) {
+    const PendingRun& gp = a->graph_pending;  // (the program copy of the captured step is still in a->pending.prog)
+    a->pending.has_prog = gp.has_prog;
+    a->pending.apply_mvcc = gp.apply_mvcc;
+    a->pending.row_begin = gp.row_begin;
+    a->pending.row_end = gp.row_end;
+    a->pending.wide = gp.wide;
+    a->pending.has_backup = gp.has_backup;
+    a->pending.timed = gp.timed;
+    a->pending.is_merge = gp.is_merge;
+    a->reset_pending = false;  // part of the graph
+    CUDA_TRY(cudaGraphLaunch(a->graph_exec, ctx->stream));
+    ++a->info.graph_replays;
+    a->prefetched = a->graph_prefetched;
+    a->stage_ev_valid = false;
+    a->pending.active = true;
+    a->info.kernel_launches = a->graph_launches;
+    return LLKV_OK;
+  }
+  if (a->exec_key == key && prev_clean) ++a->exec_same;
+  else a->exec_same = 0;
+  a->exec_key = key;
+  // capture on the third unchanged step: by then the plan is compiled and specialised, statistics, zone maps and tile
+  // lists are settled and every buffer is allocated, so the step is launches and asynchronous copies only
+  const bool capture = ctx->graph_mode && a->exec_same >= 2 && a->capture_failures < 2 && a->frozen && a->cr.fast && (!do_merge || merge_is_p2p(a));
+  if (capture) {
+    if (a->graph_exec) {
+      cudaGraphExecDestroy(a->graph_exec);
+      a->graph_exec = nullptr;
+      a->graph_key = 0;
+    }
+    a->in_capture = true;
+    cudaError_t e = cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal);
+    int32_t rc = LLKV_OK;
+    if (e == cudaSuccess) {
+      rc = agg_run_impl(a, prog, apply_mvcc, row_begin, row_end);
+      if (!rc && do_merge) rc = agg_merge_impl(a);
+      cudaGraph_t graph = nullptr;
+      e = cudaStreamEndCapture(ctx->stream, &graph);
+      if (e == cudaSuccess && !rc && graph) {
+        e = cudaGraphInstantiate(&a->graph_exec, graph, 0);
+        if (e == cudaSuccess) e = cudaGraphLaunch(a->graph_exec, ctx->stream);  // (capturing executed nothing)
+      } else if (e == cudaSuccess && rc) {
+        e = cudaErrorUnknown;
+      }
+      if (graph) cudaGraphDestroy(graph);
+    }
+    a->in_capture = false;
+    if (e == cudaSuccess && !rc) {
+      a->graph_key = key;
+      a->graph_pending = a->pending;
+      a->graph_pending.prog = llkv_gpu_program();
+      a->graph_prefetched = a->prefetched;
+      a->graph_launches = a->info.kernel_launches;
+      a->stage_ev_valid = false;
+      return LLKV_OK;
+    }
+    // the step is not capturable as it is (something in it waits for the device): run it the plain way, from scratch
+    cudaGetLastError();
+    if (a->graph_exec) cudaGraphExecDestroy(a->graph_exec);
+    a->graph_exec = nullptr;
+    a->graph_key = 0;
+    ++a->capture_failures;
+    a->pending.active = false;
+    a->prefetched = false;
+    a->reset_pending = true;
+    cudaStreamSynchronize(ctx->stream);
+    cudaGetLastError();
+  }
+  int32_t rc = agg_run_impl(a, prog, apply_mvcc, row_begin, row_end);
+  if (!rc && do_merge) rc = agg_merge_impl(a);
+  return rc;
+}
+
+extern "C" int32_t llkv_gpu_ctx_set_graphs(llkv_gpu_ctx* c, int32_t mode) {
+  if (!c) return set_error(LLKV_ERR_INVALID_ARGUMENT, "ctx is NULL");
+  if (mode < 0 || mode > 1) return set_error(LLKV_ERR_INVALID_ARGUMENT, "graph mode must be 0 or 1");
+  CTX_LOCK(c);
+  c->graph_mode = mode;
   return LLKV_OK;
 }

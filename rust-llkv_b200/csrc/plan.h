@@ -331,7 +331,10 @@ enum : uint32_t {
   FLAG_TABLE_FULL = 1u << 4,       // global group table is full
   FLAG_BAD_PLAN = 1u << 5,
   FLAG_TYPE_ERROR = 1u << 6,       // OP_RAISE: aggregate argument of a type the accumulator rejects, met on a selected row
-  FLAG_MERGE_TIMEOUT = 1u << 7     // multi-GPU merge: a peer's partial state never arrived
+  FLAG_MERGE_TIMEOUT = 1u << 7,    // multi-GPU merge: a peer's partial state never arrived
+  FLAG_MERGE_OVERSIZE = 1u << 8,   // multi-GPU merge over peer mailboxes: some rank's group table outgrew a mailbox slot
+  FLAG_MERGE_RETRY = 1u << 9,      // ... some rank's scan has to be repeated first (64-bit overflow, table full): every rank merges again
+  FLAG_MERGE_PEER_FAILED = 1u << 10 // ... some rank's scan ended with an error: no merged result on any rank
 };
 
 }  // namespace llkv

@@ -1008,9 +1008,14 @@ __device__ __forceinline__ u64 global_timer_ns() {
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
   return t;
 }
-__global__ void merge_ungrouped_p2p_kernel(u64* state, PeerMailboxes peers, int n_ranks, int rank, uint32_t n_gwords, u64 epoch,
+// The merge number (`epoch`) lives in device memory and advances with every exchange, in step on all ranks: the launch
+// has no per-merge parameter, so a captured CUDA graph replays it.
+__global__ void merge_ungrouped_p2p_kernel(u64* state, PeerMailboxes peers, int n_ranks, int rank, uint32_t n_gwords, u64* epoch_dev,
                                            const uint8_t* word_class_dev, uint32_t* flags) {
   const uint32_t w = threadIdx.x;
+  const u64 epoch = *epoch_dev + 1;
+  __syncthreads();  // every thread has read the counter
+  if (w == 0) *epoch_dev = epoch;
   const uint32_t slot = (uint32_t)(rank * 2 + (int)(epoch & 1)) * kMergeMboxWords;
   if (w < n_gwords) {
     const u64 v = state[w];
@@ -1072,12 +1077,171 @@ __global__ void merge_ungrouped_p2p_kernel(u64* state, PeerMailboxes peers, int 
   state[w] = c == WC_FSUM ? (u64)__double_as_longlong(facc) : acc;
 }
 
+// Grouped multi-GPU merge over NVLink peer memory for small group tables (TPC-H Q1: 34 rows): the same mailbox protocol as
+// the ungrouped merge, the message being the rank's whole table [flag = epoch | capacity | keys | words].  One CTA per rank:
+//   1. store the own table into the (rank, parity) slot of every peer, fence, publish with a release flag;
+//   2. wait for every rank's flag in the own mailbox;
+//   3. re-initialise the own table and fold the N received tables into it in rank order — rows of one source table have
+//      distinct keys, so they fold in parallel without atomics on the words, and the fixed rank order makes every rank end
+//      with the bit-identical table (f64 sums included).
+// No collective library, no host synchronisation, one launch.  `exchange` = 0 repeats step 3 only (the host grew the
+// table after FLAG_TABLE_FULL: the received tables are still in the mailbox).  The capacity word doubles as the sender's
+// status: a table that does not fit a slot (every rank reports FLAG_MERGE_OVERSIZE), a scan that has to be repeated on the
+// sender first (64-bit overflow, table full: every rank leaves its table alone and reports FLAG_MERGE_RETRY, the host
+// settles the scan and all ranks merge again), a scan that failed (FLAG_MERGE_PEER_FAILED everywhere).
+constexpr u64 kMsgOversize = ~0ull, kMsgRerun = ~0ull - 1, kMsgFailed = ~0ull - 2;
+struct GroupMergeArgs {
+  u64* gkeys;
+  u64* gwords;
+  u64 gcap;
+  const uint8_t* wclass;
+  uint32_t* flags;
+  PeerMailboxes peers;
+  u64* epoch_dev;  // merges so far (device memory, shared with the ungrouped merge); an exchange advances it
+  uint32_t n_gwords, slot_words;
+  int n_ranks, rank, exchange;
+};
+__global__ void __launch_bounds__(512) merge_grouped_p2p_kernel(GroupMergeArgs a) {
+  const uint32_t tid = threadIdx.x, NT = blockDim.x;
+  const u64 epoch = *a.epoch_dev + (a.exchange ? 1 : 0);
+  __syncthreads();  // every thread has read the counter
+  if (tid == 0 && a.exchange) *a.epoch_dev = epoch;
+  const uint32_t par = (uint32_t)(epoch & 1);
+  const u64 rows = a.gcap + 2;
+  const u64 n_key_words = a.gcap, n_words = rows * a.n_gwords;
+  __shared__ int s_status;
+  if (tid == 0) s_status = 0;
+  if (a.exchange) {
+    const uint32_t local = *a.flags;  // what the scan queued in front of this kernel left behind
+    u64 head = a.gcap;
+    if (local & ~(FLAG_NARROW_FAIL | FLAG_TABLE_FULL)) head = kMsgFailed;
+    else if (local) head = kMsgRerun;
+    else if (2 + n_key_words + n_words > a.slot_words) head = kMsgOversize;
+    const bool fits = head == a.gcap;
+    for (int r = 0; r < a.n_ranks; ++r) {
+      u64* dst = a.peers.box[r] + (size_t)(a.rank * 2 + par) * a.slot_words;
+      if (tid == 0) dst[1] = head;
+      if (fits) {
+        for (u64 i = tid; i < n_key_words; i += NT) dst[2 + i] = a.gkeys[i];
+        for (u64 i = tid; i < n_words; i += NT) dst[2 + n_key_words + i] = a.gwords[i];
+      }
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (tid < (uint32_t)a.n_ranks) st_release_sys(a.peers.box[tid] + (size_t)(a.rank * 2 + par) * a.slot_words, epoch);
+    if (tid < (uint32_t)a.n_ranks) {
+      const u64* flag = a.peers.box[a.rank] + (size_t)(tid * 2 + par) * a.slot_words;
+      const u64 t0 = global_timer_ns();
+      while (ld_acquire_sys(flag) != epoch) {
+        if (global_timer_ns() - t0 > 10000000000ull) {
+          atomicOr(&s_status, 1);
+          break;
+        }
+        __nanosleep(200);
+      }
+    }
+    __syncthreads();
+    __threadfence_system();
+  } else {
+    __syncthreads();
+  }
+  const u64* mine = a.peers.box[a.rank];
+  if (!s_status && tid < (uint32_t)a.n_ranks) {
+    const u64 head = mine[(size_t)(tid * 2 + par) * a.slot_words + 1];
+    if (head == kMsgOversize) atomicOr(&s_status, 2);
+    else if (head == kMsgRerun) atomicOr(&s_status, 4);
+    else if (head == kMsgFailed) atomicOr(&s_status, 8);
+  }
+  __syncthreads();
+  if (s_status) {  // the own table stays as the scan left it
+    if (tid == 0)
+      atomicOr(a.flags, (s_status & 1) ? FLAG_MERGE_TIMEOUT : (s_status & 8) ? FLAG_MERGE_PEER_FAILED : (s_status & 4) ? FLAG_MERGE_RETRY : FLAG_MERGE_OVERSIZE);
+    return;
+  }
+  // fresh table
+  for (u64 i = tid; i < n_key_words; i += NT) a.gkeys[i] = kEmptyKey;
+  for (u64 i = tid; i < n_words; i += NT) {
+    const uint8_t c = a.wclass[i % a.n_gwords];
+    a.gwords[i] = (c == WC_MIN || c == WC_MIN128 || c == WC_PAIR_LO_MIN) ? ~0ull : 0ull;
+  }
+  __syncthreads();
+  const u64 mask = a.gcap - 1;
+  uint32_t err = 0;
+  for (int r = 0; r < a.n_ranks; ++r) {
+    const u64* src = mine + (size_t)(r * 2 + par) * a.slot_words;
+    const u64 scap = src[1];
+    const u64* skeys = src + 2;
+    const u64* swords = src + 2 + scap;
+    for (u64 i = tid; i < scap + 2; i += NT) {
+      const u64* sw = swords + i * a.n_gwords;
+      u64 K = kEmptyKey, slot;
+      if (i < scap) {
+        K = skeys[i];
+        if (K == kEmptyKey) continue;
+        slot = ~0ull;
+        u64 h = mix64(K) & mask;
+        for (u64 t = 0; t <= mask; ++t) {
+          const u64 cur = a.gkeys[h];
+          if (cur == K) { slot = h; break; }
+          if (cur == kEmptyKey) {
+            const u64 old = atomicCAS(&a.gkeys[h], kEmptyKey, K);
+            if (old == kEmptyKey || old == K) { slot = h; break; }
+          }
+          h = (h + 1) & mask;
+        }
+        if (slot == ~0ull) { err |= FLAG_TABLE_FULL; continue; }
+      } else {
+        if (sw[0] == 0) continue;  // word 0 = rows folded into the group: the spare rows (reserved key value, NULL key) are empty
+        slot = a.gcap + (i - scap);
+      }
+      u64* d = a.gwords + slot * a.n_gwords;
+      for (uint32_t w = 0; w < a.n_gwords; ++w) {
+        const u64 v = sw[w];
+        switch (a.wclass[w]) {
+          case WC_SUM: d[w] += v; break;
+          case WC_FSUM: d[w] = (u64)__double_as_longlong(__longlong_as_double((i64)d[w]) + __longlong_as_double((i64)v)); break;
+          case WC_MIN: d[w] = v < d[w] ? v : d[w]; break;
+          case WC_MAX: d[w] = v > d[w] ? v : d[w]; break;
+          case WC_MIN128: case WC_MAX128: {
+            const bool is_max = a.wclass[w] == WC_MAX128;
+            const u64 h = v, l = sw[w + 1], ch = d[w], cl = d[w + 1];
+            const bool better = is_max ? (h > ch || (h == ch && l > cl)) : (h < ch || (h == ch && l < cl));
+            if (better) { d[w] = h; d[w + 1] = l; }
+            break;
+          }
+          default: break;  // low half of a pair: written with its high word
+        }
+      }
+    }
+    __syncthreads();  // the next rank's rows may meet the same groups
+  }
+  if (err) atomicOr(a.flags, err);
+}
+
 // ------------------------------------------------------------------ host-callable launchers
-cudaError_t launch_merge_ungrouped_p2p(u64* state, u64* const* peer_boxes, int n_ranks, int rank, uint32_t n_gwords, u64 epoch,
+cudaError_t launch_merge_ungrouped_p2p(u64* state, u64* const* peer_boxes, int n_ranks, int rank, uint32_t n_gwords, u64* epoch_dev,
                                        const uint8_t* word_class_dev, uint32_t* flags, cudaStream_t stream) {
   PeerMailboxes pm;
   for (int r = 0; r < 8; ++r) pm.box[r] = r < n_ranks ? peer_boxes[r] : nullptr;
-  merge_ungrouped_p2p_kernel<<<1, kMergeMboxWords, 0, stream>>>(state, pm, n_ranks, rank, n_gwords, epoch, word_class_dev, flags);
+  merge_ungrouped_p2p_kernel<<<1, kMergeMboxWords, 0, stream>>>(state, pm, n_ranks, rank, n_gwords, epoch_dev, word_class_dev, flags);
+  return cudaGetLastError();
+}
+cudaError_t launch_merge_grouped_p2p(u64* gkeys, u64* gwords, u64 gcap, uint32_t n_gwords, const uint8_t* word_class_dev, uint32_t* flags,
+                                     u64* const* peer_boxes, uint32_t slot_words, int n_ranks, int rank, u64* epoch_dev, bool exchange, cudaStream_t stream) {
+  GroupMergeArgs a;
+  a.gkeys = gkeys;
+  a.gwords = gwords;
+  a.gcap = gcap;
+  a.wclass = word_class_dev;
+  a.flags = flags;
+  for (int r = 0; r < 8; ++r) a.peers.box[r] = r < n_ranks ? peer_boxes[r] : nullptr;
+  a.epoch_dev = epoch_dev;
+  a.n_gwords = n_gwords;
+  a.slot_words = slot_words;
+  a.n_ranks = n_ranks;
+  a.rank = rank;
+  a.exchange = exchange ? 1 : 0;
+  merge_grouped_p2p_kernel<<<1, 512, 0, stream>>>(a);
   return cudaGetLastError();
 }
 cudaError_t launch_merge_ungrouped(u64* dst, const u64* all_words, int n_ranks, uint32_t n_gwords, u64 rank_stride,

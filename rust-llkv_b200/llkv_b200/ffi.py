@@ -75,7 +75,8 @@ class RunInfo(C.Structure):
                 ("algorithmic_bytes_per_row", C.c_uint32), ("physical_bytes_per_row", C.c_uint32),
                 ("grid", C.c_uint32), ("block", C.c_uint32), ("rows_per_tile", C.c_uint32), ("stages", C.c_uint32),
                 ("smem_bytes", C.c_uint32), ("fast_groups", C.c_uint32), ("last_kernel_ms", C.c_float),
-                ("used_fast_kernel", C.c_uint32), ("used_jit_kernel", C.c_uint32), ("partitions", C.c_uint32), ("tiles_pruned", C.c_uint32)]
+                ("used_fast_kernel", C.c_uint32), ("used_jit_kernel", C.c_uint32), ("partitions", C.c_uint32), ("tiles_pruned", C.c_uint32),
+                ("graph_replays", C.c_uint32), ("merged_p2p", C.c_uint32)]
 
 
 class DebugColumn(C.Structure):

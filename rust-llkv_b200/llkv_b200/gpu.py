@@ -86,6 +86,8 @@ def load():
         "llkv_gpu_agg_reset": (i32, [vp]),
         "llkv_gpu_agg_run": (i32, [vp, vp, i32, u64, u64]),
         "llkv_gpu_agg_merge": (i32, [vp]),
+        "llkv_gpu_agg_execute": (i32, [vp, vp, i32, u64, u64, i32]),
+        "llkv_gpu_ctx_set_graphs": (i32, [vp, i32]),
         "llkv_gpu_agg_group_count": (i32, [vp, P(u64)]),
         "llkv_gpu_agg_finalize": (i32, [vp, vp, vp, u64, P(u64)]),
         "llkv_gpu_agg_run_info": (i32, [vp, P(ffi.RunInfo)]),
@@ -172,6 +174,10 @@ class Context:
         """Zone-map tile skipping: 0 = never, 1 = for columns scanned again unchanged when >= 1/8 of the tiles drop out
         (default), 2 = from the first scan, whenever any tile drops out."""
         _check(self.lib.llkv_gpu_ctx_set_pruning(self.handle, mode))
+
+    def set_graphs(self, mode: int):
+        """Aggregation.execute replays a captured CUDA graph once a step repeats unchanged: 1 (default) / 0."""
+        _check(self.lib.llkv_gpu_ctx_set_graphs(self.handle, mode))
 
     def set_upload_threads(self, n_threads: int):
         """Host workers narrowing Decimal128 chunks from page-locked sources before the DMA: -1 default, 0 off."""
@@ -266,7 +272,7 @@ class DeviceColumn:
             self.next_pk += 1
 
     def append_raw(self, ptr: int, n_rows: int, row_id_base: int):
-        """One chunk from a raw host pointer (e.g. a slice of a pinned buffer)."""
+        """One chunk from a raw pointer: host memory (e.g. a slice of a pinned buffer) or device memory of this GPU."""
         _check(self.lib.llkv_gpu_column_append_chunk(self.handle, self.next_pk, C.c_void_p(ptr), n_rows, None, None, row_id_base, None))
         self.next_pk += 1
 
@@ -355,17 +361,46 @@ class Aggregation:
     def merge(self):
         _check(self.lib.llkv_gpu_agg_merge(self.handle))
 
+    def execute(self, program: Optional[Program] = None, apply_mvcc: bool = False, row_begin: int = 0, row_end: Optional[int] = None,
+                merge: bool = True):
+        """reset + run + (merge, when the context has peers) in one call (llkv_gpu_agg_execute)."""
+        row_end = self.table.n_rows if row_end is None else row_end
+        _check(self.lib.llkv_gpu_agg_execute(self.handle, program.handle if program else None, int(apply_mvcc), row_begin, row_end, int(merge)))
+
     def group_count(self) -> int:
         n = C.c_uint64()
         _check(self.lib.llkv_gpu_agg_group_count(self.handle, C.byref(n)))
         return int(n.value)
 
     def finalize_raw(self, group_capacity: int):
-        vals = (ffi.AggValue * (group_capacity * max(1, self.n_aggs)))()
-        keys = (ffi.GroupKey * (group_capacity * max(1, self.n_keys)))()
+        """llkv_gpu_agg_finalize into C arrays (llkv_agg_value / llkv_group_key), kept and reused per capacity."""
+        buf = getattr(self, "_raw", None)
+        if buf is None or buf[0] != group_capacity:
+            buf = (group_capacity, (ffi.AggValue * (group_capacity * max(1, self.n_aggs)))(),
+                   (ffi.GroupKey * (group_capacity * max(1, self.n_keys)))())
+            self._raw = buf
+        _, vals, keys = buf
         n = C.c_uint64()
         _check(self.lib.llkv_gpu_agg_finalize(self.handle, vals, keys, group_capacity, C.byref(n)))
         return vals, keys, int(n.value)
+
+    AGG_VALUE_DTYPE = np.dtype([("lo", "<u8"), ("hi", "<u8"), ("type", "<i4"), ("precision", "u1"), ("scale", "i1"), ("valid", "u1"), ("_pad", "u1")])
+    GROUP_KEY_DTYPE = np.dtype([("bits", "<u8"), ("type", "<i4"), ("valid", "u1"), ("_pad", "u1", (3,))])
+
+    def finalize_numpy(self, group_capacity: int):
+        """The finalized cells as numpy structured arrays [groups, aggregates] / [groups, keys] (for results with millions of
+        groups: no Python object per cell)."""
+        vals, keys, n = self.finalize_raw(group_capacity)
+        v = np.frombuffer(vals, dtype=self.AGG_VALUE_DTYPE, count=n * self.n_aggs).reshape(n, self.n_aggs)
+        k = np.frombuffer(keys, dtype=self.GROUP_KEY_DTYPE, count=n * self.n_keys).reshape(n, self.n_keys) if self.n_keys else None
+        return v, k, n
+
+    def decode(self, vals, keys, n):
+        rows = []
+        for g in range(n):
+            key = tuple(decode_group_key(keys[g * self.n_keys + k]) for k in range(self.n_keys))
+            rows.append((key, [AggregateValue.from_c(vals[g * self.n_aggs + a]) for a in range(self.n_aggs)]))
+        return rows
 
     def finalize(self, group_capacity: Optional[int] = None):
         """[(key_tuple, [AggregateValue, ...]), ...] in first-appearance order of the groups."""
@@ -373,11 +408,7 @@ class Aggregation:
             group_capacity = self.group_count() if self.n_keys else 1
             group_capacity = max(1, group_capacity)
         vals, keys, n = self.finalize_raw(group_capacity)
-        rows = []
-        for g in range(n):
-            key = tuple(decode_group_key(keys[g * self.n_keys + k]) for k in range(self.n_keys))
-            rows.append((key, [AggregateValue.from_c(vals[g * self.n_aggs + a]) for a in range(self.n_aggs)]))
-        return rows
+        return self.decode(vals, keys, n)
 
     def run_info(self) -> ffi.RunInfo:
         info = ffi.RunInfo()

@@ -189,3 +189,87 @@ def shard_range(n_rows: int, world_size: int, rank: int, align: int = 131072) ->
     lo = chunks * rank // world_size * align
     hi = chunks * (rank + 1) // world_size * align
     return min(lo, n_rows), min(hi, n_rows)
+
+
+# ------------------------------------------------------------------------------------------------ expected answers
+# Plain numpy restatements of the two queries over the generator's arrays: what bench.py and the full-size tests check the
+# device results against (exact integers; not the oracle, which replays the reference's algorithm row by row).
+def visible_mask(created: np.ndarray, deleted: np.ndarray, snap: Snapshot) -> np.ndarray:
+    """RowVersion::is_visible_for (llkv-transaction/src/mvcc.rs:282-334) with TxnIdManager::status (mvcc.rs:157-171:
+    MAX -> none, 1 -> committed, listed -> not committed, unknown -> committed), vectorised."""
+    txn, sid = np.uint64(snap.txn_id), np.uint64(snap.snapshot_id)
+    none = np.uint64(TXN_ID_NONE)
+    nc = np.asarray(sorted(set(int(x) for x in snap.noncommitted) - {TXN_ID_AUTO_COMMIT}), dtype=np.uint64)
+    c_comm = (created != none) & ~np.isin(created, nc)
+    d_comm = (deleted != none) & ~np.isin(deleted, nc)
+    own = snap.txn_id != TXN_ID_AUTO_COMMIT
+    own_c = (created == txn) if own else np.zeros(created.shape, bool)
+    own_d = (deleted == txn) if own else np.zeros(created.shape, bool)
+    others = c_comm & (created <= sid) & ((deleted == none) | (~own_d & (~d_comm | (deleted > sid))))
+    return np.where(own_c, ~own_d, others)
+
+
+def expected_q6(a) -> int:
+    """Raw Decimal128(15,2) revenue: every product (scale 4) is rescaled to scale 2, half away from zero, then summed
+    (SURVEY.md §8a note D1, "as written")."""
+    m = ((a["shipdate"] >= date32(1994, 1, 1)) & (a["shipdate"] < date32(1995, 1, 1)) & (a["discount"] >= 5) & (a["discount"] <= 7)
+         & (a["quantity"] < 2400))
+    prod = a["extendedprice"][m] * a["discount"][m]
+    return int(((prod + 50) // 100).sum())
+
+
+def expected_q1_partials(a, created=None, deleted=None, snap: Optional[Snapshot] = None):
+    """{(returnflag, linestatus): [sum_qty, sum_base_price, sum_disc_price, sum_charge, sum_disc, count, first_row]} as
+    exact Python ints (partial states: add them across shards, then q1_rows_from_partials)."""
+    sel = a["shipdate"] <= date32(1998, 9, 2)
+    if snap is not None:
+        sel &= visible_mask(created, deleted, snap)
+    disc_price = a["extendedprice"] * (100 - a["discount"])  # scale 4, exact in int64
+    charge = disc_price * (100 + a["tax"])                   # scale 6: < 1.4e11 per row
+    out = {}
+    code = a["returnflag"].astype(np.int64) * 256 + a["linestatus"]
+    for c in np.unique(code[sel]):
+        g = sel & (code == c)
+        key = (chr(int(c) >> 8), chr(int(c) & 255))
+        parts = np.nonzero(g)[0]
+        # int64 sums stay exact: per group < 4e7 rows x 1.4e11
+        out[key] = [int(a["quantity"][g].sum()), int(a["extendedprice"][g].sum()), int(disc_price[g].sum()), int(charge[g].sum()),
+                    int(a["discount"][g].sum()), int(parts.size), int(parts[0])]
+    return out
+
+
+def add_partials(parts):
+    out = {}
+    for rank_base, p in parts:  # (row id of the shard's first row, partials)
+        for k, v in p.items():
+            if k not in out:
+                out[k] = v[:6] + [v[6] + rank_base]
+            else:
+                cur = out[k]
+                for i in range(6):
+                    cur[i] += v[i]
+                cur[6] = min(cur[6], v[6] + rank_base)
+    return out
+
+
+def q1_rows_from_partials(p):
+    """Rows in first-appearance order, values in q1_aggregates() order (AVG = sum / count at the input scale, rounded half
+    away from zero: llkv-aggregate/src/lib.rs:1720-1761)."""
+    def avg(s, c):
+        q, r = divmod(abs(s), c)
+        q += 1 if 2 * r >= c else 0
+        return q if s >= 0 else -q
+    rows = []
+    for k, v in sorted(p.items(), key=lambda kv: kv[1][6]):
+        sq, sp, sdp, sc, sd, c, _ = v
+        rows.append((k, [sq, sp, sdp, sc, avg(sq, c), avg(sp, c), avg(sd, c), c]))
+    return rows
+
+
+def splitmix64(i: np.ndarray) -> np.ndarray:
+    """SplitMix64 of uint64 counters (the key stream of BASELINE.json configs[3]: key = SplitMix64(i) mod n_keys)."""
+    with np.errstate(over="ignore"):
+        z = i.astype(np.uint64) + np.uint64(0x9E3779B97F4A7C15)
+        z = (z ^ (z >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+        z = (z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+        return z ^ (z >> np.uint64(31))

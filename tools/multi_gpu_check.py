@@ -67,9 +67,35 @@ def main():
         agg.destroy()
         if prog:
             prog.destroy()
+    # one call per step (llkv_gpu_agg_execute): the merge is one kernel over the NVLink peer mailboxes for the ungrouped state
+    # and for Q1's small group table alike, and from the fourth unchanged step on the whole step replays as one CUDA graph
+    ctx.set_partitioning(1)
+    ctx.set_pruning(1)
+    ctx.set_jit(1)
+    for flt, specs, keys, hint in ((tpch.q6_filter(), tpch.q6_aggregates(), (), 0), (tpch.q1_filter(), tpch.q1_aggregates(), tpch.Q1_GROUP_BY, 4)):
+        want = oracle.aggregate(full, flt, specs, snap, keys, group_capacity=64)
+        prog = gpu.Program(ctx, flt)
+        agg = gpu.Aggregation(dt, specs, keys, cardinality_hint=hint)
+        for step in range(8):
+            agg.execute(prog, True, merge=True)
+            util.assert_same_result(agg.finalize(64), want, 1e-12)
+        info = agg.run_info()
+        if not os.environ.get("LLKV_GPU_NO_P2P_MERGE"):
+            assert info.merged_p2p == 1, "the merge left the peer-mailbox path"
+        assert info.graph_replays >= 3, info.graph_replays
+        agg.destroy()
+        prog.destroy()
+    # a hint that is too low: the rank tables grow on their own and the fold of the union outgrows a rank's table
+    small = gpu.Aggregation(hdt, tpch.highcard_aggregates(), (tpch.K_FIELD,), cardinality_hint=20)
+    small.execute(None, False, merge=True)
+    got = small.finalize(1 << 17)
+    want = oracle.aggregate(hc, None, tpch.highcard_aggregates(), None, (tpch.K_FIELD,), group_capacity=1 << 17)
+    util.assert_same_result(got, want, 1e-12, ordered=False)
+    small.destroy()
     dist.barrier()
     if rank == 0:
-        print(f"multi-GPU merge ok on {world} ranks: Q6 (also with tile lists), Q1 and a 40k-group hash aggregate (per-row and partitioned) match the oracle", flush=True)
+        print(f"multi-GPU merge ok on {world} ranks: Q6 (also with tile lists), Q1 and a 40k-group hash aggregate (per-row and partitioned) match the oracle; "
+              f"execute() steps merge over peer mailboxes and replay as CUDA graphs", flush=True)
     ctx.comm_destroy()
     dist.destroy_process_group()
 
