@@ -345,9 +345,9 @@ def run_ours(args):
             extra["highcard"] = bench_highcard(ctx, gpu, torch, args, big=n >= 20_000_000)
         clocks = sampler.stop() if rank == 0 else None  # sampled across the timed regions
 
+        total_rows = sum(gather_rows(dist, n, world))
         if rank == 0:
             peak, peak_src = measured_peak()
-            total_rows = sum(gather_rows(dist, n, world))
             kms = statistics.mean(q6["kernel_ms"]) if q6["kernel_ms"] else float("nan")
             # bytes per row: `arrow` = Arrow-layout value buffers (Decimal128 = 16 B), `resident` = what the kernel reads from HBM
             # (Decimal128 columns whose values fit i32 / i64 are kept as 4 / 8 B per row, DESIGN.md "data layout").  The roofline
@@ -455,7 +455,7 @@ def bench_config0(ctx, gpu, args):
     percentile), without and with the MVCC columns every SQL table carries.  Launch-latency bound at this size: the 1 B-row figure is
     the Q6 / Q1 legs' business.  Results against numpy."""
     n = 10_000_000
-    t, snap = tpch.int64_table(n, seed=1)
+    t, snap = tpch.int64_table(n, seed=1, table_id=3)
     x = t.columns[tpch.X_FIELD].values
     lo, hi = (int(v) for v in np.percentile(x[:1_000_000], [25, 75]).astype(np.int64))
     want = int(x[(x >= lo) & (x <= hi)].sum())

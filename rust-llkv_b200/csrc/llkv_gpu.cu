@@ -528,6 +528,8 @@ extern "C" int32_t llkv_gpu_ctx_create(int32_t device_ordinal, int32_t n_streams
     c->keep_wide_decimals = e && e[0] == '1';
     const char* e32 = getenv("LLKV_GPU_NO_D32");
     c->no_d32 = e32 && e32[0] == '1';
+    const char* eg = getenv("LLKV_GPU_NO_GRAPHS");  // (profilers that want plain launches)
+    if (eg && eg[0] == '1') c->graph_mode = 0;
   }
   if (n_streams < 1) n_streams = 2;
   if (n_streams > 16) n_streams = 16;
@@ -3557,6 +3559,8 @@ extern "C" int32_t llkv_gpu_agg_execute(llkv_gpu_agg* a, const llkv_gpu_program*
       return LLKV_OK;
     }
     // the step is not capturable as it is (something in it waits for the device): run it the plain way, from scratch
+    if (getenv("LLKV_GPU_VERBOSE"))
+      fprintf(stderr, "[llkv] rank %d: step not captured as a CUDA graph: %s (rc %d: %s)\n", ctx->rank, cudaGetErrorString(e), rc, rc ? g_last_error.c_str() : "-");
     cudaGetLastError();
     if (a->graph_exec) cudaGraphExecDestroy(a->graph_exec);
     a->graph_exec = nullptr;
