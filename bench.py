@@ -185,8 +185,10 @@ def run_ours(args):
     cores = os.cpu_count() or 1
     ctx = gpu.Context(local, n_streams=4, pinned_bytes=64 << 20)
     # host workers that narrow Decimal128 chunks before the DMA: this rank's share of the host threads
-    upload_threads = args.upload_threads if args.upload_threads >= 0 else max(0, min(16, cores // world))
-    if upload_threads < 2:
+    upload_threads = args.upload_threads if args.upload_threads >= 0 else max(0, min(32, cores // world - 1))
+    if args.upload_threads < 0 and upload_threads < 16:
+        # one host thread narrows ~5 GB/s of Arrow bytes: with fewer than 16 of them per rank the narrowing is slower than
+        # sending the 16-byte layout over the link (measured: 12 threads per rank at N = 2, 113 ms against 72 ms per step)
         upload_threads = 0
     ctx.set_upload_threads(upload_threads)
     if world > 1:
@@ -267,7 +269,7 @@ def run_ours(args):
         agg.execute(prog, snapshot is not None, 0, n, merge=False)
         own = plain_rows(agg.finalize(cap))
         check(own == want_own, f"{name}: rank {rank}'s own shard gives {own}, numpy says {want_own}")
-        kernel_ms, launches = [], 0
+        kernel_ms, merge_ms, launches = [], [], 0
         raw = None
 
         def step(record):
@@ -277,6 +279,7 @@ def run_ours(args):
             if record:
                 info = agg.run_info()
                 kernel_ms.append(info.last_kernel_ms)
+                merge_ms.append(info.last_merge_ms)
                 launches += info.kernel_launches + 1 + (1 if world > 1 else 0)  # scan launches + accumulator init + merge kernel
 
         for _ in range(warmup):
@@ -292,7 +295,8 @@ def run_ours(args):
         info = agg.run_info()
         agg.destroy()
         prog.destroy()
-        return {"seconds": dt, "kernel_ms": kernel_ms, "launches": launches, "info": info, "result": merged}
+        return {"seconds": dt, "kernel_ms": kernel_ms, "merge_ms": statistics.mean(merge_ms) if merge_ms and world > 1 else None, "launches": launches,
+                "info": info, "result": merged}
 
     failed = None
     sampler = ClockSampler(local)
@@ -378,6 +382,7 @@ def run_ours(args):
                            "l2_policy": "inputs larger than L2 (%.2f GB resident per pass vs 126 MB)" % (alg_bpr * n / 1e9), "chunk_bytes": chunk_bytes,
                            "step": "llkv_gpu_agg_execute (reset + scan + merge, one CUDA graph launch once the step repeats) + llkv_gpu_agg_finalize",
                            "graph_replays": q6["info"].graph_replays, "merge": ("NVLink peer mailboxes" if q6["info"].merged_p2p else "NCCL") if world > 1 else "none",
+                           "merge_kernel_ms": q6["merge_ms"],
                            "kernel": {"grid": q6["info"].grid, "block": q6["info"].block, "rows_per_tile": q6["info"].rows_per_tile,
                                       "stages": q6["info"].stages, "smem_bytes": q6["info"].smem_bytes, "wide": q6["info"].used_wide_path,
                                       "specialised": q6["info"].used_jit_kernel}},
@@ -408,6 +413,7 @@ def run_ours(args):
                                            "algorithmic_gbs": q1["info"].algorithmic_bytes_per_row * n / (k1 * 1e-3) / 1e9},
                               "groups": [[list(k), v] for k, v in q1["result"]], "graph_replays": q1["info"].graph_replays,
                               "merge": ("NVLink peer mailboxes" if q1["info"].merged_p2p else "NCCL") if world > 1 else "none",
+                              "merge_kernel_ms": q1["merge_ms"],
                               "kernel_name": kernel_name(q1["info"]), "kernel": {"grid": q1["info"].grid, "block": q1["info"].block,
                                                                                   "rows_per_tile": q1["info"].rows_per_tile, "stages": q1["info"].stages,
                                                                                   "smem_bytes": q1["info"].smem_bytes, "fast_groups": q1["info"].fast_groups,

@@ -158,6 +158,8 @@ pub struct llkv_run_info {
     pub tiles_pruned: u32,
     pub graph_replays: u32,
     pub merged_p2p: u32,
+    pub last_merge_ms: f32,
+    pub _reserved: u32,
 }
 
 #[repr(C)]

@@ -234,6 +234,8 @@ typedef struct llkv_run_info {
   uint32_t tiles_pruned;        /* tiles the scan skipped because no conjunct range predicate can match their zones */
   uint32_t graph_replays;       /* steps of this aggregate that llkv_gpu_agg_execute replayed from its captured CUDA graph */
   uint32_t merged_p2p;          /* 1 when the last merge was one kernel over NVLink peer mailboxes (no collective, no host wait) */
+  float last_merge_ms;          /* device time of that merge kernel, waiting for the slowest peer included (timing enabled) */
+  uint32_t _reserved;
 } llkv_run_info;
 
 typedef struct llkv_gpu_ctx llkv_gpu_ctx;
@@ -298,7 +300,7 @@ int32_t llkv_gpu_host_free(void* p);
 /* Host worker threads that narrow Decimal128 chunks arriving from page-locked memory to 8 or 4 bytes per value before the
  * DMA, as long as every value of the column is a sign-extended i64 / i32 (a chunk that does not fit sends the column back
  * to the Arrow layout, nothing is lost): half or a quarter of the bytes cross PCIe and the device skips its own narrowing
- * pass at seal.  -1 = default (min(16, hardware threads)), 0 = off (16-byte DMA, narrowed on the device at seal). */
+ * pass at seal.  -1 = default (min(32, hardware threads - 1)), 0 = off (16-byte DMA, narrowed on the device at seal). */
 int32_t llkv_gpu_ctx_set_upload_threads(llkv_gpu_ctx* ctx, int32_t n_threads);
 /* Page-locks memory the caller already owns — the pager's mmap-backed blobs (EntryHandle, llkv-storage/src/pager/
  * simd_r_drive_pager.rs) — so llkv_gpu_column_append_blob / _append_chunk DMA straight out of it

@@ -1588,6 +1588,14 @@ class Emitter {
       const size_t lits_mark = lits_.size();
       if (lower_fast()) {
         out_.fast = true;
+        // the lean program raises FLAG_NARROW_FAIL only from its checked operations (everything else was proven to fit)
+        bool checked = false;
+        for (uint32_t i = 0; i < p.n_finstr; ++i) {
+          const FInstr& fi = p.fcode[i];
+          const uint32_t fb = fi.a & 0x7f;
+          if ((fi.op == FO_OP_COL || fi.op == FO_OP_LIT || fi.op == FO_OP_TMP) && (fb == FB_ADD_CK || fb == FB_SUB_CK || fb == FB_MUL_CK)) checked = true;
+        }
+        out_.can_narrow_fail = checked;
         p.n_lits = (uint32_t)lits_.size();
         for (size_t i = 0; i < lits_.size(); ++i) p.lits[i] = lits_[i];
       } else {

@@ -296,6 +296,7 @@ struct llkv_gpu_ctx {
   bool keep_wide_decimals = false;  // LLKV_GPU_KEEP_WIDE_DECIMALS=1: never narrow Decimal128 columns at seal
   bool no_d32 = false;              // LLKV_GPU_NO_D32=1: narrow to i64 only (experiments)
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  cudaEvent_t ev2 = nullptr, ev3 = nullptr;  // around the peer-mailbox merge kernel (timing)
   void* nccl_comm = nullptr;
   int n_ranks = 1, rank = 0;
   // peer-memory mailboxes for the ungrouped merge (scan_kernel.cu: merge_ungrouped_p2p_kernel): every rank maps every
@@ -311,7 +312,7 @@ struct llkv_gpu_ctx {
   uint64_t state_epoch = 1;  // bumped by every call that can change what a compiled plan depends on (columns, snapshots, knobs)
   int graph_mode = 1;        // llkv_gpu_agg_execute: 1 = replay a captured CUDA graph once a step repeats unchanged, 0 = never
   // host workers that narrow Decimal128 chunks from page-locked sources before the DMA (upload.h); created on first use
-  int upload_threads = -1;  // -1 = default (min(16, hardware threads)), 0 = never narrow on the host
+  int upload_threads = -1;  // -1 = default (min(32, hardware threads - 1)), 0 = never narrow on the host
   std::unique_ptr<UploadPool> pool;
 };
 #define CTX_LOCK(c) std::lock_guard<std::recursive_mutex> _ctx_lock((c)->mu)
@@ -402,6 +403,7 @@ struct PendingRun {
   bool has_backup = false;
   bool timed = false;
   bool is_merge = false;  // a grouped peer-mailbox merge is queued behind the run (agg_resolve settles both)
+  bool timed_merge = false;
 };
 
 struct llkv_gpu_agg {
@@ -545,6 +547,8 @@ extern "C" int32_t llkv_gpu_ctx_create(int32_t device_ordinal, int32_t n_streams
   CUDA_TRY(cudaHostAlloc((void**)&c->pinned, c->slot_bytes * (uint64_t)n_streams, cudaHostAllocDefault));
   CUDA_TRY(cudaEventCreate(&c->ev0));
   CUDA_TRY(cudaEventCreate(&c->ev1));
+  CUDA_TRY(cudaEventCreate(&c->ev2));
+  CUDA_TRY(cudaEventCreate(&c->ev3));
   {
     std::lock_guard<std::mutex> lk(g_registry_mu);
     g_contexts.push_back(c);
@@ -576,6 +580,8 @@ extern "C" void llkv_gpu_ctx_destroy(llkv_gpu_ctx* c) {
   if (c->pinned) cudaFreeHost(c->pinned);
   if (c->ev0) cudaEventDestroy(c->ev0);
   if (c->ev1) cudaEventDestroy(c->ev1);
+  if (c->ev2) cudaEventDestroy(c->ev2);
+  if (c->ev3) cudaEventDestroy(c->ev3);
   delete c;
 }
 
@@ -1052,7 +1058,10 @@ static UploadPool* upload_pool(llkv_gpu_ctx* c) {
   if (c->upload_threads == 0) return nullptr;
   if (!c->pool) {
     int n = c->upload_threads;
-    if (n < 0) n = (int)std::min<unsigned>(16u, std::max<unsigned>(1u, std::thread::hardware_concurrency()));
+    if (n < 0) {  // one thread streams ~5 GB/s of Arrow bytes; the caller's thread keeps a core for issuing the appends
+      const unsigned hw = std::thread::hardware_concurrency();
+      n = (int)std::min<unsigned>(32u, hw > 2 ? hw - 1 : 1u);
+    }
     c->pool.reset(new UploadPool(c->device, n));
   }
   return c->pool.get();
@@ -2781,6 +2790,11 @@ static int32_t agg_resolve(llkv_gpu_agg* a) {
       if (cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1) == cudaSuccess) a->info.last_kernel_ms = ms;
       else cudaGetLastError();
     }
+    if (a->pending.timed_merge) {
+      float ms = 0;
+      if (cudaEventElapsedTime(&ms, ctx->ev2, ctx->ev3) == cudaSuccess) a->info.last_merge_ms = ms;
+      else cudaGetLastError();
+    }
     const uint32_t flags = *a->h_flags;
     if (flags == 0) break;
     a->prefetched = false;  // the run is repeated or failed: what travelled behind it is not the result
@@ -2897,6 +2911,7 @@ static int32_t agg_run_impl(llkv_gpu_agg* a, const llkv_gpu_program* prog, int32
   a->pending.row_end = row_end;
   a->pending.wide = false;
   a->pending.is_merge = false;
+  a->pending.timed_merge = false;
   rc = agg_launch(a, prog, apply_mvcc, row_begin, row_end, false);
   if (rc) return rc;
   a->pending.wide = a->cr.wide;
@@ -3340,7 +3355,7 @@ static bool merge_is_p2p(const llkv_gpu_agg* a) {
   if (a->cr.plan.n_keys == 0) return !a->cr.can_narrow_fail && a->n_gwords < 127;
   if (!a->hint || a->p2p_group_disabled) return false;
   const u64 cap0 = next_pow2(std::max<u64>(32, a->hint * 2)) * 4;
-  return 2 + cap0 + (cap0 + 2) * a->n_gwords <= kGroupSlotWords;
+  return 2 + cap0 + (cap0 + 2) * (a->n_gwords + 1) <= kGroupSlotWords;
 }
 
 static int32_t agg_merge_impl(llkv_gpu_agg* a) {
@@ -3365,8 +3380,11 @@ static int32_t agg_merge_impl(llkv_gpu_agg* a) {
     }
     a->info.merged_p2p = ctx->p2p_merge && a->n_gwords < 127 ? 1 : 0;
     if (ctx->p2p_merge && a->n_gwords < 127) {  // NVLink peer stores + flags, no collective library on the path
+      a->pending.timed_merge = ctx->timing;
+      if (ctx->timing) CUDA_TRY(cudaEventRecord(ctx->ev2, ctx->stream));
       CUDA_TRY(launch_merge_ungrouped_p2p(a->gwords, ctx->peer_mbox, N, ctx->rank, a->n_gwords, ctx->d_epoch, a->d_gclass, a->d_flags,
                                           ctx->stream));
+      if (ctx->timing) CUDA_TRY(cudaEventRecord(ctx->ev3, ctx->stream));
       return agg_queue_result_copy(a);  // (also the status word again: the merge kernel reports a peer that never arrives)
     }
     const size_t word_elems = (size_t)(3 * a->n_gwords);
@@ -3384,7 +3402,7 @@ static int32_t agg_merge_impl(llkv_gpu_agg* a) {
   // uses the hint and the accumulator layout, which every rank shares.
   if (a->frozen && a->cr.plan.n_keys != 0 && ctx->nccl_comm && N > 1 && ctx->p2p_merge && a->hint && !a->p2p_group_disabled) {
     const u64 cap0 = next_pow2(std::max<u64>(32, a->hint * 2)) * 4;
-    if (2 + cap0 + (cap0 + 2) * a->n_gwords <= kGroupSlotWords) {
+    if (2 + cap0 + (cap0 + 2) * (a->n_gwords + 1) <= kGroupSlotWords) {
       if (!a->pending.active) {
         a->pending.active = true;
         a->pending.timed = false;
@@ -3392,8 +3410,11 @@ static int32_t agg_merge_impl(llkv_gpu_agg* a) {
       }
       a->pending.is_merge = true;
       a->info.merged_p2p = 1;
+      a->pending.timed_merge = ctx->timing;
+      if (ctx->timing) CUDA_TRY(cudaEventRecord(ctx->ev2, ctx->stream));
       CUDA_TRY(launch_merge_grouped_p2p(a->gkeys, a->gwords, a->gcap, a->n_gwords, a->d_gclass, a->d_flags, ctx->peer_gbox, kGroupSlotWords, N, ctx->rank,
                                         ctx->d_epoch, true, ctx->stream));
+      if (ctx->timing) CUDA_TRY(cudaEventRecord(ctx->ev3, ctx->stream));
       return agg_queue_result_copy(a);
     }
   }
@@ -3511,6 +3532,7 @@ extern "C" int32_t llkv_gpu_agg_execute(llkv_gpu_agg* a, const llkv_gpu_program*
     a->pending.has_backup = gp.has_backup;
     a->pending.timed = gp.timed;
     a->pending.is_merge = gp.is_merge;
+    a->pending.timed_merge = gp.timed_merge;
     a->reset_pending = false;  // part of the graph
     CUDA_TRY(cudaGraphLaunch(a->graph_exec, ctx->stream));
     ++a->info.graph_replays;

@@ -1116,7 +1116,7 @@ __global__ void __launch_bounds__(512) merge_grouped_p2p_kernel(GroupMergeArgs a
     u64 head = a.gcap;
     if (local & ~(FLAG_NARROW_FAIL | FLAG_TABLE_FULL)) head = kMsgFailed;
     else if (local) head = kMsgRerun;
-    else if (2 + n_key_words + n_words > a.slot_words) head = kMsgOversize;
+    else if (2 + n_key_words + n_words + rows > a.slot_words) head = kMsgOversize;  // (+ rows: the receiver's scratch)
     const bool fits = head == a.gcap;
     for (int r = 0; r < a.n_ranks; ++r) {
       u64* dst = a.peers.box[r] + (size_t)(a.rank * 2 + par) * a.slot_words;
@@ -1167,49 +1167,68 @@ __global__ void __launch_bounds__(512) merge_grouped_p2p_kernel(GroupMergeArgs a
   __syncthreads();
   const u64 mask = a.gcap - 1;
   uint32_t err = 0;
+  __shared__ uint8_t s_class[kMaxWords];
+  for (uint32_t w = tid; w < a.n_gwords; w += NT) s_class[w] = a.wclass[w];
+  // (a) destination row of every occupied source row of every rank, all at once: a few dependent L2 round trips in total.
+  //     The rows land behind the rank's message in the mailbox slot (the sender left room for them).
   for (int r = 0; r < a.n_ranks; ++r) {
-    const u64* src = mine + (size_t)(r * 2 + par) * a.slot_words;
+    u64* src = const_cast<u64*>(mine) + (size_t)(r * 2 + par) * a.slot_words;
     const u64 scap = src[1];
     const u64* skeys = src + 2;
     const u64* swords = src + 2 + scap;
+    u64* dest = src + 2 + scap + (scap + 2) * a.n_gwords;
     for (u64 i = tid; i < scap + 2; i += NT) {
-      const u64* sw = swords + i * a.n_gwords;
-      u64 K = kEmptyKey, slot;
+      u64 slot = ~0ull;
       if (i < scap) {
-        K = skeys[i];
-        if (K == kEmptyKey) continue;
-        slot = ~0ull;
-        u64 h = mix64(K) & mask;
-        for (u64 t = 0; t <= mask; ++t) {
-          const u64 cur = a.gkeys[h];
-          if (cur == K) { slot = h; break; }
-          if (cur == kEmptyKey) {
-            const u64 old = atomicCAS(&a.gkeys[h], kEmptyKey, K);
-            if (old == kEmptyKey || old == K) { slot = h; break; }
+        const u64 K = skeys[i];
+        if (K != kEmptyKey) {
+          u64 h = mix64(K) & mask;
+          for (u64 t = 0; t <= mask; ++t) {
+            const u64 cur = a.gkeys[h];
+            if (cur == K) { slot = h; break; }
+            if (cur == kEmptyKey) {
+              const u64 old = atomicCAS(&a.gkeys[h], kEmptyKey, K);
+              if (old == kEmptyKey || old == K) { slot = h; break; }
+            }
+            h = (h + 1) & mask;
           }
-          h = (h + 1) & mask;
+          if (slot == ~0ull) err |= FLAG_TABLE_FULL;
         }
-        if (slot == ~0ull) { err |= FLAG_TABLE_FULL; continue; }
-      } else {
-        if (sw[0] == 0) continue;  // word 0 = rows folded into the group: the spare rows (reserved key value, NULL key) are empty
+      } else if (swords[i * a.n_gwords] != 0) {  // word 0 = rows folded into the group: the spare rows (reserved key value, NULL key)
         slot = a.gcap + (i - scap);
       }
-      u64* d = a.gwords + slot * a.n_gwords;
-      for (uint32_t w = 0; w < a.n_gwords; ++w) {
-        const u64 v = sw[w];
-        switch (a.wclass[w]) {
-          case WC_SUM: d[w] += v; break;
-          case WC_FSUM: d[w] = (u64)__double_as_longlong(__longlong_as_double((i64)d[w]) + __longlong_as_double((i64)v)); break;
-          case WC_MIN: d[w] = v < d[w] ? v : d[w]; break;
-          case WC_MAX: d[w] = v > d[w] ? v : d[w]; break;
-          case WC_MIN128: case WC_MAX128: {
-            const bool is_max = a.wclass[w] == WC_MAX128;
-            const u64 h = v, l = sw[w + 1], ch = d[w], cl = d[w + 1];
-            const bool better = is_max ? (h > ch || (h == ch && l > cl)) : (h < ch || (h == ch && l < cl));
-            if (better) { d[w] = h; d[w + 1] = l; }
-            break;
-          }
-          default: break;  // low half of a pair: written with its high word
+      dest[i] = slot;
+    }
+  }
+  __syncthreads();
+  // (b) the words, one thread per (source row, word), rank after rank: rows of one source table go to distinct groups, so
+  //     the updates need no atomics, and the fixed rank order gives every rank the same f64 sums
+  for (int r = 0; r < a.n_ranks; ++r) {
+    const u64* src = mine + (size_t)(r * 2 + par) * a.slot_words;
+    const u64 scap = src[1];
+    const u64* swords = src + 2 + scap;
+    const u64* dest = src + 2 + scap + (scap + 2) * a.n_gwords;
+    const u64 items = (scap + 2) * a.n_gwords;
+    for (u64 idx = tid; idx < items; idx += NT) {
+      const u64 i = idx / a.n_gwords;
+      const uint32_t w = (uint32_t)(idx % a.n_gwords);
+      const u64 slot = dest[i];
+      if (slot == ~0ull) continue;
+      const uint8_t c = s_class[w];
+      if (c == WC_PAIR_LO_MIN || c == WC_PAIR_LO_MAX) continue;  // written with its high word
+      const u64 v = swords[idx];
+      u64* d = a.gwords + slot * a.n_gwords + w;
+      switch (c) {
+        case WC_SUM: if (v) *d += v; break;
+        case WC_FSUM: *d = (u64)__double_as_longlong(__longlong_as_double((i64)*d) + __longlong_as_double((i64)v)); break;
+        case WC_MIN: if (v < *d) *d = v; break;
+        case WC_MAX: if (v > *d) *d = v; break;
+        default: {  // WC_MIN128 / WC_MAX128: (high, low) pair
+          const bool is_max = c == WC_MAX128;
+          const u64 l = swords[idx + 1], ch = d[0], cl = d[1];
+          const bool better = is_max ? (v > ch || (v == ch && l > cl)) : (v < ch || (v == ch && l < cl));
+          if (better) { d[0] = v; d[1] = l; }
+          break;
         }
       }
     }

@@ -2,14 +2,42 @@
 #include "upload.h"
 
 #include <string.h>
+#if defined(__SSE2__)
+#include <emmintrin.h>
+#endif
 
 namespace llkv {
 
+// The loops below are the host side of the PCIe path: 16 bytes read and 8 / 4 written per value.  With SSE2 (every
+// x86-64) four values are handled per iteration with unpack instructions; the fit check is an OR-reduction, so the loop
+// has no branch.
 bool narrow_d128_i64(const void* src, void* dst, uint64_t n) {
   const int64_t* in = static_cast<const int64_t*>(src);
   int64_t* out = static_cast<int64_t*>(dst);
   int64_t bad = 0;
-  for (uint64_t i = 0; i < n; ++i) {
+  uint64_t i = 0;
+#if defined(__SSE2__)
+  __m128i vbad = _mm_setzero_si128();
+  for (; i + 4 <= n; i += 4) {
+    const __m128i r0 = _mm_loadu_si128(reinterpret_cast<const __m128i*>(in + 2 * i));
+    const __m128i r1 = _mm_loadu_si128(reinterpret_cast<const __m128i*>(in + 2 * i + 2));
+    const __m128i r2 = _mm_loadu_si128(reinterpret_cast<const __m128i*>(in + 2 * i + 4));
+    const __m128i r3 = _mm_loadu_si128(reinterpret_cast<const __m128i*>(in + 2 * i + 6));
+    const __m128i lo01 = _mm_unpacklo_epi64(r0, r1), hi01 = _mm_unpackhi_epi64(r0, r1);
+    const __m128i lo23 = _mm_unpacklo_epi64(r2, r3), hi23 = _mm_unpackhi_epi64(r2, r3);
+    _mm_storeu_si128(reinterpret_cast<__m128i*>(out + i), lo01);
+    _mm_storeu_si128(reinterpret_cast<__m128i*>(out + i + 2), lo23);
+    const __m128i s01 = _mm_shuffle_epi32(_mm_srai_epi32(lo01, 31), _MM_SHUFFLE(3, 3, 1, 1));
+    const __m128i s23 = _mm_shuffle_epi32(_mm_srai_epi32(lo23, 31), _MM_SHUFFLE(3, 3, 1, 1));
+    vbad = _mm_or_si128(vbad, _mm_or_si128(_mm_xor_si128(hi01, s01), _mm_xor_si128(hi23, s23)));
+  }
+  {
+    int64_t t[2];
+    _mm_storeu_si128(reinterpret_cast<__m128i*>(t), vbad);
+    bad = t[0] | t[1];
+  }
+#endif
+  for (; i < n; ++i) {
     const int64_t lo = in[2 * i], hi = in[2 * i + 1];
     out[i] = lo;
     bad |= hi ^ (lo >> 63);
@@ -21,7 +49,32 @@ bool narrow_d128_i32(const void* src, void* dst, uint64_t n) {
   const int64_t* in = static_cast<const int64_t*>(src);
   int32_t* out = static_cast<int32_t*>(dst);
   int64_t bad = 0;
-  for (uint64_t i = 0; i < n; ++i) {
+  uint64_t i = 0;
+#if defined(__SSE2__)
+  __m128i vbad = _mm_setzero_si128();
+  const __m128i upper = _mm_set_epi32(-1, -1, -1, 0);  // dwords 1..3 of a value
+  for (; i + 4 <= n; i += 4) {
+    const __m128i r0 = _mm_loadu_si128(reinterpret_cast<const __m128i*>(in + 2 * i));
+    const __m128i r1 = _mm_loadu_si128(reinterpret_cast<const __m128i*>(in + 2 * i + 2));
+    const __m128i r2 = _mm_loadu_si128(reinterpret_cast<const __m128i*>(in + 2 * i + 4));
+    const __m128i r3 = _mm_loadu_si128(reinterpret_cast<const __m128i*>(in + 2 * i + 6));
+    // dword 0 of the four values
+    const __m128i a = _mm_unpacklo_epi32(r0, r1), b = _mm_unpacklo_epi32(r2, r3);
+    _mm_storeu_si128(reinterpret_cast<__m128i*>(out + i), _mm_unpacklo_epi64(a, b));
+    // dwords 1..3 must repeat the sign of dword 0
+    const __m128i x0 = _mm_xor_si128(r0, _mm_shuffle_epi32(_mm_srai_epi32(r0, 31), 0));
+    const __m128i x1 = _mm_xor_si128(r1, _mm_shuffle_epi32(_mm_srai_epi32(r1, 31), 0));
+    const __m128i x2 = _mm_xor_si128(r2, _mm_shuffle_epi32(_mm_srai_epi32(r2, 31), 0));
+    const __m128i x3 = _mm_xor_si128(r3, _mm_shuffle_epi32(_mm_srai_epi32(r3, 31), 0));
+    vbad = _mm_or_si128(vbad, _mm_and_si128(upper, _mm_or_si128(_mm_or_si128(x0, x1), _mm_or_si128(x2, x3))));
+  }
+  {
+    int64_t t[2];
+    _mm_storeu_si128(reinterpret_cast<__m128i*>(t), vbad);
+    bad = t[0] | t[1];
+  }
+#endif
+  for (; i < n; ++i) {
     const int64_t lo = in[2 * i], hi = in[2 * i + 1];
     out[i] = (int32_t)lo;
     bad |= (hi ^ (lo >> 63)) | (lo ^ (int64_t)(int32_t)lo);
