@@ -159,7 +159,7 @@ pub struct llkv_run_info {
     pub graph_replays: u32,
     pub merged_p2p: u32,
     pub last_merge_ms: f32,
-    pub _reserved: u32,
+    pub packed_tuples: u32,
 }
 
 #[repr(C)]

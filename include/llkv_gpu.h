@@ -235,7 +235,8 @@ typedef struct llkv_run_info {
   uint32_t graph_replays;       /* steps of this aggregate that llkv_gpu_agg_execute replayed from its captured CUDA graph */
   uint32_t merged_p2p;          /* 1 when the last merge was one kernel over NVLink peer mailboxes (no collective, no host wait) */
   float last_merge_ms;          /* device time of that merge kernel, waiting for the slowest peer included (timing enabled) */
-  uint32_t _reserved;
+  uint32_t packed_tuples;       /* partitioned run in its packed form (64-bit tuples, partitions aggregated in shared memory):
+                                   1 = partitions are hash ranges, 2 = key ranges (dense integer keys); 0 = first form / not partitioned */
 } llkv_run_info;
 
 typedef struct llkv_gpu_ctx llkv_gpu_ctx;
@@ -274,8 +275,11 @@ int32_t llkv_gpu_ctx_set_jit(llkv_gpu_ctx* ctx, int32_t mode);
  * 5028-5355) updates the global open-addressing table once per row.  When the table is much larger than L2 that is one
  * random DRAM sector read-modify-write per row and word; the partitioned form writes (key, row id, operands) tuples into
  * hash partitions whose table slice fits in L2 and folds them partition by partition (two streaming passes instead of
- * random access).  mode: 0 = never, 1 = when the table exceeds L2 and the scan is long enough (default), 2 = whenever
- * the plan allows it (tests).  Results are identical in every mode.  Needs the specialised kernel (jit mode != 0). */
+ * random access).  When the keys, a launch-relative row number and the SUM operands of a row fit one 64-bit word the tuples
+ * are packed, the partitions are made small enough (a few thousand groups) for one CTA to aggregate a whole partition in
+ * shared memory, and every group is written to the table once per launch.  mode: 0 = never, 1 = when the table exceeds L2
+ * and the scan is long enough (default), 2 = whenever the plan allows it (tests), 3 = as 2 but never the packed form
+ * (tests).  Results are identical in every mode.  Needs the specialised kernel (jit mode != 0). */
 int32_t llkv_gpu_ctx_set_partitioning(llkv_gpu_ctx* ctx, int32_t mode);
 
 /* Zone-map pruning on the device-resident image — the chunk skip of the reference's scans (ChunkMetadata min/max against
@@ -485,7 +489,7 @@ int32_t llkv_gpu_debug_plan(const llkv_debug_column* cols, int32_t n_cols, const
                             int32_t deleted_by_col, uint64_t txn_id, uint64_t snapshot_id, const llkv_agg_spec* specs, int32_t n_aggs,
                             const llkv_scalar_node* nodes, int32_t n_nodes, const uint64_t* group_key_fields, int32_t n_keys,
                             int32_t expr_mode, uint64_t cardinality_hint, int32_t block_threads, int32_t rows_per_thread, int32_t stages,
-                            int32_t ctas_per_sm, int32_t jit /* bit 0: specialise with NVRTC, bit 1: as the partitioned GROUP BY scan, bit 2: as the scan that walks a tile list */, const char* cubin_path, char* out_text, uint64_t out_cap);
+                            int32_t ctas_per_sm, int32_t jit /* bit 0: specialise with NVRTC, bit 1: as the partitioned GROUP BY scan, bit 2: as the scan that walks a tile list, bit 3: the partitioned scan with packed tuples */, const char* cubin_path, char* out_text, uint64_t out_cap);
 
 /* ---- multi-GPU: one context per rank, NCCL over NVLink ---- */
 #define LLKV_GPU_UNIQUE_ID_BYTES 128

@@ -2008,6 +2008,14 @@ class Emitter {
           lean_word(in.b, width, rowrel);
           if (op != FO_COUNT && op != FO_FIRSTVALID) load_acc(st.size() - 1);  // counts do not look at the value
           femit(op, a, in.b, in.c);
+          if (op == FO_SUM) {  // operand proven in [0, 2^32): its width in bits (packed tuples of a partitioned GROUP BY)
+            const Iv& v = st.back().iv;
+            if (v.known && v.lo >= 0 && v.hi < ((i128)1 << 32)) {
+              uint32_t bits = 1;
+              while (bits < 32 && (v.hi >> bits) != 0) ++bits;
+              f.back().g = bits;
+            }
+          }
           if (!keep) {
             free_sym(st.back());
             st.pop_back();

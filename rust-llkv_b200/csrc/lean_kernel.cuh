@@ -166,6 +166,7 @@ struct LeanDynCfg {
   static constexpr bool kStatic = false;
   static constexpr bool kDefer = false;
   static constexpr bool kPartition = false;
+  static constexpr bool kPacked = false;
   static constexpr int kStash = 1;
   static __host__ __device__ constexpr FInstr code(int) { return FInstr{}; }
   static __device__ __forceinline__ const LeanShape& shape(const LeanPlan& p) { return p.s; }
@@ -200,6 +201,7 @@ struct LeanTile {
   unsigned stash_m[Cfg::kStash];
   u64 pk[Cfg::kPartition ? R : 1];  // partitioned plans: the rows' packed keys, kept from GROUP to scatter()
   unsigned char* const part_smem;
+  uint32_t batch_tiles = 0;         // packed form: tiles appended to the batch buffer since the last flush
 
   __device__ __forceinline__ LeanTile(const LeanPlan& plan, const LeanShape& shape, unsigned char* smem, int tid_, int nc)
       : p(plan), S(shape), tid(tid_), NC(nc), T(shape.tile_rows), my4(smem + shape.smem_acc_off + tid_ * 4),
@@ -860,8 +862,120 @@ struct LeanTile {
       if constexpr (in.op != FO_END && PC + 1 < kMaxFastInstr) apply_tuple<PC + 1>(stage, i, gs, row);
     }
   }
+  // ---------------------------------------------------------------------------------- packed tuples (partition == 2)
+  // One 64-bit word per selected row: key | launch-relative row | SUM operands.  The CTA appends the tuples of
+  // pack_batch / tile_rows tiles to a batch buffer in shared memory (no barrier: one shared-memory atomic per warp and tile),
+  // then scatters the batch: count per partition, one global atomic per non-empty partition reserves the space, every
+  // tuple goes to its place with a streaming store.  Partitions are small enough (a few thousand groups) for
+  // partition_fold_kernel to aggregate each of them in shared memory, so no row of the scan ever updates the table in
+  // global memory; the batch makes the runs per partition long enough for L2 to assemble full lines.
+  __device__ __forceinline__ uint32_t part_of_packed(u64 t) const {
+    const u64 K = t & ((1ull << S.pack_key_bits) - 1);
+    return p.part_dense ? (uint32_t)(K >> p.part_shift) : (uint32_t)((mix64(K) & (p.gcap - 1)) >> p.part_shift);
+  }
+  template <int PC>
+  __device__ __forceinline__ u64 pack_ops(int r, uint32_t shift) const {
+    if constexpr (Cfg::kStatic) {
+      constexpr FInstr in = Cfg::code(PC);
+      u64 v = 0;
+      uint32_t next = shift;
+      if constexpr (lean_takes_operand(in.op)) {
+        v = stash_v[lean_stash_index<Cfg>(PC)][r] << shift;
+        next = shift + S.pack_op_bits[lean_field_index<Cfg>(PC) - 2];
+      }
+      if constexpr (in.op != FO_END && PC + 1 < kMaxFastInstr) v |= pack_ops<PC + 1>(r, next);
+      return v;
+    } else {
+      return 0;
+    }
+  }
+  // a tuple that found its partition full (skewed keys): applied to the table here, word by word
+  template <int PC>
+  __device__ __forceinline__ void apply_packed(u64 t, u64 gs, u64 row, uint32_t shift) {
+    if constexpr (Cfg::kStatic) {
+      constexpr FInstr in = Cfg::code(PC);
+      uint32_t next = shift;
+      if constexpr (lean_is_aggregate(in.op)) {
+        u64 v = 0;
+        if constexpr (lean_takes_operand(in.op)) {
+          const uint32_t bits = S.pack_op_bits[lean_field_index<Cfg>(PC) - 2];
+          v = (t >> shift) & ((1ull << bits) - 1);
+          next = shift + bits;
+        }
+        lean_slow_accumulate(&p.gwords[gs * S.n_gwords + in.c], in.op, in.a, (i64)v, row);
+      }
+      if constexpr (in.op != FO_END && PC + 1 < kMaxFastInstr) apply_packed<PC + 1>(t, gs, row, next);
+    }
+  }
+  __device__ __forceinline__ void flush_packed() {
+    if constexpr (Cfg::kPacked) {
+      uint32_t* const s_fill = reinterpret_cast<uint32_t*>(part_smem);
+      const uint32_t P = S.pack_parts;
+      uint32_t* const cnt = s_fill + 2;
+      uint32_t* const gbase = cnt + P;
+      const u64* const buf = reinterpret_cast<const u64*>(gbase + P);
+      lean_consumer_barrier(NC);  // every append of the batch is in the buffer
+      const uint32_t n = *s_fill;
+      for (uint32_t q = (uint32_t)tid; q < P; q += (uint32_t)NC) cnt[q] = 0;
+      lean_consumer_barrier(NC);
+      if (tid == 0) *s_fill = 0;
+      for (uint32_t i = (uint32_t)tid; i < n; i += (uint32_t)NC) atomicAdd(&cnt[part_of_packed(buf[i])], 1u);
+      lean_consumer_barrier(NC);
+      for (uint32_t q = (uint32_t)tid; q < P; q += (uint32_t)NC) {
+        const uint32_t c = cnt[q];
+        gbase[q] = c ? atomicAdd(&p.part_cursor[q], c) : 0u;
+        cnt[q] = 0;
+      }
+      lean_consumer_barrier(NC);
+      const u64 cap = p.part_cap;
+      const uint32_t kb = S.pack_key_bits, rb = S.pack_row_bits;
+      for (uint32_t i = (uint32_t)tid; i < n; i += (uint32_t)NC) {
+        const u64 t = buf[i];
+        const uint32_t q = part_of_packed(t);
+        const u64 j = (u64)gbase[q] + atomicAdd(&cnt[q], 1u);
+        if (j < cap) {
+          __stcs(&p.part_out[(u64)q * cap + j], t);  // read once, by the next kernel
+        } else {
+          const u64 K = t & ((1ull << kb) - 1);
+          const u64 gs = lean_global_slot(p.gkeys, p.gcap, S.n_keys, K, errbits);
+          const u64 row = p.row_origin + p.first_tile * (u64)T + ((t >> kb) & ((1ull << rb) - 1));
+          apply_packed<0>(t, gs, row, kb + rb);
+        }
+      }
+      lean_consumer_barrier(NC);  // the buffer is free for the next batch
+    }
+  }
+  __device__ __forceinline__ void scatter_packed() {
+    if constexpr (Cfg::kPacked) {
+      uint32_t* const s_fill = reinterpret_cast<uint32_t*>(part_smem);
+      u64* const buf = reinterpret_cast<u64*>(s_fill + 2 + 2u * S.pack_parts);
+      const int lane = tid & 31;
+      const uint32_t c = (uint32_t)__popc(actm);
+      uint32_t inc = c;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t y = __shfl_up_sync(LLKV_FULL, inc, o);
+        if (lane >= o) inc += y;
+      }
+      uint32_t wbase = 0;
+      if (lane == 31 && inc) wbase = atomicAdd(s_fill, inc);
+      wbase = __shfl_sync(LLKV_FULL, wbase, 31);
+      uint32_t at = wbase + inc - c;
+      const uint32_t kb = S.pack_key_bits, rb = S.pack_row_bits;
+#pragma unroll
+      for (int r = 0; r < R; ++r)
+        if ((actm >> r) & 1u) buf[at++] = pk[r] | ((u64)(rel0 + (uint32_t)(r * NC)) << kb) | pack_ops<0>(r, kb + rb);
+      if (++batch_tiles == S.pack_batch / T) {  // the next tile might not fit: every consumer thread counts the same tiles
+        flush_packed();
+        batch_tiles = 0;
+      }
+    }
+  }
+
   __device__ __forceinline__ void scatter() {
-    if constexpr (Cfg::kPartition) {
+    if constexpr (Cfg::kPacked) {
+      scatter_packed();
+    } else if constexpr (Cfg::kPartition) {
       uint32_t* const s_cnt = reinterpret_cast<uint32_t*>(part_smem);
       uint32_t* const s_off = s_cnt + (kMaxPartitions + 1);
       uint32_t* const s_gb = s_off + (kMaxPartitions + 1);
@@ -984,7 +1098,10 @@ __device__ __forceinline__ void lean_body(const LeanPlan& p) {
       }
   }
   for (uint32_t g = tid; g < FG; g += blockDim.x) tbl[g] = grouped ? kEmptyKey : 0ull;
-  if constexpr (Cfg::kPartition) {
+  if constexpr (Cfg::kPacked) {
+    uint32_t* const s_fill = reinterpret_cast<uint32_t*>(smem + S.smem_part_off);
+    for (uint32_t q = tid; q < 2u + 2u * S.pack_parts; q += blockDim.x) s_fill[q] = 0;
+  } else if constexpr (Cfg::kPartition) {
     uint32_t* const s_cnt = reinterpret_cast<uint32_t*>(smem + S.smem_part_off);
     for (uint32_t q = tid; q < 3u * (kMaxPartitions + 1) + 1u; q += blockDim.x) s_cnt[q] = 0;
   }
@@ -1046,6 +1163,7 @@ __device__ __forceinline__ void lean_body(const LeanPlan& p) {
         ++round;
       }
     }
+    if constexpr (Cfg::kPacked) t.flush_packed();  // what the last tiles left in the batch buffer
     errbits = t.errbits;
   }
 

@@ -33,6 +33,8 @@ cudaError_t launch_scan(const Plan* dplan, bool wide, int rows_per_thread, uint3
                         cudaStream_t stream);
 cudaError_t launch_lean(const LeanPlan& plan, uint32_t grid, cudaStream_t stream);
 cudaError_t launch_partition_apply(const PartPlan& plan, uint32_t grid, cudaStream_t stream);
+cudaError_t launch_partition_fold(const FoldPlan& plan, uint32_t grid, cudaStream_t stream);
+uint32_t fold_smem_bytes(uint32_t slots, uint32_t n_ops, bool dense);
 cudaError_t launch_init_table(u64* keys, u64* words, u64 rows, uint32_t n_gwords, const uint8_t* word_class_dev, cudaStream_t stream);
 cudaError_t launch_merge_table(const Plan* dplan, const u64* src_keys, const u64* src_words, u64 src_cap, cudaStream_t stream);
 cudaError_t launch_merge_ungrouped_p2p(u64* state, u64* const* peer_boxes, int n_ranks, int rank, uint32_t n_gwords, u64* epoch_dev,
@@ -295,6 +297,7 @@ struct llkv_gpu_ctx {
   std::map<std::string, uint32_t> shape_runs;
   bool keep_wide_decimals = false;  // LLKV_GPU_KEEP_WIDE_DECIMALS=1: never narrow Decimal128 columns at seal
   bool no_d32 = false;              // LLKV_GPU_NO_D32=1: narrow to i64 only (experiments)
+  bool no_packed = false;           // LLKV_GPU_NO_PACKED=1: partitioned GROUP BY in its first form only (experiments)
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   cudaEvent_t ev2 = nullptr, ev3 = nullptr;  // around the peer-mailbox merge kernel (timing)
   void* nccl_comm = nullptr;
@@ -438,9 +441,12 @@ struct llkv_gpu_agg {
   bool in_rerun = false;
   // the lean plan of the previous run, reusable while request_signature() does not change
   LeanPlan lean;
-  LeanPlan lean2[3];  // [0] interpreted geometry, [1] geometry of the specialised build, [2] specialised + partitioned
-  bool lean_have[3] = {false, false, false};
-  uint32_t lean_grid2[3] = {0, 0, 0}, lean_ctas2[3] = {1, 1, 1};
+  LeanPlan lean2[4];  // [0] interpreted geometry, [1] geometry of the specialised build, [2] specialised + partitioned, [3] + packed tuples
+  bool lean_have[4] = {false, false, false, false};
+  uint32_t lean_grid2[4] = {0, 0, 0, 0}, lean_ctas2[4] = {1, 1, 1, 1};
+  // packed form: partition layout of the current plan
+  uint32_t pk_parts = 0, pk_shift = 0, pk_slots = 0, pk_dense = 0, pk_key_bits = 0, pk_row_bits = 0, pk_n_ops = 0, pk_used_parts = 0;
+  uint32_t pk_op_bits[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   // partitioned high-cardinality GROUP BY: tuple partitions and their fill counters, kept across runs
   u64* part_out = nullptr;
   size_t part_out_elems = 0;
@@ -530,6 +536,8 @@ extern "C" int32_t llkv_gpu_ctx_create(int32_t device_ordinal, int32_t n_streams
     c->keep_wide_decimals = e && e[0] == '1';
     const char* e32 = getenv("LLKV_GPU_NO_D32");
     c->no_d32 = e32 && e32[0] == '1';
+    const char* ep = getenv("LLKV_GPU_NO_PACKED");
+    c->no_packed = ep && ep[0] == '1';
     const char* eg = getenv("LLKV_GPU_NO_GRAPHS");  // (profilers that want plain launches)
     if (eg && eg[0] == '1') c->graph_mode = 0;
   }
@@ -617,7 +625,7 @@ extern "C" int32_t llkv_gpu_ctx_set_jit(llkv_gpu_ctx* c, int32_t mode) {
 
 extern "C" int32_t llkv_gpu_ctx_set_partitioning(llkv_gpu_ctx* c, int32_t mode) {
   if (!c) return set_error(LLKV_ERR_INVALID_ARGUMENT, "ctx is NULL");
-  if (mode < 0 || mode > 2) return set_error(LLKV_ERR_INVALID_ARGUMENT, "partitioning mode must be 0, 1 or 2");
+  if (mode < 0 || mode > 3) return set_error(LLKV_ERR_INVALID_ARGUMENT, "partitioning mode must be 0, 1, 2 or 3");
   c->partition_mode = mode;
   ++c->state_epoch;
   return LLKV_OK;
@@ -1683,7 +1691,35 @@ struct LeanTune {
   bool interpreted = false;  // geometry for the ahead-of-time (interpreting) build: dispatch cost per instruction and tile
                              // is amortised over the rows per thread, so rows per thread weigh more than resident warps
   bool partition = false;    // partitioned high-cardinality GROUP BY: the scan emits tuples (LeanTile::scatter)
+  // packed form of it (LeanTile::scatter_packed): one 64-bit tuple per row, partitions aggregated in shared memory
+  bool packed = false;
+  uint32_t pack_key_bits = 0, pack_row_bits = 0, pack_parts = 0, pack_op_bits[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 };
+
+// The packed form needs: integer-packed keys narrower than 64 bits, after GROUP only COUNT / first row / SUMs whose
+// operands are proven in [0, 2^32), and room for all of it plus >= 20 bits of launch-relative row in one 64-bit word.
+// Returns the bits left for the row (0 = not eligible) and fills the operand widths.
+static uint32_t packed_row_bits(const Plan& p, uint32_t* key_bits_out, uint32_t op_bits[8], uint32_t* n_ops_out) {
+  if (p.n_keys == 0 || p.single_wide_key) return 0;
+  uint32_t kb = 0;
+  for (uint32_t k = 0; k < p.n_keys; ++k) kb += p.key_bits[k] + (p.key_nullable[k] ? 1u : 0u);
+  if (kb == 0 || kb > 40) return 0;
+  uint32_t used = kb, n_ops = 0;
+  bool after_group = false;
+  for (uint32_t i = 0; i < p.n_finstr; ++i) {
+    const FInstr& in = p.fcode[i];
+    if (in.op == FO_GROUP) { after_group = true; continue; }
+    if (!after_group || in.op < FO_COUNT_STAR || in.op > FO_FIRSTNAN) continue;
+    if (in.op == FO_COUNT_STAR || in.op == FO_COUNT || in.op == FO_FIRSTROW) continue;
+    if (in.op != FO_SUM || in.g == 0 || in.g > 32 || n_ops >= 4) return 0;
+    op_bits[n_ops++] = in.g;
+    used += in.g;
+  }
+  if (used + 20 > 64) return 0;
+  *key_bits_out = kb;
+  *n_ops_out = n_ops;
+  return std::min<uint32_t>(30u, 64u - used);
+}
 
 // A grouped lean plan can run partitioned when everything after GROUP is arithmetic plus aggregates whose row mask is the
 // selection itself and whose update partition_apply_kernel knows (no NaN-dependent masks).
@@ -1702,6 +1738,44 @@ static bool partition_eligible(const Plan& p) {
     if (lean_takes_operand(op)) ++fields;
   }
   return after_group && fields <= 2 + (uint32_t)kMaxPartOperands;
+}
+// Partition layout of the packed form.  Dense integer keys (the packed key range is within 4x the expected groups) make a
+// partition a key range whose shared-memory slots are indexed directly; otherwise partitions are ranges of the key's hash
+// with a small open-addressing table in shared memory (load factor <= 1/2 when the keys spread evenly).
+struct PackedLayout {
+  uint32_t parts = 0, shift = 0, slots = 0, dense = 0, key_bits = 0, row_bits = 0, n_ops = 0;
+  uint32_t op_bits[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+};
+static bool packed_layout(const Plan& p, u64 hint, u64 gcap, bool small_tables, PackedLayout& L) {
+  L = PackedLayout();
+  if (!hint) return false;
+  L.row_bits = packed_row_bits(p, &L.key_bits, L.op_bits, &L.n_ops);
+  if (!L.row_bits) return false;
+  const u64 span = 1ull << L.key_bits;  // packed keys are < 2^key_bits (the column minimum is subtracted)
+  uint32_t slots = L.n_ops <= 1 ? 8192u : 4096u;
+  const bool dense = span <= std::max<u64>(hint * 4, 1ull << 16);
+  u64 parts;
+  uint32_t shift = 0;
+  if (dense) {
+    while (small_tables && slots > 256 && span / slots < 64) slots /= 2;  // (tests: small tables still get several partitions)
+    while ((1u << shift) < slots) ++shift;
+    parts = (span + slots - 1) / slots;
+  } else {
+    if (fold_smem_bytes(slots, L.n_ops, false) > 200u * 1024u) slots /= 2;
+    while (small_tables && slots > 256 && hint * 2 / slots < 16) slots /= 2;
+    parts = next_pow2(std::max<u64>(2, (hint * 2 + slots - 1) / slots));
+    uint32_t cap_log2 = 0, bits = 0;
+    while ((1ull << cap_log2) < gcap) ++cap_log2;
+    while ((1ull << bits) < parts) ++bits;
+    if (bits > cap_log2) return false;
+    shift = cap_log2 - bits;
+  }
+  if (parts < 2 || parts > (u64)kMaxPackedPartitions || fold_smem_bytes(slots, L.n_ops, dense) > 200u * 1024u) return false;
+  L.parts = (uint32_t)parts;
+  L.shift = shift;
+  L.slots = slots;
+  L.dense = dense ? 1u : 0u;
+  return true;
 }
 static int32_t lean_geometry(const LeanTune& tn, const Plan& p, uint64_t row_begin, uint64_t row_end, uint64_t hint, LeanPlan& lp, Geometry& g,
                              uint32_t* ctas_out) {
@@ -1743,8 +1817,8 @@ static int32_t lean_geometry(const LeanTune& tn, const Plan& p, uint64_t row_beg
     s.words[w].gword = p.fast[w].gword;
     thread_bytes += s.words[w].width;
   }
-  uint32_t NC = tn.block ? (uint32_t)tn.block : 128u;
-  if (NC > 256) NC = 256;
+  uint32_t NC = tn.block ? (uint32_t)tn.block : (tn.packed ? 512u : 128u);
+  if (NC > (tn.packed ? 512u : 256u)) NC = tn.packed ? 512u : 256u;
   if (NC < 32) NC = 32;
   NC = NC / 32 * 32;
   // CTA-local group slots: every slot costs thread_bytes per consumer thread
@@ -1764,6 +1838,13 @@ static int32_t lean_geometry(const LeanTune& tn, const Plan& p, uint64_t row_beg
       s.n_fields = 2;
       for (uint32_t i = 0; i < p.n_finstr; ++i)
         if (lean_takes_operand(p.fcode[i].op)) ++s.n_fields;
+      if (tn.packed) {
+        s.partition = 2;
+        s.pack_key_bits = tn.pack_key_bits;
+        s.pack_row_bits = tn.pack_row_bits;
+        s.pack_parts = tn.pack_parts;
+        for (int j = 0; j < 8; ++j) s.pack_op_bits[j] = tn.pack_op_bits[j];
+      }
     }
     while (FG > 4 && (u64)FG * thread_bytes * NC > 64u * 1024u) FG /= 2;
   }
@@ -1771,7 +1852,7 @@ static int32_t lean_geometry(const LeanTune& tn, const Plan& p, uint64_t row_beg
   uint32_t want_stages = tn.stages ? (uint32_t)tn.stages : 0u;
   if (want_stages == 1) want_stages = 2;
   const uint32_t want_ctas = tn.ctas ? (uint32_t)tn.ctas : 0u;
-  uint32_t want_R = tn.rpt ? (uint32_t)tn.rpt : 0u;
+  uint32_t want_R = tn.rpt ? (uint32_t)tn.rpt : (tn.packed ? 2u : 0u);  // (packed: the shared memory goes to the batch buffer, not to tiles)
 
   // layout for one candidate geometry; returns the stages that fit (0 = does not fit)
   auto layout = [&](uint32_t R, uint32_t ctas, uint32_t fg, uint32_t nc) -> uint32_t {
@@ -1789,9 +1870,18 @@ static int32_t lean_geometry(const LeanTune& tn, const Plan& p, uint64_t row_beg
     }
     const uint32_t slot_stride = align_up(woff, 128);
     const uint32_t acc_bytes = align_up(fg * slot_stride, 128), tmp_bytes = align_up(p.fast_tmps * T * 8, 128), tbl_bytes = align_up(fg * 16, 128);
-    const uint32_t part_bytes = s.partition ? align_up(3u * (kMaxPartitions + 1) * 4 + 4 + s.n_fields * T * 8, 128) : 0;
-    const uint32_t fixed = 128 /* barriers */ + acc_bytes + tmp_bytes + tbl_bytes + part_bytes;
+    uint32_t part_bytes = s.partition ? align_up(3u * (kMaxPartitions + 1) * 4 + 4 + s.n_fields * T * 8, 128) : 0;
     const uint32_t per_cta = budget_total / ctas - 1024;
+    if (s.partition == 2) {  // fill word, counters and reserved bases per partition, then the batch buffer: as large as fits
+      uint32_t B = 16384;
+      for (; B >= 2 * T; B /= 2) {
+        part_bytes = align_up(8u + 2u * s.pack_parts * 4u + B * 8u, 128);
+        if (per_cta >= 128 + acc_bytes + tmp_bytes + tbl_bytes + part_bytes + 2 * stage_bytes) break;
+      }
+      if (B < 2 * T) return 0;
+      s.pack_batch = B;
+    }
+    const uint32_t fixed = 128 /* barriers */ + acc_bytes + tmp_bytes + tbl_bytes + part_bytes;
     if (!stage_bytes || per_cta < fixed + 2 * stage_bytes) return 0;
     uint32_t st = (per_cta - fixed) / stage_bytes;
     if (want_stages) {
@@ -1833,7 +1923,7 @@ static int32_t lean_geometry(const LeanTune& tn, const Plan& p, uint64_t row_beg
     const uint32_t Rs[4] = {8, 4, 2, 1};
     for (int ri = 0; ri < 4; ++ri) {
       if (want_R ? Rs[ri] != want_R : (Rs[ri] == 1 && best_score)) continue;
-      for (uint32_t ctas = 4; ctas >= 1; --ctas) {
+      for (uint32_t ctas = tn.packed ? 1 : 4; ctas >= 1; --ctas) {
         const uint32_t c = want_ctas ? want_ctas : ctas;
         const uint32_t st = layout(Rs[ri], c, fg, nc);
         if (st >= 2) {
@@ -1927,7 +2017,12 @@ static std::string lean_listing(const LeanPlan& lp, const Geometry& g, uint32_t 
   snprintf(b, sizeof(b), "lean plan: %u instr, %u cols, %u words, %u keys | NC=%u R=%u tile=%u stages=%u stage_bytes=%u fg=%u slot_stride=%u smem=%u ctas/SM=%u grid=%u\n",
            s.n_code, s.n_cols, s.n_words, s.n_keys, s.nc, s.rows_per_thread, s.tile_rows, s.stages, s.stage_bytes, s.fg, s.slot_stride, s.smem_total, ctas, g.grid);
   o += b;
-  if (s.partition) {
+  if (s.partition == 2) {
+    snprintf(b, sizeof(b), "  partitioned, packed tuples: %u key bits | %u row bits | operands %u %u %u %u; %u partitions, batch of %u tuples at smem+%u\n",
+             s.pack_key_bits, s.pack_row_bits, s.pack_op_bits[0], s.pack_op_bits[1], s.pack_op_bits[2], s.pack_op_bits[3], s.pack_parts, s.pack_batch,
+             s.smem_part_off);
+    o += b;
+  } else if (s.partition) {
     snprintf(b, sizeof(b), "  partitioned: %u fields per tuple, staging at smem+%u\n", s.n_fields, s.smem_part_off);
     o += b;
   }
@@ -2031,6 +2126,17 @@ extern "C" int32_t llkv_gpu_debug_plan(const llkv_debug_column* cols, int32_t n_
     tn.stages = stages;
     tn.ctas = ctas_per_sm;
     tn.partition = (jit & 2) != 0 && partition_eligible(cr.plan);  // jit bit 1: the partitioned form of a GROUP BY
+    if (tn.partition && (jit & 8)) {  // jit bit 3: its packed form, when the plan allows it
+      PackedLayout L;
+      const u64 gcap = next_pow2(std::max<u64>(32, cardinality_hint * 2));
+      if (packed_layout(cr.plan, cardinality_hint, gcap, true, L)) {
+        tn.packed = true;
+        tn.pack_key_bits = L.key_bits;
+        tn.pack_row_bits = L.row_bits;
+        tn.pack_parts = L.parts;
+        for (int j = 0; j < 8; ++j) tn.pack_op_bits[j] = L.op_bits[j];
+      }
+    }
     LeanPlan lp;
     Geometry g;
     uint32_t ctas = 1;
@@ -2428,7 +2534,7 @@ static int32_t agg_launch(llkv_gpu_agg* a, const llkv_gpu_program* prog, int app
   if (!(a->lean_sig == sig && a->cr.fast && a->frozen)) {
     a->lean_sig = 0;
     a->lean_jit_runs = 0;
-    a->lean_have[0] = a->lean_have[1] = a->lean_have[2] = false;
+    a->lean_have[0] = a->lean_have[1] = a->lean_have[2] = a->lean_have[3] = false;
     req.specs = a->specs.data();
     req.n_aggs = (int32_t)a->specs.size();
     req.agg_nodes = a->nodes.data();
@@ -2450,7 +2556,14 @@ static int32_t agg_launch(llkv_gpu_agg* a, const llkv_gpu_program* prog, int app
       if (a->lean_have[which]) return LLKV_OK;
       LeanTune tn = lean_tune(ctx);
       tn.interpreted = which == 0;
-      tn.partition = which == 2;
+      tn.partition = which >= 2;
+      if (which == 3) {
+        tn.packed = true;
+        tn.pack_key_bits = a->pk_key_bits;
+        tn.pack_row_bits = a->pk_row_bits;
+        tn.pack_parts = a->pk_parts;
+        for (int j = 0; j < 8; ++j) tn.pack_op_bits[j] = a->pk_op_bits[j];
+      }
       Geometry gg;
       uint32_t cc = 1;
       // (a hint below the number of groups already seen would leave groups without a CTA-local slot: every row of such a
@@ -2478,11 +2591,37 @@ static int32_t agg_launch(llkv_gpu_agg* a, const llkv_gpu_program* prog, int app
     if (ctx->partition_mode && ctx->jit_mode && a->lean2[0].s.direct_global && partition_eligible(p)) {
       const u64 table_bytes = a->gcap * (8ull + 8ull * a->n_gwords);
       const bool big = table_bytes > (64ull << 20) && row_end - row_begin >= (4ull << 20);
-      if ((big || ctx->partition_mode == 2) && a->gcap >= 64) {
-        if ((rc = geometry(2))) return rc;
-        if (jit_ready(ctx->device, a->lean2[2], (int)a->lean_ctas2[2])) {
-          which = 2;
-          use_jit = true;
+      if ((big || ctx->partition_mode >= 2) && a->gcap >= 64) {
+        // Packed form first: one 64-bit tuple per row into partitions of a few thousand groups, each aggregated in shared
+        // memory by partition_fold_kernel.  Dense integer keys (the key range is within 4x the expected groups) make a
+        // partition a key range whose slots are indexed directly; otherwise partitions are hash ranges with a small
+        // open-addressing table in shared memory.
+        PackedLayout L;
+        bool packed = false;
+        if (!ctx->no_packed && ctx->partition_mode != 3 && packed_layout(p, a->hint, a->gcap, ctx->partition_mode == 2, L)) {
+          if (a->pk_parts != L.parts || a->pk_shift != L.shift || a->pk_slots != L.slots || a->pk_dense != L.dense || a->pk_key_bits != L.key_bits ||
+              a->pk_row_bits != L.row_bits || a->pk_n_ops != L.n_ops || memcmp(a->pk_op_bits, L.op_bits, sizeof(L.op_bits)) != 0)
+            a->lean_have[3] = false;
+          a->pk_parts = L.parts;
+          a->pk_shift = L.shift;
+          a->pk_slots = L.slots;
+          a->pk_dense = L.dense;
+          a->pk_key_bits = L.key_bits;
+          a->pk_row_bits = L.row_bits;
+          a->pk_n_ops = L.n_ops;
+          memcpy(a->pk_op_bits, L.op_bits, sizeof(L.op_bits));
+          if ((rc = geometry(3)) == LLKV_OK && jit_ready(ctx->device, a->lean2[3], (int)a->lean_ctas2[3])) {
+            which = 3;
+            use_jit = true;
+            packed = true;
+          }
+        }
+        if (!packed) {
+          if ((rc = geometry(2))) return rc;
+          if (jit_ready(ctx->device, a->lean2[2], (int)a->lean_ctas2[2])) {
+            which = 2;
+            use_jit = true;
+          }
         }
       }
     }
@@ -2536,9 +2675,83 @@ static int32_t agg_launch(llkv_gpu_agg* a, const llkv_gpu_program* prog, int app
   // (capacity = the uniform share + 25 %; a partition that fills up — skewed keys — hands its surplus rows to the per-row
   // path inside the scan, so no rerun is ever needed).
   PartPlan pp;
+  FoldPlan fp;
   uint32_t part_grid = 0;
+  const bool packed = a->cr.fast && lean.s.partition == 2;
   const bool partitioned = a->cr.fast && lean.s.partition != 0;
-  if (partitioned) {
+  if (packed) {
+    // partitions that can hold keys: all of them for hash ranges; for key ranges those below the largest packed key
+    u64 used = a->pk_parts;
+    if (a->pk_dense && p.n_keys == 1 && p.key_kind[0] == KK_INT) {
+      for (const ColumnMeta& c : req.cols)
+        if (c.field_id == a->keys[0] && c.has_minmax) {
+          const u64 kmax = c.max_bits - c.min_bits;  // (two's complement difference: also right for signed columns)
+          used = std::min<u64>(used, (kmax >> a->pk_shift) + 1);
+        }
+    }
+    a->pk_used_parts = (uint32_t)used;
+    const u64 P = a->pk_parts;
+    u64 batch_rows = 1ull << a->pk_row_bits;
+    if (const char* e = getenv("LLKV_GPU_PART_BATCH_ROWS")) batch_rows = std::min<u64>(batch_rows, std::max<u64>(p.tile_rows, strtoull(e, nullptr, 10)));
+    const u64 dense_max_rows = max_rows_per_launch;
+    u64 part_cap = 0;
+    for (;;) {  // the tuple buffer of one launch; when HBM is short the launches get smaller instead
+      max_rows_per_launch = std::max<u64>(p.tile_rows, std::min<u64>(dense_max_rows, batch_rows) / p.tile_rows * p.tile_rows);
+      const u64 launch_rows = std::min<u64>(row_end - row_begin + p.tile_rows, max_rows_per_launch);
+      part_cap = (launch_rows / used + launch_rows / (4 * used) + 1024 + 15) / 16 * 16;
+      const size_t elems = (size_t)(P * part_cap);
+      if (a->part_out_elems >= elems) break;
+      if (a->part_out) CUDA_TRY(cudaFree(a->part_out));
+      a->part_out = nullptr;
+      a->part_out_elems = 0;
+      if (cudaMalloc((void**)&a->part_out, elems * 8) == cudaSuccess) {
+        a->part_out_elems = elems;
+        break;
+      }
+      cudaGetLastError();
+      a->part_out = nullptr;
+      if (batch_rows <= (1ull << 22)) return set_error(LLKV_ERR_IO, "out of device memory for the tuple partitions of a GROUP BY (%zu bytes)", elems * 8);
+      batch_rows >>= 1;
+    }
+    if (!a->part_cursor) CUDA_TRY(cudaMalloc((void**)&a->part_cursor, kMaxPackedPartitions * 4));
+    lean.part_out = a->part_out;
+    lean.part_cursor = a->part_cursor;
+    lean.part_cap = part_cap;
+    lean.part_bits = 0;
+    lean.part_shift = a->pk_shift;
+    lean.part_dense = a->pk_dense;
+    memset(&fp, 0, sizeof(fp));
+    fp.tuples = a->part_out;
+    fp.cursor = a->part_cursor;
+    fp.part_cap = part_cap;
+    fp.gkeys = a->gkeys;
+    fp.gwords = a->gwords;
+    fp.gcap = a->gcap;
+    fp.flags = a->d_flags;
+    fp.n_parts = (uint32_t)P;
+    fp.n_gwords = lean.s.n_gwords;
+    fp.n_keys = lean.s.n_keys;
+    fp.key_bits = a->pk_key_bits;
+    fp.row_bits = a->pk_row_bits;
+    fp.dense = a->pk_dense;
+    fp.part_shift = a->pk_shift;
+    fp.slots = a->pk_slots;
+    fp.first_gword = ~0u;
+    for (uint32_t i = 0; i < lean.s.n_code; ++i) {  // operands in the order of the aggregates (lean_field_index)
+      const FInstr& in = lean.s.code[i];
+      if (in.op == FO_COUNT_STAR || in.op == FO_COUNT) fp.count_gword[fp.n_counts++] = in.c;
+      else if (in.op == FO_FIRSTROW) fp.first_gword = in.c;
+      else if (in.op == FO_SUM) {
+        fp.op_bits[fp.n_ops] = in.g;
+        fp.op_gword[fp.n_ops] = in.c;
+        fp.op_wide[fp.n_ops] = (in.a & 0x80) ? 1u : 0u;
+        ++fp.n_ops;
+      }
+    }
+    part_grid = (uint32_t)std::min<u64>((u64)ctx->sm_count, used);
+    a->info.partitions = (uint32_t)used;
+    a->info.packed_tuples = 1 + a->pk_dense;
+  } else if (partitioned) {
     const u64 table_bytes = a->gcap * (8ull + 8ull * a->n_gwords);
     uint32_t cap_log2 = 0;
     while ((1ull << cap_log2) < a->gcap) ++cap_log2;
@@ -2570,7 +2783,7 @@ static int32_t agg_launch(llkv_gpu_agg* a, const llkv_gpu_program* prog, int app
       if (batch_rows <= (1ull << 22)) return set_error(LLKV_ERR_IO, "out of device memory for the tuple partitions of a GROUP BY (%zu bytes)", elems * 8);
       batch_rows >>= 1;
     }
-    if (!a->part_cursor) CUDA_TRY(cudaMalloc((void**)&a->part_cursor, kMaxPartitions * 4));
+    if (!a->part_cursor) CUDA_TRY(cudaMalloc((void**)&a->part_cursor, kMaxPackedPartitions * 4));
     lean.part_out = a->part_out;
     lean.part_cursor = a->part_cursor;
     lean.part_cap = part_cap;
@@ -2600,8 +2813,10 @@ static int32_t agg_launch(llkv_gpu_agg* a, const llkv_gpu_program* prog, int app
     }
     part_grid = (uint32_t)ctx->sm_count;  // launch_partition_apply multiplies by the kernel's resident CTAs per SM
     a->info.partitions = (uint32_t)P;
+    a->info.packed_tuples = 0;
   } else {
     a->info.partitions = 0;
+    a->info.packed_tuples = 0;
   }
   // Zone-map pruning (lean path): every FO_LEAF of the program is a conjunct (`selected &= lo <= v <= hi`), so a tile none
   // of whose zones can satisfy some leaf holds no selected row.  The surviving tiles are listed on the host from the
@@ -2716,11 +2931,16 @@ static int32_t agg_launch(llkv_gpu_agg* a, const llkv_gpu_program* prog, int app
       lean.first_tile = first_tile;
       lean.n_tiles = n_tiles;
       bool jitted = false;
-      if (partitioned) CUDA_TRY(cudaMemsetAsync(a->part_cursor, 0, kMaxPartitions * 4, ctx->stream));
+      if (partitioned) CUDA_TRY(cudaMemsetAsync(a->part_cursor, 0, kMaxPackedPartitions * 4, ctx->stream));
       if (use_jit) CUDA_TRY(jit_launch(ctx->device, lean, (int)lean_ctas, (uint32_t)grid, ctx->stream, &jitted, nullptr));
       if (partitioned) {
         if (!jitted) return set_error(LLKV_ERR_INTERNAL, "the partitioned scan needs its specialised kernel");
-        CUDA_TRY(launch_partition_apply(pp, part_grid, ctx->stream));
+        if (packed) {
+          fp.row_base = lean.row_origin + first_tile * (u64)p.tile_rows;  // launch-relative row 0
+          CUDA_TRY(launch_partition_fold(fp, part_grid, ctx->stream));
+        } else {
+          CUDA_TRY(launch_partition_apply(pp, part_grid, ctx->stream));
+        }
         ++launches;
       }
       if (!jitted) CUDA_TRY(launch_lean(lean, (uint32_t)grid, ctx->stream));
@@ -3161,7 +3381,7 @@ static int32_t agg_collect(llkv_gpu_agg* a, std::vector<u64>& hk, std::vector<u6
   std::sort(groups.begin(), groups.end(), [](const GroupRef& x, const GroupRef& y) { return x.first_row < y.first_row; });
   if (a->hint && a->hint <= 128 && groups.size() > a->hint && groups.size() > a->observed_groups) {
     a->observed_groups = groups.size();  // the caller's hint was low: later runs of this aggregate get more CTA-local slots
-    a->lean_have[0] = a->lean_have[1] = a->lean_have[2] = false;
+    a->lean_have[0] = a->lean_have[1] = a->lean_have[2] = a->lean_have[3] = false;
     ++a->plan_epoch;
   }
   return LLKV_OK;

@@ -149,4 +149,160 @@ cudaError_t launch_partition_apply(const PartPlan& plan, uint32_t grid, cudaStre
   return cudaErrorInvalidValue;
 }
 
+// ------------------------------------------------------------------------------------------------------------------------
+// Pass 2 of the packed form (LeanTile::scatter_packed): every partition holds the tuples of at most `slots` groups or so,
+// and one CTA aggregates a whole partition in shared memory — 32-bit shared-memory atomics only (64-bit shared atomics are
+// CAS loops on this architecture): a row count, the first row (MIN) and, per SUM operand, a (low, carry) pair of u32 that
+// is exact for operands below 2^32.  Dense integer keys index the slots directly (a partition is a key range); other keys
+// go through an open-addressing table of the partition's keys in shared memory.  When the partition is done each group
+// is written to the global table once: the per-row global atomics of the first form (1.2 probes + 3 REDs per row, bound by
+// L2 request rate) become one insert per group and launch.
+constexpr int kFoldThreads = 512;
+
+template <int NOPS, bool DENSE>
+__global__ void __launch_bounds__(kFoldThreads, 1) partition_fold_kernel(const __grid_constant__ FoldPlan fp) {
+  extern __shared__ __align__(16) unsigned char fold_smem[];
+  const uint32_t S = fp.slots, smask = S - 1;
+  uint32_t* const s_rows = reinterpret_cast<uint32_t*>(fold_smem);   // [S]
+  uint32_t* const s_first = s_rows + S;                               // [S]
+  uint32_t* const s_lo = s_first + S;                                 // [NOPS][S]
+  uint32_t* const s_hi = s_lo + (size_t)(NOPS ? NOPS : 1) * S;        // [NOPS][S]
+  u64* const s_keys = reinterpret_cast<u64*>(s_hi + (size_t)(NOPS ? NOPS : 1) * S);  // [S] (hashed form only)
+  const uint32_t tid = threadIdx.x;
+  const u64 kmask = (1ull << fp.key_bits) - 1, rmask = (1ull << fp.row_bits) - 1;
+  const u64 cap = fp.part_cap;
+  uint32_t errbits = 0;
+  uint32_t opshift[NOPS ? NOPS : 1];
+  u64 opmask[NOPS ? NOPS : 1];
+  {
+    uint32_t sh = fp.key_bits + fp.row_bits;
+#pragma unroll
+    for (int j = 0; j < NOPS; ++j) {
+      opshift[j] = sh;
+      opmask[j] = (1ull << fp.op_bits[j]) - 1;
+      sh += fp.op_bits[j];
+    }
+  }
+  for (uint32_t q = blockIdx.x; q < fp.n_parts; q += gridDim.x) {
+    const u64 filled = fp.cursor[q];
+    const u64 n = filled < cap ? filled : cap;  // tuples past the capacity were applied by the scan itself
+    if (n == 0) continue;
+    for (uint32_t s = tid; s < S; s += kFoldThreads) {
+      s_rows[s] = 0;
+      s_first[s] = 0xffffffffu;
+#pragma unroll
+      for (int j = 0; j < NOPS; ++j) {
+        s_lo[j * S + s] = 0;
+        s_hi[j * S + s] = 0;
+      }
+      if (!DENSE) s_keys[s] = kEmptyKey;
+    }
+    __syncthreads();
+    const u64* base = fp.tuples + (u64)q * cap;
+    constexpr int U = 4;  // tuples in flight per thread
+    for (u64 b0 = 0; b0 < n; b0 += (u64)kFoldThreads * U) {
+      u64 t[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const u64 i = b0 + (u64)u * kFoldThreads + tid;
+        t[u] = i < n ? __ldcs(base + i) : ~0ull;
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        if (b0 + (u64)u * kFoldThreads + tid >= n) continue;
+        const u64 K = t[u] & kmask;
+        uint32_t slot;
+        if (DENSE) {
+          slot = (uint32_t)K & smask;
+        } else {
+          slot = (uint32_t)(mix64(K) >> 40) & smask;  // (high bits: the low bits chose the partition)
+          uint32_t tries = 0;
+          for (;;) {
+            const u64 cur = s_keys[slot];
+            if (cur == K) break;
+            if (cur == kEmptyKey) {
+              const u64 old = atomicCAS(&s_keys[slot], kEmptyKey, K);
+              if (old == kEmptyKey || old == K) break;
+            }
+            slot = (slot + 1) & smask;
+            if (++tries > smask) { slot = ~0u; break; }
+          }
+        }
+        const uint32_t rel = (uint32_t)((t[u] >> fp.key_bits) & rmask);
+        if (slot == ~0u) {  // more distinct keys than slots in this partition (skew): this tuple goes to the table directly
+          const u64 gs = lean_global_slot(fp.gkeys, fp.gcap, fp.n_keys, K, errbits);
+          u64* w = fp.gwords + gs * fp.n_gwords;
+          for (uint32_t c = 0; c < fp.n_counts; ++c) atomicAdd(&w[fp.count_gword[c]], 1ull);
+          if (fp.first_gword != ~0u) atomicMin(&w[fp.first_gword], fp.row_base + rel);
+#pragma unroll
+          for (int j = 0; j < NOPS; ++j) {
+            const u64 v = (t[u] >> opshift[j]) & opmask[j];
+            if (fp.op_wide[j]) gadd_sum_i128(&w[fp.op_gword[j]], (i128)v);
+            else gadd_sum_i64(&w[fp.op_gword[j]], (i128)v);
+          }
+          continue;
+        }
+        atomicAdd(&s_rows[slot], 1u);
+        atomicMin(&s_first[slot], rel);
+#pragma unroll
+        for (int j = 0; j < NOPS; ++j) {
+          const uint32_t v = (uint32_t)((t[u] >> opshift[j]) & opmask[j]);
+          const uint32_t old = atomicAdd(&s_lo[j * S + slot], v);
+          if (old + v < old) atomicAdd(&s_hi[j * S + slot], 1u);
+        }
+      }
+    }
+    __syncthreads();
+    // every group of the partition, once
+    for (uint32_t s = tid; s < S; s += kFoldThreads) {
+      const uint32_t rows = s_rows[s];
+      if (!rows) continue;
+      const u64 K = DENSE ? (((u64)q << fp.part_shift) | s) : s_keys[s];
+      const u64 gs = lean_global_slot(fp.gkeys, fp.gcap, fp.n_keys, K, errbits);
+      u64* w = fp.gwords + gs * fp.n_gwords;
+      for (uint32_t c = 0; c < fp.n_counts; ++c) atomicAdd(&w[fp.count_gword[c]], (u64)rows);
+      if (fp.first_gword != ~0u) atomicMin(&w[fp.first_gword], fp.row_base + s_first[s]);
+#pragma unroll
+      for (int j = 0; j < NOPS; ++j) {
+        const u64 total = ((u64)s_hi[j * S + s] << 32) | s_lo[j * S + s];
+        if (!total) continue;
+        if (fp.op_wide[j]) gadd_sum_i128(&w[fp.op_gword[j]], (i128)total);
+        else gadd_sum_i64(&w[fp.op_gword[j]], (i128)total);
+      }
+    }
+    __syncthreads();
+  }
+  if (errbits) atomicOr(fp.flags, errbits);
+}
+
+// (the kernel is instantiated for 0, 1, 2 and 4 operands: three use the layout of four)
+uint32_t fold_smem_bytes(uint32_t slots, uint32_t n_ops, bool dense) {
+  const uint32_t ops = n_ops <= 1 ? 1 : (n_ops == 2 ? 2 : 4);
+  return slots * (8u + 8u * ops + (dense ? 0u : 8u));
+}
+
+cudaError_t launch_partition_fold(const FoldPlan& plan, uint32_t grid, cudaStream_t stream) {
+  const uint32_t smem = fold_smem_bytes(plan.slots, plan.n_ops, plan.dense != 0);
+#define LLKV_FOLD_LAUNCH(NOPS, D)                                                                                                   \
+  do {                                                                                                                              \
+    cudaError_t e = cudaFuncSetAttribute(partition_fold_kernel<NOPS, D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);   \
+    if (e != cudaSuccess) return e;                                                                                                 \
+    partition_fold_kernel<NOPS, D><<<grid, kFoldThreads, smem, stream>>>(plan);                                                    \
+    return cudaGetLastError();                                                                                                      \
+  } while (0)
+  if (plan.dense) {
+    if (plan.n_ops == 0) LLKV_FOLD_LAUNCH(0, true);
+    if (plan.n_ops == 1) LLKV_FOLD_LAUNCH(1, true);
+    if (plan.n_ops == 2) LLKV_FOLD_LAUNCH(2, true);
+    if (plan.n_ops <= 4) LLKV_FOLD_LAUNCH(4, true);
+  } else {
+    if (plan.n_ops == 0) LLKV_FOLD_LAUNCH(0, false);
+    if (plan.n_ops == 1) LLKV_FOLD_LAUNCH(1, false);
+    if (plan.n_ops == 2) LLKV_FOLD_LAUNCH(2, false);
+    if (plan.n_ops <= 4) LLKV_FOLD_LAUNCH(4, false);
+  }
+#undef LLKV_FOLD_LAUNCH
+  return cudaErrorInvalidValue;
+}
+
 }  // namespace llkv

@@ -277,8 +277,15 @@ struct LeanShape {
   uint32_t smem_part_off;  // counters [3][kMaxPartitions + 1] u32, then the tile's tuples [n_fields][tile_rows] u64
   uint32_t use_tile_list;  // 1: the launch walks LeanPlan::tile_list (zone-map pruning); part of the shape so that the
                            // specialised dense kernel carries no trace of it
+  // partition == 2, "packed" tuples: key, launch-relative row and the SUM operands of a row fit one 64-bit word
+  // (pack_key_bits | pack_row_bits | pack_op_bits[0] | ...).  The CTA collects the tuples of many tiles in a batch buffer and
+  // scatters a batch at a time into up to kMaxPackedPartitions partitions small enough for partition_fold_kernel to
+  // aggregate in shared memory.  smem_part_off: u32 fill, pad, u32 cnt[parts], u32 base[parts], u64 buf[pack_batch].
+  uint32_t pack_key_bits, pack_row_bits, pack_batch, pack_parts;
+  uint32_t pack_op_bits[8];
 };
 constexpr int kMaxPartitions = 256;
+constexpr int kMaxPackedPartitions = 4096;
 struct LeanPlan {
   LeanShape s;
   long long lits[kMaxLits];
@@ -299,6 +306,7 @@ struct LeanPlan {
   uint32_t* part_cursor;
   unsigned long long part_cap;
   uint32_t part_bits, part_shift;  // partition = (mix64(key) & (gcap - 1)) >> part_shift, 2^part_bits partitions
+  uint32_t part_dense, _pad2;      // packed tuples: 1 = partition = key >> part_shift (dense integer keys: a partition is a key range)
   // zone-map pruning: when set, the launch visits tiles tile_list[0 .. n_tiles) (ascending, >= first_tile) instead of
   // first_tile .. first_tile + n_tiles: the host dropped the tiles whose zones no conjunct range leaf can match
   const uint32_t* tile_list;
@@ -321,6 +329,27 @@ struct PartPlan {
   uint32_t n_parts, n_fields, n_keys, n_gwords, n_nops, n_vops, chunk, chunks_per_part;
   PartOp nops[kLeanMaxWords];       // aggregates without an operand (COUNT, first row)
   PartOp vops[kMaxPartOperands];    // aggregates with one: vops[j] reads tuple field 2 + j
+};
+
+// pass 2 of the packed form (partition_fold_kernel): one CTA aggregates a whole partition in shared memory and writes each
+// group of it to the global table once
+struct FoldPlan {
+  const unsigned long long* tuples;  // partition q: tuples[q * part_cap ..]
+  const uint32_t* cursor;
+  unsigned long long part_cap;
+  unsigned long long* gkeys;
+  unsigned long long* gwords;
+  unsigned long long gcap;
+  uint32_t* flags;
+  unsigned long long row_base;       // row id of launch-relative row 0
+  uint32_t n_parts, n_gwords, n_keys;
+  uint32_t key_bits, row_bits;
+  uint32_t dense, part_shift;        // dense: slot = key & (slots - 1), key = q << part_shift | slot; else a hash table in shared memory
+  uint32_t slots;                    // shared-memory slots per partition (power of two)
+  uint32_t n_ops, n_counts;
+  uint32_t op_bits[8], op_gword[8], op_wide[8];  // SUM operands: bits in the tuple, first global word, 1 = 4-limb global layout
+  uint32_t count_gword[kLeanMaxWords];           // words that count rows (COUNT(*), COUNT(col) of a non-null column)
+  uint32_t first_gword;              // word holding the group's first row id (MIN), ~0u = none
 };
 
 enum : uint32_t {

@@ -123,3 +123,84 @@ def test_group_table_sizes_that_end_on_an_allocation_boundary(gpu_ctx, hint):
             util.assert_same_result(got, want, REL)
     finally:
         dt.destroy()
+
+
+# ---------------------------------------------------------------------------------------------------- packed form
+def packed_table(kind: str, n: int, seed: int):
+    rng = np.random.default_rng(seed)
+    if kind == "dense":       # keys fill a range: partitions are key ranges, slots indexed directly
+        k = rng.integers(-3_000, 47_000, n, dtype=np.int64)
+        hint = 50_000
+    elif kind == "sparse":    # 30 000 distinct keys spread over 2^20: partitions are hash ranges
+        pool = rng.integers(0, 1 << 20, 30_000, dtype=np.int64)
+        k = pool[rng.integers(0, pool.size, n)]
+        hint = 30_000
+    else:                     # half of the rows on one key: its partition overflows into the per-row path
+        k = rng.integers(0, 30_000, n, dtype=np.int64)
+        k[rng.random(n) < 0.5] = 4242
+        hint = 30_000
+    v = rng.integers(0, 1001, n, dtype=np.int64)
+    # (key, 21+ bits of row and both operands share 64 bits; on the skewed table the hot group's sum of w passes 2^32: the carry word)
+    w = rng.integers(0, 1 << (12 if kind == "sparse" else 17), n, dtype=np.int64)
+    t = HostTable(1).add(HostColumn(tpch.K_FIELD, DataType.Int64, k)).add(HostColumn(tpch.V_FIELD, DataType.Int64, v))
+    t.add(HostColumn(3, DataType.Int64, w))
+    return t, hint
+
+
+@pytest.mark.parametrize("kind", ["dense", "sparse", "skewed"])
+def test_packed_partitions_match_oracle(gpu_ctx, kind):
+    """Partitioned GROUP BY with 64-bit packed tuples (LeanTile::scatter_packed + partition_fold_kernel: every partition is
+    aggregated in shared memory) against the oracle, the first partitioned form and the per-row path."""
+    from llkv_b200 import gpu
+    t, hint = packed_table(kind, 400_000, seed=21)
+    specs = tpch.highcard_aggregates() + [AggregateSpec("w", AggregateKind.Sum(3, DataType.Int64)), AggregateSpec("n", AggregateKind.Count(3))]
+    dt = gpu.DeviceTable.from_host(gpu_ctx, t)
+    try:
+        want = oracle.aggregate(t, None, specs, None, (tpch.K_FIELD,), group_capacity=1 << 17)
+        got, info = run(gpu_ctx, dt, None, specs, (tpch.K_FIELD,), hint)
+        assert info.packed_tuples == (2 if kind != "sparse" else 1) and info.partitions >= 2 and info.used_jit_kernel == 1, (info.packed_tuples, info.partitions)
+        util.assert_same_result(got, want, REL)
+        first_form, info1 = run(gpu_ctx, dt, None, specs, (tpch.K_FIELD,), hint, part=3)
+        assert info1.packed_tuples == 0 and info1.partitions >= 2
+        util.assert_same_result(first_form, want, REL)
+        # a filter in front, ragged row ranges
+        flt = tpch.between_filter(tpch.V_FIELD, 100, 800)
+        for lo, hi in ((0, 400_000), (3, 399_990), (123_456, 123_999)):
+            want = oracle.aggregate(t, flt, specs, None, (tpch.K_FIELD,), row_begin=lo, row_end=hi, group_capacity=1 << 17)
+            got, _ = run(gpu_ctx, dt, flt, specs, (tpch.K_FIELD,), hint, lo=lo, hi=hi)
+            util.assert_same_result(got, want, REL)
+    finally:
+        dt.destroy()
+
+
+def test_packed_partitions_in_several_launches_accumulate(gpu_ctx, monkeypatch):
+    """Every launch folds its partitions into the same global table: groups met again in a later launch are added to."""
+    from llkv_b200 import gpu
+    monkeypatch.setenv("LLKV_GPU_PART_BATCH_ROWS", "90000")
+    t, hint = packed_table("dense", 400_000, seed=22)
+    dt = gpu.DeviceTable.from_host(gpu_ctx, t)
+    try:
+        want = oracle.aggregate(t, None, tpch.highcard_aggregates(), None, (tpch.K_FIELD,), group_capacity=1 << 17)
+        got, info = run(gpu_ctx, dt, None, tpch.highcard_aggregates(), (tpch.K_FIELD,), hint)
+        assert info.packed_tuples == 2 and info.kernel_launches >= 8
+        util.assert_same_result(got, want, REL)
+    finally:
+        dt.destroy()
+
+
+def test_plans_the_packed_form_cannot_carry_keep_the_first_form(gpu_ctx):
+    """Signed SUM operands and MIN / MAX have no place in a packed tuple: those plans run partitioned in the first form."""
+    from llkv_b200 import gpu
+    rng = np.random.default_rng(23)
+    n = 200_000
+    t = HostTable(1).add(HostColumn(tpch.K_FIELD, DataType.Int64, rng.integers(0, 20_000, n, dtype=np.int64)))
+    t.add(HostColumn(tpch.V_FIELD, DataType.Int64, rng.integers(-1000, 1001, n, dtype=np.int64)))
+    specs = tpch.highcard_aggregates() + [AggregateSpec("lo", AggregateKind.Min(tpch.V_FIELD, DataType.Int64))]
+    dt = gpu.DeviceTable.from_host(gpu_ctx, t)
+    try:
+        want = oracle.aggregate(t, None, specs, None, (tpch.K_FIELD,), group_capacity=1 << 17)
+        got, info = run(gpu_ctx, dt, None, specs, (tpch.K_FIELD,), 20_000)
+        assert info.packed_tuples == 0 and info.partitions >= 2
+        util.assert_same_result(got, want, REL)
+    finally:
+        dt.destroy()
