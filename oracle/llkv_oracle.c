@@ -1,7 +1,10 @@
 /*
  * llkv_oracle.c — CPU restatement of LLKV's scan -> filter -> MVCC -> aggregate path (see llkv_oracle.h).
- * TEST INFRASTRUCTURE ONLY; never linked into the product.  Parity for arrow-arith/arrow-cast semantics is
- * UNPINNED (crates not vendored in the reference tree); everything else is pinned by tests/golden/.
+ * TEST INFRASTRUCTURE ONLY; never linked into the product.  Pinned by tests/golden/: the reference's own known answers
+ * (reference_known_answers.json) and, for the arithmetic that lives in the arrow crates (not vendored in the reference tree,
+ * no network here), known answers derived from arrow-rs' published rules and cross-checked with Python decimal and pyarrow
+ * (arrow_known_answers.json + make_arrow_golden.py).  Still unpinned: the float total order of arrow-ord and the
+ * integer/float casts of arrow-cast (no vector anywhere).
  *
  * Shape follows the reference, not the GPU design:
  *   leaf scan per predicate  -> Vec<u64> row ids -> bitmap           llkv-column-map/src/store/scan/filter.rs:931-958
@@ -600,7 +603,12 @@ static DT common_type(DT l, DT r) {
 /* i128 -> f64, round to nearest even (Rust `as f64`) */
 static inline double i128_to_f64(i128 v) { return (double)v; }
 
-/* ---- arrow-cast restatement (safe mode: failures become NULL).  UNPINNED (crate not vendored). */
+/* ---- arrow-cast restatement (safe mode: failures become NULL).  The crate is not vendored under /root/reference; the
+ * decimal -> decimal rescale (half away from zero) and the precision-overflow -> NULL rule are pinned by
+ * tests/golden/arrow_known_answers.json (decimal_mul_rescale_rounds_half_away_from_zero,
+ * decimal_mul_precision_overflow_is_null_under_safe_cast, decimal_add_aligns_scales_and_carries_one_digit,
+ * decimal_sub_aligns_scales): values derived from the published rule and cross-checked with Python decimal and pyarrow
+ * (tests/golden/make_arrow_golden.py).  The integer / float casts below have no vector of their own. */
 static int32_t arr_cast(const Arr* in, DT to, Arr* out, Err* e) {
   DT from = dt(in->type, in->p, in->s);
   if (dt_eq(from, to)) { *out = arr_clone(in); return 0; }
@@ -672,7 +680,11 @@ static int32_t arr_cast(const Arr* in, DT to, Arr* out, Err* e) {
   return 0;
 }
 
-/* ---- arrow-arith numeric::{add,sub,mul,div,rem} on equal-typed inputs (kernels.rs:112-137). UNPINNED. */
+/* ---- arrow-arith numeric::{add,sub,mul,div,rem} on equal-typed inputs (kernels.rs:112-137).  Pinned by
+ * tests/golden/arrow_known_answers.json: Decimal128 result types of mul / add / sub (the "intermediate_type" of the decimal
+ * cases, asserted against pyarrow's identical rule by the generator), checked i64 add / sub / mul / div (int64_*_overflow_*,
+ * int64_*_at_the_edge_of_the_range, int64_min_div_minus_one_overflows), truncating division and remainder
+ * (int64_div_truncates_and_zero_divisors_give_null, int64_rem_*). */
 static int32_t arr_arith(const Arr* l, const Arr* r, int op, Arr* out, Err* e) {
   size_t n = l->n;
   if (l->kind == K_NULL) { *out = arr_new(LLKV_PT_NULL, 0, 0, n); return 0; }
@@ -742,7 +754,8 @@ static int32_t arr_arith(const Arr* l, const Arr* r, int op, Arr* out, Err* e) {
   return 0;
 }
 
-/* compute_binary (kernels.rs:99-177): coerce to the common type, zeros -> NULL before div */
+/* compute_binary (kernels.rs:99-177): coerce to the common type, zeros -> NULL before div
+ * (vector: int64_div_truncates_and_zero_divisors_give_null; rem keeps its zeros: int64_rem_by_zero_is_an_error) */
 static int32_t compute_binary(const Arr* l, const Arr* r, int op, Arr* out, Err* e) {
   DT ct = common_type(dt(l->type, l->p, l->s), dt(r->type, r->p, r->s));
   Arr lc, rc;
@@ -763,7 +776,9 @@ static int32_t compute_binary(const Arr* l, const Arr* r, int op, Arr* out, Err*
   return rcode;
 }
 
-/* arrow-ord cmp::{eq,neq,lt,lt_eq,gt,gt_eq}: floats use IEEE totalOrder. UNPINNED. */
+/* arrow-ord cmp::{eq,neq,lt,lt_eq,gt,gt_eq}: floats use IEEE totalOrder.  Integer / decimal comparisons are pinned through the
+ * reference's own filter fixtures (tests/golden/reference_known_answers.json, llkv-table/src/table.rs:2206-2355,2829-2906);
+ * the float total order (NaN handling) has no reference-held vector: UNPINNED for that part only. */
 static inline int64_t f64_total_key(double d) {
   int64_t b;
   memcpy(&b, &d, 8);
