@@ -295,8 +295,9 @@ def run_ours(args):
         info = agg.run_info()
         agg.destroy()
         prog.destroy()
-        return {"seconds": dt, "kernel_ms": kernel_ms, "merge_ms": statistics.mean(merge_ms) if merge_ms and world > 1 else None, "launches": launches,
-                "info": info, "result": merged}
+        # the merge kernel's device time on every rank (it includes waiting for the slowest peer's scan)
+        merge_all = gather(statistics.mean(merge_ms)) if merge_ms and world > 1 else None
+        return {"seconds": dt, "kernel_ms": kernel_ms, "merge_ms": merge_all, "launches": launches, "info": info, "result": merged}
 
     failed = None
     sampler = ClockSampler(local)

@@ -907,34 +907,64 @@ struct LeanTile {
       if constexpr (in.op != FO_END && PC + 1 < kMaxFastInstr) apply_packed<PC + 1>(t, gs, row, next);
     }
   }
+  // Shared-memory layout of the packed form (smem_part_off): u32 fill, u32 pad, u32 off[parts], u32 gdelta[parts],
+  // u64 buf[pack_batch], u16 order[pack_batch].
   __device__ __forceinline__ void flush_packed() {
     if constexpr (Cfg::kPacked) {
       uint32_t* const s_fill = reinterpret_cast<uint32_t*>(part_smem);
       const uint32_t P = S.pack_parts;
-      uint32_t* const cnt = s_fill + 2;
-      uint32_t* const gbase = cnt + P;
-      const u64* const buf = reinterpret_cast<const u64*>(gbase + P);
+      uint32_t* const off = s_fill + 2;     // per partition: count, then first sorted position, then one past its last
+      uint32_t* const gdelta = off + P;     // reserved position in the partition's global stream minus its first sorted position
+      const u64* const buf = reinterpret_cast<const u64*>(gdelta + P);
+      unsigned short* const order = reinterpret_cast<unsigned short*>(const_cast<u64*>(buf) + S.pack_batch);
+      uint32_t* const s_scan = reinterpret_cast<uint32_t*>(order + S.pack_batch);  // one partial sum per consumer warp
       lean_consumer_barrier(NC);  // every append of the batch is in the buffer
       const uint32_t n = *s_fill;
-      for (uint32_t q = (uint32_t)tid; q < P; q += (uint32_t)NC) cnt[q] = 0;
+      for (uint32_t q = (uint32_t)tid; q < P; q += (uint32_t)NC) off[q] = 0;
       lean_consumer_barrier(NC);
       if (tid == 0) *s_fill = 0;
-      for (uint32_t i = (uint32_t)tid; i < n; i += (uint32_t)NC) atomicAdd(&cnt[part_of_packed(buf[i])], 1u);
+      for (uint32_t i = (uint32_t)tid; i < n; i += (uint32_t)NC) atomicAdd(&off[part_of_packed(buf[i])], 1u);
       lean_consumer_barrier(NC);
-      for (uint32_t q = (uint32_t)tid; q < P; q += (uint32_t)NC) {
-        const uint32_t c = cnt[q];
-        gbase[q] = c ? atomicAdd(&p.part_cursor[q], c) : 0u;
-        cnt[q] = 0;
+      // exclusive prefix of the counts (every thread owns a contiguous share of the partitions) + one global atomic per
+      // non-empty partition reserving the batch's share of its stream
+      {
+        const uint32_t per = (P + (uint32_t)NC - 1) / (uint32_t)NC;
+        const uint32_t lo = (uint32_t)tid * per, hi = lo + per < P ? lo + per : P;
+        uint32_t sum = 0;
+        for (uint32_t q = lo; q < hi; ++q) sum += off[q];
+        const int lane = tid & 31, wid = tid >> 5;
+        uint32_t inc = sum;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const uint32_t y = __shfl_up_sync(LLKV_FULL, inc, o);
+          if (lane >= o) inc += y;
+        }
+        if (lane == 31) s_scan[wid] = inc;
+        lean_consumer_barrier(NC);
+        uint32_t wbase = 0;
+        for (int w = 0; w < wid; ++w) wbase += s_scan[w];
+        uint32_t run = wbase + inc - sum;
+        for (uint32_t q = lo; q < hi; ++q) {
+          const uint32_t c = off[q];
+          const uint32_t g = c ? atomicAdd(&p.part_cursor[q], c) : 0u;
+          off[q] = run;
+          gdelta[q] = g - run;
+          run += c;
+        }
       }
       lean_consumer_barrier(NC);
+      // sorted order: position -> index of the tuple in the buffer
+      for (uint32_t i = (uint32_t)tid; i < n; i += (uint32_t)NC) order[atomicAdd(&off[part_of_packed(buf[i])], 1u)] = (unsigned short)i;
+      lean_consumer_barrier(NC);
+      // consecutive threads write consecutive tuples of a partition: whole sectors, few pages per warp
       const u64 cap = p.part_cap;
       const uint32_t kb = S.pack_key_bits, rb = S.pack_row_bits;
-      for (uint32_t i = (uint32_t)tid; i < n; i += (uint32_t)NC) {
-        const u64 t = buf[i];
+      for (uint32_t j = (uint32_t)tid; j < n; j += (uint32_t)NC) {
+        const u64 t = buf[order[j]];
         const uint32_t q = part_of_packed(t);
-        const u64 j = (u64)gbase[q] + atomicAdd(&cnt[q], 1u);
-        if (j < cap) {
-          __stcs(&p.part_out[(u64)q * cap + j], t);  // read once, by the next kernel
+        const u64 pos = (u64)(uint32_t)(gdelta[q] + j);
+        if (pos < cap) {
+          __stcs(&p.part_out[(u64)q * cap + pos], t);  // read once, by the next kernel
         } else {
           const u64 K = t & ((1ull << kb) - 1);
           const u64 gs = lean_global_slot(p.gkeys, p.gcap, S.n_keys, K, errbits);

@@ -1874,8 +1874,9 @@ static int32_t lean_geometry(const LeanTune& tn, const Plan& p, uint64_t row_beg
     const uint32_t per_cta = budget_total / ctas - 1024;
     if (s.partition == 2) {  // fill word, counters and reserved bases per partition, then the batch buffer: as large as fits
       uint32_t B = 16384;
+      if (const char* e = getenv("LLKV_GPU_PACK_BATCH")) B = (uint32_t)std::max<long>(2 * T, strtol(e, nullptr, 10));  // experiments
       for (; B >= 2 * T; B /= 2) {
-        part_bytes = align_up(8u + 2u * s.pack_parts * 4u + B * 8u, 128);
+        part_bytes = align_up(8u + 2u * s.pack_parts * 4u + B * 8u + B * 2u + 64u * 4u, 128);  // + sorted order (u16) + warp partial sums
         if (per_cta >= 128 + acc_bytes + tmp_bytes + tbl_bytes + part_bytes + 2 * stage_bytes) break;
       }
       if (B < 2 * T) return 0;
@@ -1923,6 +1924,8 @@ static int32_t lean_geometry(const LeanTune& tn, const Plan& p, uint64_t row_beg
     const uint32_t Rs[4] = {8, 4, 2, 1};
     for (int ri = 0; ri < 4; ++ri) {
       if (want_R ? Rs[ri] != want_R : (Rs[ri] == 1 && best_score)) continue;
+      // (packed: one CTA per SM, all of the shared memory for the batch buffer — what counts is the length of the sorted runs
+      // a flush writes per partition: 16384 tuples over 1221 partitions measured 2.7 ms per 2^28 rows, 2 CTAs x 4096 5.7 ms)
       for (uint32_t ctas = tn.packed ? 1 : 4; ctas >= 1; --ctas) {
         const uint32_t c = want_ctas ? want_ctas : ctas;
         const uint32_t st = layout(Rs[ri], c, fg, nc);

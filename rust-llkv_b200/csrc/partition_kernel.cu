@@ -157,7 +157,7 @@ cudaError_t launch_partition_apply(const PartPlan& plan, uint32_t grid, cudaStre
 // go through an open-addressing table of the partition's keys in shared memory.  When the partition is done each group
 // is written to the global table once: the per-row global atomics of the first form (1.2 probes + 3 REDs per row, bound by
 // L2 request rate) become one insert per group and launch.
-constexpr int kFoldThreads = 512;
+constexpr int kFoldThreads = 1024;
 
 template <int NOPS, bool DENSE>
 __global__ void __launch_bounds__(kFoldThreads, 1) partition_fold_kernel(const __grid_constant__ FoldPlan fp) {
@@ -199,13 +199,22 @@ __global__ void __launch_bounds__(kFoldThreads, 1) partition_fold_kernel(const _
     }
     __syncthreads();
     const u64* base = fp.tuples + (u64)q * cap;
-    constexpr int U = 4;  // tuples in flight per thread
+    constexpr int U = 4;  // tuples per thread and round; the next round's loads are in flight while this one is folded
+    u64 nxt[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const u64 i = (u64)u * kFoldThreads + tid;
+      nxt[u] = i < n ? __ldcs(base + i) : ~0ull;
+    }
     for (u64 b0 = 0; b0 < n; b0 += (u64)kFoldThreads * U) {
       u64 t[U];
 #pragma unroll
+      for (int u = 0; u < U; ++u) t[u] = nxt[u];
+      const u64 b1 = b0 + (u64)kFoldThreads * U;
+#pragma unroll
       for (int u = 0; u < U; ++u) {
-        const u64 i = b0 + (u64)u * kFoldThreads + tid;
-        t[u] = i < n ? __ldcs(base + i) : ~0ull;
+        const u64 i = b1 + (u64)u * kFoldThreads + tid;
+        nxt[u] = i < n ? __ldcs(base + i) : ~0ull;
       }
 #pragma unroll
       for (int u = 0; u < U; ++u) {
