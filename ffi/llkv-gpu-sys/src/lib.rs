@@ -98,7 +98,8 @@ pub struct llkv_debug_column {
     pub max_value: i64,
     pub n_rows: u64,
     pub max_strlen: u8,
-    pub _pad: [u8; 7],
+    pub nullable: u8,
+    pub _pad: [u8; 6],
 }
 
 /// ChunkMetadata (llkv-column-map/src/store/descriptor.rs:23-32).

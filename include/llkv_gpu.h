@@ -483,7 +483,8 @@ typedef struct llkv_debug_column {
   int64_t min_value, max_value;
   uint64_t n_rows;
   uint8_t max_strlen;    /* Utf8 */
-  uint8_t _pad[7];
+  uint8_t nullable;      /* the column carries a validity bitmap */
+  uint8_t _pad[6];
 } llkv_debug_column;
 int32_t llkv_gpu_debug_plan(const llkv_debug_column* cols, int32_t n_cols, const llkv_gpu_program* prog, int32_t created_by_col,
                             int32_t deleted_by_col, uint64_t txn_id, uint64_t snapshot_id, const llkv_agg_spec* specs, int32_t n_aggs,

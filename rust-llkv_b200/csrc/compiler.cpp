@@ -1678,6 +1678,7 @@ class Emitter {
     uint8_t col = 0, load = 0, tmp = 0;
     uint32_t lit = 0;
     Iv iv;
+    uint32_t nm = 0;  // plan columns whose NULLs make this value NULL
   };
 
   bool lower_fast() {
@@ -1685,7 +1686,6 @@ class Emitter {
     if (wide_ || req_.bitmap_mode) return false;
     if (plan_cols_.empty()) return false;  // nothing to stream (COUNT(*) without a filter): no tiles for the lean pipeline
     for (const ColumnMeta* c : plan_cols_) {
-      if (c->nullable) return false;
       if (c->load_kind == LK_D128 && !c->dec_fits_i64) return false;
     }
     std::vector<FInstr> f;
@@ -1799,7 +1799,15 @@ class Emitter {
           // typed leaf at the top level: PUSH_COL, PRED_*, FILTER
           if (i + 2 < n && code_[i + 2].op == OP_FILTER && i + 2 < select_end_) {
             const Instr& pr = code_[i + 1];
-            if (pr.op == OP_PRED_ALL || pr.op == OP_PRED_NOTNULL) { i += 2; break; }  // every row present: always true
+            // NULL never satisfies a typed predicate: a nullable column's leaf starts from its valid rows
+            if (c.nullable && pr.op != OP_PRED_ISNULL && (pr.op == OP_PRED_ALL || pr.op == OP_PRED_NOTNULL || pr.op == OP_PRED_I || pr.op == OP_PRED_U || pr.op == OP_PRED_D))
+              femit(FO_VALID, in.a, 0, 0);
+            if (pr.op == OP_PRED_ALL || pr.op == OP_PRED_NOTNULL) { i += 2; break; }  // every (valid) row: always true
+            if (pr.op == OP_PRED_ISNULL && c.nullable) {
+              femit(FO_VALID, in.a, 1, 0);
+              i += 2;
+              break;
+            }
             if (pr.op == OP_PRED_I || pr.op == OP_PRED_U || pr.op == OP_PRED_D || pr.op == OP_PRED_ISNULL) {
               const bool uns = pr.op == OP_PRED_U;
               i128 tmin, tmax;
@@ -1854,6 +1862,7 @@ class Emitter {
           x.col = in.a;
           x.load = in.b;
           x.iv = column_interval(c);
+          x.nm = c.nullable ? (1u << in.a) : 0u;
           st.push_back(x);
           break;
         }
@@ -1885,19 +1894,25 @@ class Emitter {
           if (iv_fits_i64(r)) fb = k == 0 ? FB_ADD : k == 1 ? FB_SUB : (iv_fits_i32(a) && iv_fits_i32(b) ? FB_MUL32 : FB_MUL);
           else if (is_d) fb = k == 0 ? FB_ADD_CK : k == 1 ? FB_SUB_CK : FB_MUL_CK;  // overflow -> rerun on the 128-bit interpreter
           else return false;  // a real i64 overflow is an error with its own message: general interpreter
+          // (a checked operation would also look at the garbage under a NULL: nullable operands keep to proven ranges)
+          const uint32_t nm = st[st.size() - 1].nm | st[st.size() - 2].nm;
+          if (nm && (fb == FB_ADD_CK || fb == FB_SUB_CK || fb == FB_MUL_CK)) return false;
           emit_binary(fb);
           st.pop_back();
           st.back().where = Sym::ACC;
           st.back().iv = iv_fits_i64(r) ? r : Iv();
+          st.back().nm = nm;
           break;
         }
         case OP_ADD_F: case OP_SUB_F: case OP_MUL_F: {
           if (st.size() < 2) return false;
+          const uint32_t nm = st[st.size() - 1].nm | st[st.size() - 2].nm;
           emit_binary(in.op == OP_ADD_F ? FB_ADD_F : in.op == OP_SUB_F ? FB_SUB_F : FB_MUL_F);
           st.pop_back();
           st.back().where = Sym::ACC;
           st.back().iv = Iv();
           st.back().iv.is_float = true;
+          st.back().nm = nm;
           break;
         }
         case OP_CAST_D_DOWN: {
@@ -1947,14 +1962,17 @@ class Emitter {
           st.back().iv.is_float = true;
           break;
         }
-        case OP_MVCC: femit(FO_MVCC, in.a, in.b, 0); break;
+        case OP_MVCC:
+          if (plan_cols_[in.a]->nullable || plan_cols_[in.b]->nullable) return false;  // (NULL created_by / deleted_by have their own defaults)
+          femit(FO_MVCC, in.a, in.b, 0);
+          break;
         case OP_SELECT_DONE: femit(FO_SELECT_DONE, 0, 0, 0); break;
         case OP_GROUP: {
           const int nk = in.a;
           if ((int)st.size() < nk) return false;
           for (int k = nk - 1; k >= 0; --k) {
             const Sym x = st.back();
-            if (x.where != Sym::COL) return false;
+            if (x.where != Sym::COL || x.nm) return false;  // (a NULL key is its own group: general interpreter)
             st.pop_back();
             p.key_col[k] = x.col;
             p.key_load[k] = (uint8_t)map_load(x.load);
@@ -2008,6 +2026,7 @@ class Emitter {
           lean_word(in.b, width, rowrel);
           if (op != FO_COUNT && op != FO_FIRSTVALID) load_acc(st.size() - 1);  // counts do not look at the value
           femit(op, a, in.b, in.c);
+          f.back().h = st.back().nm;
           if (op == FO_SUM) {  // operand proven in [0, 2^32): its width in bits (packed tuples of a partitioned GROUP BY)
             const Iv& v = st.back().iv;
             if (v.known && v.lo >= 0 && v.hi < ((i128)1 << 32)) {

@@ -229,6 +229,25 @@ struct LeanTile {
     }
   }
 
+  // validity of this thread's R rows in one column's staged bitmap tile: row r * NC + tid is bit (tid & 31) of 32-bit word
+  // r * (NC / 32) + tid / 32, the same word for the whole warp (one broadcast read per row slot)
+  __device__ __forceinline__ unsigned bits_of(const unsigned char* tile) const {
+    const uint32_t* w = reinterpret_cast<const uint32_t*>(tile) + (tid >> 5);
+    unsigned m = 0;
+#pragma unroll
+    for (int r = 0; r < R; ++r) m |= ((w[r * (NC >> 5)] >> (tid & 31)) & 1u) << r;
+    return m;
+  }
+  __device__ __forceinline__ unsigned col_valid(uint32_t col) const { return bits_of(sb + S.cols[col].vsmem_off); }
+  // rows on which every column of `cols` (bit c = plan column c) is valid
+  __device__ __forceinline__ unsigned valid_mask(uint32_t cols) const {
+    unsigned m = (1u << R) - 1u;
+#pragma unroll
+    for (uint32_t c = 0; c < (uint32_t)kMaxCols; ++c)
+      if ((cols >> c) & 1u) m &= col_valid(c);
+    return m;
+  }
+
   // acc = acc op other  (rev: other op acc)
   __device__ __forceinline__ void binop(uint32_t opr, const i64 (&o)[R]) {
     const bool rev = (opr & FB_REV) != 0;
@@ -338,6 +357,7 @@ struct LeanTile {
         if (row >= begin_rel && row < end_rel) actm |= 1u << r;
       }
     }
+    if (S.has_exists) actm &= bits_of(sb + S.exists_smem_off);  // row ids nobody holds (deleted rows, gaps) are not rows
 #pragma unroll
     for (int r = 0; r < R; ++r) {
       acc[r] = 0;
@@ -652,8 +672,9 @@ struct LeanTile {
       // CTA-local slot and word.  Ungrouped plans fold the thread's R rows in registers first.  Grouped plans update
       // per row (emit): at once when interpreted, deferred to the end of the tile when specialised (see flush()).
       case FO_COUNT_STAR: case FO_COUNT: if constexpr (live<PC>(FO_COUNT_STAR) || live<PC>(FO_COUNT)) {
-        if (has_slow) slow_rows(in.op, in.a, negm, in.c);
-        const unsigned okm = actm & ~negm;
+        const unsigned lv = in.h ? (actm & valid_mask(in.h)) : actm;  // rows whose operand is not NULL
+        if (has_slow) slow_rows(in.op, in.a, negm & lv, in.c);
+        const unsigned okm = lv & ~negm;
         const LeanWord lw = S.words[in.b];
         if (!grouped) {
           const unsigned c = __popc(okm);
@@ -668,7 +689,7 @@ struct LeanTile {
         return true;
       }
       case FO_FIRSTROW: case FO_FIRSTVALID: case FO_FIRSTNAN: if constexpr (live<PC>(FO_FIRSTROW) || live<PC>(FO_FIRSTVALID) || live<PC>(FO_FIRSTNAN)) {
-        unsigned setm = actm;
+        unsigned setm = in.h ? (actm & valid_mask(in.h)) : actm;
         if (in.op == FO_FIRSTNAN) {
 #pragma unroll
           for (int r = 0; r < R; ++r) {
@@ -686,17 +707,18 @@ struct LeanTile {
       }
       case FO_SUM: if constexpr (live<PC>(FO_SUM)) {
         const uint32_t cls = in.a & 3;  // 0: check each value
-        unsigned fastm = actm & ~negm;
+        const unsigned lv = in.h ? (actm & valid_mask(in.h)) : actm;  // rows whose operand is not NULL
+        unsigned fastm = lv & ~negm;
         if (cls == 0 && !Cfg::kPartition) {  // (tuples carry the full value; the table update is exact for any i64)
           unsigned bigm = 0;
 #pragma unroll
           for (int r = 0; r < R; ++r)
             if (!(acc[r] < ((i64)1 << 47) && acc[r] > -((i64)1 << 47))) bigm |= 1u << r;
-          bigm &= actm;
-          slow_rows(FO_SUM, in.a, bigm | negm, in.c);
+          bigm &= lv;
+          slow_rows(FO_SUM, in.a, bigm | (negm & lv), in.c);
           fastm &= ~bigm;
         } else if (has_slow) {
-          slow_rows(FO_SUM, in.a, negm, in.c);
+          slow_rows(FO_SUM, in.a, negm & lv, in.c);
         }
         const LeanWord lw = S.words[in.b];
         if (!grouped) {
@@ -715,8 +737,9 @@ struct LeanTile {
         return true;
       }
       case FO_FSUM: if constexpr (live<PC>(FO_FSUM)) {
-        if (has_slow) slow_rows(FO_FSUM, in.a, negm, in.c);
-        const unsigned okm = actm & ~negm;
+        const unsigned lv = in.h ? (actm & valid_mask(in.h)) : actm;
+        if (has_slow) slow_rows(FO_FSUM, in.a, negm & lv, in.c);
+        const unsigned okm = lv & ~negm;
         const LeanWord lw = S.words[in.b];
         if (!grouped) {
           double x = 0.0;
@@ -735,7 +758,7 @@ struct LeanTile {
       }
       case FO_MIN_I: case FO_MAX_I: case FO_MIN_F: case FO_MAX_F: if constexpr (live<PC>(FO_MIN_I) || live<PC>(FO_MAX_I) || live<PC>(FO_MIN_F) || live<PC>(FO_MAX_F)) {
         const bool is_f = in.op == FO_MIN_F || in.op == FO_MAX_F;
-        unsigned setm = actm;
+        unsigned setm = in.h ? (actm & valid_mask(in.h)) : actm;
         u64 e[R];
 #pragma unroll
         for (int r = 0; r < R; ++r) {
@@ -748,6 +771,11 @@ struct LeanTile {
         if (has_slow) slow_rows(in.op, in.a, setm & negm, in.c);
         setm &= ~negm;
         emit<PC>(in, setm, e);  // also the ungrouped case: soff[] is zero
+        return true;
+      }
+      case FO_VALID: if constexpr (live<PC>(FO_VALID)) {
+        const unsigned v = col_valid(in.a);
+        actm &= in.b ? ~v : v;
         return true;
       }
       case FO_END:
@@ -1164,8 +1192,10 @@ __device__ __forceinline__ void lean_body(const LeanPlan& p) {
           if (c < S.n_cols) {
             const uint32_t bytes = T * S.cols[c].elem_bytes;
             bulk_g2s(sbuf + S.cols[c].smem_off, reinterpret_cast<const unsigned char*>(p.col_base[c]) + tile * (u64)bytes, bytes, &full_bar[s]);
+            if (S.cols[c].has_valid) bulk_g2s(sbuf + S.cols[c].vsmem_off, p.col_valid[c] + tile * (u64)(T >> 3), T >> 3, &full_bar[s]);
           }
         }
+        if (S.has_exists) bulk_g2s(sbuf + S.exists_smem_off, p.exists_bits + tile * (u64)(T >> 3), T >> 3, &full_bar[s]);
         if (++s == ST) {
           s = 0;
           ++round;

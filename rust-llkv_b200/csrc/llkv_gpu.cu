@@ -1734,7 +1734,8 @@ static bool partition_eligible(const Plan& p) {
       continue;
     }
     if (!after_group) continue;
-    if (op == FO_LEAF || op == FO_MVCC || op == FO_SELECT_DONE || op == FO_MIN_F || op == FO_MAX_F || op == FO_FIRSTNAN) return false;
+    if (op == FO_LEAF || op == FO_MVCC || op == FO_SELECT_DONE || op == FO_MIN_F || op == FO_MAX_F || op == FO_FIRSTNAN || op == FO_VALID) return false;
+    if (op >= FO_COUNT_STAR && op <= FO_FIRSTNAN && p.fcode[i].h) return false;  // (tuples carry no per-aggregate NULL mask)
     if (lean_takes_operand(op)) ++fields;
   }
   return after_group && fields <= 2 + (uint32_t)kMaxPartOperands;
@@ -1787,10 +1788,16 @@ static int32_t lean_geometry(const LeanTune& tn, const Plan& p, uint64_t row_beg
   for (uint32_t i = 0; i < p.n_finstr; ++i) s.code[i] = p.fcode[i];
   for (uint32_t i = 0; i < p.n_lits; ++i) lp.lits[i] = (long long)p.lits[i].lo;
   s.n_cols = p.n_cols;
+  bool any_bits = p.exists_bits != nullptr;
   for (uint32_t c = 0; c < p.n_cols; ++c) {
     lp.col_base[c] = p.cols[c].base;
+    lp.col_valid[c] = p.cols[c].validity;
     s.cols[c].elem_bytes = p.cols[c].elem_bytes;
+    s.cols[c].has_valid = p.cols[c].validity ? 1u : 0u;
+    any_bits = any_bits || p.cols[c].validity;
   }
+  lp.exists_bits = p.exists_bits;
+  s.has_exists = p.exists_bits ? 1u : 0u;
   lp.txn_id = p.txn_id;
   lp.snapshot_id = p.snapshot_id;
   // TXN_ID_AUTO_COMMIT (1) is always committed (llkv-transaction/src/mvcc.rs:157-171): never listed for the kernel
@@ -1858,10 +1865,21 @@ static int32_t lean_geometry(const LeanTune& tn, const Plan& p, uint64_t row_beg
   auto layout = [&](uint32_t R, uint32_t ctas, uint32_t fg, uint32_t nc) -> uint32_t {
     const uint32_t T = nc * R;
     uint32_t stage_bytes = 0, tx = 0;
+    if (any_bits && (T % 128u)) return 0;  // bitmap tiles travel as bulk copies of T / 8 bytes: multiples of 16
     for (uint32_t c = 0; c < p.n_cols; ++c) {
       s.cols[c].smem_off = stage_bytes;
       stage_bytes += align_up(T * s.cols[c].elem_bytes, 128);
       tx += T * s.cols[c].elem_bytes;
+      if (s.cols[c].has_valid) {
+        s.cols[c].vsmem_off = stage_bytes;
+        stage_bytes += align_up(T / 8, 128);
+        tx += T / 8;
+      }
+    }
+    if (s.has_exists) {
+      s.exists_smem_off = stage_bytes;
+      stage_bytes += align_up(T / 8, 128);
+      tx += T / 8;
     }
     uint32_t woff = 0;
     for (uint32_t w = 0; w < s.n_words; ++w) {
@@ -2010,7 +2028,7 @@ static int32_t build_request(llkv_gpu_ctx* ctx, uint64_t table_id, const llkv_gp
 static const char* fast_op_name(uint32_t op) {
   static const char* names[] = {"END", "LEAF", "MVCC", "SELECT_DONE", "GROUP", "LD_COL", "LD_LIT", "LD_TMP", "ST_TMP", "OP_COL", "OP_LIT",
                                 "OP_TMP", "DIVR", "MULP", "I2F", "D2F", "COUNT_STAR", "COUNT", "FIRSTROW", "SUM", "FSUM", "MIN_I", "MAX_I",
-                                "MIN_F", "MAX_F", "FIRSTVALID", "FIRSTNAN"};
+                                "MIN_F", "MAX_F", "FIRSTVALID", "FIRSTNAN", "VALID"};
   return op < sizeof(names) / sizeof(names[0]) ? names[op] : "?";
 }
 static std::string lean_listing(const LeanPlan& lp, const Geometry& g, uint32_t ctas) {
@@ -2075,7 +2093,8 @@ extern "C" int32_t llkv_gpu_debug_plan(const llkv_debug_column* cols, int32_t n_
     m.type = d.prim_type;
     m.precision = d.precision;
     m.scale = d.scale;
-    m.nullable = false;
+    m.nullable = d.nullable != 0;
+    if (m.nullable) m.dev_validity = reinterpret_cast<const unsigned char*>((uintptr_t)0x2000);  // never dereferenced here
     m.load_kind = device_load_kind(d.prim_type);
     m.elem_bytes = device_elem_bytes(d.prim_type);
     if (m.elem_bytes == 0) return set_error(LLKV_ERR_INVALID_ARGUMENT, "column type %d does not cross this boundary", d.prim_type);

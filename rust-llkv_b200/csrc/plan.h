@@ -108,6 +108,7 @@ enum FastOp : uint16_t {
                   // accumulator stays exact over 2^15 rows per thread and launch), 0 -> not proven (checked per value);
                   // a bit7 = 4-limb global layout
   FO_FSUM, FO_MIN_I, FO_MAX_I, FO_MIN_F, FO_MAX_F, FO_FIRSTVALID, FO_FIRSTNAN,
+  FO_VALID,       // a = column, b = 0: active &= row is valid (not NULL) in the column / 1: active &= row is NULL in it
   FO_COUNT_
 };
 #if defined(__CUDACC__) || defined(__CUDACC_RTC__)
@@ -160,7 +161,8 @@ struct Instr {
 struct FInstr {  // lean-kernel instruction, pre-decoded (two 16-byte shared-memory loads, no field unpacking)
   uint32_t op, a, b, c;
   uint32_t d, e, f;  // fused operand pre-load: d = 0 none / 1 acc = literal e / 2 acc = column e of FastLoad f / 3 acc = tmp e
-  uint32_t g;        // FO_LEAF: 1 = unsigned comparison
+  uint32_t g;        // FO_LEAF: 1 = unsigned comparison; FO_SUM: operand width in bits when proven in [0, 2^32), else 0
+  uint32_t h;        // aggregates: bit c = the operand is NULL where plan column c is NULL (the row is then skipped)
 };
 // physical layouts the lean kernel reads (everything else stays on the general interpreter)
 enum FastLoad : uint32_t { LKF_4 = 0, LKF_8 = 1, LKF_16 = 2, LKF_1 = 3, LKF_S1 = 4 };
@@ -237,6 +239,7 @@ struct Plan {
   unsigned long long* out_count;  // bitmap_mode: number of selected rows
   unsigned long long row_origin;  // row id of the columns' position 0: first-row words hold row ids, so shards of one table merge into
                                   // the table's first-appearance order
+  const unsigned char* exists_bits;  // row-id-sparse tables: bit i = a row with id row_origin + i exists (null: every position is a row)
 };
 
 // ---- the lean kernel's view of a plan (lean_kernel.cuh): passed by value as a __grid_constant__ kernel parameter, so the
@@ -247,7 +250,9 @@ constexpr int kLeanMaxWords = 48;
 constexpr uint32_t kLeanRowsPerThreadLog2 = 15;  // a thread folds at most 2^15 rows per launch (keeps narrow accumulators exact)
 struct LeanCol {
   uint32_t elem_bytes;
-  uint32_t smem_off;  // byte offset of this column's tile inside a stage
+  uint32_t smem_off;   // byte offset of this column's tile inside a stage
+  uint32_t has_valid;  // the column has a validity bitmap: tile_rows / 8 bytes of it are staged with every tile
+  uint32_t vsmem_off;  // ... at this byte offset inside a stage
 };
 struct LeanWord {
   uint32_t kind;    // FastKind
@@ -283,6 +288,8 @@ struct LeanShape {
   // aggregate in shared memory.  smem_part_off: u32 fill, pad, u32 cnt[parts], u32 base[parts], u64 buf[pack_batch].
   uint32_t pack_key_bits, pack_row_bits, pack_batch, pack_parts;
   uint32_t pack_op_bits[8];
+  // row-id-sparse tables: bit i of LeanPlan::exists_bits = a row with id (origin + i) exists; staged like a validity tile
+  uint32_t has_exists, exists_smem_off;
 };
 constexpr int kMaxPartitions = 256;
 constexpr int kMaxPackedPartitions = 4096;
@@ -290,6 +297,8 @@ struct LeanPlan {
   LeanShape s;
   long long lits[kMaxLits];
   const void* col_base[kMaxCols];
+  const unsigned char* col_valid[kMaxCols];  // validity bitmaps (LSB first) of the columns with LeanCol::has_valid
+  const unsigned char* exists_bits;
   unsigned long long noncommitted[kMaxNoncommitted];
   unsigned long long key_min[kMaxKeys];
   unsigned long long txn_id, snapshot_id;

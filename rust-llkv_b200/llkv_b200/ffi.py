@@ -82,7 +82,7 @@ class RunInfo(C.Structure):
 class DebugColumn(C.Structure):
     _fields_ = [("logical_field_id", C.c_uint64), ("prim_type", C.c_int32), ("precision", C.c_uint8), ("scale", C.c_int8),
                 ("has_minmax", C.c_uint8), ("dec_fits_i64", C.c_uint8), ("min_value", C.c_int64), ("max_value", C.c_int64),
-                ("n_rows", C.c_uint64), ("max_strlen", C.c_uint8), ("_pad", C.c_uint8 * 7)]
+                ("n_rows", C.c_uint64), ("max_strlen", C.c_uint8), ("nullable", C.c_uint8), ("_pad", C.c_uint8 * 6)]
 
 
 def i128_to_words(v: int):

@@ -480,9 +480,8 @@ def debug_plan(table: HostTable, expr: Optional[Expr], specs: Sequence[Aggregate
         lfids += [logical_field_id(table.table_id, 0xFFFFFFFF, NS_TXN_CREATED_BY), logical_field_id(table.table_id, 0xFFFFFFFE, NS_TXN_DELETED_BY)]
     arr = (ffi.DebugColumn * len(host_cols))()
     for i, (c, lfid) in enumerate(zip(host_cols, lfids)):
-        if c.validity is not None:
-            raise ValueError("debug_plan describes non-nullable columns only")
         d = arr[i]
+        d.nullable = int(c.validity is not None)
         d.logical_field_id = lfid
         d.prim_type = c.dtype.type
         d.precision = c.dtype.precision
