@@ -228,6 +228,11 @@ extern "C" {
     pub fn llkv_gpu_column_flush(col: *mut llkv_gpu_column) -> i32;
     pub fn llkv_gpu_column_seal(col: *mut llkv_gpu_column) -> i32;
     pub fn llkv_gpu_column_h2d_bytes(col: *const llkv_gpu_column, out_bytes: *mut u64) -> i32;
+    /// `ColumnStore::delete_rows`: the rows become gaps of the resident image.
+    pub fn llkv_gpu_column_delete_rows(col: *mut llkv_gpu_column, row_ids: *const u64, n: u64) -> i32;
+    pub fn llkv_gpu_column_present_rows(col: *mut llkv_gpu_column, out_rows: *mut u64) -> i32;
+    /// `gather_rows` with `GatherNullPolicy::IncludeNulls`: values in request order, `out_valid[i] == 0` for absent rows.
+    pub fn llkv_gpu_column_gather(col: *mut llkv_gpu_column, row_ids: *const u64, n: u64, out_values: *mut c_void, out_bytes: u64, out_valid: *mut u8) -> i32;
     pub fn llkv_gpu_column_rows(col: *const llkv_gpu_column, out_rows: *mut u64) -> i32;
     pub fn llkv_gpu_column_read(col: *mut llkv_gpu_column, row_begin: u64, n_rows: u64, out: *mut c_void, out_bytes: u64) -> i32;
     pub fn llkv_gpu_column_clear(col: *mut llkv_gpu_column) -> i32;

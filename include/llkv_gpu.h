@@ -401,6 +401,16 @@ int32_t llkv_gpu_column_append_blob(llkv_gpu_column* col, uint64_t chunk_pk, con
 int32_t llkv_gpu_column_flush(llkv_gpu_column* col);
 /* Waits for outstanding uploads of this column; after this the column is scannable. */
 int32_t llkv_gpu_column_seal(llkv_gpu_column* col);
+/* ColumnStore::delete_rows (llkv-column-map/src/store/core.rs:1392-1776): the rows leave the column (ids it does not hold
+ * are ignored); their positions stay as gaps. */
+int32_t llkv_gpu_column_delete_rows(llkv_gpu_column* col, const uint64_t* row_ids, uint64_t n);
+/* ColumnStore::gather_rows / gather_row_window under GatherNullPolicy::IncludeNulls (llkv-column-map/src/store/projection.rs:
+ * 41-48,929-1352): the values of `row_ids` in request order, Arrow values layout; out_valid[i] = 0 where the column holds no
+ * such row (the value is then zero).  For tests and B2-level callers; aggregates never gather.  Not for Utf8. */
+int32_t llkv_gpu_column_gather(llkv_gpu_column* col, const uint64_t* row_ids, uint64_t n, void* out_values, uint64_t out_bytes,
+                               uint8_t* out_valid);
+/* Rows the column holds (llkv_gpu_column_rows counts positions, gaps included). */
+int32_t llkv_gpu_column_present_rows(llkv_gpu_column* col, uint64_t* out_rows);
 /* Bytes the column's appends have put on the host-to-device link since it was registered (for end-to-end accounting). */
 int32_t llkv_gpu_column_h2d_bytes(const llkv_gpu_column* col, uint64_t* out_bytes);
 int32_t llkv_gpu_column_rows(const llkv_gpu_column* col, uint64_t* out_rows);

@@ -70,6 +70,16 @@ int32_t llkv_set_error_message(int32_t code, const char* msg) { return set_error
                                             __FILE__, __LINE__, #expr);                                         \
   } while (0)
 
+static uint64_t fnv1a(uint64_t h, const void* data, size_t n) {
+  const unsigned char* b = static_cast<const unsigned char*>(data);
+  for (size_t i = 0; i < n; ++i) h = (h ^ b[i]) * 0x100000001b3ull;
+  return h;
+}
+template <typename T>
+static uint64_t fnv_pod(uint64_t h, const T& v) {
+  return fnv1a(h, &v, sizeof(T));
+}
+
 // ------------------------------------------------------------------------------------------------ column kernels
 struct DevStats {
   u64 min_enc, max_enc;  // order-preserving u64 image of the column's values (sign bit flipped for signed types)
@@ -223,6 +233,57 @@ __global__ void fill_bits_kernel(unsigned int* __restrict__ dst, u64 bit_begin, 
   }
 }
 
+// Row-id-sparse appends (ColumnStore::append with arbitrary row ids, llkv-column-map/src/store/core.rs:787-1126): row i of the
+// chunk lands at position row_ids[i] - origin, and its validity bit is set.  Chunks are applied in append order on one
+// stream, so a row id that arrives again overwrites the earlier value (last writer wins, core.rs:1128-1390).  Rows the
+// chunk marks NULL are skipped: the reference drops NULLs at append (core.rs:918-942).
+template <typename T>
+__global__ void scatter_rows_kernel(T* __restrict__ dst, unsigned int* __restrict__ valid, const T* __restrict__ src, const u64* __restrict__ ids,
+                                    const unsigned char* __restrict__ src_valid, u64 n, u64 origin) {
+  for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (u64)gridDim.x * blockDim.x) {
+    if (src_valid && !((src_valid[i >> 3] >> (i & 7)) & 1)) continue;
+    const u64 pos = ids[i] - origin;
+    dst[pos] = src[i];
+    atomicOr(&valid[pos >> 5], 1u << (pos & 31));
+  }
+}
+// ColumnStore::delete_rows (store/core.rs:1392-1776): the rows leave the column; their positions stay as gaps
+__global__ void clear_rows_kernel(unsigned int* __restrict__ valid, const u64* __restrict__ ids, u64 n, u64 origin, u64 n_rows) {
+  for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (u64)gridDim.x * blockDim.x) {
+    const u64 pos = ids[i] - origin;
+    if (ids[i] >= origin && pos < n_rows) atomicAnd(&valid[pos >> 5], ~(1u << (pos & 31)));
+  }
+}
+// gather_row_window (llkv-column-map/src/store/projection.rs:929-1352) under GatherNullPolicy::IncludeNulls: the values of the
+// given row ids in request order; a row id the column does not hold is NULL
+template <typename T>
+__global__ void gather_rows_kernel(const T* __restrict__ src, const unsigned int* __restrict__ valid, const u64* __restrict__ ids, u64 n, u64 origin,
+                                   u64 n_rows, T* __restrict__ out, unsigned char* __restrict__ out_valid) {
+  for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (u64)gridDim.x * blockDim.x) {
+    const u64 id = ids[i], pos = id - origin;
+    const bool have = id >= origin && pos < n_rows && (!valid || ((valid[pos >> 5] >> (pos & 31)) & 1u));
+    T v;
+    memset(&v, 0, sizeof(T));
+    if (have) v = src[pos];
+    out[i] = v;
+    out_valid[i] = have ? 1 : 0;
+  }
+}
+__global__ void or_words_kernel(unsigned int* __restrict__ dst, const unsigned int* __restrict__ src, u64 n_words) {
+  for (u64 w = (u64)blockIdx.x * blockDim.x + threadIdx.x; w < n_words; w += (u64)gridDim.x * blockDim.x) dst[w] |= src[w];
+}
+__global__ void popcount_bits_kernel(const unsigned int* __restrict__ bits, u64 n_bits, u64* __restrict__ out) {
+  u64 c = 0;
+  const u64 n_words = (n_bits + 31) / 32;
+  for (u64 w = (u64)blockIdx.x * blockDim.x + threadIdx.x; w < n_words; w += (u64)gridDim.x * blockDim.x) {
+    unsigned int v = bits[w];
+    if (w == n_words - 1 && (n_bits & 31)) v &= (1u << (n_bits & 31)) - 1u;
+    c += __popc(v);
+  }
+  for (int o = 16; o; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+  if ((threadIdx.x & 31) == 0 && c) atomicAdd(out, c);
+}
+
 // ------------------------------------------------------------------------------------------------ handles
 struct MvccState {
   llkv_gpu_column* created_by = nullptr;
@@ -289,6 +350,11 @@ struct llkv_gpu_ctx {
   int next_slot = 0;
   std::map<uint64_t, llkv_gpu_column*> columns;  // LogicalFieldId -> column
   std::map<uint64_t, MvccState> mvcc;            // table id -> snapshot
+  struct ExistsCache {  // row-id-sparse tables without MVCC columns: OR of the columns' validity bitmaps
+    unsigned int* bits = nullptr;
+    uint64_t words = 0, key = 0;
+  };
+  std::map<uint64_t, ExistsCache> exists;        // table id -> bitmap
   bool timing = false;
   int tune_ctas = 0, tune_block = 0, tune_stages = 0, tune_rpt = 0, tune_force_wide = 0;
   int jit_mode = 1;  // 0 never, 1 specialise a plan shape from its second run on, 2 always
@@ -362,6 +428,8 @@ struct llkv_gpu_column {
   UploadTicket ticket;
   std::vector<NarrowChunk> narrow_chunks;
   uint64_t h2d_bytes = 0;      // bytes this column's appends put on the link since it was registered
+  bool sparse = false;         // some chunk arrived with row ids that do not continue the column: positions = row id - origin,
+                               // absent rows are invalid bits, statistics are recomputed over the whole column at seal
   // pending coalesced upload from page-locked host memory (upload() / flush_upload())
   void* pend_dst = nullptr;
   const void* pend_src = nullptr;
@@ -1075,21 +1143,83 @@ static UploadPool* upload_pool(llkv_gpu_ctx* c) {
   return c->pool.get();
 }
 
+// A chunk whose row ids do not continue the column densely (rows appended after deletes, updates of existing rows, columns
+// that skip rows because the value is NULL): positions are row id - origin, rows nobody wrote are invalid bits.
+static int32_t append_sparse(llkv_gpu_column* col, const void* values, uint64_t n_rows, const uint8_t* validity, const uint64_t* row_ids) {
+  llkv_gpu_ctx* c = col->ctx;
+  if (col->type == LLKV_PT_UTF8) return set_error(LLKV_ERR_INVALID_ARGUMENT, "Utf8 columns take dense row-id runs only");
+  uint64_t lo = ~0ull, hi = 0;
+  for (uint64_t i = 0; i < n_rows; ++i) {
+    lo = std::min(lo, row_ids[i]);
+    hi = std::max(hi, row_ids[i]);
+  }
+  if (lo < col->row_id_origin)
+    return set_error(LLKV_ERR_INVALID_ARGUMENT, "row id %llu lies below the column's first row id %llu (name the table's first row id in row_id_base with the first chunk)",
+                     (unsigned long long)lo, (unsigned long long)col->row_id_origin);
+  const uint64_t span = hi - col->row_id_origin + 1;
+  if (span > (1ull << 40)) return set_error(LLKV_ERR_INVALID_ARGUMENT, "row ids span %llu positions: too sparse for a resident image", (unsigned long long)span);
+  int32_t rc;
+  if ((rc = flush_upload(col)) || (rc = drain_jobs(col))) return rc;
+  if (is_narrow_decimal(col) && (rc = widen_decimal(col, col->n_rows))) return rc;
+  col->sealed = false;
+  const uint64_t new_rows = std::max<uint64_t>(col->n_rows, span);
+  if ((rc = column_grow(col, new_rows))) return rc;
+  if ((rc = ensure_validity(col))) return rc;  // rows so far are valid, everything behind them is not (yet)
+  cudaStream_t s = c->copy_streams[(size_t)col->stream_index];
+  void* d_vals = nullptr;
+  u64* d_ids = nullptr;
+  unsigned char* d_bits = nullptr;
+  CUDA_TRY(cudaMalloc(&d_vals, n_rows * col->elem_bytes));
+  CUDA_TRY(cudaMalloc((void**)&d_ids, n_rows * 8));
+  if ((rc = upload(col, d_vals, values, n_rows * col->elem_bytes, source_kind(values)))) return rc;
+  if ((rc = upload(col, d_ids, row_ids, n_rows * 8, source_kind(row_ids)))) return rc;
+  if (validity) {
+    CUDA_TRY(cudaMalloc((void**)&d_bits, (n_rows + 7) / 8));
+    if ((rc = upload(col, d_bits, validity, (n_rows + 7) / 8, source_kind(validity)))) return rc;
+  }
+  if ((rc = flush_upload(col))) return rc;
+  const unsigned blocks = (unsigned)std::min<uint64_t>((n_rows + 255) / 256, 1184);
+  const u64 origin = col->row_id_origin;
+  switch (col->elem_bytes) {
+    case 1: scatter_rows_kernel<unsigned char><<<blocks, 256, 0, s>>>((unsigned char*)col->values, col->validity, (const unsigned char*)d_vals, d_ids, d_bits, n_rows, origin); break;
+    case 2: scatter_rows_kernel<unsigned short><<<blocks, 256, 0, s>>>((unsigned short*)col->values, col->validity, (const unsigned short*)d_vals, d_ids, d_bits, n_rows, origin); break;
+    case 4: scatter_rows_kernel<unsigned int><<<blocks, 256, 0, s>>>((unsigned int*)col->values, col->validity, (const unsigned int*)d_vals, d_ids, d_bits, n_rows, origin); break;
+    case 8: scatter_rows_kernel<u64><<<blocks, 256, 0, s>>>((u64*)col->values, col->validity, (const u64*)d_vals, d_ids, d_bits, n_rows, origin); break;
+    default: scatter_rows_kernel<ulonglong2><<<blocks, 256, 0, s>>>((ulonglong2*)col->values, col->validity, (const ulonglong2*)d_vals, d_ids, d_bits, n_rows, origin); break;
+  }
+  CUDA_TRY(cudaGetLastError());
+  CUDA_TRY(cudaFreeAsync(d_vals, s));
+  CUDA_TRY(cudaFreeAsync(d_ids, s));
+  if (d_bits) CUDA_TRY(cudaFreeAsync(d_bits, s));
+  CUDA_TRY(cudaStreamSynchronize(s));  // (the sources were pageable staging copies or page-locked: either way they are free now)
+  col->n_rows = new_rows;
+  col->sparse = true;
+  ++col->version;
+  ++c->state_epoch;
+  col->scans_unchanged = 0;
+  return LLKV_OK;
+}
+
 static int32_t append_chunk_impl(llkv_gpu_column* col, const void* values, uint64_t n_rows, const uint8_t* validity, const uint64_t* row_ids,
                                  uint64_t row_id_base, const void* aux) {
   llkv_gpu_ctx* c = col->ctx;
-  // row ids must continue the column densely (SURVEY.md §7 hard part (a))
-  const uint64_t first_id = row_ids && n_rows ? row_ids[0] : row_id_base;
+  // Dense run (the usual case: rows appended in row-id order to a table nobody deleted from) or arbitrary row ids?
+  uint64_t first_id = row_ids && n_rows ? row_ids[0] : row_id_base;
+  bool dense_run = true;
+  if (row_ids)
+    for (uint64_t i = 1; i < n_rows && dense_run; ++i) dense_run = row_ids[i] == first_id + i;
   if (!col->has_origin) {
-    col->row_id_origin = first_id;
+    // position 0 = the chunk's first row id, except for a first chunk of scattered ids: then row_id_base names it
+    col->row_id_origin = dense_run ? first_id : std::min<uint64_t>(row_id_base, first_id);
     col->has_origin = true;
   }
-  if (first_id != col->row_id_origin + col->n_rows)
-    return set_error(LLKV_ERR_INVALID_ARGUMENT, "chunk row ids start at %llu but the column continues at %llu: only dense row-id runs are supported",
-                     (unsigned long long)first_id, (unsigned long long)(col->row_id_origin + col->n_rows));
-  if (row_ids)
-    for (uint64_t i = 1; i < n_rows; ++i)
-      if (row_ids[i] != first_id + i) return set_error(LLKV_ERR_INVALID_ARGUMENT, "chunk row ids are not a dense run at offset %llu", (unsigned long long)i);
+  if (!dense_run || first_id != col->row_id_origin + col->n_rows) {
+    if (!row_ids)
+      return set_error(LLKV_ERR_INVALID_ARGUMENT, "chunk row ids start at %llu but the column continues at %llu: pass the row ids of a chunk that does not continue the column",
+                       (unsigned long long)first_id, (unsigned long long)(col->row_id_origin + col->n_rows));
+    if (n_rows == 0) return LLKV_OK;
+    return append_sparse(col, values, n_rows, validity, row_ids);
+  }
   if (n_rows == 0) return LLKV_OK;
   col->sealed = false;
   const SrcKind src_kind = source_kind(values);
@@ -1277,6 +1407,14 @@ extern "C" int32_t llkv_gpu_column_seal(llkv_gpu_column* col) {
   }
   for (void* p : col->deferred_free) cudaFree(p);
   col->deferred_free.clear();
+  if (col->sparse && col->load_kind != LK_STR8) {  // scattered writes: the statistics start over (values under invalid bits are zeros)
+    DevStats init;
+    memset(&init, 0, sizeof(init));
+    init.min_enc = ~0ull;
+    init.min_strlen = 0xffffffffu;
+    CUDA_TRY(cudaMemcpy(col->dstats, &init, sizeof(init), cudaMemcpyHostToDevice));
+    col->stats_rows = 0;
+  }
   if (col->stats_rows < col->n_rows && col->load_kind != LK_STR8) {  // min / max / fits-i64 over the rows appended since the last seal
     int32_t rc = launch_stats(col, col->stats_rows, col->n_rows - col->stats_rows);
     if (rc) return rc;
@@ -1342,6 +1480,113 @@ extern "C" int32_t llkv_gpu_column_seal(llkv_gpu_column* col) {
 extern "C" int32_t llkv_gpu_column_rows(const llkv_gpu_column* col, uint64_t* out_rows) {
   if (!col || !out_rows) return set_error(LLKV_ERR_INVALID_ARGUMENT, "NULL argument");
   *out_rows = col->n_rows;
+  return LLKV_OK;
+}
+
+extern "C" int32_t llkv_gpu_column_delete_rows(llkv_gpu_column* col, const uint64_t* row_ids, uint64_t n) {
+  if (!col || (n && !row_ids)) return set_error(LLKV_ERR_INVALID_ARGUMENT, "NULL argument");
+  llkv_gpu_ctx* c = col->ctx;
+  CTX_LOCK(c);
+  CUDA_TRY(cudaSetDevice(c->device));
+  if (n == 0 || col->n_rows == 0) return LLKV_OK;
+  int32_t rc;
+  if ((rc = column_flush(col))) return rc;
+  if ((rc = ensure_validity(col))) return rc;
+  cudaStream_t s = c->copy_streams[(size_t)col->stream_index];
+  u64* d_ids = nullptr;
+  CUDA_TRY(cudaMalloc((void**)&d_ids, n * 8));
+  if ((rc = upload(col, d_ids, row_ids, n * 8, source_kind(row_ids))) || (rc = flush_upload(col))) return rc;
+  clear_rows_kernel<<<(unsigned)std::min<uint64_t>((n + 255) / 256, 1184), 256, 0, s>>>(col->validity, d_ids, n, col->row_id_origin, col->n_rows);
+  CUDA_TRY(cudaGetLastError());
+  CUDA_TRY(cudaFreeAsync(d_ids, s));
+  CUDA_TRY(cudaStreamSynchronize(s));
+  col->sparse = true;
+  col->sealed = false;
+  ++col->version;
+  ++c->state_epoch;
+  col->scans_unchanged = 0;
+  return LLKV_OK;
+}
+
+extern "C" int32_t llkv_gpu_column_gather(llkv_gpu_column* col, const uint64_t* row_ids, uint64_t n, void* out_values, uint64_t out_bytes,
+                                           uint8_t* out_valid) {
+  if (!col || (n && (!row_ids || !out_values || !out_valid))) return set_error(LLKV_ERR_INVALID_ARGUMENT, "NULL argument");
+  if (col->type == LLKV_PT_UTF8) return set_error(LLKV_ERR_INVALID_ARGUMENT, "llkv_gpu_column_gather does not support Utf8 columns");
+  llkv_gpu_ctx* c = col->ctx;
+  CTX_LOCK(c);
+  CUDA_TRY(cudaSetDevice(c->device));
+  if (!col->sealed) {
+    int32_t rc = llkv_gpu_column_seal(col);
+    if (rc) return rc;
+  }
+  const uint64_t width = (uint64_t)prim_type_width(col->type);
+  if (out_bytes < n * width) return set_error(LLKV_ERR_INVALID_ARGUMENT, "output buffer too small");
+  if (n == 0) return LLKV_OK;
+  cudaStream_t s = c->stream;
+  u64* d_ids = nullptr;
+  void* d_out = nullptr;
+  ulonglong2* d_wide = nullptr;
+  unsigned char* d_valid = nullptr;
+  cudaError_t e = cudaMalloc((void**)&d_ids, n * 8);
+  if (e == cudaSuccess) e = cudaMalloc(&d_out, n * col->elem_bytes);
+  if (e == cudaSuccess) e = cudaMalloc((void**)&d_valid, n);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(d_ids, row_ids, n * 8, cudaMemcpyHostToDevice, s);
+  const unsigned blocks = (unsigned)std::min<uint64_t>((n + 255) / 256, 1184);
+  if (e == cudaSuccess) {
+    const u64 origin = col->row_id_origin, rows = col->n_rows;
+    switch (col->elem_bytes) {
+      case 1: gather_rows_kernel<unsigned char><<<blocks, 256, 0, s>>>((const unsigned char*)col->values, col->validity, d_ids, n, origin, rows, (unsigned char*)d_out, d_valid); break;
+      case 2: gather_rows_kernel<unsigned short><<<blocks, 256, 0, s>>>((const unsigned short*)col->values, col->validity, d_ids, n, origin, rows, (unsigned short*)d_out, d_valid); break;
+      case 4: gather_rows_kernel<unsigned int><<<blocks, 256, 0, s>>>((const unsigned int*)col->values, col->validity, d_ids, n, origin, rows, (unsigned int*)d_out, d_valid); break;
+      case 8: gather_rows_kernel<u64><<<blocks, 256, 0, s>>>((const u64*)col->values, col->validity, d_ids, n, origin, rows, (u64*)d_out, d_valid); break;
+      default: gather_rows_kernel<ulonglong2><<<blocks, 256, 0, s>>>((const ulonglong2*)col->values, col->validity, d_ids, n, origin, rows, (ulonglong2*)d_out, d_valid); break;
+    }
+    e = cudaGetLastError();
+  }
+  const void* result = d_out;
+  if (e == cudaSuccess && is_narrow_decimal(col)) {  // back to the Arrow layout
+    e = cudaMalloc((void**)&d_wide, n * 16);
+    if (e == cudaSuccess) {
+      if (col->load_kind == LK_D32) widen_dec32_kernel<<<blocks, 256, 0, s>>>((const int*)d_out, d_wide, n);
+      else widen_dec_kernel<<<blocks, 256, 0, s>>>((const u64*)d_out, d_wide, n);
+      e = cudaGetLastError();
+      result = d_wide;
+    }
+  }
+  if (e == cudaSuccess) e = cudaMemcpyAsync(out_values, result, n * width, cudaMemcpyDeviceToHost, s);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(out_valid, d_valid, n, cudaMemcpyDeviceToHost, s);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+  cudaFree(d_ids);
+  cudaFree(d_out);
+  cudaFree(d_valid);
+  if (d_wide) cudaFree(d_wide);
+  if (e != cudaSuccess) return set_error(LLKV_ERR_IO, "CUDA error %s gathering rows", cudaGetErrorString(e));
+  return LLKV_OK;
+}
+
+extern "C" int32_t llkv_gpu_column_present_rows(llkv_gpu_column* col, uint64_t* out_rows) {
+  if (!col || !out_rows) return set_error(LLKV_ERR_INVALID_ARGUMENT, "NULL argument");
+  llkv_gpu_ctx* c = col->ctx;
+  CTX_LOCK(c);
+  CUDA_TRY(cudaSetDevice(c->device));
+  int32_t rc = column_flush(col);
+  if (rc) return rc;
+  *out_rows = col->n_rows;
+  if (!col->validity || col->n_rows == 0) return LLKV_OK;
+  u64* d = nullptr;
+  CUDA_TRY(cudaMalloc((void**)&d, 8));
+  cudaStream_t s = c->copy_streams[(size_t)col->stream_index];
+  cudaError_t e = cudaMemsetAsync(d, 0, 8, s);
+  if (e == cudaSuccess) {
+    popcount_bits_kernel<<<(unsigned)std::min<uint64_t>((col->n_rows / 32 + 256) / 256, 1184), 256, 0, s>>>(col->validity, col->n_rows, d);
+    e = cudaGetLastError();
+  }
+  u64 h = 0;
+  if (e == cudaSuccess) e = cudaMemcpyAsync(&h, d, 8, cudaMemcpyDeviceToHost, s);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+  cudaFree(d);
+  if (e != cudaSuccess) return set_error(LLKV_ERR_IO, "CUDA error %s counting rows", cudaGetErrorString(e));
+  *out_rows = h;
   return LLKV_OK;
 }
 
@@ -1435,6 +1680,7 @@ extern "C" int32_t llkv_gpu_column_clear(llkv_gpu_column* col) {
   col->stats_rows = 0;
   col->has_origin = false;
   col->sealed = false;
+  col->sparse = false;
   ++col->version;
   ++c->state_epoch;
   col->scans_unchanged = 0;
@@ -1526,10 +1772,100 @@ extern "C" int32_t llkv_gpu_mvcc_clear(llkv_gpu_ctx* ctx, uint64_t table_id) {
 static uint64_t lfid_table(uint64_t lfid) { return (lfid >> 32) & 0xffffull; }  // llkv-types/src/ids.rs:133-152
 static uint64_t lfid_field(uint64_t lfid) { return lfid & 0xffffffffull; }
 
+// Row-id-sparse tables: every column covers positions [0, n) of the table's row-id range.  A column whose last rows are
+// absent (NULL by absence) is shorter than the others: it grows to the table's span, the new positions invalid.
+static int32_t equalise_sparse_columns(llkv_gpu_ctx* ctx, uint64_t table_id) {
+  uint64_t longest = 0;
+  bool differ = false, any = false;
+  for (auto& kv : ctx->columns) {
+    llkv_gpu_column* col = kv.second;
+    if (lfid_table(col->lfid) != (table_id & 0xffffull)) continue;
+    if (any && col->n_rows != longest) differ = true;
+    longest = std::max(longest, col->n_rows);
+    any = true;
+  }
+  if (!differ) return LLKV_OK;
+  bool sparse_table = false;
+  for (auto& kv : ctx->columns)
+    if (lfid_table(kv.second->lfid) == (table_id & 0xffffull) && kv.second->sparse) sparse_table = true;
+  if (!sparse_table) return LLKV_OK;  // dense tables keep the old rule: scans cover the rows every column has
+  for (auto& kv : ctx->columns) {
+    llkv_gpu_column* col = kv.second;
+    if (lfid_table(col->lfid) != (table_id & 0xffffull) || col->n_rows == longest || col->type == LLKV_PT_UTF8) continue;
+    int32_t rc;
+    if ((rc = column_flush(col))) return rc;
+    if (is_narrow_decimal(col) && (rc = widen_decimal(col, col->n_rows))) return rc;
+    if ((rc = column_grow(col, longest)) || (rc = ensure_validity(col))) return rc;
+    CUDA_TRY(cudaStreamSynchronize(ctx->copy_streams[(size_t)col->stream_index]));
+    col->n_rows = longest;
+    col->sparse = true;
+    col->sealed = false;
+    ++col->version;
+    ++ctx->state_epoch;
+  }
+  return LLKV_OK;
+}
+
+// The table's rows when positions are row ids: the MVCC created_by column's rows when the table has one, else the union of
+// the user columns' rows (Table::compute_table_row_ids, llkv-table/src/table.rs:1361-1421).  nullptr = every position.
+static int32_t table_exists_bits(llkv_gpu_ctx* ctx, uint64_t table_id, const std::vector<llkv_gpu_column*>& handles, uint64_t rows,
+                                 const unsigned char** out) {
+  *out = nullptr;
+  bool sparse_table = false;
+  for (llkv_gpu_column* h : handles) sparse_table = sparse_table || h->sparse;
+  if (!sparse_table) return LLKV_OK;  // chunks arrived as dense runs (NULLs, if any, as validity bits): every position is a row
+  auto it = ctx->mvcc.find(table_id);
+  llkv_gpu_column* created = nullptr;
+  for (llkv_gpu_column* h : handles)
+    if ((h->lfid >> 48) == 2 /* LogicalStorageNamespace::TxnCreatedBy */) created = h;
+  if (it != ctx->mvcc.end() && it->second.created_by) created = it->second.created_by;
+  if (created) {
+    *out = (const unsigned char*)created->validity;
+    return LLKV_OK;
+  }
+  uint64_t key = 0xcbf29ce484222325ull;
+  std::vector<llkv_gpu_column*> users;
+  for (llkv_gpu_column* h : handles) {
+    if ((h->lfid >> 48) != 0) continue;  // user columns only
+    if (!h->validity) return LLKV_OK;    // a column that holds every position: every position is a row
+    users.push_back(h);
+    key = fnv_pod(fnv_pod(key, (uint64_t)(uintptr_t)h), h->version);
+  }
+  if (users.empty() || rows == 0) return LLKV_OK;
+  if (users.size() == 1) {
+    *out = (const unsigned char*)users[0]->validity;
+    return LLKV_OK;
+  }
+  llkv_gpu_ctx::ExistsCache& ec = ctx->exists[table_id];
+  const uint64_t words = rows / 32 + 4 + kPadRows / 32;
+  if (ec.key != key || ec.words < words) {
+    if (ec.words < words) {
+      if (ec.bits) CUDA_TRY(cudaFree(ec.bits));
+      ec.bits = nullptr;
+      ec.words = 0;
+      CUDA_TRY(cudaMalloc((void**)&ec.bits, words * 4));
+      ec.words = words;
+    }
+    CUDA_TRY(cudaMemsetAsync(ec.bits, 0, ec.words * 4, ctx->stream));
+    const uint64_t nw = (rows + 31) / 32;
+    for (llkv_gpu_column* h : users) {
+      or_words_kernel<<<(unsigned)std::min<uint64_t>((nw + 255) / 256, 1184), 256, 0, ctx->stream>>>(ec.bits, h->validity, nw);
+      CUDA_TRY(cudaGetLastError());
+    }
+    ec.key = key;
+  }
+  *out = (const unsigned char*)ec.bits;
+  return LLKV_OK;
+}
+
 static int32_t collect_columns(llkv_gpu_ctx* ctx, uint64_t table_id, std::vector<ColumnMeta>& cols,
                                std::vector<llkv_gpu_column*>& handles, uint64_t* table_rows) {
   cols.clear();
   handles.clear();
+  {
+    int32_t erc = equalise_sparse_columns(ctx, table_id);
+    if (erc) return erc;
+  }
   bool have = false;
   uint64_t rows = 0;
   for (auto& kv : ctx->columns) {
@@ -2207,6 +2543,8 @@ extern "C" int32_t llkv_gpu_filter_bitmap(llkv_gpu_ctx* ctx, uint64_t table_id, 
   if (out_words && n_words < need_words) return set_error(LLKV_ERR_INVALID_ARGUMENT, "bitmap buffer too small");
   req.bitmap_mode = true;
   req.force_wide = ctx->tune_force_wide == 1;
+  const unsigned char* exists_bits = nullptr;
+  if ((rc = table_exists_bits(ctx, table_id, handles, table_rows, &exists_bits))) return rc;
   u64* d_bits = nullptr;
   Plan* d_plan = nullptr;
   uint32_t* d_flags = nullptr;
@@ -2220,6 +2558,7 @@ extern "C" int32_t llkv_gpu_filter_bitmap(llkv_gpu_ctx* ctx, uint64_t table_id, 
     if ((rc = compile_plan(req, cr))) { result = set_error(rc, "%s", cr.error.c_str()); break; }
     Geometry g;
     if ((rc = plan_geometry(ctx, cr.plan, cr.wide, false, row_begin, row_end, 0, g))) { result = rc; break; }
+    cr.plan.exists_bits = exists_bits;
     cr.plan.out_bitmap = d_bits;
     cr.plan.out_count = d_bits + alloc_words;
     cr.plan.flags = d_flags;
@@ -2406,17 +2745,10 @@ static int32_t agg_grow_table(llkv_gpu_agg* a) {
 // Everything the compiled plan of a run depends on, folded into one word: the columns as the compiler sees them (device
 // pointers, row counts, statistics), the predicate program, the snapshot, tuning.  A prepared aggregate that runs again
 // over unchanged inputs reuses its lean plan instead of recompiling (the compile is ~20 us, a Q6 scan of SF10 240 us).
-static uint64_t fnv1a(uint64_t h, const void* data, size_t n) {
-  const unsigned char* b = static_cast<const unsigned char*>(data);
-  for (size_t i = 0; i < n; ++i) h = (h ^ b[i]) * 0x100000001b3ull;
-  return h;
-}
-template <typename T>
-static uint64_t fnv_pod(uint64_t h, const T& v) {
-  return fnv1a(h, &v, sizeof(T));
-}
-static uint64_t request_signature(const llkv_gpu_ctx* ctx, const CompileRequest& req, const llkv_gpu_program* prog, bool force_wide) {
+static uint64_t request_signature(const llkv_gpu_ctx* ctx, const CompileRequest& req, const llkv_gpu_program* prog, bool force_wide,
+                                  const unsigned char* exists_bits) {
   uint64_t h = 0xcbf29ce484222325ull;
+  h = fnv_pod(h, exists_bits);
   for (const ColumnMeta& c : req.cols) {
     h = fnv_pod(h, c.field_id);
     h = fnv_pod(h, c.type);
@@ -2552,7 +2884,9 @@ static int32_t agg_launch(llkv_gpu_agg* a, const llkv_gpu_program* prog, int app
   LeanPlan& lean = a->lean;
   uint32_t lean_ctas = 1;
   bool use_jit = false;
-  const uint64_t sig = request_signature(ctx, req, prog, force_wide);
+  const unsigned char* exists_bits = nullptr;
+  if ((rc = table_exists_bits(ctx, a->table_id, handles, table_rows, &exists_bits))) return rc;
+  const uint64_t sig = request_signature(ctx, req, prog, force_wide, exists_bits);
   if (!(a->lean_sig == sig && a->cr.fast && a->frozen)) {
     a->lean_sig = 0;
     a->lean_jit_runs = 0;
@@ -2567,9 +2901,11 @@ static int32_t agg_launch(llkv_gpu_agg* a, const llkv_gpu_program* prog, int app
     req.no_fast = ctx->tune_force_wide != 0;
     if ((rc = compile_plan(req, a->cr))) return set_error(rc, "%s", a->cr.error.c_str());
     if ((rc = agg_freeze_layout(a, a->cr))) return rc;
+    p.exists_bits = exists_bits;
     if (a->cr.fast) a->lean_sig = sig;
     else if ((rc = plan_geometry(ctx, p, a->cr.wide, false, row_begin, row_end, a->hint, g))) return rc;
   }
+  p.exists_bits = exists_bits;
   if (a->cr.fast) {
     // Two geometries per plan (kept while request_signature() does not change): [0] for the interpreting build (rows per
     // thread first), [1] for a build specialised on the plan shape (resident warps first).  A shape is specialised once

@@ -125,6 +125,8 @@ __global__ void __launch_bounds__(512) scan_kernel(const Plan* __restrict__ gpla
     for (int r = 0; r < R; ++r) {
       const u64 row = row0 + (u64)r * NT + tid;
       act[r] = row >= p.row_begin && row < p.row_end;
+      // row-id-sparse tables: positions whose row id nobody holds (deleted rows, gaps) are not rows
+      if (p.exists_bits && act[r]) act[r] = (p.exists_bits[row >> 3] >> (row & 7)) & 1;
       nm[r] = 0;
       t0[r] = 0;
       t1[r] = 0;
@@ -139,7 +141,8 @@ __global__ void __launch_bounds__(512) scan_kernel(const Plan* __restrict__ gpla
     auto err_row = [&](int r) -> bool {
       if (!pred_phase) return act[r];
       const u64 row = row0 + (u64)r * NT + tid;
-      return row >= p.row_begin && row < p.row_end;
+      if (!(row >= p.row_begin && row < p.row_end)) return false;
+      return !p.exists_bits || ((p.exists_bits[row >> 3] >> (row & 7)) & 1);
     };
 
     // helpers -----------------------------------------------------------------------------------------

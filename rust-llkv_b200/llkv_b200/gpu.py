@@ -71,6 +71,9 @@ def load():
         "llkv_gpu_column_append_blob": (i32, [vp, u64, vp, u64, vp, u64]),
         "llkv_gpu_column_seal": (i32, [vp]),
         "llkv_gpu_column_flush": (i32, [vp]),
+        "llkv_gpu_column_delete_rows": (i32, [vp, vp, u64]),
+        "llkv_gpu_column_present_rows": (i32, [vp, P(u64)]),
+        "llkv_gpu_column_gather": (i32, [vp, vp, u64, vp, u64, vp]),
         "llkv_gpu_column_h2d_bytes": (i32, [vp, P(u64)]),
         "llkv_gpu_ctx_set_upload_threads": (i32, [vp, i32]),
         "llkv_gpu_column_rows": (i32, [vp, P(u64)]),
@@ -275,6 +278,43 @@ class DeviceColumn:
         """One chunk from a raw pointer: host memory (e.g. a slice of a pinned buffer) or device memory of this GPU."""
         _check(self.lib.llkv_gpu_column_append_chunk(self.handle, self.next_pk, C.c_void_p(ptr), n_rows, None, None, row_id_base, None))
         self.next_pk += 1
+
+    def append_rows(self, values: np.ndarray, row_ids: np.ndarray, first_row_id: int = 0, validity: Optional[np.ndarray] = None):
+        """One chunk with its row-id shadow column (ColumnStore::append with arbitrary row ids): rows land at position
+        row id - first_row_id; a row id that is already there is overwritten (last writer wins)."""
+        vals = np.ascontiguousarray(values)
+        ids = np.ascontiguousarray(row_ids, dtype=np.uint64)
+        vptr = C.c_void_p(validity.ctypes.data) if validity is not None else None
+        _check(self.lib.llkv_gpu_column_append_chunk(self.handle, self.next_pk, C.c_void_p(vals.ctypes.data), ids.shape[0], vptr,
+                                                      C.c_void_p(ids.ctypes.data), first_row_id, None))
+        self.next_pk += 1
+
+    def delete_rows(self, row_ids):
+        ids = np.ascontiguousarray(row_ids, dtype=np.uint64)
+        _check(self.lib.llkv_gpu_column_delete_rows(self.handle, C.c_void_p(ids.ctypes.data), ids.shape[0]))
+
+    def gather(self, row_ids):
+        """gather_rows(IncludeNulls): [value or None, ...] for the row ids, in request order (fixed-width columns)."""
+        ids = np.ascontiguousarray(row_ids, dtype=np.uint64)
+        t = self.dtype.type
+        if t == ffi.PT_DECIMAL128:
+            out = np.zeros((ids.shape[0], 2), dtype=np.uint64)
+        else:
+            np_t = {ffi.PT_UINT64: np.uint64, ffi.PT_INT64: np.int64, ffi.PT_FLOAT64: np.float64, ffi.PT_INT32: np.int32, ffi.PT_UINT32: np.uint32,
+                    ffi.PT_FLOAT32: np.float32, ffi.PT_DATE32: np.int32, ffi.PT_INT16: np.int16, ffi.PT_UINT16: np.uint16, ffi.PT_INT8: np.int8,
+                    ffi.PT_UINT8: np.uint8, ffi.PT_BOOLEAN: np.uint8, ffi.PT_DATE64: np.int64}[t]
+            out = np.zeros(ids.shape[0], dtype=np_t)
+        valid = np.zeros(ids.shape[0], dtype=np.uint8)
+        _check(self.lib.llkv_gpu_column_gather(self.handle, C.c_void_p(ids.ctypes.data), ids.shape[0], C.c_void_p(out.ctypes.data), out.nbytes,
+                                               C.c_void_p(valid.ctypes.data)))
+        if t == ffi.PT_DECIMAL128:
+            return [ffi.words_to_i128(int(lo), int(hi)) if v else None for (lo, hi), v in zip(out, valid)]
+        return [x.item() if v else None for x, v in zip(out, valid)]
+
+    def present_rows(self) -> int:
+        n = C.c_uint64()
+        _check(self.lib.llkv_gpu_column_present_rows(self.handle, C.byref(n)))
+        return int(n.value)
 
     def seal(self):
         _check(self.lib.llkv_gpu_column_seal(self.handle))
