@@ -3,11 +3,16 @@
 //! image); every call below is exercised through the same C ABI by the Python / C++ host mirrors in the test-suite.
 //!
 //! Ownership and threading follow `include/llkv_gpu.h`: handles are `Send`, calls on one handle are serialised by
-//! `&mut self`, the library never calls back into Rust, and host buffers only have to outlive the call that reads them
-//! (`append_*` until `seal`).
+//! `&mut self`, calls that share a context are serialised by the library, the library never calls back into Rust, and
+//! page-locked host buffers handed to `append_*` stay alive until `seal` / `flush` returns (pageable ones only for the call).
+//! Every child handle keeps its `Arc<Context>`: a context is destroyed after its last column, program and aggregate.
+pub mod flatten;
+pub mod path;
+pub mod storage;
+
 use std::ffi::c_void;
 use std::ptr;
-use std::sync::Arc;
+use std::sync::{Arc, Mutex};
 
 use llkv_gpu_sys as sys;
 use llkv_result::{Error, Result};
@@ -22,13 +27,18 @@ fn check(rc: i32) -> Result<()> {
     let mut buf = vec![0u8; 1024];
     let n = unsafe { sys::llkv_gpu_last_error(buf.as_mut_ptr().cast(), buf.len()) }.min(buf.len() - 1);
     let msg = String::from_utf8_lossy(&buf[..n]).into_owned();
+    // LLKV_ERR_* (include/llkv_gpu.h) = the variant order of llkv_result::Error
     Err(match rc {
         1 => Error::Io(std::io::Error::other(msg)),
+        2 => Error::Arrow(arrow::error::ArrowError::ComputeError(msg)),
         3 => Error::InvalidArgumentError(msg),
         4 => Error::NotFound,
+        5 => Error::CatalogError(msg),
+        6 => Error::ConstraintError(msg),
+        7 => Error::TransactionContextError(msg),
         9 => Error::ExprCast(msg),
         10 => Error::PredicateBuild(msg),
-        _ => Error::Internal(msg),
+        _ => Error::Internal(msg), // 8 and anything unknown
     })
 }
 
@@ -37,8 +47,11 @@ fn check(rc: i32) -> Result<()> {
 pub struct Context {
     raw: *mut sys::llkv_gpu_ctx,
 }
+// Every entry point of the library takes the context's own lock (include/llkv_gpu.h, "Conventions"): columns, programs and
+// aggregates of one context may live on different threads.  Child handles hold an `Arc<Context>`, so the context is
+// destroyed after the last of them.
 unsafe impl Send for Context {}
-unsafe impl Sync for Context {} // the registry is only mutated through handles that borrow the context
+unsafe impl Sync for Context {}
 
 impl Context {
     pub fn new(device_ordinal: i32) -> Result<Arc<Self>> {
@@ -124,18 +137,19 @@ impl Drop for ResidentColumn {
 /// `rust-llkv_b200/host/llkv_gpu.hpp: ProgramCompiler` is the same code in C++).
 pub struct Program {
     raw: *mut sys::llkv_gpu_program,
+    _ctx: Arc<Context>,
 }
 unsafe impl Send for Program {}
 
 impl Program {
-    pub fn from_flat(ctx: &Context, ops: &[sys::llkv_eval_op], literals: &[sys::llkv_literal], nodes: &[sys::llkv_scalar_node],
+    pub fn from_flat(ctx: &Arc<Context>, ops: &[sys::llkv_eval_op], literals: &[sys::llkv_literal], nodes: &[sys::llkv_scalar_node],
                      list_roots: &[i32]) -> Result<Self> {
         let mut raw = ptr::null_mut();
         check(unsafe {
             sys::llkv_gpu_program_compile(ctx.raw, ops.as_ptr(), ops.len() as i32, literals.as_ptr(), literals.len() as i32, nodes.as_ptr(),
                                           nodes.len() as i32, list_roots.as_ptr(), list_roots.len() as i32, &mut raw)
         })?;
-        Ok(Self { raw })
+        Ok(Self { raw, _ctx: ctx.clone() })
     }
 }
 impl Drop for Program {
@@ -144,13 +158,62 @@ impl Drop for Program {
     }
 }
 
-/// `MvccRowIdFilter::new(txn_manager, snapshot)` (`llkv-transaction/src/helpers.rs:259-312`): the snapshot plus every
-/// transaction id whose `TxnIdManager::status` is Active or Aborted.
-pub fn set_snapshot(ctx: &Context, table_id: u64, created_by: &ResidentColumn, deleted_by: &ResidentColumn, txn_id: u64,
-                    snapshot_id: u64, noncommitted: &[u64]) -> Result<()> {
-    check(unsafe {
-        sys::llkv_gpu_mvcc_set(ctx.raw, table_id, created_by.raw, deleted_by.raw, txn_id, snapshot_id, noncommitted.as_ptr(), noncommitted.len() as i32)
-    })
+/// The resident image of one table: its user columns and, when the table carries them, the MVCC columns.  The snapshot
+/// registered with the context refers to these columns, so it lives and dies with the table (it is cleared on drop).
+pub struct ResidentTable {
+    ctx: Arc<Context>,
+    table_id: u64,
+    columns: Vec<ResidentColumn>,
+    mvcc: Option<(ResidentColumn, ResidentColumn)>,
+    first_row_id: u64,
+    snapshot_set: Mutex<bool>,
+}
+
+impl ResidentTable {
+    pub fn new(ctx: &Arc<Context>, table_id: u64, columns: Vec<ResidentColumn>, mvcc: Option<(ResidentColumn, ResidentColumn)>, first_row_id: u64) -> Self {
+        Self { ctx: ctx.clone(), table_id, columns, mvcc, first_row_id, snapshot_set: Mutex::new(false) }
+    }
+    pub fn table_id(&self) -> u64 {
+        self.table_id
+    }
+    pub fn first_row_id(&self) -> u64 {
+        self.first_row_id
+    }
+    pub fn rows(&self) -> Result<u64> {
+        self.columns.first().map_or(Ok(0), |c| c.rows())
+    }
+    /// `MvccRowIdFilter::new(txn_manager, snapshot)` (`llkv-transaction/src/helpers.rs:259-312`): the snapshot plus every
+    /// transaction id whose `TxnIdManager::status` is Active or Aborted.  Without MVCC columns every row is visible
+    /// (`helpers.rs:141-152`).
+    pub fn set_snapshot(&self, txn_id: u64, snapshot_id: u64, noncommitted: &[u64]) -> Result<()> {
+        let Some((created, deleted)) = &self.mvcc else { return Ok(()) };
+        let mut set = self.snapshot_set.lock().unwrap();
+        check(unsafe {
+            sys::llkv_gpu_mvcc_set(self.ctx.raw, self.table_id, created.raw, deleted.raw, txn_id, snapshot_id, noncommitted.as_ptr(), noncommitted.len() as i32)
+        })?;
+        *set = true;
+        Ok(())
+    }
+    /// Selection bitmap over positions (bit i = row `first_row_id + row_begin + i`): `ScanStorage::filter_leaf` /
+    /// `RowIdFilter::filter` on the device.
+    pub fn filter_bitmap(&self, program: Option<&Program>, apply_mvcc: bool, row_begin: u64, row_end: u64) -> Result<Vec<u64>> {
+        let n_words = ((row_end - row_begin + 63) / 64) as usize;
+        let mut words = vec![0u64; n_words.max(1)];
+        let mut count = 0u64;
+        check(unsafe {
+            sys::llkv_gpu_filter_bitmap(self.ctx.raw, self.table_id, program.map_or(ptr::null(), |p| p.raw.cast_const()), apply_mvcc as i32,
+                                        row_begin, row_end, words.as_mut_ptr(), n_words as u64, &mut count)
+        })?;
+        words.truncate(n_words);
+        Ok(words)
+    }
+}
+impl Drop for ResidentTable {
+    fn drop(&mut self) {
+        if *self.snapshot_set.lock().unwrap() {
+            unsafe { sys::llkv_gpu_mvcc_clear(self.ctx.raw, self.table_id) };
+        }
+    }
 }
 
 /// A set of `AggregateState`s fused with the scan that feeds them: one call per query instead of one
@@ -160,18 +223,26 @@ pub struct Aggregation {
     raw: *mut sys::llkv_gpu_agg,
     n_aggs: usize,
     n_keys: usize,
+    _ctx: Arc<Context>,
 }
 unsafe impl Send for Aggregation {}
 
 impl Aggregation {
-    pub fn new(ctx: &Context, table_id: u64, specs: &[sys::llkv_agg_spec], nodes: &[sys::llkv_scalar_node], group_key_fields: &[u64],
+    pub fn new(ctx: &Arc<Context>, table_id: u64, specs: &[sys::llkv_agg_spec], nodes: &[sys::llkv_scalar_node], group_key_fields: &[u64],
                expr_mode: i32, cardinality_hint: u64) -> Result<Self> {
         let mut raw = ptr::null_mut();
         check(unsafe {
             sys::llkv_gpu_agg_create(ctx.raw, table_id, specs.as_ptr(), specs.len() as i32, nodes.as_ptr(), nodes.len() as i32,
                                      group_key_fields.as_ptr(), group_key_fields.len() as i32, expr_mode, cardinality_hint, &mut raw)
         })?;
-        Ok(Self { raw, n_aggs: specs.len(), n_keys: group_key_fields.len() })
+        Ok(Self { raw, n_aggs: specs.len(), n_keys: group_key_fields.len(), _ctx: ctx.clone() })
+    }
+
+    /// reset + run + (merge across the context's peers) in one call; replayed as one CUDA graph once the step repeats.
+    pub fn execute(&mut self, filter: Option<&Program>, apply_mvcc: bool, row_begin: u64, row_end: u64, merge: bool) -> Result<()> {
+        check(unsafe {
+            sys::llkv_gpu_agg_execute(self.raw, filter.map_or(ptr::null(), |p| p.raw.cast_const()), apply_mvcc as i32, row_begin, row_end, merge as i32)
+        })
     }
 
     /// Scans rows `[row_begin, row_end)`; asynchronous — `finalize` settles the run (and reruns wider / with a larger group

@@ -136,7 +136,8 @@ def test_safe_rust_crate_only_calls_declared_sys_functions():
     import re
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     sys_rs = open(os.path.join(root, "ffi", "llkv-gpu-sys", "src", "lib.rs")).read()
-    safe_rs = open(os.path.join(root, "ffi", "llkv-gpu", "src", "lib.rs")).read()
+    src_dir = os.path.join(root, "ffi", "llkv-gpu", "src")
+    safe_rs = "".join(open(os.path.join(src_dir, f)).read() for f in sorted(os.listdir(src_dir)) if f.endswith(".rs"))
     declared = set(re.findall(r"pub fn (llkv_gpu_[a-z0-9_]+)\s*\(", sys_rs)) | set(re.findall(r"pub struct (llkv_[a-z0-9_]+)", sys_rs))
     used = set(re.findall(r"sys::(llkv_[a-z0-9_]+)", safe_rs))
     assert used and not (used - declared), sorted(used - declared)
