@@ -235,6 +235,10 @@ extern "C" {
     pub fn llkv_gpu_column_gather(col: *mut llkv_gpu_column, row_ids: *const u64, n: u64, out_values: *mut c_void, out_bytes: u64, out_valid: *mut u8) -> i32;
     pub fn llkv_gpu_column_rows(col: *const llkv_gpu_column, out_rows: *mut u64) -> i32;
     pub fn llkv_gpu_column_read(col: *mut llkv_gpu_column, row_begin: u64, n_rows: u64, out: *mut c_void, out_bytes: u64) -> i32;
+    /// `ColumnStore::scan` with an unsorted visitor: one callback per chunk, values (+ row ids) borrowed for the call.
+    pub fn llkv_gpu_column_visit(col: *mut llkv_gpu_column, chunk_rows: u64, with_row_ids: i32,
+                                 visit: Option<unsafe extern "C" fn(user: *mut c_void, prim_type: i32, values: *const c_void, row_ids: *const u64, n_rows: u64) -> i32>,
+                                 user: *mut c_void) -> i32;
     pub fn llkv_gpu_column_clear(col: *mut llkv_gpu_column) -> i32;
     pub fn llkv_gpu_column_destroy(col: *mut llkv_gpu_column) -> i32;
 

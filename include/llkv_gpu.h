@@ -420,6 +420,15 @@ int32_t llkv_gpu_column_rows(const llkv_gpu_column* col, uint64_t* out_rows);
  * scan/unsorted.rs:202-345).  For tests and diagnostics of the resident image; aggregates never copy rows back.
  * LLKV_PT_UTF8 is not supported here. */
 int32_t llkv_gpu_column_read(llkv_gpu_column* col, uint64_t row_begin, uint64_t n_rows, void* out, uint64_t out_bytes);
+/* Visitor-level boundary (B3): ColumnStore::scan with an unsorted visitor — PrimitiveVisitor::{u64,i64,...}_chunk and
+ * PrimitiveWithRowIdsVisitor::*_chunk_with_rids (llkv-column-map/src/store/scan/visitors.rs:89-148, src/lib.rs:174-359,
+ * scan/unsorted.rs:202-345).  `visit` is called on the calling thread once per chunk of at most `chunk_rows` positions
+ * (0 = the append path's chunk size for the type) with the chunk's values in the Arrow layout (`prim_type` names the
+ * element type: the per-dtype method the reference would dispatch to) and, when `with_row_ids` is set, their row ids
+ * (NULL otherwise); rows the column does not hold are skipped (ScanOptions::include_nulls = false).  The buffers are only
+ * valid during the call.  A non-zero return from `visit` stops the scan and becomes the call's status. */
+typedef int32_t (*llkv_chunk_visitor)(void* user, int32_t prim_type, const void* values, const uint64_t* row_ids, uint64_t n_rows);
+int32_t llkv_gpu_column_visit(llkv_gpu_column* col, uint64_t chunk_rows, int32_t with_row_ids, llkv_chunk_visitor visit, void* user);
 /* Drops the rows but keeps the device allocation (re-upload the next batch into the same buffer). */
 int32_t llkv_gpu_column_clear(llkv_gpu_column* col);
 int32_t llkv_gpu_column_destroy(llkv_gpu_column* col);

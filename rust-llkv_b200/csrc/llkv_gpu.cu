@@ -1564,6 +1564,54 @@ extern "C" int32_t llkv_gpu_column_gather(llkv_gpu_column* col, const uint64_t* 
   return LLKV_OK;
 }
 
+// ColumnStore::scan with an unsorted visitor (llkv-column-map/src/store/scan/mod.rs:191-260, scan/unsorted.rs:202-345): the
+// column's rows chunk by chunk, values in the Arrow layout, optionally with their row ids.  Rows the column does not hold
+// (NULL by absence, deleted rows) are skipped, as with ScanOptions::include_nulls = false.
+extern "C" int32_t llkv_gpu_column_visit(llkv_gpu_column* col, uint64_t chunk_rows, int32_t with_row_ids, llkv_chunk_visitor visit, void* user) {
+  if (!col || !visit) return set_error(LLKV_ERR_INVALID_ARGUMENT, "NULL argument");
+  if (col->type == LLKV_PT_UTF8) return set_error(LLKV_ERR_INVALID_ARGUMENT, "llkv_gpu_column_visit does not support Utf8 columns");
+  llkv_gpu_ctx* c = col->ctx;
+  CTX_LOCK(c);
+  CUDA_TRY(cudaSetDevice(c->device));
+  if (!col->sealed) {
+    int32_t rc = llkv_gpu_column_seal(col);
+    if (rc) return rc;
+  }
+  const uint64_t width = (uint64_t)prim_type_width(col->type);
+  if (chunk_rows == 0) chunk_rows = width <= 8 ? (1ull << 20) / width : 4096;  // the append path's chunking (store/slicing.rs:33-43,155-166)
+  chunk_rows = (chunk_rows + 31) / 32 * 32;
+  std::vector<unsigned char> vals(chunk_rows * width), packed;
+  std::vector<unsigned int> bits(chunk_rows / 32 + 1);
+  std::vector<uint64_t> ids;
+  for (uint64_t lo = 0; lo < col->n_rows; lo += chunk_rows) {
+    const uint64_t n = std::min<uint64_t>(chunk_rows, col->n_rows - lo);
+    int32_t rc = llkv_gpu_column_read(col, lo, n, vals.data(), vals.size());
+    if (rc) return rc;
+    const unsigned char* out_vals = vals.data();
+    uint64_t out_n = n;
+    if (col->validity) {  // keep the rows the column holds
+      CUDA_TRY(cudaMemcpy(bits.data(), col->validity + lo / 32, ((n + 31) / 32) * 4, cudaMemcpyDeviceToHost));
+      packed.resize(n * width);
+      ids.clear();
+      out_n = 0;
+      for (uint64_t i = 0; i < n; ++i) {
+        if (!((bits[i >> 5] >> (i & 31)) & 1u)) continue;
+        memcpy(packed.data() + out_n * width, vals.data() + i * width, width);
+        if (with_row_ids) ids.push_back(col->row_id_origin + lo + i);
+        ++out_n;
+      }
+      out_vals = packed.data();
+    } else if (with_row_ids) {
+      ids.resize(n);
+      for (uint64_t i = 0; i < n; ++i) ids[i] = col->row_id_origin + lo + i;
+    }
+    if (out_n == 0) continue;
+    const int32_t vrc = visit(user, col->type, out_vals, with_row_ids ? ids.data() : nullptr, out_n);
+    if (vrc) return set_error(vrc, "the chunk visitor stopped the scan with status %d", vrc);
+  }
+  return LLKV_OK;
+}
+
 extern "C" int32_t llkv_gpu_column_present_rows(llkv_gpu_column* col, uint64_t* out_rows) {
   if (!col || !out_rows) return set_error(LLKV_ERR_INVALID_ARGUMENT, "NULL argument");
   llkv_gpu_ctx* c = col->ctx;

@@ -29,6 +29,8 @@ TARGET_CHUNK_BYTES = 1 << 20
 VARWIDTH_FALLBACK_ROWS = 4096
 
 _lib = None
+# llkv_chunk_visitor: (user, prim_type, values, row_ids, n_rows) -> status
+CHUNK_VISITOR = C.CFUNCTYPE(C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.POINTER(C.c_uint64), C.c_uint64)
 
 
 def load():
@@ -74,6 +76,7 @@ def load():
         "llkv_gpu_column_delete_rows": (i32, [vp, vp, u64]),
         "llkv_gpu_column_present_rows": (i32, [vp, P(u64)]),
         "llkv_gpu_column_gather": (i32, [vp, vp, u64, vp, u64, vp]),
+        "llkv_gpu_column_visit": (i32, [vp, u64, i32, CHUNK_VISITOR, vp]),
         "llkv_gpu_column_h2d_bytes": (i32, [vp, P(u64)]),
         "llkv_gpu_ctx_set_upload_threads": (i32, [vp, i32]),
         "llkv_gpu_column_rows": (i32, [vp, P(u64)]),
@@ -310,6 +313,29 @@ class DeviceColumn:
         if t == ffi.PT_DECIMAL128:
             return [ffi.words_to_i128(int(lo), int(hi)) if v else None for (lo, hi), v in zip(out, valid)]
         return [x.item() if v else None for x, v in zip(out, valid)]
+
+    def visit(self, on_chunk, chunk_rows: int = 0, with_row_ids: bool = False):
+        """ColumnStore::scan with an unsorted visitor: on_chunk(values ndarray[, row_ids ndarray]) per chunk
+        (PrimitiveVisitor::*_chunk / PrimitiveWithRowIdsVisitor::*_chunk_with_rids)."""
+        t = self.dtype.type
+        np_t = {ffi.PT_UINT64: np.uint64, ffi.PT_INT64: np.int64, ffi.PT_FLOAT64: np.float64, ffi.PT_INT32: np.int32, ffi.PT_UINT32: np.uint32,
+                ffi.PT_FLOAT32: np.float32, ffi.PT_DATE32: np.int32, ffi.PT_INT16: np.int16, ffi.PT_UINT16: np.uint16, ffi.PT_INT8: np.int8,
+                ffi.PT_UINT8: np.uint8, ffi.PT_BOOLEAN: np.uint8, ffi.PT_DATE64: np.int64, ffi.PT_DECIMAL128: np.uint64}[t]
+        per_row = 2 if t == ffi.PT_DECIMAL128 else 1
+
+        def trampoline(_user, prim_type, values, row_ids, n):
+            assert prim_type == t
+            vals = np.ctypeslib.as_array(C.cast(values, C.POINTER(np.ctypeslib.as_ctypes_type(np_t))), shape=(n * per_row,)).copy()
+            if per_row == 2:
+                vals = vals.reshape(n, 2)
+            if with_row_ids:
+                on_chunk(vals, np.ctypeslib.as_array(row_ids, shape=(n,)).copy())
+            else:
+                on_chunk(vals)
+            return 0
+
+        cb = CHUNK_VISITOR(trampoline)
+        _check(self.lib.llkv_gpu_column_visit(self.handle, chunk_rows, int(with_row_ids), cb, None))
 
     def present_rows(self) -> int:
         n = C.c_uint64()

@@ -39,6 +39,22 @@ def test_fragmented_sum_with_deletes_matches_the_reference_fixture(gpu_ctx):
         dc.seal()
         dt.n_rows = dc.rows()
         assert dc.rows() == n + rows and dc.present_rows() == f["expected_rows"]
+        # the bench's own visitor: PrimitiveVisitor::u64_chunk summing every chunk (column_sum_bench.rs:240-277), then the
+        # with-row-ids form: row id == value in this fixture
+        acc = {"sum": 0, "rows": 0, "chunks": 0}
+
+        def on_chunk(vals, rids=None):
+            acc["sum"] += int(vals.sum())
+            acc["rows"] += vals.shape[0]
+            acc["chunks"] += 1
+            if rids is not None:
+                assert np.array_equal(rids.astype(np.int64), vals)
+
+        dc.visit(on_chunk)
+        assert acc["sum"] == f["expected_final_sum"] and acc["rows"] == f["expected_rows"] and acc["chunks"] == 8  # 131 072-row chunks
+        acc.update(sum=0, rows=0, chunks=0)
+        dc.visit(on_chunk, chunk_rows=50_000, with_row_ids=True)
+        assert acc["sum"] == f["expected_final_sum"] and acc["rows"] == f["expected_rows"] and acc["chunks"] == 21
         specs = [AggregateSpec("s", AggregateKind.Sum(1, DataType.Int64)), AggregateSpec("n", AggregateKind.CountStar()),
                  AggregateSpec("c", AggregateKind.Count(1)), AggregateSpec("mn", AggregateKind.Min(1, DataType.Int64))]
         for jit in (1, 2):  # interpreted, then specialised
