@@ -1962,10 +1962,7 @@ class Emitter {
           st.back().iv.is_float = true;
           break;
         }
-        case OP_MVCC:
-          if (plan_cols_[in.a]->nullable || plan_cols_[in.b]->nullable) return false;  // (NULL created_by / deleted_by have their own defaults)
-          femit(FO_MVCC, in.a, in.b, 0);
-          break;
+        case OP_MVCC: femit(FO_MVCC, in.a, in.b, 0); break;  // (NULL created_by / deleted_by take their defaults in the kernel)
         case OP_SELECT_DONE: femit(FO_SELECT_DONE, 0, 0, 0); break;
         case OP_GROUP: {
           const int nk = in.a;

@@ -434,6 +434,19 @@ struct LeanTile {
           cb[r] = cbase[r * NC + tid];
           db[r] = dbase[r * NC + tid];
         }
+        // NULL created_by -> TXN_ID_AUTO_COMMIT, NULL deleted_by -> TXN_ID_NONE (llkv-transaction/src/helpers.rs:214-223)
+        if (S.cols[in.a].has_valid) {
+          const unsigned v = col_valid(in.a);
+#pragma unroll
+          for (int r = 0; r < R; ++r)
+            if (!((v >> r) & 1u)) cb[r] = 1ull;
+        }
+        if (S.cols[in.b].has_valid) {
+          const unsigned v = col_valid(in.b);
+#pragma unroll
+          for (int r = 0; r < R; ++r)
+            if (!((v >> r) & 1u)) db[r] = ~0ull;
+        }
         unsigned m = 0;
         if (snap != ~0ull && txn != ~0ull) {
           // creator passes iff cb <= snap (which excludes MAX) and cb is not listed; the deletion does not hide the row
