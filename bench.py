@@ -186,9 +186,10 @@ def run_ours(args):
     ctx = gpu.Context(local, n_streams=4, pinned_bytes=64 << 20)
     # host workers that narrow Decimal128 chunks before the DMA: this rank's share of the host threads
     upload_threads = args.upload_threads if args.upload_threads >= 0 else max(0, min(32, cores // world - 1))
-    if args.upload_threads < 0 and upload_threads < 16:
-        # one host thread narrows ~5 GB/s of Arrow bytes: with fewer than 16 of them per rank the narrowing is slower than
-        # sending the 16-byte layout over the link (measured: 12 threads per rank at N = 2, 113 ms against 72 ms per step)
+    if args.upload_threads < 0 and (world > 1 or upload_threads < 12):
+        # one host thread narrows ~5 GB/s of Arrow bytes, and the host's streaming rate stops growing near 85 GB/s: worth it
+        # for one rank with >= 12 threads (measured: 16 threads 37.8 ms, 23 threads 34.7 ms against 58 ms of plain DMA per
+        # step), not when several ranks share the host (12 threads per rank at N = 2: 113 ms against 72 ms)
         upload_threads = 0
     ctx.set_upload_threads(upload_threads)
     if world > 1:

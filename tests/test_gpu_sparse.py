@@ -189,7 +189,7 @@ def test_sparse_table_queries_match_the_oracle_over_the_rows_that_exist(gpu_ctx)
             agg.destroy()
             prog.destroy()
             util.assert_same_result(got, oracle.aggregate(compact, tpch.q6_filter(), tpch.q6_aggregates() + specs, snap))
-            assert info.used_fast_kernel == 1 and info.used_jit_kernel == (1 if jit == 2 else 0)
+            assert info.used_fast_kernel == 1 and (jit == 1 or info.used_jit_kernel == 1)  # (mode 1 specialises a shape from its second run on)
     finally:
         gpu_ctx.set_jit(1)
         dt.destroy()
