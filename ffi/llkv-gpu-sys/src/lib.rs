@@ -63,6 +63,27 @@ pub struct llkv_agg_spec {
     pub _pad: u8,
 }
 
+/// One ORDER BY key over the finalized rows (`OrderByPlan`, llkv-plan/src/plans.rs:1205-1225).
+#[repr(C)]
+#[derive(Clone, Copy)]
+pub struct llkv_order_key {
+    pub is_aggregate: i32,
+    pub index: i32,
+    pub descending: i32,
+    pub nulls_first: i32,
+}
+
+/// One HAVING term: output column `cmp_op` literal.
+#[repr(C)]
+#[derive(Clone, Copy)]
+pub struct llkv_having_term {
+    pub is_aggregate: i32,
+    pub index: i32,
+    pub cmp_op: i32,
+    pub _pad: i32,
+    pub literal: llkv_literal,
+}
+
 #[repr(C)]
 #[derive(Clone, Copy)]
 pub struct llkv_agg_value {
@@ -258,6 +279,8 @@ extern "C" {
     pub fn llkv_gpu_agg_execute(agg: *mut llkv_gpu_agg, prog: *const llkv_gpu_program, apply_mvcc: i32, row_begin: u64, row_end: u64, merge: i32) -> i32;
     pub fn llkv_gpu_agg_group_count(agg: *mut llkv_gpu_agg, out_groups: *mut u64) -> i32;
     pub fn llkv_gpu_agg_finalize(agg: *mut llkv_gpu_agg, out_values: *mut llkv_agg_value, out_keys: *mut llkv_group_key, group_capacity: u64, out_groups: *mut u64) -> i32;
+    /// HAVING / ORDER BY / OFFSET / LIMIT applied by every later `llkv_gpu_agg_finalize`.
+    pub fn llkv_gpu_agg_set_output(agg: *mut llkv_gpu_agg, having: *const llkv_having_term, n_having: i32, order: *const llkv_order_key, n_order: i32, offset: u64, limit: u64) -> i32;
     pub fn llkv_gpu_agg_run_info(agg: *const llkv_gpu_agg, out: *mut llkv_run_info) -> i32;
     pub fn llkv_gpu_agg_destroy(agg: *mut llkv_gpu_agg);
 

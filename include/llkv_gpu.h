@@ -187,7 +187,8 @@ typedef struct llkv_agg_spec {
   int32_t data_type; /* AggregateKind::*.data_type as LLKV_PT_* — selects the accumulator (lib.rs:463-748) */
   uint8_t precision;
   int8_t scale;
-  uint8_t distinct;  /* must be 0 on this path */
+  uint8_t distinct;  /* DISTINCT (llkv-aggregate/src/lib.rs:103-204): ungrouped COUNT / SUM / TOTAL / AVG over one bare integer column,
+                        and then every aggregate of the query must be DISTINCT over that column; otherwise 0 */
   uint8_t _pad;
 } llkv_agg_spec;
 
@@ -483,6 +484,27 @@ int32_t llkv_gpu_agg_group_count(llkv_gpu_agg* agg, uint64_t* out_groups);
  * raises during update (integer overflow, Decimal128 sum overflow, arrow arithmetic overflow) surface here. */
 int32_t llkv_gpu_agg_finalize(llkv_gpu_agg* agg, llkv_agg_value* out_values, llkv_group_key* out_keys,
                               uint64_t group_capacity, uint64_t* out_groups);
+/* HAVING / ORDER BY / OFFSET / LIMIT over the finalized rows (llkv-executor/src/lib.rs:5306-5348; plans.rs:1205-1225
+ * OrderByPlan).  A HAVING term compares one output column (group key or aggregate) with a literal; terms are ANDed and a
+ * row stays only when every term is TRUE (a NULL cell is not).  ORDER BY keys sort the remaining rows (stable; ties keep the
+ * first-appearance order), NULLs first or last as asked whatever the direction (arrow SortOptions).  limit 0 = no limit.
+ * Applies to every later llkv_gpu_agg_finalize of the handle; n_having = n_order = 0 with offset = limit = 0 restores the
+ * plain first-appearance output.  The group capacity then bounds the rows that come out, not the groups held. */
+typedef struct llkv_order_key {
+  int32_t is_aggregate; /* 0: index counts GROUP BY keys, 1: aggregates */
+  int32_t index;
+  int32_t descending;
+  int32_t nulls_first;
+} llkv_order_key;
+typedef struct llkv_having_term {
+  int32_t is_aggregate;
+  int32_t index;
+  int32_t cmp_op; /* LLKV_CMP_* : cell cmp literal */
+  int32_t _pad;
+  llkv_literal literal;
+} llkv_having_term;
+int32_t llkv_gpu_agg_set_output(llkv_gpu_agg* agg, const llkv_having_term* having, int32_t n_having, const llkv_order_key* order,
+                                int32_t n_order, uint64_t offset, uint64_t limit);
 int32_t llkv_gpu_agg_run_info(const llkv_gpu_agg* agg, llkv_run_info* out);
 void llkv_gpu_agg_destroy(llkv_gpu_agg* agg);
 

@@ -4,6 +4,7 @@
 // llkv_gpu_ctx_create fails and every other entry point needs a context.
 #include <cuda_runtime.h>
 #include <dlfcn.h>
+#include <math.h>
 #include <stdarg.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -44,9 +45,9 @@ cudaError_t launch_merge_ungrouped(u64* dst, const u64* all_words, int n_ranks, 
 cudaError_t launch_merge_grouped_p2p(u64* gkeys, u64* gwords, u64 gcap, uint32_t n_gwords, const uint8_t* word_class_dev, uint32_t* flags,
                                      u64* const* peer_boxes, uint32_t slot_words, int n_ranks, int rank, u64* epoch_dev, bool exchange, cudaStream_t stream);
 }  // namespace llkv
-// peer mailboxes (llkv_gpu_comm_init): [n_ranks][2][128] words for ungrouped state rows, then [n_ranks][2][kGroupSlotWords]
+// peer mailboxes (llkv_gpu_comm_init): [n_ranks][2][256] packets for ungrouped state rows, then [n_ranks][2][kGroupSlotWords]
 // words for small group tables
-static constexpr uint32_t kUngroupedSlotWords = 128, kGroupSlotWords = 16384;
+static constexpr uint32_t kUngroupedSlotWords = 256, kGroupSlotWords = 16384;  // (256 = scan_kernel.cu: kMergePackets)
 
 using namespace llkv;
 
@@ -553,6 +554,13 @@ struct llkv_gpu_agg {
   bool in_capture = false;
   uint32_t capture_failures = 0;
   bool stage_ev_valid = false;
+  // output shaping at finalize (llkv_gpu_agg_set_output): HAVING terms, ORDER BY keys, OFFSET / LIMIT
+  std::vector<llkv_having_term> having;
+  std::vector<llkv_order_key> order;
+  uint64_t out_offset = 0, out_limit = 0;
+  // DISTINCT aggregates: the distinct values are the groups of an inner aggregation over the argument column
+  llkv_gpu_agg* inner = nullptr;
+  bool skip_scan_copy = false;      // llkv_gpu_agg_execute with a peer-mailbox merge behind the scan: the merge queues the result copy
   bool p2p_group_disabled = false;  // a rank's group table outgrew a mailbox slot once: this aggregate merges over NCCL from then on
   int32_t err_code = 0;
   std::string err_msg;
@@ -2653,11 +2661,22 @@ extern "C" int32_t llkv_gpu_agg_create(llkv_gpu_ctx* ctx, uint64_t table_id, con
     return set_error(LLKV_ERR_INVALID_ARGUMENT, "bad aggregate arguments");
   if (n_keys > kMaxKeys) return set_error(LLKV_ERR_INVALID_ARGUMENT, "too many GROUP BY keys (max %d)", kMaxKeys);
   if (expr_mode != LLKV_EXPR_ARROW && expr_mode != LLKV_EXPR_EXACT) return set_error(LLKV_ERR_INVALID_ARGUMENT, "bad expr_mode %d", expr_mode);
+  int n_distinct = 0;
+  uint64_t distinct_field = 0;
   for (int i = 0; i < n_aggs; ++i) {
-    if (specs[i].distinct) return set_error(LLKV_ERR_INVALID_ARGUMENT, "DISTINCT aggregates are outside this path");
     if (specs[i].expr_root >= n_nodes) return set_error(LLKV_ERR_INVALID_ARGUMENT, "aggregate %d: expression root out of range", i);
     if (specs[i].expr_root < 0 && specs[i].kind != LLKV_AGG_COUNT) return set_error(LLKV_ERR_INVALID_ARGUMENT, "aggregate %d needs an argument", i);
+    if (!specs[i].distinct) continue;
+    // DISTINCT (llkv-aggregate/src/lib.rs:103-204: CountDistinctColumn, Sum/Total/AvgDistinctInt64): ungrouped, over one bare
+    // integer column, every aggregate of the query DISTINCT over that column
+    const llkv_scalar_node* arg = specs[i].expr_root >= 0 ? &nodes[specs[i].expr_root] : nullptr;
+    if (n_keys || !arg || arg->tag != LLKV_SE_COLUMN || (n_distinct && arg->field_id != distinct_field) ||
+        !(specs[i].kind == LLKV_AGG_COUNT || specs[i].kind == LLKV_AGG_SUM || specs[i].kind == LLKV_AGG_TOTAL || specs[i].kind == LLKV_AGG_AVG))
+      return set_error(LLKV_ERR_INVALID_ARGUMENT, "DISTINCT aggregates on this path: ungrouped COUNT / SUM / TOTAL / AVG over one integer column");
+    distinct_field = arg->field_id;
+    ++n_distinct;
   }
+  if (n_distinct && n_distinct != n_aggs) return set_error(LLKV_ERR_INVALID_ARGUMENT, "DISTINCT and plain aggregates cannot share one fused scan on this path");
   CTX_LOCK(ctx);
   CUDA_TRY(cudaSetDevice(ctx->device));
   llkv_gpu_agg* a = new llkv_gpu_agg();
@@ -2679,13 +2698,46 @@ extern "C" int32_t llkv_gpu_agg_create(llkv_gpu_ctx* ctx, uint64_t table_id, con
     return set_error(LLKV_ERR_IO, "CUDA error %s allocating aggregate state", cudaGetErrorString(e));
   }
   *a->h_flags = 0;
+  if (n_distinct) {  // the set of distinct values = the groups of GROUP BY <column> (COUNT(*) per value keeps the table's layout simple)
+    llkv_agg_spec count_star;
+    memset(&count_star, 0, sizeof(count_star));
+    count_star.kind = LLKV_AGG_COUNT;
+    count_star.expr_root = -1;
+    count_star.data_type = LLKV_PT_INT64;
+    const int32_t rc = llkv_gpu_agg_create(ctx, table_id, &count_star, 1, nullptr, 0, &distinct_field, 1, LLKV_EXPR_EXACT,
+                                           cardinality_hint ? cardinality_hint : 1024, &a->inner);
+    if (rc) {
+      llkv_gpu_agg_destroy(a);
+      return rc;
+    }
+  }
   *out = a;
+  return LLKV_OK;
+}
+
+extern "C" int32_t llkv_gpu_agg_set_output(llkv_gpu_agg* a, const llkv_having_term* having, int32_t n_having, const llkv_order_key* order,
+                                            int32_t n_order, uint64_t offset, uint64_t limit) {
+  if (!a || n_having < 0 || n_order < 0 || (n_having && !having) || (n_order && !order)) return set_error(LLKV_ERR_INVALID_ARGUMENT, "bad output arguments");
+  CTX_LOCK(a->ctx);
+  const int32_t n_aggs = (int32_t)a->specs.size(), n_keys = (int32_t)a->keys.size();
+  for (int i = 0; i < n_having; ++i)
+    if (having[i].index < 0 || having[i].index >= (having[i].is_aggregate ? n_aggs : n_keys) || having[i].cmp_op < LLKV_CMP_EQ || having[i].cmp_op > LLKV_CMP_GE)
+      return set_error(LLKV_ERR_INVALID_ARGUMENT, "HAVING term %d refers to output column %d", i, having[i].index);
+  for (int i = 0; i < n_order; ++i)
+    if (order[i].index < 0 || order[i].index >= (order[i].is_aggregate ? n_aggs : n_keys))
+      return set_error(LLKV_ERR_INVALID_ARGUMENT, "ORDER BY key %d refers to output column %d", i, order[i].index);
+  a->having.assign(having, having + n_having);
+  a->order.assign(order, order + n_order);
+  a->out_offset = offset;
+  a->out_limit = limit;
   return LLKV_OK;
 }
 
 extern "C" void llkv_gpu_agg_destroy(llkv_gpu_agg* a) {
   if (!a) return;
   CTX_LOCK(a->ctx);
+  if (a->inner) llkv_gpu_agg_destroy(a->inner);
+  a->inner = nullptr;
   cudaSetDevice(a->ctx->device);
   cudaStreamSynchronize(a->ctx->stream);
   if (a->d_gclass) cudaFree(a->d_gclass);
@@ -3366,7 +3418,7 @@ static int32_t agg_launch(llkv_gpu_agg* a, const llkv_gpu_program* prog, int app
     if (use_tile_list ? list_pos >= list_n : re >= row_end) break;
   }
   if (ctx->timing) CUDA_TRY(cudaEventRecord(ctx->ev1, ctx->stream));
-  if ((rc = agg_queue_result_copy(a))) return rc;
+  if (!a->skip_scan_copy && (rc = agg_queue_result_copy(a))) return rc;
   a->info.rows = row_end - row_begin;
   a->info.kernel_launches = launches;
   a->info.used_wide_path = a->cr.wide ? 1 : 0;
@@ -3504,6 +3556,7 @@ static int32_t agg_resolve(llkv_gpu_agg* a) {
 
 extern "C" int32_t llkv_gpu_agg_reset(llkv_gpu_agg* a) {
   if (!a) return set_error(LLKV_ERR_INVALID_ARGUMENT, "agg is NULL");
+  if (a->inner) return llkv_gpu_agg_reset(a->inner);
   llkv_gpu_ctx* ctx = a->ctx;
   CTX_LOCK(ctx);
   CUDA_TRY(cudaSetDevice(ctx->device));
@@ -3520,6 +3573,7 @@ extern "C" int32_t llkv_gpu_agg_reset(llkv_gpu_agg* a) {
 }
 
 static int32_t agg_run_impl(llkv_gpu_agg* a, const llkv_gpu_program* prog, int32_t apply_mvcc, uint64_t row_begin, uint64_t row_end) {
+  if (a->inner) return agg_run_impl(a->inner, prog, apply_mvcc, row_begin, row_end);
   if (a->err_code) return set_error(a->err_code, "%s", a->err_msg.c_str());
   int32_t rc = agg_resolve(a);
   if (rc) return rc;
@@ -3556,6 +3610,7 @@ extern "C" int32_t llkv_gpu_agg_run(llkv_gpu_agg* a, const llkv_gpu_program* pro
 
 extern "C" int32_t llkv_gpu_agg_run_info(const llkv_gpu_agg* a, llkv_run_info* out) {
   if (!a || !out) return set_error(LLKV_ERR_INVALID_ARGUMENT, "NULL argument");
+  if (a->inner) a = a->inner;
   *out = a->info;
   return LLKV_OK;
 }
@@ -3804,6 +3859,10 @@ static int32_t agg_ensure_layout(llkv_gpu_agg* a) {
 
 extern "C" int32_t llkv_gpu_agg_group_count(llkv_gpu_agg* a, uint64_t* out_groups) {
   if (!a || !out_groups) return set_error(LLKV_ERR_INVALID_ARGUMENT, "NULL argument");
+  if (a->inner) {  // DISTINCT aggregates are ungrouped: one row
+    *out_groups = 1;
+    return LLKV_OK;
+  }
   CTX_LOCK(a->ctx);
   CUDA_TRY(cudaSetDevice(a->ctx->device));
   if (a->err_code) return set_error(a->err_code, "%s", a->err_msg.c_str());
@@ -3817,11 +3876,124 @@ extern "C" int32_t llkv_gpu_agg_group_count(llkv_gpu_agg* a, uint64_t* out_group
   return LLKV_OK;
 }
 
+// ---- output shaping: HAVING / ORDER BY / OFFSET / LIMIT over the finalized rows (llkv-executor/src/lib.rs:5306-5348) -----
+static i128 cell_i128(const llkv_agg_value& v) { return (i128)(((u128)v.hi << 64) | (u128)v.lo); }
+static double cell_f64(const llkv_agg_value& v) {
+  double d;
+  memcpy(&d, &v.lo, 8);
+  return d;
+}
+// three-way compare of two cells of one output column (same type); NaN sorts above every number, like arrow's sort
+static int compare_values(const llkv_agg_value& x, const llkv_agg_value& y) {
+  if (x.type == LLKV_PT_FLOAT64) {
+    const double a = cell_f64(x), b = cell_f64(y);
+    const bool an = a != a, bn = b != b;
+    if (an || bn) return an == bn ? 0 : (an ? 1 : -1);
+    return a < b ? -1 : (a > b ? 1 : 0);
+  }
+  const i128 a = x.type == LLKV_PT_DECIMAL128 ? cell_i128(x) : (i128)(i64)x.lo, b = y.type == LLKV_PT_DECIMAL128 ? cell_i128(y) : (i128)(i64)y.lo;
+  return a < b ? -1 : (a > b ? 1 : 0);
+}
+static int compare_keys(const llkv_group_key& x, const llkv_group_key& y) {
+  const bool uns = x.type == LLKV_PT_UTF8 || x.type == LLKV_PT_UINT64 || x.type == LLKV_PT_UINT32 || x.type == LLKV_PT_UINT16 || x.type == LLKV_PT_UINT8 ||
+                   x.type == LLKV_PT_BOOLEAN;  // (strings: bytes from the top byte, length in the low one: byte order)
+  if (uns) return x.bits < y.bits ? -1 : (x.bits > y.bits ? 1 : 0);
+  return (i64)x.bits < (i64)y.bits ? -1 : ((i64)x.bits > (i64)y.bits ? 1 : 0);
+}
+// TRUE / FALSE of `cell cmp literal`; a NULL cell is neither (HAVING keeps rows that evaluate to TRUE only)
+static bool having_holds(const llkv_having_term& t, const llkv_agg_value* v, const llkv_group_key* k) {
+  int c;
+  if (t.is_aggregate) {
+    if (!v->valid) return false;
+    if (v->type == LLKV_PT_FLOAT64 || t.literal.kind == LLKV_LIT_FLOAT64) {
+      double lit;
+      if (t.literal.kind == LLKV_LIT_FLOAT64) memcpy(&lit, &t.literal.lo, 8);
+      else lit = (double)(i128)(((u128)t.literal.hi << 64) | t.literal.lo) / pow(10.0, t.literal.kind == LLKV_LIT_DECIMAL128 ? t.literal.scale : 0);
+      const double x = v->type == LLKV_PT_FLOAT64 ? cell_f64(*v) : (double)(v->type == LLKV_PT_DECIMAL128 ? cell_i128(*v) : (i128)(i64)v->lo) /
+                                                                       pow(10.0, v->type == LLKV_PT_DECIMAL128 ? v->scale : 0);
+      c = x < lit ? -1 : (x > lit ? 1 : 0);
+    } else {  // exact: both sides as integers at the larger scale
+      i128 x = v->type == LLKV_PT_DECIMAL128 ? cell_i128(*v) : (i128)(i64)v->lo, lit = (i128)(((u128)t.literal.hi << 64) | t.literal.lo);
+      int sx = v->type == LLKV_PT_DECIMAL128 ? v->scale : 0, sl = t.literal.kind == LLKV_LIT_DECIMAL128 ? t.literal.scale : 0;
+      for (; sx < sl; ++sx) x *= 10;
+      for (; sl < sx; ++sl) lit *= 10;
+      c = x < lit ? -1 : (x > lit ? 1 : 0);
+    }
+  } else {
+    if (!k->valid) return false;
+    llkv_group_key lit = *k;
+    if (t.literal.kind == LLKV_LIT_STRING) {  // literal bytes (little endian in lo/hi) -> the key's packed form
+      uint64_t bits = 0;
+      const unsigned len = t.literal.precision;
+      if (len > 7) return false;
+      for (unsigned i = 0; i < len; ++i) bits |= (uint64_t)((t.literal.lo >> (8 * i)) & 0xff) << (56 - 8 * i);
+      lit.bits = bits | len;
+    } else {
+      lit.bits = t.literal.lo;
+    }
+    c = compare_keys(*k, lit);
+  }
+  switch (t.cmp_op) {
+    case LLKV_CMP_EQ: return c == 0;
+    case LLKV_CMP_NE: return c != 0;
+    case LLKV_CMP_LT: return c < 0;
+    case LLKV_CMP_LE: return c <= 0;
+    case LLKV_CMP_GT: return c > 0;
+    default: return c >= 0;
+  }
+}
+
+// DISTINCT aggregates from the inner aggregation's groups (one per distinct value; the NULL group does not count)
+static int32_t finalize_distinct(llkv_gpu_agg* a, llkv_agg_value* out) {
+  llkv_gpu_agg* in = a->inner;
+  int32_t rc = agg_resolve(in);
+  if (rc) return rc;
+  if ((rc = agg_ensure_layout(in))) return rc;
+  std::vector<u64> hk, hw;
+  std::vector<GroupRef> groups;
+  if ((rc = agg_collect(in, hk, hw, groups))) return rc;
+  i128 sum = 0;
+  u64 count = 0;
+  for (const GroupRef& g : groups) {
+    if (g.slot == in->gcap + 1) continue;  // NULL key
+    llkv_group_key k;
+    decode_keys(in, g.slot < in->gcap ? hk[g.slot] : kEmptyKey, false, &k);
+    if (k.type == LLKV_PT_UTF8 || k.type == LLKV_PT_BOOLEAN) return agg_fail(a, LLKV_ERR_INVALID_ARGUMENT, "DISTINCT aggregates on this path take integer columns");
+    const bool uns = k.type == LLKV_PT_UINT64;
+    sum += uns ? (i128)k.bits : (i128)(i64)k.bits;
+    ++count;
+  }
+  for (size_t i = 0; i < a->specs.size(); ++i) {
+    llkv_agg_value* o = &out[i];
+    switch (a->specs[i].kind) {
+      case LLKV_AGG_COUNT: val_i64(o, (i64)count, 1); break;
+      case LLKV_AGG_SUM:
+        if (!count) { val_i64(o, 0, 0); break; }
+        if (sum < (i128)INT64_MIN || sum > (i128)INT64_MAX) return agg_fail(a, LLKV_ERR_INVALID_ARGUMENT, "integer overflow");
+        val_i64(o, (i64)sum, 1);
+        break;
+      case LLKV_AGG_TOTAL: val_f64(o, (double)sum, 1); break;
+      default:  // AVG
+        if (!count) { val_f64(o, 0, 0); break; }
+        val_f64(o, (double)sum / (double)count, 1);
+        break;
+    }
+  }
+  return LLKV_OK;
+}
+
 extern "C" int32_t llkv_gpu_agg_finalize(llkv_gpu_agg* a, llkv_agg_value* out_values, llkv_group_key* out_keys, uint64_t group_capacity,
                                           uint64_t* out_groups) {
   if (!a) return set_error(LLKV_ERR_INVALID_ARGUMENT, "agg is NULL");
   CTX_LOCK(a->ctx);
   CUDA_TRY(cudaSetDevice(a->ctx->device));
+  if (a->inner) {
+    if (group_capacity < 1 || !out_values) return set_error(LLKV_ERR_INVALID_ARGUMENT, "output buffer too small");
+    const int32_t drc = finalize_distinct(a, out_values);
+    if (drc) return drc;
+    if (out_groups) *out_groups = 1;
+    return LLKV_OK;
+  }
   if (a->err_code) return set_error(a->err_code, "%s", a->err_msg.c_str());
   int32_t rc = agg_resolve(a);
   if (rc) return rc;
@@ -3829,20 +4001,70 @@ extern "C" int32_t llkv_gpu_agg_finalize(llkv_gpu_agg* a, llkv_agg_value* out_va
   std::vector<u64> hk, hw;
   std::vector<GroupRef> groups;
   if ((rc = agg_collect(a, hk, hw, groups))) return rc;
-  if (groups.size() > group_capacity)
-    return set_error(LLKV_ERR_INVALID_ARGUMENT, "group capacity %llu < %llu groups", (unsigned long long)group_capacity, (unsigned long long)groups.size());
   const size_t n_aggs = a->specs.size(), n_keys = a->keys.size();
-  if ((n_aggs && !out_values) || (n_keys && !out_keys)) return set_error(LLKV_ERR_INVALID_ARGUMENT, "output buffer is NULL");
+  const bool shaped = !a->having.empty() || !a->order.empty() || a->out_offset || a->out_limit;
+  if (!shaped) {
+    if (groups.size() > group_capacity)
+      return set_error(LLKV_ERR_INVALID_ARGUMENT, "group capacity %llu < %llu groups", (unsigned long long)group_capacity, (unsigned long long)groups.size());
+    if ((n_aggs && !out_values) || (n_keys && !out_keys)) return set_error(LLKV_ERR_INVALID_ARGUMENT, "output buffer is NULL");
+    for (size_t gi = 0; gi < groups.size(); ++gi) {
+      const u64 s = groups[gi].slot;
+      if ((rc = finalize_group(a, &hw[s * a->n_gwords], out_values + gi * n_aggs))) return rc;
+      if (n_keys) {
+        const bool null_slot = s == a->gcap + 1;
+        const u64 K = s < a->gcap ? hk[s] : kEmptyKey;
+        decode_keys(a, K, null_slot, out_keys + gi * n_keys);
+      }
+    }
+    if (out_groups) *out_groups = groups.size();
+    return LLKV_OK;
+  }
+  // every group first (first-appearance order), then HAVING, ORDER BY (stable), OFFSET / LIMIT
+  std::vector<llkv_agg_value> vals(groups.size() * std::max<size_t>(1, n_aggs));
+  std::vector<llkv_group_key> keys(groups.size() * std::max<size_t>(1, n_keys));
   for (size_t gi = 0; gi < groups.size(); ++gi) {
     const u64 s = groups[gi].slot;
-    if ((rc = finalize_group(a, &hw[s * a->n_gwords], out_values + gi * n_aggs))) return rc;
-    if (n_keys) {
-      const bool null_slot = s == a->gcap + 1;
-      const u64 K = s < a->gcap ? hk[s] : kEmptyKey;
-      decode_keys(a, K, null_slot, out_keys + gi * n_keys);
-    }
+    if ((rc = finalize_group(a, &hw[s * a->n_gwords], vals.data() + gi * n_aggs))) return rc;
+    if (n_keys) decode_keys(a, s < a->gcap ? hk[s] : kEmptyKey, s == a->gcap + 1, keys.data() + gi * n_keys);
   }
-  if (out_groups) *out_groups = groups.size();
+  std::vector<size_t> rows;
+  for (size_t gi = 0; gi < groups.size(); ++gi) {
+    bool keep = true;
+    for (const llkv_having_term& t : a->having)
+      keep = keep && having_holds(t, t.is_aggregate ? &vals[gi * n_aggs + (size_t)t.index] : nullptr, t.is_aggregate ? nullptr : &keys[gi * n_keys + (size_t)t.index]);
+    if (keep) rows.push_back(gi);
+  }
+  if (!a->order.empty())
+    std::stable_sort(rows.begin(), rows.end(), [&](size_t x, size_t y) {
+      for (const llkv_order_key& o : a->order) {
+        bool xv, yv;
+        int c;
+        if (o.is_aggregate) {
+          const llkv_agg_value &vx = vals[x * n_aggs + (size_t)o.index], &vy = vals[y * n_aggs + (size_t)o.index];
+          xv = vx.valid;
+          yv = vy.valid;
+          c = xv && yv ? compare_values(vx, vy) : 0;
+        } else {
+          const llkv_group_key &kx = keys[x * n_keys + (size_t)o.index], &ky = keys[y * n_keys + (size_t)o.index];
+          xv = kx.valid;
+          yv = ky.valid;
+          c = xv && yv ? compare_keys(kx, ky) : 0;
+        }
+        if (xv != yv) return o.nulls_first ? !xv : xv;  // NULLs go where nulls_first says, whatever the direction
+        if (c) return o.descending ? c > 0 : c < 0;
+      }
+      return false;
+    });
+  const size_t begin = std::min<size_t>(rows.size(), (size_t)a->out_offset);
+  const size_t end = a->out_limit ? std::min<size_t>(rows.size(), begin + (size_t)a->out_limit) : rows.size();
+  if (end - begin > group_capacity)
+    return set_error(LLKV_ERR_INVALID_ARGUMENT, "group capacity %llu < %llu groups", (unsigned long long)group_capacity, (unsigned long long)(end - begin));
+  if ((n_aggs && !out_values) || (n_keys && !out_keys)) return set_error(LLKV_ERR_INVALID_ARGUMENT, "output buffer is NULL");
+  for (size_t i = begin; i < end; ++i) {
+    if (n_aggs) memcpy(out_values + (i - begin) * n_aggs, vals.data() + rows[i] * n_aggs, n_aggs * sizeof(llkv_agg_value));
+    if (n_keys) memcpy(out_keys + (i - begin) * n_keys, keys.data() + rows[i] * n_keys, n_keys * sizeof(llkv_group_key));
+  }
+  if (out_groups) *out_groups = end - begin;
   return LLKV_OK;
 }
 
@@ -3985,6 +4207,7 @@ static bool merge_is_p2p(const llkv_gpu_agg* a) {
 }
 
 static int32_t agg_merge_impl(llkv_gpu_agg* a) {
+  if (a->inner) return agg_merge_impl(a->inner);
   llkv_gpu_ctx* ctx = a->ctx;
   if (a->err_code) return set_error(a->err_code, "%s", a->err_msg.c_str());
   int32_t rc;
@@ -4125,6 +4348,7 @@ extern "C" int32_t llkv_gpu_agg_execute(llkv_gpu_agg* a, const llkv_gpu_program*
                                          int32_t merge) {
   if (!a) return set_error(LLKV_ERR_INVALID_ARGUMENT, "agg is NULL");
   if (row_end < row_begin) return set_error(LLKV_ERR_INVALID_ARGUMENT, "row_end < row_begin");
+  if (a->inner) return llkv_gpu_agg_execute(a->inner, prog, apply_mvcc, row_begin, row_end, merge);
   llkv_gpu_ctx* ctx = a->ctx;
   CTX_LOCK(ctx);
   CUDA_TRY(cudaSetDevice(ctx->device));
@@ -4184,7 +4408,9 @@ extern "C" int32_t llkv_gpu_agg_execute(llkv_gpu_agg* a, const llkv_gpu_program*
     cudaError_t e = cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal);
     int32_t rc = LLKV_OK;
     if (e == cudaSuccess) {
+      a->skip_scan_copy = do_merge;  // (capturing implies merge_is_p2p: the merge queues the copies)
       rc = agg_run_impl(a, prog, apply_mvcc, row_begin, row_end);
+      a->skip_scan_copy = false;
       if (!rc && do_merge) rc = agg_merge_impl(a);
       cudaGraph_t graph = nullptr;
       e = cudaStreamEndCapture(ctx->stream, &graph);
@@ -4220,7 +4446,9 @@ extern "C" int32_t llkv_gpu_agg_execute(llkv_gpu_agg* a, const llkv_gpu_program*
     cudaStreamSynchronize(ctx->stream);
     cudaGetLastError();
   }
+  a->skip_scan_copy = do_merge && merge_is_p2p(a);
   int32_t rc = agg_run_impl(a, prog, apply_mvcc, row_begin, row_end);
+  a->skip_scan_copy = false;
   if (!rc && do_merge) rc = agg_merge_impl(a);
   return rc;
 }

@@ -990,13 +990,12 @@ __global__ void merge_ungrouped_kernel(u64* dst, const u64* all_words, int n_ran
 }
 
 // Ungrouped multi-GPU merge over NVLink peer memory, no collective library on the path: every rank stores its state row
-// into a mailbox slot on every peer (plain stores into peer-mapped memory, cudaIpc), publishes it with a release flag, waits
-// for the flags of all ranks in its own mailbox and folds the rows in rank order (bit-identical states on all ranks, f64
-// sums included).  One small kernel per rank and merge; latency = one NVLink store + flag round.
-//   mailbox layout per rank: [source rank][epoch parity][kMergeMboxWords]; word kMergeMboxWords-1 is the flag (= epoch).
-// Two parities: a rank can be one merge ahead of a peer, never two (merge e+1 needs the peer's flag of e+1, which the
-// peer's stream writes after its merge e).  A peer that never arrives ends the wait after ~10 s with FLAG_MERGE_TIMEOUT.
-constexpr uint32_t kMergeMboxWords = 128;
+// into a mailbox slot on every peer (plain stores into peer-mapped memory, cudaIpc), waits for the rows of all ranks in its
+// own mailbox and folds them in rank order (bit-identical states on all ranks, f64 sums included).  One small kernel per
+// rank and merge.
+//   mailbox layout per rank: [source rank][merge parity][slot].  Two parities: a rank can be one merge ahead of a peer, never
+//   two (merge e+1 needs the peer's data of e+1, which the peer's stream writes after its merge e).  A peer that never
+//   arrives ends the wait after ~10 s with FLAG_MERGE_TIMEOUT.
 struct PeerMailboxes {
   u64* box[8];
 };
@@ -1013,51 +1012,64 @@ __device__ __forceinline__ u64 global_timer_ns() {
 }
 // The merge number (`epoch`) lives in device memory and advances with every exchange, in step on all ranks: the launch
 // has no per-merge parameter, so a captured CUDA graph replays it.
-__global__ void merge_ungrouped_p2p_kernel(u64* state, PeerMailboxes peers, int n_ranks, int rank, uint32_t n_gwords, u64* epoch_dev,
-                                           const uint8_t* word_class_dev, uint32_t* flags) {
-  const uint32_t w = threadIdx.x;
+//
+// The exchange itself is flag-in-data (the "LL" idea of collective libraries): every 64-bit state word travels as two
+// 8-byte packets (32 bits of data | the merge number), one plain store each — 8-byte stores are single-copy atomic, so a
+// packet whose upper half shows the current merge number is complete by itself.  No fence, no separate flag, no release /
+// acquire round: the latency of a merge is one NVLink store plus the poll (measured: ~20 us with fence + flag).
+constexpr uint32_t kMergePackets = 256;  // packets per (source rank, parity) slot = kUngroupedSlotWords of the runtime
+__device__ __forceinline__ void st_volatile_u64(u64* p, u64 v) { asm volatile("st.volatile.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory"); }
+__device__ __forceinline__ u64 ld_volatile_u64(const u64* p) {
+  u64 v;
+  asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__global__ void __launch_bounds__(kMergePackets) merge_ungrouped_p2p_kernel(u64* state, PeerMailboxes peers, int n_ranks, int rank, uint32_t n_gwords,
+                                                                            u64* epoch_dev, const uint8_t* word_class_dev, uint32_t* flags) {
+  const uint32_t t = threadIdx.x;  // packet index: word t / 2, half t & 1
   const u64 epoch = *epoch_dev + 1;
-  __syncthreads();  // every thread has read the counter
-  if (w == 0) *epoch_dev = epoch;
-  const uint32_t slot = (uint32_t)(rank * 2 + (int)(epoch & 1)) * kMergeMboxWords;
-  if (w < n_gwords) {
-    const u64 v = state[w];
-    for (int r = 0; r < n_ranks; ++r) peers.box[r][slot + w] = v;
-  }
-  __threadfence_system();
-  __syncthreads();
-  if (w < (uint32_t)n_ranks) st_release_sys(&peers.box[w][slot + kMergeMboxWords - 1], epoch);
+  __shared__ uint32_t s_part[8][kMergePackets];
   __shared__ int timed_out;
-  if (w == 0) timed_out = 0;
-  __syncthreads();
-  if (w < (uint32_t)n_ranks) {
-    const u64* flag = &peers.box[rank][(w * 2 + (uint32_t)(epoch & 1)) * kMergeMboxWords + kMergeMboxWords - 1];
+  if (t == 0) timed_out = 0;
+  __syncthreads();  // every thread has read the counter
+  if (t == 0) *epoch_dev = epoch;
+  const uint32_t e32 = (uint32_t)epoch, par = (uint32_t)(epoch & 1);
+  const bool on = (t >> 1) < n_gwords;
+  if (on) {
+    const u64 v = state[t >> 1];
+    const u64 pkt = ((u64)e32 << 32) | (uint32_t)((t & 1) ? (v >> 32) : v);
+    for (int r = 0; r < n_ranks; ++r) st_volatile_u64(&peers.box[r][(uint32_t)(rank * 2 + (int)par) * kMergePackets + t], pkt);
+    const u64* mine = peers.box[rank];
     const u64 t0 = global_timer_ns();
-    while (ld_acquire_sys(flag) != epoch) {
-      if (global_timer_ns() - t0 > 10000000000ull) {
-        timed_out = 1;
-        break;
+    for (int r = 0; r < n_ranks; ++r) {
+      const u64* src = &mine[((uint32_t)r * 2 + par) * kMergePackets + t];
+      u64 pk = ld_volatile_u64(src);
+      while ((uint32_t)(pk >> 32) != e32) {
+        if (global_timer_ns() - t0 > 10000000000ull) {
+          timed_out = 1;
+          break;
+        }
+        __nanosleep(100);
+        pk = ld_volatile_u64(src);
       }
-      __nanosleep(200);
+      s_part[r][t] = (uint32_t)pk;
     }
   }
   __syncthreads();
   if (timed_out) {
-    if (w == 0) atomicOr(flags, FLAG_MERGE_TIMEOUT);
+    if (t == 0) atomicOr(flags, FLAG_MERGE_TIMEOUT);
     return;
   }
-  __threadfence_system();
+  const uint32_t w = t;
   if (w >= n_gwords) return;
   const uint8_t c = word_class_dev[w];
   if (c == WC_PAIR_LO_MIN || c == WC_PAIR_LO_MAX) return;  // written with its high word
-  const u64* mine = peers.box[rank];
-  const uint32_t par = (uint32_t)(epoch & 1);
+  auto word_of = [&](int r, uint32_t x) -> u64 { return (u64)s_part[r][2 * x] | ((u64)s_part[r][2 * x + 1] << 32); };
   if (c == WC_MIN128 || c == WC_MAX128) {
     const bool is_max = c == WC_MAX128;
     u64 bh = is_max ? 0ull : ~0ull, bl = bh;
     for (int r = 0; r < n_ranks; ++r) {
-      const u64* row = mine + ((uint32_t)r * 2 + par) * kMergeMboxWords;
-      const u64 h = row[w], l = row[w + 1];
+      const u64 h = word_of(r, w), l = word_of(r, w + 1);
       const bool better = is_max ? (h > bh || (h == bh && l > bl)) : (h < bh || (h == bh && l < bl));
       if (better) { bh = h; bl = l; }
     }
@@ -1068,7 +1080,7 @@ __global__ void merge_ungrouped_p2p_kernel(u64* state, PeerMailboxes peers, int 
   u64 acc = c == WC_MIN ? ~0ull : 0ull;
   double facc = 0.0;
   for (int r = 0; r < n_ranks; ++r) {
-    const u64 v = mine[((uint32_t)r * 2 + par) * kMergeMboxWords + w];
+    const u64 v = word_of(r, w);
     switch (c) {
       case WC_SUM: acc += v; break;
       case WC_FSUM: facc += __longlong_as_double((i64)v); break;
@@ -1245,7 +1257,7 @@ cudaError_t launch_merge_ungrouped_p2p(u64* state, u64* const* peer_boxes, int n
                                        const uint8_t* word_class_dev, uint32_t* flags, cudaStream_t stream) {
   PeerMailboxes pm;
   for (int r = 0; r < 8; ++r) pm.box[r] = r < n_ranks ? peer_boxes[r] : nullptr;
-  merge_ungrouped_p2p_kernel<<<1, kMergeMboxWords, 0, stream>>>(state, pm, n_ranks, rank, n_gwords, epoch_dev, word_class_dev, flags);
+  merge_ungrouped_p2p_kernel<<<1, kMergePackets, 0, stream>>>(state, pm, n_ranks, rank, n_gwords, epoch_dev, word_class_dev, flags);
   return cudaGetLastError();
 }
 cudaError_t launch_merge_grouped_p2p(u64* gkeys, u64* gwords, u64 gcap, uint32_t n_gwords, const uint8_t* word_class_dev, uint32_t* flags,

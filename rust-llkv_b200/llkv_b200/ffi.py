@@ -61,6 +61,14 @@ class AggSpec(C.Structure):
                 ("precision", C.c_uint8), ("scale", C.c_int8), ("distinct", C.c_uint8), ("_pad", C.c_uint8)]
 
 
+class HavingTerm(C.Structure):
+    _fields_ = [("is_aggregate", C.c_int32), ("index", C.c_int32), ("cmp_op", C.c_int32), ("_pad", C.c_int32), ("literal", Literal)]
+
+
+class OrderKey(C.Structure):
+    _fields_ = [("is_aggregate", C.c_int32), ("index", C.c_int32), ("descending", C.c_int32), ("nulls_first", C.c_int32)]
+
+
 class AggValue(C.Structure):
     _fields_ = [("lo", C.c_uint64), ("hi", C.c_uint64), ("type", C.c_int32), ("precision", C.c_uint8),
                 ("scale", C.c_int8), ("valid", C.c_uint8), ("_pad", C.c_uint8)]

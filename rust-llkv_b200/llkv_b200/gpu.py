@@ -97,6 +97,7 @@ def load():
         "llkv_gpu_agg_group_count": (i32, [vp, P(u64)]),
         "llkv_gpu_agg_finalize": (i32, [vp, vp, vp, u64, P(u64)]),
         "llkv_gpu_agg_run_info": (i32, [vp, P(ffi.RunInfo)]),
+        "llkv_gpu_agg_set_output": (i32, [vp, vp, i32, vp, i32, u64, u64]),
         "llkv_gpu_agg_destroy": (None, [vp]),
         "llkv_gpu_comm_unique_id": (i32, [vp]),
         "llkv_gpu_comm_init": (i32, [vp, vp, i32, i32]),
@@ -432,6 +433,24 @@ class Aggregation:
         """reset + run + (merge, when the context has peers) in one call (llkv_gpu_agg_execute)."""
         row_end = self.table.n_rows if row_end is None else row_end
         _check(self.lib.llkv_gpu_agg_execute(self.handle, program.handle if program else None, int(apply_mvcc), row_begin, row_end, int(merge)))
+
+    def set_output(self, having=(), order_by=(), offset: int = 0, limit: int = 0):
+        """HAVING / ORDER BY / OFFSET / LIMIT over the finalized rows.  having: [("agg" | "key", index, CompareOp code, literal)],
+        order_by: [("agg" | "key", index, descending, nulls_first)]."""
+        from .expr import lit
+        h = (ffi.HavingTerm * max(1, len(having)))()
+        for i, (what, index, op, value) in enumerate(having):
+            h[i].is_aggregate = int(what == "agg")
+            h[i].index = index
+            h[i].cmp_op = op
+            h[i].literal = lit(value).to_c()
+        o = (ffi.OrderKey * max(1, len(order_by)))()
+        for i, (what, index, descending, nulls_first) in enumerate(order_by):
+            o[i].is_aggregate = int(what == "agg")
+            o[i].index = index
+            o[i].descending = int(descending)
+            o[i].nulls_first = int(nulls_first)
+        _check(self.lib.llkv_gpu_agg_set_output(self.handle, h, len(having), o, len(order_by), offset, limit))
 
     def group_count(self) -> int:
         n = C.c_uint64()
