@@ -3958,6 +3958,7 @@ static int32_t finalize_distinct(llkv_gpu_agg* a, llkv_agg_value* out) {
     if (g.slot == in->gcap + 1) continue;  // NULL key
     llkv_group_key k;
     decode_keys(in, g.slot < in->gcap ? hk[g.slot] : kEmptyKey, false, &k);
+    if (!k.valid) continue;  // (a nullable key packs its NULL flag into the key)
     if (k.type == LLKV_PT_UTF8 || k.type == LLKV_PT_BOOLEAN) return agg_fail(a, LLKV_ERR_INVALID_ARGUMENT, "DISTINCT aggregates on this path take integer columns");
     const bool uns = k.type == LLKV_PT_UINT64;
     sum += uns ? (i128)k.bits : (i128)(i64)k.bits;
