@@ -1713,7 +1713,7 @@ class Emitter {
       // a pending "acc = ..." load folds into the instruction that consumes it
       if (!f.empty() && (f.back().op == FO_LD_COL || f.back().op == FO_LD_LIT || f.back().op == FO_LD_TMP) && op != FO_LEAF &&
           op != FO_MVCC && op != FO_SELECT_DONE && op != FO_GROUP && op != FO_END && op != FO_LD_COL && op != FO_LD_LIT &&
-          op != FO_LD_TMP && op != FO_COUNT_STAR && op != FO_FIRSTROW) {
+          op != FO_LD_TMP && op != FO_COUNT_STAR && op != FO_FIRSTROW && op < FO_VALID) {
         in.d = f.back().d;
         in.e = f.back().e;
         in.f = f.back().f;
@@ -1790,25 +1790,38 @@ class Emitter {
     };
 
     const size_t n = code_.size();
+    int mask_depth = 0;  // entries on the kernel's predicate-mask stack (OR / NOT trees)
     for (size_t i = 0; i < n && ok; ++i) {
       const Instr& in = code_[i];
       switch (in.op) {
         case OP_END: femit(FO_END, 0, 0, 0); break;
         case OP_PUSH_COL: {
           const ColumnMeta& c = *plan_cols_[in.a];
-          // typed leaf at the top level: PUSH_COL, PRED_*, FILTER
-          if (i + 2 < n && code_[i + 2].op == OP_FILTER && i + 2 < select_end_) {
+          // typed leaf: PUSH_COL, PRED_*, then FILTER at the top level (a conjunct: ANDed into the selection), anything else
+          // inside an OR / NOT tree (pushed onto the predicate-mask stack)
+          const bool is_leaf = i + 1 < select_end_ && (code_[i + 1].op == OP_PRED_I || code_[i + 1].op == OP_PRED_U || code_[i + 1].op == OP_PRED_D ||
+                                                       code_[i + 1].op == OP_PRED_F || code_[i + 1].op == OP_PRED_ISNULL ||
+                                                       code_[i + 1].op == OP_PRED_NOTNULL || code_[i + 1].op == OP_PRED_ALL);
+          if (is_leaf) {
+            const bool conjunct = i + 2 < n && code_[i + 2].op == OP_FILTER && mask_depth == 0;
             const Instr& pr = code_[i + 1];
+            if (pr.op == OP_PRED_F) return false;  // float leaves stay on the general interpreter
+            if (!conjunct) {
+              if (mask_depth >= 8) return false;
+              ++mask_depth;
+            }
+            const uint32_t push = conjunct ? 0u : 1u;
             // NULL never satisfies a typed predicate: a nullable column's leaf starts from its valid rows
-            if (c.nullable && pr.op != OP_PRED_ISNULL && (pr.op == OP_PRED_ALL || pr.op == OP_PRED_NOTNULL || pr.op == OP_PRED_I || pr.op == OP_PRED_U || pr.op == OP_PRED_D))
+            if (conjunct && c.nullable && (pr.op == OP_PRED_NOTNULL || pr.op == OP_PRED_I || pr.op == OP_PRED_U || pr.op == OP_PRED_D))
               femit(FO_VALID, in.a, 0, 0);
-            if (pr.op == OP_PRED_ALL || pr.op == OP_PRED_NOTNULL) { i += 2; break; }  // every (valid) row: always true
-            if (pr.op == OP_PRED_ISNULL && c.nullable) {
-              femit(FO_VALID, in.a, 1, 0);
-              i += 2;
+            if (pr.op == OP_PRED_ALL || pr.op == OP_PRED_NOTNULL || (pr.op == OP_PRED_ISNULL && (c.nullable || push))) {
+              // Range(Unbounded, Unbounded) is true on every row, IS NOT NULL on the valid ones, IS NULL on the others
+              if (push) femit(FO_VALID, in.a, pr.op == OP_PRED_ALL ? 2 : pr.op == OP_PRED_ISNULL ? 1 : 0, 1);
+              else if (pr.op == OP_PRED_ISNULL) femit(FO_VALID, in.a, 1, 0);
+              i += conjunct ? 2 : 1;
               break;
             }
-            if (pr.op == OP_PRED_I || pr.op == OP_PRED_U || pr.op == OP_PRED_D || pr.op == OP_PRED_ISNULL) {
+            {
               const bool uns = pr.op == OP_PRED_U;
               i128 tmin, tmax;
               if (uns) { tmin = 0; tmax = (i128)UINT64_MAX; } else { tmin = (i128)INT64_MIN; tmax = (i128)INT64_MAX; }
@@ -1852,10 +1865,10 @@ class Emitter {
               femit(FO_LEAF, in.a, map_load(in.b), first);
               f.back().g = uns ? 1u : 0u;
               if (c.load_kind == LK_STR8 || c.load_kind == LK_U8 || c.load_kind == LK_U64) f.back().g = 1u;
-              i += 2;
+              f.back().e = push;  // (1: the leaf's masks go onto the predicate-mask stack)
+              i += conjunct ? 2 : 1;
               break;
             }
-            return false;  // float / IN leaves stay on the general interpreter
           }
           Sym x;
           x.where = Sym::COL;
@@ -1962,6 +1975,25 @@ class Emitter {
           st.back().iv.is_float = true;
           break;
         }
+        case OP_AND: case OP_OR:
+          if (mask_depth < 2) return false;
+          femit(in.op == OP_AND ? FO_MASK_AND : FO_MASK_OR, 0, 0, 0);
+          --mask_depth;
+          break;
+        case OP_NOT:
+          if (mask_depth < 1) return false;
+          femit(FO_MASK_NOT, 0, 0, 0);
+          break;
+        case OP_BOOL_LIT:
+          if (i >= select_end_ || mask_depth >= 8) return false;  // (also the accumulator of an IN list: not on this path)
+          femit(FO_MASK_LIT, in.a ? 1u : 0u, 0, 0);
+          ++mask_depth;
+          break;
+        case OP_FILTER:
+          if (mask_depth != 1) return false;
+          femit(FO_MASK_FILTER, 0, 0, 0);
+          mask_depth = 0;
+          break;
         case OP_MVCC: femit(FO_MVCC, in.a, in.b, 0); break;  // (NULL created_by / deleted_by take their defaults in the kernel)
         case OP_SELECT_DONE: femit(FO_SELECT_DONE, 0, 0, 0); break;
         case OP_GROUP: {

@@ -202,6 +202,9 @@ struct LeanTile {
   u64 pk[Cfg::kPartition ? R : 1];  // partitioned plans: the rows' packed keys, kept from GROUP to scatter()
   unsigned char* const part_smem;
   uint32_t batch_tiles = 0;         // packed form: tiles appended to the batch buffer since the last flush
+  // predicate trees (OR / NOT): a small stack of (rows, not-in-domain) masks, one bit per row of this thread
+  unsigned mt[8], mn[8];
+  int msp = 0;
 
   __device__ __forceinline__ LeanTile(const LeanPlan& plan, const LeanShape& shape, unsigned char* smem, int tid_, int nc)
       : p(plan), S(shape), tid(tid_), NC(nc), T(shape.tile_rows), my4(smem + shape.smem_acc_off + tid_ * 4),
@@ -347,6 +350,7 @@ struct LeanTile {
     rel0 = rel_row0 + (uint32_t)tid;  // launch-relative index of this thread's row r = 0
     negm = 0;
     has_slow = false;
+    msp = 0;
     if (rel_row0 >= begin_rel && rel_row0 + T <= end_rel) {
       actm = (1u << R) - 1u;
     } else {
@@ -417,7 +421,15 @@ struct LeanTile {
 #pragma unroll
           for (int r = 0; r < R; ++r) m |= (unsigned)(((u64)v[r] - (u64)lo) <= span) << r;
         }
-        actm &= m;
+        if (in.e) {  // inside an OR / NOT tree: (valid & in range, not valid)
+          const unsigned all = (1u << R) - 1u;
+          const unsigned v = S.cols[in.a].has_valid ? col_valid(in.a) : all;
+          mt[msp] = m & v;
+          mn[msp] = ~v & all;
+          ++msp;
+        } else {
+          actm &= m;
+        }
         return true;
       }
       case FO_MVCC: if constexpr (live<PC>(FO_MVCC)) {
@@ -787,10 +799,36 @@ struct LeanTile {
         return true;
       }
       case FO_VALID: if constexpr (live<PC>(FO_VALID)) {
-        const unsigned v = col_valid(in.a);
-        actm &= in.b ? ~v : v;
+        const unsigned all = (1u << R) - 1u;
+        const unsigned v = S.cols[in.a].has_valid ? col_valid(in.a) : all;
+        if (in.c) {  // IS NOT NULL / IS NULL / Range(Unbounded, Unbounded) inside a tree; the domain is the valid rows
+          mt[msp] = in.b == 0 ? v : in.b == 1 ? (~v & all) : all;
+          mn[msp] = ~v & all;
+          ++msp;
+        } else {
+          actm &= in.b ? ~v : v;
+        }
         return true;
       }
+      case FO_MASK_AND: case FO_MASK_OR: if constexpr (live<PC>(FO_MASK_AND) || live<PC>(FO_MASK_OR)) {
+        // rows: bitmap AND / OR; domain: intersect / unite (llkv-compute/src/program.rs:500-512)
+        const unsigned t1 = mt[msp - 2], t0 = mt[msp - 1], n1 = mn[msp - 2], n0 = mn[msp - 1];
+        mt[msp - 2] = in.op == FO_MASK_AND ? (t1 & t0) : (t1 | t0);
+        mn[msp - 2] = in.op == FO_MASK_AND ? (n1 | n0) : (n1 & n0);
+        --msp;
+        return true;
+      }
+      case FO_MASK_NOT:  // domain - rows (llkv-scan/src/predicate.rs:167-186)
+        mt[msp - 1] = ~mn[msp - 1] & ~mt[msp - 1] & ((1u << R) - 1u);
+        return true;
+      case FO_MASK_LIT:
+        mt[msp] = in.a ? (1u << R) - 1u : 0u;
+        mn[msp] = 0;
+        ++msp;
+        return true;
+      case FO_MASK_FILTER:
+        actm &= mt[--msp];
+        return true;
       case FO_END:
         if constexpr (Cfg::kStatic && PC >= 0 && !Cfg::kPartition) flush();
         return false;

@@ -2420,7 +2420,8 @@ static int32_t build_request(llkv_gpu_ctx* ctx, uint64_t table_id, const llkv_gp
 static const char* fast_op_name(uint32_t op) {
   static const char* names[] = {"END", "LEAF", "MVCC", "SELECT_DONE", "GROUP", "LD_COL", "LD_LIT", "LD_TMP", "ST_TMP", "OP_COL", "OP_LIT",
                                 "OP_TMP", "DIVR", "MULP", "I2F", "D2F", "COUNT_STAR", "COUNT", "FIRSTROW", "SUM", "FSUM", "MIN_I", "MAX_I",
-                                "MIN_F", "MAX_F", "FIRSTVALID", "FIRSTNAN", "VALID"};
+                                "MIN_F", "MAX_F", "FIRSTVALID", "FIRSTNAN", "VALID", "MASK_AND", "MASK_OR", "MASK_NOT", "MASK_LIT",
+                                "MASK_FILTER"};
   return op < sizeof(names) / sizeof(names[0]) ? names[op] : "?";
 }
 static std::string lean_listing(const LeanPlan& lp, const Geometry& g, uint32_t ctas) {
@@ -3287,7 +3288,7 @@ static int32_t agg_launch(llkv_gpu_agg* a, const llkv_gpu_program* prog, int app
     uint64_t key = fnv_pod(fnv_pod(fnv_pod(fnv_pod(sig, p.tile_rows), row_begin), row_end), ctx->prune_mode);
     for (uint32_t i = 0; i < lean.s.n_code; ++i) {
       const FInstr& in = lean.s.code[i];
-      if (in.op != FO_LEAF) continue;
+      if (in.op != FO_LEAF || in.e) continue;  // (a leaf inside an OR / NOT tree is no conjunct)
       llkv_gpu_column* col = nullptr;
       for (llkv_gpu_column* h : handles)
         if (h->values == lean.col_base[in.a]) col = h;

@@ -109,6 +109,13 @@ enum FastOp : uint16_t {
                   // a bit7 = 4-limb global layout
   FO_FSUM, FO_MIN_I, FO_MAX_I, FO_MIN_F, FO_MAX_F, FO_FIRSTVALID, FO_FIRSTNAN,
   FO_VALID,       // a = column, b = 0: active &= row is valid (not NULL) in the column / 1: active &= row is NULL in it
+                  // c = 1: pushed onto the predicate-mask stack instead (b = 2: Range(Unbounded, Unbounded), true on every row)
+  // Predicate trees (OR / NOT, llkv-scan/src/predicate.rs:32-193,665-777) on a small stack of (rows, not-in-domain) bit masks,
+  // one bit per row of the thread.  FO_LEAF with e = 1 pushes (valid & in range, ~valid) instead of ANDing into the selection.
+  FO_MASK_AND, FO_MASK_OR,  // rows: and / or; not-in-domain: or / and (domains intersect / unite, llkv-compute/src/program.rs:500-512)
+  FO_MASK_NOT,    // rows = domain - rows
+  FO_MASK_LIT,    // a = 0 / 1: push a constant, determined on every row
+  FO_MASK_FILTER, // pop: active &= rows
   FO_COUNT_
 };
 #if defined(__CUDACC__) || defined(__CUDACC_RTC__)

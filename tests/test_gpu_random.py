@@ -115,3 +115,73 @@ def test_random_plans_match_oracle(gpu_ctx, seed):
         gpu_ctx.set_jit(1)
         gpu_ctx.set_partitioning(1)
         dt.destroy()
+
+
+# ---------------------------------------------------------------------------------- OR / NOT trees, NULLs: still the lean kernel
+def random_tree(rng, depth=0):
+    """AND / OR / NOT trees over typed leaves on integer, decimal, date and boolean columns (three-valued logic with
+    domains when the columns are nullable: llkv-scan/src/predicate.rs:167-186,665-777)."""
+    leaves = [
+        lambda: pred(1, Operator.Range(Bound.Included(int(rng.integers(-900, 0))), Bound.Excluded(int(rng.integers(0, 900))))),
+        lambda: pred(2, Operator.LessThan(int(rng.integers(-40, 50)))),
+        lambda: pred(4, Operator.GreaterThanOrEquals(int(rng.integers(0, 400)))),
+        lambda: pred(5, Operator.Range(Bound.Included(Literal.Decimal128(int(rng.integers(-10**7, 0)), 2)), Bound.Included(Literal.Decimal128(int(rng.integers(0, 10**7)), 2)))),
+        lambda: pred(6, Operator.LessThanOrEquals(Literal.Date32(int(rng.integers(8000, 11000))))),
+        lambda: pred(1, Operator.Equals(int(rng.integers(-5, 5)))),
+        lambda: pred(9, Operator.Equals(bool(rng.integers(0, 2)))),
+        lambda: pred(5, Operator.IsNull),
+        lambda: pred(2, Operator.IsNotNull),
+        lambda: pred(4, Operator.Range(Bound.Unbounded, Bound.Unbounded)),
+    ]
+    r = rng.random()
+    if depth >= 3 or r < 0.35:
+        return leaves[int(rng.integers(0, len(leaves)))]()
+    if r < 0.5:
+        return Expr.Not(random_tree(rng, depth + 1))
+    kids = [random_tree(rng, depth + 1) for _ in range(int(rng.integers(2, 4)))]
+    return Expr.And(kids) if r < 0.75 else Expr.Or(kids)
+
+
+@pytest.mark.parametrize("nulls", [False, True], ids=["dense", "nullable"])
+@pytest.mark.parametrize("seed", range(4))
+def test_random_predicate_trees_stay_on_the_lean_kernel(gpu_ctx, seed, nulls):
+    from llkv_b200 import gpu
+    rng = np.random.default_rng(500 + seed)
+    n = int(rng.integers(5000, 30000))
+    t = mixed_table(n, seed=seed + 31, nulls=nulls, long_strings=False)
+    c_by, d_by, snap_all = tpch.mvcc_arrays(n, seed=seed)
+    t.add_mvcc(c_by, d_by)
+    c = ScalarExpr.Column
+    pool = [AggregateSpec("n", AggregateKind.CountStar()), AggregateSpec("c2", AggregateKind.Count(2)), AggregateSpec("s1", AggregateKind.Sum(1, DataType.Int64)),
+            AggregateSpec("a1", AggregateKind.Avg(1, DataType.Int64)), AggregateSpec("mn1", AggregateKind.Min(1, DataType.Int64)),
+            AggregateSpec("s5", AggregateKind.Sum(5, D)), AggregateSpec("a5", AggregateKind.Avg(5, D)), AggregateSpec("mx5", AggregateKind.Max(5, D)),
+            AggregateSpec("sx", AggregateKind.Sum(c(1) * c(2) - 7, DataType.Int64)), AggregateSpec("nn", AggregateKind.CountNulls(5)),
+            AggregateSpec("sdd", AggregateKind.Sum(c(5) * c(5), DataType.Decimal128(38, 4)))]
+    dt = device_table(gpu_ctx, t)
+    try:
+        for trial in range(6):
+            f = random_tree(rng)
+            specs = [pool[i] for i in sorted(rng.choice(len(pool), size=int(rng.integers(1, 6)), replace=False))]
+            snap = [None, snap_all][int(rng.integers(0, 2))]
+            lo = int(rng.integers(0, n // 3)) if rng.random() < 0.5 else 0
+            want = oracle.aggregate(t, f, specs, snap, (), row_begin=lo, row_end=n)
+            w_bits, w_count = oracle.filter_bitmap(t, f, snap, lo, n)
+            for mode in (0, 2):
+                gpu_ctx.set_jit(mode)
+                prog = gpu.Program(gpu_ctx, f)
+                dt.set_snapshot(snap)
+                agg = gpu.Aggregation(dt, specs)
+                try:
+                    agg.run(prog, snap is not None, lo, n)
+                    got = agg.finalize(1)
+                    info = agg.run_info()
+                    util.assert_same_result(got, want, REL)
+                    assert info.used_fast_kernel == 1, f"seed {seed} trial {trial}: the plan left the lean kernel: {f}"
+                finally:
+                    agg.destroy()
+                    prog.destroy()
+            g_bits, g_count = dt.filter_bitmap(f, snap, lo, n)  # (the general interpreter: the same three-valued logic)
+            assert g_count == w_count and np.array_equal(g_bits, w_bits)
+    finally:
+        gpu_ctx.set_jit(1)
+        dt.destroy()
