@@ -44,9 +44,16 @@ def test_q1_lowers_to_the_lean_program_with_narrow_accumulators(lineitem):
     assert "fg=8" in text  # six expected groups -> eight CTA-local slots
 
 
-def test_or_trees_stay_on_the_general_interpreter(lineitem):
+def test_or_and_not_trees_lower_to_the_mask_stack_of_the_lean_kernel(lineitem):
+    """OR / NOT trees run on the lean kernel since round 2: leaves push (rows, not-in-domain) masks, MASK_* combine them."""
     t, _ = lineitem
-    text = gpu.debug_plan(t, Expr.Or([tpch.q1_filter(), tpch.q6_filter()]), tpch.q6_aggregates())
+    text = gpu.debug_plan(t, Expr.Or([tpch.q1_filter(), Expr.Not(tpch.q6_filter())]), tpch.q6_aggregates())
+    assert text.startswith("lean plan")
+    ops = [ln.split()[1] for ln in text.splitlines() if ln.strip()[:1].isdigit()]
+    assert ops.count("LEAF") == 4 and "MASK_AND" in ops and "MASK_OR" in ops and "MASK_NOT" in ops and ops.count("MASK_FILTER") == 1
+    # float leaves and IN lists still take the general interpreter
+    from llkv_b200.expr import Operator, pred
+    text = gpu.debug_plan(t, Expr.Or([tpch.q1_filter(), pred(tpch.L_QUANTITY, Operator.In([100, 200]))]), tpch.q6_aggregates())
     assert text.startswith("general interpreter")
 
 
