@@ -252,6 +252,10 @@ extern "C" {
     /// `ColumnStore::delete_rows`: the rows become gaps of the resident image.
     pub fn llkv_gpu_column_delete_rows(col: *mut llkv_gpu_column, row_ids: *const u64, n: u64) -> i32;
     pub fn llkv_gpu_column_present_rows(col: *mut llkv_gpu_column, out_rows: *mut u64) -> i32;
+    /// `SortIndexOps::stage_build_for_chunk` for every chunk of the resident column, on the device.
+    pub fn llkv_gpu_column_build_sort_index(col: *mut llkv_gpu_column, chunk_rows: u64) -> i32;
+    /// One chunk's permutation as the blob the pager stores under `value_order_perm_pk`.
+    pub fn llkv_gpu_column_sort_index_blob(col: *mut llkv_gpu_column, chunk_index: u64, out_blob: *mut c_void, cap: u64, out_len: *mut u64) -> i32;
     /// `gather_rows` with `GatherNullPolicy::IncludeNulls`: values in request order, `out_valid[i] == 0` for absent rows.
     pub fn llkv_gpu_column_gather(col: *mut llkv_gpu_column, row_ids: *const u64, n: u64, out_values: *mut c_void, out_bytes: u64, out_valid: *mut u8) -> i32;
     pub fn llkv_gpu_column_rows(col: *const llkv_gpu_column, out_rows: *mut u64) -> i32;

@@ -410,6 +410,15 @@ int32_t llkv_gpu_column_delete_rows(llkv_gpu_column* col, const uint64_t* row_id
  * such row (the value is then zero).  For tests and B2-level callers; aggregates never gather.  Not for Utf8. */
 int32_t llkv_gpu_column_gather(llkv_gpu_column* col, const uint64_t* row_ids, uint64_t n, void* out_values, uint64_t out_bytes,
                                uint8_t* out_valid);
+/* Sort index (SortIndexOps::stage_build_for_chunk / stage_update_for_new_chunk,
+ * llkv-column-map/src/store/indexing/sort.rs:126-172): for every chunk of `chunk_rows` rows (0 = the append path's chunk size
+ * for the type) the permutation that lists the chunk's rows in ascending value order — what `lexsort_to_indices` gives the
+ * reference (floats by total order; equal values in row order) — built on the device, one CTA per chunk.
+ * llkv_gpu_column_sort_index_blob serialises one chunk's permutation exactly as the pager stores it under
+ * ChunkMetadata.value_order_perm_pk ("ARR0" header, PrimType UInt32; serialization.rs:41-53): `out_blob` NULL asks for the
+ * length only.  Columns with gaps / NULLs, Utf8 and Decimal128 columns that do not fit i64 have no sort index here. */
+int32_t llkv_gpu_column_build_sort_index(llkv_gpu_column* col, uint64_t chunk_rows);
+int32_t llkv_gpu_column_sort_index_blob(llkv_gpu_column* col, uint64_t chunk_index, void* out_blob, uint64_t cap, uint64_t* out_len);
 /* Rows the column holds (llkv_gpu_column_rows counts positions, gaps included). */
 int32_t llkv_gpu_column_present_rows(llkv_gpu_column* col, uint64_t* out_rows);
 /* Bytes the column's appends have put on the host-to-device link since it was registered (for end-to-end accounting). */

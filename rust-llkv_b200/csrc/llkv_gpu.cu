@@ -285,6 +285,106 @@ __global__ void popcount_bits_kernel(const unsigned int* __restrict__ bits, u64 
   if ((threadIdx.x & 31) == 0 && c) atomicAdd(out, c);
 }
 
+// Sort index (SortIndexOps::stage_build_for_chunk, llkv-column-map/src/store/indexing/sort.rs:150-172): for every chunk the
+// permutation that lists its rows in ascending value order (lexsort_to_indices).  One CTA sorts one chunk: a stable LSD radix
+// sort over 4-bit digits of the order-preserving 64-bit image of the values, (key, index) pairs ping-ponging between two
+// scratch buffers.  Every thread owns a contiguous segment of the chunk, counts its digits, a block-wide scan of the
+// [digit][thread] counters gives each (digit, thread) its first output position, and the thread scatters its segment in
+// order — which is what keeps equal keys in row order.  Index maintenance, not the scan path: a chunk is at most 1 MiB.
+constexpr int kSortThreads = 512;
+template <typename T, int KIND>  // KIND: 0 signed integer, 1 unsigned integer, 2 f32, 3 f64
+__device__ __forceinline__ u64 sort_key_of(T v) {
+  if (KIND == 0) return (u64)(i64)v ^ 0x8000000000000000ull;
+  if (KIND == 1) return (u64)v;
+  u64 b;
+  if (KIND == 2) {
+    const double d = (double)v;  // f32 through f64, as the reference's sortable encoding (codecs.rs:33-65)
+    b = (u64)__double_as_longlong(d);
+  } else {
+    b = (u64)__double_as_longlong((double)v);
+  }
+  return (b >> 63) ? ~b : (b | 0x8000000000000000ull);
+}
+template <typename T, int KIND>
+__global__ void __launch_bounds__(kSortThreads) chunk_sort_kernel(const T* __restrict__ values, u64 n_rows, u64 chunk_rows, int passes, u64* key_a, u64* key_b,
+                                                                  unsigned int* idx_a, unsigned int* idx_b, unsigned int* __restrict__ perm) {
+  __shared__ unsigned int s_cnt[16][kSortThreads];
+  __shared__ unsigned int s_part[kSortThreads];
+  const u64 base = (u64)blockIdx.x * chunk_rows;
+  if (base >= n_rows) return;
+  const unsigned int m = (unsigned int)(n_rows - base < chunk_rows ? n_rows - base : chunk_rows);
+  const unsigned int t = threadIdx.x;
+  const unsigned int per = (m + kSortThreads - 1) / kSortThreads;
+  const unsigned int lo = t * per < m ? t * per : m, hi = lo + per < m ? lo + per : m;
+  u64* ka = key_a + base;
+  u64* kb = key_b + base;
+  unsigned int* ia = idx_a + base;
+  unsigned int* ib = idx_b + base;
+  for (unsigned int i = t; i < m; i += kSortThreads) {
+    ka[i] = sort_key_of<T, KIND>(values[base + i]);
+    ia[i] = i;
+  }
+  __syncthreads();
+  for (int p = 0; p < passes; ++p) {
+    const int shift = 4 * p;
+    unsigned int c[16];
+#pragma unroll
+    for (int d = 0; d < 16; ++d) c[d] = 0;
+    for (unsigned int i = lo; i < hi; ++i) {
+      const unsigned int d = (unsigned int)(ka[i] >> shift) & 15u;
+#pragma unroll
+      for (int q = 0; q < 16; ++q) c[q] += (d == (unsigned)q);
+    }
+#pragma unroll
+    for (int d = 0; d < 16; ++d) s_cnt[d][t] = c[d];
+    __syncthreads();
+    // exclusive scan of the 16 x kSortThreads counters in digit-major order: thread t owns counters [16 t, 16 t + 16)
+    unsigned int* flat = &s_cnt[0][0];
+    unsigned int sum = 0;
+#pragma unroll
+    for (int q = 0; q < 16; ++q) sum += flat[16 * t + q];
+    unsigned int inc = sum;
+    const unsigned int lane = t & 31, wid = t >> 5;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const unsigned int y = __shfl_up_sync(0xffffffffu, inc, o);
+      if (lane >= (unsigned)o) inc += y;
+    }
+    if (lane == 31) s_part[wid] = inc;
+    __syncthreads();
+    unsigned int wbase = 0;
+    for (unsigned int w = 0; w < wid; ++w) wbase += s_part[w];
+    unsigned int run = wbase + inc - sum;
+#pragma unroll
+    for (int q = 0; q < 16; ++q) {
+      const unsigned int v = flat[16 * t + q];
+      flat[16 * t + q] = run;
+      run += v;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int d = 0; d < 16; ++d) c[d] = s_cnt[d][t];
+    for (unsigned int i = lo; i < hi; ++i) {
+      const u64 k = ka[i];
+      const unsigned int d = (unsigned int)(k >> shift) & 15u;
+      unsigned int dst = 0;
+#pragma unroll
+      for (int q = 0; q < 16; ++q)
+        if (d == (unsigned)q) dst = c[q]++;
+      kb[dst] = k;
+      ib[dst] = ia[i];
+    }
+    __syncthreads();
+    u64* tk = ka;
+    ka = kb;
+    kb = tk;
+    unsigned int* ti = ia;
+    ia = ib;
+    ib = ti;
+  }
+  for (unsigned int i = t; i < m; i += kSortThreads) perm[base + i] = ia[i];
+}
+
 // ------------------------------------------------------------------------------------------------ handles
 struct MvccState {
   llkv_gpu_column* created_by = nullptr;
@@ -429,6 +529,8 @@ struct llkv_gpu_column {
   UploadTicket ticket;
   std::vector<NarrowChunk> narrow_chunks;
   uint64_t h2d_bytes = 0;      // bytes this column's appends put on the link since it was registered
+  unsigned int* d_perm = nullptr;  // sort index: per chunk of perm_chunk_rows rows, the rows in ascending value order
+  uint64_t perm_chunk_rows = 0, perm_version = 0;
   bool sparse = false;         // some chunk arrived with row ids that do not continue the column: positions = row id - origin,
                                // absent rows are invalid bits, statistics are recomputed over the whole column at seal
   // pending coalesced upload from page-locked host memory (upload() / flush_upload())
@@ -1620,6 +1722,90 @@ extern "C" int32_t llkv_gpu_column_visit(llkv_gpu_column* col, uint64_t chunk_ro
   return LLKV_OK;
 }
 
+extern "C" int32_t llkv_gpu_column_build_sort_index(llkv_gpu_column* col, uint64_t chunk_rows) {
+  if (!col) return set_error(LLKV_ERR_INVALID_ARGUMENT, "column is NULL");
+  llkv_gpu_ctx* c = col->ctx;
+  CTX_LOCK(c);
+  CUDA_TRY(cudaSetDevice(c->device));
+  if (!col->sealed) {
+    int32_t rc = llkv_gpu_column_seal(col);
+    if (rc) return rc;
+  }
+  if (col->validity) return set_error(LLKV_ERR_INVALID_ARGUMENT, "the sort index covers columns without gaps or NULLs");
+  if (col->type == LLKV_PT_UTF8 || col->load_kind == LK_D128) return set_error(LLKV_ERR_INVALID_ARGUMENT, "no sort index for this column type");
+  const uint64_t width = (uint64_t)prim_type_width(col->type);
+  if (chunk_rows == 0) chunk_rows = width <= 8 ? (1ull << 20) / width : 4096;  // the append path's chunking (store/slicing.rs:33-43,155-166)
+  if (chunk_rows > (1ull << 20)) return set_error(LLKV_ERR_INVALID_ARGUMENT, "sort-index chunks hold at most 2^20 rows");
+  const uint64_t n = col->n_rows;
+  if (n == 0) return LLKV_OK;
+  if (col->d_perm) CUDA_TRY(cudaFree(col->d_perm));
+  col->d_perm = nullptr;
+  CUDA_TRY(cudaMalloc((void**)&col->d_perm, n * 4));
+  u64 *ka = nullptr, *kb = nullptr;
+  unsigned int *ia = nullptr, *ib = nullptr;
+  cudaError_t e = cudaMalloc((void**)&ka, n * 8);
+  if (e == cudaSuccess) e = cudaMalloc((void**)&kb, n * 8);
+  if (e == cudaSuccess) e = cudaMalloc((void**)&ia, n * 4);
+  if (e == cudaSuccess) e = cudaMalloc((void**)&ib, n * 4);
+  const unsigned grid = (unsigned)((n + chunk_rows - 1) / chunk_rows);
+  cudaStream_t s = c->stream;
+  if (e == cudaSuccess) {
+    const void* v = col->values;
+#define LLKV_SORT(T, KIND, BYTES) chunk_sort_kernel<T, KIND><<<grid, kSortThreads, 0, s>>>((const T*)v, n, chunk_rows, 2 * (BYTES), ka, kb, ia, ib, col->d_perm)
+    switch (col->load_kind) {
+      case LK_I8: LLKV_SORT(signed char, 0, 8); break;  // (the sign-extended image: all 64 bits take part)
+      case LK_I16: LLKV_SORT(short, 0, 8); break;
+      case LK_I32: case LK_D32: LLKV_SORT(int, 0, 8); break;
+      case LK_I64: case LK_D64: LLKV_SORT(i64, 0, 8); break;
+      case LK_U8: LLKV_SORT(unsigned char, 1, 1); break;
+      case LK_U16: LLKV_SORT(unsigned short, 1, 2); break;
+      case LK_U32: LLKV_SORT(unsigned int, 1, 4); break;
+      case LK_U64: LLKV_SORT(u64, 1, 8); break;
+      case LK_F32: LLKV_SORT(float, 2, 8); break;
+      case LK_F64: LLKV_SORT(double, 3, 8); break;
+      default: e = cudaErrorInvalidValue; break;
+    }
+#undef LLKV_SORT
+    if (e == cudaSuccess) e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+  }
+  cudaFree(ka);
+  cudaFree(kb);
+  cudaFree(ia);
+  cudaFree(ib);
+  if (e != cudaSuccess) return set_error(LLKV_ERR_IO, "CUDA error %s building the sort index", cudaGetErrorString(e));
+  col->perm_chunk_rows = chunk_rows;
+  col->perm_version = col->version;
+  return LLKV_OK;
+}
+
+extern "C" int32_t llkv_gpu_column_sort_index_blob(llkv_gpu_column* col, uint64_t chunk_index, void* out_blob, uint64_t cap, uint64_t* out_len) {
+  if (!col || !out_len) return set_error(LLKV_ERR_INVALID_ARGUMENT, "NULL argument");
+  llkv_gpu_ctx* c = col->ctx;
+  CTX_LOCK(c);
+  CUDA_TRY(cudaSetDevice(c->device));
+  if (!col->d_perm || col->perm_version != col->version) return set_error(LLKV_ERR_NOT_FOUND, "the column has no current sort index (llkv_gpu_column_build_sort_index)");
+  const uint64_t base = chunk_index * col->perm_chunk_rows;
+  if (base >= col->n_rows) return set_error(LLKV_ERR_NOT_FOUND, "chunk %llu is past the column's end", (unsigned long long)chunk_index);
+  const uint64_t m = std::min<uint64_t>(col->perm_chunk_rows, col->n_rows - base);
+  *out_len = 24 + 4 * m;
+  if (!out_blob) return LLKV_OK;  // (size query)
+  if (cap < *out_len) return set_error(LLKV_ERR_INVALID_ARGUMENT, "blob buffer too small (%llu bytes needed)", (unsigned long long)*out_len);
+  // "ARR0" | layout 0 (Primitive) | PrimType UInt32 | 0 | 0 | len u64 | values bytes u32 | 0  (serialization.rs:41-53,264-307)
+  unsigned char* b = (unsigned char*)out_blob;
+  memcpy(b, "ARR0", 4);
+  b[4] = 0;
+  b[5] = (unsigned char)LLKV_PT_UINT32;
+  b[6] = b[7] = 0;
+  const uint64_t len = m;
+  const uint32_t bytes = (uint32_t)(4 * m), zero = 0;
+  memcpy(b + 8, &len, 8);
+  memcpy(b + 16, &bytes, 4);
+  memcpy(b + 20, &zero, 4);
+  CUDA_TRY(cudaMemcpy(b + 24, col->d_perm + base, 4 * m, cudaMemcpyDeviceToHost));
+  return LLKV_OK;
+}
+
 extern "C" int32_t llkv_gpu_column_present_rows(llkv_gpu_column* col, uint64_t* out_rows) {
   if (!col || !out_rows) return set_error(LLKV_ERR_INVALID_ARGUMENT, "NULL argument");
   llkv_gpu_ctx* c = col->ctx;
@@ -1762,6 +1948,7 @@ extern "C" int32_t llkv_gpu_column_destroy(llkv_gpu_column* col) {
   if (col->validity) cudaFree(col->validity);
   if (col->dstats) cudaFree(col->dstats);
   if (col->d_zones) cudaFree(col->d_zones);
+  if (col->d_perm) cudaFree(col->d_perm);
   delete col;
   return LLKV_OK;
 }

@@ -75,6 +75,8 @@ def load():
         "llkv_gpu_column_flush": (i32, [vp]),
         "llkv_gpu_column_delete_rows": (i32, [vp, vp, u64]),
         "llkv_gpu_column_present_rows": (i32, [vp, P(u64)]),
+        "llkv_gpu_column_build_sort_index": (i32, [vp, u64]),
+        "llkv_gpu_column_sort_index_blob": (i32, [vp, u64, vp, u64, P(u64)]),
         "llkv_gpu_column_gather": (i32, [vp, vp, u64, vp, u64, vp]),
         "llkv_gpu_column_visit": (i32, [vp, u64, i32, CHUNK_VISITOR, vp]),
         "llkv_gpu_column_h2d_bytes": (i32, [vp, P(u64)]),
@@ -337,6 +339,17 @@ class DeviceColumn:
 
         cb = CHUNK_VISITOR(trampoline)
         _check(self.lib.llkv_gpu_column_visit(self.handle, chunk_rows, int(with_row_ids), cb, None))
+
+    def build_sort_index(self, chunk_rows: int = 0):
+        _check(self.lib.llkv_gpu_column_build_sort_index(self.handle, chunk_rows))
+
+    def sort_index_blob(self, chunk_index: int) -> bytes:
+        """The chunk's value_order_perm blob ("ARR0", UInt32 indices) as the pager would store it."""
+        n = C.c_uint64()
+        _check(self.lib.llkv_gpu_column_sort_index_blob(self.handle, chunk_index, None, 0, C.byref(n)))
+        buf = (C.c_uint8 * n.value)()
+        _check(self.lib.llkv_gpu_column_sort_index_blob(self.handle, chunk_index, buf, n.value, C.byref(n)))
+        return bytes(buf)
 
     def present_rows(self) -> int:
         n = C.c_uint64()
