@@ -317,8 +317,18 @@ fn push_operator(out: &mut FlatProgram, op: &Operator<'_>, item: &mut sys::llkv_
         }
         Operator::IsNull => item.operator_tag = OP_IS_NULL,
         Operator::IsNotNull => item.operator_tag = OP_IS_NOT_NULL,
-        Operator::StartsWith { .. } | Operator::EndsWith { .. } | Operator::Contains { .. } => {
-            return Err(Error::PredicateBuild("string pattern operators are not supported on the GPU path".into()));
+        // the pattern travels as a string literal (16 inline bytes: longer ones stay on the reference's path through the
+        // error `literal_to_c` returns); llkv_eval_op.literal_bool = 1 asks for the case-insensitive form
+        Operator::StartsWith { pattern, case_sensitive }
+        | Operator::EndsWith { pattern, case_sensitive }
+        | Operator::Contains { pattern, case_sensitive } => {
+            item.operator_tag = match op {
+                Operator::StartsWith { .. } => OP_STARTS_WITH,
+                Operator::EndsWith { .. } => OP_ENDS_WITH,
+                _ => OP_CONTAINS,
+            };
+            item.literal_bool = i32::from(!*case_sensitive);
+            out.literals.push(literal_to_c(&Literal::String(pattern.clone()))?);
         }
     }
     item.lit_count = out.literals.len() as i32 - item.lit_begin;

@@ -145,9 +145,9 @@ enum {
   LLKV_OP_LT = 4,
   LLKV_OP_LTE = 5,
   LLKV_OP_IN = 6,
-  LLKV_OP_STARTS_WITH = 7, /* not supported on this path: LLKV_ERR_PREDICATE_BUILD */
-  LLKV_OP_ENDS_WITH = 8,
-  LLKV_OP_CONTAINS = 9,
+  LLKV_OP_STARTS_WITH = 7, /* Utf8 columns; one string literal (the pattern); llkv_eval_op.literal_bool = 1 asks for the */
+  LLKV_OP_ENDS_WITH = 8,   /* case-insensitive form (typed_predicate.rs:187-209: both sides through to_lowercase()), which this  */
+  LLKV_OP_CONTAINS = 9,    /* path serves for ASCII patterns over columns without non-ASCII bytes, else LLKV_ERR_PREDICATE_BUILD */
   LLKV_OP_IS_NULL = 10,
   LLKV_OP_IS_NOT_NULL = 11
 };
@@ -167,7 +167,7 @@ typedef struct llkv_eval_op {
   int32_t cmp_op;       /* PUSH_COMPARE: LLKV_CMP_* */
   int32_t negated;      /* PUSH_IN_LIST / PUSH_IS_NULL */
   int32_t child_count;  /* AND / OR / FUSED_AND; PUSH_IN_LIST: list length */
-  int32_t literal_bool; /* PUSH_LITERAL */
+  int32_t literal_bool; /* PUSH_LITERAL; STARTS_WITH / ENDS_WITH / CONTAINS leaves: 1 = case-insensitive */
 } llkv_eval_op;
 
 /* ---- llkv_aggregate::AggregateKind (llkv-aggregate/src/lib.rs:32-69) ---- */

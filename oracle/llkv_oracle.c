@@ -201,6 +201,8 @@ typedef struct {
   int n_in;
   int dec_scale_col;  /* DOM_DEC: scale of the column */
   int dec_scale_lit;  /* DOM_DEC: scale the literals were aligned to (>= col scale) */
+  uint8_t pat[16];    /* STARTS_WITH / ENDS_WITH / CONTAINS: the pattern's bytes (lower-cased when ci) */
+  int pat_len, ci;
 } TPred;
 
 static int col_domain(const oracle_column* c) {
@@ -335,6 +337,29 @@ static int32_t build_pred(const oracle_column* c, const llkv_eval_op* op, const 
       for (int i = 0; i < op->lit_count; ++i)
         if ((rc = lit_to_native(c, l + i, &p->in[i], &ds, e))) { free(p->in); p->in = NULL; return rc; }
       break;
+    case LLKV_OP_STARTS_WITH: case LLKV_OP_ENDS_WITH: case LLKV_OP_CONTAINS:
+      /* typed_predicate.rs:25-36: every native type but String answers false; :187-209: str::starts_with / ends_with /
+       * contains, through to_lowercase() on both sides when !case_sensitive (exact here for ASCII-only data) */
+      if (op->lit_count != 1) return fail(e, LLKV_ERR_INTERNAL, "operator needs one literal");
+      if (p->dom != DOM_STR) { p->op = LLKV_OP_IN; p->n_in = 0; break; }
+      if (l->kind != LLKV_LIT_STRING) return fail(e, LLKV_ERR_PREDICATE_BUILD, "literal type mismatch: expected string");
+      if (l->precision > 16) return fail(e, LLKV_ERR_PREDICATE_BUILD, "string literal longer than the 16 inline bytes of llkv_literal");
+      memcpy(p->pat, &l->lo, 8);
+      memcpy(p->pat + 8, &l->hi, 8);
+      p->pat_len = (int)l->precision;
+      p->ci = op->literal_bool != 0;
+      if (p->ci) {
+        for (int i = 0; i < p->pat_len; ++i) {
+          if (p->pat[i] >= 0x80) return fail(e, LLKV_ERR_PREDICATE_BUILD, "case-insensitive patterns are ASCII-only on this path");
+          if (p->pat[i] >= 'A' && p->pat[i] <= 'Z') p->pat[i] = (uint8_t)(p->pat[i] + 32);
+        }
+        const int32_t* off = (const int32_t*)c->values;
+        const uint8_t* data = (const uint8_t*)c->aux;
+        for (int64_t i = off[0]; i < off[c->n_rows]; ++i)
+          if (data[i] >= 0x80)
+            return fail(e, LLKV_ERR_PREDICATE_BUILD, "case-insensitive match over a column with non-ASCII strings is not on this path");
+      }
+      break;
     default:
       return fail(e, LLKV_ERR_PREDICATE_BUILD, "operator lacks typed literal support");
   }
@@ -381,6 +406,20 @@ static inline int pred_matches(const TPred* p, PVal v) {
       for (int i = 0; i < p->n_in; ++i)
         if (pv_eq(p->dom, v, p->in[i])) return 1;
       return 0;
+    case LLKV_OP_STARTS_WITH: case LLKV_OP_ENDS_WITH: case LLKV_OP_CONTAINS: {
+      uint8_t s[8];
+      const int len = (int)(v.u & 0xff), L = p->pat_len;
+      for (int i = 0; i < len; ++i) {
+        s[i] = (uint8_t)(v.u >> (56 - 8 * i));
+        if (p->ci && s[i] >= 'A' && s[i] <= 'Z') s[i] = (uint8_t)(s[i] + 32);
+      }
+      if (L > len) return 0;
+      if (p->op == LLKV_OP_STARTS_WITH) return memcmp(s, p->pat, (size_t)L) == 0;
+      if (p->op == LLKV_OP_ENDS_WITH) return memcmp(s + len - L, p->pat, (size_t)L) == 0;
+      for (int at = 0; at + L <= len; ++at)
+        if (memcmp(s + at, p->pat, (size_t)L) == 0) return 1;
+      return 0;
+    }
   }
   return 0;
 }

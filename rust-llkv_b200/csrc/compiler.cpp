@@ -507,6 +507,10 @@ class Emitter {
         break;
       }
       case LLKV_OP_IN: emit_in_leaf(c, l, op.lit_count); return;
+      case LLKV_OP_STARTS_WITH: case LLKV_OP_ENDS_WITH: case LLKV_OP_CONTAINS:
+        if (op.lit_count != 1) fail(LLKV_ERR_INTERNAL, "operator needs one literal");
+        emit_pattern_leaf(c, op.operator_tag, *l, op.literal_bool != 0);
+        return;
       default: fail(LLKV_ERR_PREDICATE_BUILD, "operator lacks typed literal support");
     }
     // convert the bound literals to the column's native domain
@@ -633,6 +637,47 @@ class Emitter {
       }
     }
     fail(LLKV_ERR_INTERNAL, "bad domain");
+  }
+
+  // StartsWith / EndsWith / Contains (typed_predicate.rs:187-209; only String implements them: :25-36 is `false` for every
+  // other native type) over the packed short strings of this path.
+  void emit_pattern_leaf(const ColumnMeta& c, int tag, const llkv_literal& l, bool ci) {
+    if (col_domain(c) != DOM_STR) {  // the default trait methods: never matches; the domain stays the present rows
+      emit(OP_IN_BITS, 0, 0, 0);
+      return;
+    }
+    if (l.kind != LLKV_LIT_STRING) fail(LLKV_ERR_PREDICATE_BUILD, "literal type mismatch: expected string");
+    uint8_t bytes[16];
+    memcpy(bytes, &l.lo, 8);
+    memcpy(bytes + 8, &l.hi, 8);
+    const uint32_t len = l.precision;
+    if (len > 16) fail(LLKV_ERR_PREDICATE_BUILD, "string literal longer than the 16 inline bytes of llkv_literal");
+    if (ci) {
+      // to_lowercase() is Unicode's: ASCII lowering equals it exactly when neither side holds a non-ASCII character
+      for (uint32_t i = 0; i < len; ++i) {
+        if (bytes[i] >= 0x80) fail(LLKV_ERR_PREDICATE_BUILD, "case-insensitive patterns are ASCII-only on this path");
+        if (bytes[i] >= 'A' && bytes[i] <= 'Z') bytes[i] = (uint8_t)(bytes[i] + 32);
+      }
+      if (c.str_non_ascii) fail(LLKV_ERR_PREDICATE_BUILD, "case-insensitive match over a column with non-ASCII strings is not on this path");
+    }
+    if (len > 7) {  // no string of a short-string column is that long
+      emit(OP_IN_BITS, 0, 0, 0);
+      return;
+    }
+    uint64_t packed = 0;
+    pack_short_string(bytes, len, &packed);
+    if (tag == LLKV_OP_STARTS_WITH && !ci) {
+      // as a range of packed keys: the pattern's bytes on top, then anything — a key below `lo` with the same top bytes would
+      // be a shorter string, one above `hi` differs in the top bytes
+      const uint64_t rest = len == 0 ? ~0ull : ((1ull << (64 - 8 * len)) - 1);
+      std::vector<Lit> run(2);
+      run[0].lo = packed; run[0].hi = 0;
+      run[1].lo = (packed & ~rest) | rest; run[1].hi = 0;
+      emit(OP_PRED_U, (uint8_t)(LLKV_BOUND_INCLUDED | (LLKV_BOUND_INCLUDED << 2)), 0, add_lit_run(run));
+      return;
+    }
+    const uint8_t mode = tag == LLKV_OP_ENDS_WITH ? 0 : tag == LLKV_OP_CONTAINS ? 1 : 2;
+    emit(OP_PRED_STR, (uint8_t)(mode | (ci ? 4 : 0)), (uint8_t)len, add_lit(packed, 0));
   }
 
   void emit_in_leaf(const ColumnMeta& c, const llkv_literal* l, int n) {

@@ -37,6 +37,7 @@ struct ColumnMeta {
   uint64_t min_bits = 0, max_bits = 0;  // integers/dates/bool: order by the column's signedness
   bool has_minmax = false;
   uint8_t max_strlen = 0;  // Utf8
+  bool str_non_ascii = false;  // Utf8: some string holds a byte >= 0x80
 };
 
 struct ProgramView {

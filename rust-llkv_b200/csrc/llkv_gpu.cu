@@ -166,12 +166,13 @@ __global__ void pack_utf8_kernel(const int* __restrict__ off, const unsigned cha
     const int b = off[i] - first, e = off[i + 1] - first;
     const unsigned int len = (unsigned int)(e - b);
     u64 k = 0;
-    if (len > 7) bad = 1;
+    if (len > 7) bad |= 1;
     else {
       for (unsigned int j = 0; j < len; ++j) k |= (u64)data[b + j] << (56 - 8 * j);
       k |= len;
     }
     out[i] = k;
+    if (k & 0x8080808080808000ull) bad |= 2;  // (a byte >= 0x80: case-insensitive patterns need to know)
     mx = len > mx ? len : mx;
     mn = len < mn ? len : mn;
   }
@@ -179,7 +180,7 @@ __global__ void pack_utf8_kernel(const int* __restrict__ off, const unsigned cha
     atomicMax(&st->max_strlen, mx);
     atomicMin(&st->min_strlen, mn);
   }
-  if (bad) atomicOr(&st->bad_string, 1u);
+  if (bad) atomicOr(&st->bad_string, bad);
 }
 __global__ void narrow_str_kernel(const u64* __restrict__ in, unsigned char* __restrict__ out, u64 n) {
   for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (u64)gridDim.x * blockDim.x) out[i] = (unsigned char)(in[i] >> 56);
@@ -1535,7 +1536,7 @@ extern "C" int32_t llkv_gpu_column_seal(llkv_gpu_column* col) {
   CUDA_TRY(cudaMemcpy(&col->hstats, col->dstats, sizeof(DevStats), cudaMemcpyDeviceToHost));
   col->hstats.data_bytes = data_bytes;
   if (col->type == LLKV_PT_UTF8) {
-    if (col->hstats.bad_string) return set_error(LLKV_ERR_INVALID_ARGUMENT, "string longer than 7 bytes in short-string column");
+    if (col->hstats.bad_string & 1u) return set_error(LLKV_ERR_INVALID_ARGUMENT, "string longer than 7 bytes in short-string column");
     // every string exactly one byte long: keep one byte per row
     if (col->load_kind == LK_U64 && col->n_rows && col->hstats.max_strlen == 1 && col->hstats.min_strlen == 1) {
       unsigned char* nv = nullptr;
@@ -1967,9 +1968,6 @@ extern "C" int32_t llkv_gpu_program_compile(llkv_gpu_ctx* ctx, const llkv_eval_o
     const int t = ops[i].tag;
     if (!((t >= LLKV_EV_PUSH_PREDICATE && t <= LLKV_EV_NOT) || t == LLKV_EV_FILTER_ITEM))
       return set_error(LLKV_ERR_INTERNAL, "unknown eval op tag %d", t);
-    if ((t == LLKV_EV_PUSH_PREDICATE || t == LLKV_EV_FILTER_ITEM) &&
-        (ops[i].operator_tag == LLKV_OP_STARTS_WITH || ops[i].operator_tag == LLKV_OP_ENDS_WITH || ops[i].operator_tag == LLKV_OP_CONTAINS))
-      return set_error(LLKV_ERR_PREDICATE_BUILD, "string pattern operators are not supported on this path");
   }
   llkv_gpu_program* p = new llkv_gpu_program();
   static std::atomic<uint64_t> next_serial{1};
@@ -2143,6 +2141,7 @@ static int32_t collect_columns(llkv_gpu_ctx* ctx, uint64_t table_id, std::vector
       m.max_bits = (is_signed || dec_narrow) ? (col->hstats.max_enc ^ 0x8000000000000000ull) : col->hstats.max_enc;
     }
     m.max_strlen = (uint8_t)col->hstats.max_strlen;
+    m.str_non_ascii = (col->hstats.bad_string & 2u) != 0;
     cols.push_back(m);
     handles.push_back(col);
     if (!have) {
@@ -3053,6 +3052,7 @@ static uint64_t request_signature(const llkv_gpu_ctx* ctx, const CompileRequest&
     h = fnv_pod(h, c.min_bits);
     h = fnv_pod(h, c.max_bits);
     h = fnv_pod(h, c.max_strlen);
+    h = fnv_pod(h, c.str_non_ascii);
   }
   if (prog) {
     h = fnv1a(h, prog->ops.data(), prog->ops.size() * sizeof(llkv_eval_op));

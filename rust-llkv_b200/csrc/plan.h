@@ -59,6 +59,8 @@ enum Op : uint16_t {
   OP_PRED_I, OP_PRED_U, OP_PRED_F, OP_PRED_D,
   OP_IN_BITS,    // b = count, c = first literal (I/U/short-string/bool: bit equality)
   OP_IN_F, OP_IN_D,
+  OP_PRED_STR,   // packed short string against a pattern: a = 0 ends-with / 1 contains / 2 starts-with, | 4 = ASCII case-insensitive;
+                 // b = pattern length (<= 7), c = literal (the packed pattern, lower-cased already when case-insensitive)
   OP_PRED_ISNULL, OP_PRED_NOTNULL, OP_PRED_ALL,  // leaf IsNull / IsNotNull / Range(Unbounded,Unbounded): domain = field present
   OP_ISNULL,     // Expr::IsNull{expr,negated}: a = negated; domain = all rows
   OP_INLIST_FOLD, // pops item-compare result into the (matched, saw_null) accumulator below it: internal to PushInList

@@ -513,6 +513,31 @@ __global__ void __launch_bounds__(512) scan_kernel(const Plan* __restrict__ gpla
           }
           break;
         }
+        case OP_PRED_STR: {
+          const u64 pat = p.lits[in.c].lo;
+          const unsigned L = in.b, mode = in.a & 3u;
+          const u64 top = L ? (pat >> (64 - 8 * L)) : 0;
+#pragma unroll
+          for (int r = 0; r < R; ++r) {
+            const bool n = is_null(r, sp - 1);
+            u64 k = (u64)(i64)t0[r];
+            const unsigned len = (unsigned)(k & 0xffu);
+            if (in.a & 4u) {  // ASCII lower case of the seven string bytes (the plan proved there is no byte >= 0x80)
+              const u64 b = k & ~0xffull;
+              k |= (((b + 0x3f3f3f3f3f3f3f00ull) & ~(b + 0x2525252525252500ull)) & 0x8080808080808000ull) >> 2;
+            }
+            bool m = false;
+            if (len >= L) {
+              if (L == 0) m = true;
+              else if (mode == 2) m = (k >> (64 - 8 * L)) == top;
+              else if (mode == 0) m = ((k << (8 * (len - L))) >> (64 - 8 * L)) == top;
+              else
+                for (unsigned s0 = 0; s0 + L <= len; ++s0) m = m || (((k << (8 * s0)) >> (64 - 8 * L)) == top);
+            }
+            t0[r] = (V)(m && !n);
+          }
+          break;
+        }
         case OP_PRED_ISNULL:
 #pragma unroll
           for (int r = 0; r < R; ++r) {

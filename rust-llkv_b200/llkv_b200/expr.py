@@ -120,6 +120,7 @@ class Operator:
     literals: Tuple[Literal, ...] = ()
     lower: Bound = Bound.Unbounded
     upper: Bound = Bound.Unbounded
+    case_sensitive: bool = True  # StartsWith / EndsWith / Contains
 
     @staticmethod
     def Equals(v) -> "Operator":
@@ -152,11 +153,15 @@ class Operator:
 
     @staticmethod
     def StartsWith(pattern: str, case_sensitive: bool = True) -> "Operator":
-        return Operator(ffi.OP_STARTS_WITH, (lit(pattern),))
+        return Operator(ffi.OP_STARTS_WITH, (lit(pattern),), case_sensitive=case_sensitive)
+
+    @staticmethod
+    def EndsWith(pattern: str, case_sensitive: bool = True) -> "Operator":
+        return Operator(ffi.OP_ENDS_WITH, (lit(pattern),), case_sensitive=case_sensitive)
 
     @staticmethod
     def Contains(pattern: str, case_sensitive: bool = True) -> "Operator":
-        return Operator(ffi.OP_CONTAINS, (lit(pattern),))
+        return Operator(ffi.OP_CONTAINS, (lit(pattern),), case_sensitive=case_sensitive)
 
 
 Operator.IsNull = Operator(ffi.OP_IS_NULL)
@@ -396,6 +401,7 @@ class ProgramCompiler:
         op.upper_kind = f.op.upper.kind
         op.lit_begin = len(prog.literals)
         op.lit_count = len(f.op.literals)
+        op.literal_bool = 0 if f.op.case_sensitive else 1
         prog.literals.extend(l.to_c() for l in f.op.literals)
         return op
 
