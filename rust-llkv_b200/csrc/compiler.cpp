@@ -1846,19 +1846,99 @@ class Emitter {
           // inside an OR / NOT tree (pushed onto the predicate-mask stack)
           const bool is_leaf = i + 1 < select_end_ && (code_[i + 1].op == OP_PRED_I || code_[i + 1].op == OP_PRED_U || code_[i + 1].op == OP_PRED_D ||
                                                        code_[i + 1].op == OP_PRED_F || code_[i + 1].op == OP_PRED_ISNULL ||
-                                                       code_[i + 1].op == OP_PRED_NOTNULL || code_[i + 1].op == OP_PRED_ALL);
+                                                       code_[i + 1].op == OP_PRED_NOTNULL || code_[i + 1].op == OP_PRED_ALL ||
+                                                       code_[i + 1].op == OP_IN_BITS || code_[i + 1].op == OP_IN_D);
           if (is_leaf) {
             const bool conjunct = i + 2 < n && code_[i + 2].op == OP_FILTER && mask_depth == 0;
             const Instr& pr = code_[i + 1];
-            if (pr.op == OP_PRED_F) return false;  // float leaves stay on the general interpreter
+            if (pr.op == OP_PRED_F && c.load_kind != LK_F64 && c.load_kind != LK_F32) return false;
             if (!conjunct) {
               if (mask_depth >= 8) return false;
               ++mask_depth;
             }
             const uint32_t push = conjunct ? 0u : 1u;
             // NULL never satisfies a typed predicate: a nullable column's leaf starts from its valid rows
-            if (conjunct && c.nullable && (pr.op == OP_PRED_NOTNULL || pr.op == OP_PRED_I || pr.op == OP_PRED_U || pr.op == OP_PRED_D))
+            if (conjunct && c.nullable && (pr.op == OP_PRED_NOTNULL || pr.op == OP_PRED_I || pr.op == OP_PRED_U || pr.op == OP_PRED_D ||
+                                           pr.op == OP_PRED_F || pr.op == OP_IN_BITS || pr.op == OP_IN_D))
               femit(FO_VALID, in.a, 0, 0);
+            if (pr.op == OP_IN_BITS || pr.op == OP_IN_D) {
+              // IN list: equality of the 64-bit images (Decimal128 entries that fit i64; the others can match no narrow value)
+              std::vector<Lit> run;
+              for (uint32_t k = 0; k < pr.b; ++k) {
+                const Lit& L = lits_[pr.c + k];
+                if (pr.op == OP_IN_D) {
+                  const i128 v = (i128)(((u128)L.hi << 64) | (u128)L.lo);
+                  if (!fits_i64(v)) {
+                    if (c.load_kind == LK_D128) return false;
+                    continue;
+                  }
+                }
+                run.push_back(mk_lit_i((i128)(int64_t)L.lo));
+              }
+              if (c.load_kind == LK_D128 && !c.dec_fits_i64) return false;
+              if (lits_.size() + run.size() + 1 > (size_t)kMaxLits) return false;  // (+1: the kernel reads a (lo, hi) pair before it looks at g)
+              const uint32_t first = run.empty() ? 0u : add_lit_run(run);
+              femit(FO_LEAF, in.a, map_load(in.b), first);
+              f.back().g = 3u;
+              f.back().f = (uint32_t)run.size();
+              f.back().e = push;
+              i += conjunct ? 2 : 1;
+              break;
+            }
+            if (pr.op == OP_PRED_F) {
+              // floats compare by partial_cmp (NaN matches nothing, -0 == +0): as a signed range over the order-preserving
+              // integer image  k(v) = bits ^ ((bits >> sign) & MAX)  of the column's own width
+              const bool f32 = c.load_kind == LK_F32;
+              auto key = [&](double d) -> int64_t {
+                if (f32) {
+                  const float x = (float)d;
+                  int32_t b;
+                  memcpy(&b, &x, 4);
+                  return (int64_t)(b ^ ((b >> 31) & INT32_MAX));
+                }
+                int64_t b;
+                memcpy(&b, &d, 8);
+                return b ^ ((b >> 63) & INT64_MAX);
+              };
+              auto lit_f = [&](uint32_t idx) { double d; const uint64_t b = lits_[idx].lo; memcpy(&d, &b, 8); return d; };
+              const int64_t kninf = key(-INFINITY), kpinf = key(INFINITY);
+              int64_t lo = kninf, hi = kpinf;
+              bool empty = false;
+              const int lk = pr.a & 3, uk = (pr.a >> 2) & 3, eq = (pr.a >> 4) & 1;
+              if (eq) {
+                const double a = lit_f(pr.c);
+                if (a != a) empty = true;
+                else if (a == 0.0) { lo = -1; hi = 0; }
+                else lo = hi = key(a);
+              } else {
+                uint32_t li = pr.c;
+                if (lk != LLKV_BOUND_UNBOUNDED) {
+                  const double a = lit_f(li++);
+                  if (a != a) empty = true;
+                  else if (lk == LLKV_BOUND_INCLUDED) lo = a == 0.0 ? -1 : key(a);
+                  else if (a == INFINITY) empty = true;
+                  else lo = (a == 0.0 ? 0 : key(a)) + 1;
+                }
+                if (uk != LLKV_BOUND_UNBOUNDED) {
+                  const double b = lit_f(li);
+                  if (b != b) empty = true;
+                  else if (uk == LLKV_BOUND_INCLUDED) hi = b == 0.0 ? 0 : key(b);
+                  else if (b == -INFINITY) empty = true;
+                  else hi = (b == 0.0 ? -1 : key(b)) - 1;
+                }
+              }
+              if (lo < kninf) lo = kninf;
+              if (hi > kpinf) hi = kpinf;
+              if (lo > hi) empty = true;
+              std::vector<Lit> run = {mk_lit_i(empty ? 1 : lo), mk_lit_i(empty ? 0 : hi)};
+              if (lits_.size() + 2 > (size_t)kMaxLits) return false;
+              const uint32_t first = add_lit_run(run);
+              femit(FO_LEAF, in.a, f32 ? (uint32_t)LKF_4 : (uint32_t)LKF_8, first);
+              f.back().g = 2u;
+              f.back().e = push;
+              i += conjunct ? 2 : 1;
+              break;
+            }
             if (pr.op == OP_PRED_ALL || pr.op == OP_PRED_NOTNULL || (pr.op == OP_PRED_ISNULL && (c.nullable || push))) {
               // Range(Unbounded, Unbounded) is true on every row, IS NOT NULL on the valid ones, IS NULL on the others
               if (push) femit(FO_VALID, in.a, pr.op == OP_PRED_ALL ? 2 : pr.op == OP_PRED_ISNULL ? 1 : 0, 1);

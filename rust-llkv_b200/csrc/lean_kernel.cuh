@@ -396,8 +396,32 @@ struct LeanTile {
         const i64 lo = p.lits[in.c], hi = p.lits[in.c + 1];
         const unsigned char* base = sb + S.cols[in.a].smem_off;
         unsigned m = 0;
-        if (in.g ? (u64)hi < (u64)lo : hi < lo) {
+        if (in.g == 3) {  // IN list of in.f entries: equality of the 64-bit images
+          i64 v[R];
+          load_col(in.a, in.b, v);
+          for (uint32_t k = 0; k < in.f; ++k) {
+            const i64 L = p.lits[in.c + k];
+#pragma unroll
+            for (int r = 0; r < R; ++r) m |= (unsigned)(v[r] == L) << r;
+          }
+        } else if (in.g == 1 ? (u64)hi < (u64)lo : hi < lo) {
           // empty range: nothing matches
+        } else if (in.g == 2) {  // floats through their order-preserving integer image (NaNs lie outside [k(-inf), k(+inf)])
+          if (in.b == LKF_4) {
+            const uint32_t l = (uint32_t)(int)lo, span = (uint32_t)(int)hi - l;
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+              const int b = reinterpret_cast<const int*>(base)[r * NC + tid];
+              m |= (unsigned)(((uint32_t)(b ^ ((b >> 31) & 0x7fffffff)) - l) <= span) << r;
+            }
+          } else {
+            const u64 span = (u64)hi - (u64)lo;
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+              const i64 b = reinterpret_cast<const i64*>(base)[r * NC + tid];
+              m |= (unsigned)(((u64)(b ^ ((b >> 63) & 0x7fffffffffffffffll)) - (u64)lo) <= span) << r;
+            }
+          }
         } else if (in.b == LKF_4) {
           // lo <= v <= hi as one unsigned compare of (v - lo)
           const uint32_t l = (uint32_t)(int)lo, span = (uint32_t)(int)hi - l;
@@ -406,7 +430,7 @@ struct LeanTile {
             const uint32_t v = reinterpret_cast<const uint32_t*>(base)[r * NC + tid];
             m |= (unsigned)((v - l) <= span) << r;
           }
-        } else if ((in.b == LKF_8 || in.b == LKF_16) && !in.g) {
+        } else if ((in.b == LKF_8 || in.b == LKF_16) && in.g == 0) {
           const u64 span = (u64)hi - (u64)lo;
           const int stride = in.b == LKF_16 ? 2 : 1;
 #pragma unroll

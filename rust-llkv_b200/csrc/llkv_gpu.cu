@@ -2644,7 +2644,9 @@ static std::string lean_listing(const LeanPlan& lp, const Geometry& g, uint32_t 
       o += b;
     }
     if (in.op == FO_LEAF) {
-      snprintf(b, sizeof(b), "  range [%lld, %lld]%s", lp.lits[in.c], lp.lits[in.c + 1], in.g ? " unsigned" : "");
+      if (in.g == 3) snprintf(b, sizeof(b), "  IN list of %u literals%s", in.f, in.e ? " (pushed)" : "");
+      else snprintf(b, sizeof(b), "  range [%lld, %lld]%s%s", lp.lits[in.c], lp.lits[in.c + 1],
+                    in.g == 1 ? " unsigned" : in.g == 2 ? " over the ordered image of the float bits" : "", in.e ? " (pushed)" : "");
       o += b;
     }
     if (in.op == FO_OP_LIT || in.op == FO_LD_LIT) {

@@ -170,7 +170,7 @@ struct Instr {
 struct FInstr {  // lean-kernel instruction, pre-decoded (two 16-byte shared-memory loads, no field unpacking)
   uint32_t op, a, b, c;
   uint32_t d, e, f;  // fused operand pre-load: d = 0 none / 1 acc = literal e / 2 acc = column e of FastLoad f / 3 acc = tmp e
-  uint32_t g;        // FO_LEAF: 1 = unsigned comparison; FO_SUM: operand width in bits when proven in [0, 2^32), else 0
+  uint32_t g;        // FO_LEAF: 1 = unsigned comparison, 2 = floats by their ordered integer image, 3 = IN list of f literals; FO_SUM: operand width in bits when proven in [0, 2^32), else 0
   uint32_t h;        // aggregates: bit c = the operand is NULL where plan column c is NULL (the row is then skipped)
 };
 // physical layouts the lean kernel reads (everything else stays on the general interpreter)

@@ -11,7 +11,7 @@ import pytest
 from llkv_b200 import gpu, tpch
 import numpy as np
 
-from llkv_b200.expr import AggregateKind, AggregateSpec, DataType, Expr
+from llkv_b200.expr import AggregateKind, AggregateSpec, DataType, Expr, Literal, Operator, pred
 from llkv_b200.table import HostColumn, HostTable
 
 
@@ -51,10 +51,10 @@ def test_or_and_not_trees_lower_to_the_mask_stack_of_the_lean_kernel(lineitem):
     assert text.startswith("lean plan")
     ops = [ln.split()[1] for ln in text.splitlines() if ln.strip()[:1].isdigit()]
     assert ops.count("LEAF") == 4 and "MASK_AND" in ops and "MASK_OR" in ops and "MASK_NOT" in ops and ops.count("MASK_FILTER") == 1
-    # float leaves and IN lists still take the general interpreter
+    # IN lists too (decimal entries compare as the 64-bit images the narrowed column holds)
     from llkv_b200.expr import Operator, pred
     text = gpu.debug_plan(t, Expr.Or([tpch.q1_filter(), pred(tpch.L_QUANTITY, Operator.In([100, 200]))]), tpch.q6_aggregates())
-    assert text.startswith("general interpreter")
+    assert text.startswith("lean plan") and "IN list of 2 literals (pushed)" in text
 
 
 def test_geometry_respects_tuning_and_shared_memory(lineitem):
@@ -176,3 +176,23 @@ def test_every_kernel_variant_specialises_without_a_stack_frame(lineitem, tmp_pa
         if os.path.exists(cuobjdump):
             usage = subprocess.run([cuobjdump, "-res-usage", cubin], capture_output=True, text=True, check=True).stdout
             assert int(usage.split("STACK:")[1].split()[0]) == 0, (name, usage)
+
+
+def test_float_in_list_and_prefix_leaves_lower_to_the_lean_kernel():
+    """Float ranges (as integer ranges over the ordered image of the bits), IN lists and string prefixes (a range of packed
+    keys) are lean-kernel leaves, also inside OR / NOT trees over nullable columns; the specialised kernel compiles."""
+    from test_gpu_parity import mixed_table
+    t = mixed_table(1000, 1, nulls=True, long_strings=False)
+    specs = [AggregateSpec("n", AggregateKind.CountStar()), AggregateSpec("s1", AggregateKind.Sum(1, DataType.Int64))]
+    f = Expr.And([pred(3, Operator.GreaterThan(-0.0)), pred(7, Operator.Equals(0.25)), pred(1, Operator.In([1, 2, -3])),
+                  Expr.Or([pred(10, Operator.StartsWith("a")), pred(5, Operator.In([Literal.Decimal128(100, 2), Literal.Int128(7)])),
+                           Expr.Not(pred(3, Operator.LessThan(float("nan"))))])])
+    listing = gpu.debug_plan(t, f, specs, jit=True)
+    assert listing.startswith("lean plan") and "specialised cubin" in listing
+    assert "range [1, 9218868437227405312] over the ordered image of the float bits" in listing  # (0, +inf]: -0 == +0
+    assert "range [1048576000, 1048576000] over the ordered image" in listing                    # f32 0.25
+    assert "IN list of 3 literals" in listing and "IN list of 2 literals (pushed)" in listing
+    assert "range [1, 0] over the ordered image of the float bits (pushed)" in listing           # NaN literal: empty
+    # suffix / substring patterns are interpreter ops
+    g = gpu.debug_plan(t, pred(10, Operator.Contains("a")), specs)
+    assert g.startswith("general interpreter")
