@@ -428,8 +428,8 @@ def test_every_kernel_geometry_agrees(gpu_ctx, tuning):
 
 
 def test_lean_kernel_runs_the_benchmark_plans(gpu_ctx):
-    """Q6, Q1, the filtered SUM and (since round 2) OR / NOT trees lower to the lean kernel; float leaves and IN lists stay on
-    the general interpreter."""
+    """Q6, Q1, the filtered SUM and (since round 2) OR / NOT trees and IN lists lower to the lean kernel; suffix / substring
+    patterns stay on the general interpreter."""
     from llkv_b200 import gpu
     t, snap = tpch.lineitem_table(50_000, seed=3, with_q1=True, with_mvcc=True)
     dt = device_table(gpu_ctx, t)
@@ -439,7 +439,8 @@ def test_lean_kernel_runs_the_benchmark_plans(gpu_ctx):
             (tpch.q6_filter(), tpch.q6_aggregates(), (), False, 1),
             (tpch.q1_filter(), tpch.q1_aggregates(), tpch.Q1_GROUP_BY, True, 1),
             (Expr.Or([tpch.q1_filter(), tpch.q6_filter()]), tpch.q6_aggregates(), (), False, 1),
-            (Expr.Or([tpch.q1_filter(), pred(tpch.L_QUANTITY, Operator.In([100, 200]))]), tpch.q6_aggregates(), (), False, 0),
+            (Expr.Or([tpch.q1_filter(), pred(tpch.L_QUANTITY, Operator.In([100, 200]))]), tpch.q6_aggregates(), (), False, 1),
+                (Expr.And([tpch.q1_filter(), pred(tpch.L_RETURNFLAG, Operator.EndsWith("N"))]), tpch.q6_aggregates(), (), False, 0),
         ]:
             prog = gpu.Program(gpu_ctx, expr)
             agg = gpu.Aggregation(dt, specs, keys, cardinality_hint=6 if keys else 0)
