@@ -102,7 +102,9 @@ pub struct llkv_group_key {
     pub bits: u64,
     pub type_: i32,
     pub valid: u8,
-    pub _pad: [u8; 3],
+    /// 1 = `bits` is a code of the key column's dictionary (`llkv_gpu_column_dict_entry`)
+    pub dict: u8,
+    pub _pad: [u8; 2],
 }
 
 /// One column as `llkv_gpu_debug_plan` sees it: type and statistics, no data.
@@ -252,6 +254,10 @@ extern "C" {
     /// `ColumnStore::delete_rows`: the rows become gaps of the resident image.
     pub fn llkv_gpu_column_delete_rows(col: *mut llkv_gpu_column, row_ids: *const u64, n: u64) -> i32;
     pub fn llkv_gpu_column_present_rows(col: *mut llkv_gpu_column, out_rows: *mut u64) -> i32;
+    /// Entries of the dictionary of a Utf8 column that holds strings longer than 7 bytes (0: packed short strings).
+    pub fn llkv_gpu_column_dict_size(col: *mut llkv_gpu_column, out_entries: *mut u64) -> i32;
+    /// The string behind a `llkv_group_key` whose `dict` is 1.
+    pub fn llkv_gpu_column_dict_entry(col: *mut llkv_gpu_column, code: u64, out_bytes: *mut *const u8, out_len: *mut u64) -> i32;
     /// `SortIndexOps::stage_build_for_chunk` for every chunk of the resident column, on the device.
     pub fn llkv_gpu_column_build_sort_index(col: *mut llkv_gpu_column, chunk_rows: u64) -> i32;
     /// One chunk's permutation as the blob the pager stores under `value_order_perm_pk`.

@@ -139,8 +139,8 @@ fn empty_literal() -> sys::llkv_literal {
     sys::llkv_literal { kind: LIT_NULL, precision: 0, scale: 0, _pad: [0; 2], lo: 0, hi: 0 }
 }
 
-/// `llkv_types::Literal` (`llkv-types/src/literal.rs:26-41`) -> `llkv_literal`.  Strings travel inline (<= 15 bytes: the
-/// path compares short strings only); struct and interval literals have no place on this path.
+/// `llkv_types::Literal` (`llkv-types/src/literal.rs:26-41`) -> `llkv_literal`.  Strings of up to 15 bytes travel inline
+/// (longer ones by reference: `FlatProgram::literal`); struct and interval literals have no place on this path.
 pub fn literal_to_c(lit: &Literal) -> Result<sys::llkv_literal> {
     let mut out = empty_literal();
     match lit {
@@ -194,6 +194,31 @@ pub struct FlatProgram {
     pub literals: Vec<sys::llkv_literal>,
     pub nodes: Vec<sys::llkv_scalar_node>,
     pub list_roots: Vec<i32>,
+    /// Bytes behind string literals passed by reference (`LLKV_LIT_STRING_BY_REF`, strings over 15 bytes).  Boxed, so the
+    /// addresses stored in `literals` survive this vector growing; `llkv_gpu_program_compile` copies them.
+    pub strings: Vec<Box<[u8]>>,
+}
+
+pub const LIT_STRING_BY_REF: u8 = 255;
+
+impl FlatProgram {
+    /// The C form of `lit`: long strings are owned by the program and referenced, everything else travels inline.
+    fn literal(&mut self, lit: &Literal) -> Result<sys::llkv_literal> {
+        match lit {
+            Literal::String(s) if s.len() > 15 => Ok(self.string_by_ref(s.as_bytes())),
+            other => literal_to_c(other),
+        }
+    }
+    fn string_by_ref(&mut self, bytes: &[u8]) -> sys::llkv_literal {
+        self.strings.push(bytes.to_vec().into_boxed_slice());
+        let stored = self.strings.last().unwrap();
+        let mut out = empty_literal();
+        out.kind = LIT_STRING;
+        out.precision = LIT_STRING_BY_REF;
+        out.lo = stored.as_ptr() as u64;
+        out.hi = stored.len() as u64;
+        out
+    }
 }
 
 fn empty_op(tag: i32) -> sys::llkv_eval_op {
@@ -283,7 +308,8 @@ fn push_operator(out: &mut FlatProgram, op: &Operator<'_>, item: &mut sys::llkv_
     item.lit_begin = out.literals.len() as i32;
     let mut one = |out: &mut FlatProgram, tag: i32, lit: &Literal| -> Result<()> {
         item.operator_tag = tag;
-        out.literals.push(literal_to_c(lit)?);
+        let c = out.literal(lit)?;
+        out.literals.push(c);
         Ok(())
     };
     match op {
@@ -299,11 +325,13 @@ fn push_operator(out: &mut FlatProgram, op: &Operator<'_>, item: &mut sys::llkv_
                 match bound {
                     Bound::Included(l) => {
                         *kind = BOUND_INCLUDED;
-                        out.literals.push(literal_to_c(l)?);
+                        let c = out.literal(l)?;
+                        out.literals.push(c);
                     }
                     Bound::Excluded(l) => {
                         *kind = BOUND_EXCLUDED;
-                        out.literals.push(literal_to_c(l)?);
+                        let c = out.literal(l)?;
+                        out.literals.push(c);
                     }
                     Bound::Unbounded => *kind = BOUND_UNBOUNDED,
                 }
@@ -312,13 +340,13 @@ fn push_operator(out: &mut FlatProgram, op: &Operator<'_>, item: &mut sys::llkv_
         Operator::In(list) => {
             item.operator_tag = OP_IN;
             for l in list.iter() {
-                out.literals.push(literal_to_c(l)?);
+                let c = out.literal(l)?;
+                        out.literals.push(c);
             }
         }
         Operator::IsNull => item.operator_tag = OP_IS_NULL,
         Operator::IsNotNull => item.operator_tag = OP_IS_NOT_NULL,
-        // the pattern travels as a string literal (16 inline bytes: longer ones stay on the reference's path through the
-        // error `literal_to_c` returns); llkv_eval_op.literal_bool = 1 asks for the case-insensitive form
+        // the pattern travels as a string literal; llkv_eval_op.literal_bool = 1 asks for the case-insensitive form
         Operator::StartsWith { pattern, case_sensitive }
         | Operator::EndsWith { pattern, case_sensitive }
         | Operator::Contains { pattern, case_sensitive } => {
@@ -328,7 +356,8 @@ fn push_operator(out: &mut FlatProgram, op: &Operator<'_>, item: &mut sys::llkv_
                 _ => OP_CONTAINS,
             };
             item.literal_bool = i32::from(!*case_sensitive);
-            out.literals.push(literal_to_c(&Literal::String(pattern.clone()))?);
+            let c = out.literal(&Literal::String(pattern.clone()))?; // (long patterns are copied into out.strings)
+            out.literals.push(c);
         }
     }
     item.lit_count = out.literals.len() as i32 - item.lit_begin;

@@ -79,11 +79,14 @@ enum {
   LLKV_LIT_INT128 = 1,     /* lo/hi = two's complement i128 */
   LLKV_LIT_FLOAT64 = 2,    /* lo = IEEE-754 bits */
   LLKV_LIT_DECIMAL128 = 3, /* lo/hi = raw i128, scale = DecimalValue::scale */
-  LLKV_LIT_STRING = 4,     /* precision = byte length (<= 15), bytes little-endian in lo/hi */
+  LLKV_LIT_STRING = 4,     /* precision = byte length (<= 15), bytes little-endian in lo/hi; or precision = 255
+                              (LLKV_LIT_STRING_BY_REF): lo = address of the bytes, hi = byte length — the call that
+                              receives the literal copies the bytes before it returns */
   LLKV_LIT_BOOLEAN = 5,    /* lo = 0/1 */
   LLKV_LIT_DATE32 = 6      /* lo = sign-extended days since epoch */
 };
 
+#define LLKV_LIT_STRING_BY_REF 255
 typedef struct llkv_literal {
   int32_t kind;
   uint8_t precision; /* Decimal128: informational; String: length */
@@ -213,10 +216,13 @@ typedef struct llkv_agg_value {
 
 /* One GROUP BY key cell (llkv-executor/src/lib.rs:99-106 GroupKeyValue). */
 typedef struct llkv_group_key {
-  uint64_t bits;  /* Int: i64; Bool: 0/1; String: bytes big-endian from the top byte, length in the low byte */
+  uint64_t bits;  /* Int: i64; Bool: 0/1; String: bytes big-endian from the top byte, length in the low byte — or, when
+                     `dict` = 1, the string's code in the key column's dictionary (llkv_gpu_column_dict_entry) */
   int32_t type;   /* LLKV_PT_* of the key column */
   uint8_t valid;  /* 0 => NULL key (its own group) */
-  uint8_t _pad[3];
+  uint8_t dict;   /* Utf8 keys of a column that holds strings longer than 7 bytes: 1 = `bits` is a dictionary code
+                     (2 is used by the test oracle only: `bits` is the position of a row holding the string) */
+  uint8_t _pad[2];
 } llkv_group_key;
 
 /* Facts about the most recent llkv_gpu_agg_run / llkv_gpu_filter_bitmap on a handle (for bench.py and ncu notes). */
@@ -410,6 +416,18 @@ int32_t llkv_gpu_column_delete_rows(llkv_gpu_column* col, const uint64_t* row_id
  * such row (the value is then zero).  For tests and B2-level callers; aggregates never gather.  Not for Utf8. */
 int32_t llkv_gpu_column_gather(llkv_gpu_column* col, const uint64_t* row_ids, uint64_t n, void* out_values, uint64_t out_bytes,
                                uint8_t* out_valid);
+/* Utf8 columns.  Strings of up to 7 bytes are resident as packed 8-byte keys.  A column that receives a longer string
+ * becomes dictionary-coded: the host side of append_chunk interns every string (the bytes of such a column never cross
+ * PCIe: 8 bytes per row do), `seal` orders the dictionary byte-wise (Rust's str: Ord) and the resident codes become ranks,
+ * so equality, IN, ranges and prefixes are integer leaves on the specialised kernel, suffix / substring / case-insensitive
+ * patterns are evaluated once per dictionary entry at plan time (at most 255 matching entries, else
+ * LLKV_ERR_PREDICATE_BUILD), and GROUP BY keys take ceil(log2(entries)) bits (GroupKeyValue::String,
+ * llkv-executor/src/lib.rs:99-106,9362-9456).  Group keys of such a column come back with llkv_group_key.dict = 1.
+ * Limits: 2^24 distinct strings per column; scalar
+ * expressions over a dictionary-coded column and merging its group keys across GPUs are LLKV_ERR_INVALID_ARGUMENT.
+ * llkv_gpu_column_dict_entry: the bytes stay valid until the next append to / clear of the column. */
+int32_t llkv_gpu_column_dict_size(llkv_gpu_column* col, uint64_t* out_entries);
+int32_t llkv_gpu_column_dict_entry(llkv_gpu_column* col, uint64_t code, const uint8_t** out_bytes, uint64_t* out_len);
 /* Sort index (SortIndexOps::stage_build_for_chunk / stage_update_for_new_chunk,
  * llkv-column-map/src/store/indexing/sort.rs:126-172): for every chunk of `chunk_rows` rows (0 = the append path's chunk size
  * for the type) the permutation that lists the chunk's rows in ascending value order — what `lexsort_to_indices` gives the

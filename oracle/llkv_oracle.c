@@ -191,6 +191,7 @@ typedef union {
   uint64_t u;
   double f;
   i128 d;
+  struct { const uint8_t* p; uint64_t n; } s; /* DOM_STR: the string's bytes (any length) */
 } PVal;
 typedef struct {
   int op; /* LLKV_OP_*; RANGE with both unbounded is Predicate::All */
@@ -201,8 +202,12 @@ typedef struct {
   int n_in;
   int dec_scale_col;  /* DOM_DEC: scale of the column */
   int dec_scale_lit;  /* DOM_DEC: scale the literals were aligned to (>= col scale) */
-  uint8_t pat[16];    /* STARTS_WITH / ENDS_WITH / CONTAINS: the pattern's bytes (lower-cased when ci) */
+  uint8_t pat[16];    /* STARTS_WITH / ENDS_WITH / CONTAINS: the pattern's inline bytes */
+  const uint8_t* pat_long;
+  uint8_t* pat_ptr;   /* the pattern (owned copy; lower-cased when ci) */
   int pat_len, ci;
+  uint8_t* strbuf;    /* DOM_STR: the bytes of the string literals a / b / in[] point into */
+  int n_str;
 } TPred;
 
 static int col_domain(const oracle_column* c) {
@@ -216,7 +221,7 @@ static int col_domain(const oracle_column* c) {
 }
 
 /* FromLiteral for the column's native type. Returns 0 or LLKV_ERR_PREDICATE_BUILD. */
-static int32_t lit_to_native(const oracle_column* c, const llkv_literal* l, PVal* out, int* dec_scale, Err* e) {
+static int32_t lit_to_native(const oracle_column* c, const llkv_literal* l, PVal* out, int* dec_scale, uint8_t* str_store, Err* e) {
   int dom = col_domain(c);
   switch (dom) {
     case DOM_I64:
@@ -282,12 +287,17 @@ static int32_t lit_to_native(const oracle_column* c, const llkv_literal* l, PVal
       return 0;
     }
     case DOM_STR: {
+      /* String::from_literal: the literal's bytes; the column side compares whole strings (str: Ord is byte-wise) */
       if (l->kind != LLKV_LIT_STRING) return fail(e, LLKV_ERR_PREDICATE_BUILD, "literal type mismatch: expected string");
-      uint8_t bytes[16];
-      memcpy(bytes, &l->lo, 8);
-      memcpy(bytes + 8, &l->hi, 8);
-      if (!pack_short_string(bytes, l->precision, &out->u))
-        return fail(e, LLKV_ERR_PREDICATE_BUILD, "string literal longer than 7 bytes");
+      if (l->precision == LLKV_LIT_STRING_BY_REF) { /* by reference: the caller's bytes outlive this call */
+        out->s.p = (const uint8_t*)(uintptr_t)l->lo;
+        out->s.n = l->hi;
+        return 0;
+      }
+      memcpy(str_store, &l->lo, 8);
+      memcpy(str_store + 8, &l->hi, 8);
+      out->s.p = str_store;
+      out->s.n = l->precision > 15 ? 15 : l->precision;
       return 0;
     }
   }
@@ -303,10 +313,11 @@ static int32_t build_pred(const oracle_column* c, const llkv_eval_op* op, const 
   int ds = -1;
   int32_t rc;
   const llkv_literal* l = lits + op->lit_begin;
+  p->strbuf = (uint8_t*)calloc((size_t)(op->lit_count > 2 ? op->lit_count : 2), 16);
   switch (op->operator_tag) {
     case LLKV_OP_EQUALS: case LLKV_OP_GT: case LLKV_OP_GTE: case LLKV_OP_LT: case LLKV_OP_LTE:
       if (op->lit_count != 1) return fail(e, LLKV_ERR_INTERNAL, "operator needs one literal");
-      if ((rc = lit_to_native(c, l, &p->a, &ds, e))) return rc;
+      if ((rc = lit_to_native(c, l, &p->a, &ds, p->strbuf, e))) return rc;
       break;
     case LLKV_OP_RANGE: {
       int k = 0;
@@ -320,8 +331,8 @@ static int32_t build_pred(const oracle_column* c, const llkv_eval_op* op, const 
         }
         if (c->scale > ds) ds = c->scale;
       }
-      if (op->lower_kind != LLKV_BOUND_UNBOUNDED) { if ((rc = lit_to_native(c, l + k, &p->a, &ds, e))) return rc; ++k; }
-      if (op->upper_kind != LLKV_BOUND_UNBOUNDED) { if ((rc = lit_to_native(c, l + k, &p->b, &ds, e))) return rc; ++k; }
+      if (op->lower_kind != LLKV_BOUND_UNBOUNDED) { if ((rc = lit_to_native(c, l + k, &p->a, &ds, p->strbuf, e))) return rc; ++k; }
+      if (op->upper_kind != LLKV_BOUND_UNBOUNDED) { if ((rc = lit_to_native(c, l + k, &p->b, &ds, p->strbuf + 16, e))) return rc; ++k; }
       break;
     }
     case LLKV_OP_IN:
@@ -335,7 +346,7 @@ static int32_t build_pred(const oracle_column* c, const llkv_eval_op* op, const 
         if (c->scale > ds) ds = c->scale;
       }
       for (int i = 0; i < op->lit_count; ++i)
-        if ((rc = lit_to_native(c, l + i, &p->in[i], &ds, e))) { free(p->in); p->in = NULL; return rc; }
+        if ((rc = lit_to_native(c, l + i, &p->in[i], &ds, p->strbuf + 16 * i, e))) { free(p->in); p->in = NULL; return rc; }
       break;
     case LLKV_OP_STARTS_WITH: case LLKV_OP_ENDS_WITH: case LLKV_OP_CONTAINS:
       /* typed_predicate.rs:25-36: every native type but String answers false; :187-209: str::starts_with / ends_with /
@@ -343,15 +354,23 @@ static int32_t build_pred(const oracle_column* c, const llkv_eval_op* op, const 
       if (op->lit_count != 1) return fail(e, LLKV_ERR_INTERNAL, "operator needs one literal");
       if (p->dom != DOM_STR) { p->op = LLKV_OP_IN; p->n_in = 0; break; }
       if (l->kind != LLKV_LIT_STRING) return fail(e, LLKV_ERR_PREDICATE_BUILD, "literal type mismatch: expected string");
-      if (l->precision > 16) return fail(e, LLKV_ERR_PREDICATE_BUILD, "string literal longer than the 16 inline bytes of llkv_literal");
-      memcpy(p->pat, &l->lo, 8);
-      memcpy(p->pat + 8, &l->hi, 8);
-      p->pat_len = (int)l->precision;
+      if (l->precision == LLKV_LIT_STRING_BY_REF) {
+        p->pat_long = (const uint8_t*)(uintptr_t)l->lo;
+        p->pat_len = (int)l->hi;
+        p->pat_ptr = (uint8_t*)malloc((size_t)p->pat_len + 1);
+        memcpy(p->pat_ptr, p->pat_long, (size_t)p->pat_len);
+      } else {
+        memcpy(p->pat, &l->lo, 8);
+        memcpy(p->pat + 8, &l->hi, 8);
+        p->pat_len = (int)(l->precision > 15 ? 15 : l->precision);
+        p->pat_ptr = (uint8_t*)malloc(16);
+        memcpy(p->pat_ptr, p->pat, 16);
+      }
       p->ci = op->literal_bool != 0;
       if (p->ci) {
         for (int i = 0; i < p->pat_len; ++i) {
-          if (p->pat[i] >= 0x80) return fail(e, LLKV_ERR_PREDICATE_BUILD, "case-insensitive patterns are ASCII-only on this path");
-          if (p->pat[i] >= 'A' && p->pat[i] <= 'Z') p->pat[i] = (uint8_t)(p->pat[i] + 32);
+          if (p->pat_ptr[i] >= 0x80) return fail(e, LLKV_ERR_PREDICATE_BUILD, "case-insensitive patterns are ASCII-only on this path");
+          if (p->pat_ptr[i] >= 'A' && p->pat_ptr[i] <= 'Z') p->pat_ptr[i] = (uint8_t)(p->pat_ptr[i] + 32);
         }
         const int32_t* off = (const int32_t*)c->values;
         const uint8_t* data = (const uint8_t*)c->aux;
@@ -371,7 +390,12 @@ static int32_t build_pred(const oracle_column* c, const llkv_eval_op* op, const 
 static inline int pv_cmp(int dom, PVal v, PVal t) {
   switch (dom) {
     case DOM_I64: return v.i < t.i ? -1 : v.i > t.i;
-    case DOM_U64: case DOM_STR: case DOM_BOOL: return v.u < t.u ? -1 : v.u > t.u;
+    case DOM_U64: case DOM_BOOL: return v.u < t.u ? -1 : v.u > t.u;
+    case DOM_STR: { /* str::cmp: byte-wise, then by length */
+      int c = memcmp(v.s.p, t.s.p, (size_t)(v.s.n < t.s.n ? v.s.n : t.s.n));
+      if (c) return c < 0 ? -1 : 1;
+      return v.s.n < t.s.n ? -1 : v.s.n > t.s.n;
+    }
     case DOM_DEC: return v.d < t.d ? -1 : v.d > t.d;
     default: if (v.f != v.f || t.f != t.f) return 2; return v.f < t.f ? -1 : v.f > t.f;
   }
@@ -379,7 +403,8 @@ static inline int pv_cmp(int dom, PVal v, PVal t) {
 static inline int pv_eq(int dom, PVal v, PVal t) {
   switch (dom) {
     case DOM_I64: return v.i == t.i;
-    case DOM_U64: case DOM_STR: case DOM_BOOL: return v.u == t.u;
+    case DOM_U64: case DOM_BOOL: return v.u == t.u;
+    case DOM_STR: return v.s.n == t.s.n && memcmp(v.s.p, t.s.p, (size_t)v.s.n) == 0;
     case DOM_DEC: return v.d == t.d;
     default: return v.f == t.f;
   }
@@ -407,17 +432,19 @@ static inline int pred_matches(const TPred* p, PVal v) {
         if (pv_eq(p->dom, v, p->in[i])) return 1;
       return 0;
     case LLKV_OP_STARTS_WITH: case LLKV_OP_ENDS_WITH: case LLKV_OP_CONTAINS: {
-      uint8_t s[8];
-      const int len = (int)(v.u & 0xff), L = p->pat_len;
-      for (int i = 0; i < len; ++i) {
-        s[i] = (uint8_t)(v.u >> (56 - 8 * i));
-        if (p->ci && s[i] >= 'A' && s[i] <= 'Z') s[i] = (uint8_t)(s[i] + 32);
-      }
+      const int64_t len = (int64_t)v.s.n, L = p->pat_len;
       if (L > len) return 0;
-      if (p->op == LLKV_OP_STARTS_WITH) return memcmp(s, p->pat, (size_t)L) == 0;
-      if (p->op == LLKV_OP_ENDS_WITH) return memcmp(s + len - L, p->pat, (size_t)L) == 0;
-      for (int at = 0; at + L <= len; ++at)
-        if (memcmp(s + at, p->pat, (size_t)L) == 0) return 1;
+      const int64_t first = p->op == LLKV_OP_ENDS_WITH ? len - L : 0;
+      const int64_t last = p->op == LLKV_OP_STARTS_WITH ? 0 : len - L;
+      for (int64_t at = first; at <= last; ++at) {
+        int64_t k = 0;
+        for (; k < L; ++k) {
+          uint8_t ch = v.s.p[at + k];
+          if (p->ci && ch >= 'A' && ch <= 'Z') ch = (uint8_t)(ch + 32);
+          if (ch != p->pat_ptr[k]) break;
+        }
+        if (k == L) return 1;
+      }
       return 0;
     }
   }
@@ -440,7 +467,12 @@ static inline int load_pval(const oracle_column* c, const TPred* p, uint64_t i, 
       v->d = x;
       return 1;
     }
-    case DOM_STR: return load_str(c, i, &v->u);
+    case DOM_STR: {
+      const int32_t* off = (const int32_t*)c->values;
+      v->s.p = (const uint8_t*)c->aux + off[i];
+      v->s.n = (uint64_t)(off[i + 1] - off[i]);
+      return 1;
+    }
   }
   return 0;
 }
@@ -897,7 +929,9 @@ static Arr literal_to_array(const llkv_literal* l) { /* eval.rs:521-543 */
       uint8_t bytes[16];
       memcpy(bytes, &l->lo, 8);
       memcpy(bytes + 8, &l->hi, 8);
-      pack_short_string(bytes, l->precision > 7 ? 7 : l->precision, &((uint64_t*)a.data)[0]);
+      if (l->precision == LLKV_LIT_STRING_BY_REF) memcpy(bytes, (const void*)(uintptr_t)l->lo, l->hi < 7 ? (size_t)l->hi : 7);
+      uint32_t n = l->precision == LLKV_LIT_STRING_BY_REF ? (uint32_t)(l->hi < 7 ? l->hi : 7) : (uint32_t)(l->precision > 7 ? 7 : l->precision);
+      pack_short_string(bytes, n, &((uint64_t*)a.data)[0]);
       break;
     }
     default: a = arr_new(LLKV_PT_NULL, 0, 0, 1); break;
@@ -1256,9 +1290,11 @@ static int32_t eval_leaf(const ProgCtx* pc, const llkv_eval_op* op, StackEnt* ou
     bits_fill(&out->t); /* all table rows (table.rs:1146-1154) */
   } else {
     TPred p;
-    if ((rc = build_pred(c, op, pc->prog->literals, &p, e))) { bits_free(&out->t); return rc; }
+    if ((rc = build_pred(c, op, pc->prog->literals, &p, e))) { free(p.strbuf); free(p.pat_ptr); bits_free(&out->t); return rc; }
     rc = leaf_scan(c, &p, pc->rb, pc->re, pc->n_threads, &out->t, e);
     free(p.in);
+    free(p.strbuf);
+    free(p.pat_ptr);
     if (rc) { bits_free(&out->t); return rc; }
   }
   if (pc->need_domain) { /* DomainOp::PushFieldAll(field) */
@@ -1792,6 +1828,57 @@ static size_t gm_find_or_add(GroupMap* m, const uint64_t* k, const uint8_t* v) {
   return m->n++;
 }
 
+/* GroupKeyValue::String for columns that hold strings longer than the 7 bytes a packed key carries: the key is the first
+ * row (in scan order) holding the same bytes, found through a hash set of rows compared by content.  The caller reads the
+ * string from its own column (llkv_group_key.dict = 2). */
+typedef struct {
+  const oracle_column* c;
+  uint64_t* slot; /* row + 1, 0 = empty */
+  size_t cap, n;
+} StrIntern;
+static uint64_t str_hash(const oracle_column* c, uint64_t row) {
+  const int32_t* off = (const int32_t*)c->values;
+  const uint8_t* p = (const uint8_t*)c->aux + off[row];
+  uint64_t h = 1469598103934665603ull;
+  for (int32_t i = 0; i < off[row + 1] - off[row]; ++i) h = (h ^ p[i]) * 1099511628211ull;
+  return h;
+}
+static int str_same(const oracle_column* c, uint64_t a, uint64_t b) {
+  const int32_t* off = (const int32_t*)c->values;
+  const int32_t la = off[a + 1] - off[a], lb = off[b + 1] - off[b];
+  return la == lb && memcmp((const uint8_t*)c->aux + off[a], (const uint8_t*)c->aux + off[b], (size_t)la) == 0;
+}
+static uint64_t intern_row(StrIntern* t, uint64_t row) {
+  if ((t->n + 1) * 2 > t->cap) {
+    size_t ncap = t->cap ? t->cap * 2 : 1024;
+    uint64_t* ns = (uint64_t*)calloc(ncap, 8);
+    for (size_t i = 0; i < t->cap; ++i)
+      if (t->slot[i]) {
+        size_t h = (size_t)str_hash(t->c, t->slot[i] - 1) & (ncap - 1);
+        while (ns[h]) h = (h + 1) & (ncap - 1);
+        ns[h] = t->slot[i];
+      }
+    free(t->slot);
+    t->slot = ns;
+    t->cap = ncap;
+  }
+  size_t h = (size_t)str_hash(t->c, row) & (t->cap - 1);
+  while (t->slot[h]) {
+    if (str_same(t->c, t->slot[h] - 1, row)) return t->slot[h] - 1;
+    h = (h + 1) & (t->cap - 1);
+  }
+  t->slot[h] = row + 1;
+  ++t->n;
+  return row;
+}
+static int col_has_long_string(const oracle_column* c) {
+  if (c->type != LLKV_PT_UTF8) return 0;
+  const int32_t* off = (const int32_t*)c->values;
+  for (uint64_t i = 0; i < c->n_rows; ++i)
+    if (off[i + 1] - off[i] > 7) return 1;
+  return 0;
+}
+
 /* group_key_value (llkv-executor/src/lib.rs:9362-9456): ints/Date32 -> i64, bool, Utf8; others unsupported */
 static int32_t key_value(const oracle_column* c, uint64_t row, uint64_t* bits, uint8_t* valid, Err* e) {
   *valid = (uint8_t)col_valid(c, row);
@@ -1819,6 +1906,9 @@ static int32_t run_grouped(const EvalCtx* base, const Bits* sel, uint64_t rb, co
   uint64_t kb[16];
   uint8_t kv[16];
   int32_t rc = 0;
+  StrIntern* interns = (StrIntern*)calloc((size_t)n_keys, sizeof(StrIntern));
+  for (int k = 0; k < n_keys; ++k)
+    if (col_has_long_string(kc[k])) interns[k].c = kc[k];
   /* pass 1: key -> group index, (row) lists */
   for (uint64_t w = 0; w < sel->nwords && !rc; ++w) {
     uint64_t cur = sel->w[w];
@@ -1826,7 +1916,14 @@ static int32_t run_grouped(const EvalCtx* base, const Bits* sel, uint64_t rb, co
       int b = __builtin_ctzll(cur);
       cur &= cur - 1;
       uint64_t row = rb + w * 64 + (uint64_t)b;
-      for (int k = 0; k < n_keys && !rc; ++k) rc = key_value(kc[k], row, &kb[k], &kv[k], e);
+      for (int k = 0; k < n_keys && !rc; ++k) {
+        if (interns[k].c) {
+          kv[k] = (uint8_t)col_valid(kc[k], row);
+          kb[k] = kv[k] ? intern_row(&interns[k], row) : 0;
+        } else {
+          rc = key_value(kc[k], row, &kb[k], &kv[k], e);
+        }
+      }
       if (rc) break;
       size_t gi = gm_find_or_add(&gm, kb, kv);
       rv_push(&gm.g[gi].rows, row);
@@ -1854,9 +1951,12 @@ static int32_t run_grouped(const EvalCtx* base, const Bits* sel, uint64_t rb, co
       ok->bits = g->keys[k];
       ok->valid = g->kvalid[k];
       ok->type = kc[k]->type;
+      ok->dict = interns[k].c ? 2 : 0;
     }
   }
   if (!rc) *out_groups = gm.n;
+  for (int k = 0; k < n_keys; ++k) free(interns[k].slot);
+  free(interns);
   for (size_t gi = 0; gi < gm.n; ++gi) { free(gm.g[gi].keys); free(gm.g[gi].kvalid); free(gm.g[gi].rows.v); }
   free(gm.g);
   free(gm.table);

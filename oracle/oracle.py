@@ -94,7 +94,7 @@ class _Bound:
         if expr is not None:
             cp = ProgramCompiler(expr).compile()
             ops, n_ops, lits, n_lits, nodes, n_nodes, roots, n_roots = cp.c_arrays()
-            self.keep += [ops, lits, nodes, roots]
+            self.keep += [cp, ops, lits, nodes, roots]  # (cp owns the bytes of by-reference string literals)
             self.prog.ops, self.prog.n_ops = ops, n_ops
             self.prog.literals, self.prog.n_literals = lits, n_lits
             self.prog.nodes, self.prog.n_nodes = nodes, n_nodes
@@ -157,7 +157,7 @@ def aggregate(table: HostTable, expr: Optional[Expr], specs: Sequence[AggregateS
     rows = []
     nk = len(group_by)
     for g in range(n_groups.value):
-        key = tuple(decode_group_key(out_keys[g * nk + k]) for k in range(nk))
+        key = tuple(decode_group_key(out_keys[g * nk + k], lambda kind, row, k=k: table.columns[group_by[k]].string_at(row)) for k in range(nk))
         vals = [AggregateValue.from_c(out_vals[g * n_aggs + a]) for a in range(n_aggs)]
         rows.append((key, vals))
     return rows

@@ -2,6 +2,8 @@
 // the stack program of the fused scan kernel.  No CUDA here.
 #include "compiler.h"
 
+#include <algorithm>
+
 #include <math.h>
 #include <stdarg.h>
 #include <stdio.h>
@@ -486,6 +488,10 @@ class Emitter {
       emit(OP_PRED_ALL, 0, 0, 0);
       return;
     }
+    if (c.dict_sorted) {
+      emit_dict_leaf(c, op, l);
+      return;
+    }
     int lower = LLKV_BOUND_UNBOUNDED, upper = LLKV_BOUND_UNBOUNDED, eq = 0;
     const llkv_literal *ll = nullptr, *ul = nullptr;
     switch (op.operator_tag) {
@@ -627,16 +633,117 @@ class Emitter {
         return out;
       case DOM_STR: {
         if (l.kind != LLKV_LIT_STRING) fail(LLKV_ERR_PREDICATE_BUILD, "literal type mismatch: expected string");
-        uint8_t bytes[16];
-        memcpy(bytes, &l.lo, 8);
-        memcpy(bytes + 8, &l.hi, 8);
+        const char* bytes;
+        size_t len;
+        literal_bytes(l, &bytes, &len);
         uint64_t packed = 0;
-        if (!pack_short_string(bytes, l.precision, &packed)) fail(LLKV_ERR_PREDICATE_BUILD, "string literal longer than 7 bytes");
+        if (!pack_short_string((const uint8_t*)bytes, (uint32_t)std::min<size_t>(len, 8), &packed))
+          fail(LLKV_ERR_PREDICATE_BUILD, "string literal longer than 7 bytes against a short-string column");
         out.lo = packed;
         return out;
       }
     }
     fail(LLKV_ERR_INTERNAL, "bad domain");
+  }
+
+  // Typed leaves over a dictionary-coded Utf8 column (strings longer than 7 bytes): the resident values are ranks in the
+  // byte-ordered dictionary, so every leaf becomes an integer leaf over ranks — equality and IN by looking the literal up,
+  // ranges by lower/upper bound, patterns by testing each entry once here (typed_predicate.rs:75-209 on String).
+  static std::string lit_string(const llkv_literal& l) {
+    if (l.kind != LLKV_LIT_STRING) fail(LLKV_ERR_PREDICATE_BUILD, "literal type mismatch: expected string");
+    const char* bytes;
+    size_t len;
+    literal_bytes(l, &bytes, &len);
+    return std::string(bytes, len);
+  }
+  void emit_rank_range(int64_t lo, int64_t hi) {  // inclusive; lo > hi: nothing matches
+    if (lo > hi) {
+      emit(OP_IN_BITS, 0, 0, 0);
+      return;
+    }
+    std::vector<Lit> run(2);
+    run[0].lo = (uint64_t)lo; run[0].hi = 0;
+    run[1].lo = (uint64_t)hi; run[1].hi = 0;
+    emit(OP_PRED_U, (uint8_t)(LLKV_BOUND_INCLUDED | (LLKV_BOUND_INCLUDED << 2)), 0, add_lit_run(run));
+  }
+  void emit_rank_set(const std::vector<uint32_t>& ranks) {  // ascending
+    if (ranks.empty()) { emit(OP_IN_BITS, 0, 0, 0); return; }
+    if ((size_t)(ranks.back() - ranks.front()) + 1 == ranks.size()) { emit_rank_range(ranks.front(), ranks.back()); return; }
+    if (ranks.size() > 255) fail(LLKV_ERR_PREDICATE_BUILD, "the predicate matches %zu scattered dictionary entries (at most 255 on this path)", ranks.size());
+    std::vector<Lit> run(ranks.size());
+    for (size_t i = 0; i < ranks.size(); ++i) { run[i].lo = ranks[i]; run[i].hi = 0; }
+    emit(OP_IN_BITS, 0, (uint8_t)run.size(), add_lit_run(run));
+  }
+  void emit_dict_leaf(const ColumnMeta& c, const llkv_eval_op& op, const llkv_literal* l) {
+    const std::vector<std::string>& dict = *c.dict_sorted;
+    const int64_t D = (int64_t)dict.size();
+    auto lb = [&](const std::string& x) { return (int64_t)(std::lower_bound(dict.begin(), dict.end(), x) - dict.begin()); };
+    auto ub = [&](const std::string& x) { return (int64_t)(std::upper_bound(dict.begin(), dict.end(), x) - dict.begin()); };
+    switch (op.operator_tag) {
+      case LLKV_OP_EQUALS: case LLKV_OP_GT: case LLKV_OP_GTE: case LLKV_OP_LT: case LLKV_OP_LTE: {
+        if (op.lit_count != 1) fail(LLKV_ERR_INTERNAL, "operator needs one literal");
+        const std::string x = lit_string(l[0]);
+        if (op.operator_tag == LLKV_OP_EQUALS) emit_rank_range(lb(x), ub(x) - 1);
+        else if (op.operator_tag == LLKV_OP_GT) emit_rank_range(ub(x), D - 1);
+        else if (op.operator_tag == LLKV_OP_GTE) emit_rank_range(lb(x), D - 1);
+        else if (op.operator_tag == LLKV_OP_LT) emit_rank_range(0, lb(x) - 1);
+        else emit_rank_range(0, ub(x) - 1);
+        return;
+      }
+      case LLKV_OP_RANGE: {
+        int k = 0;
+        int64_t lo = 0, hi = D - 1;
+        if (op.lower_kind != LLKV_BOUND_UNBOUNDED) {
+          if (k >= op.lit_count) fail(LLKV_ERR_INTERNAL, "range bounds without literals");
+          const std::string x = lit_string(l[k++]);
+          lo = op.lower_kind == LLKV_BOUND_INCLUDED ? lb(x) : ub(x);
+        }
+        if (op.upper_kind != LLKV_BOUND_UNBOUNDED) {
+          if (k >= op.lit_count) fail(LLKV_ERR_INTERNAL, "range bounds without literals");
+          const std::string x = lit_string(l[k++]);
+          hi = op.upper_kind == LLKV_BOUND_INCLUDED ? ub(x) - 1 : lb(x) - 1;
+        }
+        emit_rank_range(lo, hi);
+        return;
+      }
+      case LLKV_OP_IN: {
+        std::vector<uint32_t> ranks;
+        for (int i = 0; i < op.lit_count; ++i) {
+          const std::string x = lit_string(l[i]);
+          const int64_t r = lb(x);
+          if (r < D && dict[(size_t)r] == x) ranks.push_back((uint32_t)r);
+        }
+        std::sort(ranks.begin(), ranks.end());
+        ranks.erase(std::unique(ranks.begin(), ranks.end()), ranks.end());
+        emit_rank_set(ranks);
+        return;
+      }
+      case LLKV_OP_STARTS_WITH: case LLKV_OP_ENDS_WITH: case LLKV_OP_CONTAINS: {
+        if (op.lit_count != 1) fail(LLKV_ERR_INTERNAL, "operator needs one literal");
+        std::string pat = lit_string(l[0]);
+        const bool ci = op.literal_bool != 0;
+        auto lower = [](std::string& x) { for (char& ch : x) if (ch >= 'A' && ch <= 'Z') ch = (char)(ch + 32); };
+        if (ci) {
+          for (char ch : pat) if ((unsigned char)ch >= 0x80) fail(LLKV_ERR_PREDICATE_BUILD, "case-insensitive patterns are ASCII-only on this path");
+          if (c.str_non_ascii) fail(LLKV_ERR_PREDICATE_BUILD, "case-insensitive match over a column with non-ASCII strings is not on this path");
+          lower(pat);
+        }
+        std::vector<uint32_t> ranks;
+        for (int64_t r = 0; r < D; ++r) {
+          std::string v = dict[(size_t)r];
+          if (ci) lower(v);
+          bool m;
+          if (pat.size() > v.size()) m = false;
+          else if (op.operator_tag == LLKV_OP_STARTS_WITH) m = v.compare(0, pat.size(), pat) == 0;
+          else if (op.operator_tag == LLKV_OP_ENDS_WITH) m = v.compare(v.size() - pat.size(), pat.size(), pat) == 0;
+          else m = v.find(pat) != std::string::npos;
+          if (m) ranks.push_back((uint32_t)r);
+        }
+        emit_rank_set(ranks);
+        return;
+      }
+      default: fail(LLKV_ERR_PREDICATE_BUILD, "operator lacks typed literal support");
+    }
   }
 
   // StartsWith / EndsWith / Contains (typed_predicate.rs:187-209; only String implements them: :25-36 is `false` for every
@@ -647,11 +754,15 @@ class Emitter {
       return;
     }
     if (l.kind != LLKV_LIT_STRING) fail(LLKV_ERR_PREDICATE_BUILD, "literal type mismatch: expected string");
-    uint8_t bytes[16];
-    memcpy(bytes, &l.lo, 8);
-    memcpy(bytes + 8, &l.hi, 8);
-    const uint32_t len = l.precision;
-    if (len > 16) fail(LLKV_ERR_PREDICATE_BUILD, "string literal longer than the 16 inline bytes of llkv_literal");
+    const char* src;
+    size_t full_len;
+    literal_bytes(l, &src, &full_len);
+    if (ci)
+      for (size_t i = 0; i < full_len; ++i)
+        if ((unsigned char)src[i] >= 0x80) fail(LLKV_ERR_PREDICATE_BUILD, "case-insensitive patterns are ASCII-only on this path");
+    uint8_t bytes[16] = {0};
+    memcpy(bytes, src, std::min<size_t>(full_len, 16));
+    const uint32_t len = (uint32_t)std::min<size_t>(full_len, 16);  // (anything above 7 matches no short string)
     if (ci) {
       // to_lowercase() is Unicode's: ASCII lowering equals it exactly when neither side holds a non-ASCII character
       for (uint32_t i = 0; i < len; ++i) {
@@ -910,11 +1021,11 @@ class Emitter {
       case LLKV_LIT_DECIMAL128: push_lit_i(lit_i128(l)); break;
       case LLKV_LIT_DATE32: push_lit_i((i128)(int64_t)l.lo); break;
       case LLKV_LIT_STRING: {
-        uint8_t bytes[16];
-        memcpy(bytes, &l.lo, 8);
-        memcpy(bytes + 8, &l.hi, 8);
+        const char* bytes;
+        size_t len;
+        literal_bytes(l, &bytes, &len);
         uint64_t k = 0;
-        pack_short_string(bytes, l.precision > 7 ? 7 : l.precision, &k);
+        pack_short_string((const uint8_t*)bytes, (uint32_t)std::min<size_t>(len, 7), &k);
         push_lit_bits(k);
         break;
       }
@@ -1007,6 +1118,16 @@ class Emitter {
     return v.t;
   }
 
+  // string comparisons inside scalar expressions work on packed short strings; dictionary codes of different columns (or a
+  // code and a packed literal) do not compare
+  void reject_dict_columns() const {
+    for (const ColumnMeta& c : req_.cols)
+      if (c.dict_sorted && c.type == LLKV_PT_UTF8)
+        for (int i = 0; i < n_nodes_; ++i)
+          if (nodes_[i].tag == LLKV_SE_COLUMN && find_col(nodes_[i].field_id) >= 0 && &req_.cols[find_col(nodes_[i].field_id)] == &c)
+            fail(LLKV_ERR_INVALID_ARGUMENT, "scalar expressions over a dictionary-coded (long string) column are not on this path: use a typed predicate");
+  }
+
   // compute_compare (kernels.rs:269-297) over two sub-expressions -> B on the stack
   void emit_compare(int left, int cmp, int right, bool batch) {
     check_node(left);
@@ -1023,7 +1144,8 @@ class Emitter {
     uint16_t opc;
     switch (kind_of_type(ct.type)) {
       case K_I64: case K_DATE32: opc = OP_CMP_I; break;
-      case K_U64: case K_STR: case K_BOOL: opc = OP_CMP_U; break;
+      case K_STR: reject_dict_columns(); opc = OP_CMP_U; break;
+      case K_U64: case K_BOOL: opc = OP_CMP_U; break;
       case K_F64: opc = OP_CMP_F; break;
       case K_DEC: opc = OP_CMP_D; break;
       default: fail(LLKV_ERR_INTERNAL, "compare on type %d is not supported on this path", ct.type);
@@ -1069,7 +1191,8 @@ class Emitter {
       uint16_t opc;
       switch (kind_of_type(ct.type)) {
         case K_I64: case K_DATE32: opc = OP_CMP_I; break;
-        case K_U64: case K_STR: case K_BOOL: opc = OP_CMP_U; break;
+        case K_STR: reject_dict_columns(); opc = OP_CMP_U; break;
+      case K_U64: case K_BOOL: opc = OP_CMP_U; break;
         case K_F64: opc = OP_CMP_F; break;
         case K_DEC: opc = OP_CMP_D; break;
         default: fail(LLKV_ERR_INTERNAL, "compare on type %d is not supported on this path", ct.type);
@@ -1239,6 +1362,14 @@ class Emitter {
           kl.bits = (uint8_t)width;
           kl.min = 0;
         }
+      } else if (c.type == LLKV_PT_UTF8 && c.dict_sorted) {  // dictionary codes: ranks 0 .. entries-1
+        kl.kind = KK_INT;
+        kl.dict = true;
+        const uint64_t range = c.dict_sorted->empty() ? 0 : c.dict_sorted->size() - 1;
+        int b = 1;
+        while (b < 64 && (range >> b)) ++b;
+        kl.bits = (uint8_t)b;
+        kl.min = 0;
       } else if (c.type == LLKV_PT_UTF8) {
         kl.kind = KK_STR;
         kl.strlen = c.max_strlen;

@@ -38,7 +38,21 @@ struct ColumnMeta {
   bool has_minmax = false;
   uint8_t max_strlen = 0;  // Utf8
   bool str_non_ascii = false;  // Utf8: some string holds a byte >= 0x80
+  // Utf8 column in dictionary form (strings longer than 7 bytes): the resident values are ranks in this byte-ordered list
+  const std::vector<std::string>* dict_sorted = nullptr;
+  uint64_t dict_epoch = 0;
 };
+
+// bytes of a string literal: inline (precision <= 15; lo and hi are adjacent, little endian) or by reference
+inline void literal_bytes(const llkv_literal& l, const char** p, size_t* n) {
+  if (l.precision == LLKV_LIT_STRING_BY_REF) {
+    *p = reinterpret_cast<const char*>(static_cast<uintptr_t>(l.lo));
+    *n = static_cast<size_t>(l.hi);
+  } else {
+    *p = reinterpret_cast<const char*>(&l.lo);
+    *n = l.precision > 15 ? 15 : l.precision;
+  }
+}
 
 struct ProgramView {
   const llkv_eval_op* ops = nullptr;
@@ -89,6 +103,7 @@ struct KeyLayout {
   uint8_t kind = 0, bits = 0, strlen = 0, nullable = 0;
   uint64_t min = 0;
   bool is_signed = false;
+  bool dict = false;  // Utf8 key whose field is a dictionary code
 };
 
 struct CompileRequest {

@@ -16,7 +16,10 @@
 #include <memory>
 #include <mutex>
 #include <string>
+#include <deque>
+#include <string_view>
 #include <thread>
+#include <unordered_map>
 #include <vector>
 
 #include "../../include/llkv_gpu.h"
@@ -181,6 +184,10 @@ __global__ void pack_utf8_kernel(const int* __restrict__ off, const unsigned cha
     atomicMin(&st->min_strlen, mn);
   }
   if (bad) atomicOr(&st->bad_string, bad);
+}
+// dictionary-coded strings: codes -> ranks after the dictionary has been re-ordered at seal
+__global__ void remap_codes_kernel(u64* __restrict__ v, u64 n, const unsigned int* __restrict__ remap) {
+  for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (u64)gridDim.x * blockDim.x) v[i] = remap[v[i]];
 }
 __global__ void narrow_str_kernel(const u64* __restrict__ in, unsigned char* __restrict__ out, u64 n) {
   for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (u64)gridDim.x * blockDim.x) out[i] = (unsigned char)(in[i] >> 56);
@@ -497,8 +504,33 @@ struct NarrowChunk {  // a chunk appended through the host-narrowing path since 
   uint64_t first_row, n_rows;
 };
 
+// Dictionary of a Utf8 column that holds strings longer than the 7 bytes of a packed key (llkv_gpu.h, "Utf8 columns").
+// Ids are handed out in order of first appearance by the host side of append; seal orders the entries byte-wise and turns
+// the resident codes into ranks.  Between seals codes below `sealed` are ranks, codes from `sealed` up are raw ids.
+struct StrDict {
+  std::deque<std::string> strings;  // by id; a deque keeps the addresses the map's keys point to
+  std::unordered_map<std::string_view, uint32_t> id_of;
+  std::vector<uint32_t> rank_of_id, id_of_rank;  // over ids < sealed
+  std::vector<std::string> sorted;               // by rank: what plans search and finalize decodes
+  uint32_t sealed = 0;
+  uint64_t epoch = 0;
+  bool non_ascii = false;
+  uint32_t intern(const char* p, size_t n) {
+    auto it = id_of.find(std::string_view(p, n));
+    if (it != id_of.end()) return it->second;
+    strings.emplace_back(p, n);
+    const uint32_t id = (uint32_t)strings.size() - 1;
+    id_of.emplace(std::string_view(strings.back()), id);
+    for (size_t i = 0; i < n && !non_ascii; ++i) non_ascii = (unsigned char)p[i] >= 0x80;
+    return id;
+  }
+  uint64_t code_of(uint32_t id) const { return id < sealed ? rank_of_id[id] : id; }
+};
+constexpr size_t kMaxDictEntries = 1u << 24;
+
 struct llkv_gpu_column {
   llkv_gpu_ctx* ctx = nullptr;
+  std::unique_ptr<StrDict> dict;
   uint64_t lfid = 0;
   int32_t type = 0;
   uint8_t precision = 0;
@@ -549,8 +581,18 @@ struct llkv_gpu_column {
   uint32_t scans_unchanged = 0;  // fused scans with a range leaf on this column since the content last changed
 };
 
+// String literals passed by reference are copied into storage the receiving handle owns (shared: handles are copied)
+typedef std::shared_ptr<std::deque<std::string>> StringStore;
+static void own_string_literal(llkv_literal& l, StringStore& store) {
+  if (l.kind != LLKV_LIT_STRING || l.precision != LLKV_LIT_STRING_BY_REF) return;
+  if (!store) store = std::make_shared<std::deque<std::string>>();
+  store->emplace_back(reinterpret_cast<const char*>(static_cast<uintptr_t>(l.lo)), static_cast<size_t>(l.hi));
+  l.lo = static_cast<uint64_t>(reinterpret_cast<uintptr_t>(store->back().data()));
+}
+
 struct llkv_gpu_program {
   uint64_t serial = 0;  // identity of the compiled program (handles can be freed and their addresses reused)
+  StringStore strings;
   std::vector<llkv_eval_op> ops;
   std::vector<llkv_literal> literals;
   std::vector<llkv_scalar_node> nodes;
@@ -583,6 +625,7 @@ struct PendingRun {
 
 struct llkv_gpu_agg {
   llkv_gpu_ctx* ctx = nullptr;
+  StringStore strings;
   uint64_t table_id = 0;
   std::vector<llkv_agg_spec> specs;
   std::vector<llkv_scalar_node> nodes;
@@ -1311,6 +1354,68 @@ static int32_t append_sparse(llkv_gpu_column* col, const void* values, uint64_t 
   return LLKV_OK;
 }
 
+// A Utf8 column meets its first string longer than 7 bytes: the rows it already holds (packed keys, which carry their bytes)
+// are read back once, interned, and rewritten as dictionary codes.
+static int32_t enter_dict_mode(llkv_gpu_column* col) {
+  llkv_gpu_ctx* c = col->ctx;
+  int32_t rc = flush_upload(col);
+  if (rc) return rc;
+  cudaStream_t s = c->copy_streams[(size_t)col->stream_index];
+  CUDA_TRY(cudaStreamSynchronize(s));
+  CUDA_TRY(cudaStreamSynchronize(c->stream));
+  col->dict.reset(new StrDict());
+  StrDict& d = *col->dict;
+  if (col->n_rows) {
+    std::vector<u64> keys((size_t)col->n_rows);
+    CUDA_TRY(cudaMemcpy(keys.data(), col->values, col->n_rows * 8, cudaMemcpyDeviceToHost));
+    std::unordered_map<u64, uint32_t> seen;
+    for (u64& k : keys) {
+      auto it = seen.find(k);
+      if (it == seen.end()) {
+        char b[8];
+        const size_t len = (size_t)(k & 0xff) > 7 ? 0 : (size_t)(k & 0xff);
+        for (size_t j = 0; j < len; ++j) b[j] = (char)(k >> (56 - 8 * j));
+        it = seen.emplace(k, d.intern(b, len)).first;
+      }
+      k = it->second;
+    }
+    CUDA_TRY(cudaMemcpy(col->values, keys.data(), col->n_rows * 8, cudaMemcpyHostToDevice));
+    col->h2d_bytes += col->n_rows * 8;
+  }
+  return LLKV_OK;
+}
+
+// seal of a dictionary-coded column: entries in byte order (str: Ord), resident codes -> ranks
+static int32_t dict_seal(llkv_gpu_column* col) {
+  llkv_gpu_ctx* c = col->ctx;
+  StrDict& d = *col->dict;
+  const uint32_t D = (uint32_t)d.strings.size();
+  if (D == d.sealed) return LLKV_OK;
+  std::vector<uint32_t> order(D);
+  for (uint32_t i = 0; i < D; ++i) order[i] = i;
+  std::sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return d.strings[a] < d.strings[b]; });  // (char_traits<char>::compare is memcmp)
+  std::vector<uint32_t> new_rank(D), remap(D);
+  for (uint32_t r = 0; r < D; ++r) new_rank[order[r]] = r;
+  for (uint32_t code = 0; code < D; ++code) remap[code] = code < d.sealed ? new_rank[d.id_of_rank[code]] : new_rank[code];
+  unsigned int* d_remap = nullptr;
+  cudaStream_t s = c->copy_streams[(size_t)col->stream_index];
+  CUDA_TRY(cudaMalloc((void**)&d_remap, (size_t)D * 4));
+  CUDA_TRY(cudaMemcpyAsync(d_remap, remap.data(), (size_t)D * 4, cudaMemcpyHostToDevice, s));
+  if (col->n_rows) {
+    remap_codes_kernel<<<1184, 256, 0, s>>>((u64*)col->values, col->n_rows, d_remap);
+    CUDA_TRY(cudaGetLastError());
+  }
+  CUDA_TRY(cudaStreamSynchronize(s));
+  CUDA_TRY(cudaFree(d_remap));
+  d.rank_of_id = new_rank;
+  d.id_of_rank = order;
+  d.sorted.resize(D);
+  for (uint32_t r = 0; r < D; ++r) d.sorted[r] = d.strings[order[r]];
+  d.sealed = D;
+  ++d.epoch;
+  return LLKV_OK;
+}
+
 static int32_t append_chunk_impl(llkv_gpu_column* col, const void* values, uint64_t n_rows, const uint8_t* validity, const uint64_t* row_ids,
                                  uint64_t row_id_base, const void* aux) {
   llkv_gpu_ctx* c = col->ctx;
@@ -1386,9 +1491,28 @@ static int32_t append_chunk_impl(llkv_gpu_column* col, const void* values, uint6
     const int32_t* off = (const int32_t*)values;
     const int64_t first = off[0], data_bytes = (int64_t)off[n_rows] - first;
     if (first < 0 || data_bytes < 0) return set_error(LLKV_ERR_INVALID_ARGUMENT, "Utf8 offsets are negative or not monotonic");
-    for (uint64_t i = 0; i < n_rows; ++i)
+    bool has_long = false;
+    for (uint64_t i = 0; i < n_rows; ++i) {
       if (off[i + 1] < off[i]) return set_error(LLKV_ERR_INVALID_ARGUMENT, "Utf8 offsets are not monotonic at row %llu", (unsigned long long)i);
+      has_long = has_long || off[i + 1] - off[i] > 7;
+    }
     if (data_bytes && !aux) return set_error(LLKV_ERR_INVALID_ARGUMENT, "Utf8 data buffer is NULL");
+    if (has_long && !col->dict && (rc = enter_dict_mode(col))) return rc;
+    if (col->dict) {
+      // the host interns every string; 8 bytes of code per row cross the link, the bytes of the strings never do
+      StrDict& d = *col->dict;
+      std::vector<u64> codes((size_t)n_rows);
+      const char* data = (const char*)aux;
+      for (uint64_t i = 0; i < n_rows; ++i) {
+        const bool valid = !validity || ((validity[i >> 3] >> (i & 7)) & 1);
+        codes[(size_t)i] = valid ? d.code_of(d.intern(data + off[i], (size_t)(off[i + 1] - off[i]))) : 0;
+      }
+      if (d.strings.size() > kMaxDictEntries) return set_error(LLKV_ERR_INVALID_ARGUMENT, "more than %zu distinct strings in a dictionary-coded column", kMaxDictEntries);
+      if ((rc = upload(col, (u64*)col->values + col->n_rows, codes.data(), n_rows * 8, SRC_PAGEABLE))) return rc;
+      if ((rc = flush_upload(col))) return rc;
+      CUDA_TRY(cudaStreamSynchronize(s));  // `codes` goes away with this scope
+      col->hstats.data_bytes += (u64)data_bytes;
+    } else {
     int* d_off = nullptr;
     unsigned char* d_data = nullptr;
     CUDA_TRY(cudaMalloc((void**)&d_off, (n_rows + 1) * 4));
@@ -1402,6 +1526,7 @@ static int32_t append_chunk_impl(llkv_gpu_column* col, const void* values, uint6
     CUDA_TRY(cudaFreeAsync(d_off, s));  // stream-ordered: released once the pack kernel has read them
     CUDA_TRY(cudaFreeAsync(d_data, s));
     col->hstats.data_bytes += (u64)data_bytes;
+    }
   } else if (host_kind >= 0) {
     col->narrow_chunks.push_back(NarrowChunk{values, col->n_rows, n_rows});
     col->h2d_bytes += n_rows * col->elem_bytes;
@@ -1535,8 +1660,11 @@ extern "C" int32_t llkv_gpu_column_seal(llkv_gpu_column* col) {
   const u64 data_bytes = col->hstats.data_bytes;
   CUDA_TRY(cudaMemcpy(&col->hstats, col->dstats, sizeof(DevStats), cudaMemcpyDeviceToHost));
   col->hstats.data_bytes = data_bytes;
-  if (col->type == LLKV_PT_UTF8) {
-    if (col->hstats.bad_string & 1u) return set_error(LLKV_ERR_INVALID_ARGUMENT, "string longer than 7 bytes in short-string column");
+  if (col->type == LLKV_PT_UTF8 && col->dict) {
+    int32_t rc = dict_seal(col);
+    if (rc) return rc;
+  } else if (col->type == LLKV_PT_UTF8) {
+    if (col->hstats.bad_string & 1u) return set_error(LLKV_ERR_INTERNAL, "string longer than 7 bytes in a packed short-string column");
     // every string exactly one byte long: keep one byte per row
     if (col->load_kind == LK_U64 && col->n_rows && col->hstats.max_strlen == 1 && col->hstats.min_strlen == 1) {
       unsigned char* nv = nullptr;
@@ -1723,6 +1851,28 @@ extern "C" int32_t llkv_gpu_column_visit(llkv_gpu_column* col, uint64_t chunk_ro
   return LLKV_OK;
 }
 
+extern "C" int32_t llkv_gpu_column_dict_size(llkv_gpu_column* col, uint64_t* out_entries) {
+  if (!col || !out_entries) return set_error(LLKV_ERR_INVALID_ARGUMENT, "NULL argument");
+  CTX_LOCK(col->ctx);
+  if (col->dict && !col->sealed) {
+    int32_t rc = llkv_gpu_column_seal(col);
+    if (rc) return rc;
+  }
+  *out_entries = col->dict ? col->dict->sorted.size() : 0;
+  return LLKV_OK;
+}
+
+extern "C" int32_t llkv_gpu_column_dict_entry(llkv_gpu_column* col, uint64_t code, const uint8_t** out_bytes, uint64_t* out_len) {
+  if (!col || !out_bytes || !out_len) return set_error(LLKV_ERR_INVALID_ARGUMENT, "NULL argument");
+  CTX_LOCK(col->ctx);
+  if (!col->dict) return set_error(LLKV_ERR_INVALID_ARGUMENT, "the column is not dictionary-coded");
+  if (code >= col->dict->sorted.size()) return set_error(LLKV_ERR_NOT_FOUND, "no dictionary entry %llu", (unsigned long long)code);
+  const std::string& e = col->dict->sorted[(size_t)code];
+  *out_bytes = (const uint8_t*)e.data();
+  *out_len = e.size();
+  return LLKV_OK;
+}
+
 extern "C" int32_t llkv_gpu_column_build_sort_index(llkv_gpu_column* col, uint64_t chunk_rows) {
   if (!col) return set_error(LLKV_ERR_INVALID_ARGUMENT, "column is NULL");
   llkv_gpu_ctx* c = col->ctx;
@@ -1894,6 +2044,7 @@ extern "C" int32_t llkv_gpu_column_clear(llkv_gpu_column* col) {
     col->elem_bytes = 8;
     col->load_kind = LK_U64;
   }
+  col->dict.reset();
   col->reupload_hint = true;
   if (is_narrow_decimal(col)) {  // back to the Arrow layout for new appends; the narrow buffer is parked for the next batch
     if (col->narrow && col->narrow != col->values) CUDA_TRY(cudaFree(col->narrow));
@@ -1976,6 +2127,9 @@ extern "C" int32_t llkv_gpu_program_compile(llkv_gpu_ctx* ctx, const llkv_eval_o
   p->literals.assign(literals, literals + n_literals);
   p->nodes.assign(nodes, nodes + n_nodes);
   p->list_roots.assign(list_roots, list_roots + n_list_roots);
+  for (llkv_literal& l : p->literals) own_string_literal(l, p->strings);
+  for (llkv_scalar_node& nd : p->nodes)
+    if (nd.tag == LLKV_SE_LITERAL) own_string_literal(nd.literal, p->strings);
   p->bind();
   *out = p;
   return LLKV_OK;
@@ -2142,6 +2296,14 @@ static int32_t collect_columns(llkv_gpu_ctx* ctx, uint64_t table_id, std::vector
     }
     m.max_strlen = (uint8_t)col->hstats.max_strlen;
     m.str_non_ascii = (col->hstats.bad_string & 2u) != 0;
+    if (col->dict) {  // codes are ranks 0 .. entries-1: an unsigned integer column as far as leaves and keys are concerned
+      m.dict_sorted = &col->dict->sorted;
+      m.dict_epoch = col->dict->epoch;
+      m.str_non_ascii = col->dict->non_ascii;
+      m.has_minmax = !col->dict->sorted.empty();
+      m.min_bits = 0;
+      m.max_bits = col->dict->sorted.empty() ? 0 : col->dict->sorted.size() - 1;
+    }
     cols.push_back(m);
     handles.push_back(col);
     if (!have) {
@@ -2873,6 +3035,8 @@ extern "C" int32_t llkv_gpu_agg_create(llkv_gpu_ctx* ctx, uint64_t table_id, con
   a->table_id = table_id;
   a->specs.assign(specs, specs + n_aggs);
   a->nodes.assign(nodes, nodes + n_nodes);
+  for (llkv_scalar_node& nd : a->nodes)
+    if (nd.tag == LLKV_SE_LITERAL) own_string_literal(nd.literal, a->strings);
   a->keys.assign(group_key_fields, group_key_fields + n_keys);
   a->expr_mode = expr_mode;
   a->hint = cardinality_hint;
@@ -2916,6 +3080,7 @@ extern "C" int32_t llkv_gpu_agg_set_output(llkv_gpu_agg* a, const llkv_having_te
     if (order[i].index < 0 || order[i].index >= (order[i].is_aggregate ? n_aggs : n_keys))
       return set_error(LLKV_ERR_INVALID_ARGUMENT, "ORDER BY key %d refers to output column %d", i, order[i].index);
   a->having.assign(having, having + n_having);
+  for (llkv_having_term& t : a->having) own_string_literal(t.literal, a->strings);
   a->order.assign(order, order + n_order);
   a->out_offset = offset;
   a->out_limit = limit;
@@ -3055,10 +3220,14 @@ static uint64_t request_signature(const llkv_gpu_ctx* ctx, const CompileRequest&
     h = fnv_pod(h, c.max_bits);
     h = fnv_pod(h, c.max_strlen);
     h = fnv_pod(h, c.str_non_ascii);
+    h = fnv_pod(h, c.dict_epoch);
+    h = fnv_pod(h, (uint64_t)(c.dict_sorted ? c.dict_sorted->size() + 1 : 0));
   }
   if (prog) {
     h = fnv1a(h, prog->ops.data(), prog->ops.size() * sizeof(llkv_eval_op));
     h = fnv1a(h, prog->literals.data(), prog->literals.size() * sizeof(llkv_literal));
+    if (prog->strings)  // (literals by reference hash as addresses above: their bytes decide)
+      for (const std::string& x : *prog->strings) h = fnv1a(fnv_pod(h, x.size()), x.data(), x.size());
     h = fnv1a(h, prog->nodes.data(), prog->nodes.size() * sizeof(llkv_scalar_node));
     h = fnv1a(h, prog->list_roots.data(), prog->list_roots.size() * sizeof(int32_t));
   }
@@ -3970,6 +4139,7 @@ static void decode_keys(const llkv_gpu_agg* a, u64 K, bool null_slot, llkv_group
     }
     o->valid = isnull ? 0 : 1;
     if (isnull) continue;
+    o->dict = kl.dict ? 1 : 0;
     if (kl.kind == KK_STR) {
       const int L = kl.strlen;
       const u64 len = field & 7, bytes = field >> 3;
@@ -4091,7 +4261,15 @@ static int compare_keys(const llkv_group_key& x, const llkv_group_key& y) {
   return (i64)x.bits < (i64)y.bits ? -1 : ((i64)x.bits > (i64)y.bits ? 1 : 0);
 }
 // TRUE / FALSE of `cell cmp literal`; a NULL cell is neither (HAVING keeps rows that evaluate to TRUE only)
-static bool having_holds(const llkv_having_term& t, const llkv_agg_value* v, const llkv_group_key* k) {
+// the dictionary behind key `index` of an aggregate whose key column is dictionary-coded, else null
+static const StrDict* key_dict(const llkv_gpu_agg* a, size_t index) {
+  if (index >= a->cr.keys.size() || !a->cr.keys[index].dict) return nullptr;
+  for (auto& kv : a->ctx->columns)
+    if (lfid_table(kv.second->lfid) == (a->table_id & 0xffffull) && lfid_field(kv.second->lfid) == a->cr.keys[index].field_id) return kv.second->dict.get();
+  return nullptr;
+}
+
+static bool having_holds(const llkv_having_term& t, const llkv_agg_value* v, const llkv_group_key* k, const StrDict* dict = nullptr) {
   int c;
   if (t.is_aggregate) {
     if (!v->valid) return false;
@@ -4112,16 +4290,25 @@ static bool having_holds(const llkv_having_term& t, const llkv_agg_value* v, con
   } else {
     if (!k->valid) return false;
     llkv_group_key lit = *k;
-    if (t.literal.kind == LLKV_LIT_STRING) {  // literal bytes (little endian in lo/hi) -> the key's packed form
+    if (k->dict) {  // a dictionary code: compare the entry's bytes with the literal's (str: Ord)
+      if (!dict || t.literal.kind != LLKV_LIT_STRING || k->bits >= dict->sorted.size()) return false;
+      const char* bytes;
+      size_t len;
+      literal_bytes(t.literal, &bytes, &len);
+      c = dict->sorted[(size_t)k->bits].compare(std::string(bytes, len));
+      c = c < 0 ? -1 : (c > 0 ? 1 : 0);
+    } else if (t.literal.kind == LLKV_LIT_STRING) {  // literal bytes (little endian in lo/hi) -> the key's packed form
       uint64_t bits = 0;
-      const unsigned len = t.literal.precision;
+      const char* bytes;
+      size_t len;
+      literal_bytes(t.literal, &bytes, &len);
       if (len > 7) return false;
-      for (unsigned i = 0; i < len; ++i) bits |= (uint64_t)((t.literal.lo >> (8 * i)) & 0xff) << (56 - 8 * i);
+      for (size_t i = 0; i < len; ++i) bits |= (uint64_t)(unsigned char)bytes[i] << (56 - 8 * i);
       lit.bits = bits | len;
     } else {
       lit.bits = t.literal.lo;
     }
-    c = compare_keys(*k, lit);
+    if (!k->dict) c = compare_keys(*k, lit);
   }
   switch (t.cmp_op) {
     case LLKV_CMP_EQ: return c == 0;
@@ -4222,7 +4409,8 @@ extern "C" int32_t llkv_gpu_agg_finalize(llkv_gpu_agg* a, llkv_agg_value* out_va
   for (size_t gi = 0; gi < groups.size(); ++gi) {
     bool keep = true;
     for (const llkv_having_term& t : a->having)
-      keep = keep && having_holds(t, t.is_aggregate ? &vals[gi * n_aggs + (size_t)t.index] : nullptr, t.is_aggregate ? nullptr : &keys[gi * n_keys + (size_t)t.index]);
+      keep = keep && having_holds(t, t.is_aggregate ? &vals[gi * n_aggs + (size_t)t.index] : nullptr, t.is_aggregate ? nullptr : &keys[gi * n_keys + (size_t)t.index],
+                                  t.is_aggregate ? nullptr : key_dict(a, (size_t)t.index));
     if (keep) rows.push_back(gi);
   }
   if (!a->order.empty())
@@ -4401,6 +4589,9 @@ static int32_t agg_merge_impl(llkv_gpu_agg* a) {
   if (a->inner) return agg_merge_impl(a->inner);
   llkv_gpu_ctx* ctx = a->ctx;
   if (a->err_code) return set_error(a->err_code, "%s", a->err_msg.c_str());
+  if (ctx->n_ranks > 1)
+    for (const KeyLayout& kl : a->cr.keys)
+      if (kl.dict) return set_error(LLKV_ERR_INVALID_ARGUMENT, "GROUP BY keys of a dictionary-coded (long string) column do not merge across GPUs: every rank has its own dictionary");
   int32_t rc;
   if (!a->pending.active && (rc = agg_apply_reset(a))) return rc;
   a->prefetched = false;  // the merge rewrites the table

@@ -38,6 +38,7 @@ inline void check(int32_t rc) {
 // ------------------------------------------------------------------------------------------------ Literal
 struct Literal {
   llkv_literal c{};
+  std::shared_ptr<std::string> long_string;  // bytes behind a by-reference string literal (> 15 bytes)
   static Literal Null() { return Literal(); }
   static Literal Int128(__int128 v) {
     Literal l;
@@ -62,9 +63,15 @@ struct Literal {
     return l;
   }
   static Literal String(const std::string& s) {
-    if (s.size() > 15) throw std::invalid_argument("string literals longer than 15 bytes do not cross this boundary");
     Literal l;
     l.c.kind = LLKV_LIT_STRING;
+    if (s.size() > 15) {  // by reference: the library copies the bytes in the call that receives the literal
+      l.long_string = std::make_shared<std::string>(s);
+      l.c.lo = (uint64_t)(uintptr_t)l.long_string->data();
+      l.c.hi = l.long_string->size();
+      l.c.precision = LLKV_LIT_STRING_BY_REF;
+      return l;
+    }
     unsigned char b[16] = {0};
     std::memcpy(b, s.data(), s.size());
     std::memcpy(&l.c.lo, b, 8);

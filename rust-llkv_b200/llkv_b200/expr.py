@@ -71,11 +71,14 @@ class Literal:
             out.lo = self.value & 0xFFFFFFFFFFFFFFFF
         elif self.kind == ffi.LIT_STRING:
             b = self.value.encode("utf-8")
-            if len(b) > 15:
-                raise ValueError("string literals longer than 15 bytes do not cross this boundary")
-            padded = b + b"\0" * (16 - len(b))
-            out.lo, out.hi = struct.unpack("<QQ", padded)
-            out.precision = len(b)
+            if len(b) > 15:  # by reference (LLKV_LIT_STRING_BY_REF): the receiving call copies the bytes
+                import ctypes
+                out._bytes = ctypes.create_string_buffer(b, len(b))  # kept alive by this struct
+                out.lo, out.hi, out.precision = ctypes.addressof(out._bytes), len(b), 255
+            else:
+                padded = b + b"\0" * (16 - len(b))
+                out.lo, out.hi = struct.unpack("<QQ", padded)
+                out.precision = len(b)
         return out
 
 
@@ -564,10 +567,13 @@ class AggregateValue:
         return AggregateValue(v.type, int(val))
 
 
-def decode_group_key(k: ffi.GroupKey):
-    """GroupKeyValue (llkv-executor/src/lib.rs:99-106)."""
+def decode_group_key(k: ffi.GroupKey, resolve=None):
+    """GroupKeyValue (llkv-executor/src/lib.rs:99-106).  `resolve(dict_kind, bits)` turns a dictionary-coded string key
+    (llkv_group_key.dict != 0) into its string."""
     if not k.valid:
         return None
+    if k.type == ffi.PT_UTF8 and k.dict:
+        return resolve(int(k.dict), int(k.bits))
     if k.type == ffi.PT_UTF8:
         n = k.bits & 0xFF
         return bytes((k.bits >> (56 - 8 * i)) & 0xFF for i in range(n)).decode("utf-8")

@@ -75,7 +75,8 @@ class AggValue(C.Structure):
 
 
 class GroupKey(C.Structure):
-    _fields_ = [("bits", C.c_uint64), ("type", C.c_int32), ("valid", C.c_uint8), ("_pad", C.c_uint8 * 3)]
+    _fields_ = [("bits", C.c_uint64), ("type", C.c_int32), ("valid", C.c_uint8), ("dict", C.c_uint8),
+                ("_pad", C.c_uint8 * 2)]
 
 
 class RunInfo(C.Structure):

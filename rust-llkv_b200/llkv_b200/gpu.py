@@ -75,6 +75,8 @@ def load():
         "llkv_gpu_column_flush": (i32, [vp]),
         "llkv_gpu_column_delete_rows": (i32, [vp, vp, u64]),
         "llkv_gpu_column_present_rows": (i32, [vp, P(u64)]),
+        "llkv_gpu_column_dict_size": (i32, [vp, P(u64)]),
+        "llkv_gpu_column_dict_entry": (i32, [vp, u64, P(vp), P(u64)]),
         "llkv_gpu_column_build_sort_index": (i32, [vp, u64]),
         "llkv_gpu_column_sort_index_blob": (i32, [vp, u64, vp, u64, P(u64)]),
         "llkv_gpu_column_gather": (i32, [vp, vp, u64, vp, u64, vp]),
@@ -351,6 +353,18 @@ class DeviceColumn:
         _check(self.lib.llkv_gpu_column_sort_index_blob(self.handle, chunk_index, buf, n.value, C.byref(n)))
         return bytes(buf)
 
+    def dict_size(self) -> int:
+        """Distinct strings of a Utf8 column that holds strings longer than 7 bytes (0: the column is not dictionary-coded)."""
+        n = C.c_uint64()
+        _check(self.lib.llkv_gpu_column_dict_size(self.handle, C.byref(n)))
+        return n.value
+
+    def dict_entry(self, code: int) -> str:
+        ptr = C.c_void_p()
+        n = C.c_uint64()
+        _check(self.lib.llkv_gpu_column_dict_entry(self.handle, code, C.byref(ptr), C.byref(n)))
+        return C.string_at(ptr, n.value).decode("utf-8") if n.value else ""
+
     def present_rows(self) -> int:
         n = C.c_uint64()
         _check(self.lib.llkv_gpu_column_present_rows(self.handle, C.byref(n)))
@@ -422,6 +436,7 @@ class Aggregation:
         self.lib = table.ctx.lib
         self.n_aggs = len(specs)
         self.n_keys = len(group_by)
+        self.group_by = tuple(group_by)
         if expr_mode is None:
             expr_mode = ffi.EXPR_EXACT if group_by else ffi.EXPR_ARROW
         aggs, n_aggs, nodes, n_nodes = flatten_aggregates(specs)
@@ -483,7 +498,7 @@ class Aggregation:
         return vals, keys, int(n.value)
 
     AGG_VALUE_DTYPE = np.dtype([("lo", "<u8"), ("hi", "<u8"), ("type", "<i4"), ("precision", "u1"), ("scale", "i1"), ("valid", "u1"), ("_pad", "u1")])
-    GROUP_KEY_DTYPE = np.dtype([("bits", "<u8"), ("type", "<i4"), ("valid", "u1"), ("_pad", "u1", (3,))])
+    GROUP_KEY_DTYPE = np.dtype([("bits", "<u8"), ("type", "<i4"), ("valid", "u1"), ("dict", "u1"), ("_pad", "u1", (2,))])
 
     def finalize_numpy(self, group_capacity: int):
         """The finalized cells as numpy structured arrays [groups, aggregates] / [groups, keys] (for results with millions of
@@ -496,7 +511,8 @@ class Aggregation:
     def decode(self, vals, keys, n):
         rows = []
         for g in range(n):
-            key = tuple(decode_group_key(keys[g * self.n_keys + k]) for k in range(self.n_keys))
+            key = tuple(decode_group_key(keys[g * self.n_keys + k], lambda kind, code, k=k: self.table.columns[self.group_by[k]].dict_entry(code))
+                        for k in range(self.n_keys))
             rows.append((key, [AggregateValue.from_c(vals[g * self.n_aggs + a]) for a in range(self.n_aggs)]))
         return rows
 

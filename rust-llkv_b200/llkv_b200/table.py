@@ -102,6 +102,9 @@ class HostColumn:
             col.validity = pack_validity(valid)
         return col
 
+    def string_at(self, row: int) -> str:
+        return bytes(self.aux[self.values[row]:self.values[row + 1]]).decode("utf-8")
+
     def serialize(self) -> bytes:
         """serialize_array for primitive layouts (llkv-column-map/src/serialization.rs:264-307): 24-byte header + values."""
         t = self.dtype.type
