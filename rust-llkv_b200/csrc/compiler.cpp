@@ -1386,7 +1386,14 @@ class Emitter {
       out_.keys[0].bits = 64;
       out_.keys[0].min = 0;
     } else if (total > 64) {
-      fail(LLKV_ERR_INVALID_ARGUMENT, "GROUP BY key of %d bits does not fit the 64-bit packed key of this path", total);
+      // wider than one word: group by a 64-bit hash of the keys' images; the runtime verifies it and reads the key values
+      // back from the columns (plan.h: single_wide_key == 2)
+      p.single_wide_key = 2;
+      for (KeyLayout& kl : out_.keys) {
+        kl.kind = KK_INT;
+        kl.bits = 64;
+        kl.min = 0;
+      }
     }
     for (int k = 0; k < nk; ++k) {
       p.key_bits[k] = out_.keys[k].bits;

@@ -123,11 +123,12 @@ static __device__ __noinline__ u64 lean_row_key(const LeanPlan& p, const LeanSha
     } else {
       f = (u64)v - p.key_min[k];
     }
-    if (S.single_wide_key) K = (u64)v;
+    if (S.single_wide_key == 2) K = key_hash_step(k == 0 ? key_hash_init() : K, (u64)v, false);
+    else if (S.single_wide_key) K = (u64)v;
     else K |= (bits == 64 ? f : (f & ((1ull << bits) - 1))) << shift;
     shift += bits;
   }
-  return K;
+  return S.single_wide_key == 2 ? key_hash_done(K) : K;
 }
 
 __device__ __forceinline__ void mbar_wait_parked(void* bar, uint32_t parity) {
@@ -319,11 +320,16 @@ struct LeanTile {
 #pragma unroll
         for (int r = 0; r < R; ++r) {
           const u64 f = is_str ? ((L ? (((u64)v[r] >> (64 - 8 * L)) << 3) : 0ull) | ((u64)v[r] & 7ull)) : (u64)v[r] - kmin;
-          if (S.single_wide_key) keys[r] = (u64)v[r];
+          if (S.single_wide_key == 2) keys[r] = key_hash_step(k == 0 ? key_hash_init() : keys[r], (u64)v[r], false);
+          else if (S.single_wide_key) keys[r] = (u64)v[r];
           else keys[r] |= (f & mask) << shift;
         }
         shift += bits;
       }
+    }
+    if (S.single_wide_key == 2) {
+#pragma unroll
+      for (int r = 0; r < R; ++r) keys[r] = key_hash_done(keys[r]);
     }
   }
 

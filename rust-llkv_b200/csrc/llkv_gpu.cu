@@ -293,6 +293,86 @@ __global__ void popcount_bits_kernel(const unsigned int* __restrict__ bits, u64 
   if ((threadIdx.x & 31) == 0 && c) atomicAdd(out, c);
 }
 
+// Wide GROUP BY keys (Plan::single_wide_key == 2): groups are keyed by a 64-bit hash of the keys' images.  After a run the
+// verification pass recomputes every row's hash, finds its group and compares the row's key fields with those of the
+// group's first row: two different keys in one group raise FLAG_KEY_COLLISION (the run is then an error, never a wrong
+// answer).  The gather pass reads the key fields of each group's first row: that is where the key values come from.
+struct WideKeyCols {
+  const void* values[kMaxKeys];
+  const unsigned int* validity[kMaxKeys];
+  uint32_t load_kind[kMaxKeys];
+  uint32_t n_keys;
+};
+__device__ __forceinline__ u64 wide_key_image(const WideKeyCols& c, int k, u64 pos, bool* isnull) {
+  const unsigned int* v = c.validity[k];
+  *isnull = v && !((v[pos >> 5] >> (pos & 31)) & 1u);
+  const void* b = c.values[k];
+  switch (c.load_kind[k]) {  // the image the scan kernels hash: (u64)(i64) of the value as they load it
+    case LK_I8: return (u64)(i64) static_cast<const signed char*>(b)[pos];
+    case LK_I16: return (u64)(i64) static_cast<const short*>(b)[pos];
+    case LK_I32: case LK_D32: return (u64)(i64) static_cast<const int*>(b)[pos];
+    case LK_U8: return (u64) static_cast<const unsigned char*>(b)[pos];
+    case LK_U16: return (u64) static_cast<const unsigned short*>(b)[pos];
+    case LK_U32: return (u64) static_cast<const unsigned int*>(b)[pos];
+    case LK_STR8: return ((u64) static_cast<const unsigned char*>(b)[pos] << 56) | 1ull;
+    default: return static_cast<const u64*>(b)[pos];
+  }
+}
+__device__ __forceinline__ u64 wide_key_mix(u64 x) {  // = mix64 of device_util.cuh (the table's home-slot hash)
+  x ^= x >> 33;
+  x *= 0xff51afd7ed558ccdULL;
+  x ^= x >> 33;
+  x *= 0xc4ceb9fe1a85ec53ULL;
+  x ^= x >> 33;
+  return x;
+}
+__global__ void wide_key_verify_kernel(WideKeyCols c, u64 n_rows, u64 origin, const u64* __restrict__ gkeys, const u64* __restrict__ gwords, u64 gcap,
+                                       uint32_t n_gwords, unsigned int* flag) {
+  for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n_rows; i += (u64)gridDim.x * blockDim.x) {
+    u64 img[kMaxKeys];
+    bool nul[kMaxKeys];
+    u64 K = key_hash_init();
+    for (uint32_t k = 0; k < c.n_keys; ++k) {
+      img[k] = wide_key_image(c, (int)k, i, &nul[k]);
+      K = key_hash_step(K, img[k], nul[k]);
+    }
+    K = key_hash_done(K);
+    const u64 mask = gcap - 1;
+    u64 h = wide_key_mix(K) & mask;
+    for (u64 probe = 0; probe <= mask; ++probe) {
+      const u64 cur = gkeys[h];
+      if (cur == kEmptyKey) break;  // no group has this hash: the row was not selected
+      if (cur == K) {
+        const u64 first = gwords[h * n_gwords + 1] - origin;  // (word 1: the group's first row id)
+        if (first < n_rows && first != i) {
+          bool same = true;
+          for (uint32_t k = 0; k < c.n_keys; ++k) {
+            bool fn;
+            const u64 fi = wide_key_image(c, (int)k, first, &fn);
+            same = same && fn == nul[k] && (fn || fi == img[k]);
+          }
+          if (!same) atomicOr(flag, 1u);
+        }
+        break;
+      }
+      h = (h + 1) & mask;
+    }
+  }
+}
+__global__ void wide_key_gather_kernel(WideKeyCols c, const u64* __restrict__ first_pos, u64 n_groups, u64 n_rows, u64* __restrict__ out_bits,
+                                       unsigned char* __restrict__ out_null) {
+  for (u64 g = (u64)blockIdx.x * blockDim.x + threadIdx.x; g < n_groups; g += (u64)gridDim.x * blockDim.x) {
+    const u64 pos = first_pos[g];
+    for (uint32_t k = 0; k < c.n_keys; ++k) {
+      bool n = true;
+      u64 v = 0;
+      if (pos < n_rows) v = wide_key_image(c, (int)k, pos, &n);
+      out_bits[g * c.n_keys + k] = n ? 0 : v;
+      out_null[g * c.n_keys + k] = n ? 1 : 0;
+    }
+  }
+}
+
 // Sort index (SortIndexOps::stage_build_for_chunk, llkv-column-map/src/store/indexing/sort.rs:150-172): for every chunk the
 // permutation that lists its rows in ascending value order (lexsort_to_indices).  One CTA sorts one chunk: a stable LSD radix
 // sort over 4-bit digits of the order-preserving 64-bit image of the values, (key, index) pairs ping-ponging between two
@@ -626,6 +706,7 @@ struct PendingRun {
 struct llkv_gpu_agg {
   llkv_gpu_ctx* ctx = nullptr;
   StringStore strings;
+  uint64_t runs_done = 0, wide_verified = ~0ull;  // hashed wide keys: the run the verification pass last covered
   uint64_t table_id = 0;
   std::vector<llkv_agg_spec> specs;
   std::vector<llkv_scalar_node> nodes;
@@ -3955,6 +4036,7 @@ static int32_t agg_run_impl(llkv_gpu_agg* a, const llkv_gpu_program* prog, int32
   if (rc) return rc;
   a->pending.wide = a->cr.wide;
   a->pending.active = true;
+  ++a->runs_done;
   return LLKV_OK;
 }
 
@@ -4124,7 +4206,7 @@ static void decode_keys(const llkv_gpu_agg* a, u64 K, bool null_slot, llkv_group
     llkv_group_key* o = &out[k];
     memset(o, 0, sizeof(*o));
     o->type = kl.type;
-    if (p.single_wide_key) {
+    if (p.single_wide_key == 1) {
       o->valid = null_slot ? 0 : 1;
       o->bits = null_slot ? 0 : K;
       if (kl.type == LLKV_PT_BOOLEAN && o->valid) o->bits = o->bits != 0;
@@ -4157,6 +4239,84 @@ static void decode_keys(const llkv_gpu_agg* a, u64 K, bool null_slot, llkv_group
 struct GroupRef {
   u64 slot, first_row;
 };
+
+static bool wide_key_cols(const llkv_gpu_agg* a, WideKeyCols* out, u64* n_rows, u64* origin) {
+  memset(out, 0, sizeof(*out));
+  const std::vector<KeyLayout>& keys = a->cr.keys;
+  out->n_keys = (uint32_t)keys.size();
+  *n_rows = ~0ull;
+  *origin = 0;
+  for (size_t k = 0; k < keys.size(); ++k) {
+    llkv_gpu_column* col = nullptr;
+    for (auto& kv : a->ctx->columns)
+      if (lfid_table(kv.second->lfid) == (a->table_id & 0xffffull) && lfid_field(kv.second->lfid) == keys[k].field_id) col = kv.second;
+    if (!col) return false;
+    out->values[k] = col->values;
+    out->validity[k] = col->validity;
+    out->load_kind[k] = col->load_kind;
+    *n_rows = std::min<u64>(*n_rows, col->n_rows);
+    if (col->has_origin) *origin = col->row_id_origin;
+  }
+  return true;
+}
+
+// Hashed wide keys: proves once per run that no two different keys share a group, then reads every group's key values
+// from the columns at the group's first row.
+static int32_t wide_keys_fetch(llkv_gpu_agg* a, const std::vector<GroupRef>& groups, std::vector<llkv_group_key>& out) {
+  llkv_gpu_ctx* ctx = a->ctx;
+  const std::vector<KeyLayout>& keys = a->cr.keys;
+  const size_t nk = keys.size(), ng = groups.size();
+  out.assign(ng * nk, llkv_group_key());
+  if (ng == 0) return LLKV_OK;
+  WideKeyCols cols;
+  u64 n_rows, origin;
+  if (!wide_key_cols(a, &cols, &n_rows, &origin)) return set_error(LLKV_ERR_INTERNAL, "a GROUP BY key column is gone");
+  cudaStream_t s = ctx->stream;
+  if (a->wide_verified != a->runs_done) {
+    unsigned int* d_flag = nullptr;
+    CUDA_TRY(cudaMalloc((void**)&d_flag, 4));
+    CUDA_TRY(cudaMemsetAsync(d_flag, 0, 4, s));
+    wide_key_verify_kernel<<<1184, 256, 0, s>>>(cols, n_rows, origin, a->gkeys, a->gwords, a->gcap, a->n_gwords, d_flag);
+    CUDA_TRY(cudaGetLastError());
+    unsigned int flag = 0;
+    CUDA_TRY(cudaMemcpyAsync(&flag, d_flag, 4, cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaStreamSynchronize(s));
+    CUDA_TRY(cudaFree(d_flag));
+    if (flag) return agg_fail(a, LLKV_ERR_INTERNAL, "two different GROUP BY keys share a 64-bit hash (FLAG_KEY_COLLISION): this query cannot run on this path");
+    a->wide_verified = a->runs_done;
+  }
+  std::vector<u64> pos(ng);
+  for (size_t g = 0; g < ng; ++g) pos[g] = groups[g].first_row - origin;
+  u64 *d_pos = nullptr, *d_bits = nullptr;
+  unsigned char* d_null = nullptr;
+  CUDA_TRY(cudaMalloc((void**)&d_pos, ng * 8));
+  cudaError_t e = cudaMalloc((void**)&d_bits, ng * nk * 8);
+  if (e == cudaSuccess) e = cudaMalloc((void**)&d_null, ng * nk);
+  std::vector<u64> bits(ng * nk);
+  std::vector<unsigned char> nul(ng * nk);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(d_pos, pos.data(), ng * 8, cudaMemcpyHostToDevice, s);
+  if (e == cudaSuccess) {
+    wide_key_gather_kernel<<<(unsigned)std::min<u64>((ng + 255) / 256, 1184), 256, 0, s>>>(cols, d_pos, ng, n_rows, d_bits, d_null);
+    e = cudaGetLastError();
+  }
+  if (e == cudaSuccess) e = cudaMemcpyAsync(bits.data(), d_bits, ng * nk * 8, cudaMemcpyDeviceToHost, s);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(nul.data(), d_null, ng * nk, cudaMemcpyDeviceToHost, s);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+  cudaFree(d_pos);
+  if (d_bits) cudaFree(d_bits);
+  if (d_null) cudaFree(d_null);
+  if (e != cudaSuccess) return set_error(LLKV_ERR_IO, "CUDA error %s reading GROUP BY keys", cudaGetErrorString(e));
+  for (size_t g = 0; g < ng; ++g)
+    for (size_t k = 0; k < nk; ++k) {
+      llkv_group_key* o = &out[g * nk + k];
+      o->type = keys[k].type;
+      o->valid = nul[g * nk + k] ? 0 : 1;
+      if (!o->valid) continue;
+      o->dict = keys[k].dict ? 1 : 0;
+      o->bits = keys[k].type == LLKV_PT_BOOLEAN ? (u64)(bits[g * nk + k] != 0) : bits[g * nk + k];
+    }
+  return LLKV_OK;
+}
 
 static int32_t agg_collect(llkv_gpu_agg* a, std::vector<u64>& hk, std::vector<u64>& hw, std::vector<GroupRef>& groups) {
   llkv_gpu_ctx* ctx = a->ctx;
@@ -4381,6 +4541,9 @@ extern "C" int32_t llkv_gpu_agg_finalize(llkv_gpu_agg* a, llkv_agg_value* out_va
   if ((rc = agg_collect(a, hk, hw, groups))) return rc;
   const size_t n_aggs = a->specs.size(), n_keys = a->keys.size();
   const bool shaped = !a->having.empty() || !a->order.empty() || a->out_offset || a->out_limit;
+  const bool hashed = n_keys && a->cr.plan.single_wide_key == 2;
+  std::vector<llkv_group_key> wide;
+  if (hashed && (rc = wide_keys_fetch(a, groups, wide))) return rc;
   if (!shaped) {
     if (groups.size() > group_capacity)
       return set_error(LLKV_ERR_INVALID_ARGUMENT, "group capacity %llu < %llu groups", (unsigned long long)group_capacity, (unsigned long long)groups.size());
@@ -4388,7 +4551,9 @@ extern "C" int32_t llkv_gpu_agg_finalize(llkv_gpu_agg* a, llkv_agg_value* out_va
     for (size_t gi = 0; gi < groups.size(); ++gi) {
       const u64 s = groups[gi].slot;
       if ((rc = finalize_group(a, &hw[s * a->n_gwords], out_values + gi * n_aggs))) return rc;
-      if (n_keys) {
+      if (hashed) {
+        memcpy(out_keys + gi * n_keys, wide.data() + gi * n_keys, n_keys * sizeof(llkv_group_key));
+      } else if (n_keys) {
         const bool null_slot = s == a->gcap + 1;
         const u64 K = s < a->gcap ? hk[s] : kEmptyKey;
         decode_keys(a, K, null_slot, out_keys + gi * n_keys);
@@ -4403,7 +4568,8 @@ extern "C" int32_t llkv_gpu_agg_finalize(llkv_gpu_agg* a, llkv_agg_value* out_va
   for (size_t gi = 0; gi < groups.size(); ++gi) {
     const u64 s = groups[gi].slot;
     if ((rc = finalize_group(a, &hw[s * a->n_gwords], vals.data() + gi * n_aggs))) return rc;
-    if (n_keys) decode_keys(a, s < a->gcap ? hk[s] : kEmptyKey, s == a->gcap + 1, keys.data() + gi * n_keys);
+    if (hashed) memcpy(keys.data() + gi * n_keys, wide.data() + gi * n_keys, n_keys * sizeof(llkv_group_key));
+    else if (n_keys) decode_keys(a, s < a->gcap ? hk[s] : kEmptyKey, s == a->gcap + 1, keys.data() + gi * n_keys);
   }
   std::vector<size_t> rows;
   for (size_t gi = 0; gi < groups.size(); ++gi) {
@@ -4592,6 +4758,8 @@ static int32_t agg_merge_impl(llkv_gpu_agg* a) {
   if (ctx->n_ranks > 1)
     for (const KeyLayout& kl : a->cr.keys)
       if (kl.dict) return set_error(LLKV_ERR_INVALID_ARGUMENT, "GROUP BY keys of a dictionary-coded (long string) column do not merge across GPUs: every rank has its own dictionary");
+  if (ctx->n_ranks > 1 && a->cr.plan.single_wide_key == 2)
+    return set_error(LLKV_ERR_INVALID_ARGUMENT, "GROUP BY keys wider than 64 bits do not merge across GPUs: a group's key values are read from the shard that holds its first row");
   int32_t rc;
   if (!a->pending.active && (rc = agg_apply_reset(a))) return rc;
   a->prefetched = false;  // the merge rewrites the table

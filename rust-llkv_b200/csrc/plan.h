@@ -125,6 +125,16 @@ enum FastOp : uint16_t {
 #else
 #define LLKV_HD
 #endif
+// Hash of a wide GROUP BY key (single_wide_key == 2): chained over the keys in order, NULL keys by a constant
+LLKV_HD constexpr unsigned long long key_hash_init() { return 0x243F6A8885A308D3ull; }
+LLKV_HD constexpr unsigned long long key_hash_step(unsigned long long h, unsigned long long field, bool isnull) {
+  h = (h ^ (isnull ? 0xD6E8FEB86659FD93ull : field)) * 0x9E3779B97F4A7C15ull;
+  h ^= h >> 29;
+  h *= 0xBF58476D1CE4E5B9ull;
+  h ^= h >> 32;
+  return h;
+}
+LLKV_HD constexpr unsigned long long key_hash_done(unsigned long long h) { return h == ~0ull ? 1ull : h; }  // (~0 = the table's empty marker)
 // aggregates whose update needs the row's operand value (the others need the row id or nothing)
 LLKV_HD constexpr bool lean_takes_operand(uint32_t op) {
   return op == FO_SUM || op == FO_FSUM || op == FO_MIN_I || op == FO_MAX_I || op == FO_MIN_F || op == FO_MAX_F;
@@ -210,6 +220,9 @@ struct Plan {
   // ---- group keys: each key value is reduced to key_bits[k] bits (+1 null bit when key_nullable) and packed
   uint32_t n_keys;
   uint32_t single_wide_key;       // 1: one 64-bit key, K = value, NULL key -> dedicated slot
+                                  // 2: keys that do not pack into 64 bits: K = key_hash_* over the keys' 64-bit images and
+                                  // NULL flags; the values come back from the columns at the group's first row and a
+                                  // verification pass proves that no two different keys met in one K (FLAG_KEY_COLLISION)
   uint8_t key_bits[kMaxKeys];
   uint8_t key_nullable[kMaxKeys];
   uint8_t key_kind[kMaxKeys];     // KeyKind
@@ -381,7 +394,8 @@ enum : uint32_t {
   FLAG_MERGE_TIMEOUT = 1u << 7,    // multi-GPU merge: a peer's partial state never arrived
   FLAG_MERGE_OVERSIZE = 1u << 8,   // multi-GPU merge over peer mailboxes: some rank's group table outgrew a mailbox slot
   FLAG_MERGE_RETRY = 1u << 9,      // ... some rank's scan has to be repeated first (64-bit overflow, table full): every rank merges again
-  FLAG_MERGE_PEER_FAILED = 1u << 10 // ... some rank's scan ended with an error: no merged result on any rank
+  FLAG_MERGE_PEER_FAILED = 1u << 10, // ... some rank's scan ended with an error: no merged result on any rank
+  FLAG_KEY_COLLISION = 1u << 11     // hashed wide GROUP BY keys: two different keys share a 64-bit hash
 };
 
 }  // namespace llkv

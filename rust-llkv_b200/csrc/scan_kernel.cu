@@ -675,9 +675,18 @@ __global__ void __launch_bounds__(512) scan_kernel(const Plan* __restrict__ gpla
           for (int r = 0; r < R; ++r) {
             u64 K = 0;
             bool knull = false;
-            if (p.single_wide_key) {
+            if (p.single_wide_key == 1) {
               K = (u64)(i64)t0[r];
               knull = is_null(r, sp - 1);
+            } else if (p.single_wide_key == 2) {
+              K = key_hash_init();
+              for (int k = 0; k < nk; ++k) {
+                const int pos = sp - nk + k;
+                const int d = sp - 1 - pos;
+                const u64 v = (u64)(i64)(d == 0 ? t0[r] : d == 1 ? t1[r] : *spill_ptr(pos, r));
+                K = key_hash_step(K, v, is_null(r, pos));
+              }
+              K = key_hash_done(K);
             } else {
               int shift = 0;
               for (int k = 0; k < nk; ++k) {
