@@ -66,7 +66,8 @@ enum {
   LLKV_PT_UINT16 = 9,
   LLKV_PT_UINT8 = 10,
   LLKV_PT_FLOAT64 = 11,
-  LLKV_PT_UTF8 = 12,     /* short strings only (<= 7 bytes), used as GROUP BY keys / equality predicates */
+  LLKV_PT_UTF8 = 12,     /* typed predicates and GROUP BY keys; <= 7 bytes as packed keys, longer ones dictionary-coded
+                            (see "Utf8 columns" below) */
   LLKV_PT_BOOLEAN = 15,  /* one byte per value at this boundary (0/1) */
   LLKV_PT_DATE32 = 16,
   LLKV_PT_DATE64 = 17,
@@ -485,6 +486,11 @@ int32_t llkv_gpu_filter_bitmap(llkv_gpu_ctx* ctx, uint64_t table_id, const llkv_
 /* ---- aggregates: AggregateAccumulator::{new_with_projection_index,update,finalize}
  *      (llkv-aggregate/src/lib.rs:463,759,1488) fused with the scan that feeds them
  *      (llkv-executor/src/lib.rs:5357-5682 ungrouped, 4405-4542 + 5028-5355 GROUP BY). ---- */
+/* GROUP BY keys (group_key_value, llkv-executor/src/lib.rs:9362-9456: integers, Date32, Boolean, Utf8) are packed into
+ * one 64-bit word from the columns' value ranges when they fit.  Wider key tuples are grouped by a 64-bit hash of the key
+ * values: after the run a verification pass proves that no two different tuples share a group (otherwise
+ * LLKV_ERR_INTERNAL, never a wrong answer) and finalize reads each group's key values from the columns at the group's
+ * first row; such aggregates do not merge across GPUs (LLKV_ERR_INVALID_ARGUMENT). */
 int32_t llkv_gpu_agg_create(llkv_gpu_ctx* ctx, uint64_t table_id, const llkv_agg_spec* specs, int32_t n_aggs,
                             const llkv_scalar_node* nodes, int32_t n_nodes, const uint64_t* group_key_fields,
                             int32_t n_keys, int32_t expr_mode, uint64_t cardinality_hint, llkv_gpu_agg** out);
