@@ -107,6 +107,26 @@ pub struct llkv_group_key {
     pub _pad: [u8; 2],
 }
 
+/// `ScanOptions` (`llkv-column-map/src/store/scan/options.rs:13-37`) for `llkv_gpu_column_scan`.
+#[repr(C)]
+#[derive(Clone, Copy, Debug, Default)]
+pub struct llkv_scan_options {
+    pub sorted: i32,
+    pub reverse: i32,
+    pub with_row_ids: i32,
+    pub include_nulls: i32,
+    pub nulls_first: i32,
+    pub has_lower: i32,
+    pub lower_inclusive: i32,
+    pub has_upper: i32,
+    pub upper_inclusive: i32,
+    pub _pad: i32,
+    pub lower_bits: u64,
+    pub upper_bits: u64,
+    pub offset: u64,
+    pub limit: u64,
+}
+
 /// One column as `llkv_gpu_debug_plan` sees it: type and statistics, no data.
 #[repr(C)]
 #[derive(Clone, Copy, Default)]
@@ -254,6 +274,10 @@ extern "C" {
     /// `ColumnStore::delete_rows`: the rows become gaps of the resident image.
     pub fn llkv_gpu_column_delete_rows(col: *mut llkv_gpu_column, row_ids: *const u64, n: u64) -> i32;
     pub fn llkv_gpu_column_present_rows(col: *mut llkv_gpu_column, out_rows: *mut u64) -> i32;
+    /// `ColumnStore::scan(field, ScanOptions, visitor)`: sorted on the device, paginated, with null runs.
+    pub fn llkv_gpu_column_scan(col: *mut llkv_gpu_column, anchor: *mut llkv_gpu_column, options: *const llkv_scan_options, chunk_rows: u64,
+                                visit: Option<unsafe extern "C" fn(user: *mut c_void, prim_type: i32, values: *const c_void, row_ids: *const u64, n_rows: u64) -> i32>,
+                                user: *mut c_void) -> i32;
     /// Entries of the dictionary of a Utf8 column that holds strings longer than 7 bytes (0: packed short strings).
     pub fn llkv_gpu_column_dict_size(col: *mut llkv_gpu_column, out_entries: *mut u64) -> i32;
     /// The string behind a `llkv_group_key` whose `dict` is 1.

@@ -458,6 +458,24 @@ int32_t llkv_gpu_column_read(llkv_gpu_column* col, uint64_t row_begin, uint64_t 
  * valid during the call.  A non-zero return from `visit` stops the scan and becomes the call's status. */
 typedef int32_t (*llkv_chunk_visitor)(void* user, int32_t prim_type, const void* values, const uint64_t* row_ids, uint64_t n_rows);
 int32_t llkv_gpu_column_visit(llkv_gpu_column* col, uint64_t chunk_rows, int32_t with_row_ids, llkv_chunk_visitor visit, void* user);
+/* ColumnStore::scan(field, ScanOptions, visitor) with the options of llkv-column-map/src/store/scan/options.rs:13-37:
+ * unsorted (append order) or sorted by value (ascending, or descending with `reverse`; floats in total order; equal values
+ * in row order), paginated by offset / limit across chunks (PaginateVisitor; limit 0 = unbounded), restricted to a value
+ * range (`ranges`; bounds are the values' bits in the column's type, signed ones sign-extended), and — sorted scans with
+ * row ids only — with the rows of `anchor` that the column does not hold as null runs (`visit` is then called with
+ * values = NULL and the row ids: PrimitiveSortedWithRowIdsVisitor::null_run), before or after the values (nulls_first),
+ * ascending by row id (descending for reverse scans).  The sort runs on the device (a whole-column stable radix sort: the
+ * reference merges its per-chunk value_order_perm runs on the CPU, scan/sorted.rs); pages are gathered and handed to
+ * `visit` chunk by chunk in the Arrow layout.  Utf8 and wide Decimal128 columns are LLKV_ERR_INVALID_ARGUMENT. */
+typedef struct llkv_scan_options {
+  int32_t sorted, reverse, with_row_ids, include_nulls, nulls_first;
+  int32_t has_lower, lower_inclusive, has_upper, upper_inclusive;
+  int32_t _pad;
+  uint64_t lower_bits, upper_bits;
+  uint64_t offset, limit;
+} llkv_scan_options;
+int32_t llkv_gpu_column_scan(llkv_gpu_column* col, llkv_gpu_column* anchor, const llkv_scan_options* options, uint64_t chunk_rows,
+                             llkv_chunk_visitor visit, void* user);
 /* Drops the rows but keeps the device allocation (re-upload the next batch into the same buffer). */
 int32_t llkv_gpu_column_clear(llkv_gpu_column* col);
 int32_t llkv_gpu_column_destroy(llkv_gpu_column* col);

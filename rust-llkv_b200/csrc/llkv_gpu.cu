@@ -473,6 +473,97 @@ __global__ void __launch_bounds__(kSortThreads) chunk_sort_kernel(const T* __res
   for (unsigned int i = t; i < m; i += kSortThreads) perm[base + i] = ia[i];
 }
 
+// Whole-column sort for sorted scans (ColumnStore::scan with ScanOptions::sorted, llkv-column-map/src/store/scan/sorted.rs:
+// the reference merges its per-chunk value_order_perm runs on the CPU).  A stable LSD radix sort over 4-bit digits of the
+// order-preserving key image across the whole grid: every thread of every CTA owns one contiguous segment, counts its
+// digits (gsort_count), one CTA scans the [digit][segment] counters (gsort_scan), every thread scatters its segment in
+// order (gsort_scatter) — equal keys keep row order.  Pass "-1" partitions by a flag instead of a digit: rows the column
+// does not hold or that fall outside the requested value range go behind the others, which the digit passes then ignore.
+constexpr unsigned kGsortThreads = 512;
+__device__ __forceinline__ u64 gs_min(u64 a, u64 b) { return a < b ? a : b; }
+template <typename T, int KIND>
+__global__ void gsort_init_kernel(const T* __restrict__ v, const unsigned int* __restrict__ validity, u64 n, u64 lo, u64 hi, u64* __restrict__ key,
+                                  unsigned int* __restrict__ idx, unsigned char* __restrict__ flag, u64* red) {
+  u64 a = ~0ull, o = 0;
+  for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (u64)gridDim.x * blockDim.x) {
+    const u64 k = sort_key_of<T, KIND>(v[i]);
+    const bool keep = (!validity || ((validity[i >> 5] >> (i & 31)) & 1u)) && k >= lo && k <= hi;
+    key[i] = k;
+    idx[i] = (unsigned int)i;
+    flag[i] = keep ? 0 : 1;
+    if (keep) {
+      a &= k;
+      o |= k;
+    }
+  }
+  for (int w = 16; w; w >>= 1) {
+    a &= __shfl_xor_sync(0xffffffffu, a, w);
+    o |= __shfl_xor_sync(0xffffffffu, o, w);
+  }
+  if ((threadIdx.x & 31) == 0) {
+    atomicAnd((unsigned long long*)&red[0], (unsigned long long)a);
+    atomicOr((unsigned long long*)&red[1], (unsigned long long)o);
+  }
+}
+__device__ __forceinline__ unsigned gsort_digit(const u64* key, const unsigned char* flag, u64 i, int shift) {
+  return shift < 0 ? (unsigned)flag[i] : (unsigned)(key[i] >> shift) & 15u;
+}
+__global__ void __launch_bounds__(kGsortThreads) gsort_count_kernel(const u64* __restrict__ key, const unsigned char* __restrict__ flag, u64 n, int shift,
+                                                                    unsigned int* __restrict__ counts, u64 seg, unsigned S) {
+  const unsigned g = blockIdx.x * kGsortThreads + threadIdx.x;
+  const u64 lo = gs_min((u64)g * seg, n), hi = gs_min(lo + seg, n);
+  unsigned c[16];
+#pragma unroll
+  for (int d = 0; d < 16; ++d) c[d] = 0;
+  for (u64 i = lo; i < hi; ++i) {
+    const unsigned d = gsort_digit(key, flag, i, shift);
+#pragma unroll
+    for (int q = 0; q < 16; ++q) c[q] += (d == (unsigned)q);
+  }
+#pragma unroll
+  for (int d = 0; d < 16; ++d) counts[(size_t)d * S + g] = c[d];
+}
+__global__ void __launch_bounds__(1024) gsort_scan_kernel(unsigned int* counts, u64 total) {  // one CTA: exclusive scan in place
+  __shared__ unsigned int part[1024];
+  const u64 per = (total + 1023) / 1024;
+  const u64 lo = gs_min((u64)threadIdx.x * per, total), hi = gs_min(lo + per, total);
+  unsigned int sum = 0;
+  for (u64 i = lo; i < hi; ++i) sum += counts[i];
+  part[threadIdx.x] = sum;
+  __syncthreads();
+  for (unsigned o = 1; o < 1024; o <<= 1) {
+    const unsigned int y = threadIdx.x >= o ? part[threadIdx.x - o] : 0;
+    __syncthreads();
+    part[threadIdx.x] += y;
+    __syncthreads();
+  }
+  unsigned int run = part[threadIdx.x] - sum;
+  for (u64 i = lo; i < hi; ++i) {
+    const unsigned int v = counts[i];
+    counts[i] = run;
+    run += v;
+  }
+}
+__global__ void __launch_bounds__(kGsortThreads) gsort_scatter_kernel(const u64* __restrict__ kin, const unsigned int* __restrict__ iin,
+                                                                      const unsigned char* __restrict__ flag, u64 n, int shift,
+                                                                      const unsigned int* __restrict__ counts, u64 seg, unsigned S, u64* __restrict__ kout,
+                                                                      unsigned int* __restrict__ iout) {
+  const unsigned g = blockIdx.x * kGsortThreads + threadIdx.x;
+  const u64 lo = gs_min((u64)g * seg, n), hi = gs_min(lo + seg, n);
+  unsigned c[16];
+#pragma unroll
+  for (int d = 0; d < 16; ++d) c[d] = counts[(size_t)d * S + g];
+  for (u64 i = lo; i < hi; ++i) {
+    const unsigned d = gsort_digit(kin, flag, i, shift);
+    unsigned dst = 0;
+#pragma unroll
+    for (int q = 0; q < 16; ++q)
+      if (d == (unsigned)q) dst = c[q]++;
+    kout[dst] = kin[i];
+    iout[dst] = iin[i];
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ handles
 struct MvccState {
   llkv_gpu_column* created_by = nullptr;
@@ -1930,6 +2021,205 @@ extern "C" int32_t llkv_gpu_column_visit(llkv_gpu_column* col, uint64_t chunk_ro
     if (vrc) return set_error(vrc, "the chunk visitor stopped the scan with status %d", vrc);
   }
   return LLKV_OK;
+}
+
+// ColumnStore::scan(field, ScanOptions, visitor) (llkv-column-map/src/store/scan/mod.rs:191-1080): unsorted or sorted,
+// forward or reverse, paginated, optionally with the rows the column does not hold as null runs.
+struct ScanEmit {
+  llkv_gpu_column* col;
+  llkv_chunk_visitor visit;
+  void* user;
+  uint64_t skip, left;  // pagination state across chunks (PaginateVisitor)
+  bool bounded, with_ids;
+  int32_t emit(const void* values, const uint64_t* ids, uint64_t n, uint64_t width) {
+    if (skip >= n) { skip -= n; return LLKV_OK; }
+    const uint64_t first = skip;
+    skip = 0;
+    uint64_t m = n - first;
+    if (bounded) {
+      if (left == 0) return LLKV_OK;
+      m = std::min(m, left);
+      left -= m;
+    }
+    const int32_t vrc = visit(user, col->type, values ? (const char*)values + first * width : nullptr, ids && (with_ids || !values) ? ids + first : nullptr, m);
+    return vrc ? set_error(vrc, "the visitor stopped the scan with status %d", vrc) : LLKV_OK;
+  }
+  bool done() const { return bounded && left == 0; }
+};
+
+extern "C" int32_t llkv_gpu_column_scan(llkv_gpu_column* col, llkv_gpu_column* anchor, const llkv_scan_options* o, uint64_t chunk_rows,
+                                         llkv_chunk_visitor visit, void* user) {
+  if (!col || !o || !visit) return set_error(LLKV_ERR_INVALID_ARGUMENT, "NULL argument");
+  if (col->type == LLKV_PT_UTF8 || col->load_kind == LK_D128) return set_error(LLKV_ERR_INVALID_ARGUMENT, "llkv_gpu_column_scan does not support this column type");
+  if (o->include_nulls && (!o->with_row_ids || !anchor)) return set_error(LLKV_ERR_INVALID_ARGUMENT, "include_nulls needs with_row_ids and an anchor column");
+  if (o->include_nulls && !o->sorted) return set_error(LLKV_ERR_INVALID_ARGUMENT, "null runs are emitted by sorted scans on this path");
+  llkv_gpu_ctx* c = col->ctx;
+  CTX_LOCK(c);
+  CUDA_TRY(cudaSetDevice(c->device));
+  int32_t rc;
+  if (!col->sealed && (rc = llkv_gpu_column_seal(col))) return rc;
+  if (anchor && !anchor->sealed && (rc = llkv_gpu_column_seal(anchor))) return rc;
+  const uint64_t width = (uint64_t)prim_type_width(col->type);
+  if (chunk_rows == 0) chunk_rows = width <= 8 ? (1ull << 20) / width : 4096;
+  ScanEmit em{col, visit, user, o->offset, o->limit, o->limit != 0, o->with_row_ids != 0};
+  const uint64_t n = col->n_rows, origin = col->row_id_origin;
+  if (n >= (1ull << 32)) return set_error(LLKV_ERR_INVALID_ARGUMENT, "llkv_gpu_column_scan handles columns of up to 2^32 positions");
+  if (!o->sorted) {  // append order; rows the column does not hold are skipped
+    std::vector<unsigned char> vals(chunk_rows * width), packed(chunk_rows * width);
+    std::vector<unsigned int> bits(chunk_rows / 32 + 2);
+    std::vector<uint64_t> ids(chunk_rows);
+    for (uint64_t lo = 0; lo < n && !em.done(); lo += chunk_rows) {
+      const uint64_t m = std::min<uint64_t>(chunk_rows, n - lo);
+      if ((rc = llkv_gpu_column_read(col, lo, m, vals.data(), vals.size()))) return rc;
+      uint64_t out_n = 0;
+      if (col->validity) CUDA_TRY(cudaMemcpy(bits.data(), col->validity + lo / 32, ((lo % 32 + m + 31) / 32) * 4, cudaMemcpyDeviceToHost));
+      for (uint64_t i = 0; i < m; ++i) {
+        const uint64_t b = lo % 32 + i;
+        if (col->validity && !((bits[b >> 5] >> (b & 31)) & 1u)) continue;
+        memcpy(packed.data() + out_n * width, vals.data() + i * width, width);
+        ids[out_n++] = origin + lo + i;
+      }
+      if (out_n && (rc = em.emit(packed.data(), ids.data(), out_n, width))) return rc;
+    }
+    return LLKV_OK;
+  }
+  // ---- sorted: the order-preserving key image of every row, a stable partition (held and in range first), LSD passes
+  u64 klo = 0, khi = ~0ull;
+  auto image = [&](uint64_t bits) -> u64 {  // bound given as the value's bits in the column's type
+    switch (col->load_kind) {
+      case LK_F32: case LK_F64: {
+        double d;
+        if (col->load_kind == LK_F32) { float f; uint32_t b = (uint32_t)bits; memcpy(&f, &b, 4); d = f; } else memcpy(&d, &bits, 8);
+        u64 b; memcpy(&b, &d, 8);
+        return (b >> 63) ? ~b : (b | 0x8000000000000000ull);
+      }
+      case LK_U8: case LK_U16: case LK_U32: case LK_U64: return bits;
+      default: return bits ^ 0x8000000000000000ull;  // signed (sign-extended by the caller)
+    }
+  };
+  if (o->has_lower) { klo = image(o->lower_bits); if (!o->lower_inclusive) { if (klo == ~0ull) return LLKV_OK; ++klo; } }
+  if (o->has_upper) { khi = image(o->upper_bits); if (!o->upper_inclusive) { if (khi == 0) return LLKV_OK; --khi; } }
+  uint64_t m = 0;
+  unsigned int* d_perm = nullptr;  // (points into the scratch below)
+  u64 *ka = nullptr, *kb = nullptr, *d_red = nullptr;
+  unsigned int *ia = nullptr, *ib = nullptr, *d_counts = nullptr;
+  unsigned char* d_flag = nullptr;
+  cudaStream_t s = c->stream;
+  const unsigned G = 148, S = G * kGsortThreads;
+  auto release = [&]() {
+    cudaFree(ka); cudaFree(kb); cudaFree(ia); cudaFree(ib); cudaFree(d_flag); cudaFree(d_counts); cudaFree(d_red);
+  };
+  if (n) {
+    cudaError_t e = cudaMalloc((void**)&ka, n * 8);
+    if (e == cudaSuccess) e = cudaMalloc((void**)&kb, n * 8);
+    if (e == cudaSuccess) e = cudaMalloc((void**)&ia, n * 4);
+    if (e == cudaSuccess) e = cudaMalloc((void**)&ib, n * 4);
+    if (e == cudaSuccess) e = cudaMalloc((void**)&d_flag, n);
+    if (e == cudaSuccess) e = cudaMalloc((void**)&d_counts, (size_t)16 * S * 4);
+    if (e == cudaSuccess) e = cudaMalloc((void**)&d_red, 16);
+    u64 red[2] = {~0ull, 0};
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_red, red, 16, cudaMemcpyHostToDevice, s);
+    if (e == cudaSuccess) {
+      const void* v = col->values;
+#define LLKV_GSORT_INIT(T, KIND) gsort_init_kernel<T, KIND><<<1184, 256, 0, s>>>((const T*)v, col->validity, n, klo, khi, ka, ia, d_flag, d_red)
+      switch (col->load_kind) {
+        case LK_I8: LLKV_GSORT_INIT(signed char, 0); break;
+        case LK_I16: LLKV_GSORT_INIT(short, 0); break;
+        case LK_I32: case LK_D32: LLKV_GSORT_INIT(int, 0); break;
+        case LK_I64: case LK_D64: LLKV_GSORT_INIT(i64, 0); break;
+        case LK_U8: LLKV_GSORT_INIT(unsigned char, 1); break;
+        case LK_U16: LLKV_GSORT_INIT(unsigned short, 1); break;
+        case LK_U32: LLKV_GSORT_INIT(unsigned int, 1); break;
+        case LK_U64: LLKV_GSORT_INIT(u64, 1); break;
+        case LK_F32: LLKV_GSORT_INIT(float, 2); break;
+        case LK_F64: LLKV_GSORT_INIT(double, 3); break;
+        default: e = cudaErrorInvalidValue; break;
+      }
+#undef LLKV_GSORT_INIT
+      if (e == cudaSuccess) e = cudaGetLastError();
+    }
+    auto pass = [&](int shift, u64 count) -> cudaError_t {
+      const u64 seg = (count + S - 1) / S;
+      gsort_count_kernel<<<G, kGsortThreads, 0, s>>>(ka, d_flag, count, shift, d_counts, seg, S);
+      gsort_scan_kernel<<<1, 1024, 0, s>>>(d_counts, (u64)16 * S);
+      gsort_scatter_kernel<<<G, kGsortThreads, 0, s>>>(ka, ia, d_flag, count, shift, d_counts, seg, S, kb, ib);
+      std::swap(ka, kb);
+      std::swap(ia, ib);
+      return cudaGetLastError();
+    };
+    m = n;
+    const bool filtered = col->validity || o->has_lower || o->has_upper;
+    if (e == cudaSuccess && filtered) {
+      e = pass(-1, n);
+      unsigned int kept = 0;  // exclusive offset of the first flagged row = rows kept
+      if (e == cudaSuccess) e = cudaMemcpyAsync(&kept, d_counts + S, 4, cudaMemcpyDeviceToHost, s);
+      if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+      m = kept;
+    }
+    if (e == cudaSuccess) e = cudaMemcpyAsync(red, d_red, 16, cudaMemcpyDeviceToHost, s);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+    const u64 varying = m ? (red[0] ^ red[1]) : 0;  // bits in which the kept keys differ: the other digits need no pass
+    for (int shift = 0; shift < 64 && e == cudaSuccess && m > 1; shift += 4)
+      if ((varying >> shift) & 15u) e = pass(shift, m);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+    if (e != cudaSuccess) {
+      release();
+      return set_error(LLKV_ERR_IO, "CUDA error %s sorting the column", cudaGetErrorString(e));
+    }
+    d_perm = ia;
+  }
+  // rows of the anchor that the column does not hold, ascending (descending for reverse scans)
+  std::vector<uint64_t> nulls;
+  if (o->include_nulls) {
+    const uint64_t an = anchor->n_rows;
+    std::vector<unsigned int> av((an + 31) / 32 + 1, 0xffffffffu), cv((n + 31) / 32 + 1, 0xffffffffu);
+    cudaError_t e = cudaSuccess;
+    if (anchor->validity && an) e = cudaMemcpy(av.data(), anchor->validity, ((an + 31) / 32) * 4, cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess && col->validity && n) e = cudaMemcpy(cv.data(), col->validity, ((n + 31) / 32) * 4, cudaMemcpyDeviceToHost);
+    if (e != cudaSuccess) { release(); return set_error(LLKV_ERR_IO, "CUDA error %s", cudaGetErrorString(e)); }
+    for (uint64_t i = 0; i < an; ++i) {
+      if (!((av[i >> 5] >> (i & 31)) & 1u)) continue;
+      const uint64_t rid = anchor->row_id_origin + i, pos = rid - origin;
+      const bool held = rid >= origin && pos < n && ((cv[pos >> 5] >> (pos & 31)) & 1u);
+      if (!held) nulls.push_back(rid);
+    }
+    if (o->reverse) std::reverse(nulls.begin(), nulls.end());
+  }
+  auto emit_nulls = [&]() -> int32_t {
+    for (uint64_t lo = 0; lo < nulls.size() && !em.done(); lo += chunk_rows) {
+      const int32_t r = em.emit(nullptr, nulls.data() + lo, std::min<uint64_t>(chunk_rows, nulls.size() - lo), 0);
+      if (r) return r;
+    }
+    return LLKV_OK;
+  };
+  auto emit_values = [&]() -> int32_t {
+    std::vector<unsigned int> perm(chunk_rows);
+    std::vector<uint64_t> ids(chunk_rows);
+    std::vector<unsigned char> vals(chunk_rows * width), valid(chunk_rows);
+    uint64_t at = 0;
+    if (em.skip >= m) { em.skip -= m; return LLKV_OK; }  // the page starts behind the values
+    at = em.skip;
+    em.skip = 0;
+    while (at < m && !em.done()) {
+      uint64_t k = std::min<uint64_t>(chunk_rows, m - at);
+      if (em.bounded) k = std::min(k, em.left);
+      const uint64_t src = o->reverse ? m - at - k : at;
+      CUDA_TRY(cudaMemcpy(perm.data(), d_perm + src, k * 4, cudaMemcpyDeviceToHost));
+      for (uint64_t i = 0; i < k; ++i) ids[i] = origin + perm[o->reverse ? k - 1 - i : i];
+      int32_t r = llkv_gpu_column_gather(col, ids.data(), k, vals.data(), vals.size(), valid.data());
+      if (r) return r;
+      if ((r = em.emit(vals.data(), ids.data(), k, width))) return r;
+      at += k;
+    }
+    return LLKV_OK;
+  };
+  rc = LLKV_OK;
+  if (o->include_nulls && o->nulls_first) rc = emit_nulls();
+  if (!rc && m) rc = emit_values();
+  else if (!rc && !m) { /* nothing held */ }
+  if (!rc && o->include_nulls && !o->nulls_first) rc = emit_nulls();
+  release();
+  return rc;
 }
 
 extern "C" int32_t llkv_gpu_column_dict_size(llkv_gpu_column* col, uint64_t* out_entries) {

@@ -79,6 +79,14 @@ class GroupKey(C.Structure):
                 ("_pad", C.c_uint8 * 2)]
 
 
+class ScanOptions(C.Structure):
+    """llkv_scan_options = ScanOptions (llkv-column-map/src/store/scan/options.rs:13-37)."""
+    _fields_ = [("sorted", C.c_int32), ("reverse", C.c_int32), ("with_row_ids", C.c_int32), ("include_nulls", C.c_int32),
+                ("nulls_first", C.c_int32), ("has_lower", C.c_int32), ("lower_inclusive", C.c_int32), ("has_upper", C.c_int32),
+                ("upper_inclusive", C.c_int32), ("_pad", C.c_int32), ("lower_bits", C.c_uint64), ("upper_bits", C.c_uint64),
+                ("offset", C.c_uint64), ("limit", C.c_uint64)]
+
+
 class RunInfo(C.Structure):
     _fields_ = [("rows", C.c_uint64), ("kernel_launches", C.c_uint32), ("used_wide_path", C.c_uint32),
                 ("algorithmic_bytes_per_row", C.c_uint32), ("physical_bytes_per_row", C.c_uint32),

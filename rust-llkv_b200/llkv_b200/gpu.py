@@ -81,6 +81,7 @@ def load():
         "llkv_gpu_column_sort_index_blob": (i32, [vp, u64, vp, u64, P(u64)]),
         "llkv_gpu_column_gather": (i32, [vp, vp, u64, vp, u64, vp]),
         "llkv_gpu_column_visit": (i32, [vp, u64, i32, CHUNK_VISITOR, vp]),
+        "llkv_gpu_column_scan": (i32, [vp, vp, P(ffi.ScanOptions), u64, CHUNK_VISITOR, vp]),
         "llkv_gpu_column_h2d_bytes": (i32, [vp, P(u64)]),
         "llkv_gpu_ctx_set_upload_threads": (i32, [vp, i32]),
         "llkv_gpu_column_rows": (i32, [vp, P(u64)]),
@@ -341,6 +342,46 @@ class DeviceColumn:
 
         cb = CHUNK_VISITOR(trampoline)
         _check(self.lib.llkv_gpu_column_visit(self.handle, chunk_rows, int(with_row_ids), cb, None))
+
+    def scan(self, on_run, sorted: bool = False, reverse: bool = False, with_row_ids: bool = False, limit: Optional[int] = None, offset: int = 0,
+             include_nulls: bool = False, nulls_first: bool = False, anchor: Optional["DeviceColumn"] = None, lower=None, upper=None,
+             chunk_rows: int = 0):
+        """ColumnStore::scan(field, ScanOptions, visitor): on_run(values | None, row_ids | None) per chunk; values None = a null run.
+        lower / upper: (value, inclusive) bounds in the column's type."""
+        t = self.dtype.type
+        np_t = {ffi.PT_UINT64: np.uint64, ffi.PT_INT64: np.int64, ffi.PT_FLOAT64: np.float64, ffi.PT_INT32: np.int32, ffi.PT_UINT32: np.uint32,
+                ffi.PT_FLOAT32: np.float32, ffi.PT_DATE32: np.int32, ffi.PT_INT16: np.int16, ffi.PT_UINT16: np.uint16, ffi.PT_INT8: np.int8,
+                ffi.PT_UINT8: np.uint8, ffi.PT_BOOLEAN: np.uint8, ffi.PT_DATE64: np.int64, ffi.PT_DECIMAL128: np.uint64}[t]
+        per_row = 2 if t == ffi.PT_DECIMAL128 else 1
+        o = ffi.ScanOptions()
+        o.sorted, o.reverse, o.with_row_ids, o.include_nulls, o.nulls_first = int(sorted), int(reverse), int(with_row_ids), int(include_nulls), int(nulls_first)
+        o.offset, o.limit = offset, 0 if limit is None else limit
+        if limit == 0:
+            return
+
+        def bits_of(v):
+            if np_t in (np.float64,):
+                return int(np.array([v], np.float64).view(np.uint64)[0])
+            if np_t in (np.float32,):
+                return int(np.array([v], np.float32).view(np.uint32)[0])
+            return int(v) & 0xFFFFFFFFFFFFFFFF
+
+        if lower is not None:
+            o.has_lower, o.lower_inclusive, o.lower_bits = 1, int(lower[1]), bits_of(lower[0])
+        if upper is not None:
+            o.has_upper, o.upper_inclusive, o.upper_bits = 1, int(upper[1]), bits_of(upper[0])
+
+        def trampoline(_user, prim_type, values, row_ids, n):
+            ids = np.ctypeslib.as_array(row_ids, shape=(n,)).copy() if row_ids else None
+            if not values:
+                on_run(None, ids)
+                return 0
+            vals = np.ctypeslib.as_array(C.cast(values, C.POINTER(np.ctypeslib.as_ctypes_type(np_t))), shape=(n * per_row,)).copy()
+            on_run(vals.reshape(n, 2) if per_row == 2 else vals, ids)
+            return 0
+
+        cb = CHUNK_VISITOR(trampoline)
+        _check(self.lib.llkv_gpu_column_scan(self.handle, anchor.handle if anchor else None, C.byref(o), chunk_rows, cb, None))
 
     def build_sort_index(self, chunk_rows: int = 0):
         _check(self.lib.llkv_gpu_column_build_sort_index(self.handle, chunk_rows))
