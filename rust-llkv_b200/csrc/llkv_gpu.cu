@@ -2050,7 +2050,7 @@ struct ScanEmit {
 extern "C" int32_t llkv_gpu_column_scan(llkv_gpu_column* col, llkv_gpu_column* anchor, const llkv_scan_options* o, uint64_t chunk_rows,
                                          llkv_chunk_visitor visit, void* user) {
   if (!col || !o || !visit) return set_error(LLKV_ERR_INVALID_ARGUMENT, "NULL argument");
-  if (col->type == LLKV_PT_UTF8 || col->load_kind == LK_D128) return set_error(LLKV_ERR_INVALID_ARGUMENT, "llkv_gpu_column_scan does not support this column type");
+  if (col->type == LLKV_PT_UTF8) return set_error(LLKV_ERR_INVALID_ARGUMENT, "llkv_gpu_column_scan does not support Utf8 columns");
   if (o->include_nulls && (!o->with_row_ids || !anchor)) return set_error(LLKV_ERR_INVALID_ARGUMENT, "include_nulls needs with_row_ids and an anchor column");
   if (o->include_nulls && !o->sorted) return set_error(LLKV_ERR_INVALID_ARGUMENT, "null runs are emitted by sorted scans on this path");
   llkv_gpu_ctx* c = col->ctx;
@@ -2059,6 +2059,7 @@ extern "C" int32_t llkv_gpu_column_scan(llkv_gpu_column* col, llkv_gpu_column* a
   int32_t rc;
   if (!col->sealed && (rc = llkv_gpu_column_seal(col))) return rc;
   if (anchor && !anchor->sealed && (rc = llkv_gpu_column_seal(anchor))) return rc;
+  if (o->sorted && col->load_kind == LK_D128) return set_error(LLKV_ERR_INVALID_ARGUMENT, "sorted scans take Decimal128 columns whose values fit i64");
   const uint64_t width = (uint64_t)prim_type_width(col->type);
   if (chunk_rows == 0) chunk_rows = width <= 8 ? (1ull << 20) / width : 4096;
   ScanEmit em{col, visit, user, o->offset, o->limit, o->limit != 0, o->with_row_ids != 0};
