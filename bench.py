@@ -186,11 +186,14 @@ def run_ours(args):
     ctx = gpu.Context(local, n_streams=4, pinned_bytes=64 << 20)
     # host workers that narrow Decimal128 chunks before the DMA: this rank's share of the host threads
     upload_threads = args.upload_threads if args.upload_threads >= 0 else max(0, min(32, cores // world - 1))
-    if args.upload_threads < 0 and (world > 1 or upload_threads < 12):
-        # one host thread narrows ~5 GB/s of Arrow bytes, and the host's streaming rate stops growing near 85 GB/s: worth it
-        # for one rank with >= 12 threads (measured: 16 threads 37.8 ms, 23 threads 34.7 ms against 58 ms of plain DMA per
-        # step), not when several ranks share the host (12 threads per rank at N = 2: 113 ms against 72 ms)
+    if args.upload_threads < 0 and world > 1:
+        # several ranks share the host's memory system: narrowing on the host loses against plain DMA there
+        # (12 threads per rank at N = 2: 113 ms against 72 ms per step)
         upload_threads = 0
+    # N = 1: a hybrid upload — the workers narrow their share of the Decimal128 bytes (about 4.5 GB/s of Arrow bytes each,
+    # bound by the host's memory system), the copy engine takes the rest as it lies and a kernel narrows it on the device;
+    # the split follows the worker count (llkv_gpu_ctx_set_dma_share, -1)
+    ctx.set_dma_share(args.dma_share)
     ctx.set_upload_threads(upload_threads)
     if world > 1:
         ids = [ctx.comm_unique_id() if rank == 0 else None]
@@ -395,7 +398,7 @@ def run_ours(args):
                              "resident_bytes_per_row": alg_bpr, "algorithmic_bytes_per_row": arrow_bpr,
                              "algorithmic_gbs": achieved_arrow},
                 "e2e": {"value": total_rows * e2e_steps / e2e_dt, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                        "host_bytes_per_step": host_bytes, "upload_threads": upload_threads,
+                        "host_bytes_per_step": host_bytes, "upload_threads": upload_threads, "dma_share_percent": args.dma_share,
                         "note": "host buffers hold the Arrow layout (Decimal128 = 16 B/value); host workers narrow the chunks that fit before the DMA, "
                                 "h2d_bytes_per_step is what crossed the link (llkv_gpu_column_h2d_bytes)",
                         "ms_per_step": e2e_dt / e2e_steps * 1e3, "steps": e2e_steps},
@@ -701,6 +704,7 @@ def main():
     ap.add_argument("--rows", type=int, default=0, help="override the row count per GPU (smoke runs)")
     ap.add_argument("--highcard-rows", type=int, default=0, help="override the row count of the configs[3] leg")
     ap.add_argument("--upload-threads", type=int, default=-1, help="host workers narrowing Decimal128 chunks before the DMA (0 = off)")
+    ap.add_argument("--dma-share", type=int, default=-1, help="percent of the Decimal128 bytes of the end-to-end upload that take the copy engine unnarrowed (-1 = from the worker count)")
     ap.add_argument("--no-q1", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-highcard", action="store_true")

@@ -246,6 +246,8 @@ extern "C" {
     pub fn llkv_gpu_host_unregister(p: *const c_void) -> i32;
     /// Host workers narrowing Decimal128 chunks from page-locked sources before the DMA: -1 default, 0 off.
     pub fn llkv_gpu_ctx_set_upload_threads(ctx: *mut llkv_gpu_ctx, n_threads: i32) -> i32;
+    /// Share (percent) of a hybrid Decimal128 upload that takes the copy engine and is narrowed on the device; -1 = automatic.
+    pub fn llkv_gpu_ctx_set_dma_share(ctx: *mut llkv_gpu_ctx, percent: i32) -> i32;
     /// llkv_gpu_agg_execute replays a captured CUDA graph once a step repeats unchanged: 1 (default) / 0.
     pub fn llkv_gpu_ctx_set_graphs(ctx: *mut llkv_gpu_ctx, mode: i32) -> i32;
 

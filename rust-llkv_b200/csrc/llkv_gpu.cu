@@ -195,6 +195,26 @@ __global__ void narrow_str_kernel(const u64* __restrict__ in, unsigned char* __r
 __global__ void narrow_dec_kernel(const ulonglong2* __restrict__ in, u64* __restrict__ out, u64 n) {
   for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (u64)gridDim.x * blockDim.x) out[i] = in[i].x;
 }
+// the same narrowing for chunks that crossed the link in the Arrow layout (the DMA share of a hybrid upload): the fit
+// check the host workers make is made here, a value that does not fit raises *bad
+__global__ void narrow_dec32_check_kernel(const ulonglong2* __restrict__ in, int* __restrict__ out, u64 n, unsigned int* bad) {
+  bool b = false;
+  for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (u64)gridDim.x * blockDim.x) {
+    const ulonglong2 w = in[i];
+    out[i] = (int)w.x;
+    b = b || (i64)w.y != ((i64)w.x >> 63) || (i64)w.x != (i64)(int)w.x;
+  }
+  if (b) atomicOr(bad, 1u);
+}
+__global__ void narrow_dec64_check_kernel(const ulonglong2* __restrict__ in, u64* __restrict__ out, u64 n, unsigned int* bad) {
+  bool b = false;
+  for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (u64)gridDim.x * blockDim.x) {
+    const ulonglong2 w = in[i];
+    out[i] = w.x;
+    b = b || (i64)w.y != ((i64)w.x >> 63);
+  }
+  if (b) atomicOr(bad, 1u);
+}
 __global__ void narrow_dec32_kernel(const ulonglong2* __restrict__ in, int* __restrict__ out, u64 n) {
   for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (u64)gridDim.x * blockDim.x) out[i] = (int)in[i].x;
 }
@@ -662,6 +682,7 @@ struct llkv_gpu_ctx {
   int graph_mode = 1;        // llkv_gpu_agg_execute: 1 = replay a captured CUDA graph once a step repeats unchanged, 0 = never
   // host workers that narrow Decimal128 chunks from page-locked sources before the DMA (upload.h); created on first use
   int upload_threads = -1;  // -1 = default (min(32, hardware threads - 1)), 0 = never narrow on the host
+  int dma_share = -1;       // percent of the Decimal128 bytes of a hybrid upload that take the copy engine; -1 = from the thread count
   std::unique_ptr<UploadPool> pool;
 };
 #define CTX_LOCK(c) std::lock_guard<std::recursive_mutex> _ctx_lock((c)->mu)
@@ -699,9 +720,23 @@ struct StrDict {
 };
 constexpr size_t kMaxDictEntries = 1u << 24;
 
+constexpr uint64_t kDmaSlotRows = 512u << 10;  // 8 MiB of Arrow Decimal128 per staged copy
+
 struct llkv_gpu_column {
   llkv_gpu_ctx* ctx = nullptr;
   std::unique_ptr<StrDict> dict;
+  // Hybrid upload of Decimal128 chunks from page-locked memory: the host workers narrow their share before the DMA, the
+  // copy engine takes the rest as it lies (16 B/value) into one of two staging slots and a kernel narrows it on the
+  // device.  Both feed the same narrow column; consecutive chunks of the DMA share travel as one copy.
+  void* dma_slot[2] = {nullptr, nullptr};
+  cudaEvent_t dma_ev[2] = {nullptr, nullptr};
+  bool dma_ev_used[2] = {false, false};
+  unsigned dma_turn = 0;
+  const char* dma_src = nullptr;  // pending run: source, first row, rows, narrowing kind
+  uint64_t dma_first_row = 0, dma_rows = 0;
+  int dma_kind = 0;
+  unsigned int* d_fit = nullptr;  // device flag: a value of the DMA share did not fit
+  bool dma_used = false;
   uint64_t lfid = 0;
   int32_t type = 0;
   uint8_t precision = 0;
@@ -932,6 +967,8 @@ extern "C" int32_t llkv_gpu_ctx_create(int32_t device_ordinal, int32_t n_streams
     c->no_d32 = e32 && e32[0] == '1';
     const char* ep = getenv("LLKV_GPU_NO_PACKED");
     c->no_packed = ep && ep[0] == '1';
+    const char* ed = getenv("LLKV_GPU_DMA_SHARE");  // percent (experiments)
+    if (ed && ed[0]) c->dma_share = std::max(-1, std::min(100, atoi(ed)));
     const char* eg = getenv("LLKV_GPU_NO_GRAPHS");  // (profilers that want plain launches)
     if (eg && eg[0] == '1') c->graph_mode = 0;
   }
@@ -1124,6 +1161,18 @@ extern "C" int32_t llkv_gpu_ctx_set_upload_threads(llkv_gpu_ctx* c, int32_t n_th
   return LLKV_OK;
 }
 
+extern "C" int32_t llkv_gpu_ctx_set_dma_share(llkv_gpu_ctx* c, int32_t percent) {
+  if (!c) return set_error(LLKV_ERR_INVALID_ARGUMENT, "ctx is NULL");
+  if (percent < -1 || percent > 100) return set_error(LLKV_ERR_INVALID_ARGUMENT, "the DMA share is -1 (from the worker count) or 0..100 percent");
+  CTX_LOCK(c);
+  for (auto& kv : c->columns) {
+    const int32_t rc = column_flush(kv.second);
+    if (rc) return rc;
+  }
+  c->dma_share = percent;
+  return LLKV_OK;
+}
+
 // ------------------------------------------------------------------------------------------------ columns
 static uint32_t device_elem_bytes(int32_t type) {
   if (type == LLKV_PT_UTF8) return 8;
@@ -1183,7 +1232,76 @@ extern "C" int32_t llkv_gpu_column_register(llkv_gpu_ctx* c, uint64_t lfid, int3
 
 // Issues the column's pending coalesced host->device copy (see upload()).  Must run before anything on the column's
 // stream reads or moves the destination: follow-up kernels, seal, grow, clear, destroy.
+static int32_t flush_dma_run(llkv_gpu_column* col) {
+  if (!col->dma_rows) return LLKV_OK;
+  llkv_gpu_ctx* c = col->ctx;
+  cudaStream_t cs = c->copy_streams[(size_t)col->stream_index];
+  const unsigned slot = col->dma_turn++ & 1u;
+  const uint64_t rows = col->dma_rows;
+  col->dma_rows = 0;
+  if (!col->dma_slot[slot]) {
+    CUDA_TRY(cudaMalloc(&col->dma_slot[slot], kDmaSlotRows * 16));
+    CUDA_TRY(cudaEventCreateWithFlags(&col->dma_ev[slot], cudaEventDisableTiming));
+  }
+  if (!col->d_fit) {
+    CUDA_TRY(cudaMalloc((void**)&col->d_fit, 4));
+    CUDA_TRY(cudaMemsetAsync(col->d_fit, 0, 4, cs));
+  }
+  if (col->dma_ev_used[slot]) CUDA_TRY(cudaEventSynchronize(col->dma_ev[slot]));  // the kernel that read the slot last has finished
+  CUDA_TRY(cudaMemcpyAsync(col->dma_slot[slot], col->dma_src, rows * 16, cudaMemcpyHostToDevice, cs));
+  const unsigned blocks = (unsigned)std::min<uint64_t>((rows + 255) / 256, 592);
+  if (col->dma_kind == UP_NARROW_D128_I32)
+    narrow_dec32_check_kernel<<<blocks, 256, 0, cs>>>((const ulonglong2*)col->dma_slot[slot], (int*)col->values + col->dma_first_row, rows, col->d_fit);
+  else
+    narrow_dec64_check_kernel<<<blocks, 256, 0, cs>>>((const ulonglong2*)col->dma_slot[slot], (u64*)col->values + col->dma_first_row, rows, col->d_fit);
+  CUDA_TRY(cudaGetLastError());
+  CUDA_TRY(cudaEventRecord(col->dma_ev[slot], cs));
+  col->dma_ev_used[slot] = true;
+  col->dma_used = true;
+  col->h2d_bytes += rows * 16;
+  return LLKV_OK;
+}
+// one chunk of the DMA share: joins the pending run when it continues it, else the run is issued and a new one starts
+static int32_t dma_narrow_chunk(llkv_gpu_column* col, const void* values, uint64_t first_row, uint64_t n_rows, int kind) {
+  const char* src = static_cast<const char*>(values);
+  while (n_rows) {
+    const bool joins = col->dma_rows && col->dma_kind == kind && col->dma_src + col->dma_rows * 16 == src && col->dma_first_row + col->dma_rows == first_row &&
+                       col->dma_rows < kDmaSlotRows;
+    if (!joins) {
+      int32_t rc = flush_dma_run(col);
+      if (rc) return rc;
+      col->dma_src = src;
+      col->dma_first_row = first_row;
+      col->dma_kind = kind;
+    }
+    const uint64_t take = std::min<uint64_t>(n_rows, kDmaSlotRows - col->dma_rows);
+    col->dma_rows += take;
+    src += take * 16;
+    first_row += take;
+    n_rows -= take;
+  }
+  return LLKV_OK;
+}
+// Which way a Decimal128 chunk of a hybrid upload goes: by 8 MiB blocks of the column's Arrow image, so that the chunks of
+// one block form one copy, `share` percent of the blocks to the copy engine.
+static bool route_to_dma(const llkv_gpu_column* col, uint64_t first_row) {
+  const llkv_gpu_ctx* c = col->ctx;
+  int share = c->dma_share;
+  if (share < 0) {  // a worker streams about 4.5 GB/s of Arrow bytes, the link about 48
+    const double workers = c->pool ? (double)c->pool->threads() : 0.0;
+    share = (int)(100.0 * 48.0 / (48.0 + 4.5 * workers));
+  }
+  if (share <= 0) return false;
+  if (share >= 100) return true;
+  const uint64_t block = (first_row * 16) >> 23;
+  return (block + 1) * (uint64_t)share / 100 > block * (uint64_t)share / 100;
+}
+
 static int32_t flush_upload(llkv_gpu_column* col) {
+  if (col->dma_rows) {
+    const int32_t rc = flush_dma_run(col);
+    if (rc) return rc;
+  }
   if (!col->pend_bytes) return LLKV_OK;
   cudaStream_t cs = col->ctx->copy_streams[(size_t)col->stream_index];
   const uint64_t n = col->pend_bytes;
@@ -1701,8 +1819,12 @@ static int32_t append_chunk_impl(llkv_gpu_column* col, const void* values, uint6
     }
   } else if (host_kind >= 0) {
     col->narrow_chunks.push_back(NarrowChunk{values, col->n_rows, n_rows});
-    col->h2d_bytes += n_rows * col->elem_bytes;
-    c->pool->submit(&col->ticket, values, (char*)col->values + col->n_rows * col->elem_bytes, n_rows, host_kind);
+    if (route_to_dma(col, col->n_rows)) {
+      if ((rc = dma_narrow_chunk(col, values, col->n_rows, n_rows, host_kind))) return rc;
+    } else {
+      col->h2d_bytes += n_rows * col->elem_bytes;
+      c->pool->submit(&col->ticket, values, (char*)col->values + col->n_rows * col->elem_bytes, n_rows, host_kind);
+    }
   } else {
     if ((rc = upload(col, (char*)col->values + col->n_rows * col->elem_bytes, values, n_rows * col->elem_bytes, src_kind))) return rc;
   }
@@ -1791,6 +1913,15 @@ static int32_t column_flush(llkv_gpu_column* col) {
   int32_t rc = flush_upload(col);
   if (rc) return rc;
   if ((rc = drain_jobs(col))) return rc;
+  if (col->dma_used) {  // the DMA share's fit check ran on the device
+    unsigned int bad = 0;
+    cudaStream_t cs = c->copy_streams[(size_t)col->stream_index];
+    CUDA_TRY(cudaMemcpyAsync(&bad, col->d_fit, 4, cudaMemcpyDeviceToHost, cs));
+    CUDA_TRY(cudaMemsetAsync(col->d_fit, 0, 4, cs));
+    CUDA_TRY(cudaStreamSynchronize(cs));
+    col->dma_used = false;
+    if (bad) col->ticket.failed.store(1);
+  }
   if (col->ticket.failed.load() && (rc = recover_wide(col))) return rc;
   col->narrow_chunks.clear();
   for (cudaStream_t s : c->copy_streams) CUDA_TRY(cudaStreamSynchronize(s));
@@ -2402,6 +2533,7 @@ extern "C" int32_t llkv_gpu_column_clear(llkv_gpu_column* col) {
   CUDA_TRY(cudaSetDevice(c->device));
   cudaStream_t s = c->copy_streams[(size_t)col->stream_index];
   col->pend_bytes = 0;  // rows that were never copied are dropped with the rest
+  col->dma_rows = 0;
   {
     int32_t rc = drain_jobs(col);
     if (rc) return rc;
@@ -2473,6 +2605,11 @@ extern "C" int32_t llkv_gpu_column_destroy(llkv_gpu_column* col) {
   if (col->dstats) cudaFree(col->dstats);
   if (col->d_zones) cudaFree(col->d_zones);
   if (col->d_perm) cudaFree(col->d_perm);
+  for (int i = 0; i < 2; ++i) {
+    if (col->dma_slot[i]) cudaFree(col->dma_slot[i]);
+    if (col->dma_ev[i]) cudaEventDestroy(col->dma_ev[i]);
+  }
+  if (col->d_fit) cudaFree(col->d_fit);
   delete col;
   return LLKV_OK;
 }

@@ -84,6 +84,7 @@ def load():
         "llkv_gpu_column_scan": (i32, [vp, vp, P(ffi.ScanOptions), u64, CHUNK_VISITOR, vp]),
         "llkv_gpu_column_h2d_bytes": (i32, [vp, P(u64)]),
         "llkv_gpu_ctx_set_upload_threads": (i32, [vp, i32]),
+        "llkv_gpu_ctx_set_dma_share": (i32, [vp, i32]),
         "llkv_gpu_column_rows": (i32, [vp, P(u64)]),
         "llkv_gpu_column_read": (i32, [vp, u64, u64, vp, u64]),
         "llkv_gpu_column_clear": (i32, [vp]),
@@ -194,6 +195,10 @@ class Context:
     def set_upload_threads(self, n_threads: int):
         """Host workers narrowing Decimal128 chunks from page-locked sources before the DMA: -1 default, 0 off."""
         _check(self.lib.llkv_gpu_ctx_set_upload_threads(self.handle, n_threads))
+
+    def set_dma_share(self, percent: int = -1):
+        """Share of a hybrid Decimal128 upload that goes to the copy engine as it lies (narrowed on the device); -1 = automatic."""
+        _check(self.lib.llkv_gpu_ctx_set_dma_share(self.handle, percent))
 
     # ---- multi-GPU (NCCL over NVLink): the unique id travels through whatever the host uses for rendezvous
     def comm_unique_id(self) -> bytes:

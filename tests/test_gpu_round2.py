@@ -31,23 +31,30 @@ def pinned_decimal(gpu, values_i64: np.ndarray, hi_override=None):
     return buf.view(wide.dtype).reshape(wide.shape), ptr
 
 
+@pytest.mark.parametrize("share", [0, 50, 100], ids=["workers", "hybrid", "dma"])
 @pytest.mark.parametrize("case", ["fits_i32", "fits_i64", "late_i64_value", "late_wide_value"])
-def test_host_narrowed_upload_from_pinned_memory(gpu_ctx, case):
+def test_host_narrowed_upload_from_pinned_memory(gpu_ctx, case, share):
     """Decimal128 chunks appended from page-locked memory are narrowed by the host workers before the DMA; a chunk that
     stops fitting sends the column back to the Arrow layout without losing a value (llkv_gpu.h: llkv_gpu_ctx_set_upload_threads)."""
     from llkv_b200 import gpu
-    n, chunk = 300_000, 65_536
+    n, chunk = 1_300_000, 65_536  # three 8 MiB blocks of Arrow bytes: at 50 % the middle one takes the copy engine
     rng = np.random.default_rng(11)
     v = rng.integers(-2_000_000, 2_000_000, n, dtype=np.int64)
     hi = None
     if case == "fits_i64":
         v = v * 10_000_000
     if case == "late_i64_value":
-        v[250_000] = 1 << 40
+        v[1_000_000] = 1 << 40  # (in the middle block: found by the workers or by the device, depending on the share)
     if case == "late_wide_value":
-        hi = {250_000: 5}  # a value that needs more than 64 bits
+        hi = {1_000_000: 5}  # a value that needs more than 64 bits
     view, ptr = pinned_decimal(gpu, v, hi)
     gpu_ctx.set_upload_threads(4)
+    gpu_ctx.set_dma_share(share)  # percent of the Arrow bytes (8 MiB blocks) that cross as they lie and are narrowed on the device
+    # rows of the DMA share: blocks of 2^19 values, `share` percent of them
+    blocks = [(b + 1) * share // 100 > b * share // 100 for b in range((n * 16 >> 23) + 1)]
+
+    def dma_rows(lo_row=0, hi_row=n):
+        return sum(min(chunk, hi_row - lo) for lo in range(lo_row, hi_row, chunk) if blocks[(lo * 16) >> 23])
     col = HostColumn(1, DEC, view)
     dc = gpu.DeviceColumn(gpu_ctx, gpu.logical_field_id(7, 1), col)
     try:
@@ -56,12 +63,13 @@ def test_host_narrowed_upload_from_pinned_memory(gpu_ctx, case):
             dc.append_raw(base + lo * 16, min(chunk, n - lo), lo)
         dc.seal()
         moved = dc.h2d_bytes()
+        d = dma_rows()
         if case == "fits_i32":
-            assert moved == n * 4
+            assert moved == (n - d) * 4 + d * 16
         elif case == "fits_i64":
-            assert moved == n * 8
+            assert moved == (n - d) * 8 + d * 16
         else:  # narrowed first, then everything since the last seal again in the Arrow layout
-            assert moved == n * 4 + n * 16
+            assert moved == (n - d) * 4 + d * 16 + n * 16
         back = dc.read()
         assert np.array_equal(back.reshape(-1), view.reshape(-1))
         if case != "late_wide_value":
@@ -81,12 +89,13 @@ def test_host_narrowed_upload_from_pinned_memory(gpu_ctx, case):
             dc.append_raw(base + lo * 16, min(chunk, n - lo), lo)
         dc.seal()
         again = dc.h2d_bytes() - before
-        expect = {"fits_i32": n * 4, "fits_i64": n * 8, "late_i64_value": n * 8, "late_wide_value": n * 8 + n * 16}[case]
-        assert again == expect
+        w = {"fits_i32": 4, "fits_i64": 8, "late_i64_value": 8, "late_wide_value": 8}[case]
+        assert again == (n - d) * w + d * 16 + (n * 16 if case == "late_wide_value" else 0)
         assert np.array_equal(dc.read().reshape(-1), view.reshape(-1))
     finally:
         dc.destroy()
         gpu_ctx.set_upload_threads(-1)
+        gpu_ctx.set_dma_share(-1)
         gpu.pinned_free(ptr)
 
 
