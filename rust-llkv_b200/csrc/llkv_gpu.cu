@@ -720,21 +720,12 @@ struct StrDict {
 };
 constexpr size_t kMaxDictEntries = 1u << 24;
 
-constexpr uint64_t kDmaSlotRows = 512u << 10;  // 8 MiB of Arrow Decimal128 per staged copy
-
 struct llkv_gpu_column {
   llkv_gpu_ctx* ctx = nullptr;
   std::unique_ptr<StrDict> dict;
   // Hybrid upload of Decimal128 chunks from page-locked memory: the host workers narrow their share before the DMA, the
-  // copy engine takes the rest as it lies (16 B/value) into one of two staging slots and a kernel narrows it on the
-  // device.  Both feed the same narrow column; consecutive chunks of the DMA share travel as one copy.
-  void* dma_slot[2] = {nullptr, nullptr};
-  cudaEvent_t dma_ev[2] = {nullptr, nullptr};
-  bool dma_ev_used[2] = {false, false};
-  unsigned dma_turn = 0;
-  const char* dma_src = nullptr;  // pending run: source, first row, rows, narrowing kind
-  uint64_t dma_first_row = 0, dma_rows = 0;
-  int dma_kind = 0;
+  // pool's DMA thread takes the rest as it lies (16 B/value) and a kernel narrows it on the device; both feed the same
+  // narrow column.
   unsigned int* d_fit = nullptr;  // device flag: a value of the DMA share did not fit
   bool dma_used = false;
   uint64_t lfid = 0;
@@ -1232,56 +1223,6 @@ extern "C" int32_t llkv_gpu_column_register(llkv_gpu_ctx* c, uint64_t lfid, int3
 
 // Issues the column's pending coalesced host->device copy (see upload()).  Must run before anything on the column's
 // stream reads or moves the destination: follow-up kernels, seal, grow, clear, destroy.
-static int32_t flush_dma_run(llkv_gpu_column* col) {
-  if (!col->dma_rows) return LLKV_OK;
-  llkv_gpu_ctx* c = col->ctx;
-  cudaStream_t cs = c->copy_streams[(size_t)col->stream_index];
-  const unsigned slot = col->dma_turn++ & 1u;
-  const uint64_t rows = col->dma_rows;
-  col->dma_rows = 0;
-  if (!col->dma_slot[slot]) {
-    CUDA_TRY(cudaMalloc(&col->dma_slot[slot], kDmaSlotRows * 16));
-    CUDA_TRY(cudaEventCreateWithFlags(&col->dma_ev[slot], cudaEventDisableTiming));
-  }
-  if (!col->d_fit) {
-    CUDA_TRY(cudaMalloc((void**)&col->d_fit, 4));
-    CUDA_TRY(cudaMemsetAsync(col->d_fit, 0, 4, cs));
-  }
-  if (col->dma_ev_used[slot]) CUDA_TRY(cudaEventSynchronize(col->dma_ev[slot]));  // the kernel that read the slot last has finished
-  CUDA_TRY(cudaMemcpyAsync(col->dma_slot[slot], col->dma_src, rows * 16, cudaMemcpyHostToDevice, cs));
-  const unsigned blocks = (unsigned)std::min<uint64_t>((rows + 255) / 256, 592);
-  if (col->dma_kind == UP_NARROW_D128_I32)
-    narrow_dec32_check_kernel<<<blocks, 256, 0, cs>>>((const ulonglong2*)col->dma_slot[slot], (int*)col->values + col->dma_first_row, rows, col->d_fit);
-  else
-    narrow_dec64_check_kernel<<<blocks, 256, 0, cs>>>((const ulonglong2*)col->dma_slot[slot], (u64*)col->values + col->dma_first_row, rows, col->d_fit);
-  CUDA_TRY(cudaGetLastError());
-  CUDA_TRY(cudaEventRecord(col->dma_ev[slot], cs));
-  col->dma_ev_used[slot] = true;
-  col->dma_used = true;
-  col->h2d_bytes += rows * 16;
-  return LLKV_OK;
-}
-// one chunk of the DMA share: joins the pending run when it continues it, else the run is issued and a new one starts
-static int32_t dma_narrow_chunk(llkv_gpu_column* col, const void* values, uint64_t first_row, uint64_t n_rows, int kind) {
-  const char* src = static_cast<const char*>(values);
-  while (n_rows) {
-    const bool joins = col->dma_rows && col->dma_kind == kind && col->dma_src + col->dma_rows * 16 == src && col->dma_first_row + col->dma_rows == first_row &&
-                       col->dma_rows < kDmaSlotRows;
-    if (!joins) {
-      int32_t rc = flush_dma_run(col);
-      if (rc) return rc;
-      col->dma_src = src;
-      col->dma_first_row = first_row;
-      col->dma_kind = kind;
-    }
-    const uint64_t take = std::min<uint64_t>(n_rows, kDmaSlotRows - col->dma_rows);
-    col->dma_rows += take;
-    src += take * 16;
-    first_row += take;
-    n_rows -= take;
-  }
-  return LLKV_OK;
-}
 // Which way a Decimal128 chunk of a hybrid upload goes: by 8 MiB blocks of the column's Arrow image, so that the chunks of
 // one block form one copy, `share` percent of the blocks to the copy engine.
 static bool route_to_dma(const llkv_gpu_column* col, uint64_t first_row) {
@@ -1298,10 +1239,6 @@ static bool route_to_dma(const llkv_gpu_column* col, uint64_t first_row) {
 }
 
 static int32_t flush_upload(llkv_gpu_column* col) {
-  if (col->dma_rows) {
-    const int32_t rc = flush_dma_run(col);
-    if (rc) return rc;
-  }
   if (!col->pend_bytes) return LLKV_OK;
   cudaStream_t cs = col->ctx->copy_streams[(size_t)col->stream_index];
   const uint64_t n = col->pend_bytes;
@@ -1574,6 +1511,13 @@ static int32_t begin_narrow_landing(llkv_gpu_column* col, uint32_t width, uint64
   return LLKV_OK;
 }
 
+static cudaError_t launch_narrow_check(int kind, const void* wide, void* dst, uint64_t n_rows, unsigned int* d_flag, cudaStream_t s) {
+  const unsigned blocks = (unsigned)std::min<uint64_t>((n_rows + 255) / 256, 592);
+  if (kind == UP_NARROW_D128_I32) narrow_dec32_check_kernel<<<blocks, 256, 0, s>>>((const ulonglong2*)wide, (int*)dst, n_rows, d_flag);
+  else narrow_dec64_check_kernel<<<blocks, 256, 0, s>>>((const ulonglong2*)wide, (u64*)dst, n_rows, d_flag);
+  return cudaGetLastError();
+}
+
 static UploadPool* upload_pool(llkv_gpu_ctx* c) {
   if (c->upload_threads == 0) return nullptr;
   if (!c->pool) {
@@ -1583,6 +1527,7 @@ static UploadPool* upload_pool(llkv_gpu_ctx* c) {
       n = (int)std::min<unsigned>(32u, hw > 2 ? hw - 1 : 1u);
     }
     c->pool.reset(new UploadPool(c->device, n));
+    c->pool->set_narrow_launcher(launch_narrow_check);
   }
   return c->pool.get();
 }
@@ -1820,7 +1765,13 @@ static int32_t append_chunk_impl(llkv_gpu_column* col, const void* values, uint6
   } else if (host_kind >= 0) {
     col->narrow_chunks.push_back(NarrowChunk{values, col->n_rows, n_rows});
     if (route_to_dma(col, col->n_rows)) {
-      if ((rc = dma_narrow_chunk(col, values, col->n_rows, n_rows, host_kind))) return rc;
+      if (!col->d_fit) {
+        CUDA_TRY(cudaMalloc((void**)&col->d_fit, 4));
+        CUDA_TRY(cudaMemset(col->d_fit, 0, 4));
+      }
+      col->dma_used = true;
+      col->h2d_bytes += n_rows * 16;
+      c->pool->submit_dma(&col->ticket, values, (char*)col->values + col->n_rows * col->elem_bytes, n_rows, host_kind, col->d_fit);
     } else {
       col->h2d_bytes += n_rows * col->elem_bytes;
       c->pool->submit(&col->ticket, values, (char*)col->values + col->n_rows * col->elem_bytes, n_rows, host_kind);
@@ -2533,7 +2484,6 @@ extern "C" int32_t llkv_gpu_column_clear(llkv_gpu_column* col) {
   CUDA_TRY(cudaSetDevice(c->device));
   cudaStream_t s = c->copy_streams[(size_t)col->stream_index];
   col->pend_bytes = 0;  // rows that were never copied are dropped with the rest
-  col->dma_rows = 0;
   {
     int32_t rc = drain_jobs(col);
     if (rc) return rc;
@@ -2605,10 +2555,6 @@ extern "C" int32_t llkv_gpu_column_destroy(llkv_gpu_column* col) {
   if (col->dstats) cudaFree(col->dstats);
   if (col->d_zones) cudaFree(col->d_zones);
   if (col->d_perm) cudaFree(col->d_perm);
-  for (int i = 0; i < 2; ++i) {
-    if (col->dma_slot[i]) cudaFree(col->dma_slot[i]);
-    if (col->dma_ev[i]) cudaEventDestroy(col->dma_ev[i]);
-  }
   if (col->d_fit) cudaFree(col->d_fit);
   delete col;
   return LLKV_OK;

@@ -84,11 +84,12 @@ bool narrow_d128_i32(const void* src, void* dst, uint64_t n) {
 
 UploadPool::UploadPool(int device, int n_threads) : device_(device) {
   if (n_threads < 1) n_threads = 1;
-  streams_.assign((size_t)n_threads, nullptr);
+  streams_.assign((size_t)n_threads + 1, nullptr);  // (the last one belongs to the DMA thread)
   for (int i = 0; i < n_threads; ++i) workers_.emplace_back([this, i] { run(i); });
+  dma_thread_ = std::thread([this] { run_dma(); });
   // the streams exist before the first wait()
   std::unique_lock<std::mutex> lk(mu_);
-  cv_done_.wait(lk, [&] { return ready_.load() == (int)workers_.size(); });
+  cv_done_.wait(lk, [&] { return ready_.load() == (int)workers_.size() + 1; });
 }
 
 UploadPool::~UploadPool() {
@@ -97,7 +98,94 @@ UploadPool::~UploadPool() {
     stop_ = true;
   }
   cv_job_.notify_all();
+  cv_dma_.notify_all();
   for (std::thread& t : workers_) t.join();
+  dma_thread_.join();
+}
+
+void UploadPool::submit_dma(UploadTicket* ticket, const void* src, void* dst, uint64_t n_rows, int kind, unsigned int* d_flag) {
+  if (!n_rows) return;
+  {
+    std::lock_guard<std::mutex> lk(mu_);
+    ticket->outstanding.fetch_add(1);
+    UploadJob j{ticket, src, dst, n_rows, kind};
+    j.d_flag = d_flag;
+    dma_queue_.push_back(j);
+  }
+  cv_dma_.notify_one();
+}
+
+void UploadPool::run_dma() {
+  cudaError_t e = cudaSetDevice(device_);
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev[2] = {nullptr, nullptr};
+  bool used[2] = {false, false};
+  void* slot[2] = {nullptr, nullptr};
+  if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking);
+  for (int i = 0; i < 2 && e == cudaSuccess; ++i) e = cudaEventCreateWithFlags(&ev[i], cudaEventDisableTiming);
+  const cudaError_t init_error = e;
+  {
+    std::lock_guard<std::mutex> lk(mu_);
+    streams_.back() = stream;
+    ready_.fetch_add(1);
+  }
+  cv_done_.notify_all();
+  unsigned turn = 0;
+  std::vector<UploadJob> run;  // jobs that travel as one copy
+  for (;;) {
+    run.clear();
+    {
+      std::unique_lock<std::mutex> lk(mu_);
+      cv_dma_.wait(lk, [&] { return stop_ || !dma_queue_.empty(); });
+      if (dma_queue_.empty()) break;  // stop_
+      run.push_back(dma_queue_.front());
+      dma_queue_.pop_front();
+      uint64_t rows = run[0].n_rows;
+      const uint64_t out_w = run[0].kind == UP_NARROW_D128_I32 ? 4 : 8;
+      while (!dma_queue_.empty()) {  // the next job continues this one on both sides: one copy
+        const UploadJob& n = dma_queue_.front();
+        const UploadJob& l = run.back();
+        if (n.kind != l.kind || n.d_flag != l.d_flag || static_cast<const char*>(l.src) + l.n_rows * 16 != n.src ||
+            static_cast<char*>(l.dst) + l.n_rows * out_w != n.dst || rows + n.n_rows > kDmaSlotRows)
+          break;
+        rows += n.n_rows;
+        run.push_back(n);
+        dma_queue_.pop_front();
+      }
+    }
+    cudaError_t je = init_error;
+    uint64_t rows = 0;
+    for (const UploadJob& j : run) rows += j.n_rows;
+    const UploadJob& first = run[0];
+    uint64_t done = 0;
+    while (je == cudaSuccess && done < rows) {  // (a single job larger than a slot goes in slices)
+      const uint64_t take = rows - done < kDmaSlotRows ? rows - done : kDmaSlotRows;
+      const unsigned s = turn++ & 1u;
+      if (!slot[s]) je = cudaMalloc(&slot[s], kDmaSlotRows * 16);
+      if (je == cudaSuccess && used[s]) je = cudaEventSynchronize(ev[s]);  // the kernel that read the slot last is done
+      const uint64_t out_w = first.kind == UP_NARROW_D128_I32 ? 4 : 8;
+      if (je == cudaSuccess) je = cudaMemcpyAsync(slot[s], static_cast<const char*>(first.src) + done * 16, take * 16, cudaMemcpyHostToDevice, stream);
+      if (je == cudaSuccess) je = narrow_launch_ ? narrow_launch_(first.kind, slot[s], static_cast<char*>(first.dst) + done * out_w, take, first.d_flag, stream) : cudaErrorNotSupported;
+      if (je == cudaSuccess) je = cudaEventRecord(ev[s], stream);
+      used[s] = true;
+      done += take;
+    }
+    for (const UploadJob& j : run) {
+      if (je != cudaSuccess) {
+        uint32_t expected = 0;
+        j.ticket->cuda_error.compare_exchange_strong(expected, (uint32_t)je);
+      }
+      std::lock_guard<std::mutex> lk(mu_);
+      j.ticket->outstanding.fetch_sub(1);
+    }
+    cv_done_.notify_all();
+  }
+  if (stream) cudaStreamSynchronize(stream);
+  for (int i = 0; i < 2; ++i) {
+    if (slot[i]) cudaFree(slot[i]);
+    if (ev[i]) cudaEventDestroy(ev[i]);
+  }
+  if (stream) cudaStreamDestroy(stream);
 }
 
 void UploadPool::submit(UploadTicket* ticket, const void* src, void* dst, uint64_t n_rows, int kind) {

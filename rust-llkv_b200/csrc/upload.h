@@ -35,7 +35,12 @@ struct UploadJob {
   void* dst;  // device
   uint64_t n_rows;
   int kind;
+  unsigned int* d_flag = nullptr;  // DMA share: device word the narrowing kernel raises when a value does not fit
 };
+
+// Launches the device-side narrowing of `n_rows` values that crossed the link in the Arrow layout (defined next to the
+// kernels, llkv_gpu.cu): wide -> dst, *d_flag |= 1 when a value does not fit.
+typedef cudaError_t (*NarrowLaunchFn)(int kind, const void* wide, void* dst, uint64_t n_rows, unsigned int* d_flag, cudaStream_t s);
 
 class UploadPool {
  public:
@@ -44,13 +49,24 @@ class UploadPool {
   int threads() const { return (int)workers_.size(); }
   // splits [src, src + n_rows) into pieces of at most kPieceRows rows and queues them
   void submit(UploadTicket* ticket, const void* src, void* dst, uint64_t n_rows, int kind);
+  // The DMA share of a hybrid upload: the rows travel as they lie (16 B/value), in copies of up to kDmaSlotRows rows
+  // (consecutive jobs that continue each other are merged), into one of two device staging slots, and are narrowed there.
+  // A thread of its own issues them, so the appender never waits for a slot and the workers never wait for the appender.
+  void submit_dma(UploadTicket* ticket, const void* src, void* dst, uint64_t n_rows, int kind, unsigned int* d_flag);
+  void set_narrow_launcher(NarrowLaunchFn fn) { narrow_launch_ = fn; }
   // blocks until every job of `ticket` has been issued to its worker's stream, then until those streams have drained
   cudaError_t wait(UploadTicket* ticket);
   static constexpr uint64_t kPieceRows = 65536;
+  static constexpr uint64_t kDmaSlotRows = 512u << 10;  // 8 MiB of Arrow Decimal128
 
  private:
   void run(int index);
+  void run_dma();
   int device_;
+  NarrowLaunchFn narrow_launch_ = nullptr;
+  std::thread dma_thread_;
+  std::deque<UploadJob> dma_queue_;
+  std::condition_variable cv_dma_;
   std::vector<std::thread> workers_;
   std::vector<cudaStream_t> streams_;
   std::mutex mu_;
