@@ -314,10 +314,12 @@ int32_t llkv_gpu_host_free(void* p);
  * to the Arrow layout, nothing is lost): half or a quarter of the bytes cross PCIe and the device skips its own narrowing
  * pass at seal.  -1 = default (min(32, hardware threads - 1)), 0 = off (16-byte DMA, narrowed on the device at seal). */
 int32_t llkv_gpu_ctx_set_upload_threads(llkv_gpu_ctx* ctx, int32_t n_threads);
-/* The host workers are bound by the host's memory system (each streams a few GB/s of Arrow bytes), the copy engine by the
- * link: a hybrid upload uses both at once.  `percent` of a Decimal128 column's Arrow bytes (in 8 MiB blocks) take the copy
- * engine as they lie and are narrowed, and checked, by a kernel on the device; the workers narrow the rest before their
- * DMA.  -1 = default: from the worker count, 48 GB/s for the link against 4.5 GB/s per worker; 0 = workers only. */
+/* Hybrid upload: `percent` of a Decimal128 column's Arrow bytes (in 8 MiB blocks) cross the link as they lie, issued by a
+ * thread of the pool, and are narrowed and checked by a kernel on the device, while the workers narrow the rest before
+ * their DMA.  Both ways read the same host memory, which is the limit they share: the copy engine helps when there are
+ * few workers (8 workers: 56 ms -> 48 ms per 2.9 GB) and not when the workers alone saturate the host (15 workers:
+ * 37 ms either way).  -1 = default: what the workers leave of the host's streaming budget (0 from 12 workers up);
+ * 0 = workers only; 100 = copy engine only. */
 int32_t llkv_gpu_ctx_set_dma_share(llkv_gpu_ctx* ctx, int32_t percent);
 /* Page-locks memory the caller already owns — the pager's mmap-backed blobs (EntryHandle, llkv-storage/src/pager/
  * simd_r_drive_pager.rs) — so llkv_gpu_column_append_blob / _append_chunk DMA straight out of it
