@@ -3106,7 +3106,12 @@ static int32_t lean_geometry(const LeanTune& tn, const Plan& p, uint64_t row_beg
     if (want_stages) {
       if (st < want_stages) return 0;
       st = want_stages;
-    } else if (st > 4) st = 4;
+    } else {
+      if (st > 4) st = 4;
+      // More than ~160 KB of bulk copies in flight per SM buys nothing and costs DRAM efficiency (Q6 at SF10, tools/sweep_q6.py:
+      // 4 CTAs x 3 stages x 16 KB = 192 KB in flight 0.155 ms; 4 x 2 x 16 KB 0.145 ms; 3 x 3 x 16 KB 0.144 ms; 4 x 4 x 8 KB 0.145 ms)
+      while (st > 2 && (uint64_t)ctas * st * stage_bytes > 160u * 1024u) --st;
+    }
     uint32_t off = 0;
     s.smem_bar_off = off;
     off += 128;
