@@ -195,6 +195,32 @@ def test_gpu_column_turns_long_in_a_later_chunk_and_grows_after_seal(gpu_ctx):
 
 
 @pytest.mark.gpu
+def test_gpu_clear_drops_the_dictionary(gpu_ctx):
+    """clear() + short strings: the column is a packed short-string column again (no dictionary, keys come back inline)."""
+    from llkv_b200 import gpu
+    long_col = HostColumn.utf8(1, ["DELIVER IN PERSON", "NONE", "DELIVER IN PERSON"])
+    dc = gpu.DeviceColumn(gpu_ctx, gpu.logical_field_id(65, 1), long_col)
+    nc = gpu.DeviceColumn(gpu_ctx, gpu.logical_field_id(65, 2), HostColumn(2, DataType.Int64, np.arange(3, dtype=np.int64)))
+    dt = gpu.DeviceTable(gpu_ctx, 65)
+    dt.columns[1], dt.columns[2] = dc, nc
+    try:
+        dc.append(long_col)
+        nc.append(HostColumn(2, DataType.Int64, np.arange(3, dtype=np.int64)))
+        dt.n_rows = 3
+        assert dc.dict_size() == 2
+        got = dt.aggregate(None, SPECS[:2], None, (1,), cardinality_hint=4)
+        assert [k[0] for k, _ in got] == ["DELIVER IN PERSON", "NONE"]
+        dc.clear()
+        short = HostColumn.utf8(1, ["N", "xy", "N"])
+        dc.append(short)
+        assert dc.dict_size() == 0
+        t = HostTable(65).add(short).add(HostColumn(2, DataType.Int64, np.arange(3, dtype=np.int64)))
+        util.assert_same_result(dt.aggregate(None, SPECS[:2], None, (1,), cardinality_hint=4), oracle.aggregate(t, None, SPECS[:2], None, (1,)))
+    finally:
+        dt.destroy()
+
+
+@pytest.mark.gpu
 def test_gpu_long_string_limits_are_errors(gpu_ctx):
     from llkv_b200 import gpu
     t, _ = table(n=3000)

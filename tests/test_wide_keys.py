@@ -80,3 +80,19 @@ def test_gpu_wide_keys_having_order_by_and_repeated_steps(gpu_ctx):
         agg.destroy()
     finally:
         dt.destroy()
+
+
+@pytest.mark.gpu
+def test_gpu_wide_keys_survive_table_growth(gpu_ctx):
+    """5000 wide-key groups against a hint of 16: the table fills, grows and is rehashed by the (hashed) key; first-row words
+    — where the key values are read from — move with their groups."""
+    t = wide_table(60_000, 9, groups=5000, tid=73)
+    dt = gpu.DeviceTable.from_host(gpu_ctx, t)
+    try:
+        want = oracle.aggregate(t, None, SPECS, None, (2, 1), group_capacity=1 << 14)
+        for mode in (0, 2):
+            gpu_ctx.set_jit(mode)
+            util.assert_same_result(dt.aggregate(None, SPECS, None, (2, 1), cardinality_hint=16), want)
+    finally:
+        gpu_ctx.set_jit(1)
+        dt.destroy()
