@@ -432,7 +432,9 @@ int32_t llkv_gpu_column_gather(llkv_gpu_column* col, const uint64_t* row_ids, ui
  * LLKV_ERR_PREDICATE_BUILD), and GROUP BY keys take ceil(log2(entries)) bits (GroupKeyValue::String,
  * llkv-executor/src/lib.rs:99-106,9362-9456).  Group keys of such a column come back with llkv_group_key.dict = 1.
  * Limits: 2^24 distinct strings per column; scalar
- * expressions over a dictionary-coded column and merging its group keys across GPUs are LLKV_ERR_INVALID_ARGUMENT.
+ * expressions over a dictionary-coded column are LLKV_ERR_INVALID_ARGUMENT.  Across GPUs the ranks agree on one dictionary
+ * per Utf8 key column before a grouped plan is compiled (an all-gather of their entries; a rank whose shard holds short
+ * strings only switches to dictionary form with the others), so codes mean the same string on every rank.
  * llkv_gpu_column_dict_entry: the bytes stay valid until the next append to / clear of the column. */
 int32_t llkv_gpu_column_dict_size(llkv_gpu_column* col, uint64_t* out_entries);
 int32_t llkv_gpu_column_dict_entry(llkv_gpu_column* col, uint64_t code, const uint8_t** out_bytes, uint64_t* out_len);

@@ -823,6 +823,7 @@ struct PendingRun {
 struct llkv_gpu_agg {
   llkv_gpu_ctx* ctx = nullptr;
   StringStore strings;
+  uint64_t dict_agreed_epoch = ~0ull;  // context state the ranks last agreed their key dictionaries at
   uint64_t runs_done = 0, wide_verified = ~0ull;  // hashed wide keys: the run the verification pass last covered
   uint64_t table_id = 0;
   std::vector<llkv_agg_spec> specs;
@@ -1594,6 +1595,21 @@ static int32_t append_sparse(llkv_gpu_column* col, const void* values, uint64_t 
   return LLKV_OK;
 }
 
+static int32_t widen_str8(llkv_gpu_column* col) {
+  u64* wide = nullptr;
+  CUDA_TRY(cudaDeviceSynchronize());
+  CUDA_TRY(cudaMalloc((void**)&wide, col->cap_rows * 8));
+  CUDA_TRY(cudaMemset(wide, 0, col->cap_rows * 8));
+  widen_str_kernel<<<1184, 256>>>((const unsigned char*)col->values, wide, col->n_rows);
+  CUDA_TRY(cudaGetLastError());
+  CUDA_TRY(cudaDeviceSynchronize());
+  CUDA_TRY(cudaFree(col->values));
+  col->values = wide;
+  col->elem_bytes = 8;
+  col->load_kind = LK_U64;
+  return LLKV_OK;
+}
+
 // A Utf8 column meets its first string longer than 7 bytes: the rows it already holds (packed keys, which carry their bytes)
 // are read back once, interned, and rewritten as dictionary codes.
 static int32_t enter_dict_mode(llkv_gpu_column* col) {
@@ -1680,19 +1696,8 @@ static int32_t append_chunk_impl(llkv_gpu_column* col, const void* values, uint6
   col->sealed = false;
   const SrcKind src_kind = source_kind(values);
   const bool pinned_src = src_kind == SRC_PINNED;
-  if (col->load_kind == LK_STR8) {  // sealed as one byte per string: back to packed keys before more chunks arrive
-    u64* wide = nullptr;
-    CUDA_TRY(cudaDeviceSynchronize());
-    CUDA_TRY(cudaMalloc((void**)&wide, col->cap_rows * 8));
-    CUDA_TRY(cudaMemset(wide, 0, col->cap_rows * 8));
-    widen_str_kernel<<<1184, 256>>>((const unsigned char*)col->values, wide, col->n_rows);
-    CUDA_TRY(cudaGetLastError());
-    CUDA_TRY(cudaDeviceSynchronize());
-    CUDA_TRY(cudaFree(col->values));
-    col->values = wide;
-    col->elem_bytes = 8;
-    col->load_kind = LK_U64;
-  }
+  int32_t rc0;
+  if (col->load_kind == LK_STR8 && (rc0 = widen_str8(col))) return rc0;  // sealed as one byte per string: back to packed keys before more chunks arrive
   // Decimal128: chunks from page-locked memory are narrowed by the host workers while the column's values keep fitting
   // (upload.h); everything else lands in the Arrow layout and is narrowed on the device at seal.
   int host_kind = -2;
@@ -3710,6 +3715,104 @@ static uint64_t request_signature(const llkv_gpu_ctx* ctx, const CompileRequest&
   return h ? h : 1;
 }
 
+// Multi-GPU GROUP BY over Utf8 keys: dictionary codes only merge if every rank codes alike.  When any rank holds a key
+// column in dictionary form, every rank switches that column to dictionary form, the ranks exchange their entries
+// (all-gather), intern what they did not have and re-rank (dict_seal): equal sets of strings give equal ranks everywhere.
+// Collective; skipped (by all ranks alike) while nothing a plan depends on has changed since the last agreement.
+static int32_t agree_dictionaries(llkv_gpu_ctx* ctx, llkv_gpu_agg* a, const std::vector<llkv_gpu_column*>& handles, bool* changed) {
+  *changed = false;
+  std::vector<llkv_gpu_column*> cols;
+  for (uint64_t f : a->keys)
+    for (llkv_gpu_column* h : handles)
+      if (lfid_field(h->lfid) == f && h->type == LLKV_PT_UTF8) cols.push_back(h);
+  if (cols.empty() || a->in_rerun || a->dict_agreed_epoch == ctx->state_epoch) return LLKV_OK;
+  const int N = ctx->n_ranks;
+  cudaStream_t s = ctx->stream;
+  std::vector<u64> v(cols.size());
+  u64* d_v = nullptr;
+  CUDA_TRY(cudaMalloc((void**)&d_v, v.size() * 8));
+  auto all_max = [&]() -> int32_t {
+    CUDA_TRY(cudaMemcpyAsync(d_v, v.data(), v.size() * 8, cudaMemcpyHostToDevice, s));
+    NCCL_TRY(g_nccl.all_reduce(d_v, d_v, v.size(), 5 /* ncclUint64 */, 2 /* ncclMax */, ctx->nccl_comm, s));
+    CUDA_TRY(cudaMemcpyAsync(v.data(), d_v, v.size() * 8, cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaStreamSynchronize(s));
+    return LLKV_OK;
+  };
+  int32_t rc = LLKV_OK;
+  for (size_t i = 0; i < cols.size(); ++i) v[i] = cols[i]->dict ? 1 : 0;
+  if ((rc = all_max())) { cudaFree(d_v); return rc; }
+  std::vector<char> coded(cols.size());
+  bool any = false;
+  for (size_t i = 0; i < cols.size() && !rc; ++i) {
+    coded[i] = v[i] != 0;
+    if (!coded[i]) continue;
+    any = true;
+    llkv_gpu_column* col = cols[i];
+    if (!col->dict) {  // this rank's shard has short strings only: into dictionary form like the others
+      if ((rc = column_flush(col))) break;
+      if (col->load_kind == LK_STR8 && (rc = widen_str8(col))) break;
+      if ((rc = enter_dict_mode(col))) break;
+      *changed = true;
+    }
+  }
+  if (!rc && any) {
+    // entries as [u32 length][bytes]..., padded to the longest rank's size
+    std::vector<std::string> blob(cols.size());
+    for (size_t i = 0; i < cols.size(); ++i) {
+      v[i] = 0;
+      if (!coded[i]) continue;
+      for (const std::string& e : cols[i]->dict->strings) {
+        const uint32_t len = (uint32_t)e.size();
+        blob[i].append(reinterpret_cast<const char*>(&len), 4);
+        blob[i].append(e);
+      }
+      v[i] = blob[i].size();
+    }
+    rc = all_max();
+    for (size_t i = 0; i < cols.size() && !rc; ++i) {
+      if (!coded[i]) continue;
+      const size_t slot = (size_t)((v[i] + 8 + 7) / 8 * 8);  // [u64 bytes][entries...]
+      std::vector<char> mine(slot, 0), all(slot * (size_t)N);
+      const u64 bytes = blob[i].size();
+      memcpy(mine.data(), &bytes, 8);
+      memcpy(mine.data() + 8, blob[i].data(), blob[i].size());
+      char *d_mine = nullptr, *d_all = nullptr;
+      CUDA_TRY(cudaMalloc((void**)&d_mine, slot));
+      CUDA_TRY(cudaMalloc((void**)&d_all, slot * (size_t)N));
+      CUDA_TRY(cudaMemcpyAsync(d_mine, mine.data(), slot, cudaMemcpyHostToDevice, s));
+      NCCL_TRY(g_nccl.all_gather(d_mine, d_all, slot, 0 /* ncclInt8 */, ctx->nccl_comm, s));
+      CUDA_TRY(cudaMemcpyAsync(all.data(), d_all, slot * (size_t)N, cudaMemcpyDeviceToHost, s));
+      CUDA_TRY(cudaStreamSynchronize(s));
+      CUDA_TRY(cudaFree(d_mine));
+      CUDA_TRY(cudaFree(d_all));
+      StrDict& d = *cols[i]->dict;
+      const size_t before = d.strings.size();
+      for (int r = 0; r < N; ++r) {
+        const char* p = all.data() + slot * (size_t)r;
+        u64 n;
+        memcpy(&n, p, 8);
+        for (u64 at = 0; at + 4 <= n;) {
+          uint32_t len;
+          memcpy(&len, p + 8 + at, 4);
+          d.intern(p + 8 + at + 4, len);
+          at += 4 + len;
+        }
+      }
+      if (d.strings.size() > kMaxDictEntries) rc = set_error(LLKV_ERR_INVALID_ARGUMENT, "more than %zu distinct strings in a dictionary-coded column", kMaxDictEntries);
+      if (!rc && (d.strings.size() != before || d.strings.size() != d.sealed)) {
+        rc = dict_seal(cols[i]);
+        ++cols[i]->version;
+        ++ctx->state_epoch;
+        *changed = true;
+      }
+    }
+  }
+  cudaFree(d_v);
+  if (any) a->agreed_epoch = ~0ull;  // every rank agrees the key statistics again (a rank-invariant decision: `any` is)
+  if (!rc) a->dict_agreed_epoch = ctx->state_epoch;
+  return rc;
+}
+
 static int32_t agree_key_stats(llkv_gpu_ctx* ctx, llkv_gpu_agg* a, CompileRequest& req) {
   const size_t nk = a->keys.size();
   std::vector<u64> v(nk * 4);
@@ -3802,7 +3905,16 @@ static int32_t agg_launch(llkv_gpu_agg* a, const llkv_gpu_program* prog, int app
   // Multi-GPU GROUP BY: the packed key layout (bits, minimum, string length per key) comes from column statistics, and
   // partial tables can only be merged key by key if every rank packs alike.  The ranks agree on the statistics of the
   // key columns (min of minima, max of maxima / string lengths) with one small all-reduce before compiling.
-  if (ctx->nccl_comm && ctx->n_ranks > 1 && !a->keys.empty() && (rc = agree_key_stats(ctx, a, req))) return rc;
+  if (ctx->nccl_comm && ctx->n_ranks > 1 && !a->keys.empty()) {
+    bool changed = false;
+    if ((rc = agree_dictionaries(ctx, a, handles, &changed))) return rc;
+    if (changed) {  // columns were re-coded: their descriptions again
+      req = CompileRequest();
+      handles.clear();
+      if ((rc = build_request(ctx, a->table_id, prog, apply_mvcc, req, handles, &table_rows))) return rc;
+    }
+    if ((rc = agree_key_stats(ctx, a, req))) return rc;
+  }
   Plan& p = a->cr.plan;
   Geometry g;
   LeanPlan& lean = a->lean;
@@ -5139,9 +5251,6 @@ static int32_t agg_merge_impl(llkv_gpu_agg* a) {
   if (a->inner) return agg_merge_impl(a->inner);
   llkv_gpu_ctx* ctx = a->ctx;
   if (a->err_code) return set_error(a->err_code, "%s", a->err_msg.c_str());
-  if (ctx->n_ranks > 1)
-    for (const KeyLayout& kl : a->cr.keys)
-      if (kl.dict) return set_error(LLKV_ERR_INVALID_ARGUMENT, "GROUP BY keys of a dictionary-coded (long string) column do not merge across GPUs: every rank has its own dictionary");
   if (ctx->n_ranks > 1 && a->cr.plan.single_wide_key == 2)
     return set_error(LLKV_ERR_INVALID_ARGUMENT, "GROUP BY keys wider than 64 bits do not merge across GPUs: a group's key values are read from the shard that holds its first row");
   int32_t rc;

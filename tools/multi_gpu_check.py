@@ -12,6 +12,7 @@ import torch.distributed as dist
 
 import util
 from llkv_b200 import gpu, tpch
+from llkv_b200.expr import AggregateKind, AggregateSpec, DataType, Operator, pred
 from llkv_b200.table import HostColumn, HostTable
 from oracle import oracle
 
@@ -92,9 +93,34 @@ def main():
     want = oracle.aggregate(hc, None, tpch.highcard_aggregates(), None, (tpch.K_FIELD,), group_capacity=1 << 17)
     util.assert_same_result(got, want, 1e-12, ordered=False)
     small.destroy()
+    # GROUP BY over a Utf8 column with strings longer than 7 bytes: every rank interns its own shard's strings, rank 1 sees short
+    # ones only (a packed column until the ranks agree); the ranks exchange their dictionaries before the plan is compiled
+    long_words = ["DELIVER IN PERSON", "TAKE BACK RETURN", "COLLECT COD", "NONE", "AIR", "x"]
+    rng = np.random.default_rng(21)
+    m = 60_000
+    pick = rng.integers(0, len(long_words), m)
+    slo, shi = tpch.shard_range(m, world, rank, align=4096)
+    if world > 1:
+        r1lo, r1hi = tpch.shard_range(m, world, 1, align=4096)
+        pick[r1lo:r1hi] = 3 + pick[r1lo:r1hi] % 3  # rank 1: "NONE", "AIR", "x"
+    strs = [long_words[i] for i in pick]
+    vals = rng.integers(-100, 100, m, dtype=np.int64)
+    whole = HostTable(3).add(HostColumn.utf8(1, strs)).add(HostColumn(2, DataType.Int64, vals))
+    part = HostTable(3).add(HostColumn.utf8(1, strs[slo:shi])).add(HostColumn(2, DataType.Int64, vals[slo:shi].copy()))
+    sdt = from_host_at(ctx, part, slo)
+    sspecs = [AggregateSpec("c", AggregateKind.CountStar()), AggregateSpec("s", AggregateKind.Sum(2, DataType.Int64))]
+    sagg = gpu.Aggregation(sdt, sspecs, (1,), cardinality_hint=8)
+    flt = pred(1, Operator.GreaterThanOrEquals("COLLECT COD"))
+    sprog = gpu.Program(ctx, flt)
+    want = oracle.aggregate(whole, flt, sspecs, None, (1,))
+    for step in range(5):
+        sagg.execute(sprog, False, merge=True)
+        util.assert_same_result(sagg.finalize(16), want, 1e-12)
+    sagg.destroy()
+    sprog.destroy()
     dist.barrier()
     if rank == 0:
-        print(f"multi-GPU merge ok on {world} ranks: Q6 (also with tile lists), Q1 and a 40k-group hash aggregate (per-row and partitioned) match the oracle; "
+        print(f"multi-GPU merge ok on {world} ranks: Q6 (also with tile lists), Q1 and a 40k-group hash aggregate (per-row and partitioned) match the oracle; long-string group keys merge through agreed dictionaries; "
               f"execute() steps merge over peer mailboxes and replay as CUDA graphs", flush=True)
     ctx.comm_destroy()
     dist.destroy_process_group()
