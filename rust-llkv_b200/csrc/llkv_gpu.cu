@@ -4473,7 +4473,7 @@ static int32_t agg_resolve(llkv_gpu_agg* a) {
     }
     a->pending.active = false;
     if (flags & FLAG_BAD_PLAN) return agg_fail(a, LLKV_ERR_INTERNAL, "device interpreter met an unknown instruction");
-    if (flags & FLAG_MERGE_TIMEOUT) return agg_fail(a, LLKV_ERR_IO, "multi-GPU merge: a peer's partial state did not arrive within 10 s");
+    if (flags & FLAG_MERGE_TIMEOUT) return agg_fail(a, LLKV_ERR_IO, "multi-GPU merge: a peer's partial state did not arrive within 120 s");
     if (flags & FLAG_TYPE_ERROR) {
       for (const AggLayout& L : a->cr.aggs)
         if (L.raise_code) return agg_fail(a, L.raise_code, "%s", L.raise_message.c_str());

@@ -1029,7 +1029,8 @@ __global__ void merge_ungrouped_kernel(u64* dst, const u64* all_words, int n_ran
 // rank and merge.
 //   mailbox layout per rank: [source rank][merge parity][slot].  Two parities: a rank can be one merge ahead of a peer, never
 //   two (merge e+1 needs the peer's data of e+1, which the peer's stream writes after its merge e).  A peer that never
-//   arrives ends the wait after ~10 s with FLAG_MERGE_TIMEOUT.
+//   arrives ends the wait after kMergeWaitNs (120 s) with FLAG_MERGE_TIMEOUT.  The limit is long on purpose: ranks reach their
+//   first merge seconds apart when one of them compiles a kernel or pages the library in from a cold disk.
 struct PeerMailboxes {
   u64* box[8];
 };
@@ -1039,6 +1040,7 @@ __device__ __forceinline__ u64 ld_acquire_sys(const u64* p) {
   return v;
 }
 __device__ __forceinline__ void st_release_sys(u64* p, u64 v) { asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory"); }
+constexpr u64 kMergeWaitNs = 120000000000ull;
 __device__ __forceinline__ u64 global_timer_ns() {
   u64 t;
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
@@ -1079,7 +1081,7 @@ __global__ void __launch_bounds__(kMergePackets) merge_ungrouped_p2p_kernel(u64*
       const u64* src = &mine[((uint32_t)r * 2 + par) * kMergePackets + t];
       u64 pk = ld_volatile_u64(src);
       while ((uint32_t)(pk >> 32) != e32) {
-        if (global_timer_ns() - t0 > 10000000000ull) {
+        if (global_timer_ns() - t0 > kMergeWaitNs) {
           timed_out = 1;
           break;
         }
@@ -1182,7 +1184,7 @@ __global__ void __launch_bounds__(512) merge_grouped_p2p_kernel(GroupMergeArgs a
       const u64* flag = a.peers.box[a.rank] + (size_t)(tid * 2 + par) * a.slot_words;
       const u64 t0 = global_timer_ns();
       while (ld_acquire_sys(flag) != epoch) {
-        if (global_timer_ns() - t0 > 10000000000ull) {
+        if (global_timer_ns() - t0 > kMergeWaitNs) {
           atomicOr(&s_status, 1);
           break;
         }
