@@ -7,6 +7,7 @@
 #include <math.h>
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <map>
@@ -1864,12 +1865,19 @@ class Emitter {
     uint32_t nm = 0;  // plan columns whose NULLs make this value NULL
   };
 
+  // (LLKV_GPU_VERBOSE=2 names the line at which a plan left the lean lowering)
+  static bool lf_fail(int line) {
+    static const bool verbose = [] { const char* e = getenv("LLKV_GPU_VERBOSE"); return e && atoi(e) >= 2; }();
+    if (verbose && line < 0) fprintf(stderr, "[llkv] lean lowering gave up at interpreter op %d\n", -line);
+    else if (verbose) fprintf(stderr, "[llkv] lean lowering gave up at compiler.cpp:%d\n", line);
+    return false;
+  }
   bool lower_fast() {
     Plan& p = out_.plan;
-    if (wide_ || req_.bitmap_mode) return false;
-    if (plan_cols_.empty()) return false;  // nothing to stream (COUNT(*) without a filter): no tiles for the lean pipeline
+    if (wide_ || req_.bitmap_mode) return lf_fail(__LINE__);
+    if (plan_cols_.empty()) return lf_fail(__LINE__);  // nothing to stream (COUNT(*) without a filter): no tiles for the lean pipeline
     for (const ColumnMeta* c : plan_cols_) {
-      if (c->load_kind == LK_D128 && !c->dec_fits_i64) return false;
+      if (c->load_kind == LK_D128 && !c->dec_fits_i64) return lf_fail(__LINE__);
     }
     std::vector<FInstr> f;
     std::vector<Sym> st;
@@ -1883,6 +1891,11 @@ class Emitter {
         case LK_D128: return LKF_16;
         case LK_U8: return LKF_1;
         case LK_STR8: return LKF_S1;
+        case LK_I8: return LKF_1S;
+        case LK_I16: return LKF_2;
+        case LK_U16: return LKF_2U;
+        case LK_U32: return LKF_4U;
+        case LK_F32: return LKF_4F;
         default: ok = false; return LKF_8;
       }
     };
@@ -1963,7 +1976,7 @@ class Emitter {
     };
 
     // per-thread accumulator width of fast word w in the lean kernel (the widest any of its ops needs)
-    if (p.n_fast_words > (uint32_t)kLeanMaxWords) return false;
+    if (p.n_fast_words > (uint32_t)kLeanMaxWords) return lf_fail(__LINE__);
     for (uint32_t w = 0; w < p.n_fast_words; ++w) p.fast[w].lean_width = p.fast[w].lean_rowrel = 0;
     auto lean_word = [&](uint32_t w, uint8_t width, bool rowrel) {
       if (w >= p.n_fast_words) { ok = false; return; }
@@ -1989,9 +2002,9 @@ class Emitter {
           if (is_leaf) {
             const bool conjunct = i + 2 < n && code_[i + 2].op == OP_FILTER && mask_depth == 0;
             const Instr& pr = code_[i + 1];
-            if (pr.op == OP_PRED_F && c.load_kind != LK_F64 && c.load_kind != LK_F32) return false;
+            if (pr.op == OP_PRED_F && c.load_kind != LK_F64 && c.load_kind != LK_F32) return lf_fail(__LINE__);
             if (!conjunct) {
-              if (mask_depth >= 8) return false;
+              if (mask_depth >= 8) return lf_fail(__LINE__);
               ++mask_depth;
             }
             const uint32_t push = conjunct ? 0u : 1u;
@@ -2007,14 +2020,14 @@ class Emitter {
                 if (pr.op == OP_IN_D) {
                   const i128 v = (i128)(((u128)L.hi << 64) | (u128)L.lo);
                   if (!fits_i64(v)) {
-                    if (c.load_kind == LK_D128) return false;
+                    if (c.load_kind == LK_D128) return lf_fail(__LINE__);
                     continue;
                   }
                 }
                 run.push_back(mk_lit_i((i128)(int64_t)L.lo));
               }
-              if (c.load_kind == LK_D128 && !c.dec_fits_i64) return false;
-              if (lits_.size() + run.size() + 1 > (size_t)kMaxLits) return false;  // (+1: the kernel reads a (lo, hi) pair before it looks at g)
+              if (c.load_kind == LK_D128 && !c.dec_fits_i64) return lf_fail(__LINE__);
+              if (lits_.size() + run.size() + 1 > (size_t)kMaxLits) return lf_fail(__LINE__);  // (+1: the kernel reads a (lo, hi) pair before it looks at g)
               const uint32_t first = run.empty() ? 0u : add_lit_run(run);
               femit(FO_LEAF, in.a, map_load(in.b), first);
               f.back().g = 3u;
@@ -2069,7 +2082,7 @@ class Emitter {
               if (hi > kpinf) hi = kpinf;
               if (lo > hi) empty = true;
               std::vector<Lit> run = {mk_lit_i(empty ? 1 : lo), mk_lit_i(empty ? 0 : hi)};
-              if (lits_.size() + 2 > (size_t)kMaxLits) return false;
+              if (lits_.size() + 2 > (size_t)kMaxLits) return lf_fail(__LINE__);
               const uint32_t first = add_lit_run(run);
               femit(FO_LEAF, in.a, f32 ? (uint32_t)LKF_4 : (uint32_t)LKF_8, first);
               f.back().g = 2u;
@@ -2123,7 +2136,7 @@ class Emitter {
               if (empty) { a = mk_lit_i(1); b = mk_lit_i(0); }
               else { a = mk_lit_i(lo); b = mk_lit_i(hi); }
               std::vector<Lit> run = {a, b};
-              if (lits_.size() + 2 > (size_t)kMaxLits) return false;
+              if (lits_.size() + 2 > (size_t)kMaxLits) return lf_fail(__LINE__);
               const uint32_t first = add_lit_run(run);
               femit(FO_LEAF, in.a, map_load(in.b), first);
               f.back().g = uns ? 1u : 0u;
@@ -2143,7 +2156,7 @@ class Emitter {
           break;
         }
         case OP_PUSH_LIT: {
-          if (in.b) return false;
+          if (in.b) return lf_fail(__LINE__);
           const Lit& L = lits_[in.c];
           const i128 v = (i128)(((u128)L.hi << 64) | (u128)L.lo);
           Sym x;
@@ -2151,17 +2164,17 @@ class Emitter {
           x.lit = in.c;
           if (fits_i64(v)) x.iv = iv_exact(v);
           else if (L.hi == 0) x.iv = iv_exact((i128)(int64_t)L.lo);  // f64 bits / unsigned stored with hi = 0
-          else return false;
+          else return lf_fail(__LINE__);
           st.push_back(x);
           break;
         }
         case OP_POP:
-          if (st.empty()) return false;
+          if (st.empty()) return lf_fail(__LINE__);
           free_sym(st.back());
           st.pop_back();
           break;
         case OP_ADD_I: case OP_SUB_I: case OP_MUL_I: case OP_ADD_D: case OP_SUB_D: case OP_MUL_D: {
-          if (st.size() < 2) return false;
+          if (st.size() < 2) return lf_fail(__LINE__);
           const Iv b = st[st.size() - 1].iv, a = st[st.size() - 2].iv;
           const bool is_d = in.op == OP_ADD_D || in.op == OP_SUB_D || in.op == OP_MUL_D;
           const int k = (in.op == OP_ADD_I || in.op == OP_ADD_D) ? 0 : (in.op == OP_SUB_I || in.op == OP_SUB_D) ? 1 : 2;
@@ -2169,10 +2182,10 @@ class Emitter {
           uint8_t fb;
           if (iv_fits_i64(r)) fb = k == 0 ? FB_ADD : k == 1 ? FB_SUB : (iv_fits_i32(a) && iv_fits_i32(b) ? FB_MUL32 : FB_MUL);
           else if (is_d) fb = k == 0 ? FB_ADD_CK : k == 1 ? FB_SUB_CK : FB_MUL_CK;  // overflow -> rerun on the 128-bit interpreter
-          else return false;  // a real i64 overflow is an error with its own message: general interpreter
+          else return lf_fail(__LINE__);  // a real i64 overflow is an error with its own message: general interpreter
           // (a checked operation would also look at the garbage under a NULL: nullable operands keep to proven ranges)
           const uint32_t nm = st[st.size() - 1].nm | st[st.size() - 2].nm;
-          if (nm && (fb == FB_ADD_CK || fb == FB_SUB_CK || fb == FB_MUL_CK)) return false;
+          if (nm && (fb == FB_ADD_CK || fb == FB_SUB_CK || fb == FB_MUL_CK)) return lf_fail(__LINE__);
           emit_binary(fb);
           st.pop_back();
           st.back().where = Sym::ACC;
@@ -2181,7 +2194,7 @@ class Emitter {
           break;
         }
         case OP_ADD_F: case OP_SUB_F: case OP_MUL_F: {
-          if (st.size() < 2) return false;
+          if (st.size() < 2) return lf_fail(__LINE__);
           const uint32_t nm = st[st.size() - 1].nm | st[st.size() - 2].nm;
           emit_binary(in.op == OP_ADD_F ? FB_ADD_F : in.op == OP_SUB_F ? FB_SUB_F : FB_MUL_F);
           st.pop_back();
@@ -2192,14 +2205,14 @@ class Emitter {
           break;
         }
         case OP_CAST_D_DOWN: {
-          if (st.empty() || !st.back().iv.known || in.a > 18) return false;
+          if (st.empty() || !st.back().iv.known || in.a > 18) return lf_fail(__LINE__);
           const i128 d = pow10_i128(in.a);
           const Iv src = st.back().iv;
           Iv x = src;
           x.lo = round_div(x.lo, d);
           x.hi = round_div(x.hi, d);
           const i128 lim = in.b >= 39 ? ((i128)1 << 126) : pow10_i128(in.b);
-          if (!(x.lo > -lim && x.hi < lim)) return false;  // the precision check could turn a value into NULL
+          if (!(x.lo > -lim && x.hi < lim)) return lf_fail(__LINE__);  // the precision check could turn a value into NULL
           if (st.back().where == Sym::LIT) { fold_lit(st.back(), x.lo); break; }
           load_acc(st.size() - 1);
           femit(FO_DIVR, in.a, src.lo >= 0 ? (src.hi < ((i128)1 << 32) ? 2 : 1) : 0, 0);
@@ -2207,13 +2220,13 @@ class Emitter {
           break;
         }
         case OP_CAST_I_D: case OP_CAST_D_UP: case OP_RESCALE_DX: {
-          if (st.empty() || !st.back().iv.known || in.a > 18) return false;
-          if (in.op == OP_CAST_I_D && in.c) return false;
+          if (st.empty() || !st.back().iv.known || in.a > 18) return lf_fail(__LINE__);
+          if (in.op == OP_CAST_I_D && in.c) return lf_fail(__LINE__);
           const Iv r = iv_arith(2, st.back().iv, iv_exact(pow10_i128(in.a)));
-          if (!iv_fits_i64(r)) return false;
+          if (!iv_fits_i64(r)) return lf_fail(__LINE__);
           if (in.op != OP_RESCALE_DX) {
             const i128 lim = in.b >= 39 ? ((i128)1 << 126) : pow10_i128(in.b);
-            if (!(r.lo > -lim && r.hi < lim)) return false;
+            if (!(r.lo > -lim && r.hi < lim)) return lf_fail(__LINE__);
           }
           if (st.back().where == Sym::LIT) { fold_lit(st.back(), r.lo); break; }
           if (in.a) {
@@ -2224,13 +2237,13 @@ class Emitter {
           break;
         }
         case OP_CAST_I_I: {
-          if (st.empty()) return false;
+          if (st.empty()) return lf_fail(__LINE__);
           const int bits = in.a;
-          if (bits < 64 && !iv_fits(st.back().iv, -((i128)1 << (bits - 1)), ((i128)1 << (bits - 1)) - 1)) return false;
+          if (bits < 64 && !iv_fits(st.back().iv, -((i128)1 << (bits - 1)), ((i128)1 << (bits - 1)) - 1)) return lf_fail(__LINE__);
           break;
         }
         case OP_CAST_I_F: case OP_CAST_D_F: {
-          if (st.empty()) return false;
+          if (st.empty()) return lf_fail(__LINE__);
           load_acc(st.size() - 1);
           if (in.op == OP_CAST_I_F) femit(FO_I2F, 0, 0, 0);
           else femit(FO_D2F, 0, 0, in.c);
@@ -2239,21 +2252,21 @@ class Emitter {
           break;
         }
         case OP_AND: case OP_OR:
-          if (mask_depth < 2) return false;
+          if (mask_depth < 2) return lf_fail(__LINE__);
           femit(in.op == OP_AND ? FO_MASK_AND : FO_MASK_OR, 0, 0, 0);
           --mask_depth;
           break;
         case OP_NOT:
-          if (mask_depth < 1) return false;
+          if (mask_depth < 1) return lf_fail(__LINE__);
           femit(FO_MASK_NOT, 0, 0, 0);
           break;
         case OP_BOOL_LIT:
-          if (i >= select_end_ || mask_depth >= 8) return false;  // (also the accumulator of an IN list: not on this path)
+          if (i >= select_end_ || mask_depth >= 8) return lf_fail(__LINE__);  // (also the accumulator of an IN list: not on this path)
           femit(FO_MASK_LIT, in.a ? 1u : 0u, 0, 0);
           ++mask_depth;
           break;
         case OP_FILTER:
-          if (mask_depth != 1) return false;
+          if (mask_depth != 1) return lf_fail(__LINE__);
           femit(FO_MASK_FILTER, 0, 0, 0);
           mask_depth = 0;
           break;
@@ -2261,10 +2274,10 @@ class Emitter {
         case OP_SELECT_DONE: femit(FO_SELECT_DONE, 0, 0, 0); break;
         case OP_GROUP: {
           const int nk = in.a;
-          if ((int)st.size() < nk) return false;
+          if ((int)st.size() < nk) return lf_fail(__LINE__);
           for (int k = nk - 1; k >= 0; --k) {
             const Sym x = st.back();
-            if (x.where != Sym::COL || x.nm) return false;  // (a NULL key is its own group: general interpreter)
+            if (x.where != Sym::COL || x.nm) return lf_fail(__LINE__);  // (a NULL key is its own group: general interpreter)
             st.pop_back();
             p.key_col[k] = x.col;
             p.key_load[k] = (uint8_t)map_load(x.load);
@@ -2276,7 +2289,7 @@ class Emitter {
         case OP_AGG_FIRSTROW: femit(FO_FIRSTROW, 0, in.b, in.c); lean_word(in.b, 4, true); break;
         case OP_AGG_COUNT: case OP_AGG_SUM_I: case OP_AGG_SUM_D: case OP_AGG_FSUM: case OP_AGG_MIN_I: case OP_AGG_MAX_I:
         case OP_AGG_MIN_F: case OP_AGG_MAX_F: case OP_AGG_FIRSTVALID: case OP_AGG_FIRSTNAN: case OP_AGG_MIN_D: case OP_AGG_MAX_D: {
-          if (st.empty()) return false;
+          if (st.empty()) return lf_fail(__LINE__);
           uint8_t a = 0;
           uint16_t op;
           bool keep = (in.a & 1) != 0;
@@ -2287,7 +2300,7 @@ class Emitter {
               // Decimal128 MIN/MAX over values proven to sit strictly inside i64: the thread-private state is one
               // order-preserving u64 (its identity is then never a real value); the global state stays the 128-bit pair
               const Iv& v = st.back().iv;
-              if (!v.known || !(v.lo > (i128)INT64_MIN && v.hi < (i128)INT64_MAX)) return false;
+              if (!v.known || !(v.lo > (i128)INT64_MIN && v.hi < (i128)INT64_MAX)) return lf_fail(__LINE__);
               op = in.op == OP_AGG_MIN_D ? FO_MIN_I : FO_MAX_I;
               a = 0x80;
               break;
@@ -2333,11 +2346,11 @@ class Emitter {
           }
           break;
         }
-        default: return false;  // anything else (OR/NOT trees, IN lists, float leaves, divisions, 128-bit min/max, ...)
+        default: return lf_fail(-(int)in.op);  // anything else (OR/NOT trees, IN lists, float leaves, divisions, 128-bit min/max, ...)
       }
-      if (f.size() >= (size_t)kMaxFastInstr) return false;
+      if (f.size() >= (size_t)kMaxFastInstr) return lf_fail(__LINE__);
     }
-    if (!ok) return false;
+    if (!ok) return lf_fail(__LINE__);
     p.n_finstr = (uint32_t)f.size();
     p.fast_tmps = (uint32_t)max_tmps;
     for (size_t i = 0; i < f.size(); ++i) p.fcode[i] = f[i];

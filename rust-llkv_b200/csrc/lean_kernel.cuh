@@ -112,6 +112,10 @@ static __device__ __noinline__ u64 lean_row_key(const LeanPlan& p, const LeanSha
     i64 v;
     if (kind == LKF_S1) v = (i64)(((u64)base[idx] << 56) | 1ull);
     else if (kind == LKF_1) v = base[idx];
+    else if (kind == LKF_1S) v = reinterpret_cast<const signed char*>(base)[idx];
+    else if (kind == LKF_2) v = reinterpret_cast<const short*>(base)[idx];
+    else if (kind == LKF_2U) v = reinterpret_cast<const unsigned short*>(base)[idx];
+    else if (kind == LKF_4U) v = reinterpret_cast<const unsigned int*>(base)[idx];
     else if (kind == LKF_4) v = reinterpret_cast<const int*>(base)[idx];
     else if (kind == LKF_16) v = reinterpret_cast<const i64*>(base)[2 * idx];
     else v = reinterpret_cast<const i64*>(base)[idx];
@@ -227,6 +231,21 @@ struct LeanTile {
     } else if (kind == LKF_1) {
 #pragma unroll
       for (int r = 0; r < R; ++r) out[r] = base[r * NC + tid];
+    } else if (kind == LKF_1S) {
+#pragma unroll
+      for (int r = 0; r < R; ++r) out[r] = reinterpret_cast<const signed char*>(base)[r * NC + tid];
+    } else if (kind == LKF_2) {
+#pragma unroll
+      for (int r = 0; r < R; ++r) out[r] = reinterpret_cast<const short*>(base)[r * NC + tid];
+    } else if (kind == LKF_2U) {
+#pragma unroll
+      for (int r = 0; r < R; ++r) out[r] = reinterpret_cast<const unsigned short*>(base)[r * NC + tid];
+    } else if (kind == LKF_4U) {
+#pragma unroll
+      for (int r = 0; r < R; ++r) out[r] = reinterpret_cast<const unsigned int*>(base)[r * NC + tid];
+    } else if (kind == LKF_4F) {
+#pragma unroll
+      for (int r = 0; r < R; ++r) out[r] = lean_bits((double)reinterpret_cast<const float*>(base)[r * NC + tid]);
     } else {  // LKF_S1: one-byte strings as packed keys
 #pragma unroll
       for (int r = 0; r < R; ++r) out[r] = (i64)(((u64)base[r * NC + tid] << 56) | 1ull);

@@ -184,7 +184,11 @@ struct FInstr {  // lean-kernel instruction, pre-decoded (two 16-byte shared-mem
   uint32_t h;        // aggregates: bit c = the operand is NULL where plan column c is NULL (the row is then skipped)
 };
 // physical layouts the lean kernel reads (everything else stays on the general interpreter)
-enum FastLoad : uint32_t { LKF_4 = 0, LKF_8 = 1, LKF_16 = 2, LKF_1 = 3, LKF_S1 = 4 };
+enum FastLoad : uint32_t {
+  LKF_4 = 0, LKF_8 = 1, LKF_16 = 2, LKF_1 = 3, LKF_S1 = 4,  // i32 / 8 bytes / low half of 16 / u8 / one-byte string as a packed key
+  LKF_1S = 5, LKF_2 = 6, LKF_2U = 7, LKF_4U = 8,            // i8 / i16 / u16 / u32
+  LKF_4F = 9                                                // f32, widened to the f64 the arithmetic works in
+};
 
 struct Lit {
   unsigned long long lo, hi;
