@@ -70,6 +70,17 @@ pub const AGG_MAX: i32 = 5;
 pub const AGG_COUNT_NULLS: i32 = 6;
 
 // on-disk PrimType codes (llkv-column-map/src/serialization.rs:146-166)
+/// Bytes per value of the Arrow layout a `PrimType` crosses the boundary in (Boolean: one byte; Utf8: its int32 offsets).
+pub fn prim_type_width(prim_type: i32) -> usize {
+    match prim_type {
+        PT_INT8 | PT_UINT8 | PT_BOOLEAN => 1,
+        PT_INT16 | PT_UINT16 => 2,
+        PT_INT32 | PT_UINT32 | PT_FLOAT32 | PT_DATE32 | PT_UTF8 => 4,
+        PT_DECIMAL128 => 16,
+        _ => 8,
+    }
+}
+
 pub const PT_NULL: i32 = 0;
 pub const PT_UINT64: i32 = 1;
 pub const PT_INT32: i32 = 2;

@@ -70,6 +70,7 @@ impl Drop for Context {
 pub struct ResidentColumn {
     ctx: Arc<Context>,
     raw: *mut sys::llkv_gpu_column,
+    logical_field_id: u64,
 }
 unsafe impl Send for ResidentColumn {}
 
@@ -81,7 +82,7 @@ impl ResidentColumn {
                           precision: u8, scale: i8) -> Result<Self> {
         let mut raw = ptr::null_mut();
         check(unsafe { sys::llkv_gpu_column_register(ctx.raw, logical_field_id, prim_type, precision, scale, &mut raw) })?;
-        let col = Self { ctx: ctx.clone(), raw };
+        let col = Self { ctx: ctx.clone(), raw, logical_field_id };
         let get_one = |key: PhysicalKey| -> Result<P::Blob> {
             match pager.batch_get(&[BatchGet::Raw { key }])?.pop() {
                 Some(GetResult::Raw { bytes, .. }) => Ok(bytes),
@@ -124,7 +125,96 @@ impl ResidentColumn {
         check(unsafe { sys::llkv_gpu_column_rows(self.raw, &mut n) })?;
         Ok(n)
     }
+
+    /// The field id part of the column's `LogicalFieldId` (`llkv-types/src/ids.rs:133-152`: the low 32 bits).
+    pub fn field_id(&self) -> u32 {
+        self.logical_field_id as u32
+    }
+
+    /// Entries of the column's dictionary (a Utf8 column that holds strings longer than 7 bytes), 0 otherwise.
+    pub fn dict_size(&self) -> Result<u64> {
+        let mut n = 0u64;
+        check(unsafe { sys::llkv_gpu_column_dict_size(self.raw, &mut n) })?;
+        Ok(n)
+    }
+
+    /// The string behind a dictionary code (`llkv_group_key.dict == 1`).
+    pub fn dict_entry(&self, code: u64) -> Result<String> {
+        let (mut p, mut n) = (ptr::null(), 0u64);
+        check(unsafe { sys::llkv_gpu_column_dict_entry(self.raw, code, &mut p, &mut n) })?;
+        let bytes = if n == 0 { &[][..] } else { unsafe { std::slice::from_raw_parts(p, n as usize) } };
+        String::from_utf8(bytes.to_vec()).map_err(|e| Error::Internal(e.to_string()))
+    }
+
+    /// `GroupKeyValue` (`llkv-executor/src/lib.rs:99-106`) of one finalized key cell of this column.
+    pub fn group_key_value(&self, k: &sys::llkv_group_key) -> Result<GroupKey> {
+        if k.valid == 0 {
+            return Ok(GroupKey::Null);
+        }
+        Ok(match k.type_ {
+            flatten::PT_UTF8 if k.dict == 1 => GroupKey::String(self.dict_entry(k.bits)?),
+            flatten::PT_UTF8 => {
+                // packed short string: bytes big-endian from the top byte, length in the low byte
+                let n = (k.bits & 0xff) as usize;
+                let bytes: Vec<u8> = (0..n).map(|i| (k.bits >> (56 - 8 * i)) as u8).collect();
+                GroupKey::String(String::from_utf8(bytes).map_err(|e| Error::Internal(e.to_string()))?)
+            }
+            flatten::PT_BOOLEAN => GroupKey::Bool(k.bits != 0),
+            _ => GroupKey::Int(k.bits as i64),
+        })
+    }
+
+    /// `SortIndexOps::stage_build_for_chunk` for every chunk, on the device; the blobs go to the pager under
+    /// `ChunkMetadata.value_order_perm_pk` (`llkv-column-map/src/store/indexing/sort.rs:126-172`).
+    pub fn sort_index_blobs(&self, chunk_rows: u64) -> Result<Vec<Vec<u8>>> {
+        check(unsafe { sys::llkv_gpu_column_build_sort_index(self.raw, chunk_rows) })?;
+        let mut out = Vec::new();
+        for chunk in 0u64.. {
+            let mut len = 0u64;
+            match unsafe { sys::llkv_gpu_column_sort_index_blob(self.raw, chunk, ptr::null_mut(), 0, &mut len) } {
+                0 => {}
+                4 => break, // NotFound: past the last chunk
+                rc => check(rc)?,
+            }
+            let mut blob = vec![0u8; len as usize];
+            check(unsafe { sys::llkv_gpu_column_sort_index_blob(self.raw, chunk, blob.as_mut_ptr().cast(), len, &mut len) })?;
+            out.push(blob);
+        }
+        Ok(out)
+    }
+
+    /// `ColumnStore::scan(field, ScanOptions, visitor)` (`llkv-column-map/src/store/scan/mod.rs:191-1080`): `on_run` gets
+    /// each chunk's values (`None` = a null run) and row ids; sorted scans are sorted on the device.
+    pub fn scan<F>(&self, anchor: Option<&ResidentColumn>, options: &sys::llkv_scan_options, chunk_rows: u64, mut on_run: F) -> Result<()>
+    where
+        F: FnMut(i32, Option<&[u8]>, Option<&[u64]>, u64),
+    {
+        unsafe extern "C" fn trampoline<F: FnMut(i32, Option<&[u8]>, Option<&[u64]>, u64)>(
+            user: *mut c_void, prim_type: i32, values: *const c_void, row_ids: *const u64, n_rows: u64,
+        ) -> i32 {
+            let f = &mut *(user as *mut F);
+            let width = flatten::prim_type_width(prim_type);
+            let vals = if values.is_null() { None } else { Some(std::slice::from_raw_parts(values as *const u8, n_rows as usize * width)) };
+            let ids = if row_ids.is_null() { None } else { Some(std::slice::from_raw_parts(row_ids, n_rows as usize)) };
+            f(prim_type, vals, ids, n_rows);
+            0
+        }
+        check(unsafe {
+            sys::llkv_gpu_column_scan(self.raw, anchor.map_or(ptr::null_mut(), |a| a.raw), options, chunk_rows, Some(trampoline::<F>),
+                                      (&mut on_run as *mut F).cast())
+        })
+    }
 }
+
+/// `GroupKeyValue` (`llkv-executor/src/lib.rs:99-106`).
+#[derive(Clone, Debug, PartialEq, Eq, Hash)]
+pub enum GroupKey {
+    Null,
+    Int(i64),
+    Bool(bool),
+    String(String),
+}
+
 impl Drop for ResidentColumn {
     fn drop(&mut self) {
         unsafe { sys::llkv_gpu_column_destroy(self.raw) };
@@ -181,6 +271,10 @@ impl ResidentTable {
     }
     pub fn rows(&self) -> Result<u64> {
         self.columns.first().map_or(Ok(0), |c| c.rows())
+    }
+    /// The resident column of a field (group keys of dictionary-coded columns are resolved through it).
+    pub fn column(&self, field_id: u32) -> Option<&ResidentColumn> {
+        self.columns.iter().find(|c| c.field_id() == field_id)
     }
     /// `MvccRowIdFilter::new(txn_manager, snapshot)` (`llkv-transaction/src/helpers.rs:259-312`): the snapshot plus every
     /// transaction id whose `TxnIdManager::status` is Active or Aborted.  Without MVCC columns every row is visible

@@ -18,7 +18,7 @@ use llkv_types::FieldId;
 use simd_r_drive_entry_handle::EntryHandle;
 
 use crate::flatten::{self, FlatProgram};
-use crate::{Aggregation, Context, Program, ResidentTable};
+use crate::{Aggregation, Context, GroupKey, Program, ResidentTable};
 
 /// `LLKV_EXPR_ARROW` / `LLKV_EXPR_EXACT`: ungrouped aggregates type their arguments with the arrow kernels
 /// (`llkv-compute/src/eval.rs:565-614`), GROUP BY evaluates them per row with exact decimal arithmetic
@@ -151,5 +151,22 @@ impl GpuPath {
         let mut agg = Aggregation::new(ctx, table.table_id(), &query.specs, &query.nodes, &keys, query.expr_mode, query.cardinality_hint)?;
         agg.execute(program.as_ref(), snapshot.is_some(), 0, table.rows()?, true)?;
         agg.finalize()
+    }
+
+    /// The key tuple of every group as `GroupKeyValue`s (`llkv-executor/src/lib.rs:99-106`): dictionary-coded string keys are
+    /// resolved through their column's dictionary.
+    pub fn group_keys(table: &ResidentTable, query: &GpuQuery, keys: &[sys::llkv_group_key]) -> Result<Vec<Vec<GroupKey>>> {
+        let nk = query.group_by.len();
+        if nk == 0 {
+            return Ok(Vec::new());
+        }
+        keys.chunks(nk)
+            .map(|row| {
+                row.iter()
+                    .zip(&query.group_by)
+                    .map(|(k, field)| table.column(*field as u32).ok_or(Error::NotFound)?.group_key_value(k))
+                    .collect()
+            })
+            .collect()
     }
 }
