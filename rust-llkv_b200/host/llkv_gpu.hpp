@@ -17,6 +17,7 @@
 #include <memory>
 #include <stdexcept>
 #include <string>
+#include <type_traits>
 #include <utility>
 #include <vector>
 
@@ -125,6 +126,7 @@ struct Operator {
   int32_t tag = LLKV_OP_EQUALS;
   std::vector<Literal> literals;
   Bound lower, upper;
+  bool case_sensitive = true;  // StartsWith / EndsWith / Contains
   static Operator Equals(Literal v) { return Operator{LLKV_OP_EQUALS, {v}, {}, {}}; }
   static Operator Range(Bound lower, Bound upper) {
     Operator o{LLKV_OP_RANGE, {}, lower, upper};
@@ -137,6 +139,15 @@ struct Operator {
   static Operator LessThan(Literal v) { return Operator{LLKV_OP_LT, {v}, {}, {}}; }
   static Operator LessThanOrEquals(Literal v) { return Operator{LLKV_OP_LTE, {v}, {}, {}}; }
   static Operator In(std::vector<Literal> values) { return Operator{LLKV_OP_IN, std::move(values), {}, {}}; }
+  // Operator::{StartsWith, EndsWith, Contains} { pattern, case_sensitive } (llkv-expr/src/expr.rs:388-399)
+  static Operator StartsWith(const std::string& pattern, bool case_sensitive = true) { return pattern_op(LLKV_OP_STARTS_WITH, pattern, case_sensitive); }
+  static Operator EndsWith(const std::string& pattern, bool case_sensitive = true) { return pattern_op(LLKV_OP_ENDS_WITH, pattern, case_sensitive); }
+  static Operator Contains(const std::string& pattern, bool case_sensitive = true) { return pattern_op(LLKV_OP_CONTAINS, pattern, case_sensitive); }
+  static Operator pattern_op(int32_t tag, const std::string& pattern, bool case_sensitive) {
+    Operator o{tag, {Literal::String(pattern)}, {}, {}};
+    o.case_sensitive = case_sensitive;
+    return o;
+  }
   static Operator IsNull() { return Operator{LLKV_OP_IS_NULL, {}, {}, {}}; }
   static Operator IsNotNull() { return Operator{LLKV_OP_IS_NOT_NULL, {}, {}, {}}; }
 };
@@ -332,7 +343,8 @@ class ProgramCompiler {
     op.upper_kind = f.op.upper.kind;
     op.lit_begin = (int32_t)p.literals.size();
     op.lit_count = (int32_t)f.op.literals.size();
-    for (const Literal& l : f.op.literals) p.literals.push_back(l.c);
+    op.literal_bool = f.op.case_sensitive ? 0 : 1;
+    for (const Literal& l : f.op.literals) p.literals.push_back(l.c);  // (by-reference strings stay owned by the Expr tree)
     return op;
   }
   static void emit(const Expr& node, CompiledProgram& p) {
@@ -521,6 +533,43 @@ class Column {
     check(llkv_gpu_column_rows(h_, &n));
     return n;
   }
+  // ColumnStore::append with the row-id shadow column: rows land at (row id - first_row_id), an existing row id is overwritten
+  void append_rows(const void* values, const uint64_t* row_ids, uint64_t n_rows, uint64_t first_row_id = 0, const uint8_t* validity = nullptr) {
+    check(llkv_gpu_column_append_chunk(h_, next_pk_++, values, n_rows, validity, row_ids, first_row_id, nullptr));
+  }
+  void delete_rows(const std::vector<uint64_t>& row_ids) { check(llkv_gpu_column_delete_rows(h_, row_ids.data(), row_ids.size())); }
+  // page-locked sources may be reused after this returns
+  void flush() { check(llkv_gpu_column_flush(h_)); }
+  // the string behind a group key whose `dict` flag is set (columns holding strings longer than 7 bytes)
+  std::string dict_entry(uint64_t code) const {
+    const uint8_t* p = nullptr;
+    uint64_t n = 0;
+    check(llkv_gpu_column_dict_entry(h_, code, &p, &n));
+    return std::string(reinterpret_cast<const char*>(p), (size_t)n);
+  }
+  // ColumnStore::scan(field, ScanOptions, visitor): `visit(prim_type, values or nullptr (a null run), row ids or nullptr, rows)`
+  template <typename F>
+  void scan(const llkv_scan_options& options, F&& visit, const Column* anchor = nullptr, uint64_t chunk_rows = 0) {
+    auto tramp = [](void* user, int32_t prim_type, const void* values, const uint64_t* row_ids, uint64_t n) -> int32_t {
+      (*static_cast<typename std::remove_reference<F>::type*>(user))(prim_type, values, row_ids, n);
+      return 0;
+    };
+    check(llkv_gpu_column_scan(h_, anchor ? anchor->get() : nullptr, &options, chunk_rows, tramp, &visit));
+  }
+  // per-chunk value_order_perm blobs (SortIndexOps::stage_build_for_chunk), built on the device
+  std::vector<std::vector<uint8_t>> sort_index_blobs(uint64_t chunk_rows = 0) {
+    check(llkv_gpu_column_build_sort_index(h_, chunk_rows));
+    std::vector<std::vector<uint8_t>> out;
+    for (uint64_t chunk = 0;; ++chunk) {
+      uint64_t len = 0;
+      const int32_t rc = llkv_gpu_column_sort_index_blob(h_, chunk, nullptr, 0, &len);
+      if (rc == LLKV_ERR_NOT_FOUND) break;
+      check(rc);
+      out.emplace_back((size_t)len);
+      check(llkv_gpu_column_sort_index_blob(h_, chunk, out.back().data(), len, &len));
+    }
+    return out;
+  }
 
  private:
   llkv_gpu_column* h_ = nullptr;
@@ -568,6 +617,14 @@ class Aggregation {
     check(llkv_gpu_agg_run(h_, prog ? prog->get() : nullptr, apply_mvcc ? 1 : 0, row_begin, row_end));
   }
   void merge() { check(llkv_gpu_agg_merge(h_)); }
+  // one step: new states + scan + (multi-GPU) merge; replayed as a CUDA graph once it repeats unchanged
+  void execute(const Program* prog, bool apply_mvcc, uint64_t row_begin, uint64_t row_end, bool merge = true) {
+    check(llkv_gpu_agg_execute(h_, prog ? prog->get() : nullptr, apply_mvcc ? 1 : 0, row_begin, row_end, merge ? 1 : 0));
+  }
+  // HAVING / ORDER BY / OFFSET / LIMIT over the group rows (llkv-executor/src/lib.rs:5256-5355), applied at finalize
+  void set_output(const std::vector<llkv_having_term>& having, const std::vector<llkv_order_key>& order_by, uint64_t offset = 0, uint64_t limit = 0) {
+    check(llkv_gpu_agg_set_output(h_, having.data(), (int32_t)having.size(), order_by.data(), (int32_t)order_by.size(), offset, limit));
+  }
   std::vector<GroupRow> finalize(uint64_t group_capacity = 1) {
     std::vector<llkv_agg_value> vals(group_capacity * (n_aggs_ ? n_aggs_ : 1));
     std::vector<llkv_group_key> keys(group_capacity * (n_keys_ ? n_keys_ : 1));
