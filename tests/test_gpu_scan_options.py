@@ -128,3 +128,23 @@ def test_sorted_scan_of_a_narrowed_decimal_column(gpu_ctx):
         assert np.array_equal(np.concatenate(vals).reshape(-1, 2), decimal_from_i64(v[order]).reshape(-1, 2))
     finally:
         dc.destroy()
+
+
+@pytest.mark.parametrize("dtype,np_t,values,low,high", [
+    (DataType.Float64, np.float64, [12.5, -3.2, 45.6, 0.0, 18.75, 99.9, -42.1, 5.5, 18.75, 64.0, -0.01, 23.4], -10.0, 50.0),
+    (DataType.Float32, np.float32, [1.25, -8.5, 12.0, 3.5, 6.75, 42.125, -16.0, 3.5, 9.0, 15.5, 27.25, -0.5], -5.0, 20.0),
+], ids=["float64", "float32"])
+def test_reference_float_sorted_scan_and_ranges(gpu_ctx, dtype, np_t, values, low, high):
+    """float_scan_tests.rs:101-275 (`float64_sorted_scan_and_ranges`, `float32_sorted_scan_and_ranges`): the fixture values,
+    an ascending scan, and the inclusive range low..=high with values and with row ids."""
+    v = np.array(values, dtype=np_t)
+    dc = column(gpu_ctx, 85, 1, dtype, v)
+    try:
+        asc = flat(collect(dc, sorted=True)[0])
+        assert np.all(asc[:-1] <= asc[1:]) and len(asc) == len(v)
+        pairs = sorted(((x, i) for i, x in enumerate(v)), key=lambda p: (p[0], p[1]))
+        want = [(x, i) for x, i in pairs if low <= x <= high]
+        vals, ids = collect(dc, sorted=True, with_row_ids=True, lower=(np_t(low), True), upper=(np_t(high), True))
+        assert list(flat(vals)) == [x for x, _ in want] and list(flat(ids)) == [i for _, i in want]
+    finally:
+        dc.destroy()
