@@ -112,6 +112,7 @@ std::string shape_source(const LeanShape& s, int ctas_per_sm) {
        "  static constexpr bool kPartition = kJitShape.partition != 0;\n"
        "  static constexpr bool kPacked = kJitShape.partition == 2;\n"
        "  static constexpr bool kDefer = kJitShape.n_keys != 0 && (kJitShape.direct_global == 0 || kPartition);\n"
+       "  static constexpr bool kSplitSlow = kJitShape.n_keys != 0 && kJitShape.direct_global == 0 && !kPartition;\n"
        "  static constexpr int kStash = " << n_stash << ";\n"
        "};\n"
        "}  // namespace llkv\n"

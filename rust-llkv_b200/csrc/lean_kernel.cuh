@@ -41,6 +41,9 @@
 namespace llkv {
 
 #define LLKV_FULL 0xffffffffu
+// has_slow as a branch condition (inside LeanTile::step): SLOW is false in the copy of a specialised program that runs
+// after a GROUP instruction found a CTA-local slot for every row of the warp
+#define LLKV_SLOW_HERE (SLOW && has_slow)
 
 __device__ __forceinline__ double lean_f64(i64 v) { return __longlong_as_double(v); }
 __device__ __forceinline__ i64 lean_bits(double d) { return __double_as_longlong(d); }
@@ -172,6 +175,7 @@ struct LeanDynCfg {
   static constexpr bool kDefer = false;
   static constexpr bool kPartition = false;
   static constexpr bool kPacked = false;
+  static constexpr bool kSplitSlow = false;
   static constexpr int kStash = 1;
   static __host__ __device__ constexpr FInstr code(int) { return FInstr{}; }
   static __device__ __forceinline__ const LeanShape& shape(const LeanPlan& p) { return p.s; }
@@ -403,7 +407,7 @@ struct LeanTile {
     if constexpr (Cfg::kStatic && PC >= 0) return Cfg::code(PC).op == op;
     else return true;
   }
-  template <int PC>
+  template <int PC, bool SLOW = true>
   __device__ __forceinline__ bool step(const FInstr& in) {
     // optional operand pre-load fused into the instruction: acc = literal / column / temporary
     if (in.d == 2) load_col(in.e, in.f, acc);
@@ -416,6 +420,7 @@ struct LeanTile {
 #pragma unroll
       for (int r = 0; r < R; ++r) acc[r] = t[r * NC + tid];
     }
+    const unsigned ng = SLOW ? negm : 0u;  // (no row of the warp is in negm when the SLOW = false copy runs)
     switch (in.op) {
       case FO_LEAF: if constexpr (live<PC>(FO_LEAF)) {
         const i64 lo = p.lits[in.c], hi = p.lits[in.c + 1];
@@ -513,28 +518,37 @@ struct LeanTile {
           // creator passes iff cb <= snap (which excludes MAX) and cb is not listed; the deletion does not hide the row
           // iff db > snap (which includes MAX = never deleted) or db is listed.  Rows this transaction created / deleted
           // follow rules (1) and (5).
-          // Fast path per row slot of the warp: rows written by auto-commit and never deleted (created_by = 1,
+          // Fast path per pair of row slots of the warp: rows written by auto-commit and never deleted (created_by = 1,
           // deleted_by = MAX: all of a bulk-loaded table) are visible to every snapshot >= 1; when all 32 lanes hold
-          // such a row the rule is skipped.
+          // such rows the rule is skipped.  Otherwise the pair goes through the rule together, without branches: the
+          // list loop is kept rolled (the host lists only ids <= snapshot, usually none or one).
 #pragma unroll
-          for (int r = 0; r < R; ++r) {
-            const bool trivial = cb[r] == 1ull && db[r] == ~0ull;
+          for (int r0 = 0; r0 < R; r0 += 2) {
+            const int r1 = r0 + 1 < R ? r0 + 1 : r0;
+            const bool trivial = cb[r0] == 1ull && db[r0] == ~0ull && cb[r1] == 1ull && db[r1] == ~0ull;
             if (__all_sync(LLKV_FULL, trivial)) {
-              m |= (unsigned)(snap >= 1ull) << r;
+              m |= (snap >= 1ull ? (r1 != r0 ? 3u : 1u) : 0u) << r0;
               continue;
             }
-            bool c_listed = false, d_listed = false;  // created_by / deleted_by is a non-committed transaction
+            bool cl0 = false, dl0 = false, cl1 = false, dl1 = false;  // created_by / deleted_by is a non-committed transaction
+#pragma unroll 1
             for (uint32_t k = 0; k < p.n_noncommitted; ++k) {
               const u64 id = p.noncommitted[k];
-              c_listed = c_listed || cb[r] == id;
-              d_listed = d_listed || db[r] == id;
+              cl0 |= cb[r0] == id;
+              dl0 |= db[r0] == id;
+              cl1 |= cb[r1] == id;
+              dl1 |= db[r1] == id;
             }
-            const bool own_c = own_enabled && cb[r] == txn;
-            const bool own_d = own_enabled && db[r] == txn;
-            const bool c_ok = cb[r] <= snap && !c_listed;
-            const bool d_ok = db[r] > snap || d_listed;
-            const bool vis = !own_d && (own_c || (c_ok && d_ok));
-            m |= (unsigned)vis << r;
+            {
+              const bool own_c = own_enabled && cb[r0] == txn, own_d = own_enabled && db[r0] == txn;
+              const bool c_ok = cb[r0] <= snap && !cl0, d_ok = db[r0] > snap || dl0;
+              m |= (unsigned)(!own_d && (own_c || (c_ok && d_ok))) << r0;
+            }
+            if (r1 != r0) {
+              const bool own_c = own_enabled && cb[r1] == txn, own_d = own_enabled && db[r1] == txn;
+              const bool c_ok = cb[r1] <= snap && !cl1, d_ok = db[r1] > snap || dl1;
+              m |= (unsigned)(!own_d && (own_c || (c_ok && d_ok))) << r1;
+            }
           }
         } else {  // degenerate snapshot ids: the rule as written
 #pragma unroll
@@ -747,8 +761,8 @@ struct LeanTile {
       // per row (emit): at once when interpreted, deferred to the end of the tile when specialised (see flush()).
       case FO_COUNT_STAR: case FO_COUNT: if constexpr (live<PC>(FO_COUNT_STAR) || live<PC>(FO_COUNT)) {
         const unsigned lv = in.h ? (actm & valid_mask(in.h)) : actm;  // rows whose operand is not NULL
-        if (has_slow) slow_rows(in.op, in.a, negm & lv, in.c);
-        const unsigned okm = lv & ~negm;
+        if (LLKV_SLOW_HERE) slow_rows(in.op, in.a, ng & lv, in.c);
+        const unsigned okm = lv & ~ng;
         const LeanWord lw = S.words[in.b];
         if (!grouped) {
           const unsigned c = __popc(okm);
@@ -771,8 +785,8 @@ struct LeanTile {
             if (d == d) setm &= ~(1u << r);
           }
         }
-        if (has_slow) slow_rows(in.op, in.a, setm & negm, in.c);
-        setm &= ~negm;
+        if (LLKV_SLOW_HERE) slow_rows(in.op, in.a, setm & ng, in.c);
+        setm &= ~ng;
         u64 none[R];
 #pragma unroll
         for (int r = 0; r < R; ++r) none[r] = 0;
@@ -782,17 +796,17 @@ struct LeanTile {
       case FO_SUM: if constexpr (live<PC>(FO_SUM)) {
         const uint32_t cls = in.a & 3;  // 0: check each value
         const unsigned lv = in.h ? (actm & valid_mask(in.h)) : actm;  // rows whose operand is not NULL
-        unsigned fastm = lv & ~negm;
+        unsigned fastm = lv & ~ng;
         if (cls == 0 && !Cfg::kPartition) {  // (tuples carry the full value; the table update is exact for any i64)
           unsigned bigm = 0;
 #pragma unroll
           for (int r = 0; r < R; ++r)
             if (!(acc[r] < ((i64)1 << 47) && acc[r] > -((i64)1 << 47))) bigm |= 1u << r;
           bigm &= lv;
-          slow_rows(FO_SUM, in.a, bigm | (negm & lv), in.c);
+          slow_rows(FO_SUM, in.a, bigm | (ng & lv), in.c);
           fastm &= ~bigm;
-        } else if (has_slow) {
-          slow_rows(FO_SUM, in.a, negm & lv, in.c);
+        } else if (LLKV_SLOW_HERE) {
+          slow_rows(FO_SUM, in.a, ng & lv, in.c);
         }
         const LeanWord lw = S.words[in.b];
         if (!grouped) {
@@ -812,8 +826,8 @@ struct LeanTile {
       }
       case FO_FSUM: if constexpr (live<PC>(FO_FSUM)) {
         const unsigned lv = in.h ? (actm & valid_mask(in.h)) : actm;
-        if (has_slow) slow_rows(FO_FSUM, in.a, negm & lv, in.c);
-        const unsigned okm = lv & ~negm;
+        if (LLKV_SLOW_HERE) slow_rows(FO_FSUM, in.a, ng & lv, in.c);
+        const unsigned okm = lv & ~ng;
         const LeanWord lw = S.words[in.b];
         if (!grouped) {
           double x = 0.0;
@@ -842,8 +856,8 @@ struct LeanTile {
             e[r] = enc_f64(d);
           } else e[r] = enc_i64(acc[r]);
         }
-        if (has_slow) slow_rows(in.op, in.a, setm & negm, in.c);
-        setm &= ~negm;
+        if (LLKV_SLOW_HERE) slow_rows(in.op, in.a, setm & ng, in.c);
+        setm &= ~ng;
         emit<PC>(in, setm, e);  // also the ungrouped case: soff[] is zero
         return true;
       }
@@ -1200,12 +1214,22 @@ struct LeanTile {
   }
 
   // specialised: one instantiation of step() per program position, the instruction is a compile-time constant
-  template <int PC>
+  // Grouped plans with CTA-local slots (kSplitSlow): the instructions after GROUP exist twice.  A warp whose rows all
+  // found a slot (every tile of a low-cardinality GROUP BY after the first few) runs the copy without the per-aggregate
+  // "rows for the global table?" branches: one branch per tile instead of one taken branch over cold code per aggregate.
+  template <int PC, bool SLOW = true>
   __device__ __forceinline__ void run_static() {
     if constexpr (Cfg::kStatic) {
       constexpr FInstr in = Cfg::code(PC);
-      if (!step<PC>(in)) return;
-      if constexpr (in.op != FO_END && PC + 1 < kMaxFastInstr) run_static<PC + 1>();
+      if (!step<PC, SLOW>(in)) return;
+      if constexpr (in.op != FO_END && PC + 1 < kMaxFastInstr) {
+        if constexpr (in.op == FO_GROUP && Cfg::kSplitSlow) {
+          if (has_slow) run_static<PC + 1, true>();
+          else run_static<PC + 1, false>();
+        } else {
+          run_static<PC + 1, SLOW>();
+        }
+      }
     }
   }
   // interpreted: the next instruction is fetched early so the constant-cache latency overlaps this instruction's work

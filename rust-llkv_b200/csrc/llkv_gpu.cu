@@ -3005,10 +3005,12 @@ static int32_t lean_geometry(const LeanTune& tn, const Plan& p, uint64_t row_beg
   s.has_exists = p.exists_bits ? 1u : 0u;
   lp.txn_id = p.txn_id;
   lp.snapshot_id = p.snapshot_id;
-  // TXN_ID_AUTO_COMMIT (1) is always committed (llkv-transaction/src/mvcc.rs:157-171): never listed for the kernel
+  // TXN_ID_AUTO_COMMIT (1) is always committed (llkv-transaction/src/mvcc.rs:157-171): never listed for the kernel.
+  // Neither are ids above the snapshot: a row created by one fails created_by <= snapshot whether or not the id is
+  // listed, and a deletion by one passes deleted_by > snapshot either way.
   lp.n_noncommitted = 0;
   for (uint32_t i = 0; i < p.n_noncommitted; ++i)
-    if (p.noncommitted[i] != 1ull) lp.noncommitted[lp.n_noncommitted++] = p.noncommitted[i];
+    if (p.noncommitted[i] != 1ull && p.noncommitted[i] <= p.snapshot_id) lp.noncommitted[lp.n_noncommitted++] = p.noncommitted[i];
   s.n_keys = p.n_keys;
   s.single_wide_key = p.single_wide_key;
   for (int k = 0; k < kMaxKeys; ++k) {
