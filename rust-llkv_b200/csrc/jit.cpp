@@ -95,6 +95,9 @@ std::string shape_source(const LeanShape& s, int ctas_per_sm) {
   for (uint32_t i = 0; i < s.n_code && i < (uint32_t)kMaxFastInstr; ++i)
     if (s.code[i].op >= FO_COUNT_STAR && s.code[i].op <= FO_FIRSTNAN) ++n_stash;
   if (n_stash == 0) n_stash = 1;
+  int n_tmps = 1;  // temporaries live in registers in a specialised build (LeanTile::treg)
+  for (uint32_t i = 0; i < (uint32_t)kMaxFastInstr && s.code[i].op != FO_END; ++i)
+    if (s.code[i].op == FO_ST_TMP && (int)s.code[i].a + 1 > n_tmps) n_tmps = (int)s.code[i].a + 1;
   std::ostringstream o;
   o << "#include \"lean_kernel.cuh\"\n"
        "namespace llkv {\n"
@@ -114,6 +117,7 @@ std::string shape_source(const LeanShape& s, int ctas_per_sm) {
        "  static constexpr bool kDefer = kJitShape.n_keys != 0 && (kJitShape.direct_global == 0 || kPartition);\n"
        "  static constexpr bool kSplitSlow = kJitShape.n_keys != 0 && kJitShape.direct_global == 0 && !kPartition;\n"
        "  static constexpr int kStash = " << n_stash << ";\n"
+       "  static constexpr int kTmps = " << n_tmps << ";\n"
        "};\n"
        "}  // namespace llkv\n"
        "extern \"C\" __global__ void __launch_bounds__("

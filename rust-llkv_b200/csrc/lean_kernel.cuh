@@ -177,6 +177,7 @@ struct LeanDynCfg {
   static constexpr bool kPacked = false;
   static constexpr bool kSplitSlow = false;
   static constexpr int kStash = 1;
+  static constexpr int kTmps = 1;
   static __host__ __device__ constexpr FInstr code(int) { return FInstr{}; }
   static __device__ __forceinline__ const LeanShape& shape(const LeanPlan& p) { return p.s; }
 };
@@ -208,6 +209,7 @@ struct LeanTile {
   // specialised + grouped: operands / row masks of the tile's aggregate instructions, applied by flush()
   u64 stash_v[Cfg::kStash][R];
   unsigned stash_m[Cfg::kStash];
+  i64 treg[Cfg::kTmps][R];  // specialised: the program's temporaries (a thread only ever reads its own rows' entries)
   u64 pk[Cfg::kPartition ? R : 1];  // partitioned plans: the rows' packed keys, kept from GROUP to scatter()
   unsigned char* const part_smem;
   uint32_t batch_tiles = 0;         // packed form: tiles appended to the batch buffer since the last flush
@@ -416,9 +418,15 @@ struct LeanTile {
 #pragma unroll
       for (int r = 0; r < R; ++r) acc[r] = v;
     } else if (in.d == 3) {
-      const i64* t = tmp_base + (size_t)in.e * T;
+      if constexpr (Cfg::kStatic && PC >= 0) {
+        constexpr uint32_t slot = Cfg::code(PC).e;
 #pragma unroll
-      for (int r = 0; r < R; ++r) acc[r] = t[r * NC + tid];
+        for (int r = 0; r < R; ++r) acc[r] = treg[slot][r];
+      } else {
+        const i64* t = tmp_base + (size_t)in.e * T;
+#pragma unroll
+        for (int r = 0; r < R; ++r) acc[r] = t[r * NC + tid];
+      }
     }
     const unsigned ng = SLOW ? negm : 0u;  // (no row of the warp is in negm when the SLOW = false copy runs)
     switch (in.op) {
@@ -631,13 +639,25 @@ struct LeanTile {
           // footprint of an eight-slot table, which is what bounds the resident warps of a grouped plan.
           const ulonglong2 k01 = *reinterpret_cast<const ulonglong2*>(&tbl[0]);
           const ulonglong2 k23 = *reinterpret_cast<const ulonglong2*>(&tbl[2]);
+          // packed keys of at most 31 bits: the low halves decide (a free entry's low half is all ones, no such key has it)
+          uint32_t kb_total = 0;
+#pragma unroll
+          for (uint32_t k = 0; k < (uint32_t)kMaxKeys; ++k)
+            if (k < S.n_keys) kb_total += S.key_bits[k];
+          const bool narrow = S.single_wide_key == 0 && kb_total <= 31;
 #pragma unroll
           for (int r = 0; r < R; ++r) {
             const u64 K = keys[r];
-            const bool h0 = K == k01.x, h1 = K == k01.y, h2 = K == k23.x, h3 = K == k23.y;
+            bool h0, h1, h2, h3;
+            if (narrow) {
+              const uint32_t k32 = (uint32_t)K;
+              h0 = k32 == (uint32_t)k01.x, h1 = k32 == (uint32_t)k01.y, h2 = k32 == (uint32_t)k23.x, h3 = k32 == (uint32_t)k23.y;
+            } else {
+              h0 = K == k01.x, h1 = K == k01.y, h2 = K == k23.x, h3 = K == k23.y;
+            }
             const uint32_t sl = h0 ? 0u : h1 ? 1u : h2 ? 2u : 3u;
             soff[r] = sl * S.slot_stride;
-            if (!((h0 || h1 || h2 || h3) && K != kEmptyKey) && ((actm >> r) & 1u)) miss |= 1u << r;
+            if (!((h0 || h1 || h2 || h3) && (narrow || K != kEmptyKey)) && ((actm >> r) & 1u)) miss |= 1u << r;
           }
         } else {
           // Probe without branches: the key's home pair of slots (two adjacent entries, one 16-byte read).  Probe order
@@ -689,9 +709,15 @@ struct LeanTile {
 
       case FO_LD_COL: case FO_LD_LIT: case FO_LD_TMP: return true;  // the pre-load above is the whole instruction
       case FO_ST_TMP: if constexpr (live<PC>(FO_ST_TMP)) {
-        i64* t = tmp_base + (size_t)in.a * T;
+        if constexpr (Cfg::kStatic && PC >= 0) {
+          constexpr uint32_t slot = Cfg::code(PC).a;
 #pragma unroll
-        for (int r = 0; r < R; ++r) t[r * NC + tid] = acc[r];
+          for (int r = 0; r < R; ++r) treg[slot][r] = acc[r];
+        } else {
+          i64* t = tmp_base + (size_t)in.a * T;
+#pragma unroll
+          for (int r = 0; r < R; ++r) t[r * NC + tid] = acc[r];
+        }
         return true;
       }
       case FO_OP_COL: if constexpr (live<PC>(FO_OP_COL)) {
@@ -710,9 +736,15 @@ struct LeanTile {
       }
       case FO_OP_TMP: if constexpr (live<PC>(FO_OP_TMP)) {
         i64 v[R];
-        const i64* t = tmp_base + (size_t)in.b * T;
+        if constexpr (Cfg::kStatic && PC >= 0) {
+          constexpr uint32_t slot = Cfg::code(PC).b;
 #pragma unroll
-        for (int r = 0; r < R; ++r) v[r] = t[r * NC + tid];
+          for (int r = 0; r < R; ++r) v[r] = treg[slot][r];
+        } else {
+          const i64* t = tmp_base + (size_t)in.b * T;
+#pragma unroll
+          for (int r = 0; r < R; ++r) v[r] = t[r * NC + tid];
+        }
         binop(in.a, v);
         return true;
       }
