@@ -1909,7 +1909,7 @@ class Emitter {
       // a pending "acc = ..." load folds into the instruction that consumes it
       if (!f.empty() && (f.back().op == FO_LD_COL || f.back().op == FO_LD_LIT || f.back().op == FO_LD_TMP) && op != FO_LEAF &&
           op != FO_MVCC && op != FO_SELECT_DONE && op != FO_GROUP && op != FO_END && op != FO_LD_COL && op != FO_LD_LIT &&
-          op != FO_LD_TMP && op != FO_COUNT_STAR && op != FO_FIRSTROW && op < FO_VALID) {
+          op != FO_LD_TMP && op != FO_COUNT_STAR && op != FO_FIRSTROW && (op < FO_VALID || op == FO_CMP)) {
         in.d = f.back().d;
         in.e = f.back().e;
         in.f = f.back().f;
@@ -2251,6 +2251,36 @@ class Emitter {
           st.back().iv.is_float = true;
           break;
         }
+        case OP_CMP_I: case OP_CMP_U: case OP_CMP_F: case OP_CMP_D: {
+          // compute_compare over two scalar expressions: both sides are exact 64-bit images here (anything wider left the
+          // lowering earlier), so the comparison is one of bit patterns; the result goes onto the predicate-mask stack
+          if (i >= select_end_ || st.size() < 2 || mask_depth >= 8 || in.a > LLKV_CMP_GE) return lf_fail(__LINE__);
+          const size_t n2 = st.size();
+          uint32_t cmp = in.a;
+          const Sym* other;
+          if (st[n2 - 2].where == Sym::ACC) other = &st[n2 - 1];
+          else if (st[n2 - 1].where == Sym::ACC) {  // operand cmp acc: the mirrored comparison of acc with the operand
+            static const uint8_t mirrored[6] = {LLKV_CMP_EQ, LLKV_CMP_NE, LLKV_CMP_GT, LLKV_CMP_GE, LLKV_CMP_LT, LLKV_CMP_LE};
+            other = &st[n2 - 2];
+            cmp = mirrored[cmp];
+          } else {
+            load_acc(n2 - 2);
+            other = &st[n2 - 1];
+          }
+          if (!ok) return lf_fail(__LINE__);
+          const uint32_t kind = in.op == OP_CMP_U ? 1u : in.op == OP_CMP_F ? 2u : 0u;
+          const uint32_t nm = st[n2 - 1].nm | st[n2 - 2].nm;
+          if (other->where == Sym::COL) femit(FO_CMP, cmp | (kind << 4), 0u | (map_load(other->load) << 8), other->col);
+          else if (other->where == Sym::LIT) femit(FO_CMP, cmp | (kind << 4), 1u, other->lit);
+          else femit(FO_CMP, cmp | (kind << 4), 2u, other->tmp);
+          f.back().h = nm;
+          free_sym(st[n2 - 1]);
+          free_sym(st[n2 - 2]);
+          st.pop_back();
+          st.pop_back();
+          ++mask_depth;
+          break;
+        }
         case OP_AND: case OP_OR:
           if (mask_depth < 2) return lf_fail(__LINE__);
           femit(in.op == OP_AND ? FO_MASK_AND : FO_MASK_OR, 0, 0, 0);
@@ -2277,7 +2307,10 @@ class Emitter {
           if ((int)st.size() < nk) return lf_fail(__LINE__);
           for (int k = nk - 1; k >= 0; --k) {
             const Sym x = st.back();
-            if (x.where != Sym::COL || x.nm) return lf_fail(__LINE__);  // (a NULL key is its own group: general interpreter)
+            if (x.where != Sym::COL) return lf_fail(__LINE__);
+            // a NULL key value is its own group: packed keys carry a null bit per nullable key; the single wide integer
+            // key (a separate NULL row) and hashed keys stay on the general interpreter
+            if (x.nm && (p.single_wide_key || !p.key_nullable[k])) return lf_fail(__LINE__);
             st.pop_back();
             p.key_col[k] = x.col;
             p.key_load[k] = (uint8_t)map_load(x.load);

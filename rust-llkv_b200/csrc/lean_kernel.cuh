@@ -132,8 +132,16 @@ static __device__ __noinline__ u64 lean_row_key(const LeanPlan& p, const LeanSha
     }
     if (S.single_wide_key == 2) K = key_hash_step(k == 0 ? key_hash_init() : K, (u64)v, false);
     else if (S.single_wide_key) K = (u64)v;
-    else K |= (bits == 64 ? f : (f & ((1ull << bits) - 1))) << shift;
-    shift += bits;
+    else {
+      bool is_null = false;
+      if (S.key_nullable[k] && S.cols[S.key_col[k]].has_valid) {
+        const uint32_t* w = reinterpret_cast<const uint32_t*>(sb + S.cols[S.key_col[k]].vsmem_off);
+        is_null = !((w[idx >> 5] >> (idx & 31)) & 1u);
+      }
+      if (!is_null) K |= (bits == 64 ? f : (f & ((1ull << bits) - 1))) << shift;
+      if (S.key_nullable[k]) K |= (u64)is_null << (shift + bits);
+    }
+    shift += bits + (S.single_wide_key == 0 && S.key_nullable[k] ? 1 : 0);
   }
   return S.single_wide_key == 2 ? key_hash_done(K) : K;
 }
@@ -342,14 +350,18 @@ struct LeanTile {
         const bool is_str = S.key_kind[k] == KK_STR;
         const int L = (int)S.key_strlen[k];
         const u64 mask = bits == 64 ? ~0ull : ((1ull << bits) - 1);
+        // nullable packed key: field 0 and the null bit set where the value is NULL
+        const bool nullable = S.single_wide_key == 0 && S.key_nullable[k] != 0;
+        const unsigned valid = nullable && S.cols[S.key_col[k]].has_valid ? col_valid(S.key_col[k]) : (1u << R) - 1u;
 #pragma unroll
         for (int r = 0; r < R; ++r) {
           const u64 f = is_str ? ((L ? (((u64)v[r] >> (64 - 8 * L)) << 3) : 0ull) | ((u64)v[r] & 7ull)) : (u64)v[r] - kmin;
           if (S.single_wide_key == 2) keys[r] = key_hash_step(k == 0 ? key_hash_init() : keys[r], (u64)v[r], false);
           else if (S.single_wide_key) keys[r] = (u64)v[r];
+          else if (nullable) keys[r] |= ((valid >> r) & 1u) ? (f & mask) << shift : 1ull << (shift + bits);
           else keys[r] |= (f & mask) << shift;
         }
-        shift += bits;
+        shift += bits + (nullable ? 1 : 0);
       }
     }
     if (S.single_wide_key == 2) {
@@ -643,7 +655,7 @@ struct LeanTile {
           uint32_t kb_total = 0;
 #pragma unroll
           for (uint32_t k = 0; k < (uint32_t)kMaxKeys; ++k)
-            if (k < S.n_keys) kb_total += S.key_bits[k];
+            if (k < S.n_keys) kb_total += S.key_bits[k] + (S.key_nullable[k] ? 1u : 0u);
           const bool narrow = S.single_wide_key == 0 && kb_total <= 31;
 #pragma unroll
           for (int r = 0; r < R; ++r) {
@@ -903,6 +915,52 @@ struct LeanTile {
         } else {
           actm &= in.b ? ~v : v;
         }
+        return true;
+      }
+      case FO_CMP: if constexpr (live<PC>(FO_CMP)) {
+        // compute_compare (llkv-compute/src/kernels.rs:269-297) on the 64-bit images; a NULL on either side is NULL
+        i64 v[R];
+        const uint32_t src = in.b & 0xffu;
+        if (src == 0) load_col(in.c, in.b >> 8, v);
+        else if (src == 1) {
+          const i64 l = p.lits[in.c];
+#pragma unroll
+          for (int r = 0; r < R; ++r) v[r] = l;
+        } else {
+          if constexpr (Cfg::kStatic && PC >= 0) {
+            constexpr uint32_t slot = Cfg::code(PC).c;
+#pragma unroll
+            for (int r = 0; r < R; ++r) v[r] = treg[slot < (uint32_t)Cfg::kTmps ? slot : 0][r];
+          } else {
+            const i64* t = tmp_base + (size_t)in.c * T;
+#pragma unroll
+            for (int r = 0; r < R; ++r) v[r] = t[r * NC + tid];
+          }
+        }
+        const uint32_t cmp = in.a & 0xfu, kind = in.a >> 4;
+        unsigned m = 0;
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+          bool lt, eq;
+          if (kind == 1) {
+            lt = (u64)acc[r] < (u64)v[r];
+            eq = acc[r] == v[r];
+          } else if (kind == 2) {
+            const i64 a = f64_total_key(lean_f64(acc[r])), b = f64_total_key(lean_f64(v[r]));
+            lt = a < b;
+            eq = a == b;
+          } else {
+            lt = acc[r] < v[r];
+            eq = acc[r] == v[r];
+          }
+          const bool res = cmp == 0 ? eq : cmp == 1 ? !eq : cmp == 2 ? lt : cmp == 3 ? (lt || eq) : cmp == 4 ? !(lt || eq) : !lt;
+          m |= (unsigned)res << r;
+        }
+        const unsigned all = (1u << R) - 1u;
+        const unsigned valid = in.h ? valid_mask(in.h) : all;
+        mt[msp] = m & valid;
+        mn[msp] = ~valid & all;
+        ++msp;
         return true;
       }
       case FO_MASK_AND: case FO_MASK_OR: if constexpr (live<PC>(FO_MASK_AND) || live<PC>(FO_MASK_OR)) {

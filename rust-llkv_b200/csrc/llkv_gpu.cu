@@ -3019,6 +3019,7 @@ static int32_t lean_geometry(const LeanTune& tn, const Plan& p, uint64_t row_beg
     s.key_strlen[k] = p.key_strlen[k];
     s.key_col[k] = p.key_col[k];
     s.key_load[k] = p.key_load[k];
+    s.key_nullable[k] = p.key_nullable[k];
     lp.key_min[k] = p.key_min[k];
   }
   s.n_words = p.n_fast_words;
@@ -3241,7 +3242,7 @@ static const char* fast_op_name(uint32_t op) {
   static const char* names[] = {"END", "LEAF", "MVCC", "SELECT_DONE", "GROUP", "LD_COL", "LD_LIT", "LD_TMP", "ST_TMP", "OP_COL", "OP_LIT",
                                 "OP_TMP", "DIVR", "MULP", "I2F", "D2F", "COUNT_STAR", "COUNT", "FIRSTROW", "SUM", "FSUM", "MIN_I", "MAX_I",
                                 "MIN_F", "MAX_F", "FIRSTVALID", "FIRSTNAN", "VALID", "MASK_AND", "MASK_OR", "MASK_NOT", "MASK_LIT",
-                                "MASK_FILTER"};
+                                "MASK_FILTER", "CMP"};
   return op < sizeof(names) / sizeof(names[0]) ? names[op] : "?";
 }
 static std::string lean_listing(const LeanPlan& lp, const Geometry& g, uint32_t ctas) {

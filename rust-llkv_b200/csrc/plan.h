@@ -118,6 +118,10 @@ enum FastOp : uint16_t {
   FO_MASK_NOT,    // rows = domain - rows
   FO_MASK_LIT,    // a = 0 / 1: push a constant, determined on every row
   FO_MASK_FILTER, // pop: active &= rows
+  FO_CMP,         // general comparison of two scalar expressions (compute_compare, llkv-compute/src/kernels.rs:269-297): push
+                  // (acc cmp operand) onto the predicate-mask stack.  a = LLKV_CMP_* | kind << 4 (0 signed, 1 unsigned, 2 f64
+                  // by total order); b = operand source (0 column c, 1 literal c, 2 tmp c) | FastLoad << 8; h = plan columns
+                  // whose NULLs make the comparison NULL (neither selected nor in the domain of a NOT)
   FO_COUNT_
 };
 #if defined(__CUDACC__) || defined(__CUDACC_RTC__)
@@ -292,6 +296,7 @@ struct LeanShape {
   LeanCol cols[kMaxCols];
   LeanWord words[kLeanMaxWords];
   uint32_t key_bits[kMaxKeys], key_kind[kMaxKeys], key_strlen[kMaxKeys], key_col[kMaxKeys], key_load[kMaxKeys];
+  uint32_t key_nullable[kMaxKeys];  // packed keys: the field is followed by a null bit (a NULL key value is its own group)
   uint32_t n_code, n_cols, n_words, n_gwords, n_keys, single_wide_key;
   uint32_t direct_global;  // high-cardinality GROUP BY: no CTA-local slots, every selected row updates the global table
   uint32_t nc;           // consumer threads per CTA

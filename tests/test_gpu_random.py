@@ -5,7 +5,7 @@ import numpy as np
 import pytest
 
 import util
-from llkv_b200.expr import AggregateKind, AggregateSpec, Bound, DataType, Expr, Literal, Operator, ScalarExpr, pred
+from llkv_b200.expr import AggregateKind, AggregateSpec, Bound, CompareOp, DataType, Expr, Literal, Operator, ScalarExpr, pred
 from llkv_b200 import tpch
 from llkv_b200.table import LlkvError, Snapshot
 from oracle import oracle
@@ -118,7 +118,7 @@ def test_random_plans_match_oracle(gpu_ctx, seed):
 
 
 # ---------------------------------------------------------------------------------- OR / NOT trees, NULLs: still the lean kernel
-def random_tree(rng, depth=0):
+def random_tree(rng, depth=0, compares=False):
     """AND / OR / NOT trees over typed leaves on integer, float, decimal, date, boolean and short-string columns — ranges,
     equalities, IN lists, prefixes, IS [NOT] NULL (three-valued logic with
     domains when the columns are nullable: llkv-scan/src/predicate.rs:167-186,665-777)."""
@@ -143,18 +143,47 @@ def random_tree(rng, depth=0):
         lambda: pred(10, Operator.In(["A", "xy", "zz"])),
         lambda: pred(10, Operator.StartsWith(str(rng.choice(["", "a", "ab", "x", "N"])))),
     ]
+    if compares:
+        # general comparisons of two scalar expressions (compute_compare, llkv-compute/src/kernels.rs:269-297): a NULL on
+        # either side is NULL; integers, decimals (rescaled to the common scale), dates, floats by total order
+        c = ScalarExpr.Column
+        ops = [CompareOp.Eq, CompareOp.NotEq, CompareOp.Lt, CompareOp.LtEq, CompareOp.Gt, CompareOp.GtEq]
+        op = lambda: ops[int(rng.integers(0, len(ops)))]
+        leaves = leaves[:6] + [
+            lambda: Expr.Compare(c(1) + c(2), op(), ScalarExpr.Literal(int(rng.integers(-300, 300)))),
+            lambda: Expr.Compare(c(1), op(), c(2) * int(rng.integers(-20, 20))),
+            lambda: Expr.Compare(c(2) * c(2) - c(1), op(), c(1)),
+            lambda: Expr.Compare(c(3), op(), c(1)),
+            lambda: Expr.Compare(c(3) * 0.5, op(), c(7)),
+            lambda: Expr.Compare(c(5), op(), ScalarExpr.Literal(Literal.Decimal128(int(rng.integers(-10**6, 10**6)), 2))),
+            lambda: Expr.Compare(c(5) * c(5), op(), ScalarExpr.Literal(Literal.Decimal128(int(rng.integers(0, 10**12)), 4))),
+            lambda: Expr.Compare(c(6), op(), ScalarExpr.Literal(Literal.Date32(int(rng.integers(8000, 11000))))),
+            lambda: Expr.Compare(ScalarExpr.Literal(int(rng.integers(-50, 50))), op(), c(2)),
+        ]
     r = rng.random()
     if depth >= 3 or r < 0.35:
         return leaves[int(rng.integers(0, len(leaves)))]()
     if r < 0.5:
-        return Expr.Not(random_tree(rng, depth + 1))
-    kids = [random_tree(rng, depth + 1) for _ in range(int(rng.integers(2, 4)))]
+        return Expr.Not(random_tree(rng, depth + 1, compares))
+    kids = [random_tree(rng, depth + 1, compares) for _ in range(int(rng.integers(2, 4)))]
     return Expr.And(kids) if r < 0.75 else Expr.Or(kids)
 
 
 @pytest.mark.parametrize("nulls", [False, True], ids=["dense", "nullable"])
 @pytest.mark.parametrize("seed", range(6))
 def test_random_predicate_trees_stay_on_the_lean_kernel(gpu_ctx, seed, nulls):
+    _random_trees(gpu_ctx, seed, nulls, compares=False)
+
+
+@pytest.mark.parametrize("nulls", [False, True], ids=["dense", "nullable"])
+@pytest.mark.parametrize("seed", range(3))
+def test_random_trees_with_expression_comparisons_stay_on_the_lean_kernel(gpu_ctx, seed, nulls):
+    """Expr::Compare leaves (two scalar expressions) inside AND / OR / NOT trees: lowered to the lean kernel's FO_CMP, checked
+    against the oracle through aggregates (both builds of the lean kernel) and through the general interpreter's bitmap."""
+    _random_trees(gpu_ctx, 40 + seed, nulls, compares=True)
+
+
+def _random_trees(gpu_ctx, seed, nulls, compares):
     from llkv_b200 import gpu
     rng = np.random.default_rng(500 + seed)
     n = int(rng.integers(5000, 30000))
@@ -170,7 +199,7 @@ def test_random_predicate_trees_stay_on_the_lean_kernel(gpu_ctx, seed, nulls):
     dt = device_table(gpu_ctx, t)
     try:
         for trial in range(6):
-            f = random_tree(rng)
+            f = random_tree(rng, compares=compares)
             specs = [pool[i] for i in sorted(rng.choice(len(pool), size=int(rng.integers(1, 6)), replace=False))]
             snap = [None, snap_all][int(rng.integers(0, 2))]
             lo = int(rng.integers(0, n // 3)) if rng.random() < 0.5 else 0
