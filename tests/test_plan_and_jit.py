@@ -57,6 +57,41 @@ def test_or_and_not_trees_lower_to_the_mask_stack_of_the_lean_kernel(lineitem):
     assert text.startswith("lean plan") and "IN list of 2 literals (pushed)" in text
 
 
+def test_expression_comparisons_lower_to_the_lean_kernel(lineitem):
+    """Expr::Compare over two scalar expressions (compute_compare, llkv-compute/src/kernels.rs:269-297) is a lean
+    instruction: one side in the accumulator, the other a column / literal / temporary, the result on the mask stack."""
+    from llkv_b200.expr import CompareOp, ScalarExpr
+    t, _ = lineitem
+    c = ScalarExpr.Column
+    price, disc, qty = tpch.L_EXTENDEDPRICE, tpch.L_DISCOUNT, tpch.L_QUANTITY
+    big = Expr.Compare(c(price) * c(disc), CompareOp.Gt, ScalarExpr.Literal(Literal.Decimal128(50_000_0000, 4)))
+    text = gpu.debug_plan(t, big, tpch.q6_aggregates())
+    ops = [ln.split()[1] for ln in text.splitlines() if ln.strip()[:1].isdigit()]
+    assert text.startswith("lean plan") and ops.count("CMP") == 1 and ops.count("MASK_FILTER") == 1
+    # inside a tree, next to typed leaves; operand order mirrored when the right side ends up in the accumulator
+    tree = Expr.Or([Expr.Not(big), Expr.And([tpch.q6_filter(), Expr.Compare(c(qty), CompareOp.LtEq, c(disc) * c(disc))])])
+    text = gpu.debug_plan(t, tree, tpch.q6_aggregates())
+    ops = [ln.split()[1] for ln in text.splitlines() if ln.strip()[:1].isdigit()]
+    assert text.startswith("lean plan") and ops.count("CMP") == 2 and "MASK_NOT" in ops and "MASK_OR" in ops
+    if _nvrtc_available():
+        assert "specialised cubin:" in gpu.debug_plan(t, tree, tpch.q6_aggregates(), jit=True)
+
+
+def test_nullable_group_keys_lower_to_the_lean_kernel():
+    """A nullable key column adds a null bit to its field of the packed key (NULL is its own group): GROUP BY over columns
+    with NULLs no longer leaves the lean kernel."""
+    rng = np.random.default_rng(3)
+    n = 4000
+    t = HostTable(1)
+    k = HostColumn(1, DataType.Int32, rng.integers(0, 40, n).astype(np.int32))
+    k.validity = np.packbits(rng.random(n) > 0.2, bitorder="little")
+    t.add(k)
+    t.add(HostColumn(2, DataType.Int64, rng.integers(-1000, 1000, n, dtype=np.int64)))
+    specs = [AggregateSpec("n", AggregateKind.CountStar()), AggregateSpec("s", AggregateKind.Sum(2, DataType.Int64))]
+    text = gpu.debug_plan(t, None, specs, group_by=(1,), cardinality_hint=64)
+    assert text.startswith("lean plan") and " GROUP " in text
+
+
 def test_geometry_respects_tuning_and_shared_memory(lineitem):
     t, snap = lineitem
     text = gpu.debug_plan(t, tpch.q1_filter(), tpch.q1_aggregates(), snap, group_by=tpch.Q1_GROUP_BY, cardinality_hint=6,
