@@ -5,7 +5,7 @@ import pytest
 
 import util
 from llkv_b200 import tpch
-from llkv_b200.expr import AggregateKind, AggregateSpec, DataType, Expr, ScalarExpr
+from llkv_b200.expr import AggregateKind, AggregateSpec, CompareOp, DataType, Expr, ScalarExpr
 from llkv_b200.table import HostColumn, HostTable, LlkvError, Snapshot
 from oracle import oracle
 from test_gpu_parity import PREDICATES, REL, all_aggs, device_table, mixed_table
@@ -214,6 +214,35 @@ def test_four_slot_associative_group_table(gpu_ctx, mode, hint):
             dm.destroy()
     finally:
         gpu_ctx.set_jit(1)
+
+
+@pytest.mark.parametrize("mode", [0, 2], ids=["interpreted", "specialised"])
+def test_nullable_keys_in_the_four_slot_table(gpu_ctx, mode):
+    """Three key values + NULL under a hint of 4: the four-slot table compares the packed keys, null bit included, in 32 bits;
+    with two nullable keys (nine + groups) the surplus groups take the global-table copy of the program."""
+    rng = np.random.default_rng(17)
+    n = 50_000
+    t = HostTable(1)
+    for fid, hi in ((1, 3), (2, 2)):
+        c = HostColumn(fid, DataType.Int32, rng.integers(0, hi, n).astype(np.int32))
+        c.validity = np.packbits(rng.random(n) > 0.15, bitorder="little")
+        t.add(c)
+    v = HostColumn(3, DataType.Int64, rng.integers(-1000, 1000, n, dtype=np.int64))
+    v.validity = np.packbits(rng.random(n) > 0.1, bitorder="little")
+    t.add(v)
+    specs = [AggregateSpec("n", AggregateKind.CountStar()), AggregateSpec("c", AggregateKind.Count(3)),
+             AggregateSpec("s", AggregateKind.Sum(3, DataType.Int64)), AggregateSpec("mn", AggregateKind.Min(3, DataType.Int64))]
+    gpu_ctx.set_jit(mode)
+    dt = device_table(gpu_ctx, t)
+    try:
+        for keys in [(1,), (1, 2)]:
+            for e in (None, Expr.Compare(ScalarExpr.Column(3) + ScalarExpr.Column(1), CompareOp.Gt, ScalarExpr.Column(2) * ScalarExpr.Column(2))):
+                got, info = run(gpu_ctx, dt, e, specs, group_by=keys, hint=4, cap=64)
+                assert info.used_fast_kernel == 1 and info.fast_groups == 4 and info.used_jit_kernel == (1 if mode else 0)
+                util.assert_same_result(got, oracle.aggregate(t, e, specs, group_by=keys, group_capacity=64), REL)
+    finally:
+        gpu_ctx.set_jit(1)
+        dt.destroy()
 
 
 def test_a_low_cardinality_hint_is_corrected_after_the_first_finalize(gpu_ctx):

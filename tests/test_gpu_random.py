@@ -159,6 +159,9 @@ def random_tree(rng, depth=0, compares=False):
             lambda: Expr.Compare(c(5) * c(5), op(), ScalarExpr.Literal(Literal.Decimal128(int(rng.integers(0, 10**12)), 4))),
             lambda: Expr.Compare(c(6), op(), ScalarExpr.Literal(Literal.Date32(int(rng.integers(8000, 11000))))),
             lambda: Expr.Compare(ScalarExpr.Literal(int(rng.integers(-50, 50))), op(), c(2)),
+            # both sides computed: the left one waits in a temporary while the right one takes the accumulator
+            lambda: Expr.Compare(c(1) + c(2), op(), c(2) * c(2) - int(rng.integers(0, 500))),
+            lambda: Expr.Compare(c(5) * c(5), op(), c(5) * int(rng.integers(-100, 100)) * int(rng.integers(1, 1000))),
         ]
     r = rng.random()
     if depth >= 3 or r < 0.35:
