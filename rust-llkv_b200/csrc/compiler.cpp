@@ -1998,11 +1998,11 @@ class Emitter {
           const bool is_leaf = i + 1 < select_end_ && (code_[i + 1].op == OP_PRED_I || code_[i + 1].op == OP_PRED_U || code_[i + 1].op == OP_PRED_D ||
                                                        code_[i + 1].op == OP_PRED_F || code_[i + 1].op == OP_PRED_ISNULL ||
                                                        code_[i + 1].op == OP_PRED_NOTNULL || code_[i + 1].op == OP_PRED_ALL ||
-                                                       code_[i + 1].op == OP_IN_BITS || code_[i + 1].op == OP_IN_D);
+                                                       code_[i + 1].op == OP_IN_BITS || code_[i + 1].op == OP_IN_D || code_[i + 1].op == OP_IN_F);
           if (is_leaf) {
             const bool conjunct = i + 2 < n && code_[i + 2].op == OP_FILTER && mask_depth == 0;
             const Instr& pr = code_[i + 1];
-            if (pr.op == OP_PRED_F && c.load_kind != LK_F64 && c.load_kind != LK_F32) return lf_fail(__LINE__);
+            if ((pr.op == OP_PRED_F || pr.op == OP_IN_F) && c.load_kind != LK_F64 && c.load_kind != LK_F32) return lf_fail(__LINE__);
             if (!conjunct) {
               if (mask_depth >= 8) return lf_fail(__LINE__);
               ++mask_depth;
@@ -2010,13 +2010,27 @@ class Emitter {
             const uint32_t push = conjunct ? 0u : 1u;
             // NULL never satisfies a typed predicate: a nullable column's leaf starts from its valid rows
             if (conjunct && c.nullable && (pr.op == OP_PRED_NOTNULL || pr.op == OP_PRED_I || pr.op == OP_PRED_U || pr.op == OP_PRED_D ||
-                                           pr.op == OP_PRED_F || pr.op == OP_IN_BITS || pr.op == OP_IN_D))
+                                           pr.op == OP_PRED_F || pr.op == OP_IN_BITS || pr.op == OP_IN_D || pr.op == OP_IN_F))
               femit(FO_VALID, in.a, 0, 0);
-            if (pr.op == OP_IN_BITS || pr.op == OP_IN_D) {
+            if (pr.op == OP_IN_BITS || pr.op == OP_IN_D || pr.op == OP_IN_F) {
               // IN list: equality of the 64-bit images (Decimal128 entries that fit i64; the others can match no narrow value)
               std::vector<Lit> run;
               for (uint32_t k = 0; k < pr.b; ++k) {
                 const Lit& L = lits_[pr.c + k];
+                if (pr.op == OP_IN_F) {
+                  // IEEE equality on the f64 image (an f32 column is widened as it is loaded): NaN equals nothing, a zero
+                  // of either sign equals both
+                  double d;
+                  memcpy(&d, &L.lo, 8);
+                  if (d != d) continue;
+                  if (d == 0.0) {
+                    run.push_back(mk_lit_i((i128)0));
+                    run.push_back(mk_lit_i((i128)INT64_MIN));
+                  } else {
+                    run.push_back(mk_lit_i((i128)(int64_t)L.lo));
+                  }
+                  continue;
+                }
                 if (pr.op == OP_IN_D) {
                   const i128 v = (i128)(((u128)L.hi << 64) | (u128)L.lo);
                   if (!fits_i64(v)) {
@@ -2242,10 +2256,13 @@ class Emitter {
           if (bits < 64 && !iv_fits(st.back().iv, -((i128)1 << (bits - 1)), ((i128)1 << (bits - 1)) - 1)) return lf_fail(__LINE__);
           break;
         }
+        case OP_CAST_U_F:  // an unsigned value proven below 2^63 converts like the signed image the accumulator holds
+          if (st.empty() || !iv_fits(st.back().iv, 0, (i128)INT64_MAX)) return lf_fail(__LINE__);
+          [[fallthrough]];
         case OP_CAST_I_F: case OP_CAST_D_F: {
           if (st.empty()) return lf_fail(__LINE__);
           load_acc(st.size() - 1);
-          if (in.op == OP_CAST_I_F) femit(FO_I2F, 0, 0, 0);
+          if (in.op == OP_CAST_I_F || in.op == OP_CAST_U_F) femit(FO_I2F, 0, 0, 0);
           else femit(FO_D2F, 0, 0, in.c);
           st.back().iv = Iv();
           st.back().iv.is_float = true;

@@ -4227,6 +4227,7 @@ static int32_t agg_launch(llkv_gpu_agg* a, const llkv_gpu_program* prog, int app
     for (uint32_t i = 0; i < lean.s.n_code; ++i) {
       const FInstr& in = lean.s.code[i];
       if (in.op != FO_LEAF || in.e) continue;  // (a leaf inside an OR / NOT tree is no conjunct)
+      if (in.g >= 2) continue;                 // (float images and IN lists are not ranges of the zone order)
       llkv_gpu_column* col = nullptr;
       for (llkv_gpu_column* h : handles)
         if (h->values == lean.col_base[in.a]) col = h;

@@ -189,3 +189,32 @@ def test_pruned_scan_feeding_the_partitioned_group_by(gpu_ctx, monkeypatch, batc
         util.assert_same_result(got, want, REL)
     finally:
         dt.destroy()
+
+
+def test_an_in_list_over_a_sorted_unsigned_column_prunes_nothing(gpu_ctx):
+    """An IN-list leaf is a set, not a range: its first two entries must not be read as the bounds of a zone test (they were
+    for UInt64 columns, whose leaves and zones share the unsigned order).  Entries far apart in a sorted column: every tile
+    between them holds matches of the other entries."""
+    from llkv_b200 import gpu
+    n = 200_000
+    t = HostTable(1)
+    t.add(HostColumn(1, DataType.UInt64, np.arange(n, dtype=np.uint64)))
+    t.add(HostColumn(2, DataType.Int64, np.arange(n, dtype=np.int64) % 1000))
+    wanted = [5, 7, 60_000, 120_001, 199_999]
+    f = pred(1, Operator.In(wanted))
+    specs = [AggregateSpec("n", AggregateKind.CountStar()), AggregateSpec("s", AggregateKind.Sum(2, DataType.Int64))]
+    dt = gpu.DeviceTable.from_host(gpu_ctx, t)
+    try:
+        want = oracle.aggregate(t, f, specs)
+        for jit in (0, 2):
+            for _ in range(2):  # (mode 1 would only prune from the second unchanged scan on; mode 2 always)
+                got, info = run(gpu_ctx, dt, f, specs, jit=jit)
+                util.assert_same_result(got, want, REL)
+                assert info.used_fast_kernel == 1 and info.tiles_pruned == 0
+        # the same values as ranges do prune
+        rng_f = Expr.And([pred(1, Operator.GreaterThanOrEquals(60_000)), pred(1, Operator.LessThan(60_100))])
+        got, info = run(gpu_ctx, dt, rng_f, specs)
+        util.assert_same_result(got, oracle.aggregate(t, rng_f, specs), REL)
+        assert info.tiles_pruned > 0
+    finally:
+        dt.destroy()

@@ -162,6 +162,11 @@ def random_tree(rng, depth=0, compares=False):
             # both sides computed: the left one waits in a temporary while the right one takes the accumulator
             lambda: Expr.Compare(c(1) + c(2), op(), c(2) * c(2) - int(rng.integers(0, 500))),
             lambda: Expr.Compare(c(5) * c(5), op(), c(5) * int(rng.integers(-100, 100)) * int(rng.integers(1, 1000))),
+            # Int64 against UInt64 compares as Float64 (the unsigned side is proven below 2^63)
+            lambda: Expr.Compare(c(1) * 2, op(), c(4)),
+            # float IN lists: IEEE equality (a zero of either sign matches both, NaN matches nothing)
+            lambda: pred(7, Operator.In([float(x) for x in rng.choice([0.0, -0.0, 0.25, -1.0, 3.5, 4.75], size=int(rng.integers(0, 5)))])),
+            lambda: pred(3, Operator.In([float(x) for x in rng.choice([0.0, -0.0, 12.5, float("nan"), float("inf")], size=3)])),
         ]
     r = rng.random()
     if depth >= 3 or r < 0.35:
