@@ -2298,6 +2298,18 @@ class Emitter {
           ++mask_depth;
           break;
         }
+        case OP_ISNULL: {
+          // Expr::IsNull over a scalar expression: NULL exactly where some column it depends on is NULL (data-dependent
+          // NULLs — a division by zero, a failed safe cast — never reach this lowering); the result itself is never NULL
+          if (i >= select_end_ || st.empty() || mask_depth >= 8) return lf_fail(__LINE__);
+          const uint32_t nm = st.back().nm;
+          free_sym(st.back());
+          st.pop_back();
+          femit(FO_ISNULL, in.a ? 1u : 0u, 0, 0);
+          f.back().h = nm;
+          ++mask_depth;
+          break;
+        }
         case OP_AND: case OP_OR:
           if (mask_depth < 2) return lf_fail(__LINE__);
           femit(in.op == OP_AND ? FO_MASK_AND : FO_MASK_OR, 0, 0, 0);

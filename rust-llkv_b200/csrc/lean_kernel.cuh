@@ -963,6 +963,14 @@ struct LeanTile {
         ++msp;
         return true;
       }
+      case FO_ISNULL: if constexpr (live<PC>(FO_ISNULL)) {
+        const unsigned all = (1u << R) - 1u;
+        const unsigned valid = in.h ? valid_mask(in.h) : all;
+        mt[msp] = (in.a ? valid : ~valid) & all;
+        mn[msp] = 0;
+        ++msp;
+        return true;
+      }
       case FO_MASK_AND: case FO_MASK_OR: if constexpr (live<PC>(FO_MASK_AND) || live<PC>(FO_MASK_OR)) {
         // rows: bitmap AND / OR; domain: intersect / unite (llkv-compute/src/program.rs:500-512)
         const unsigned t1 = mt[msp - 2], t0 = mt[msp - 1], n1 = mn[msp - 2], n0 = mn[msp - 1];

@@ -3242,7 +3242,7 @@ static const char* fast_op_name(uint32_t op) {
   static const char* names[] = {"END", "LEAF", "MVCC", "SELECT_DONE", "GROUP", "LD_COL", "LD_LIT", "LD_TMP", "ST_TMP", "OP_COL", "OP_LIT",
                                 "OP_TMP", "DIVR", "MULP", "I2F", "D2F", "COUNT_STAR", "COUNT", "FIRSTROW", "SUM", "FSUM", "MIN_I", "MAX_I",
                                 "MIN_F", "MAX_F", "FIRSTVALID", "FIRSTNAN", "VALID", "MASK_AND", "MASK_OR", "MASK_NOT", "MASK_LIT",
-                                "MASK_FILTER", "CMP"};
+                                "MASK_FILTER", "CMP", "ISNULL"};
   return op < sizeof(names) / sizeof(names[0]) ? names[op] : "?";
 }
 static std::string lean_listing(const LeanPlan& lp, const Geometry& g, uint32_t ctas) {

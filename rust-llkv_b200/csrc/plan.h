@@ -122,6 +122,8 @@ enum FastOp : uint16_t {
                   // (acc cmp operand) onto the predicate-mask stack.  a = LLKV_CMP_* | kind << 4 (0 signed, 1 unsigned, 2 f64
                   // by total order); b = operand source (0 column c, 1 literal c, 2 tmp c) | FastLoad << 8; h = plan columns
                   // whose NULLs make the comparison NULL (neither selected nor in the domain of a NOT)
+  FO_ISNULL,      // Expr::IsNull { expr, negated } over a scalar expression: push (expr IS [NOT] NULL, determined on every row).
+                  // a = negated; h = plan columns whose NULLs make the expression NULL
   FO_COUNT_
 };
 #if defined(__CUDACC__) || defined(__CUDACC_RTC__)

@@ -167,6 +167,9 @@ def random_tree(rng, depth=0, compares=False):
             # float IN lists: IEEE equality (a zero of either sign matches both, NaN matches nothing)
             lambda: pred(7, Operator.In([float(x) for x in rng.choice([0.0, -0.0, 0.25, -1.0, 3.5, 4.75], size=int(rng.integers(0, 5)))])),
             lambda: pred(3, Operator.In([float(x) for x in rng.choice([0.0, -0.0, 12.5, float("nan"), float("inf")], size=3)])),
+            # Expr::IsNull over an expression: NULL where any column it reads is NULL; never NULL itself
+            lambda: Expr.IsNull(c(1) + c(2), negated=bool(rng.integers(0, 2))),
+            lambda: Expr.IsNull(c(5) * c(5) - c(5), negated=bool(rng.integers(0, 2))),
         ]
     r = rng.random()
     if depth >= 3 or r < 0.35:
