@@ -69,6 +69,33 @@ def test_filter_known_answers(gpu_ctx, case):
     assert util.host_values(t.columns[case["select"]], pos) == case["expect"]
 
 
+@pytest.mark.parametrize("mode", [0, 2], ids=["interpreted", "specialised"])
+def test_filter_known_answers_through_the_lean_kernel(gpu_ctx, mode):
+    """The same reference-held filters (llkv-table/src/table.rs tests: ranges, IN lists, floats, AND / OR / NOT, the
+    two-column `a + c > 220` comparison) as the selection of an aggregate: every one of them runs on the lean kernel, and
+    COUNT(*) is the number of rows the reference's test expects."""
+    from llkv_b200 import gpu
+    t = util.table_from_json(G["table_t4"])
+    dt = device_table(gpu_ctx, t)
+    gpu_ctx.set_jit(mode)
+    try:
+        for case in G["filter_cases"]:
+            prog = gpu.Program(gpu_ctx, util.expr_from_json(case["filter"]))
+            agg = gpu.Aggregation(dt, [AggregateSpec("n", AggregateKind.CountStar()), AggregateSpec("c", AggregateKind.Count(case["select"]))])
+            try:
+                agg.run(prog, False)
+                (_, vals), = agg.finalize(1)
+                assert agg.run_info().used_fast_kernel == 1, case["name"]
+                assert vals[0].value == len(case["expect"]), case["name"]
+                assert vals[1].value == sum(v is not None for v in case["expect"]), case["name"]
+            finally:
+                agg.destroy()
+                prog.destroy()
+    finally:
+        gpu_ctx.set_jit(1)
+        dt.destroy()
+
+
 @pytest.mark.parametrize("case", G["aggregate_cases"], ids=lambda c: c["name"])
 def test_aggregate_known_answers(gpu_ctx, case):
     col = util.column_from_json(1, case["column"])

@@ -77,6 +77,22 @@ def test_expression_comparisons_lower_to_the_lean_kernel(lineitem):
         assert "specialised cubin:" in gpu.debug_plan(t, tree, tpch.q6_aggregates(), jit=True)
 
 
+def test_every_reference_held_filter_lowers_to_the_lean_kernel():
+    """The reference's own filter tests (tests/golden: ranges, IN lists over integers and floats, AND / OR / NOT, the
+    two-column comparison) as the selection of COUNT(*): each is a lean program, and the oracle counts what the reference's
+    test expects."""
+    import util
+    from oracle import oracle
+    G = util.golden()
+    t = util.table_from_json(G["table_t4"])
+    for case in G["filter_cases"]:
+        f = util.expr_from_json(case["filter"])
+        specs = [AggregateSpec("n", AggregateKind.CountStar())]
+        assert gpu.debug_plan(t, f, specs).startswith("lean plan"), case["name"]
+        (_, vals), = oracle.aggregate(t, f, specs)
+        assert vals[0].value == len(case["expect"]), case["name"]
+
+
 def test_nullable_group_keys_lower_to_the_lean_kernel():
     """A nullable key column adds a null bit to its field of the packed key (NULL is its own group): GROUP BY over columns
     with NULLs no longer leaves the lean kernel."""
