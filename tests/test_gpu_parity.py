@@ -96,6 +96,33 @@ def test_filter_known_answers_through_the_lean_kernel(gpu_ctx, mode):
         dt.destroy()
 
 
+def test_count_with_a_complex_expression_filter(gpu_ctx):
+    """llkv-slt-tester/tests/slt/duckdb/constraints/primarykey/test_pk_append_many_duplicates.slt:27-39 through the GPU:
+    `SELECT COUNT(*) FROM integers WHERE i+i = ${val}*2` is 1 for every val of 0..99 (an Expr::Compare of two scalar
+    expressions; the lean kernel's FO_CMP, specialised once: the literal is a run-time parameter)."""
+    from llkv_b200 import gpu
+    t = HostTable(1).add(HostColumn(1, DataType.Int64, np.arange(100, dtype=np.int64)))
+    dt = device_table(gpu_ctx, t)
+    i = ScalarExpr.Column(1)
+    try:
+        agg = gpu.Aggregation(dt, [AggregateSpec("n", AggregateKind.CountStar())])
+        try:
+            for val in list(range(100)) + [100, -1]:
+                prog = gpu.Program(gpu_ctx, Expr.Compare(i + i, CompareOp.Eq, ScalarExpr.Literal(val) * 2))
+                try:
+                    agg.reset()
+                    agg.run(prog, False)
+                    (_, vals), = agg.finalize(1)
+                    assert vals[0].value == (1 if 0 <= val < 100 else 0), val
+                    assert agg.run_info().used_fast_kernel == 1
+                finally:
+                    prog.destroy()
+        finally:
+            agg.destroy()
+    finally:
+        dt.destroy()
+
+
 @pytest.mark.parametrize("case", G["aggregate_cases"], ids=lambda c: c["name"])
 def test_aggregate_known_answers(gpu_ctx, case):
     col = util.column_from_json(1, case["column"])

@@ -94,3 +94,19 @@ def test_aggregates_over_nullable_integers(case):
     names, specs = util.nullable_aggregate_specs(case)
     got = oracle.aggregate(t, None, specs)[0][1]
     assert {n: v.value for n, v in zip(names, got)} == case["expect"]
+
+
+def test_count_with_a_complex_expression_filter():
+    """llkv-slt-tester/tests/slt/duckdb/constraints/primarykey/test_pk_append_many_duplicates.slt:27-39: integers(i) holds
+    0..99; for every val `SELECT COUNT(*) FROM integers WHERE i+i = ${val}*2` ("a complex expression to prevent index
+    lookup") and `... WHERE i = ${val}` return 1.  The first is an Expr::Compare of two scalar expressions."""
+    from llkv_b200.expr import CompareOp, Expr, Operator, ScalarExpr, pred
+    t = HostTable(1).add(HostColumn(1, DataType.Int64, np.arange(100, dtype=np.int64)))
+    count = [AggregateSpec("n", AggregateKind.CountStar())]
+    i = ScalarExpr.Column(1)
+    for val in range(100):
+        complex_filter = Expr.Compare(i + i, CompareOp.Eq, ScalarExpr.Literal(val) * 2)
+        assert oracle.aggregate(t, complex_filter, count)[0][1][0].value == 1
+        assert oracle.aggregate(t, pred(1, Operator.Equals(val)), count)[0][1][0].value == 1
+    # (outside the loaded range both are 0)
+    assert oracle.aggregate(t, Expr.Compare(i + i, CompareOp.Eq, ScalarExpr.Literal(100) * 2), count)[0][1][0].value == 0
