@@ -1234,8 +1234,10 @@ static bool route_to_dma(const llkv_gpu_column* col, uint64_t first_row) {
     // this pool a worker streams about 6.4 GB/s and the host's memory system gives out near 78 GB/s in total (15 workers:
     // 37 ms per 2.9 GB with or without help from the copy engine; 8 workers: 56 ms alone, 48 ms with half the bytes on the
     // copy engine).  The copy engine gets what the workers leave of that budget.
+    // (6.4 GB/s is the SSE2 form of the narrowing loop; the AVX2 / AVX-512 forms with their software prefetch stream about
+    // 11 GB/s per worker, so from eight workers on nothing is left for the copy engine)
     const double workers = c->pool ? (double)c->pool->threads() : 0.0;
-    const double left = 78.0 - 6.4 * workers;
+    const double left = 78.0 - (llkv::narrow_isa() >= 2 ? 11.0 : 6.4) * workers;
     share = left <= 0 ? 0 : (int)(100.0 * left / 78.0);
   }
   if (share <= 0) return false;

@@ -1,21 +1,50 @@
 // upload.cpp — see upload.h.
 #include "upload.h"
 
+#include <stdlib.h>
 #include <string.h>
-#if defined(__SSE2__)
-#include <emmintrin.h>
+#if defined(__x86_64__)
+#include <immintrin.h>
 #endif
 
 namespace llkv {
 
-// The loops below are the host side of the PCIe path: 16 bytes read and 8 / 4 written per value.  With SSE2 (every
-// x86-64) four values are handled per iteration with unpack instructions; the fit check is an OR-reduction, so the loop
-// has no branch.
-bool narrow_d128_i64(const void* src, void* dst, uint64_t n) {
+// The loops below are the host side of the PCIe path: 16 bytes read and 8 / 4 written per value, with a branch-free fit
+// check (an OR-reduction over "the upper words repeat the sign").  One thread of the SSE2 form moves ~5.5 GB/s of Arrow
+// bytes on the hosts of this pool — the end-to-end step was bound by exactly that (15 workers x 6 GB/s) — so the loop is
+// dispatched once per process on what the CPU has: AVX-512 (two 64-byte loads and one cross-lane permute per eight
+// values) or AVX2, both with a software prefetch 2 KB ahead (a single core's demand misses alone do not keep enough
+// lines in flight); ~12 GB/s per thread.  Every form gives bit-identical output and the same verdict
+// (tests/test_host_logic.py runs them against each other).
+namespace {
+
+enum { ISA_SSE2 = 1, ISA_AVX2 = 2, ISA_AVX512 = 3 };
+constexpr int kPrefetchAhead = 2048;
+
+inline bool tail_i64(const int64_t* in, int64_t* out, uint64_t i, uint64_t n) {
+  int64_t bad = 0;
+  for (; i < n; ++i) {
+    const int64_t lo = in[2 * i], hi = in[2 * i + 1];
+    out[i] = lo;
+    bad |= hi ^ (lo >> 63);
+  }
+  return bad == 0;
+}
+inline bool tail_i32(const int64_t* in, int32_t* out, uint64_t i, uint64_t n) {
+  int64_t bad = 0;
+  for (; i < n; ++i) {
+    const int64_t lo = in[2 * i], hi = in[2 * i + 1];
+    out[i] = (int32_t)lo;
+    bad |= (hi ^ (lo >> 63)) | (lo ^ (int64_t)(int32_t)lo);
+  }
+  return bad == 0;
+}
+
+bool narrow_i64_sse2(const void* src, void* dst, uint64_t n) {
   const int64_t* in = static_cast<const int64_t*>(src);
   int64_t* out = static_cast<int64_t*>(dst);
-  int64_t bad = 0;
   uint64_t i = 0;
+  bool ok = true;
 #if defined(__SSE2__)
   __m128i vbad = _mm_setzero_si128();
   for (; i + 4 <= n; i += 4) {
@@ -31,25 +60,18 @@ bool narrow_d128_i64(const void* src, void* dst, uint64_t n) {
     const __m128i s23 = _mm_shuffle_epi32(_mm_srai_epi32(lo23, 31), _MM_SHUFFLE(3, 3, 1, 1));
     vbad = _mm_or_si128(vbad, _mm_or_si128(_mm_xor_si128(hi01, s01), _mm_xor_si128(hi23, s23)));
   }
-  {
-    int64_t t[2];
-    _mm_storeu_si128(reinterpret_cast<__m128i*>(t), vbad);
-    bad = t[0] | t[1];
-  }
+  int64_t t[2];
+  _mm_storeu_si128(reinterpret_cast<__m128i*>(t), vbad);
+  ok = (t[0] | t[1]) == 0;
 #endif
-  for (; i < n; ++i) {
-    const int64_t lo = in[2 * i], hi = in[2 * i + 1];
-    out[i] = lo;
-    bad |= hi ^ (lo >> 63);
-  }
-  return bad == 0;
+  return tail_i64(in, out, i, n) && ok;
 }
 
-bool narrow_d128_i32(const void* src, void* dst, uint64_t n) {
+bool narrow_i32_sse2(const void* src, void* dst, uint64_t n) {
   const int64_t* in = static_cast<const int64_t*>(src);
   int32_t* out = static_cast<int32_t*>(dst);
-  int64_t bad = 0;
   uint64_t i = 0;
+  bool ok = true;
 #if defined(__SSE2__)
   __m128i vbad = _mm_setzero_si128();
   const __m128i upper = _mm_set_epi32(-1, -1, -1, 0);  // dwords 1..3 of a value
@@ -68,19 +90,158 @@ bool narrow_d128_i32(const void* src, void* dst, uint64_t n) {
     const __m128i x3 = _mm_xor_si128(r3, _mm_shuffle_epi32(_mm_srai_epi32(r3, 31), 0));
     vbad = _mm_or_si128(vbad, _mm_and_si128(upper, _mm_or_si128(_mm_or_si128(x0, x1), _mm_or_si128(x2, x3))));
   }
-  {
-    int64_t t[2];
-    _mm_storeu_si128(reinterpret_cast<__m128i*>(t), vbad);
-    bad = t[0] | t[1];
-  }
+  int64_t t[2];
+  _mm_storeu_si128(reinterpret_cast<__m128i*>(t), vbad);
+  ok = (t[0] | t[1]) == 0;
 #endif
-  for (; i < n; ++i) {
-    const int64_t lo = in[2 * i], hi = in[2 * i + 1];
-    out[i] = (int32_t)lo;
-    bad |= (hi ^ (lo >> 63)) | (lo ^ (int64_t)(int32_t)lo);
-  }
-  return bad == 0;
+  return tail_i32(in, out, i, n) && ok;
 }
+
+#if defined(__x86_64__) && defined(__GNUC__)
+#define LLKV_HAVE_WIDE_NARROW 1
+__attribute__((target("avx2"))) bool narrow_i32_avx2(const void* src, void* dst, uint64_t n) {
+  const char* in = static_cast<const char*>(src);
+  int32_t* out = static_cast<int32_t*>(dst);
+  uint64_t i = 0;
+  __m256i bad = _mm256_setzero_si256();
+  const __m256i upper = _mm256_setr_epi32(0, -1, -1, -1, 0, -1, -1, -1);
+  const __m256i order = _mm256_setr_epi32(0, 4, 1, 5, 2, 6, 3, 7);
+  for (; i + 8 <= n; i += 8) {
+    _mm_prefetch(in + i * 16 + kPrefetchAhead, _MM_HINT_T0);
+    _mm_prefetch(in + i * 16 + kPrefetchAhead + 64, _MM_HINT_T0);
+    const __m256i y0 = _mm256_loadu_si256(reinterpret_cast<const __m256i*>(in + i * 16));        // values 0, 1
+    const __m256i y1 = _mm256_loadu_si256(reinterpret_cast<const __m256i*>(in + i * 16 + 32));   // values 2, 3
+    const __m256i y2 = _mm256_loadu_si256(reinterpret_cast<const __m256i*>(in + i * 16 + 64));   // values 4, 5
+    const __m256i y3 = _mm256_loadu_si256(reinterpret_cast<const __m256i*>(in + i * 16 + 96));   // values 6, 7
+    const __m256i a = _mm256_unpacklo_epi32(y0, y1), b = _mm256_unpacklo_epi32(y2, y3);  // dword 0 of (0,2 | 1,3), (4,6 | 5,7)
+    const __m256i c = _mm256_unpacklo_epi64(a, b);                                        // values 0 2 4 6 | 1 3 5 7
+    _mm256_storeu_si256(reinterpret_cast<__m256i*>(out + i), _mm256_permutevar8x32_epi32(c, order));
+    const __m256i x0 = _mm256_xor_si256(y0, _mm256_shuffle_epi32(_mm256_srai_epi32(y0, 31), 0));
+    const __m256i x1 = _mm256_xor_si256(y1, _mm256_shuffle_epi32(_mm256_srai_epi32(y1, 31), 0));
+    const __m256i x2 = _mm256_xor_si256(y2, _mm256_shuffle_epi32(_mm256_srai_epi32(y2, 31), 0));
+    const __m256i x3 = _mm256_xor_si256(y3, _mm256_shuffle_epi32(_mm256_srai_epi32(y3, 31), 0));
+    bad = _mm256_or_si256(bad, _mm256_or_si256(_mm256_or_si256(x0, x1), _mm256_or_si256(x2, x3)));
+  }
+  const bool ok = _mm256_testz_si256(bad, upper) != 0;
+  return tail_i32(static_cast<const int64_t*>(src), out, i, n) && ok;
+}
+
+__attribute__((target("avx2"))) bool narrow_i64_avx2(const void* src, void* dst, uint64_t n) {
+  const char* in = static_cast<const char*>(src);
+  int64_t* out = static_cast<int64_t*>(dst);
+  uint64_t i = 0;
+  __m256i bad = _mm256_setzero_si256();
+  const __m256i upper = _mm256_setr_epi32(0, 0, -1, -1, 0, 0, -1, -1);  // the high qword of a value
+  for (; i + 8 <= n; i += 8) {
+    _mm_prefetch(in + i * 16 + kPrefetchAhead, _MM_HINT_T0);
+    _mm_prefetch(in + i * 16 + kPrefetchAhead + 64, _MM_HINT_T0);
+    const __m256i y0 = _mm256_loadu_si256(reinterpret_cast<const __m256i*>(in + i * 16));
+    const __m256i y1 = _mm256_loadu_si256(reinterpret_cast<const __m256i*>(in + i * 16 + 32));
+    const __m256i y2 = _mm256_loadu_si256(reinterpret_cast<const __m256i*>(in + i * 16 + 64));
+    const __m256i y3 = _mm256_loadu_si256(reinterpret_cast<const __m256i*>(in + i * 16 + 96));
+    // low qwords: (0, 2 | 1, 3) -> 0 1 2 3
+    _mm256_storeu_si256(reinterpret_cast<__m256i*>(out + i), _mm256_permute4x64_epi64(_mm256_unpacklo_epi64(y0, y1), 0xD8));
+    _mm256_storeu_si256(reinterpret_cast<__m256i*>(out + i + 4), _mm256_permute4x64_epi64(_mm256_unpacklo_epi64(y2, y3), 0xD8));
+    // the high qword must repeat the sign of the low one (the sign sits in dword 1)
+    const __m256i x0 = _mm256_xor_si256(y0, _mm256_shuffle_epi32(_mm256_srai_epi32(y0, 31), _MM_SHUFFLE(1, 1, 1, 1)));
+    const __m256i x1 = _mm256_xor_si256(y1, _mm256_shuffle_epi32(_mm256_srai_epi32(y1, 31), _MM_SHUFFLE(1, 1, 1, 1)));
+    const __m256i x2 = _mm256_xor_si256(y2, _mm256_shuffle_epi32(_mm256_srai_epi32(y2, 31), _MM_SHUFFLE(1, 1, 1, 1)));
+    const __m256i x3 = _mm256_xor_si256(y3, _mm256_shuffle_epi32(_mm256_srai_epi32(y3, 31), _MM_SHUFFLE(1, 1, 1, 1)));
+    bad = _mm256_or_si256(bad, _mm256_or_si256(_mm256_or_si256(x0, x1), _mm256_or_si256(x2, x3)));
+  }
+  const bool ok = _mm256_testz_si256(bad, upper) != 0;
+  return tail_i64(static_cast<const int64_t*>(src), out, i, n) && ok;
+}
+
+__attribute__((target("avx512f,avx512bw,avx512vl"))) bool narrow_i32_avx512(const void* src, void* dst, uint64_t n) {
+  const char* in = static_cast<const char*>(src);
+  int32_t* out = static_cast<int32_t*>(dst);
+  uint64_t i = 0;
+  const __m512i first = _mm512_setr_epi32(0, 4, 8, 12, 16, 20, 24, 28, 0, 0, 0, 0, 0, 0, 0, 0);  // dword 0 of eight values in two registers
+  __m512i bad0 = _mm512_setzero_si512(), bad1 = bad0;
+  for (; i + 16 <= n; i += 16) {
+    _mm_prefetch(in + i * 16 + kPrefetchAhead, _MM_HINT_T0);
+    _mm_prefetch(in + i * 16 + kPrefetchAhead + 64, _MM_HINT_T0);
+    _mm_prefetch(in + i * 16 + kPrefetchAhead + 128, _MM_HINT_T0);
+    _mm_prefetch(in + i * 16 + kPrefetchAhead + 192, _MM_HINT_T0);
+    const __m512i z0 = _mm512_loadu_si512(in + i * 16), z1 = _mm512_loadu_si512(in + i * 16 + 64);
+    const __m512i z2 = _mm512_loadu_si512(in + i * 16 + 128), z3 = _mm512_loadu_si512(in + i * 16 + 192);
+    const __m512i v0 = _mm512_permutex2var_epi32(z0, first, z1), v1 = _mm512_permutex2var_epi32(z2, first, z3);
+    _mm512_storeu_si512(out + i, _mm512_inserti64x4(v0, _mm512_castsi512_si256(v1), 1));
+    // dwords 1..3 must repeat the sign of dword 0
+    const __m512i x0 = _mm512_xor_si512(z0, _mm512_shuffle_epi32(_mm512_srai_epi32(z0, 31), (_MM_PERM_ENUM)0x00));
+    const __m512i x1 = _mm512_xor_si512(z1, _mm512_shuffle_epi32(_mm512_srai_epi32(z1, 31), (_MM_PERM_ENUM)0x00));
+    const __m512i x2 = _mm512_xor_si512(z2, _mm512_shuffle_epi32(_mm512_srai_epi32(z2, 31), (_MM_PERM_ENUM)0x00));
+    const __m512i x3 = _mm512_xor_si512(z3, _mm512_shuffle_epi32(_mm512_srai_epi32(z3, 31), (_MM_PERM_ENUM)0x00));
+    bad0 = _mm512_or_si512(bad0, _mm512_or_si512(x0, x1));
+    bad1 = _mm512_or_si512(bad1, _mm512_or_si512(x2, x3));
+  }
+  bad0 = _mm512_or_si512(bad0, bad1);
+  const bool ok = _mm512_mask_test_epi32_mask((__mmask16)0xEEEE, bad0, bad0) == 0;
+  return tail_i32(static_cast<const int64_t*>(src), out, i, n) && ok;
+}
+
+__attribute__((target("avx512f,avx512bw,avx512vl"))) bool narrow_i64_avx512(const void* src, void* dst, uint64_t n) {
+  const char* in = static_cast<const char*>(src);
+  int64_t* out = static_cast<int64_t*>(dst);
+  uint64_t i = 0;
+  const __m512i low = _mm512_setr_epi64(0, 2, 4, 6, 8, 10, 12, 14);  // the low qword of eight values in two registers
+  __m512i bad0 = _mm512_setzero_si512(), bad1 = bad0;
+  for (; i + 16 <= n; i += 16) {
+    _mm_prefetch(in + i * 16 + kPrefetchAhead, _MM_HINT_T0);
+    _mm_prefetch(in + i * 16 + kPrefetchAhead + 64, _MM_HINT_T0);
+    _mm_prefetch(in + i * 16 + kPrefetchAhead + 128, _MM_HINT_T0);
+    _mm_prefetch(in + i * 16 + kPrefetchAhead + 192, _MM_HINT_T0);
+    const __m512i z0 = _mm512_loadu_si512(in + i * 16), z1 = _mm512_loadu_si512(in + i * 16 + 64);
+    const __m512i z2 = _mm512_loadu_si512(in + i * 16 + 128), z3 = _mm512_loadu_si512(in + i * 16 + 192);
+    _mm512_storeu_si512(out + i, _mm512_permutex2var_epi64(z0, low, z1));
+    _mm512_storeu_si512(out + i + 8, _mm512_permutex2var_epi64(z2, low, z3));
+    // the high qword must repeat the sign of the low one: (sign, sign) of qword 0 copied over qword 1
+    const __m512i x0 = _mm512_xor_si512(z0, _mm512_shuffle_epi32(_mm512_srai_epi64(z0, 63), (_MM_PERM_ENUM)0x44));
+    const __m512i x1 = _mm512_xor_si512(z1, _mm512_shuffle_epi32(_mm512_srai_epi64(z1, 63), (_MM_PERM_ENUM)0x44));
+    const __m512i x2 = _mm512_xor_si512(z2, _mm512_shuffle_epi32(_mm512_srai_epi64(z2, 63), (_MM_PERM_ENUM)0x44));
+    const __m512i x3 = _mm512_xor_si512(z3, _mm512_shuffle_epi32(_mm512_srai_epi64(z3, 63), (_MM_PERM_ENUM)0x44));
+    bad0 = _mm512_or_si512(bad0, _mm512_or_si512(x0, x1));
+    bad1 = _mm512_or_si512(bad1, _mm512_or_si512(x2, x3));
+  }
+  bad0 = _mm512_or_si512(bad0, bad1);
+  const bool ok = _mm512_mask_test_epi64_mask((__mmask8)0xAA, bad0, bad0) == 0;
+  return tail_i64(static_cast<const int64_t*>(src), out, i, n) && ok;
+}
+#endif
+
+// best form this CPU (and the OS: the wide register state must be enabled) runs; LLKV_GPU_HOST_ISA=sse2|avx2|avx512 caps it
+int host_isa() {
+  static const int level = [] {
+    int have = ISA_SSE2;
+#ifdef LLKV_HAVE_WIDE_NARROW
+    __builtin_cpu_init();
+    if (__builtin_cpu_supports("avx2")) have = ISA_AVX2;
+    if (have == ISA_AVX2 && __builtin_cpu_supports("avx512f") && __builtin_cpu_supports("avx512bw") && __builtin_cpu_supports("avx512vl"))
+      have = ISA_AVX512;
+#endif
+    if (const char* e = getenv("LLKV_GPU_HOST_ISA")) {
+      const int cap = !strcmp(e, "sse2") ? ISA_SSE2 : !strcmp(e, "avx2") ? ISA_AVX2 : ISA_AVX512;
+      if (cap < have) have = cap;
+    }
+    return have;
+  }();
+  return level;
+}
+
+bool narrow_with(int isa, int out_width, const void* src, void* dst, uint64_t n) {
+#ifdef LLKV_HAVE_WIDE_NARROW
+  if (isa == ISA_AVX512) return out_width == 4 ? narrow_i32_avx512(src, dst, n) : narrow_i64_avx512(src, dst, n);
+  if (isa == ISA_AVX2) return out_width == 4 ? narrow_i32_avx2(src, dst, n) : narrow_i64_avx2(src, dst, n);
+#endif
+  return out_width == 4 ? narrow_i32_sse2(src, dst, n) : narrow_i64_sse2(src, dst, n);
+}
+
+}  // namespace
+
+int narrow_isa() { return host_isa(); }
+bool narrow_d128_i64(const void* src, void* dst, uint64_t n) { return narrow_with(host_isa(), 8, src, dst, n); }
+bool narrow_d128_i32(const void* src, void* dst, uint64_t n) { return narrow_with(host_isa(), 4, src, dst, n); }
 
 UploadPool::UploadPool(int device, int n_threads) : device_(device) {
   if (n_threads < 1) n_threads = 1;
@@ -274,3 +435,20 @@ void UploadPool::run(int index) {
 }
 
 }  // namespace llkv
+
+// Test hook (not part of include/llkv_gpu.h): one narrowing loop in a chosen instruction-set form.  isa: 0 = what the
+// process dispatches to, 1 = SSE2, 2 = AVX2, 3 = AVX-512.  Returns 1 = every value fits, 0 = some value does not fit
+// (dst holds the truncated values), -1 = this CPU does not have that form.
+extern "C" int llkv_internal_narrow_d128(int out_width, int isa, const void* src, void* dst, uint64_t n) {
+  if (out_width != 4 && out_width != 8) return -1;
+  int have = llkv::ISA_SSE2;
+#ifdef LLKV_HAVE_WIDE_NARROW
+  __builtin_cpu_init();
+  if (__builtin_cpu_supports("avx2")) have = llkv::ISA_AVX2;
+  if (have == llkv::ISA_AVX2 && __builtin_cpu_supports("avx512f") && __builtin_cpu_supports("avx512bw") && __builtin_cpu_supports("avx512vl"))
+    have = llkv::ISA_AVX512;
+#endif
+  if (isa == 0) isa = llkv::host_isa();
+  if (isa < llkv::ISA_SSE2 || isa > have) return -1;
+  return llkv::narrow_with(isa, out_width, src, dst, n) ? 1 : 0;
+}

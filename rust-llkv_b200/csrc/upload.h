@@ -79,5 +79,7 @@ class UploadPool {
 // checked narrowing loops (also used directly for sources that are not page-locked: they replace the staging memcpy)
 bool narrow_d128_i64(const void* src, void* dst, uint64_t n);
 bool narrow_d128_i32(const void* src, void* dst, uint64_t n);
+// instruction-set form the two loops dispatch to in this process: 1 = SSE2, 2 = AVX2, 3 = AVX-512 (upload.cpp)
+int narrow_isa();
 
 }  // namespace llkv

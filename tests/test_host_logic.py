@@ -141,3 +141,56 @@ def test_safe_rust_crate_only_calls_declared_sys_functions():
     declared = set(re.findall(r"pub fn (llkv_gpu_[a-z0-9_]+)\s*\(", sys_rs)) | set(re.findall(r"pub struct (llkv_[a-z0-9_]+)", sys_rs))
     used = set(re.findall(r"sys::(llkv_[a-z0-9_]+)", safe_rs))
     assert used and not (used - declared), sorted(used - declared)
+
+
+def test_narrowing_loops_agree_in_every_instruction_set_form():
+    """upload.cpp narrows Arrow Decimal128 values to i64 / i32 on the host before the DMA, with a fit check.  The loop is
+    dispatched on the CPU (SSE2 / AVX2 / AVX-512): every form this machine can run must write the same bytes and return the
+    same verdict as a numpy restatement — for every length around the vector widths, unaligned sources, both signs, values
+    at the edges of the narrow type, and a misfit at every position of a vector."""
+    from llkv_b200 import gpu
+    lib = C.CDLL(gpu.LIB_PATH)
+    fn = lib.llkv_internal_narrow_d128
+    fn.restype = C.c_int
+    fn.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_uint64]
+    rng = np.random.default_rng(12)
+    forms = [isa for isa in (0, 1, 2, 3) if fn(4, isa, None, None, 0) >= 0]
+    assert 0 in forms and 1 in forms
+
+    def check(width, lo, hi):
+        n = lo.size
+        raw = np.zeros(2 * n + 1, dtype=np.int64)  # (+1: an unaligned view below)
+        src = raw[:2 * n].reshape(n, 2) if n else raw[:0].reshape(0, 2)
+        src[:, 0], src[:, 1] = lo, hi
+        narrow_ok = (hi == (lo >> 63)) & ((lo == lo.astype(np.int32)) if width == 4 else True)
+        want_ok = bool(np.all(narrow_ok))
+        want = lo.astype(np.int32) if width == 4 else lo.copy()
+        # an 8-byte-aligned but not 16/32/64-byte-aligned source, as ARR0 payloads are (24-byte header)
+        shifted = np.zeros(2 * n + 3, dtype=np.int64)
+        shifted[1:2 * n + 1] = src.reshape(-1)
+        for isa in forms:
+            for buf, off in ((src, 0), (shifted, 8)):
+                out = np.full(n + 2, 0x5A5A5A5A, dtype=np.int32 if width == 4 else np.int64)
+                rc = fn(width, isa, buf.ctypes.data + off, out.ctypes.data, n)
+                assert rc == int(want_ok), (width, isa, n, off)
+                assert np.array_equal(out[:n], want) and np.all(out[n:] == 0x5A5A5A5A), (width, isa, n, off)
+
+    for width in (4, 8):
+        lim = 2**31 if width == 4 else 2**63
+        for n in list(range(0, 70)) + [127, 128, 129, 1000, 65536 + 5]:
+            lo = rng.integers(-lim, lim, n, dtype=np.int64)
+            if n:
+                lo[rng.integers(0, n, min(n, 4))] = [lim - 1, -lim, 0, -1][:min(n, 4)]
+            check(width, lo, lo >> 63)
+        # one misfit at every position of a 64-value block: a wrong high word, a value outside the narrow type
+        base = rng.integers(-1000, 1000, 64, dtype=np.int64)
+        for pos in range(64):
+            for bad_hi in (1, -2, 2**62, (base[pos] >> 63) ^ 1):
+                hi = base >> 63
+                hi[pos] = bad_hi
+                check(width, base.copy(), hi)
+            if width == 4:
+                for v in (2**31, -2**31 - 1, 2**40, -2**62):
+                    lo = base.copy()
+                    lo[pos] = v
+                    check(width, lo, lo >> 63)
