@@ -1,8 +1,10 @@
 // lean_kernel.cuh — body of the lean scan -> filter -> MVCC -> project -> aggregate kernel for sm_100a.
 //
-// Runs the FastOp program the compiler lowers (compiler.cpp: lower_fast) when a plan has no NULLs and range analysis over
-// the columns' min/max statistics proves that every value fits 64 bits.  Everything else runs on the general
-// interpreter (scan_kernel.cu); both produce identical accumulator states.
+// Runs the FastOp program the compiler lowers (compiler.cpp: lower_fast) when range analysis over the columns' min/max
+// statistics proves that every value fits 64 bits: typed leaves, IN lists, general comparisons and IS NULL over scalar
+// expressions, AND / OR / NOT trees with domains, validity bitmaps (NULL-skipping aggregates, nullable GROUP BY keys),
+// MVCC, projection arithmetic, aggregates.  Everything else runs on the general interpreter (scan_kernel.cu); both
+// produce identical accumulator states.
 //
 // The same source is compiled twice:
 //   * ahead of time (lean_kernel.cu, nvcc): Cfg = LeanDynCfg, the program and layout are read from the __grid_constant__

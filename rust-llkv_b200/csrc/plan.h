@@ -83,10 +83,11 @@ enum Op : uint16_t {
   OP_COUNT_
 };
 
-// ---- opcodes of the lean kernel (fast_kernel.cu): the hot subset of the machine above as an accumulator machine,
-// lowered by the compiler's range analysis for plans without NULLs whose values provably fit 64 bits.  One i64 (or f64
-// bits) accumulator per row lives in registers; other operands come straight from column tiles, literals or tile-sized
-// temporaries in shared memory.  No NULL flags, no overflow checks that the analysis proved dead.
+// ---- opcodes of the lean kernel (lean_kernel.cuh): the hot subset of the machine above as an accumulator machine,
+// lowered by the compiler's range analysis for plans whose values provably fit 64 bits.  One i64 (or f64 bits)
+// accumulator per row lives in registers; other operands come straight from column tiles, literals or temporaries
+// (registers in a specialised build, a tile-sized shared-memory array otherwise).  NULLs are static: an operand is NULL
+// exactly where one of the columns it reads is (FInstr::h names them); no overflow checks that the analysis proved dead.
 enum FastOp : uint16_t {
   FO_END = 0,
   FO_LEAF,        // a = column, b = LoadKind, c = literal index of (lo, hi): active &= lo <= v <= hi (signed unless LK_U*/LK_STR8)
