@@ -399,6 +399,7 @@ def run_ours(args):
                              "algorithmic_gbs": achieved_arrow},
                 "e2e": {"value": total_rows * e2e_steps / e2e_dt, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "host_bytes_per_step": host_bytes, "upload_threads": upload_threads, "dma_share_percent": args.dma_share,
+                        "narrow_isa": host_narrow_isa(),
                         "note": "host buffers hold the Arrow layout (Decimal128 = 16 B/value); host workers narrow the chunks that fit before the DMA, "
                                 "h2d_bytes_per_step is what crossed the link (llkv_gpu_column_h2d_bytes)",
                         "ms_per_step": e2e_dt / e2e_steps * 1e3, "steps": e2e_steps},
@@ -688,6 +689,19 @@ def emit(obj):
         os.write(1, data)
     else:
         os.write(_REAL_STDOUT, data)
+
+
+def host_narrow_isa():
+    """Widest form of the host narrowing loops this CPU runs (upload.cpp dispatches to it), through the library's test hook."""
+    try:
+        import ctypes
+        from llkv_b200 import gpu
+        fn = ctypes.CDLL(gpu.LIB_PATH).llkv_internal_narrow_d128
+        fn.restype = ctypes.c_int
+        fn.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_uint64]
+        return {1: "sse2", 2: "avx2", 3: "avx512"}[max(i for i in (1, 2, 3) if fn(4, i, None, None, 0) >= 0)]
+    except Exception as e:  # (a label only: never fail the bench over it)
+        return f"unknown ({e!r})"
 
 
 def main():
